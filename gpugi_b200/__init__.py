@@ -1,0 +1,391 @@
+"""gpugi_b200 -- B200-native light-transport hot path behind gpugi's Renderer API.
+
+Python is only glue here: these classes are thin ctypes views of
+  * the C ABI of include/gpugi_b200.h            (class Device)
+  * the C++ host layer mirroring the reference   (classes Scene, RendererSystem, LightSampler)
+The light transport itself runs in the CUDA kernels of csrc/gi_device.cu; there is no Python or
+CPU implementation of it in this package.
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+
+from . import _capi as capi
+from ._capi import (GI_RENDERER_PT, GI_RENDERER_LPT, GI_RENDERER_BPT, GI_TRAVERSAL_FAST, GI_TRAVERSAL_REFERENCE,
+                    GI_OPT_TRAVERSAL, GI_OPT_TEXTURE_FILTER, GI_OPT_SCHEDULER, RAY_MAX)
+
+RAY_DTYPE = np.dtype([("origin", "<f4", 3), ("t_max", "<f4"), ("direction", "<f4", 3), ("flags", "<u4")])
+HIT_DTYPE = np.dtype([("t", "<f4"), ("leaf_tri", "<i4"), ("bary_y", "<f4"), ("bary_z", "<f4")])
+LIGHT_SAMPLE_DTYPE = np.dtype([("position", "<f4", 3), ("normal_phi", "<f4"), ("intensity", "<f4", 3), ("normal_theta_cos", "<f4")])
+NODE_DTYPE = np.dtype([("min", "<f4", 3), ("first_child", "<u4"), ("max", "<f4", 3), ("escape", "<u4")])
+TRIANGLE_DTYPE = np.dtype([("v", "<u4", 3), ("material", "<u4")])
+
+RENDERERS = {"PT": GI_RENDERER_PT, "LPT": GI_RENDERER_LPT, "BPT": GI_RENDERER_BPT}
+
+
+class GpugiError(RuntimeError):
+    pass
+
+
+def _vp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _f3(v):
+    return (C.c_float * 3)(*[float(x) for x in v])
+
+
+def wang_hash(x):
+    """utilities/random.cpp:5-13"""
+    return int(capi.host.gih_wanghash(C.c_uint32(x & 0xFFFFFFFF)))
+
+
+def set_path_length(n):
+    """GlobalConfig parameter "pathLength" (application.cpp:123); latched by a renderer in SetScene."""
+    capi.host.gih_set_path_length(int(n))
+
+
+def camera_params(pos, lookat, yfov, width, height, up=(0.0, 1.0, 0.0)):
+    """Camera::ComputeCameraParams + PixelArea (camera.cpp:76-85, renderersystem.cpp:208) -> GiCamera."""
+    out = capi.GiCamera()
+    capi.host.gih_camera_params(_f3(pos), _f3(lookat), _f3(up), float(yfov), float(width) / float(height), int(width), int(height), C.byref(out))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+class Scene:
+    """Host mirror of gpugi's Scene (gpugi/scene/scene.hpp)."""
+
+    def __init__(self, handle):
+        if not handle:
+            raise GpugiError("Scene: " + capi.host.gih_last_error().decode())
+        self._h = C.c_void_p(handle)
+
+    @classmethod
+    def load(cls, json_path, bvh_type=0):
+        """Scene(file, bvhType): JSON environment file + .bim (scene.cpp:15-59)."""
+        return cls(capi.host.gih_scene_load(os.fsencode(json_path), int(bvh_type)))
+
+    @classmethod
+    def from_mesh(cls, positions, normals, texcoords, triangles, tri_materials, materials, texture_dir="", build_method="sah"):
+        """Synthetic scene: mesh arrays + material dict (JSON 'materials' object, order = material index)."""
+        positions = np.ascontiguousarray(positions, dtype=np.float32)
+        normals = np.ascontiguousarray(normals, dtype=np.float32)
+        texcoords = np.ascontiguousarray(texcoords, dtype=np.float32)
+        triangles = np.ascontiguousarray(triangles, dtype=np.uint32)
+        tri_materials = np.ascontiguousarray(tri_materials, dtype=np.uint32)
+        assert positions.shape == normals.shape and positions.shape[1] == 3 and texcoords.shape == (positions.shape[0], 2)
+        assert triangles.shape[1] == 3 and tri_materials.shape[0] == triangles.shape[0]
+        env = json.dumps({"scene": "", "accelerator": "aabox", "materials": materials, "lights": {}, "cameras": {}})
+        h = capi.host.gih_scene_from_mesh(_vp(positions), _vp(normals), _vp(texcoords), positions.shape[0], _vp(triangles), _vp(tri_materials),
+                                          triangles.shape[0], env.encode(), os.fsencode(texture_dir), 1 if build_method == "kd" else 0)
+        return cls(h)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            capi.host.gih_scene_destroy(self._h)
+            self._h = None
+
+    def store(self, json_path, bim_name):
+        """Write <json_path> and the .bim next to it (BinaryModel::store*)."""
+        if capi.host.gih_scene_store(self._h, os.fsencode(json_path), os.fsencode(bim_name)) != 0:
+            raise GpugiError(capi.host.gih_last_error().decode())
+
+    def add_point_light(self, position, intensity):
+        """Scene::AddPointLight ("addPointLight" command, application.cpp:158-163)."""
+        capi.host.gih_scene_add_point_light(self._h, _f3(position), _f3(intensity))
+
+    @property
+    def desc(self):
+        d = capi.GiSceneDesc()
+        capi.host.gih_scene_desc(self._h, C.byref(d))
+        return d
+
+    @property
+    def info(self):
+        i = capi.GihSceneInfo()
+        capi.host.gih_scene_info(self._h, C.byref(i))
+        return i
+
+    # numpy views (copies) of the arrays the reference would upload
+    def nodes(self):
+        d = self.desc
+        return np.ctypeslib.as_array(C.cast(d.nodes, C.POINTER(C.c_uint8)), shape=(d.num_nodes * 32,)).view(NODE_DTYPE).copy()
+
+    def leaf_triangles(self):
+        d = self.desc
+        return np.ctypeslib.as_array(C.cast(d.leaf_triangles, C.POINTER(C.c_uint8)), shape=(d.num_leaf_triangles * 16,)).view(TRIANGLE_DTYPE).copy()
+
+    def positions(self):
+        d = self.desc
+        return np.ctypeslib.as_array(d.positions, shape=(d.num_vertices, 3)).copy()
+
+    def vertex_info(self):
+        d = self.desc
+        return np.ctypeslib.as_array(C.cast(d.vertex_info, C.POINTER(C.c_float)), shape=(d.num_vertices, 4)).copy()
+
+    def triangles(self):
+        i = self.info
+        return np.ctypeslib.as_array(i.triangles, shape=(i.num_triangles, 3)).copy()
+
+    def triangle_materials(self):
+        i = self.info
+        return np.ctypeslib.as_array(i.triangle_materials, shape=(i.num_triangles,)).copy()
+
+    def parents(self):
+        i = self.info
+        return np.ctypeslib.as_array(i.parents, shape=(i.num_nodes,)).copy()
+
+    def emissivity(self):
+        out = np.zeros((self.info.num_materials, 3), dtype=np.float32)
+        capi.host.gih_scene_emissivity(self._h, _vp(out))
+        return out
+
+    def point_lights(self):
+        out = np.zeros((self.info.num_point_lights, 6), dtype=np.float32)
+        if out.size:
+            capi.host.gih_scene_point_lights(self._h, _vp(out))
+        return out
+
+
+class LightSampler:
+    """LightSampler (gpugi/scene/lightsampler.cpp) on its own, for host-logic tests."""
+
+    def __init__(self, scene):
+        self._scene = scene
+        self._h = C.c_void_p(capi.host.gih_light_sampler_create(scene._h))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            capi.host.gih_light_sampler_destroy(self._h)
+            self._h = None
+
+    def seed(self, s):
+        capi.host.gih_light_sampler_seed(self._h, C.c_uint64(s))
+
+    def generate(self, n, position_bias=1.0e-4):
+        out = np.zeros(n, dtype=LIGHT_SAMPLE_DTYPE)
+        capi.host.gih_light_sampler_generate(self._h, _vp(out), n, float(position_bias))
+        return out
+
+
+# ---------------------------------------------------------------------------------------------------
+class Device:
+    """Raw view of a GiContext (include/gpugi_b200.h).  Owns it unless borrowed from a RendererSystem."""
+
+    def __init__(self, device=0, _borrowed=None):
+        self._owned = _borrowed is None
+        if _borrowed is not None:
+            self._c = C.c_void_p(_borrowed)
+            return
+        ctx = C.c_void_p()
+        st = capi.dev.gi_create(int(device), C.byref(ctx))
+        if st != capi.GI_OK:
+            raise GpugiError("gi_create: " + capi.dev.gi_last_error(None).decode())
+        self._c = ctx
+
+    def close(self):
+        if self._owned and getattr(self, "_c", None):
+            capi.dev.gi_destroy(self._c)
+        self._c = None
+
+    __del__ = close
+
+    def _check(self, st, what):
+        if st != capi.GI_OK:
+            raise GpugiError("%s failed (%d): %s" % (what, st, capi.dev.gi_last_error(self._c).decode()))
+
+    def set_stream(self, cuda_stream_ptr):
+        self._check(capi.dev.gi_set_stream(self._c, C.c_void_p(cuda_stream_ptr)), "gi_set_stream")
+
+    def set_option(self, option, value):
+        self._check(capi.dev.gi_set_option(self._c, option, value), "gi_set_option")
+
+    def upload_scene(self, scene):
+        d = scene.desc
+        self._check(capi.dev.gi_upload_scene(self._c, C.byref(d)), "gi_upload_scene")
+
+    def set_camera(self, cam):
+        self._check(capi.dev.gi_set_camera(self._c, C.byref(cam)), "gi_set_camera")
+
+    def set_screen_size(self, w, h):
+        self._w, self._h = int(w), int(h)
+        self._check(capi.dev.gi_set_screen_size(self._c, int(w), int(h)), "gi_set_screen_size")
+
+    def set_light_samples(self, samples):
+        samples = np.ascontiguousarray(samples, dtype=LIGHT_SAMPLE_DTYPE)
+        self._check(capi.dev.gi_set_light_samples(self._c, C.cast(_vp(samples), C.POINTER(capi.GiLightSample)), samples.shape[0]), "gi_set_light_samples")
+
+    def set_environment_constant(self, srgb8):
+        """1x1 cube with the same sRGB8 colour on all faces (the reference default is black)."""
+        face = np.array([srgb8[0], srgb8[1], srgb8[2], 255], dtype=np.uint8)
+        arr = (C.c_void_p * 6)(*[face.ctypes.data] * 6)
+        self._check(capi.dev.gi_set_environment_map(self._c, 1, arr), "gi_set_environment_map")
+
+    def clear(self):
+        self._check(capi.dev.gi_clear_accumulator(self._c), "gi_clear_accumulator")
+
+    def alloc_light_cache(self, capacity):
+        self._check(capi.dev.gi_alloc_light_cache(self._c, int(capacity)), "gi_alloc_light_cache")
+
+    def render_iteration(self, renderer, frame_seed, max_path_length=16, num_rays_per_light_sample=0, light_cache_capacity=0, warmup=0):
+        p = capi.GiIterationParams(renderer=int(renderer), frame_seed=int(frame_seed) & 0xFFFFFFFF, max_path_length=int(max_path_length),
+                                   num_rays_per_light_sample=int(num_rays_per_light_sample), light_cache_capacity=int(light_cache_capacity),
+                                   warmup=int(warmup))
+        self._check(capi.dev.gi_render_iteration(self._c, C.byref(p)), "gi_render_iteration")
+
+    def show_light_caches(self):
+        self._check(capi.dev.gi_show_light_caches(self._c), "gi_show_light_caches")
+
+    def trace(self, rays):
+        """gi_trace: host ray batch in, host hits out."""
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        hits = np.zeros(rays.shape[0], dtype=HIT_DTYPE)
+        self._check(capi.dev.gi_trace(self._c, _vp(rays), rays.shape[0], _vp(hits)), "gi_trace")
+        return hits
+
+    def trace_device(self, d_rays_ptr, n, d_hits_ptr):
+        self._check(capi.dev.gi_trace_device(self._c, C.c_void_p(d_rays_ptr), int(n), C.c_void_p(d_hits_ptr)), "gi_trace_device")
+
+    def synchronize(self):
+        self._check(capi.dev.gi_synchronize(self._c), "gi_synchronize")
+
+    def read_accumulator(self, w=None, h=None, out=None):
+        w = w or self._w
+        h = h or self._h
+        if out is None:
+            out = np.zeros((h, w, 4), dtype=np.float32)
+        self._check(capi.dev.gi_read_accumulator(self._c, _vp(out)), "gi_read_accumulator")
+        return out
+
+    def accumulator_device(self):
+        ptr, nbytes = C.c_void_p(), C.c_size_t()
+        self._check(capi.dev.gi_accumulator_device(self._c, C.byref(ptr), C.byref(nbytes)), "gi_accumulator_device")
+        return ptr.value, nbytes.value
+
+    def compute_mse(self, reference_rgb, divisor):
+        ref = np.ascontiguousarray(reference_rgb, dtype=np.float32)
+        out = C.c_float()
+        self._check(capi.dev.gi_compute_mse(self._c, _vp(ref), int(divisor), C.byref(out)), "gi_compute_mse")
+        return out.value
+
+    def counters(self):
+        c = capi.GiCounters()
+        self._check(capi.dev.gi_get_counters(self._c, C.byref(c)), "gi_get_counters")
+        return {name: getattr(c, name) for name, _ in capi.GiCounters._fields_}
+
+    def reset_counters(self):
+        self._check(capi.dev.gi_reset_counters(self._c), "gi_reset_counters")
+
+    def kernel_launches(self):
+        return int(capi.dev.gi_kernel_launches(self._c))
+
+
+# ---------------------------------------------------------------------------------------------------
+class RendererSystem:
+    """Host mirror of gpugi's RendererSystem + active Renderer (renderersystem.hpp:27-144)."""
+
+    def __init__(self, device=0):
+        h = capi.host.gih_rs_create(int(device))
+        if not h:
+            raise GpugiError("RendererSystem: " + capi.host.gih_last_error().decode())
+        self._h = C.c_void_p(h)
+        self._scene = None
+        self._size = None
+        self.device = Device(_borrowed=capi.host.gih_rs_device(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            capi.host.gih_rs_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def SetScene(self, scene):
+        self._scene = scene
+        capi.host.gih_rs_set_scene(self._h, scene._h)
+
+    def SetScreenSize(self, w, h):
+        self._size = (int(w), int(h))
+        self.device._w, self.device._h = int(w), int(h)
+        capi.host.gih_rs_set_screen_size(self._h, int(w), int(h))
+
+    def SetCamera(self, pos, lookat, yfov):
+        capi.host.gih_rs_set_camera(self._h, _f3(pos), _f3(lookat), float(yfov))
+
+    def SetRenderer(self, name):
+        if capi.host.gih_rs_set_renderer(self._h, RENDERERS[name] if isinstance(name, str) else int(name)) != 0:
+            raise GpugiError(capi.host.gih_last_error().decode())
+
+    def GetRendererName(self):
+        return capi.host.gih_rs_renderer_name(self._h).decode()
+
+    def SetIterationShard(self, rank, world):
+        capi.host.gih_rs_set_shard(self._h, int(rank), int(world))
+
+    def SetSynchronousDraw(self, sync):
+        capi.host.gih_rs_set_synchronous(self._h, 1 if sync else 0)
+
+    def Draw(self):
+        capi.host.gih_rs_draw(self._h)
+
+    def GetIterationCount(self):
+        return int(capi.host.gih_rs_iteration_count(self._h))
+
+    def GetRenderTime(self):
+        return int(capi.host.gih_rs_render_time_ms(self._h))
+
+    def GetFrameSeed(self):
+        return int(capi.host.gih_rs_frame_seed(self._h))
+
+    def GetGlobalIterationIndex(self):
+        return int(capi.host.gih_rs_global_iteration(self._h))
+
+    def GetNumInitialLightSamples(self):
+        return int(capi.host.gih_rs_num_light_samples(self._h))
+
+    def GetInitialLightSamples(self):
+        out = np.zeros(self.GetNumInitialLightSamples(), dtype=LIGHT_SAMPLE_DTYPE)
+        if out.size:
+            capi.host.gih_rs_light_samples(self._h, _vp(out))
+        return out
+
+    def GetCamera(self):
+        out = capi.GiCamera()
+        capi.host.gih_rs_camera(self._h, C.byref(out))
+        return out
+
+    def GetRendererInfo(self):
+        a, b, c = C.c_int32(), C.c_uint32(), C.c_int32()
+        capi.host.gih_rs_renderer_info(self._h, C.byref(a), C.byref(b), C.byref(c))
+        return {"num_rays_per_light_sample": a.value, "light_cache_capacity": b.value, "average_light_path_length": c.value}
+
+    def ReadBackbuffer(self, out=None):
+        w, h = self._size
+        if out is None:
+            out = np.zeros((h, w, 4), dtype=np.float32)
+        if capi.host.gih_rs_read_backbuffer(self._h, _vp(out)) != 0:
+            raise GpugiError("ReadBackbuffer: " + capi.dev.gi_last_error(self.device._c).decode())
+        return out
+
+
+def write_pfm(path, rgba, divisor=1):
+    """WritePfm (imageut/hdrimage.cpp:6-33)."""
+    rgba = np.ascontiguousarray(rgba, dtype=np.float32)
+    if capi.host.gih_write_pfm(os.fsencode(path), _vp(rgba), rgba.shape[1], rgba.shape[0], int(divisor)) != 0:
+        raise GpugiError("WritePfm failed: " + str(path))
+
+
+def load_pfm(path):
+    """LoadPfm (imageut/hdrimage.cpp:35-60) -> (h, w, 3) float32."""
+    w, h = C.c_int(), C.c_int()
+    probe = np.zeros(3, dtype=np.float32)
+    st = capi.host.gih_load_pfm(os.fsencode(path), _vp(probe), 0, C.byref(w), C.byref(h))
+    if st == 1:
+        raise GpugiError("LoadPfm failed: " + str(path))
+    out = np.zeros((h.value, w.value, 3), dtype=np.float32)
+    if capi.host.gih_load_pfm(os.fsencode(path), _vp(out), w.value * h.value, C.byref(w), C.byref(h)) != 0:
+        raise GpugiError("LoadPfm failed: " + str(path))
+    return out

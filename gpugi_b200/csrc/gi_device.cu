@@ -1,0 +1,696 @@
+// gi_device.cu -- CUDA kernels (sm_100a) and the C ABI of include/gpugi_b200.h.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+// There is no CPU path in this file: every compute entry point needs a live sm_100 device.
+#include "gi_core.h"
+#include "gi_layout.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace gik;
+
+// =====================================================================================================
+// kernels
+// =====================================================================================================
+
+// 64-bit device counters (GiCounters order, first 7 entries)
+enum { CNT_CLOSEST = 0, CNT_ANY, CNT_CAMERA, CNT_LIGHT, CNT_SHADED, CNT_SPLATS, CNT_FALLBACK, CNT_NODES, CNT_TRIS, CNT_COUNT };
+
+__device__ __forceinline__ void flushCounters(unsigned long long* counters, const PathCounters& pc, const TraceStats& st)
+{
+	// warp-aggregate, one atomic per warp and counter
+	const unsigned mask = __activemask();
+	unsigned v[CNT_COUNT] = {pc.closestRays, pc.anyRays, pc.cameraPaths, pc.lightPaths, pc.shadedVertices, pc.splats, pc.fallbackRays, st.nodes, st.tris};
+	const int lane = threadIdx.x & 31;
+	const int leader = __ffs(mask) - 1;
+#pragma unroll
+	for (int i = 0; i < CNT_COUNT; ++i)
+	{
+		unsigned s = __reduce_add_sync(mask, v[i]);
+		if (lane == leader && s) atomicAdd(counters + i, (unsigned long long)s);
+	}
+}
+
+// TraceRay / TraceRayAnyHit over a ray batch (traceray.glsl:19-180): one thread per ray.
+__global__ void __launch_bounds__(128) k_trace(DScene s, const GiRay* __restrict__ rays, uint32_t n, GiHit* __restrict__ hits, int mode,
+                                               unsigned long long* counters)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	PathCounters pc = {};
+	TraceStats st = {0, 0};
+	if (i < n)
+	{
+		const F4 r0 = ld4(reinterpret_cast<const F4*>(rays) + 2 * size_t(i));
+		const F4 r1 = ld4(reinterpret_cast<const F4*>(rays) + 2 * size_t(i) + 1);
+		const F3 o = f3(r0.x, r0.y, r0.z), d = f3(r1.x, r1.y, r1.z);
+		const float tMax = r0.w;
+		const uint32_t flags = uint32_t(f2i(r1.w));
+		F4 out;
+		if (flags & 1u)
+		{
+			++pc.anyRays;
+			bool occluded = traceAny(s, mode, o, d, tMax, &st);
+			out.x = tMax; out.y = i2f(occluded ? 1 : 0); out.z = 0.0f; out.w = 0.0f;
+		}
+		else
+		{
+			++pc.closestRays;
+			Hit h; bool fb = false;
+			traceClosest(s, mode, o, d, tMax, h, &st, &fb);
+			if (fb) ++pc.fallbackRays;
+			out.x = h.t; out.y = i2f(h.leafTri); out.z = h.leafTri >= 0 ? h.bary.y : 0.0f; out.w = h.leafTri >= 0 ? h.bary.z : 0.0f;
+		}
+		*reinterpret_cast<float4*>(hits + i) = make_float4(out.x, out.y, out.z, out.w);
+	}
+	flushCounters(counters, pc, st);
+}
+
+// pathtracer.comp: 8x8 work groups, grid (W/8, H/8) (pathtracer.cpp:50).
+__global__ void __launch_bounds__(64) k_pathtrace(DFrame f, unsigned long long* counters)
+{
+	const int gx = blockIdx.x * 8 + (threadIdx.x & 7);
+	const int gy = blockIdx.y * 8 + (threadIdx.x >> 3);
+	PathCounters pc = {};
+	TraceStats st = {0, 0};
+	pathtracePixel(f, gx, gy, pc, &st);
+	flushCounters(counters, pc, st);
+}
+
+// pathtracer_bidir.comp: same launch shape (bidirectionalpathtracer.cpp:200).
+__global__ void __launch_bounds__(64) k_bidir_eye(DFrame f, unsigned long long* counters)
+{
+	const int gx = blockIdx.x * 8 + (threadIdx.x & 7);
+	const int gy = blockIdx.y * 8 + (threadIdx.x >> 3);
+	PathCounters pc = {};
+	TraceStats st = {0, 0};
+	bidirPathtracePixel(f, gx, gy, pc, &st);
+	flushCounters(counters, pc, st);
+}
+
+// lighttracer.comp: 64 paths per group, NumInitialLightSamples*NumRaysPerLightSample/64 groups (lightpathtracer.cpp:48).
+template <bool SAVE, bool WARMUP>
+__global__ void __launch_bounds__(64) k_lighttrace(DFrame f, unsigned long long* counters)
+{
+	const uint32_t gid = blockIdx.x * 64u + threadIdx.x;
+	PathCounters pc = {};
+	TraceStats st = {0, 0};
+	lighttracePath<SAVE, WARMUP>(f, gid, pc, &st);
+	flushCounters(counters, pc, st);
+}
+
+// showlightcaches.comp restated with NumInitialLightSamples threads.
+__global__ void __launch_bounds__(64) k_show_light_caches(DFrame f, unsigned long long* counters)
+{
+	const int i = blockIdx.x * 64 + threadIdx.x;
+	PathCounters pc = {};
+	TraceStats st = {0, 0};
+	if (i < f.numLightSamples) showLightCache(f, i, pc, &st);
+	flushCounters(counters, pc, st);
+}
+
+// resetcounter.comp:10-11
+__global__ void k_reset_counter(uint32_t* lightCacheCount, uint32_t* lightPathLengthSum, uint32_t initial)
+{
+	*lightCacheCount = initial;
+	*lightPathLengthSum = 0u;
+}
+
+// sqerror.frag:16-17 + mean (texturemse.cpp:58-62): per-block partial sums in double.
+__global__ void __launch_bounds__(256) k_mse(const float4* __restrict__ accum, const float* __restrict__ ref, uint32_t numPixels, float invDivisor,
+                                              double* result)
+{
+	double sum = 0.0;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < numPixels; i += gridDim.x * blockDim.x)
+	{
+		float4 a = accum[i];
+		float d0 = a.x * invDivisor - ref[3 * size_t(i)], d1 = a.y * invDivisor - ref[3 * size_t(i) + 1], d2 = a.z * invDivisor - ref[3 * size_t(i) + 2];
+		sum += double(d0 * d0 + d1 * d1 + d2 * d2);
+	}
+	for (int o = 16; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o);
+	__shared__ double warpSums[8];
+	if ((threadIdx.x & 31) == 0) warpSums[threadIdx.x >> 5] = sum;
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		double s = 0.0;
+		for (int w = 0; w < 8; ++w) s += warpSums[w];
+		atomicAdd(result, s);
+	}
+}
+
+// =====================================================================================================
+// context
+// =====================================================================================================
+struct GiContext
+{
+	int device = 0;
+	cudaStream_t ownStream = nullptr;
+	cudaStream_t stream = nullptr;
+	std::string error;
+	uint64_t launches = 0;
+
+	// scene
+	bool haveScene = false;
+	DScene scene = {};
+	std::vector<void*> sceneAllocs;
+	std::vector<cudaArray_t> arrays;
+	std::vector<cudaTextureObject_t> texObjects;
+	bool fastValid = false;
+
+	// environment
+	cudaArray_t envArray = nullptr;
+	cudaTextureObject_t envTex = 0;
+	F3 envColor = {0.0f, 0.0f, 0.0f};
+
+	// frame
+	GiCamera cam = {};
+	bool haveCamera = false;
+	int width = 0, height = 0;
+	float* accum = nullptr;
+	F4* lightSamples = nullptr;
+	uint32_t lightSampleCapacity = 0;
+	int numLightSamples = 0;
+
+	// light cache
+	F4* lightCache = nullptr;
+	uint32_t lightCacheCapacity = 0;
+	uint32_t* bptCounters = nullptr; // [0] NumLightCacheEntries, [1] LightPathLengthSum
+
+	// counters
+	unsigned long long* counters = nullptr;
+	double* mseResult = nullptr;
+
+	// options
+	int traversal = GI_TRAVERSAL_FAST;
+	int textureFilterExact = 0;
+	int scheduler = 0;
+};
+
+static std::string g_createError;
+
+static int fail(GiContext* ctx, int code, const std::string& msg)
+{
+	if (ctx) ctx->error = msg;
+	else g_createError = msg;
+	return code;
+}
+
+#define GI_CUDA(ctx, call)                                                                                         \
+	do                                                                                                             \
+	{                                                                                                              \
+		cudaError_t e_ = (call);                                                                                   \
+		if (e_ != cudaSuccess)                                                                                     \
+			return fail(ctx, GI_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                    \
+	} while (0)
+
+static void freeScene(GiContext* c)
+{
+	for (cudaTextureObject_t t : c->texObjects) cudaDestroyTextureObject(t);
+	for (cudaArray_t a : c->arrays) cudaFreeArray(a);
+	for (void* p : c->sceneAllocs) cudaFree(p);
+	c->texObjects.clear(); c->arrays.clear(); c->sceneAllocs.clear();
+	c->haveScene = false;
+	std::memset(&c->scene, 0, sizeof(c->scene));
+}
+
+template <typename T>
+static cudaError_t uploadVector(GiContext* c, const std::vector<T>& v, const T** out)
+{
+	void* d = nullptr;
+	size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
+	cudaError_t e = cudaMalloc(&d, bytes);
+	if (e != cudaSuccess) return e;
+	c->sceneAllocs.push_back(d);
+	if (!v.empty()) e = cudaMemcpyAsync(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, c->stream);
+	*out = static_cast<const T*>(d);
+	return e;
+}
+
+static DFrame makeFrame(GiContext* c, const GiIterationParams* p)
+{
+	DFrame f;
+	std::memset(&f, 0, sizeof(f));
+	f.scene = c->scene;
+	f.scene.textureFilterExact = c->textureFilterExact;
+	f.cam = c->cam;
+	f.width = c->width; f.height = c->height;
+	f.lightSamples = c->lightSamples;
+	f.numLightSamples = c->numLightSamples;
+	f.frameSeed = p ? p->frame_seed : 0u;
+	f.maxPathLength = p ? p->max_path_length : 16;
+	f.traversalMode = c->fastValid ? c->traversal : GI_TRAVERSAL_REFERENCE;
+	f.accum = c->accum;
+	f.envColor = c->envColor;
+	f.envCube = (unsigned long long)c->envTex;
+	f.numRaysPerLightSample = p ? p->num_rays_per_light_sample : 0;
+	f.lightCache = c->lightCache;
+	f.lightCacheCapacity = 0;
+	f.lightCacheCount = c->bptCounters;
+	f.lightPathLengthSum = c->bptCounters + 1;
+	return f;
+}
+
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" {
+
+int gi_version(void) { return 100; }
+
+const char* gi_last_error(const GiContext* ctx) { return ctx ? ctx->error.c_str() : g_createError.c_str(); }
+
+int gi_create(int device, GiContext** out_ctx)
+{
+	if (!out_ctx) return fail(nullptr, GI_ERR_INVALID, "gi_create: out_ctx is NULL");
+	*out_ctx = nullptr;
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess || count == 0)
+		return fail(nullptr, GI_ERR_CUDA, std::string("no CUDA device available (") + cudaGetErrorString(e) + "); gpugi_b200 has no CPU fallback");
+	if (device < 0 || device >= count) return fail(nullptr, GI_ERR_INVALID, "gi_create: device ordinal out of range");
+	cudaDeviceProp prop;
+	GI_CUDA(nullptr, cudaGetDeviceProperties(&prop, device));
+	if (prop.major != 10)
+		return fail(nullptr, GI_ERR_CUDA, std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+		                                      "; this library carries sm_100a code only");
+	GI_CUDA(nullptr, cudaSetDevice(device));
+	GiContext* c = new GiContext();
+	c->device = device;
+	e = cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking);
+	if (e != cudaSuccess) { delete c; return fail(nullptr, GI_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e)); }
+	c->stream = c->ownStream;
+	bool ok = cudaMalloc(reinterpret_cast<void**>(&c->counters), CNT_COUNT * sizeof(unsigned long long)) == cudaSuccess &&
+	          cudaMalloc(reinterpret_cast<void**>(&c->bptCounters), 2 * sizeof(uint32_t)) == cudaSuccess &&
+	          cudaMalloc(reinterpret_cast<void**>(&c->mseResult), sizeof(double)) == cudaSuccess &&
+	          cudaMemset(c->counters, 0, CNT_COUNT * sizeof(unsigned long long)) == cudaSuccess && cudaMemset(c->bptCounters, 0, 2 * sizeof(uint32_t)) == cudaSuccess;
+	if (!ok) { gi_destroy(c); return fail(nullptr, GI_ERR_CUDA, "gi_create: device allocation failed"); }
+	*out_ctx = c;
+	return GI_OK;
+}
+
+void gi_destroy(GiContext* c)
+{
+	if (!c) return;
+	cudaSetDevice(c->device);
+	cudaDeviceSynchronize();
+	freeScene(c);
+	if (c->envTex) cudaDestroyTextureObject(c->envTex);
+	if (c->envArray) cudaFreeArray(c->envArray);
+	cudaFree(c->accum); cudaFree(c->lightSamples); cudaFree(c->lightCache); cudaFree(c->bptCounters); cudaFree(c->counters); cudaFree(c->mseResult);
+	if (c->ownStream) cudaStreamDestroy(c->ownStream);
+	delete c;
+}
+
+int gi_set_stream(GiContext* c, void* cuda_stream)
+{
+	if (!c) return GI_ERR_INVALID;
+	GI_CUDA(c, cudaStreamSynchronize(c->stream));
+	c->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->ownStream;
+	return GI_OK;
+}
+
+int gi_set_option(GiContext* c, int option, int value)
+{
+	if (!c) return GI_ERR_INVALID;
+	switch (option)
+	{
+	case GI_OPT_TRAVERSAL:
+		if (value != GI_TRAVERSAL_FAST && value != GI_TRAVERSAL_REFERENCE) return fail(c, GI_ERR_INVALID, "GI_OPT_TRAVERSAL: unknown mode");
+		c->traversal = value; return GI_OK;
+	case GI_OPT_TEXTURE_FILTER: c->textureFilterExact = value ? 1 : 0; return GI_OK;
+	case GI_OPT_SCHEDULER: c->scheduler = value; return GI_OK;
+	}
+	return fail(c, GI_ERR_INVALID, "gi_set_option: unknown option");
+}
+
+int gi_clear_accumulator(GiContext* c)
+{
+	if (!c) return GI_ERR_INVALID;
+	if (c->accum) GI_CUDA(c, cudaMemsetAsync(c->accum, 0, size_t(c->width) * c->height * 4 * sizeof(float), c->stream));
+	return GI_OK;
+}
+
+int gi_upload_scene(GiContext* c, const GiSceneDesc* d)
+{
+	if (!c || !d) return GI_ERR_INVALID;
+	if (!d->nodes || d->num_nodes == 0 || !d->leaf_triangles || d->num_leaf_triangles == 0 || (d->num_leaf_triangles & 1u) || !d->positions ||
+	    !d->vertex_info || d->num_vertices == 0 || !d->materials || d->num_materials == 0)
+		return fail(c, GI_ERR_INVALID, "gi_upload_scene: incomplete scene description");
+	GI_CUDA(c, cudaSetDevice(c->device));
+	GI_CUDA(c, cudaStreamSynchronize(c->stream));
+	freeScene(c);
+
+	// ---- validate + re-lay out on the host (gi_layout.h), then upload
+	HostLayout L;
+	std::string lerr;
+	if (!buildHostLayout(d, L, lerr)) return fail(c, GI_ERR_INVALID, "gi_upload_scene: " + lerr);
+	c->fastValid = L.binary;
+
+	// ---- textures: CUDA arrays + texture objects (hardware filter) and a linear copy (fp32 filter)
+	std::vector<cudaTextureObject_t> objOfTexture(d->num_textures, 0);
+	std::vector<const void*> rawOfTexture(d->num_textures, nullptr);
+	for (uint32_t ti = 0; ti < d->num_textures; ++ti)
+	{
+		const GiTexture& t = d->textures[ti];
+		if (t.width == 1 && t.height == 1) continue; // folded into the material record
+		const bool isFloat = t.format == GI_TEX_RGBA32F;
+		const size_t texelBytes = isFloat ? 16 : 4;
+		cudaChannelFormatDesc cd = isFloat ? cudaCreateChannelDesc<float4>() : cudaCreateChannelDesc<uchar4>();
+		cudaArray_t arr = nullptr;
+		GI_CUDA(c, cudaMallocArray(&arr, &cd, size_t(t.width), size_t(t.height)));
+		c->arrays.push_back(arr);
+		GI_CUDA(c, cudaMemcpy2DToArrayAsync(arr, 0, 0, t.pixels, t.width * texelBytes, t.width * texelBytes, size_t(t.height), cudaMemcpyHostToDevice, c->stream));
+		cudaResourceDesc rd;
+		std::memset(&rd, 0, sizeof(rd));
+		rd.resType = cudaResourceTypeArray;
+		rd.res.array.array = arr;
+		cudaTextureDesc td;
+		std::memset(&td, 0, sizeof(td));
+		td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeWrap; // REPEAT (scene.cpp:20)
+		td.filterMode = cudaFilterModeLinear;                                             // mag LINEAR, LOD 0
+		td.readMode = isFloat ? cudaReadModeElementType : cudaReadModeNormalizedFloat;
+		td.sRGB = t.format == GI_TEX_SRGB8_ALPHA8 ? 1 : 0;
+		td.normalizedCoords = 1;
+		cudaTextureObject_t obj = 0;
+		GI_CUDA(c, cudaCreateTextureObject(&obj, &rd, &td, nullptr));
+		c->texObjects.push_back(obj);
+		objOfTexture[ti] = obj;
+		void* raw = nullptr;
+		GI_CUDA(c, cudaMalloc(&raw, size_t(t.width) * t.height * texelBytes));
+		c->sceneAllocs.push_back(raw);
+		GI_CUDA(c, cudaMemcpyAsync(raw, t.pixels, size_t(t.width) * t.height * texelBytes, cudaMemcpyHostToDevice, c->stream));
+		rawOfTexture[ti] = raw;
+	}
+	for (uint32_t mi = 0; mi < d->num_materials; ++mi)
+		for (int sl = 0; sl < 4; ++sl)
+		{
+			const int32_t ti = L.materialTexture[size_t(mi) * 4 + sl];
+			L.texels[size_t(mi) * 4 + sl].pixels = rawOfTexture[ti];
+			L.materials[mi].tex[sl] = (unsigned long long)objOfTexture[ti]; // 0 for folded constants
+		}
+
+	// ---- upload
+	DScene s = L.scene;
+	GI_CUDA(c, uploadVector(c, L.refNodes, &s.refNodes));
+	GI_CUDA(c, uploadVector(c, L.fastNodes, &s.fastNodes));
+	GI_CUDA(c, uploadVector(c, L.leafPos, &s.leafPos));
+	GI_CUDA(c, uploadVector(c, L.leafTris, &s.leafTris));
+	GI_CUDA(c, uploadVector(c, L.vertexInfo, &s.vertexInfo));
+	GI_CUDA(c, uploadVector(c, L.materials, &s.materials));
+	GI_CUDA(c, uploadVector(c, L.texels, &s.texels));
+	GI_CUDA(c, cudaStreamSynchronize(c->stream)); // host staging vectors die here
+	c->scene = s;
+	c->haveScene = true;
+	return gi_clear_accumulator(c);
+}
+
+int gi_set_environment_map(GiContext* c, int size, const uint8_t* const* faces)
+{
+	if (!c) return GI_ERR_INVALID;
+	GI_CUDA(c, cudaSetDevice(c->device));
+	GI_CUDA(c, cudaStreamSynchronize(c->stream));
+	if (c->envTex) { cudaDestroyTextureObject(c->envTex); c->envTex = 0; }
+	if (c->envArray) { cudaFreeArray(c->envArray); c->envArray = nullptr; }
+	c->envColor = f3(0.0f);
+	if (!faces || size <= 0) return GI_OK;
+	if (size == 1)
+	{
+		// a 1x1 cube is a constant per face; the reference's default is all-black (renderersystem.cpp:39-47).
+		bool same = true;
+		for (int f = 1; f < 6; ++f) same = same && std::memcmp(faces[0], faces[f], 3) == 0;
+		if (same) { c->envColor = f3(srgbDecodeHost(faces[0][0]), srgbDecodeHost(faces[0][1]), srgbDecodeHost(faces[0][2])); return GI_OK; }
+	}
+	cudaChannelFormatDesc cd = cudaCreateChannelDesc<uchar4>();
+	GI_CUDA(c, cudaMalloc3DArray(&c->envArray, &cd, make_cudaExtent(size_t(size), size_t(size), 6), cudaArrayCubemap));
+	// CUDA cubemap layer order: +X,-X,+Y,-Y,+Z,-Z; ours: -X,+X,-Y,+Y,-Z,+Z
+	const int order[6] = {1, 0, 3, 2, 5, 4};
+	std::vector<uint8_t> staging(size_t(size) * size * 4 * 6);
+	for (int l = 0; l < 6; ++l) std::memcpy(staging.data() + size_t(l) * size * size * 4, faces[order[l]], size_t(size) * size * 4);
+	cudaMemcpy3DParms cp;
+	std::memset(&cp, 0, sizeof(cp));
+	cp.srcPtr = make_cudaPitchedPtr(staging.data(), size_t(size) * 4, size_t(size), size_t(size));
+	cp.dstArray = c->envArray;
+	cp.extent = make_cudaExtent(size_t(size), size_t(size), 6);
+	cp.kind = cudaMemcpyHostToDevice;
+	GI_CUDA(c, cudaMemcpy3D(&cp));
+	cudaResourceDesc rd;
+	std::memset(&rd, 0, sizeof(rd));
+	rd.resType = cudaResourceTypeArray;
+	rd.res.array.array = c->envArray;
+	cudaTextureDesc td;
+	std::memset(&td, 0, sizeof(td));
+	td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+	td.filterMode = cudaFilterModeLinear;
+	td.readMode = cudaReadModeNormalizedFloat;
+	td.sRGB = 1;
+	td.normalizedCoords = 1;
+	GI_CUDA(c, cudaCreateTextureObject(&c->envTex, &rd, &td, nullptr));
+	return GI_OK;
+}
+
+int gi_set_camera(GiContext* c, const GiCamera* cam)
+{
+	if (!c || !cam) return GI_ERR_INVALID;
+	c->cam = *cam;
+	c->haveCamera = true;
+	return gi_clear_accumulator(c);
+}
+
+int gi_set_screen_size(GiContext* c, int width, int height)
+{
+	if (!c || width <= 0 || height <= 0) return fail(c, GI_ERR_INVALID, "gi_set_screen_size: bad size");
+	GI_CUDA(c, cudaSetDevice(c->device));
+	GI_CUDA(c, cudaStreamSynchronize(c->stream));
+	if (c->accum) { cudaFree(c->accum); c->accum = nullptr; }
+	c->width = width; c->height = height;
+	GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->accum), size_t(width) * height * 4 * sizeof(float)));
+	return gi_clear_accumulator(c);
+}
+
+int gi_set_light_samples(GiContext* c, const GiLightSample* samples, uint32_t n)
+{
+	if (!c || !samples || n == 0) return fail(c, GI_ERR_INVALID, "gi_set_light_samples: no samples");
+	GI_CUDA(c, cudaSetDevice(c->device));
+	if (n > c->lightSampleCapacity)
+	{
+		GI_CUDA(c, cudaStreamSynchronize(c->stream));
+		if (c->lightSamples) cudaFree(c->lightSamples);
+		c->lightSamples = nullptr;
+		GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->lightSamples), size_t(n) * sizeof(GiLightSample)));
+		c->lightSampleCapacity = n;
+	}
+	// pageable source: the runtime stages the bytes before returning, so the caller may reuse `samples`;
+	// stream order keeps the previous iteration's reads ahead of this write.
+	GI_CUDA(c, cudaMemcpyAsync(c->lightSamples, samples, size_t(n) * sizeof(GiLightSample), cudaMemcpyHostToDevice, c->stream));
+	c->numLightSamples = int(n);
+	return GI_OK;
+}
+
+int gi_alloc_light_cache(GiContext* c, uint32_t capacity)
+{
+	if (!c || capacity == 0) return fail(c, GI_ERR_INVALID, "gi_alloc_light_cache: zero capacity");
+	GI_CUDA(c, cudaSetDevice(c->device));
+	GI_CUDA(c, cudaStreamSynchronize(c->stream));
+	if (c->lightCache) { cudaFree(c->lightCache); c->lightCache = nullptr; c->lightCacheCapacity = 0; }
+	GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->lightCache), size_t(capacity) * 64));
+	c->lightCacheCapacity = capacity;
+	return GI_OK;
+}
+
+static int checkRenderState(GiContext* c)
+{
+	if (!c->haveScene) return fail(c, GI_ERR_NOSCENE, "no scene uploaded");
+	if (!c->accum) return fail(c, GI_ERR_INVALID, "gi_set_screen_size was not called");
+	if (!c->haveCamera) return fail(c, GI_ERR_INVALID, "gi_set_camera was not called");
+	if (c->numLightSamples <= 0) return fail(c, GI_ERR_INVALID, "gi_set_light_samples was not called");
+	return GI_OK;
+}
+
+int gi_render_iteration(GiContext* c, const GiIterationParams* p)
+{
+	if (!c || !p) return GI_ERR_INVALID;
+	int st = checkRenderState(c);
+	if (st != GI_OK) return st;
+	if (p->max_path_length <= 0) return fail(c, GI_ERR_INVALID, "max_path_length must be positive");
+	GI_CUDA(c, cudaSetDevice(c->device));
+	DFrame f = makeFrame(c, p);
+	const dim3 pixelGrid(unsigned(c->width / 8), unsigned(c->height / 8), 1); // integer division, pathtracer.cpp:50
+	switch (p->renderer)
+	{
+	case GI_RENDERER_PT:
+		if (pixelGrid.x && pixelGrid.y)
+		{
+			k_pathtrace<<<pixelGrid, 64, 0, c->stream>>>(f, c->counters);
+			++c->launches;
+		}
+		break;
+	case GI_RENDERER_LPT:
+	{
+		if (p->num_rays_per_light_sample <= 0) return fail(c, GI_ERR_INVALID, "num_rays_per_light_sample must be positive");
+		const unsigned groups = unsigned(c->numLightSamples) * unsigned(p->num_rays_per_light_sample) / 64u; // lightpathtracer.cpp:48
+		if (groups)
+		{
+			k_lighttrace<false, false><<<groups, 64, 0, c->stream>>>(f, c->counters);
+			++c->launches;
+		}
+		break;
+	}
+	case GI_RENDERER_BPT:
+	{
+		if (p->num_rays_per_light_sample <= 0) return fail(c, GI_ERR_INVALID, "num_rays_per_light_sample must be positive");
+		const unsigned numLightPaths = unsigned(c->numLightSamples) * unsigned(p->num_rays_per_light_sample);
+		const unsigned groups = numLightPaths / 64u;
+		// resetcounter.comp (bidirectionalpathtracer.cpp:190)
+		k_reset_counter<<<1, 1, 0, c->stream>>>(c->bptCounters, c->bptCounters + 1, numLightPaths);
+		++c->launches;
+		if (p->warmup)
+		{
+			f.lightCacheCapacity = 0x7fffffffu;
+			if (groups) { k_lighttrace<true, true><<<groups, 64, 0, c->stream>>>(f, c->counters); ++c->launches; }
+			break;
+		}
+		if (!c->lightCache) return fail(c, GI_ERR_CAPACITY, "BPT needs gi_alloc_light_cache first");
+		if (p->light_cache_capacity <= 0 || uint32_t(p->light_cache_capacity) > c->lightCacheCapacity)
+			return fail(c, GI_ERR_CAPACITY, "light_cache_capacity exceeds the allocated light cache");
+		if (uint32_t(p->light_cache_capacity) < numLightPaths)
+			return fail(c, GI_ERR_CAPACITY, "light_cache_capacity is smaller than the number of light paths (their origins occupy the first slots)");
+		f.lightCacheCapacity = uint32_t(p->light_cache_capacity);
+		if (groups) { k_lighttrace<true, false><<<groups, 64, 0, c->stream>>>(f, c->counters); ++c->launches; }
+		if (pixelGrid.x && pixelGrid.y) { k_bidir_eye<<<pixelGrid, 64, 0, c->stream>>>(f, c->counters); ++c->launches; }
+		break;
+	}
+	default: return fail(c, GI_ERR_INVALID, "unknown renderer");
+	}
+	GI_CUDA(c, cudaGetLastError());
+	return GI_OK;
+}
+
+int gi_show_light_caches(GiContext* c)
+{
+	if (!c) return GI_ERR_INVALID;
+	int st = checkRenderState(c);
+	if (st != GI_OK) return st;
+	GI_CUDA(c, cudaSetDevice(c->device));
+	DFrame f = makeFrame(c, nullptr);
+	k_show_light_caches<<<(c->numLightSamples + 63) / 64, 64, 0, c->stream>>>(f, c->counters);
+	++c->launches;
+	GI_CUDA(c, cudaGetLastError());
+	return GI_OK;
+}
+
+int gi_trace_device(GiContext* c, const GiRay* d_rays, uint32_t n, GiHit* d_hits)
+{
+	if (!c || (n && (!d_rays || !d_hits))) return GI_ERR_INVALID;
+	if (!c->haveScene) return fail(c, GI_ERR_NOSCENE, "no scene uploaded");
+	if (n == 0) return GI_OK;
+	GI_CUDA(c, cudaSetDevice(c->device));
+	DScene s = c->scene;
+	const int mode = c->fastValid ? c->traversal : GI_TRAVERSAL_REFERENCE;
+	k_trace<<<(n + 127) / 128, 128, 0, c->stream>>>(s, d_rays, n, d_hits, mode, c->counters);
+	++c->launches;
+	GI_CUDA(c, cudaGetLastError());
+	return GI_OK;
+}
+
+int gi_trace(GiContext* c, const GiRay* rays, uint32_t n, GiHit* hits)
+{
+	if (!c || (n && (!rays || !hits))) return GI_ERR_INVALID;
+	if (!c->haveScene) return fail(c, GI_ERR_NOSCENE, "no scene uploaded");
+	if (n == 0) return GI_OK;
+	GI_CUDA(c, cudaSetDevice(c->device));
+	GiRay* dr = nullptr; GiHit* dh = nullptr;
+	GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&dr), size_t(n) * sizeof(GiRay)));
+	cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&dh), size_t(n) * sizeof(GiHit));
+	if (e != cudaSuccess) { cudaFree(dr); return fail(c, GI_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
+	int st = GI_OK;
+	e = cudaMemcpyAsync(dr, rays, size_t(n) * sizeof(GiRay), cudaMemcpyHostToDevice, c->stream);
+	if (e == cudaSuccess) st = gi_trace_device(c, dr, n, dh);
+	if (e == cudaSuccess && st == GI_OK) e = cudaMemcpyAsync(hits, dh, size_t(n) * sizeof(GiHit), cudaMemcpyDeviceToHost, c->stream);
+	if (e == cudaSuccess && st == GI_OK) e = cudaStreamSynchronize(c->stream);
+	cudaFree(dr); cudaFree(dh);
+	if (e != cudaSuccess) return fail(c, GI_ERR_CUDA, std::string("gi_trace: ") + cudaGetErrorString(e));
+	return st;
+}
+
+int gi_synchronize(GiContext* c)
+{
+	if (!c) return GI_ERR_INVALID;
+	GI_CUDA(c, cudaStreamSynchronize(c->stream));
+	return GI_OK;
+}
+
+int gi_read_accumulator(GiContext* c, float* rgba)
+{
+	if (!c || !rgba) return GI_ERR_INVALID;
+	if (!c->accum) return fail(c, GI_ERR_INVALID, "gi_set_screen_size was not called");
+	GI_CUDA(c, cudaMemcpyAsync(rgba, c->accum, size_t(c->width) * c->height * 4 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+	GI_CUDA(c, cudaStreamSynchronize(c->stream));
+	return GI_OK;
+}
+
+int gi_accumulator_device(GiContext* c, void** device_ptr, size_t* num_bytes)
+{
+	if (!c || !device_ptr) return GI_ERR_INVALID;
+	if (!c->accum) return fail(c, GI_ERR_INVALID, "gi_set_screen_size was not called");
+	*device_ptr = c->accum;
+	if (num_bytes) *num_bytes = size_t(c->width) * c->height * 4 * sizeof(float);
+	return GI_OK;
+}
+
+int gi_compute_mse(GiContext* c, const float* reference_rgb, uint32_t divisor, float* mse)
+{
+	if (!c || !reference_rgb || !mse || divisor == 0) return GI_ERR_INVALID;
+	if (!c->accum) return fail(c, GI_ERR_INVALID, "gi_set_screen_size was not called");
+	GI_CUDA(c, cudaSetDevice(c->device));
+	const uint32_t numPixels = uint32_t(c->width) * uint32_t(c->height);
+	float* dref = nullptr;
+	GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&dref), size_t(numPixels) * 3 * sizeof(float)));
+	cudaError_t e = cudaMemcpyAsync(dref, reference_rgb, size_t(numPixels) * 3 * sizeof(float), cudaMemcpyHostToDevice, c->stream);
+	if (e == cudaSuccess) e = cudaMemsetAsync(c->mseResult, 0, sizeof(double), c->stream);
+	if (e == cudaSuccess)
+	{
+		k_mse<<<296, 256, 0, c->stream>>>(reinterpret_cast<const float4*>(c->accum), dref, numPixels, 1.0f / float(divisor), c->mseResult);
+		++c->launches;
+		e = cudaGetLastError();
+	}
+	double sum = 0.0;
+	if (e == cudaSuccess) e = cudaMemcpyAsync(&sum, c->mseResult, sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+	cudaFree(dref);
+	if (e != cudaSuccess) return fail(c, GI_ERR_CUDA, std::string("gi_compute_mse: ") + cudaGetErrorString(e));
+	*mse = float(sum / double(numPixels));
+	return GI_OK;
+}
+
+int gi_get_counters(GiContext* c, GiCounters* out)
+{
+	if (!c || !out) return GI_ERR_INVALID;
+	unsigned long long h[CNT_COUNT];
+	uint32_t b[2];
+	GI_CUDA(c, cudaMemcpyAsync(h, c->counters, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+	GI_CUDA(c, cudaMemcpyAsync(b, c->bptCounters, sizeof(b), cudaMemcpyDeviceToHost, c->stream));
+	GI_CUDA(c, cudaStreamSynchronize(c->stream));
+	out->closest_rays = h[CNT_CLOSEST]; out->any_rays = h[CNT_ANY]; out->camera_paths = h[CNT_CAMERA]; out->light_paths = h[CNT_LIGHT];
+	out->shaded_vertices = h[CNT_SHADED]; out->splats = h[CNT_SPLATS]; out->exact_fallback_rays = h[CNT_FALLBACK];
+	out->node_tests = h[CNT_NODES]; out->triangle_tests = h[CNT_TRIS];
+	out->light_cache_entries = b[0]; out->light_path_length_sum = b[1];
+	return GI_OK;
+}
+
+int gi_reset_counters(GiContext* c)
+{
+	if (!c) return GI_ERR_INVALID;
+	GI_CUDA(c, cudaMemsetAsync(c->counters, 0, CNT_COUNT * sizeof(unsigned long long), c->stream));
+	return GI_OK;
+}
+
+uint64_t gi_kernel_launches(const GiContext* c) { return c ? c->launches : 0; }
+
+} // extern "C"

@@ -1,0 +1,248 @@
+// capi.cpp -- flat C entry points over the C++ host classes (Scene, RendererSystem, the three
+// renderers, PFM I/O) so that Python (ctypes) tests and bench.py can drive the same objects a C++
+// embedder would.  Not part of the device C ABI (include/gpugi_b200.h); see include/gpugi_b200_host.h.
+#include "../../include/gpugi_b200_host.h"
+
+#include "bidirectionalpathtracer.hpp"
+#include "globalconfig.hpp"
+#include "hdrimage.hpp"
+#include "lightpathtracer.hpp"
+#include "logger.hpp"
+#include "pathtracer.hpp"
+#include "random.hpp"
+#include "renderersystem.hpp"
+#include "scene.hpp"
+
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+
+using gi::bim::BinaryModel;
+using gi::bim::Chunk;
+
+struct GihScene { std::shared_ptr<Scene> scene; };
+struct GihRendererSystem { std::unique_ptr<RendererSystem> rs; };
+
+extern "C" {
+
+const char* gih_last_error(void) { return gi::LastHostError().c_str(); }
+
+uint32_t gih_wanghash(uint32_t x) { return WangHash(x); }
+
+void gih_set_path_length(int n) { GlobalConfig::SetParameter("pathLength", {Variant(n)}); }
+
+GihScene* gih_scene_load(const char* json_path, int bvh_type)
+{
+	gi::LastHostError().clear();
+	std::unique_ptr<GihScene> h(new GihScene());
+	h->scene = std::make_shared<Scene>(json_path, bvh_type == 0 ? ei::Types3D::BOX : ei::Types3D::OBOX);
+	if (!h->scene->IsValid()) return nullptr;
+	return h.release();
+}
+
+GihScene* gih_scene_from_mesh(const float* positions, const float* normals, const float* texcoords, uint32_t num_vertices, const uint32_t* triangles,
+                              const uint32_t* tri_materials, uint32_t num_triangles, const char* env_json, const char* texture_dir, int build_method)
+{
+	gi::LastHostError().clear();
+	std::unique_ptr<BinaryModel> model(new BinaryModel());
+	std::string err;
+	if (!model->loadEnvironmentText(env_json, &err)) { LOG_ERROR("materials JSON: " << err); return nullptr; }
+	model->chunk().setMesh(reinterpret_cast<const gi::bim::Vec3*>(positions), reinterpret_cast<const gi::bim::Vec3*>(normals),
+	                       reinterpret_cast<const gi::bim::Vec2*>(texcoords), num_vertices, reinterpret_cast<const gi::bim::UVec3*>(triangles), tri_materials,
+	                       num_triangles);
+	model->useJsonMaterialOrder(); // TRIANGLE_MAT indices follow the order of the JSON "materials" object
+	model->chunk().buildHierarchy(build_method == 1 ? Chunk::BuildMethod::KD_TREE : Chunk::BuildMethod::SAH);
+	model->chunk().computeBVHAABoxes();
+	std::unique_ptr<GihScene> h(new GihScene());
+	h->scene = std::make_shared<Scene>(std::move(model), texture_dir ? texture_dir : "", ei::Types3D::BOX);
+	if (!h->scene->IsValid()) return nullptr;
+	return h.release();
+}
+
+void gih_scene_destroy(GihScene* s) { delete s; }
+
+int gih_scene_store(GihScene* s, const char* json_path, const char* bim_name)
+{
+	std::string err;
+	if (!s->scene->GetModel().store(json_path, bim_name, &err)) { LOG_ERROR(err); return 1; }
+	return 0;
+}
+
+void gih_scene_desc(GihScene* s, GiSceneDesc* out) { *out = s->scene->GetSceneDesc(); }
+
+void gih_scene_add_point_light(GihScene* s, const float pos[3], const float intensity[3])
+{
+	Scene::PointLight l;
+	l.position = ei::Vec3(pos[0], pos[1], pos[2]);
+	l.intensity = ei::Vec3(intensity[0], intensity[1], intensity[2]);
+	s->scene->AddPointLight(l);
+}
+
+void gih_scene_info(GihScene* s, GihSceneInfo* out)
+{
+	const Scene& sc = *s->scene;
+	const Chunk& c = sc.GetModel().chunk();
+	out->num_triangles = c.getNumTriangles();
+	out->num_vertices = c.getNumVertices();
+	out->num_nodes = c.getNumNodes();
+	out->num_leaf_triangles = sc.GetNumLeafTriangles();
+	out->num_materials = sc.GetNumMaterials();
+	out->num_tree_levels = c.getNumTreeLevels();
+	out->num_light_triangles = sc.GetNumLightTriangles();
+	out->num_point_lights = uint32_t(sc.GetPointLights().size());
+	out->triangles = reinterpret_cast<const uint32_t*>(c.getTriangles());
+	out->triangle_materials = c.getTriangleMaterials();
+	out->parents = c.getHierarchyParents();
+	ei::Box b = sc.GetBoundingBox();
+	out->bbox_min[0] = b.min.x; out->bbox_min[1] = b.min.y; out->bbox_min[2] = b.min.z;
+	out->bbox_max[0] = b.max.x; out->bbox_max[1] = b.max.y; out->bbox_max[2] = b.max.z;
+	out->light_area_sum = sc.GetLightAreaSum();
+	out->total_area_light_flux = sc.GetTotalAreaLightFlux();
+	out->total_point_light_flux = sc.GetTotalPointLightFlux();
+}
+
+void gih_scene_emissivity(GihScene* s, float* out_rgb)
+{
+	const std::vector<ei::Vec3>& e = s->scene->GetConstantEmissivity();
+	for (size_t i = 0; i < e.size(); ++i) { out_rgb[3 * i] = e[i].x; out_rgb[3 * i + 1] = e[i].y; out_rgb[3 * i + 2] = e[i].z; }
+}
+
+void gih_scene_point_lights(GihScene* s, float* out_pos_intensity)
+{
+	const auto& l = s->scene->GetPointLights();
+	for (size_t i = 0; i < l.size(); ++i)
+	{
+		float* o = out_pos_intensity + 6 * i;
+		o[0] = l[i].position.x; o[1] = l[i].position.y; o[2] = l[i].position.z;
+		o[3] = l[i].intensity.x; o[4] = l[i].intensity.y; o[5] = l[i].intensity.z;
+	}
+}
+
+// ---- standalone light sampler (host code under test against the oracle's restatement)
+struct GihLightSampler { LightSampler sampler; };
+GihLightSampler* gih_light_sampler_create(GihScene* s)
+{
+	GihLightSampler* ls = new GihLightSampler();
+	ls->sampler.SetScene(s->scene);
+	return ls;
+}
+void gih_light_sampler_destroy(GihLightSampler* ls) { delete ls; }
+void gih_light_sampler_seed(GihLightSampler* ls, uint64_t seed) { ls->sampler.SetSeed(seed); }
+void gih_light_sampler_generate(GihLightSampler* ls, GiLightSample* dst, uint32_t n, float bias) { ls->sampler.GenerateRandomSamples(dst, n, bias); }
+
+void gih_camera_params(const float pos[3], const float lookat[3], const float up[3], float yfov, float aspect, int w, int h, GiCamera* out)
+{
+	Camera cam(ei::Vec3(pos[0], pos[1], pos[2]), ei::Vec3(lookat[0], lookat[1], lookat[2]), aspect, yfov, ei::Vec3(up[0], up[1], up[2]));
+	ei::Vec3 U, V, W;
+	cam.ComputeCameraParams(U, V, W);
+	out->position[0] = pos[0]; out->position[1] = pos[1]; out->position[2] = pos[2];
+	out->u[0] = U.x; out->u[1] = U.y; out->u[2] = U.z;
+	out->v[0] = V.x; out->v[1] = V.y; out->v[2] = V.z;
+	out->w[0] = W.x; out->w[1] = W.y; out->w[2] = W.z;
+	out->pixel_area = ei::len(U) * ei::len(V) * 4.0f / (w * h);
+}
+
+// ---- RendererSystem
+GihRendererSystem* gih_rs_create(int device)
+{
+	gi::LastHostError().clear();
+	try
+	{
+		std::unique_ptr<GihRendererSystem> h(new GihRendererSystem());
+		h->rs.reset(new RendererSystem(device));
+		return h.release();
+	}
+	catch (const std::exception& e)
+	{
+		LOG_ERROR(e.what());
+		return nullptr;
+	}
+}
+void gih_rs_destroy(GihRendererSystem* h) { delete h; }
+GiContext* gih_rs_device(GihRendererSystem* h) { return h->rs->GetDevice(); }
+void gih_rs_set_scene(GihRendererSystem* h, GihScene* s) { h->rs->SetScene(s->scene); }
+void gih_rs_set_screen_size(GihRendererSystem* h, int w, int hgt)
+{
+	h->rs->SetScreenSize(ei::IVec2(w, hgt));
+	// application.cpp:128-131: the aspect ratio follows the resolution
+	Camera cam = h->rs->GetCamera();
+	cam.SetAspectRatio(float(w) / float(hgt));
+	h->rs->SetCamera(cam);
+}
+void gih_rs_set_camera(GihRendererSystem* h, const float pos[3], const float lookat[3], float yfov)
+{
+	Camera cam = h->rs->GetCamera();
+	cam.SetPosition(ei::Vec3(pos[0], pos[1], pos[2]));
+	cam.SetLookAt(ei::Vec3(lookat[0], lookat[1], lookat[2]));
+	cam.SetVFov(yfov);
+	h->rs->SetCamera(cam);
+}
+int gih_rs_set_renderer(GihRendererSystem* h, int renderer)
+{
+	switch (renderer)
+	{
+	case GI_RENDERER_PT: h->rs->SetRenderer<Pathtracer>(); return 0;
+	case GI_RENDERER_LPT: h->rs->SetRenderer<LightPathtracer>(); return 0;
+	case GI_RENDERER_BPT: h->rs->SetRenderer<BidirectionalPathtracer>(); return 0;
+	}
+	LOG_ERROR("Unknown renderer index " << renderer << " (0 PT, 1 LPT, 2 BPT)");
+	return 1;
+}
+const char* gih_rs_renderer_name(GihRendererSystem* h)
+{
+	static thread_local std::string name;
+	name = h->rs->GetActiveRenderer() ? h->rs->GetActiveRenderer()->GetName() : "";
+	return name.c_str();
+}
+void gih_rs_set_shard(GihRendererSystem* h, unsigned rank, unsigned world) { h->rs->SetIterationShard(rank, world); }
+void gih_rs_set_synchronous(GihRendererSystem* h, int sync) { h->rs->SetSynchronousDraw(sync != 0); }
+void gih_rs_draw(GihRendererSystem* h) { h->rs->Draw(); }
+uint64_t gih_rs_iteration_count(GihRendererSystem* h) { return h->rs->GetIterationCount(); }
+uint64_t gih_rs_render_time_ms(GihRendererSystem* h) { return h->rs->GetRenderTime(); }
+uint32_t gih_rs_frame_seed(GihRendererSystem* h) { return h->rs->GetFrameSeed(); }
+uint64_t gih_rs_global_iteration(GihRendererSystem* h) { return h->rs->GetGlobalIterationIndex(); }
+int gih_rs_read_backbuffer(GihRendererSystem* h, float* rgba) { return h->rs->GetBackbuffer().ReadImage(rgba) ? 0 : 1; }
+uint32_t gih_rs_num_light_samples(GihRendererSystem* h) { return h->rs->GetNumInitialLightSamples(); }
+void gih_rs_light_samples(GihRendererSystem* h, GiLightSample* out)
+{
+	const auto& v = h->rs->GetInitialLightSamples();
+	if (!v.empty()) std::memcpy(out, v.data(), v.size() * sizeof(GiLightSample));
+}
+void gih_rs_camera(GihRendererSystem* h, GiCamera* out)
+{
+	const Camera& cam = h->rs->GetCamera();
+	float p[3] = {cam.GetPosition().x, cam.GetPosition().y, cam.GetPosition().z};
+	float l[3] = {cam.GetLookAt().x, cam.GetLookAt().y, cam.GetLookAt().z};
+	float u[3] = {cam.GetUp().x, cam.GetUp().y, cam.GetUp().z};
+	gih_camera_params(p, l, u, cam.GetVFov(), cam.GetAspectRatio(), h->rs->GetBackbuffer().GetWidth(), h->rs->GetBackbuffer().GetHeight(), out);
+}
+void gih_rs_renderer_info(GihRendererSystem* h, int32_t* num_rays_per_light_sample, uint32_t* light_cache_capacity, int32_t* avg_light_path_length)
+{
+	*num_rays_per_light_sample = 0; *light_cache_capacity = 0; *avg_light_path_length = 0;
+	Renderer* r = h->rs->GetActiveRenderer();
+	if (auto* l = dynamic_cast<LightPathtracer*>(r)) *num_rays_per_light_sample = l->GetNumRaysPerLightSample();
+	if (auto* b = dynamic_cast<BidirectionalPathtracer*>(r))
+	{
+		*num_rays_per_light_sample = b->GetNumRaysPerLightSample();
+		*light_cache_capacity = b->GetLightCacheCapacity();
+		*avg_light_path_length = b->GetAverageLightPathLength();
+	}
+}
+
+// ---- PFM
+int gih_write_pfm(const char* path, const float* rgba, int w, int h, uint32_t divisor)
+{
+	return WritePfm(reinterpret_cast<const ei::Vec4*>(rgba), ei::IVec2(w, h), path, divisor) ? 0 : 1;
+}
+int gih_load_pfm(const char* path, float* rgb, int capacity_pixels, int* w, int* h)
+{
+	ei::IVec2 size;
+	std::unique_ptr<ei::Vec3[]> img = LoadPfm(path, size);
+	if (!img) return 1;
+	*w = size.x; *h = size.y;
+	if (size.x * size.y > capacity_pixels) return 2;
+	std::memcpy(rgb, img.get(), size_t(size.x) * size.y * sizeof(ei::Vec3));
+	return 0;
+}
+
+} // extern "C"

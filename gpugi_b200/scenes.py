@@ -1,0 +1,365 @@
+"""Seeded, deterministic synthetic stand-ins for the reference's benchmark scenes.
+
+The reference repository ships no geometry (*.bim, textures and env maps are git-ignored,
+.gitignore:57-65), only the scene scripts (scenes/*.txt: camera, point lights, resolution) and the
+material tables (scenes/*/*.json).  Each generator below rebuilds a scene of the named *shape* --
+same materials / lights / camera as the script, procedural geometry of the stated triangle count --
+and hands it to the host layer (Scene.from_mesh), which builds the bim hierarchy.  SURVEY.md 8d.
+
+This module only produces INPUT data (numpy); no light transport happens here.
+"""
+import os
+
+import numpy as np
+
+from . import Scene
+
+# --------------------------------------------------------------------------------------------------
+# mesh assembly
+# --------------------------------------------------------------------------------------------------
+
+
+class MeshBuilder:
+    def __init__(self):
+        self.pos, self.nrm, self.uv, self.tri, self.mat = [], [], [], [], []
+        self.nv = 0
+
+    def add(self, pos, nrm, uv, tri, material):
+        pos = np.asarray(pos, dtype=np.float32).reshape(-1, 3)
+        nrm = np.asarray(nrm, dtype=np.float32).reshape(-1, 3)
+        uv = np.asarray(uv, dtype=np.float32).reshape(-1, 2)
+        tri = np.asarray(tri, dtype=np.uint32).reshape(-1, 3)
+        self.pos.append(pos); self.nrm.append(nrm); self.uv.append(uv)
+        self.tri.append(tri + np.uint32(self.nv))
+        self.mat.append(np.full(tri.shape[0], material, dtype=np.uint32))
+        self.nv += pos.shape[0]
+
+    def num_triangles(self):
+        return int(sum(t.shape[0] for t in self.tri))
+
+    def grid(self, origin, eu, ev, nu, nv, material, uv_scale=(1.0, 1.0), displace=None, flip=False):
+        """(nu x nv) quads spanning origin + s*eu + t*ev, s,t in [0,1]; normal = normalize(eu x ev) (flipped if flip)."""
+        origin = np.asarray(origin, dtype=np.float64); eu = np.asarray(eu, dtype=np.float64); ev = np.asarray(ev, dtype=np.float64)
+        s, t = np.meshgrid(np.linspace(0.0, 1.0, nu + 1), np.linspace(0.0, 1.0, nv + 1), indexing="xy")
+        p = origin[None, None, :] + s[..., None] * eu[None, None, :] + t[..., None] * ev[None, None, :]
+        n = np.cross(eu, ev)
+        n = n / np.linalg.norm(n)
+        if flip:
+            n = -n
+        normals = np.broadcast_to(n, p.shape).copy()
+        if displace is not None:
+            d, normals = displace(s, t, p, n)
+            p = p + d
+        uv = np.stack([s * uv_scale[0], t * uv_scale[1]], axis=-1)
+        idx = np.arange((nu + 1) * (nv + 1)).reshape(nv + 1, nu + 1)
+        a, b, c, d_ = idx[:-1, :-1].ravel(), idx[:-1, 1:].ravel(), idx[1:, 1:].ravel(), idx[1:, :-1].ravel()
+        if flip:
+            tris = np.concatenate([np.stack([a, c, b], 1), np.stack([a, d_, c], 1)], 0)
+        else:
+            tris = np.concatenate([np.stack([a, b, c], 1), np.stack([a, c, d_], 1)], 0)
+        self.add(p.reshape(-1, 3), normals.reshape(-1, 3), uv.reshape(-1, 2), tris, material)
+
+    def box(self, lo, hi, material, tess=1, uv_scale=(1.0, 1.0), inward=False, skip_faces=()):
+        """Axis-aligned box; outward normals (inward=True: a room seen from inside).
+        skip_faces: indices into (-x,+x,-y,+y,-z,+z) to leave out (e.g. a bottom face resting on a floor)."""
+        lo = np.asarray(lo, dtype=np.float64); hi = np.asarray(hi, dtype=np.float64)
+        dx, dy, dz = np.array([hi[0] - lo[0], 0, 0.0]), np.array([0, hi[1] - lo[1], 0.0]), np.array([0, 0, hi[2] - lo[2]])
+        faces = [
+            (lo, dz, dy),                     # -x
+            (lo + dx, dy, dz),                # +x
+            (lo, dx, dz),                     # -y
+            (lo + dy, dz, dx),                # +y
+            (lo, dy, dx),                     # -z
+            (lo + dz, dx, dy),                # +z
+        ]
+        mats = material if isinstance(material, (list, tuple)) else [material] * 6
+        for k, ((o, eu, ev), m) in enumerate(zip(faces, mats)):
+            if k in skip_faces:
+                continue
+            self.grid(o, eu, ev, tess, tess, m, uv_scale, flip=inward)
+
+    def cylinder(self, base, radius, height, material, segments=24, rings=8, uv_scale=(1.0, 1.0), axis=1):
+        base = np.asarray(base, dtype=np.float64)
+        th = np.linspace(0.0, 2.0 * np.pi, segments + 1)
+        hh = np.linspace(0.0, 1.0, rings + 1)
+        T, H = np.meshgrid(th, hh, indexing="xy")
+        ring = np.stack([np.cos(T), np.zeros_like(T), np.sin(T)], -1)
+        up = np.zeros(3); up[1] = 1.0
+        p = ring * radius + H[..., None] * height * up
+        n = ring.copy()
+        if axis != 1:
+            perm = [1, 0, 2] if axis == 0 else [0, 2, 1]
+            p = p[..., perm]; n = n[..., perm]
+        p = p + base
+        uv = np.stack([T / (2 * np.pi) * uv_scale[0], H * uv_scale[1]], -1)
+        idx = np.arange((segments + 1) * (rings + 1)).reshape(rings + 1, segments + 1)
+        a, b, c, d_ = idx[:-1, :-1].ravel(), idx[:-1, 1:].ravel(), idx[1:, 1:].ravel(), idx[1:, :-1].ravel()
+        tris = np.concatenate([np.stack([a, c, b], 1), np.stack([a, d_, c], 1)], 0)
+        self.add(p.reshape(-1, 3), n.reshape(-1, 3), uv.reshape(-1, 2), tris, material)
+
+    def sphere(self, center, radius, material, segments=24, rings=12, uv_scale=(1.0, 1.0), squash=(1.0, 1.0, 1.0)):
+        center = np.asarray(center, dtype=np.float64)
+        th = np.linspace(0.0, 2.0 * np.pi, segments + 1)
+        ph = np.linspace(1e-3, np.pi - 1e-3, rings + 1)
+        T, Ph = np.meshgrid(th, ph, indexing="xy")
+        n = np.stack([np.sin(Ph) * np.cos(T), np.cos(Ph), np.sin(Ph) * np.sin(T)], -1)
+        p = n * radius * np.asarray(squash) + center
+        nn = n / np.asarray(squash)
+        nn = nn / np.linalg.norm(nn, axis=-1, keepdims=True)
+        uv = np.stack([T / (2 * np.pi) * uv_scale[0], Ph / np.pi * uv_scale[1]], -1)
+        idx = np.arange((segments + 1) * (rings + 1)).reshape(rings + 1, segments + 1)
+        a, b, c, d_ = idx[:-1, :-1].ravel(), idx[:-1, 1:].ravel(), idx[1:, 1:].ravel(), idx[1:, :-1].ravel()
+        tris = np.concatenate([np.stack([a, b, c], 1), np.stack([a, c, d_], 1)], 0)
+        self.add(p.reshape(-1, 3), nn.reshape(-1, 3), uv.reshape(-1, 2), tris, material)
+
+    def arrays(self):
+        return (np.concatenate(self.pos), np.concatenate(self.nrm), np.concatenate(self.uv), np.concatenate(self.tri), np.concatenate(self.mat))
+
+
+def legacy_material(albedo=(0.5, 0.5, 0.5), specular=(0.0, 0.0, 0.0), roughness=1.0, opacity=1.0, emissivity=(0.0, 0.0, 0.0), refraction_index=None,
+                    albedo_texture=None):
+    """One entry of the JSON 'materials' object with the keys Scene::LoadMaterial reads (scene.cpp:138-146)."""
+    m = {"type": "legacy", "specularColor": list(map(float, specular)), "roughness": [float(roughness)], "opacity": [float(opacity)] * 3,
+         "emissivity": list(map(float, emissivity))}
+    if albedo_texture is not None:
+        m["albedo"] = albedo_texture
+    else:
+        m["albedo"] = list(map(float, albedo))
+    if refraction_index is not None:
+        m["refractionIndex"] = [float(refraction_index)]
+    return m
+
+
+# --------------------------------------------------------------------------------------------------
+# procedural textures (binary PPM, read by the host Scene as SRGB8_ALPHA8)
+# --------------------------------------------------------------------------------------------------
+
+
+def _write_ppm(path, rgb):
+    h, w, _ = rgb.shape
+    with open(path, "wb") as f:
+        f.write(b"P6\n%d %d\n255\n" % (w, h))
+        f.write(np.ascontiguousarray(rgb, dtype=np.uint8).tobytes())
+
+
+def procedural_texture(kind, size, seed):
+    rng = np.random.RandomState(seed)
+    y, x = np.mgrid[0:size, 0:size].astype(np.float32) / np.float32(size)
+    base = rng.uniform(0.25, 0.85, size=3).astype(np.float32)
+    alt = np.clip(base * rng.uniform(0.3, 0.8) + rng.uniform(-0.1, 0.1, size=3), 0.02, 0.95).astype(np.float32)
+    if kind == 0:    # bricks
+        rows = 16
+        yy = y * rows
+        xx = x * rows / 2 + 0.5 * (np.floor(yy) % 2)
+        mortar = ((yy % 1.0) < 0.08) | ((xx % 1.0) < 0.04)
+        t = mortar.astype(np.float32)
+    elif kind == 1:  # checker
+        n = 8 + (seed % 5) * 4
+        t = ((np.floor(x * n) + np.floor(y * n)) % 2).astype(np.float32)
+    elif kind == 2:  # stripes
+        n = 6 + (seed % 7) * 3
+        t = (0.5 + 0.5 * np.sin(2 * np.pi * n * (x + 0.3 * y))).astype(np.float32)
+    elif kind == 3:  # value noise (wraps)
+        t = np.zeros_like(x)
+        amp = 0.5
+        for octave in range(5):
+            n = 4 << octave
+            g = rng.rand(n, n).astype(np.float32)
+            fx, fy = x * n, y * n
+            ix, iy = np.floor(fx).astype(np.int64), np.floor(fy).astype(np.int64)
+            ax, ay = fx - ix, fy - iy
+            g00 = g[iy % n, ix % n]; g10 = g[iy % n, (ix + 1) % n]; g01 = g[(iy + 1) % n, ix % n]; g11 = g[(iy + 1) % n, (ix + 1) % n]
+            t += amp * ((g00 * (1 - ax) + g10 * ax) * (1 - ay) + (g01 * (1 - ax) + g11 * ax) * ay)
+            amp *= 0.5
+        t = np.clip(t, 0, 1)
+    else:            # tiles with rosettes
+        n = 4 + (seed % 4) * 2
+        u, v = (x * n) % 1.0 - 0.5, (y * n) % 1.0 - 0.5
+        r = np.sqrt(u * u + v * v)
+        t = (0.5 + 0.5 * np.cos(18.0 * r + 3.0 * np.arctan2(v, u))).astype(np.float32)
+    grain = rng.rand(size, size).astype(np.float32) * 0.08
+    rgb = base[None, None, :] * (1 - t[..., None]) + alt[None, None, :] * t[..., None] + grain[..., None] - 0.04
+    return np.clip(rgb * 255.0 + 0.5, 0, 255).astype(np.uint8)
+
+
+def write_textures(directory, count, size, seed=1):
+    os.makedirs(directory, exist_ok=True)
+    names = []
+    for i in range(count):
+        name = "tex%02d.ppm" % i
+        _write_ppm(os.path.join(directory, name), procedural_texture(i % 5, size, seed * 1000 + i))
+        names.append(name)
+    return names
+
+
+# --------------------------------------------------------------------------------------------------
+# C1  box1 (scenes/box1.txt, scenes/box1/box1.json)
+# --------------------------------------------------------------------------------------------------
+
+BOX1_MATERIAL_NAMES = ["DefaultMaterial", "Glass", "Floor", "RightWall", "Wall", "LeftWall", "White", "LightR", "LightL"]
+
+BOX1_CAMERA = {"pos": (0.0, 1.5, 2.27), "lookat": (0.0, 1.5, 2.0), "fov": 67.0}   # scenes/box1.txt:2-4
+
+
+def box1_materials():
+    """scenes/box1/box1.json:4-86, verbatim values."""
+    return {
+        "DefaultMaterial": legacy_material((0.6, 0.6, 0.6), (0, 0, 0), 1.0, 1.0),
+        "Glass": legacy_material((0.5882, 0.5882, 0.5882), (0.035, 0.035, 0.035), 0.01, 0.0),
+        "Floor": legacy_material((0.5882, 0.5882, 0.5882), (0, 0, 0), 0.9, 1.0),
+        "RightWall": legacy_material((0.02, 0.2863, 0.02), (0, 0, 0), 0.9, 1.0),
+        "Wall": legacy_material((0.5882, 0.5882, 0.5882), (0, 0, 0), 0.9, 1.0),
+        "LeftWall": legacy_material((0.02, 0.02, 0.3373), (0, 0, 0), 0.9, 1.0),
+        "White": legacy_material((1, 1, 1), (0, 0, 0), 0.9, 1.0),
+        "LightR": legacy_material((0.5882, 0.5882, 0.5882), (0, 0, 0), 1.0, 1.0, (803.9, 192.2, 19.6)),
+        "LightL": legacy_material((0.5882, 0.5882, 0.5882), (0, 0, 0), 1.0, 1.0, (98.0, 392.2, 788.2)),
+    }
+
+
+def make_box1(tess=4, build_method="sah", coincident_faces=False):
+    """Closed room x in [-1.5,1.5], y in [0,3], z in [-3,2.3] + a white box, a glass box and two emissive quads.
+    coincident_faces=True keeps the boxes' bottom faces, which lie exactly in the floor plane: a
+    deliberate exact-tie case for the traversal parity tests."""
+    M = {n: i for i, n in enumerate(BOX1_MATERIAL_NAMES)}
+    mb = MeshBuilder()
+    lo, hi = np.array([-1.5, 0.0, -3.0]), np.array([1.5, 3.0, 2.3])
+    # room, seen from inside: faces -x,+x,-y,+y,-z,+z
+    mb.box(lo, hi, [M["LeftWall"], M["RightWall"], M["Floor"], M["Wall"], M["Wall"], M["Wall"]], tess=tess, inward=True)
+    skip = () if coincident_faces else (2,)
+    mb.box([-1.0, 0.0, -2.2], [-0.1, 1.7, -1.3], M["White"], tess=max(1, tess // 2), skip_faces=skip)
+    mb.box([0.25, 0.0, -1.3], [1.05, 0.8, -0.5], M["Glass"], tess=max(1, tess // 2), skip_faces=skip)
+    # emissive quads just below the ceiling, facing down (normal -y): eu x ev must point to -y
+    mb.grid([0.35, 2.98, -1.9], [0.6, 0, 0], [0, 0, 0.6], 2, 2, M["LightR"])
+    mb.grid([-0.95, 2.98, -1.9], [0.6, 0, 0], [0, 0, 0.6], 2, 2, M["LightL"])
+    pos, nrm, uv, tri, mat = mb.arrays()
+    return Scene.from_mesh(pos, nrm, uv, tri, mat, box1_materials(), "", build_method)
+
+
+# --------------------------------------------------------------------------------------------------
+# C2  Sponza-shaped atrium (scenes/cryteksponza.txt)
+# --------------------------------------------------------------------------------------------------
+
+SPONZA_CAMERA = {"pos": (784.069214, 525.171387, -123.871895), "lookat": (-784.925598, -525.603210, 124.154999), "fov": 70.0}  # cryteksponza.txt:2-4
+SPONZA_POINT_LIGHTS = [((-382.0, 160.0, -180.0), (50000.0, 50000.0, 50000.0)), ((-382.0, 160.0, 150.0), (50000.0, 50000.0, 50000.0)),
+                       ((487.4, 160.0, -180.0), (50000.0, 50000.0, 50000.0)), ((487.4, 160.0, 150.0), (50000.0, 50000.0, 50000.0))]   # :8-11
+
+
+def make_sponza_like(texture_dir, target_triangles=262144, texture_size=1024, num_materials=25, seed=7, build_method="sah"):
+    """Two-storey colonnaded atrium, extent ~3700 x 1500 x 2300, `num_materials` textured materials."""
+    rng = np.random.RandomState(seed)
+    tex = write_textures(texture_dir, num_materials, texture_size, seed)
+    materials = {}
+    for i in range(num_materials):
+        rough = [1.0, 0.9, 0.7, 0.5, 0.3][i % 5]
+        spec = 0.0 if i % 3 else 0.04
+        materials["mat%02d" % i] = legacy_material(specular=(spec, spec, spec), roughness=rough, albedo_texture=tex[i])
+    mb = MeshBuilder()
+    X, Y, Z = 1850.0, 1500.0, 1150.0
+
+    def m(i):
+        return i % num_materials
+
+    # shell: floor, roof, four walls (finely tessellated so the BVH has work everywhere)
+    mb.grid([-X, 0, -Z], [0, 0, 2 * Z], [2 * X, 0, 0], 48, 64, m(0), (12, 20))                 # floor, normal +y
+    mb.grid([-X, Y, -Z], [2 * X, 0, 0], [0, 0, 2 * Z], 32, 24, m(1), (10, 6))                  # roof, normal -y
+    mb.grid([-X, 0, -Z], [2 * X, 0, 0], [0, Y, 0], 64, 24, m(2), (16, 6))                      # z = -Z, normal +z
+    mb.grid([-X, 0, Z], [0, Y, 0], [2 * X, 0, 0], 24, 64, m(3), (6, 16))                       # z = +Z, normal -z
+    mb.grid([-X, 0, -Z], [0, Y, 0], [0, 0, 2 * Z], 24, 40, m(4), (6, 10))                      # x = -X, normal +x
+    mb.grid([X, 0, -Z], [0, 0, 2 * Z], [0, Y, 0], 40, 24, m(5), (10, 6))                       # x = +X, normal -x
+    # galleries: slabs along both long sides on the upper floor, with a parapet
+    for side in (-1.0, 1.0):
+        z0, z1 = (side * 420.0, side * Z) if side > 0 else (side * Z, side * 420.0)
+        mb.box([-X + 1, 480.0, z0], [X - 1, 520.0, z1], m(6), tess=12, uv_scale=(12, 3))
+        zp = side * 420.0
+        mb.box([-X + 1, 520.0, zp - 8], [X - 1, 600.0, zp + 8], m(7), tess=10, uv_scale=(20, 1))
+    # colonnades: two rows x two storeys of columns with capitals and bases
+    col_x = np.linspace(-1600.0, 1600.0, 14)
+    k = 0
+    for side in (-1.0, 1.0):
+        for x in col_x:
+            for (y0, hgt, rad) in ((0.0, 480.0, 42.0), (520.0, 520.0, 34.0)):
+                mb.cylinder([x, y0 + 30, side * 420.0], rad, hgt - 60, m(8 + k % 3), segments=28, rings=10, uv_scale=(2, 4))
+                mb.box([x - rad * 1.4, y0, side * 420.0 - rad * 1.4], [x + rad * 1.4, y0 + 30, side * 420.0 + rad * 1.4], m(11), tess=2)
+                mb.box([x - rad * 1.4, y0 + hgt - 30, side * 420.0 - rad * 1.4], [x + rad * 1.4, y0 + hgt, side * 420.0 + rad * 1.4], m(11), tess=2)
+                k += 1
+    # arches between columns approximated by lintels
+    for side in (-1.0, 1.0):
+        for i in range(len(col_x) - 1):
+            xa, xb = col_x[i] + 50, col_x[i + 1] - 50
+            mb.box([xa, 400.0, side * 420.0 - 25], [xb, 480.0, side * 420.0 + 25], m(12), tess=3, uv_scale=(3, 1))
+            mb.box([xa, 960.0, side * 420.0 - 20], [xb, 1040.0, side * 420.0 + 20], m(12), tess=3, uv_scale=(3, 1))
+    # hanging curtains: wavy, finely tessellated sheets between upper columns
+    def wave(amp, freq, phase):
+        def f(s, t, p, n):
+            d = amp * np.sin(2 * np.pi * freq * s + phase) * (0.3 + 0.7 * t)
+            dd = amp * 2 * np.pi * freq * np.cos(2 * np.pi * freq * s + phase) * (0.3 + 0.7 * t)
+            disp = d[..., None] * n[None, None, :]
+            # approximate normal: n - dd * tangent_u (unit) / |eu|
+            nn = np.broadcast_to(n, p.shape).copy()
+            nn[..., 0] -= dd / 300.0
+            nn /= np.linalg.norm(nn, axis=-1, keepdims=True)
+            return disp, nn
+        return f
+    for i in range(0, len(col_x) - 1, 2):
+        for side in (-1.0, 1.0):
+            xa, xb = col_x[i] + 40, col_x[i + 1] - 40
+            mb.grid([xa, 560.0, side * 400.0], [xb - xa, 0, 0], [0, 380.0, 0], 40, 28, m(13 + (i // 2) % 4), (2, 2), displace=wave(14.0, 3.0, 0.7 * i), flip=side < 0)
+    # props on the floor: vases (squashed spheres) and plinths
+    for i in range(24):
+        x = rng.uniform(-1500, 1500); z = rng.uniform(-330, 330)
+        mb.box([x - 40, 0, z - 40], [x + 40, 60, z + 40], m(17), tess=2, skip_faces=(2,))
+        mb.sphere([x, 60 + 55, z], 55.0, m(18 + i % 4), segments=28, rings=16, squash=(1.0, 1.3, 1.0))
+    # a central fountain basin
+    mb.cylinder([0, 0, 0], 260.0, 70.0, m(22), segments=64, rings=4, uv_scale=(8, 1))
+    mb.sphere([0, 150, 0], 90.0, m(23), segments=40, rings=24)
+    # fill up to the exact triangle target with a relief frieze along the end walls
+    remaining = target_triangles - mb.num_triangles()
+    if remaining < 0:
+        raise ValueError("sponza-like base geometry already has %d triangles" % mb.num_triangles())
+    def relief(s, t, p, n):
+        d = 6.0 * np.sin(40 * np.pi * s) * np.sin(6 * np.pi * t)
+        disp = d[..., None] * n[None, None, :]
+        return disp, np.broadcast_to(n, p.shape).copy()
+    quads = remaining // 2
+    if quads > 0:
+        rows = 64
+        cols = quads // rows
+        if cols > 0:
+            mb.grid([-X + 2, 600.0, -Z + 4], [0, 500.0, 0], [0, 0, 2 * Z - 8], rows, cols, m(24), (2, 12), displace=relief)
+        rest = quads - rows * cols
+        if rest > 0:
+            mb.grid([X - 2, 600.0, -Z + 4], [0, 0, 2 * Z - 8], [0, 500.0, 0], rest, 1, m(24), (12, 2))
+    if (target_triangles - mb.num_triangles()) == 1:  # odd target: one more small triangle
+        mb.add([[0, 1400, 0], [10, 1400, 0], [0, 1400, 10]], [[0, -1, 0]] * 3, [[0, 0], [1, 0], [0, 1]], [[0, 1, 2]], m(24))
+    pos, nrm, uv, tri, mat = mb.arrays()
+    scene = Scene.from_mesh(pos, nrm, uv, tri, mat, materials, texture_dir, build_method)
+    for p, i in SPONZA_POINT_LIGHTS:
+        scene.add_point_light(p, i)
+    return scene
+
+
+# --------------------------------------------------------------------------------------------------
+# small analytic scenes for tests
+# --------------------------------------------------------------------------------------------------
+
+
+def make_random_triangles(n, seed=0, extent=10.0, size=1.0, build_method="sah"):
+    """n random triangles in a cube: the adversarial case for traversal parity (overlaps, slivers)."""
+    rng = np.random.RandomState(seed)
+    c = rng.uniform(-extent, extent, size=(n, 1, 3))
+    p = (c + rng.uniform(-size, size, size=(n, 3, 3))).astype(np.float32).reshape(-1, 3)
+    nrm = np.tile(np.array([0, 1, 0], dtype=np.float32), (3 * n, 1))
+    uv = rng.rand(3 * n, 2).astype(np.float32)
+    tri = np.arange(3 * n, dtype=np.uint32).reshape(n, 3)
+    mat = (np.arange(n) % 2).astype(np.uint32)
+    mats = {"a": legacy_material((0.7, 0.7, 0.7)), "b": legacy_material((0.3, 0.5, 0.7), (0.04, 0.04, 0.04), 0.3)}
+    return Scene.from_mesh(p, nrm, uv, tri, mat, mats, "", build_method)
+
+
+def make_furnace(albedo=0.5, emission=1.0, tess=2):
+    """Closed box whose walls all emit `emission` with albedo `albedo`: radiance = emission/(1-albedo) everywhere."""
+    mb = MeshBuilder()
+    mb.box([-1, -1, -1], [1, 1, 1], 0, tess=tess, inward=True)
+    pos, nrm, uv, tri, mat = mb.arrays()
+    mats = {"wall": legacy_material((albedo,) * 3, (0, 0, 0), 1.0, 1.0, (emission,) * 3)}
+    return Scene.from_mesh(pos, nrm, uv, tri, mat, mats, "")

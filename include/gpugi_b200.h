@@ -1,0 +1,301 @@
+/*
+ * gpugi_b200.h -- C ABI of the B200-native light-transport hot path.
+ *
+ * This is the drop-in boundary for gpugi's `Renderer` seam.  The reference has no
+ * FFI layer; the seam is the abstract C++ class `Renderer`
+ * (gpugi/renderer/renderer.hpp:25-51) plus the services of `RendererSystem`
+ * (gpugi/renderer/renderersystem.hpp:37-144).  Every entry point below cites the
+ * reference interface it replaces.  Conventions:
+ *   - plain C, opaque handle, `int` status (0 = GI_OK), no exceptions, no torch types;
+ *   - all pointer arguments are HOST memory and are copied during the call unless
+ *     the name says `_device`;
+ *   - one host thread per context (the reference runs everything on one GL thread,
+ *     scriptprocessing.cpp:174-181); render calls are asynchronous on the context's
+ *     CUDA stream, `gi_synchronize` / read-back calls are the sync points
+ *     (the reference's `glFinish`, renderersystem.cpp:249-253).
+ *   - there is NO CPU fallback: every compute entry point fails with GI_ERR_CUDA
+ *     when no sm_100 device is usable.
+ */
+#ifndef GPUGI_B200_H
+#define GPUGI_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GI_API __attribute__((visibility("default")))
+
+typedef struct GiContext GiContext;   /* opaque; owns device buffers, textures, stream */
+
+/* ------------------------------------------------------------------ status */
+enum {
+	GI_OK = 0,
+	GI_ERR_INVALID = 1,   /* bad argument / call order                         */
+	GI_ERR_CUDA = 2,      /* CUDA runtime error, text in gi_last_error()       */
+	GI_ERR_NOSCENE = 3,   /* render/trace before gi_upload_scene               */
+	GI_ERR_CAPACITY = 4   /* light cache / queue capacity exceeded             */
+};
+
+/* ------------------------------------------------------------------ scene PODs
+ * Byte-identical to what the reference uploads into its four texture buffers. */
+
+/* Scene::TreeNode<ei::Box>, gpugi/scene/scene.hpp:31-38; consumed by
+ * FetchIntersectBoxNode, gpugi/shader/intersectiontests.glsl:100-111.
+ * first_child: MSB set => leaf, low 31 bits = leaf index (2 triangles per leaf).
+ * escape: next node in preorder when this subtree is skipped; 0 terminates.   */
+typedef struct GiNode {
+	float    min[3];
+	uint32_t first_child;
+	float    max[3];
+	uint32_t escape;
+} GiNode;
+
+/* Scene::Triangle, scene.hpp:63-67 == bim leaf UVec4 (bim_sahspilt.cpp:44-46).
+ * An unused leaf slot is all zero (v[0]==v[1] marks it, traceray.glsl:127).   */
+typedef struct GiTriangle {
+	uint32_t v[3];
+	uint32_t material;
+} GiTriangle;
+
+/* Scene::VertexInfo, scene.hpp:71-75: (atan2(n.y,n.x), n.z, u, v).            */
+typedef struct GiVertexInfo {
+	float normal_phi;
+	float normal_z;
+	float texcoord[2];
+} GiVertexInfo;
+
+/* LightSampler::LightSample, gpugi/scene/lightsampler.hpp:19-25.
+ * normal_theta_cos > 1.5 marks an omnidirectional point light
+ * (lightsource.glsl:25, lightsampler.cpp:92).                                 */
+typedef struct GiLightSample {
+	float position[3];
+	float normal_phi;
+	float intensity[3];
+	float normal_theta_cos;
+} GiLightSample;
+
+/* Texture payload formats (replace the GL formats of scene.cpp:196,206-242). */
+enum {
+	GI_TEX_SRGB8_ALPHA8 = 0, /* 4 x u8, sRGB decode on RGB (file textures, texture2d.cpp:31-52) */
+	GI_TEX_RGBA8        = 1, /* 4 x u8 linear unorm (1x1 RGB8 constants, alpha = 255)           */
+	GI_TEX_RGBA32F      = 2  /* 4 x f32 (1x1 RGB32F / RGBA32F constants, alpha = 1 for RGB)      */
+};
+
+/* One 2D texture, level 0 only.  Sampler state is fixed to the reference's
+ * (min NEAREST / mag LINEAR / REPEAT, scene.cpp:16-21) => bilinear + wrap.   */
+typedef struct GiTexture {
+	int32_t     width;
+	int32_t     height;
+	int32_t     format;   /* GI_TEX_*                                          */
+	int32_t     reserved;
+	const void* pixels;   /* width*height texels, row 0 first                  */
+} GiTexture;
+
+/* Scene::Material, scene.hpp:79-89, with the 64-bit bindless GL handles
+ * replaced by indices into GiSceneDesc::textures.                            */
+typedef struct GiMaterial {
+	int32_t diffuse_tex;
+	int32_t opacity_tex;
+	int32_t reflectiveness_tex;
+	int32_t emissivity_tex;
+	float   fresnel0[3];
+	float   refraction_index_avg;
+	float   fresnel1[3];
+	float   padding;
+} GiMaterial;
+
+/* Everything Scene::UploadGeometry / UploadHierarchy / LoadMaterial hand to GL
+ * (scene.cpp:75-130,132-180) and RendererSystem::SetScene binds
+ * (renderersystem.cpp:132-152).                                              */
+typedef struct GiSceneDesc {
+	const GiNode*       nodes;
+	uint32_t            num_nodes;
+	const GiTriangle*   leaf_triangles;      /* 2 per leaf                      */
+	uint32_t            num_leaf_triangles;
+	const float*        positions;           /* 3 floats per vertex             */
+	const GiVertexInfo* vertex_info;
+	uint32_t            num_vertices;
+	const GiMaterial*   materials;
+	uint32_t            num_materials;
+	const GiTexture*    textures;
+	uint32_t            num_textures;
+	uint32_t            num_tree_levels;     /* Chunk::getNumTreeLevels, 0 = unknown */
+} GiSceneDesc;
+
+/* Camera UBO, gpugi/shader/globaluniforms.glsl:7-15, filled by
+ * RendererSystem::SetCamera, renderersystem.cpp:196-213.                     */
+typedef struct GiCamera {
+	float position[3];
+	float u[3];
+	float v[3];
+	float w[3];
+	float pixel_area;
+} GiCamera;
+
+/* Ray batch records for gi_trace (parity + Mrays/s).                         */
+typedef struct GiRay {
+	float origin[3];
+	float t_max;          /* closest-hit: initial rayLength (RAY_MAX = 3.402823466e38 for "infinite");
+	                         any-hit: the finite rayLength                     */
+	float direction[3];
+	uint32_t flags;       /* bit 0: any-hit query                              */
+} GiRay;
+
+typedef struct GiHit {
+	float   t;            /* closest-hit distance; t_max unchanged if missed   */
+	int32_t leaf_tri;     /* HIT_INDEX_OUTPUT .y: index into leaf_triangles, -1 = miss (traceray.glsl:153-156).
+	                         any-hit: 1 = occluded, 0 = free                   */
+	float   bary_y;       /* barycentricCoord.y / .z (x = 1-(z+y))             */
+	float   bary_z;
+} GiHit;
+
+/* Renderer selection = Application::SwitchRenderer cases 0,1,2 (application.cpp:233-241). */
+enum { GI_RENDERER_PT = 0, GI_RENDERER_LPT = 1, GI_RENDERER_BPT = 2 };
+
+/* gi_trace / gi_set_option modes */
+enum {
+	GI_TRAVERSAL_FAST = 0,      /* ordered short-stack traversal + exact fallback (default)      */
+	GI_TRAVERSAL_REFERENCE = 1  /* stackless escape-pointer walk in the reference's visit order  */
+};
+enum {
+	GI_OPT_TRAVERSAL = 0,       /* GI_TRAVERSAL_*                                                */
+	GI_OPT_TEXTURE_FILTER = 1,  /* 0 = hardware bilinear (9-bit weights), 1 = fp32 bilinear      */
+	GI_OPT_SCHEDULER = 2        /* 0 = wavefront (default when available), 1 = megakernel        */
+};
+
+/* Per-iteration parameters: the compile-time #defines and small UBOs of the three renderers. */
+typedef struct GiIterationParams {
+	int32_t  renderer;                  /* GI_RENDERER_*                                          */
+	uint32_t frame_seed;                /* PerIteration.FrameSeed = WangHash(iteration), renderersystem.cpp:101 */
+	int32_t  max_path_length;           /* MAX_PATHLENGTH, pathtracer.cpp:61                      */
+	int32_t  num_rays_per_light_sample; /* LightPathTrace.NumRaysPerLightSample, lightpathtracer.cpp:34 */
+	int32_t  light_cache_capacity;      /* LightPathTrace.LightCacheCapacity, bidirectionalpathtracer.cpp:112-126 */
+	int32_t  warmup;                    /* 1 = SAVE_LIGHT_CACHE_WARMUP light pass only (bidirectionalpathtracer.cpp:76-108) */
+	int32_t  reserved[2];
+} GiIterationParams;
+
+/* Work counters (TRACERAY_DEBUG_VARS-style, stdheader.glsl:17-22) + BPT counters
+ * (lightcache.glsl:27-37).  Cumulative since the last gi_reset_counters.      */
+typedef struct GiCounters {
+	uint64_t closest_rays;       /* TraceRay calls                                         */
+	uint64_t any_rays;           /* TraceRayAnyHit calls                                   */
+	uint64_t camera_paths;       /* eye paths started                                      */
+	uint64_t light_paths;        /* light paths started                                    */
+	uint64_t shaded_vertices;    /* GetTriangleHitInfo+SampleMaterialData evaluations       */
+	uint64_t splats;             /* WriteAtomic calls                                      */
+	uint64_t exact_fallback_rays;/* fast traversal rays re-traced in reference order       */
+	uint64_t node_tests;         /* box tests actually executed by the device traversal    */
+	uint64_t triangle_tests;     /* triangle tests actually executed                       */
+	uint32_t light_cache_entries;/* NumLightCacheEntries after the last light pass         */
+	uint32_t light_path_length_sum; /* LightPathLengthSum (warm-up)                        */
+} GiCounters;
+
+/* ------------------------------------------------------------------ lifecycle */
+
+/* Library/ABI version (major*100 + minor). */
+GI_API int gi_version(void);
+
+/* Replaces RendererSystem::RendererSystem (renderersystem.cpp:23-48): creates the
+ * context on CUDA device `device` (one process per GPU, LOCAL_RANK).  Fails with
+ * GI_ERR_CUDA if the device is missing or is not sm_100 -- there is no CPU path. */
+GI_API int gi_create(int device, GiContext** out_ctx);
+
+/* Replaces RendererSystem::~RendererSystem (renderersystem.cpp:50-55) and Scene::~Scene. */
+GI_API void gi_destroy(GiContext* ctx);
+
+/* Text of the last error on this context (ctx may be NULL: last gi_create error).
+ * Replaces LOG_ERROR + GL debug output (scene.cpp:31,42; outputwindow.cpp:68-70). */
+GI_API const char* gi_last_error(const GiContext* ctx);
+
+/* Launch all following work on `cuda_stream` (a cudaStream_t; NULL = the context's own
+ * stream).  Lets the caller time with events on its own stream. */
+GI_API int gi_set_stream(GiContext* ctx, void* cuda_stream);
+
+/* GI_OPT_* switches; the shader-#define equivalents that are not per-iteration. */
+GI_API int gi_set_option(GiContext* ctx, int option, int value);
+
+/* ------------------------------------------------------------------ scene / camera / screen */
+
+/* Replaces Scene::UploadGeometry + UploadHierarchy + LoadMaterial (scene.cpp:75-242)
+ * and RendererSystem::SetScene (renderersystem.cpp:132-168): copies the bim hierarchy,
+ * re-lays it out for the device (DESIGN.md "HBM layout"), creates texture objects,
+ * resets the iteration state and clears the accumulator. */
+GI_API int gi_upload_scene(GiContext* ctx, const GiSceneDesc* scene);
+
+/* Replaces RendererSystem::SetEnvironmentMap (renderersystem.cpp:173-186) /
+ * Pathtracer::SetEnvironmentMap (pathtracer.cpp:41-45).  faces = -X,+X,-Y,+Y,-Z,+Z,
+ * each size*size RGBA8 sRGB; faces == NULL restores the 1x1 black default
+ * (renderersystem.cpp:39-47). */
+GI_API int gi_set_environment_map(GiContext* ctx, int size, const uint8_t* const* faces);
+
+/* Replaces RendererSystem::SetCamera (renderersystem.cpp:188-219): uploads the camera
+ * UBO values and clears the accumulator. */
+GI_API int gi_set_camera(GiContext* ctx, const GiCamera* camera);
+
+/* Replaces RendererSystem::SetScreenSize + Renderer::SetScreenSize
+ * (renderersystem.cpp:221-233; pathtracer.cpp:36-39): (re)allocates the RGBA32F sum
+ * accumulator and clears it. */
+GI_API int gi_set_screen_size(GiContext* ctx, int width, int height);
+
+/* Replaces the light-sample half of RendererSystem::PerIterationBufferUpdate
+ * (renderersystem.cpp:106-111) and SetNumInitialLightSamples (:118-130): the next
+ * iteration uses these `n` initial light samples.  Copied at call time. */
+GI_API int gi_set_light_samples(GiContext* ctx, const GiLightSample* samples, uint32_t n);
+
+/* Replaces gl::Texture2D::ClearToZero on the backbuffer (renderersystem.hpp:79). */
+GI_API int gi_clear_accumulator(GiContext* ctx);
+
+/* Allocates the BPT light cache for `capacity` 64-byte entries
+ * (bidirectionalpathtracer.cpp:116-131). */
+GI_API int gi_alloc_light_cache(GiContext* ctx, uint32_t capacity);
+
+/* ------------------------------------------------------------------ hot path */
+
+/* Replaces Renderer::Draw (renderer.hpp:42) of Pathtracer (pathtracer.cpp:47-50),
+ * LightPathtracer (lightpathtracer.cpp:45-48, without the show-light-cache pass) and
+ * BidirectionalPathtracer (bidirectionalpathtracer.cpp:190-200; with params->warmup the
+ * warm-up pass of :90-93).  Adds one sample pass into the accumulator.  Asynchronous. */
+GI_API int gi_render_iteration(GiContext* ctx, const GiIterationParams* params);
+
+/* Replaces RendererSystem::DispatchShowLightCacheShader (renderersystem.cpp:277-281):
+ * splats the directly visible initial light samples (showlightcaches.comp). */
+GI_API int gi_show_light_caches(GiContext* ctx);
+
+/* Replaces TraceRay / TraceRayAnyHit (traceray.glsl:19-180) for a host ray batch:
+ * copies rays in, traces, copies hits out (synchronous). */
+GI_API int gi_trace(GiContext* ctx, const GiRay* rays, uint32_t n, GiHit* hits);
+
+/* Same, on device-resident buffers (asynchronous on the context stream). */
+GI_API int gi_trace_device(GiContext* ctx, const GiRay* d_rays, uint32_t n, GiHit* d_hits);
+
+/* Replaces glFinish (renderersystem.cpp:249,253). */
+GI_API int gi_synchronize(GiContext* ctx);
+
+/* ------------------------------------------------------------------ read-out */
+
+/* Replaces glGetTextureImage(RGBA32F) in Application::SaveImage (application.cpp:411):
+ * copies the width*height*4 float SUM accumulator to host (synchronous).  Division by
+ * the iteration count stays with the caller (hdrimage.cpp:21, displayHDR.frag:12). */
+GI_API int gi_read_accumulator(GiContext* ctx, float* rgba);
+
+/* Device address of the accumulator (for the NCCL sum-reduce across ranks). */
+GI_API int gi_accumulator_device(GiContext* ctx, void** device_ptr, size_t* num_bytes);
+
+/* Replaces TextureMSE::ComputeCurrentMSE (texturemse.cpp:39-66, sqerror.frag:16-17):
+ * mean over pixels of sum_rgb (acc/divisor - ref)^2, ref = width*height*3 floats. */
+GI_API int gi_compute_mse(GiContext* ctx, const float* reference_rgb, uint32_t divisor, float* mse);
+
+/* Work counters (see GiCounters). */
+GI_API int gi_get_counters(GiContext* ctx, GiCounters* out);
+GI_API int gi_reset_counters(GiContext* ctx);
+
+/* Number of CUDA kernel launches issued by this context since creation. */
+GI_API uint64_t gi_kernel_launches(const GiContext* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPUGI_B200_H */

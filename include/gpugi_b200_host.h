@@ -1,0 +1,86 @@
+/*
+ * gpugi_b200_host.h -- flat C view of the C++ host layer (gpugi_b200/host/): the classes that keep
+ * the reference's API surface (Scene, Camera, LightSampler, RendererSystem, Pathtracer,
+ * LightPathtracer, BidirectionalPathtracer, PFM I/O).  C++ embedders include the .hpp files
+ * directly; this header exists so that Python (ctypes) can drive the very same objects.
+ * The device hot path is behind include/gpugi_b200.h; nothing here computes light transport.
+ */
+#ifndef GPUGI_B200_HOST_H
+#define GPUGI_B200_HOST_H
+
+#include "gpugi_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct GihScene GihScene;                   /* std::shared_ptr<Scene>           */
+typedef struct GihRendererSystem GihRendererSystem; /* RendererSystem + active renderer */
+typedef struct GihLightSampler GihLightSampler;
+
+typedef struct GihSceneInfo {
+	uint32_t num_triangles, num_vertices, num_nodes, num_leaf_triangles, num_materials, num_tree_levels;
+	uint32_t num_light_triangles, num_point_lights;
+	const uint32_t* triangles;          /* chunk triangle list, 3 indices each (not the leaf list)  */
+	const uint32_t* triangle_materials;
+	const uint32_t* parents;            /* HIERARCHY_PARENTS                                         */
+	float bbox_min[3], bbox_max[3];
+	float light_area_sum, total_area_light_flux, total_point_light_flux;
+} GihSceneInfo;
+
+GI_API const char* gih_last_error(void);
+GI_API uint32_t gih_wanghash(uint32_t x);                         /* utilities/random.cpp:5-13     */
+GI_API void gih_set_path_length(int n);                           /* GlobalConfig "pathLength"      */
+
+/* Scene::Scene(file, bvhType), scene.cpp:15-59.  NULL on failure (gih_last_error).                */
+GI_API GihScene* gih_scene_load(const char* json_path, int bvh_type);
+/* Synthetic scenes: mesh + environment JSON text -> hierarchy build (0 SAH, 1 kd) -> Scene.       */
+GI_API GihScene* gih_scene_from_mesh(const float* positions, const float* normals, const float* texcoords, uint32_t num_vertices,
+                                     const uint32_t* triangles, const uint32_t* tri_materials, uint32_t num_triangles, const char* env_json,
+                                     const char* texture_dir, int build_method);
+GI_API void gih_scene_destroy(GihScene* s);
+/* BinaryModel::storeEnvironmentFile/storeBinaryHeader/storeChunk: writes <json_path> and <dir>/<bim_name>. */
+GI_API int gih_scene_store(GihScene* s, const char* json_path, const char* bim_name);
+GI_API void gih_scene_desc(GihScene* s, GiSceneDesc* out);
+GI_API void gih_scene_info(GihScene* s, GihSceneInfo* out);
+GI_API void gih_scene_add_point_light(GihScene* s, const float pos[3], const float intensity[3]); /* application.cpp:158-163 */
+GI_API void gih_scene_emissivity(GihScene* s, float* out_rgb /* num_materials*3 */);
+GI_API void gih_scene_point_lights(GihScene* s, float* out_pos_intensity /* num_point_lights*6 */);
+
+/* LightSampler (lightsampler.cpp) and Camera::ComputeCameraParams (camera.cpp:76-85) on their own. */
+GI_API GihLightSampler* gih_light_sampler_create(GihScene* s);
+GI_API void gih_light_sampler_destroy(GihLightSampler* ls);
+GI_API void gih_light_sampler_seed(GihLightSampler* ls, uint64_t seed);
+GI_API void gih_light_sampler_generate(GihLightSampler* ls, GiLightSample* dst, uint32_t n, float position_bias);
+GI_API void gih_camera_params(const float pos[3], const float lookat[3], const float up[3], float yfov_deg, float aspect, int w, int h, GiCamera* out);
+
+/* RendererSystem (renderersystem.hpp:27-144) */
+GI_API GihRendererSystem* gih_rs_create(int device);
+GI_API void gih_rs_destroy(GihRendererSystem* rs);
+GI_API GiContext* gih_rs_device(GihRendererSystem* rs);
+GI_API void gih_rs_set_scene(GihRendererSystem* rs, GihScene* s);
+GI_API void gih_rs_set_screen_size(GihRendererSystem* rs, int w, int h);     /* "resolution" command */
+GI_API void gih_rs_set_camera(GihRendererSystem* rs, const float pos[3], const float lookat[3], float yfov_deg);
+GI_API int gih_rs_set_renderer(GihRendererSystem* rs, int renderer);         /* "renderer" command: 0 PT, 1 LPT, 2 BPT */
+GI_API const char* gih_rs_renderer_name(GihRendererSystem* rs);
+GI_API void gih_rs_set_shard(GihRendererSystem* rs, unsigned rank, unsigned world);
+GI_API void gih_rs_set_synchronous(GihRendererSystem* rs, int sync);
+GI_API void gih_rs_draw(GihRendererSystem* rs);
+GI_API uint64_t gih_rs_iteration_count(GihRendererSystem* rs);
+GI_API uint64_t gih_rs_render_time_ms(GihRendererSystem* rs);
+GI_API uint32_t gih_rs_frame_seed(GihRendererSystem* rs);
+GI_API uint64_t gih_rs_global_iteration(GihRendererSystem* rs);
+GI_API int gih_rs_read_backbuffer(GihRendererSystem* rs, float* rgba);
+GI_API uint32_t gih_rs_num_light_samples(GihRendererSystem* rs);
+GI_API void gih_rs_light_samples(GihRendererSystem* rs, GiLightSample* out);
+GI_API void gih_rs_camera(GihRendererSystem* rs, GiCamera* out);
+GI_API void gih_rs_renderer_info(GihRendererSystem* rs, int32_t* num_rays_per_light_sample, uint32_t* light_cache_capacity, int32_t* avg_light_path_length);
+
+/* WritePfm / LoadPfm (imageut/hdrimage.cpp:6-60) */
+GI_API int gih_write_pfm(const char* path, const float* rgba, int w, int h, uint32_t divisor);
+GI_API int gih_load_pfm(const char* path, float* rgb, int capacity_pixels, int* w, int* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

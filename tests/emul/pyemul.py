@@ -1,0 +1,76 @@
+"""ctypes view of tests/emul/libgi_emul.so (host build of the device logic) -- tests only."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgi_emul.so")
+
+
+def build():
+    subprocess.check_call(["make", "-C", _HERE, "-s"])
+
+
+build()
+lib = C.CDLL(LIB_PATH)
+vp, u32 = C.c_void_p, C.c_uint32
+
+RAY_DTYPE = np.dtype([("origin", "<f4", 3), ("t_max", "<f4"), ("direction", "<f4", 3), ("flags", "<u4")])
+HIT_DTYPE = np.dtype([("t", "<f4"), ("leaf_tri", "<i4"), ("bary_y", "<f4"), ("bary_z", "<f4")])
+LIGHT_SAMPLE_DTYPE = np.dtype([("position", "<f4", 3), ("normal_phi", "<f4"), ("intensity", "<f4", 3), ("normal_theta_cos", "<f4")])
+
+
+class EmCounters(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ["closest_rays", "any_rays", "camera_paths", "light_paths", "shaded_vertices", "splats", "fallback_rays",
+                                          "node_tests", "tri_tests"]] + [("light_cache_entries", u32), ("light_path_length_sum", u32)]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+class IterationParams(C.Structure):
+    _fields_ = [("renderer", C.c_int32), ("frame_seed", u32), ("max_path_length", C.c_int32), ("num_rays_per_light_sample", C.c_int32),
+                ("light_cache_capacity", C.c_int32), ("warmup", C.c_int32), ("reserved", C.c_int32 * 2)]
+
+
+lib.em_trace.restype = C.c_int
+lib.em_trace.argtypes = [vp, vp, u32, vp, C.c_int, C.POINTER(C.c_int), vp]
+lib.em_render.restype = C.c_int
+lib.em_render.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, vp, vp]
+
+
+def _p(a):
+    return a.ctypes.data_as(vp)
+
+
+def trace(scene_desc, rays, mode=0):
+    rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+    hits = np.zeros(rays.shape[0], dtype=HIT_DTYPE)
+    cnt = EmCounters()
+    fast = C.c_int()
+    st = lib.em_trace(C.addressof(scene_desc), _p(rays), rays.shape[0], _p(hits), mode, C.byref(fast), C.addressof(cnt))
+    if st != 0:
+        raise RuntimeError("em_trace rejected the scene")
+    d = cnt.as_dict()
+    d["fast_valid"] = fast.value
+    return hits, d
+
+
+def render(scene_desc, cam, w, h, light_samples, renderer, frame_seed, max_len=16, num_rays_per_light_sample=0, capacity=0, warmup=False, mode=0,
+           env_rgb=None, show_light_caches=False, accum=None):
+    ls = np.ascontiguousarray(light_samples, dtype=LIGHT_SAMPLE_DTYPE)
+    if accum is None:
+        accum = np.zeros((h, w, 4), dtype=np.float32)
+    p = IterationParams(renderer=renderer, frame_seed=frame_seed & 0xFFFFFFFF, max_path_length=max_len, num_rays_per_light_sample=num_rays_per_light_sample,
+                        light_cache_capacity=capacity, warmup=1 if warmup else 0)
+    cache = np.zeros(max(int(capacity), 1) * 16, dtype=np.float32)
+    cnt = EmCounters()
+    env = np.ascontiguousarray(env_rgb, dtype=np.float32) if env_rgb is not None else None
+    camp = _p(cam) if isinstance(cam, np.ndarray) else C.addressof(cam)
+    st = lib.em_render(C.addressof(scene_desc), camp, w, h, _p(ls), ls.shape[0], C.addressof(p), mode, _p(env) if env is not None else None,
+                       1 if show_light_caches else 0, _p(cache), _p(accum), C.addressof(cnt))
+    if st != 0:
+        raise RuntimeError("em_render failed: %d" % st)
+    return accum, cnt.as_dict()
