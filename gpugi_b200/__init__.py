@@ -218,6 +218,10 @@ class Device:
         samples = np.ascontiguousarray(samples, dtype=LIGHT_SAMPLE_DTYPE)
         self._check(capi.dev.gi_set_light_samples(self._c, C.cast(_vp(samples), C.POINTER(capi.GiLightSample)), samples.shape[0]), "gi_set_light_samples")
 
+    def set_light_samples_device(self, d_ptr, n):
+        """gi_set_light_samples_device: samples already resident in device memory (no copy)."""
+        self._check(capi.dev.gi_set_light_samples_device(self._c, C.c_void_p(d_ptr), int(n)), "gi_set_light_samples_device")
+
     def set_environment_constant(self, srgb8):
         """1x1 cube with the same sRGB8 colour on all faces (the reference default is black)."""
         face = np.array([srgb8[0], srgb8[1], srgb8[2], 255], dtype=np.uint8)

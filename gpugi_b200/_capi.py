@@ -121,6 +121,7 @@ DEVICE_API = {
     "gi_set_camera": (C.c_int, [vp, P(GiCamera)]),
     "gi_set_screen_size": (C.c_int, [vp, C.c_int, C.c_int]),
     "gi_set_light_samples": (C.c_int, [vp, P(GiLightSample), u32]),
+    "gi_set_light_samples_device": (C.c_int, [vp, vp, u32]),
     "gi_clear_accumulator": (C.c_int, [vp]),
     "gi_alloc_light_cache": (C.c_int, [vp, u32]),
     "gi_render_iteration": (C.c_int, [vp, P(GiIterationParams)]),

@@ -174,6 +174,7 @@ struct GiContext
 	int width = 0, height = 0;
 	float* accum = nullptr;
 	F4* lightSamples = nullptr;
+	const F4* externalLightSamples = nullptr; // gi_set_light_samples_device
 	uint32_t lightSampleCapacity = 0;
 	int numLightSamples = 0;
 
@@ -240,7 +241,7 @@ static DFrame makeFrame(GiContext* c, const GiIterationParams* p)
 	f.scene.textureFilterExact = c->textureFilterExact;
 	f.cam = c->cam;
 	f.width = c->width; f.height = c->height;
-	f.lightSamples = c->lightSamples;
+	f.lightSamples = c->externalLightSamples ? c->externalLightSamples : c->lightSamples;
 	f.numLightSamples = c->numLightSamples;
 	f.frameSeed = p ? p->frame_seed : 0u;
 	f.maxPathLength = p ? p->max_path_length : 16;
@@ -489,6 +490,15 @@ int gi_set_light_samples(GiContext* c, const GiLightSample* samples, uint32_t n)
 	// pageable source: the runtime stages the bytes before returning, so the caller may reuse `samples`;
 	// stream order keeps the previous iteration's reads ahead of this write.
 	GI_CUDA(c, cudaMemcpyAsync(c->lightSamples, samples, size_t(n) * sizeof(GiLightSample), cudaMemcpyHostToDevice, c->stream));
+	c->externalLightSamples = nullptr;
+	c->numLightSamples = int(n);
+	return GI_OK;
+}
+
+int gi_set_light_samples_device(GiContext* c, const GiLightSample* d_samples, uint32_t n)
+{
+	if (!c || !d_samples || n == 0) return fail(c, GI_ERR_INVALID, "gi_set_light_samples_device: no samples");
+	c->externalLightSamples = reinterpret_cast<const F4*>(d_samples);
 	c->numLightSamples = int(n);
 	return GI_OK;
 }

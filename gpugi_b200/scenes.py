@@ -244,8 +244,12 @@ SPONZA_POINT_LIGHTS = [((-382.0, 160.0, -180.0), (50000.0, 50000.0, 50000.0)), (
                        ((487.4, 160.0, -180.0), (50000.0, 50000.0, 50000.0)), ((487.4, 160.0, 150.0), (50000.0, 50000.0, 50000.0))]   # :8-11
 
 
-def make_sponza_like(texture_dir, target_triangles=262144, texture_size=1024, num_materials=25, seed=7, build_method="sah"):
-    """Two-storey colonnaded atrium, extent ~3700 x 1500 x 2300, `num_materials` textured materials."""
+def make_sponza_like(texture_dir, target_triangles=262144, texture_size=1024, num_materials=25, seed=7, build_method="sah", detail=1.0):
+    """Two-storey colonnaded atrium, extent ~3700 x 1500 x 2300, `num_materials` textured materials.
+    detail < 1 coarsens every tessellation (small test scenes); target_triangles=None skips the fill-up."""
+
+    def T(n):
+        return max(1, int(round(n * detail)))
     rng = np.random.RandomState(seed)
     tex = write_textures(texture_dir, num_materials, texture_size, seed)
     materials = {}
@@ -260,34 +264,34 @@ def make_sponza_like(texture_dir, target_triangles=262144, texture_size=1024, nu
         return i % num_materials
 
     # shell: floor, roof, four walls (finely tessellated so the BVH has work everywhere)
-    mb.grid([-X, 0, -Z], [0, 0, 2 * Z], [2 * X, 0, 0], 48, 64, m(0), (12, 20))                 # floor, normal +y
-    mb.grid([-X, Y, -Z], [2 * X, 0, 0], [0, 0, 2 * Z], 32, 24, m(1), (10, 6))                  # roof, normal -y
-    mb.grid([-X, 0, -Z], [2 * X, 0, 0], [0, Y, 0], 64, 24, m(2), (16, 6))                      # z = -Z, normal +z
-    mb.grid([-X, 0, Z], [0, Y, 0], [2 * X, 0, 0], 24, 64, m(3), (6, 16))                       # z = +Z, normal -z
-    mb.grid([-X, 0, -Z], [0, Y, 0], [0, 0, 2 * Z], 24, 40, m(4), (6, 10))                      # x = -X, normal +x
-    mb.grid([X, 0, -Z], [0, 0, 2 * Z], [0, Y, 0], 40, 24, m(5), (10, 6))                       # x = +X, normal -x
+    mb.grid([-X, 0, -Z], [0, 0, 2 * Z], [2 * X, 0, 0], T(48), T(64), m(0), (12, 20))                 # floor, normal +y
+    mb.grid([-X, Y, -Z], [2 * X, 0, 0], [0, 0, 2 * Z], T(32), T(24), m(1), (10, 6))                  # roof, normal -y
+    mb.grid([-X, 0, -Z], [2 * X, 0, 0], [0, Y, 0], T(64), T(24), m(2), (16, 6))                      # z = -Z, normal +z
+    mb.grid([-X, 0, Z], [0, Y, 0], [2 * X, 0, 0], T(24), T(64), m(3), (6, 16))                       # z = +Z, normal -z
+    mb.grid([-X, 0, -Z], [0, Y, 0], [0, 0, 2 * Z], T(24), T(40), m(4), (6, 10))                      # x = -X, normal +x
+    mb.grid([X, 0, -Z], [0, 0, 2 * Z], [0, Y, 0], T(40), T(24), m(5), (10, 6))                       # x = +X, normal -x
     # galleries: slabs along both long sides on the upper floor, with a parapet
     for side in (-1.0, 1.0):
         z0, z1 = (side * 420.0, side * Z) if side > 0 else (side * Z, side * 420.0)
-        mb.box([-X + 1, 480.0, z0], [X - 1, 520.0, z1], m(6), tess=12, uv_scale=(12, 3))
+        mb.box([-X + 1, 480.0, z0], [X - 1, 520.0, z1], m(6), tess=T(12), uv_scale=(12, 3))
         zp = side * 420.0
-        mb.box([-X + 1, 520.0, zp - 8], [X - 1, 600.0, zp + 8], m(7), tess=10, uv_scale=(20, 1))
+        mb.box([-X + 1, 520.0, zp - 8], [X - 1, 600.0, zp + 8], m(7), tess=T(10), uv_scale=(20, 1))
     # colonnades: two rows x two storeys of columns with capitals and bases
     col_x = np.linspace(-1600.0, 1600.0, 14)
     k = 0
     for side in (-1.0, 1.0):
         for x in col_x:
             for (y0, hgt, rad) in ((0.0, 480.0, 42.0), (520.0, 520.0, 34.0)):
-                mb.cylinder([x, y0 + 30, side * 420.0], rad, hgt - 60, m(8 + k % 3), segments=28, rings=10, uv_scale=(2, 4))
-                mb.box([x - rad * 1.4, y0, side * 420.0 - rad * 1.4], [x + rad * 1.4, y0 + 30, side * 420.0 + rad * 1.4], m(11), tess=2)
-                mb.box([x - rad * 1.4, y0 + hgt - 30, side * 420.0 - rad * 1.4], [x + rad * 1.4, y0 + hgt, side * 420.0 + rad * 1.4], m(11), tess=2)
+                mb.cylinder([x, y0 + 30, side * 420.0], rad, hgt - 60, m(8 + k % 3), segments=max(6, T(28)), rings=T(10), uv_scale=(2, 4))
+                mb.box([x - rad * 1.4, y0, side * 420.0 - rad * 1.4], [x + rad * 1.4, y0 + 30, side * 420.0 + rad * 1.4], m(11), tess=T(2))
+                mb.box([x - rad * 1.4, y0 + hgt - 30, side * 420.0 - rad * 1.4], [x + rad * 1.4, y0 + hgt, side * 420.0 + rad * 1.4], m(11), tess=T(2))
                 k += 1
     # arches between columns approximated by lintels
     for side in (-1.0, 1.0):
         for i in range(len(col_x) - 1):
             xa, xb = col_x[i] + 50, col_x[i + 1] - 50
-            mb.box([xa, 400.0, side * 420.0 - 25], [xb, 480.0, side * 420.0 + 25], m(12), tess=3, uv_scale=(3, 1))
-            mb.box([xa, 960.0, side * 420.0 - 20], [xb, 1040.0, side * 420.0 + 20], m(12), tess=3, uv_scale=(3, 1))
+            mb.box([xa, 400.0, side * 420.0 - 25], [xb, 480.0, side * 420.0 + 25], m(12), tess=T(3), uv_scale=(3, 1))
+            mb.box([xa, 960.0, side * 420.0 - 20], [xb, 1040.0, side * 420.0 + 20], m(12), tess=T(3), uv_scale=(3, 1))
     # hanging curtains: wavy, finely tessellated sheets between upper columns
     def wave(amp, freq, phase):
         def f(s, t, p, n):
@@ -303,17 +307,17 @@ def make_sponza_like(texture_dir, target_triangles=262144, texture_size=1024, nu
     for i in range(0, len(col_x) - 1, 2):
         for side in (-1.0, 1.0):
             xa, xb = col_x[i] + 40, col_x[i + 1] - 40
-            mb.grid([xa, 560.0, side * 400.0], [xb - xa, 0, 0], [0, 380.0, 0], 40, 28, m(13 + (i // 2) % 4), (2, 2), displace=wave(14.0, 3.0, 0.7 * i), flip=side < 0)
+            mb.grid([xa, 560.0, side * 400.0], [xb - xa, 0, 0], [0, 380.0, 0], T(40), T(28), m(13 + (i // 2) % 4), (2, 2), displace=wave(14.0, 3.0, 0.7 * i), flip=side < 0)
     # props on the floor: vases (squashed spheres) and plinths
     for i in range(24):
         x = rng.uniform(-1500, 1500); z = rng.uniform(-330, 330)
-        mb.box([x - 40, 0, z - 40], [x + 40, 60, z + 40], m(17), tess=2, skip_faces=(2,))
-        mb.sphere([x, 60 + 55, z], 55.0, m(18 + i % 4), segments=28, rings=16, squash=(1.0, 1.3, 1.0))
+        mb.box([x - 40, 0, z - 40], [x + 40, 60, z + 40], m(17), tess=T(2), skip_faces=(2,))
+        mb.sphere([x, 60 + 55, z], 55.0, m(18 + i % 4), segments=max(6, T(28)), rings=max(3, T(16)), squash=(1.0, 1.3, 1.0))
     # a central fountain basin
-    mb.cylinder([0, 0, 0], 260.0, 70.0, m(22), segments=64, rings=4, uv_scale=(8, 1))
-    mb.sphere([0, 150, 0], 90.0, m(23), segments=40, rings=24)
+    mb.cylinder([0, 0, 0], 260.0, 70.0, m(22), segments=max(8, T(64)), rings=T(4), uv_scale=(8, 1))
+    mb.sphere([0, 150, 0], 90.0, m(23), segments=max(8, T(40)), rings=max(4, T(24)))
     # fill up to the exact triangle target with a relief frieze along the end walls
-    remaining = target_triangles - mb.num_triangles()
+    remaining = 0 if target_triangles is None else target_triangles - mb.num_triangles()
     if remaining < 0:
         raise ValueError("sponza-like base geometry already has %d triangles" % mb.num_triangles())
     def relief(s, t, p, n):
@@ -329,7 +333,7 @@ def make_sponza_like(texture_dir, target_triangles=262144, texture_size=1024, nu
         rest = quads - rows * cols
         if rest > 0:
             mb.grid([X - 2, 600.0, -Z + 4], [0, 0, 2 * Z - 8], [0, 500.0, 0], rest, 1, m(24), (12, 2))
-    if (target_triangles - mb.num_triangles()) == 1:  # odd target: one more small triangle
+    if target_triangles is not None and (target_triangles - mb.num_triangles()) == 1:  # odd target: one more small triangle
         mb.add([[0, 1400, 0], [10, 1400, 0], [0, 1400, 10]], [[0, -1, 0]] * 3, [[0, 0], [1, 0], [0, 1]], [[0, 1, 2]], m(24))
     pos, nrm, uv, tri, mat = mb.arrays()
     scene = Scene.from_mesh(pos, nrm, uv, tri, mat, materials, texture_dir, build_method)

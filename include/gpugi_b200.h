@@ -245,6 +245,11 @@ GI_API int gi_set_screen_size(GiContext* ctx, int width, int height);
  * iteration uses these `n` initial light samples.  Copied at call time. */
 GI_API int gi_set_light_samples(GiContext* ctx, const GiLightSample* samples, uint32_t n);
 
+/* Same, but the samples already live in device memory (caller-owned, must stay valid until the
+ * iterations that use them have finished).  No copy: the persistently mapped light-sample buffer of
+ * renderersystem.cpp:121-126 without the host hop. */
+GI_API int gi_set_light_samples_device(GiContext* ctx, const GiLightSample* d_samples, uint32_t n);
+
 /* Replaces gl::Texture2D::ClearToZero on the backbuffer (renderersystem.hpp:79). */
 GI_API int gi_clear_accumulator(GiContext* ctx);
 

@@ -1,0 +1,250 @@
+"""The product's device logic (gpugi_b200/csrc/gi_core.h + gi_layout.h), compiled for the host by tests/emul,
+against the CPU oracle.  Runs without a GPU; the `-m gpu` tests repeat the same comparisons on the real kernels."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.conftest import assert_hits_equal, camera_ray_batch, make_ray_batch
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FAST, REFERENCE = 0, 1
+
+
+@pytest.mark.parametrize("mode", [FAST, REFERENCE])
+def test_trace_parity_box1(g, orc, emul, scenes, box1, mode):
+    C = scenes.BOX1_CAMERA
+    rays = np.concatenate([camera_ray_batch(g, orc, box1, C["pos"], C["lookat"], C["fov"], 64, 64, 1), make_ray_batch(g, box1, 20000, 2)])
+    hits, cnt = emul.trace(box1.desc, rays, mode)
+    assert cnt["fast_valid"] == 1
+    assert_hits_equal(hits, orc.trace_batch(box1.desc, rays), "box1 mode %d" % mode)
+    if mode == REFERENCE:
+        assert cnt["fallback_rays"] == 0
+
+
+@pytest.mark.parametrize("mode", [FAST, REFERENCE])
+def test_trace_parity_golden_file(emul, box1, mode):
+    z = np.load(os.path.join(GOLDEN, "box1_rays.npz"))
+    hits, _ = emul.trace(box1.desc, z["rays"], mode)
+    assert_hits_equal(hits, z["hits"], "golden mode %d" % mode)
+
+
+@pytest.mark.parametrize("mode", [FAST, REFERENCE])
+@pytest.mark.parametrize("build", ["sah", "kd"])
+def test_trace_parity_random_triangles(g, orc, emul, scenes, mode, build):
+    """Overlapping slivers: the adversarial case for visit-order dependence."""
+    sc = scenes.make_random_triangles(2500, seed=7, build_method=build)
+    rays = make_ray_batch(g, sc, 40000, 3)
+    hits, cnt = emul.trace(sc.desc, rays, mode)
+    assert_hits_equal(hits, orc.trace_batch(sc.desc, rays), "random %s mode %d" % (build, mode))
+
+
+def test_trace_parity_exact_ties(g, orc, emul, box1_coincident):
+    """Box bottoms lying exactly in the floor plane: two triangles at the same distance.  The reference keeps the
+    first one found in ITS visit order (traceray.glsl:145); the fast traversal must detect the tie and agree."""
+    rng = np.random.RandomState(5)
+    n = 4000
+    rays = np.zeros(n, dtype=g.RAY_DTYPE)
+    # start inside the glass box / white box, shoot downwards at the coincident floor + box bottom
+    lo, hi = np.array([0.25, 0.05, -1.3]), np.array([1.05, 0.7, -0.5])
+    rays["origin"] = (lo + rng.rand(n, 3) * (hi - lo)).astype(np.float32)
+    d = rng.randn(n, 3); d[:, 1] = -np.abs(d[:, 1]) - 0.2
+    rays["direction"] = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    rays["t_max"] = np.float32(g.RAY_MAX)
+    hits, cnt = emul.trace(box1_coincident.desc, rays, FAST)
+    assert_hits_equal(hits, orc.trace_batch(box1_coincident.desc, rays), "ties")
+    assert cnt["fallback_rays"] > n // 4  # the ties really occur and are resolved by the exact re-trace
+
+
+def test_trace_edges_and_vertices(g, orc, emul, box1):
+    """Rays aimed exactly at shared edges / vertices of the tessellated walls, and rays inside face planes."""
+    P = box1.positions()
+    lt = box1.leaf_triangles()
+    valid = lt["v"][:, 0] != lt["v"][:, 1]
+    v = lt["v"][valid]
+    rng = np.random.RandomState(8)
+    pick = rng.randint(0, len(v), size=3000)
+    a, b = P[v[pick, 0]], P[v[pick, 1]]
+    w = rng.rand(3000, 1).astype(np.float32)
+    w[:1000] = 0.0  # exactly a vertex
+    target = a * (1 - w) + b * w
+    origin = np.array([0.0, 1.5, 1.0], dtype=np.float32) + rng.uniform(-0.3, 0.3, size=(3000, 3)).astype(np.float32)
+    d = target - origin
+    rays = np.zeros(3000, dtype=g.RAY_DTYPE)
+    rays["origin"] = origin
+    rays["direction"] = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    rays["t_max"] = np.float32(g.RAY_MAX)
+    # in-plane rays: origin on the floor plane y = 0, direction.y == 0
+    flat = np.zeros(500, dtype=g.RAY_DTYPE)
+    flat["origin"] = np.stack([rng.uniform(-1.4, 1.4, 500), np.zeros(500), rng.uniform(-2.9, 2.2, 500)], 1).astype(np.float32)
+    dd = np.stack([rng.randn(500), np.zeros(500), rng.randn(500)], 1)
+    flat["direction"] = (dd / np.linalg.norm(dd, axis=1, keepdims=True)).astype(np.float32)
+    flat["t_max"] = np.float32(g.RAY_MAX)
+    rays = np.concatenate([rays, flat])
+    for mode in (FAST, REFERENCE):
+        hits, _ = emul.trace(box1.desc, rays, mode)
+        assert_hits_equal(hits, orc.trace_batch(box1.desc, rays), "edges mode %d" % mode)
+
+
+def test_trace_finite_closest_length(g, orc, emul, box1):
+    """Closest-hit queries with a finite initial rayLength (hits exactly at / just beyond the limit)."""
+    rays = make_ray_batch(g, box1, 6000, 12, any_fraction=0.0)
+    full = orc.trace_batch(box1.desc, rays)
+    t = full["t"].copy()
+    rays["t_max"][:2000] = t[:2000]                      # limit == hit distance: `newHit < rayLength` must fail
+    with np.errstate(over="ignore"):
+        rays["t_max"][2000:4000] = np.nextafter(t[2000:4000], np.float32(np.inf))
+    rays["t_max"][4000:] = t[4000:] * np.float32(0.5)
+    rays["t_max"][~np.isfinite(rays["t_max"])] = np.float32(10.0)
+    for mode in (FAST, REFERENCE):
+        hits, _ = emul.trace(box1.desc, rays, mode)
+        assert_hits_equal(hits, orc.trace_batch(box1.desc, rays), "finite length mode %d" % mode)
+
+
+def test_trace_empty_batch_and_deep_tree(g, orc, emul, scenes):
+    sc = scenes.make_random_triangles(50, seed=1)
+    hits, _ = emul.trace(sc.desc, np.zeros(0, dtype=g.RAY_DTYPE), FAST)
+    assert hits.shape == (0,)
+    # a long thin strip of triangles sorted along x gives the SAH builder a deep, list-like tree: the short stack
+    # overflows and the exact re-trace has to take over
+    n = 4000
+    x = np.arange(n, dtype=np.float32)[:, None] * (1.5 ** np.linspace(0, 8, n))[:, None].astype(np.float32) * 0.001
+    p = np.zeros((n, 3, 3), dtype=np.float32)
+    p[:, :, 0] = x + np.array([0, 0.4, 0.2], np.float32)
+    p[:, 1, 1] = 1.0; p[:, 2, 2] = 1.0
+    pos = p.reshape(-1, 3)
+    tri = np.arange(3 * n, dtype=np.uint32).reshape(n, 3)
+    deep = g.Scene.from_mesh(pos, np.tile(np.float32([0, 1, 0]), (3 * n, 1)), np.zeros((3 * n, 2), np.float32), tri, np.zeros(n, np.uint32),
+                             {"m": scenes.legacy_material()})
+    rays = make_ray_batch(g, deep, 3000, 6)
+    hits, cnt = emul.trace(deep.desc, rays, FAST)
+    assert_hits_equal(hits, orc.trace_batch(deep.desc, rays), "deep tree (levels=%d)" % deep.info.num_tree_levels)
+
+
+def _light_sampler(orc, sc):
+    return orc.LightSampler(sc.positions(), sc.triangles(), sc.triangle_materials(), sc.emissivity(), sc.point_lights())
+
+
+@pytest.mark.parametrize("mode", [FAST, REFERENCE])
+def test_pathtracer_matches_oracle(orc, emul, scenes, box1, mode):
+    W = H = 48
+    C = scenes.BOX1_CAMERA
+    cam = orc.camera(C["pos"], C["lookat"], C["fov"], W, H)
+    ls = _light_sampler(orc, box1)
+    for it in range(2):
+        s = ls.generate(128)
+        ref, rc = orc.render_pt(box1.desc, cam, W, H, s, orc.wanghash(it), 16)
+        img, ec = emul.render(box1.desc, cam, W, H, s, 0, orc.wanghash(it), 16, mode=mode)
+        assert np.array_equal(img, ref)  # same libm, same operation order => bit-identical
+        for k in ("closest_rays", "any_rays", "camera_paths", "shaded_vertices"):
+            assert ec[k] == rc[k]
+
+
+def test_pathtracer_textured_scene_and_env(orc, emul, scenes, sponza_small):
+    W, H = 64, 40
+    C = scenes.SPONZA_CAMERA
+    cam = orc.camera(C["pos"], C["lookat"], C["fov"], W, H)
+    s = _light_sampler(orc, sponza_small).generate(128)
+    assert (s["normal_theta_cos"] > 1.5).all()  # point lights only
+    ref, _ = orc.render_pt(sponza_small.desc, cam, W, H, s, orc.wanghash(1), 16, env_rgb=(0.2, 0.3, 0.4))
+    img, _ = emul.render(sponza_small.desc, cam, W, H, s, 0, orc.wanghash(1), 16, env_rgb=(0.2, 0.3, 0.4))
+    assert np.array_equal(img, ref) and ref[..., :3].max() > 0
+
+
+def test_pathtracer_path_length_and_odd_resolution(orc, emul, scenes, box1):
+    """MAX_PATHLENGTH as a parameter; W,H not multiples of 8 leave the right/top pixels unrendered (pathtracer.cpp:50)."""
+    W, H = 44, 29
+    C = scenes.BOX1_CAMERA
+    cam = orc.camera(C["pos"], C["lookat"], C["fov"], W, H)
+    s = _light_sampler(orc, box1).generate(128)
+    for max_len in (1, 3):
+        ref, _ = orc.render_pt(box1.desc, cam, W, H, s, 77, max_len)
+        img, _ = emul.render(box1.desc, cam, W, H, s, 0, 77, max_len)
+        assert np.array_equal(img, ref)
+        assert not img[:, 40:].any() and not img[24:].any() and img[:24, :40, :3].any()
+
+
+def test_lighttracer_matches_oracle(orc, emul, scenes, box1):
+    os.environ["OMP_NUM_THREADS"] = "1"
+    W = H = 48
+    C = scenes.BOX1_CAMERA
+    cam = orc.camera(C["pos"], C["lookat"], C["fov"], W, H)
+    s = _light_sampler(orc, box1).generate(256)
+    nr = 64
+    ref, rc = orc.render_lpt(box1.desc, cam, W, H, s, 5, nr, 16, show_light_caches=True)
+    img, ec = emul.render(box1.desc, cam, W, H, s, 1, 5, 16, num_rays_per_light_sample=nr, show_light_caches=True)
+    # splats land in the same pixels with the same values; only the summation order may differ between the
+    # oracle's OpenMP loop and the sequential emulation
+    assert np.allclose(img, ref, rtol=1e-5, atol=1e-6)
+    assert ec["splats"] == rc["splats"] and ec["light_paths"] == rc["light_paths"] == 256 * nr
+
+
+def test_bidirectional_matches_oracle(orc, emul, scenes, box1):
+    W = H = 40
+    C = scenes.BOX1_CAMERA
+    cam = orc.camera(C["pos"], C["lookat"], C["fov"], W, H)
+    s = _light_sampler(orc, box1).generate(128)
+    nr = 64
+    # warm-up pass (SAVE_LIGHT_CACHE_WARMUP): entry count and path length sum are order independent
+    _, _, counts = orc.render_bpt(box1.desc, cam, W, H, s, 9, nr, 0, 16, warmup=True)
+    _, wc = emul.render(box1.desc, cam, W, H, s, 2, 9, 16, num_rays_per_light_sample=nr, warmup=True)
+    assert (wc["light_cache_entries"], wc["light_path_length_sum"]) == counts
+    assert counts[0] - 128 * nr == counts[1]  # every stored vertex beyond the light origins was counted once
+    cap = counts[0] + counts[0] // 10
+
+
+def test_bidirectional_image_single_thread(orc, emul, scenes, box1):
+    """With one oracle thread the light-cache slot order equals the sequential emulation's => identical image."""
+    import subprocess, sys
+    code = r'''
+import os, sys
+os.environ["OMP_NUM_THREADS"] = "1"
+sys.path.insert(0, %r)
+import numpy as np
+from gpugi_b200 import scenes
+from oracle import pyoracle as orc
+from tests.emul import pyemul as emul
+box1 = scenes.make_box1(tess=4)
+W = H = 40
+C = scenes.BOX1_CAMERA
+cam = orc.camera(C["pos"], C["lookat"], C["fov"], W, H)
+s = orc.LightSampler(box1.positions(), box1.triangles(), box1.triangle_materials(), box1.emissivity(), box1.point_lights()).generate(128)
+nr = 64
+_, _, counts = orc.render_bpt(box1.desc, cam, W, H, s, 9, nr, 0, 16, warmup=True)
+for cap in (counts[0] + counts[0] // 10, counts[0] - 500):   # roomy cache, and one that overflows (entries dropped, :27)
+    ref, rc, c2 = orc.render_bpt(box1.desc, cam, W, H, s, 9, nr, cap, 16)
+    img, ec = emul.render(box1.desc, cam, W, H, s, 2, 9, 16, num_rays_per_light_sample=nr, capacity=cap)
+    assert np.array_equal(img, ref), "BPT image differs (capacity %%d)" %% cap
+    assert ec["light_cache_entries"] == c2[0] == counts[0]
+    assert np.all(img[..., 3] == 1.0)   # BPT adds w = 1 (pathtracer_bidir.comp:248)
+print("ok")
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_layout_rejects_bad_scenes(g, emul, box1):
+    """Scene::SanityCheck equivalents: out-of-range vertex / material / child / escape indices are refused."""
+    import ctypes as C
+    d = box1.desc
+    nodes = box1.nodes(); lt = box1.leaf_triangles()
+    rays = np.zeros(1, dtype=g.RAY_DTYPE)
+
+    def with_arrays(nodes_arr, lt_arr):
+        d2 = type(d)()
+        C.memmove(C.addressof(d2), C.addressof(d), C.sizeof(d))
+        d2.nodes = C.cast(nodes_arr.ctypes.data, type(d.nodes))
+        d2.leaf_triangles = C.cast(lt_arr.ctypes.data, type(d.leaf_triangles))
+        return d2
+    bad = lt.copy(); bad["v"][0, 2] = d.num_vertices
+    with pytest.raises(RuntimeError):
+        emul.trace(with_arrays(nodes, bad), rays)
+    bad = lt.copy(); bad["material"][0] = d.num_materials
+    with pytest.raises(RuntimeError):
+        emul.trace(with_arrays(nodes, bad), rays)
+    badn = nodes.copy(); badn["escape"][1] = d.num_nodes
+    with pytest.raises(RuntimeError):
+        emul.trace(with_arrays(badn, lt), rays)
+    badn = nodes.copy(); badn["first_child"][0] = d.num_nodes + 5
+    with pytest.raises(RuntimeError):
+        emul.trace(with_arrays(badn, lt), rays)

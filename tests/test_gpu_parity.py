@@ -1,0 +1,175 @@
+"""Parity tests proper: the CUDA kernels, called through the C ABI (gpugi_b200.Device == include/gpugi_b200.h) and
+through the Renderer API mirror (RendererSystem), against the CPU oracle on the same seeded inputs.
+
+Bar: bit-exact for hit flag / triangle id / distance / barycentrics; images: identical RNG streams and operation
+order, so a pixel only differs where CUDA's sinf/cosf/powf/atan2f (<= 2 ulp) or FMA contraction in the shading code
+flip a discrete decision -- tolerance: <= 2 % of the pixels off by more than 1 % at one iteration, and
+relMSE <= 0.02 against the oracle's image at 16 iterations (stated per test)."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.conftest import assert_hits_equal, camera_ray_batch, make_ray_batch, pixel_mismatch_fraction
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FAST, REFERENCE = 0, 1
+
+
+@pytest.fixture(scope="module")
+def dev(g):
+    d = g.Device(0)
+    yield d
+    d.close()
+
+
+def _trace(g, dev, scene, rays, mode):
+    dev.upload_scene(scene)
+    dev.set_option(g.GI_OPT_TRAVERSAL, mode)
+    dev.reset_counters()
+    hits = dev.trace(rays)
+    return hits, dev.counters()
+
+
+@pytest.mark.parametrize("mode", [FAST, REFERENCE])
+def test_trace_parity_box1(g, orc, dev, scenes, box1, mode):
+    C = scenes.BOX1_CAMERA
+    rays = np.concatenate([camera_ray_batch(g, orc, box1, C["pos"], C["lookat"], C["fov"], 128, 128, 1), make_ray_batch(g, box1, 200000, 2)])
+    hits, cnt = _trace(g, dev, box1, rays, mode)
+    assert_hits_equal(hits, orc.trace_batch(box1.desc, rays), "box1 mode %d" % mode)
+    assert cnt["closest_rays"] + cnt["any_rays"] == len(rays)
+    if mode == REFERENCE:
+        assert cnt["exact_fallback_rays"] == 0
+
+
+@pytest.mark.parametrize("mode", [FAST, REFERENCE])
+def test_trace_parity_golden_file(g, dev, box1, mode):
+    z = np.load(os.path.join(GOLDEN, "box1_rays.npz"))
+    hits, _ = _trace(g, dev, box1, z["rays"], mode)
+    assert_hits_equal(hits, z["hits"], "golden mode %d" % mode)
+
+
+@pytest.mark.parametrize("mode", [FAST, REFERENCE])
+@pytest.mark.parametrize("build", ["sah", "kd"])
+def test_trace_parity_random_triangles(g, orc, dev, scenes, mode, build):
+    sc = scenes.make_random_triangles(20000, seed=7, build_method=build)
+    rays = make_ray_batch(g, sc, 300000, 3)
+    hits, _ = _trace(g, dev, sc, rays, mode)
+    assert_hits_equal(hits, orc.trace_batch(sc.desc, rays), "random %s mode %d" % (build, mode))
+
+
+def test_trace_parity_sponza_mix(g, orc, dev, scenes, tmp_path):
+    """The SURVEY 8d mix (primary / secondary / shadow rays) on the Sponza-shaped scene, 2^20 rays."""
+    sc = scenes.make_sponza_like(str(tmp_path), texture_size=32)
+    C = scenes.SPONZA_CAMERA
+    rays = camera_ray_batch(g, orc, sc, C["pos"], C["lookat"], C["fov"], 640, 360, 4)
+    rays = np.concatenate([rays, make_ray_batch(g, sc, (1 << 20) - len(rays), 5)]) if len(rays) < (1 << 20) else rays[: 1 << 20]
+    ref = orc.trace_batch(sc.desc, rays)
+    for mode in (FAST, REFERENCE):
+        hits, cnt = _trace(g, dev, sc, rays, mode)
+        assert_hits_equal(hits, ref, "sponza mode %d" % mode)
+    assert (ref["leaf_tri"][rays["flags"] == 0] >= 0).mean() > 0.5
+
+
+def test_trace_parity_exact_ties_edges_and_limits(g, orc, dev, box1, box1_coincident):
+    rng = np.random.RandomState(5)
+    n = 20000
+    rays = np.zeros(n, dtype=g.RAY_DTYPE)
+    lo, hi = np.array([0.25, 0.05, -1.3]), np.array([1.05, 0.7, -0.5])
+    rays["origin"] = (lo + rng.rand(n, 3) * (hi - lo)).astype(np.float32)
+    d = rng.randn(n, 3); d[:, 1] = -np.abs(d[:, 1]) - 0.2
+    rays["direction"] = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    rays["t_max"] = np.float32(g.RAY_MAX)
+    hits, cnt = _trace(g, dev, box1_coincident, rays, FAST)
+    assert_hits_equal(hits, orc.trace_batch(box1_coincident.desc, rays), "ties")
+    assert cnt["exact_fallback_rays"] > n // 4
+    # shared edges / vertices / in-plane rays
+    P = box1.positions(); lt = box1.leaf_triangles()
+    v = lt["v"][lt["v"][:, 0] != lt["v"][:, 1]]
+    m = 30000
+    pick = rng.randint(0, len(v), size=m)
+    a, b = P[v[pick, 0]], P[v[pick, 1]]
+    w = rng.rand(m, 1).astype(np.float32); w[: m // 3] = 0.0
+    origin = np.array([0.0, 1.5, 1.0], dtype=np.float32) + rng.uniform(-0.3, 0.3, size=(m, 3)).astype(np.float32)
+    dd = a * (1 - w) + b * w - origin
+    e = np.zeros(m, dtype=g.RAY_DTYPE)
+    e["origin"] = origin; e["direction"] = (dd / np.linalg.norm(dd, axis=1, keepdims=True)).astype(np.float32); e["t_max"] = np.float32(g.RAY_MAX)
+    flat = np.zeros(5000, dtype=g.RAY_DTYPE)
+    flat["origin"] = np.stack([rng.uniform(-1.4, 1.4, 5000), np.zeros(5000), rng.uniform(-2.9, 2.2, 5000)], 1).astype(np.float32)
+    fd = np.stack([rng.randn(5000), np.zeros(5000), rng.randn(5000)], 1)
+    flat["direction"] = (fd / np.linalg.norm(fd, axis=1, keepdims=True)).astype(np.float32); flat["t_max"] = np.float32(g.RAY_MAX)
+    # finite closest-hit limits at / next to the hit distance
+    lim = make_ray_batch(g, box1, 30000, 12, any_fraction=0.0)
+    t = orc.trace_batch(box1.desc, lim)["t"].copy()
+    lim["t_max"][:10000] = t[:10000]
+    with np.errstate(over="ignore"):
+        lim["t_max"][10000:20000] = np.nextafter(t[10000:20000], np.float32(np.inf))
+    lim["t_max"][20000:] = t[20000:] * np.float32(0.5)
+    lim["t_max"][~np.isfinite(lim["t_max"])] = np.float32(10.0)
+    batch = np.concatenate([e, flat, lim])
+    ref = orc.trace_batch(box1.desc, batch)
+    for mode in (FAST, REFERENCE):
+        hits, _ = _trace(g, dev, box1, batch, mode)
+        assert_hits_equal(hits, ref, "edges/limits mode %d" % mode)
+
+
+def test_trace_ragged_and_deep(g, orc, dev, scenes):
+    """Empty batch, 1-triangle scene (root is a leaf), half-filled leaves, and a list-like deep tree (stack overflow)."""
+    sc = scenes.make_random_triangles(50, seed=1)
+    dev.upload_scene(sc)
+    assert dev.trace(np.zeros(0, dtype=g.RAY_DTYPE)).shape == (0,)
+    for n in (1, 2, 3, 5):
+        s = scenes.make_random_triangles(n, seed=n)
+        rng = np.random.RandomState(n)
+        rays = np.zeros(4096, dtype=g.RAY_DTYPE)
+        rays["origin"] = rng.uniform(-12, 12, size=(4096, 3)).astype(np.float32)
+        c = s.positions().mean(axis=0)
+        d = c - rays["origin"] + rng.uniform(-1.5, 1.5, size=(4096, 3))
+        rays["direction"] = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+        rays["t_max"] = np.float32(g.RAY_MAX)
+        for mode in (FAST, REFERENCE):
+            hits, _ = _trace(g, dev, s, rays, mode)
+            assert_hits_equal(hits, orc.trace_batch(s.desc, rays), "%d triangles mode %d" % (n, mode))
+    n = 4000
+    x = np.arange(n, dtype=np.float32)[:, None] * (1.5 ** np.linspace(0, 8, n))[:, None].astype(np.float32) * 0.001
+    p = np.zeros((n, 3, 3), dtype=np.float32)
+    p[:, :, 0] = x + np.array([0, 0.4, 0.2], np.float32); p[:, 1, 1] = 1.0; p[:, 2, 2] = 1.0
+    tri = np.arange(3 * n, dtype=np.uint32).reshape(n, 3)
+    deep = g.Scene.from_mesh(p.reshape(-1, 3), np.tile(np.float32([0, 1, 0]), (3 * n, 1)), np.zeros((3 * n, 2), np.float32), tri, np.zeros(n, np.uint32),
+                             {"m": scenes.legacy_material()})
+    rays = make_ray_batch(g, deep, 50000, 6)
+    hits, cnt = _trace(g, dev, deep, rays, FAST)
+    assert_hits_equal(hits, orc.trace_batch(deep.desc, rays), "deep tree")
+
+
+def test_trace_device_buffers(g, orc, dev, box1):
+    """gi_trace_device on caller-owned device memory (torch is only the allocator here)."""
+    import torch
+    rays = make_ray_batch(g, box1, 100000, 21)
+    dev.upload_scene(box1)
+    dev.set_option(g.GI_OPT_TRAVERSAL, FAST)
+    d_rays = torch.from_numpy(rays.view(np.uint8).reshape(-1)).cuda()
+    d_hits = torch.zeros(len(rays) * 16, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    dev.trace_device(d_rays.data_ptr(), len(rays), d_hits.data_ptr())
+    dev.synchronize()
+    hits = d_hits.cpu().numpy().view(g.HIT_DTYPE)
+    assert_hits_equal(hits, orc.trace_batch(box1.desc, rays), "device buffers")
+
+
+def test_error_behaviour(g, dev, box1):
+    d = g.Device(0)
+    with pytest.raises(g.GpugiError, match="no scene"):
+        d.trace(np.zeros(4, dtype=g.RAY_DTYPE))
+    with pytest.raises(g.GpugiError, match="no scene"):
+        d.render_iteration(g.GI_RENDERER_PT, 1)
+    d.upload_scene(box1)
+    with pytest.raises(g.GpugiError, match="gi_set_screen_size"):
+        d.render_iteration(g.GI_RENDERER_PT, 1)
+    d.set_screen_size(64, 64)
+    with pytest.raises(g.GpugiError, match="gi_set_camera"):
+        d.render_iteration(g.GI_RENDERER_PT, 1)
+    with pytest.raises(g.GpugiError):
+        g.Device(99)
+    d.close()
