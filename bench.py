@@ -136,7 +136,7 @@ def cpu_baseline(scene, budget_s=12.0):
     secs = 0.0
     it = 0
     tot = {}
-    while secs < budget_s and it < 64:
+    while secs < budget_s and it < 400:
         p, r, dt, cnt = oracle_pass(orc, scene, cam, sampler, it, regions)
         paths += p; rays += r; secs += dt; it += 1
         for k, v in cnt.items():
@@ -196,7 +196,9 @@ def run_ours(args, rank, world, local_rank):
 
     rs = g.RendererSystem(local_rank)
     dev = rs.device
-    stream = torch.cuda.current_stream()
+    # a non-default torch stream carries every launch, so torch.cuda.Event times exactly our kernels
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     dev.set_stream(stream.cuda_stream)
     rs.SetScene(scene)
     rs.SetScreenSize(WIDTH, HEIGHT)

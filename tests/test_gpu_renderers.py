@@ -179,7 +179,10 @@ def test_bidirectional_matches_oracle(g, orc, scenes, box1):
     # 16-iteration means, both noisy => tolerance 0.25; mean energy within 3 %
     a, b = img[..., :3] / N, ref[..., :3] / N
     assert abs(a.mean() - b.mean()) / b.mean() < 0.03
-    assert rel_mse(a, b) < 0.25
+    # per-pixel values are two independent noisy estimates; compare 8x8 block means (12x12 blocks)
+    ab = a.reshape(12, 8, 12, 8, 3).mean(axis=(1, 3))
+    bb = b.reshape(12, 8, 12, 8, 3).mean(axis=(1, 3))
+    assert rel_mse(ab, bb) < 0.1
     rs.close()
 
 
