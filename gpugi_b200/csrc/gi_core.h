@@ -114,6 +114,8 @@ struct DScene
 	const F4* vertexInfo;    // GiVertexInfo per vertex
 	const DMaterial* materials;
 	const DTexel* texels;    // 4 per material, same order as DMaterial::tex (fp32 filter / emulation)
+	const uint32_t* leafNode; // reference node index of every leaf (its own box: the reference's cull test for the leaf)
+	int leafPreorder;        // leaf indices increase in the reference's preorder walk (tie-break order == leaf slot order)
 	uint32_t numNodes;
 	uint32_t numLeafTris;
 	uint32_t numMaterials;
@@ -739,9 +741,18 @@ GI_HD F3 environmentRadiance(const DFrame& f, F3 dir)
 	return f.envColor;
 }
 
-// EstimateDirectLight, lightsource.glsl:3-93
-GI_HD F3 estimateDirectLight(const DFrame& f, F3 pos, F3 normal, int lightSampleIndex, F3 viewDir, const MaterialData& md, bool sampleAreaLights,
-                             PathCounters& pc, TraceStats* st)
+// EstimateDirectLight, lightsource.glsl:3-93, split in two: everything up to the shadow ray (prepareDirectLight) and the
+// any-hit query.  The value returned for an unoccluded sample does not depend on the query, so the wavefront scheduler
+// evaluates it before the shadow ray is traced; the megakernel calls both halves back to back (estimateDirectLight).
+struct DirectLightQuery
+{
+	F3 origin, dir;   // shadow ray
+	float len;        // rayLength of the any-hit query
+	F3 radiance;      // EstimateDirectLight's result when the ray is free
+};
+
+GI_HD bool prepareDirectLight(const DFrame& f, F3 pos, F3 normal, int lightSampleIndex, F3 viewDir, const MaterialData& md, bool sampleAreaLights,
+                              DirectLightQuery& q)
 {
 	F4 l0 = ld4(f.lightSamples + 2 * lightSampleIndex), l1 = ld4(f.lightSamples + 2 * lightSampleIndex + 1);
 	F3 dir = f3(l0.x, l0.y, l0.z) - pos;
@@ -749,38 +760,39 @@ GI_HD F3 estimateDirectLight(const DFrame& f, F3 pos, F3 normal, int lightSample
 	float lightDist = sqrtf(lightDistSq);
 	dir = dir / lightDist;
 	float surfaceCos = saturate(dot(dir, normal));
-	if (surfaceCos <= 0.0f) return f3(0.0f);
+	if (surfaceCos <= 0.0f) return false;
 	F3 intensity = f3(l1.x, l1.y, l1.z);
 	if (l1.w > 1.5f)
 	{
-		F3 origin = GI_RAY_HIT_EPSILON * dir + pos;
-		++pc.anyRays;
-		if (!traceAny(f.scene, f.traversalMode, origin, dir, lightDist - GI_RAY_HIT_EPSILON * 2, st))
-		{
-			F3 irradiance = (surfaceCos / lightDistSq) * intensity;
-			float pdf;
-			return irradiance * BSDF(viewDir, dir, md, normal, pdf);
-		}
+		// point light (lightsource.glsl:25-47)
 	}
 	else if (sampleAreaLights)
 	{
 		F3 lightNormal = unpackNormal(l0.w, l1.w);
 		float factor = saturate(dot(lightNormal, -dir));
-		if (factor > 0.0f)
-		{
-			F3 origin = GI_RAY_HIT_EPSILON * dir + pos;
-			++pc.anyRays;
-			if (!traceAny(f.scene, f.traversalMode, origin, dir, lightDist - GI_RAY_HIT_EPSILON * 2, st))
-			{
-				float pdf;
-				F3 lightSampleIntensity = intensity * factor;
-				F3 bsdf = BSDF(viewDir, dir, md, normal, pdf);
-				F3 irradiance = (surfaceCos / lightDistSq) * lightSampleIntensity;
-				return irradiance * bsdf;
-			}
-		}
+		if (!(factor > 0.0f)) return false;
+		intensity = intensity * factor;
 	}
-	return f3(0.0f);
+	else
+		return false;
+	q.origin = GI_RAY_HIT_EPSILON * dir + pos;
+	q.dir = dir;
+	q.len = lightDist - GI_RAY_HIT_EPSILON * 2;
+	float pdf;
+	F3 bsdf = BSDF(viewDir, dir, md, normal, pdf);
+	F3 irradiance = (surfaceCos / lightDistSq) * intensity;
+	q.radiance = irradiance * bsdf;
+	return true;
+}
+
+GI_HD F3 estimateDirectLight(const DFrame& f, F3 pos, F3 normal, int lightSampleIndex, F3 viewDir, const MaterialData& md, bool sampleAreaLights,
+                             PathCounters& pc, TraceStats* st)
+{
+	DirectLightQuery q;
+	if (!prepareDirectLight(f, pos, normal, lightSampleIndex, viewDir, md, sampleAreaLights, q)) return f3(0.0f);
+	++pc.anyRays;
+	if (traceAny(f.scene, f.traversalMode, q.origin, q.dir, q.len, st)) return f3(0.0f);
+	return q.radiance;
 }
 
 // pathtracer.comp:16-110, one invocation (pixel gx,gy)

@@ -4,11 +4,13 @@
 // There is no CPU path in this file: every compute entry point needs a live sm_100 device.
 #include "gi_core.h"
 #include "gi_layout.h"
+#include "gi_wavefront.cuh"
 
 #include <cuda_runtime.h>
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -20,6 +22,7 @@ using namespace gik;
 // =====================================================================================================
 
 // 64-bit device counters (GiCounters order, first 7 entries)
+static_assert(true, "");
 enum { CNT_CLOSEST = 0, CNT_ANY, CNT_CAMERA, CNT_LIGHT, CNT_SHADED, CNT_SPLATS, CNT_FALLBACK, CNT_NODES, CNT_TRIS, CNT_COUNT };
 
 __device__ __forceinline__ void flushCounters(unsigned long long* counters, const PathCounters& pc, const TraceStats& st)
@@ -121,6 +124,82 @@ __global__ void k_reset_counter(uint32_t* lightCacheCount, uint32_t* lightPathLe
 	*lightPathLengthSum = 0u;
 }
 
+// ---- wavefront scheduler (gi_wavefront.cuh) -------------------------------------------------------------
+#define WF_TRACE_THREADS 128
+#define WF_SHADE_THREADS 128
+
+// Camera rays of all W/8 x H/8 work groups (pathtracer.comp:36-46) into the extension queue of bounce 0.
+__global__ void __launch_bounds__(256) k_wf_generate(WfFrame w, unsigned long long* counters)
+{
+	const uint32_t stride = gridDim.x * blockDim.x;
+	for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < w.numPaths; slot += stride)
+	{
+		const uint32_t pixel = wfSlotToPixel(w, slot);
+		const int gx = int(pixel % uint32_t(w.f.width)), gy = int(pixel / uint32_t(w.f.width));
+		uint32_t seed = initRandomSeed(w.f.frameSeed, pixel);
+		const F3 dir = cameraRayDirection(w.f, seed, gx, gy);
+		F4* rp = w.q.rays[0] + 2 * size_t(slot);
+		*reinterpret_cast<float4*>(rp) = make_float4(w.f.cam.position[0], w.f.cam.position[1], w.f.cam.position[2], GI_RAY_MAX);
+		*reinterpret_cast<float4*>(rp + 1) = make_float4(dir.x, dir.y, dir.z, i2f(int(pixel)));
+	}
+	if (blockIdx.x == 0 && threadIdx.x == 0)
+	{
+		w.q.counts[0] = w.numPaths;
+		atomicAdd(counters + CNT_CLOSEST, (unsigned long long)w.numPaths);
+		atomicAdd(counters + CNT_CAMERA, (unsigned long long)w.numPaths);
+	}
+}
+
+// trace(b): extension rays of bounce b + shadow rays pushed by shade(b-1); persistent warps, dynamic refill.
+template <bool REFERENCE>
+__global__ void __launch_bounds__(WF_TRACE_THREADS) k_wf_trace(WfFrame w, int bounce, unsigned long long* counters)
+{
+	WfQueueIO io;
+	io.q.rays = w.q.rays[bounce & 1];
+	io.q.hits = w.q.hits;
+	io.q.shadow = w.q.shadow;
+	io.q.stateC = w.q.stateC;
+	io.q.accum = w.f.accum;
+	io.q.width = w.f.width; io.q.height = w.f.height;
+	io.q.numClosest = bounce < w.f.maxPathLength ? w.q.counts[WF_COUNTS_PER_BOUNCE * bounce] : 0u;
+	io.q.numShadow = bounce > 0 ? w.q.counts[WF_COUNTS_PER_BOUNCE * (bounce - 1) + 1] : 0u;
+	unsigned cnt[WFC_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+	if (REFERENCE) wfTraceLoopReference(w.f.scene, io, w.q.counts + WF_COUNTS_PER_BOUNCE * bounce + 2, cnt);
+	else wfTraceLoop(w.f.scene, io, w.q.counts + WF_COUNTS_PER_BOUNCE * bounce + 2, w.tune, cnt);
+	flushWarpCounters(counters, cnt, WFC_COUNT);
+}
+
+// gi_trace_device on the same persistent loop.
+__global__ void __launch_bounds__(WF_TRACE_THREADS) k_wf_trace_batch(DScene s, const GiRay* __restrict__ rays, uint32_t n, GiHit* __restrict__ hits, WfTune tune,
+                                                                      uint32_t* workCounter, unsigned long long* counters)
+{
+	WfBatchIO io;
+	io.rays = reinterpret_cast<const F4*>(rays);
+	io.hits = reinterpret_cast<float4*>(hits);
+	io.n = n;
+	unsigned cnt[WFC_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+	wfTraceLoop(s, io, workCounter, tune, cnt);
+	flushWarpCounters(counters, cnt, WFC_COUNT);
+}
+
+// shade(b) of the path tracer: one lane per hit record, 32 consecutive queue slots per warp and fetch.
+__global__ void __launch_bounds__(WF_SHADE_THREADS) k_wf_shade_pt(WfFrame w, int bounce, unsigned long long* counters)
+{
+	uint32_t* counts = w.q.counts + WF_COUNTS_PER_BOUNCE * bounce;
+	const uint32_t n = counts[0];
+	unsigned cnt[WFC_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+	for (;;)
+	{
+		uint32_t base = 0;
+		if (laneId() == 0) base = atomicAdd(counts + 3, 32u);
+		base = __shfl_sync(0xffffffffu, base, 0);
+		if (base >= n) break;
+		const uint32_t slot = base + laneId();
+		wfShadePT(w, bounce, slot, slot < n, cnt);
+	}
+	flushWarpCounters(counters, cnt, WFC_COUNT);
+}
+
 // sqerror.frag:16-17 + mean (texturemse.cpp:58-62): per-block partial sums in double.
 __global__ void __launch_bounds__(256) k_mse(const float4* __restrict__ accum, const float* __restrict__ ref, uint32_t numPixels, float invDivisor,
                                               double* result)
@@ -190,7 +269,16 @@ struct GiContext
 	// options
 	int traversal = GI_TRAVERSAL_FAST;
 	int textureFilterExact = 0;
-	int scheduler = 0;
+	int scheduler = GI_SCHEDULER_WAVEFRONT;
+	WfTune tune = {16, 20, 0};
+
+	// wavefront queues
+	WfQueues wf = {};
+	uint32_t wfCountsLen = 0;
+	uint32_t wfNumIds = 0;
+	uint32_t* traceWork = nullptr;   // work counter of k_wf_trace_batch
+	int numSMs = 148;
+	int traceBlocksPerSM = 1, shadeBlocksPerSM = 1;
 };
 
 static std::string g_createError;
@@ -258,6 +346,104 @@ static DFrame makeFrame(GiContext* c, const GiIterationParams* p)
 }
 
 
+// ---- wavefront queue storage: 2 ray queues, hit records, shadow queue, path state, per-bounce counters
+static void freeWavefront(GiContext* c)
+{
+	cudaFree(c->wf.rays[0]); cudaFree(c->wf.rays[1]); cudaFree(c->wf.hits); cudaFree(c->wf.shadow); cudaFree(c->wf.stateT); cudaFree(c->wf.stateC);
+	cudaFree(c->wf.counts);
+	c->wf = WfQueues{};
+	c->wfCountsLen = 0;
+	c->wfNumIds = 0;
+}
+
+// capacity: queue slots (paths per iteration); numIds: size of the per-path state arrays, which are indexed by path id
+// (PT/BPT: the pixel index, which is not dense when the frame size is not a multiple of 8).
+static int ensureWavefront(GiContext* c, uint32_t capacity, uint32_t numIds, int maxPathLength)
+{
+	const uint32_t countsLen = WF_COUNTS_PER_BOUNCE * uint32_t(maxPathLength + 2);
+	if (c->wf.capacity >= capacity && c->wfNumIds >= numIds && c->wfCountsLen >= countsLen) return GI_OK;
+	if (capacity > WF_ID_MASK || numIds > WF_ID_MASK) return fail(c, GI_ERR_CAPACITY, "wavefront scheduler: more than 2^30 paths per iteration");
+	GI_CUDA(c, cudaStreamSynchronize(c->stream));
+	const uint32_t cap = std::max(capacity, c->wf.capacity);
+	const uint32_t ids = std::max(numIds, c->wfNumIds);
+	const uint32_t len = std::max(countsLen, c->wfCountsLen);
+	freeWavefront(c);
+	GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->wf.rays[0]), size_t(cap) * 32));
+	GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->wf.rays[1]), size_t(cap) * 32));
+	GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->wf.hits), size_t(cap) * 8));
+	GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->wf.shadow), size_t(cap) * 48));
+	GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->wf.stateT), size_t(ids) * 16));
+	GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->wf.stateC), size_t(ids) * 16));
+	GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->wf.counts), size_t(len) * sizeof(uint32_t)));
+	c->wf.capacity = cap;
+	c->wfNumIds = ids;
+	c->wfCountsLen = len;
+	return GI_OK;
+}
+
+// One path-tracer iteration as waves: generate, then trace(b) / shade(b) per bounce, then the shadow rays of the last bounce.
+static int renderWavefrontPT(GiContext* c, const DFrame& f)
+{
+	WfFrame w;
+	std::memset(&w, 0, sizeof(w));
+	w.f = f;
+	w.tilesX = c->width / 8; w.tilesY = c->height / 8; // integer division, pathtracer.cpp:50
+	w.numPaths = uint32_t(w.tilesX) * uint32_t(w.tilesY) * 64u;
+	if (w.numPaths == 0) return GI_OK;
+	int st = ensureWavefront(c, w.numPaths, uint32_t(c->width) * uint32_t(c->height), f.maxPathLength);
+	if (st != GI_OK) return st;
+	w.q = c->wf;
+	w.tune = c->tune;
+	GI_CUDA(c, cudaMemsetAsync(c->wf.counts, 0, size_t(c->wfCountsLen) * sizeof(uint32_t), c->stream));
+	const unsigned traceGrid = unsigned(c->numSMs * c->traceBlocksPerSM), shadeGrid = unsigned(c->numSMs * c->shadeBlocksPerSM);
+	// GI_WF_PROFILE=1: per-kernel CUDA-event timings of this iteration on stderr (warm caches, unlike an ncu replay)
+	static const bool profile = std::getenv("GI_WF_PROFILE") != nullptr;
+	std::vector<cudaEvent_t> ev;
+	std::vector<std::string> evName;
+	auto mark = [&](const char* what, int b) {
+		if (!profile) return;
+		cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, c->stream);
+		ev.push_back(e); evName.push_back(std::string(what) + "(" + std::to_string(b) + ")");
+	};
+	const bool ref = f.traversalMode == GI_TRAVERSAL_REFERENCE;
+	auto trace = [&](int b) {
+		if (ref) k_wf_trace<true><<<traceGrid, WF_TRACE_THREADS, 0, c->stream>>>(w, b, c->counters);
+		else k_wf_trace<false><<<traceGrid, WF_TRACE_THREADS, 0, c->stream>>>(w, b, c->counters);
+		++c->launches;
+		mark("trace", b);
+	};
+	mark("start", 0);
+	k_wf_generate<<<unsigned(c->numSMs) * 8u, 256, 0, c->stream>>>(w, c->counters);
+	++c->launches;
+	mark("generate", 0);
+	for (int b = 0; b < f.maxPathLength; ++b)
+	{
+		trace(b);
+		k_wf_shade_pt<<<shadeGrid, WF_SHADE_THREADS, 0, c->stream>>>(w, b, c->counters);
+		++c->launches;
+		mark("shade", b);
+	}
+	trace(f.maxPathLength);
+	if (profile)
+	{
+		cudaStreamSynchronize(c->stream);
+		std::vector<uint32_t> h(c->wfCountsLen);
+		cudaMemcpy(h.data(), c->wf.counts, h.size() * 4, cudaMemcpyDeviceToHost);
+		float total = 0.0f;
+		for (size_t i = 1; i < ev.size(); ++i)
+		{
+			float ms = 0.0f; cudaEventElapsedTime(&ms, ev[i - 1], ev[i]); total += ms;
+			std::fprintf(stderr, "[wf] %-10s %8.1f us", evName[i].c_str(), ms * 1e3f);
+			if (evName[i][0] == 't') { int b = int(i - 2) / 2; std::fprintf(stderr, "   closest %8u shadow %8u", h[4 * b], b > 0 ? h[4 * (b - 1) + 1] : 0u); }
+			std::fprintf(stderr, "\n");
+		}
+		std::fprintf(stderr, "[wf] total      %8.1f us\n", total * 1e3f);
+		for (cudaEvent_t e : ev) cudaEventDestroy(e);
+	}
+	return GI_OK;
+}
+
+
 // =====================================================================================================
 // C ABI
 // =====================================================================================================
@@ -291,7 +477,14 @@ int gi_create(int device, GiContext** out_ctx)
 	          cudaMalloc(reinterpret_cast<void**>(&c->bptCounters), 2 * sizeof(uint32_t)) == cudaSuccess &&
 	          cudaMalloc(reinterpret_cast<void**>(&c->mseResult), sizeof(double)) == cudaSuccess &&
 	          cudaMemset(c->counters, 0, CNT_COUNT * sizeof(unsigned long long)) == cudaSuccess && cudaMemset(c->bptCounters, 0, 2 * sizeof(uint32_t)) == cudaSuccess;
+	ok = ok && cudaMalloc(reinterpret_cast<void**>(&c->traceWork), sizeof(uint32_t)) == cudaSuccess;
 	if (!ok) { gi_destroy(c); return fail(nullptr, GI_ERR_CUDA, "gi_create: device allocation failed"); }
+	// persistent kernels: one resident wave, grid = SMs x resident blocks per SM
+	c->numSMs = prop.multiProcessorCount;
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->traceBlocksPerSM, k_wf_trace<false>, WF_TRACE_THREADS, 0);
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->shadeBlocksPerSM, k_wf_shade_pt, WF_SHADE_THREADS, 0);
+	c->traceBlocksPerSM = std::max(c->traceBlocksPerSM, 1);
+	c->shadeBlocksPerSM = std::max(c->shadeBlocksPerSM, 1);
 	*out_ctx = c;
 	return GI_OK;
 }
@@ -302,6 +495,8 @@ void gi_destroy(GiContext* c)
 	cudaSetDevice(c->device);
 	cudaDeviceSynchronize();
 	freeScene(c);
+	freeWavefront(c);
+	cudaFree(c->traceWork);
 	if (c->envTex) cudaDestroyTextureObject(c->envTex);
 	if (c->envArray) cudaFreeArray(c->envArray);
 	cudaFree(c->accum); cudaFree(c->lightSamples); cudaFree(c->lightCache); cudaFree(c->bptCounters); cudaFree(c->counters); cudaFree(c->mseResult);
@@ -326,7 +521,15 @@ int gi_set_option(GiContext* c, int option, int value)
 		if (value != GI_TRAVERSAL_FAST && value != GI_TRAVERSAL_REFERENCE) return fail(c, GI_ERR_INVALID, "GI_OPT_TRAVERSAL: unknown mode");
 		c->traversal = value; return GI_OK;
 	case GI_OPT_TEXTURE_FILTER: c->textureFilterExact = value ? 1 : 0; return GI_OK;
-	case GI_OPT_SCHEDULER: c->scheduler = value; return GI_OK;
+	case GI_OPT_SCHEDULER:
+		if (value != GI_SCHEDULER_WAVEFRONT && value != GI_SCHEDULER_MEGAKERNEL) return fail(c, GI_ERR_INVALID, "GI_OPT_SCHEDULER: unknown scheduler");
+		c->scheduler = value; return GI_OK;
+	case GI_OPT_WF_REFILL_THRESHOLD: c->tune.refillThreshold = std::min(std::max(value, 1), 32); return GI_OK;
+	case GI_OPT_WF_MIN_INNER: c->tune.minInner = std::min(std::max(value, 1), 32); return GI_OK;
+	case GI_OPT_WF_BLOCKS_PER_SM:
+		if (value > 0) c->traceBlocksPerSM = value;
+		else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->traceBlocksPerSM, k_wf_trace<false>, WF_TRACE_THREADS, 0);
+		return GI_OK;
 	}
 	return fail(c, GI_ERR_INVALID, "gi_set_option: unknown option");
 }
@@ -403,6 +606,7 @@ int gi_upload_scene(GiContext* c, const GiSceneDesc* d)
 	GI_CUDA(c, uploadVector(c, L.fastNodes, &s.fastNodes));
 	GI_CUDA(c, uploadVector(c, L.leafPos, &s.leafPos));
 	GI_CUDA(c, uploadVector(c, L.leafTris, &s.leafTris));
+	GI_CUDA(c, uploadVector(c, L.leafNode, &s.leafNode));
 	GI_CUDA(c, uploadVector(c, L.vertexInfo, &s.vertexInfo));
 	GI_CUDA(c, uploadVector(c, L.materials, &s.materials));
 	GI_CUDA(c, uploadVector(c, L.texels, &s.texels));
@@ -535,7 +739,12 @@ int gi_render_iteration(GiContext* c, const GiIterationParams* p)
 	switch (p->renderer)
 	{
 	case GI_RENDERER_PT:
-		if (pixelGrid.x && pixelGrid.y)
+		if (c->scheduler == GI_SCHEDULER_WAVEFRONT)
+		{
+			st = renderWavefrontPT(c, f);
+			if (st != GI_OK) return st;
+		}
+		else if (pixelGrid.x && pixelGrid.y)
 		{
 			k_pathtrace<<<pixelGrid, 64, 0, c->stream>>>(f, c->counters);
 			++c->launches;
@@ -603,8 +812,18 @@ int gi_trace_device(GiContext* c, const GiRay* d_rays, uint32_t n, GiHit* d_hits
 	GI_CUDA(c, cudaSetDevice(c->device));
 	DScene s = c->scene;
 	const int mode = c->fastValid ? c->traversal : GI_TRAVERSAL_REFERENCE;
-	k_trace<<<(n + 127) / 128, 128, 0, c->stream>>>(s, d_rays, n, d_hits, mode, c->counters);
-	++c->launches;
+	if (mode == GI_TRAVERSAL_FAST && c->scheduler == GI_SCHEDULER_WAVEFRONT)
+	{
+		GI_CUDA(c, cudaMemsetAsync(c->traceWork, 0, sizeof(uint32_t), c->stream));
+		const unsigned grid = std::min(unsigned(c->numSMs * c->traceBlocksPerSM), (n + WF_TRACE_THREADS - 1) / WF_TRACE_THREADS);
+		k_wf_trace_batch<<<grid, WF_TRACE_THREADS, 0, c->stream>>>(s, d_rays, n, d_hits, c->tune, c->traceWork, c->counters);
+		++c->launches;
+	}
+	else
+	{
+		k_trace<<<(n + 127) / 128, 128, 0, c->stream>>>(s, d_rays, n, d_hits, mode, c->counters);
+		++c->launches;
+	}
 	GI_CUDA(c, cudaGetLastError());
 	return GI_OK;
 }

@@ -20,6 +20,7 @@ struct HostLayout
 {
 	std::vector<F4> refNodes, fastNodes, leafPos, vertexInfo;
 	std::vector<I4> leafTris;
+	std::vector<uint32_t> leafNode;         // leaf -> index of the node that points to it
 	std::vector<DMaterial> materials;
 	std::vector<DTexel> texels;             // 4 per material; .pixels still points at HOST memory here
 	std::vector<int32_t> materialTexture;   // 4 per material: index into GiSceneDesc::textures
@@ -134,6 +135,31 @@ inline bool buildHostLayout(const GiSceneDesc* d, HostLayout& L, std::string& er
 		q[3] = ch;
 	}
 
+	// ---- leaf -> node map, and whether leaf indices increase along the reference's preorder walk (node -> firstChild,
+	// leaf/skip -> escape; with every box "hit" this enumerates all leaves in tie-break order)
+	L.leafNode.assign(numLeaves, 0u);
+	bool preorder = true;
+	{
+		std::vector<uint8_t> seen(numLeaves, 0);
+		uint32_t node = 0, steps = 0;
+		int64_t lastLeaf = -1;
+		do
+		{
+			const GiNode& n = d->nodes[node];
+			if (n.first_child & 0x80000000u)
+			{
+				const uint32_t leaf = n.first_child & 0x7fffffffu;
+				if (seen[leaf] || int64_t(leaf) <= lastLeaf) preorder = false;
+				seen[leaf] = 1; lastLeaf = leaf;
+				L.leafNode[leaf] = node;
+				node = n.escape;
+			}
+			else
+				node = n.first_child;
+			if (++steps > 2u * d->num_nodes) { preorder = false; break; } // malformed escape chain
+		} while (node != 0);
+	}
+
 	// ---- materials
 	L.materials.resize(d->num_materials);
 	L.texels.resize(size_t(d->num_materials) * 4);
@@ -183,6 +209,7 @@ inline bool buildHostLayout(const GiSceneDesc* d, HostLayout& L, std::string& er
 	L.scene.numMaterials = d->num_materials;
 	L.scene.rootIsLeaf = (d->nodes[0].first_child & 0x80000000u) ? 1 : 0;
 	L.scene.fastOrderValid = L.binary ? 1 : 0;
+	L.scene.leafPreorder = preorder ? 1 : 0;
 	{
 		const GiNode& r = d->nodes[0];
 		float dx = r.max[0] - r.min[0], dy = r.max[1] - r.min[1], dz = r.max[2] - r.min[2];

@@ -1,0 +1,404 @@
+// gi_wavefront.cuh -- wavefront scheduling of the three integrators (device only, sm_100a).
+//
+// The reference runs one GL compute invocation per path from the first ray to the last bounce
+// (pathtracer.comp:16-110, lighttracer.comp:49-193, pathtracer_bidir.comp:16-251).  On a GPU without RT cores
+// that shape is divergence-bound: Russian roulette ends most paths after 1-2 bounces while a few run to 16, and
+// inner-node / leaf / shading code serialise inside a warp (profiles/r01_ncu_pathtrace.md: 6.95 of 32 lanes active).
+// Here an iteration is a sequence of waves over HBM-resident queues:
+//
+//   generate -> [ trace(b) -> shade(b) ] for b = 0 .. maxPathLength-1 -> trace(maxPathLength)   (shadow rays only)
+//
+//   trace(b)  persistent warps; every lane owns one ray and refills itself from the extension queue of bounce b
+//             and the shadow queue of bounce b-1 as soon as enough lanes of its warp ran dry (ballot + popc, one
+//             atomicAdd per warp).  Inner-node steps and leaf steps are scheduled per warp by vote so that the two
+//             code paths never serialise against each other.  Same tree, same box/triangle arithmetic, same
+//             ambiguity rule as traceFast() (gi_core.h) -- the result per ray is bit-identical.
+//   shade(b)  one lane per hit: GetTriangleHitInfo, SampleMaterialData, emission, next-event estimation (pushes a
+//             shadow ray carrying its contribution), SampleBSDF, Russian roulette, and a ballot-compacted push of
+//             the surviving ray into the queue of bounce b+1.
+//
+// Every path keeps the reference's private RNG stream and its floating-point operation order (the radiance sum of a
+// path is kept in the path state and added to the accumulator once, at the path's end), so an iteration is a
+// deterministic function of (scene, camera, frame seed, light samples) exactly as in the megakernel.
+#pragma once
+
+#include "gi_core.h"
+#include "gi_lane.h"
+
+namespace gik {
+
+// ------------------------------------------------------------------ queues (HBM)
+// ray record      2 x F4: (origin.xyz, tMax) (direction.xyz, path word)
+// hit record      float2: (t, leafTri bits), leafTri = -1: miss; always the reference's exact answer
+// shadow record   3 x F4: (origin.xyz, rayLength) (direction.xyz, target word) (value.rgb, -)
+// path word       bits 0..29 path id (pixel index / light path index), bit 30 didNEE
+// target word     bits 0..29 path id or pixel index, bit 30 splat (atomic add into the accumulator instead of the
+//                 path's radiance sum), bit 31 terminal (flush the path's radiance sum to the accumulator)
+#define WF_ID_MASK 0x3fffffffu
+#define WF_FLAG_NEE 0x40000000u
+#define WF_FLAG_SPLAT 0x40000000u
+#define WF_FLAG_TERMINAL 0x80000000u
+#define WF_COUNTS_PER_BOUNCE 4 // [0] extension rays of bounce b, [1] shadow rays pushed by shade(b), [2] trace work counter, [3] shade work counter
+
+struct WfQueues
+{
+	F4* rays[2];
+	float2* hits;
+	F4* shadow;
+	F4* stateT;          // (throughput.xyz, seed bits)
+	F4* stateC;          // (radiance sum.xyz, -)
+	uint32_t* counts;    // WF_COUNTS_PER_BOUNCE x (maxPathLength + 2), zeroed per iteration
+	uint32_t capacity;   // slots per queue
+};
+
+// tuning knobs (uniform kernel arguments so that one build can be swept)
+struct WfTune
+{
+	int refillThreshold; // refill a warp's idle lanes once this many are idle
+	int minInner;        // keep taking inner-node steps while this many (of 32 active) lanes are at inner nodes
+	int reserved;
+};
+
+GI_D unsigned laneId() { return threadIdx.x & 31u; }
+GI_D unsigned lanemaskLt() { unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
+
+// ballot-compacted slot allocation: one atomicAdd per warp (all 32 lanes must call)
+GI_D uint32_t warpPush(uint32_t* counter, bool pred)
+{
+	const unsigned m = __ballot_sync(0xffffffffu, pred);
+	if (m == 0u) return 0u;
+	uint32_t base = 0;
+	const int leader = __ffs(m) - 1;
+	if (int(laneId()) == leader) base = atomicAdd(counter, uint32_t(__popc(m)));
+	base = __shfl_sync(0xffffffffu, base, leader);
+	return base + __popc(m & lanemaskLt());
+}
+
+GI_D void flushWarpCounters(unsigned long long* counters, const unsigned* v, int n)
+{
+	for (int i = 0; i < n; ++i)
+	{
+		unsigned s = __reduce_add_sync(0xffffffffu, v[i]);
+		if (laneId() == 0 && s) atomicAdd(counters + i, (unsigned long long)s);
+	}
+}
+
+// Work source / sink of the wavefront trace kernel: extension rays of bounce b, then shadow rays of bounce b-1.
+struct WfTraceIO
+{
+	const F4* rays;
+	float2* hits;
+	const F4* shadow;
+	F4* stateC;
+	float* accum;
+	int width, height;
+	uint32_t numClosest, numShadow;
+};
+
+GI_D void wfSplat(float* accum, int width, int height, uint32_t pixel, F3 v)
+{
+	float* p = accum + 4 * size_t(pixel);
+	atomicAdd(reinterpret_cast<float4*>(p), make_float4(v.x, v.y, v.z, 0.0f));
+}
+
+GI_D void wfFinishShadow(const WfTraceIO& io, uint32_t slot, bool occluded)
+{
+	const F4 s1 = ld4(io.shadow + 3 * size_t(slot) + 1);
+	const uint32_t word = uint32_t(f2i(s1.w));
+	const uint32_t id = word & WF_ID_MASK;
+	if (word & WF_FLAG_SPLAT)
+	{
+		if (!occluded)
+		{
+			const F4 v = ld4(io.shadow + 3 * size_t(slot) + 2);
+			wfSplat(io.accum, io.width, io.height, id, f3(v.x, v.y, v.z));
+		}
+		return;
+	}
+	const bool terminal = (word & WF_FLAG_TERMINAL) != 0u;
+	if (occluded && !terminal) return;
+	float4 c = *reinterpret_cast<const float4*>(io.stateC + id);
+	if (!occluded)
+	{
+		const F4 v = ld4(io.shadow + 3 * size_t(slot) + 2);
+		c.x += v.x; c.y += v.y; c.z += v.z;
+	}
+	if (terminal)
+	{
+		float4* px = reinterpret_cast<float4*>(io.accum) + id;
+		float4 a = *px;
+		a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w;
+		*px = a;
+	}
+	else
+		*reinterpret_cast<float4*>(io.stateC + id) = c;
+}
+
+// The persistent trace loop.  IO provides: total(), load(index, lane state), finish(lane state).
+// Lane states are encoded in L.node: >= 0 at an inner node, < 0 at a leaf, WF_NODE_DONE finished (active: waiting to be
+// retired) or idle.  One outer iteration retires finished rays, refills idle lanes, runs ONE leaf step for the lanes
+// waiting at a leaf and then inner-node steps for as long as enough lanes of the warp are at inner nodes (one vote per
+// step), so leaf code, retire/refill code and inner-node code never serialise against each other inside the hot loop.
+template <class IO>
+GI_D void wfTraceLoop(const DScene& s, const IO& io, uint32_t* workCounter, WfTune tune, unsigned* cnt)
+{
+	StackEntry stack[GI_STACK_SIZE];
+	WfCand cand[WF_MAX_CAND];
+	WfLane L;
+	L.node = WF_NODE_DONE;
+	bool active = false;
+	bool poolEmpty = false;
+	const uint32_t total = io.total();
+	const unsigned lane = laneId();
+	for (;;)
+	{
+		// ---- retire finished rays
+		if (active && L.node == WF_NODE_DONE && wfEndOfWalk(L, s, cand, cnt))
+		{
+			io.finish(s, L, cnt);
+			active = false;
+		}
+		// ---- refill idle lanes from the queue
+		const unsigned idle = __ballot_sync(0xffffffffu, !active);
+		if (!poolEmpty && (__popc(idle) >= tune.refillThreshold || idle == 0xffffffffu))
+		{
+			const int n = __popc(idle);
+			const int leader = __ffs(idle) - 1;
+			uint32_t base = 0;
+			if (int(lane) == leader) base = atomicAdd(workCounter, uint32_t(n));
+			base = __shfl_sync(0xffffffffu, base, leader);
+			const uint32_t mine = base + __popc(idle & lanemaskLt());
+			if (!active && mine < total)
+			{
+				io.load(s, mine, L, cnt);
+				active = true;
+			}
+			if (base + uint32_t(n) >= total) poolEmpty = true;
+		}
+		const unsigned activeMask = __ballot_sync(0xffffffffu, active);
+		if (activeMask == 0u)
+		{
+			if (poolEmpty) break;
+			continue;
+		}
+		// ---- one leaf step for the lanes waiting at a leaf
+		if (L.node < 0 && L.node != WF_NODE_DONE) wfLeafStep(L, s, stack, cand, cnt);
+		// ---- inner-node steps while enough lanes are at inner nodes
+		unsigned innerMask = __ballot_sync(0xffffffffu, L.node >= 0);
+		if (innerMask == 0u) continue;
+		const int keepGoing = max(1, (__popc(activeMask) * tune.minInner) >> 5);
+		do
+		{
+			if (L.node >= 0) wfInnerStep(L, s, stack, cnt);
+			innerMask = __ballot_sync(0xffffffffu, L.node >= 0);
+		} while (__popc(innerMask) >= keepGoing);
+	}
+}
+
+// Reference-order variant (GI_TRAVERSAL_REFERENCE): same work distribution, every lane walks its ray with the
+// stackless escape-pointer loop of traceray.glsl from start to end.
+template <class IO>
+GI_D void wfTraceLoopReference(const DScene& s, const IO& io, uint32_t* workCounter, unsigned* cnt)
+{
+	const uint32_t total = io.total();
+	for (;;)
+	{
+		uint32_t base = 0;
+		if (laneId() == 0) base = atomicAdd(workCounter, 32u);
+		base = __shfl_sync(0xffffffffu, base, 0);
+		if (base >= total) break;
+		const uint32_t mine = base + laneId();
+		if (mine < total)
+		{
+			WfLane L;
+			unsigned dummy[WFC_COUNT];
+			io.load(s, mine, L, dummy); // ray + root test (the walk below repeats the root test itself)
+			TraceStats st = {0, 0};
+			float len = L.tMaxInit; int leafTri = -1;
+			if (L.flags & WFL_ANY) { if (traceReference<true>(s, L.o, L.d, len, leafTri, &st)) L.flags |= WFL_OCCLUDED; }
+			else traceReference<false>(s, L.o, L.d, len, leafTri, &st);
+			cnt[WFC_NODES] += st.nodes; cnt[WFC_TRIS] += st.tris;
+			L.best = len; L.hitLeaf = leafTri; L.flags |= WFL_EXACT;
+			io.finish(s, L, cnt);
+		}
+	}
+}
+
+struct WfQueueIO
+{
+	WfTraceIO q;
+	GI_D uint32_t total() const { return q.numClosest + q.numShadow; }
+	GI_D void load(const DScene& s, uint32_t index, WfLane& L, unsigned* cnt) const
+	{
+		const bool isAny = index >= q.numClosest;
+		const F4* p = isAny ? q.shadow + 3 * size_t(index - q.numClosest) : q.rays + 2 * size_t(index);
+		const F4 r0 = ld4(p), r1 = ld4(p + 1);
+		wfBegin(L, s, f3(r0.x, r0.y, r0.z), f3(r1.x, r1.y, r1.z), r0.w, isAny, index, cnt);
+	}
+	GI_D void finish(const DScene& s, WfLane& L, unsigned* cnt) const
+	{
+		if (L.flags & WFL_ANY) wfFinishShadow(q, L.index - q.numClosest, (L.flags & WFL_OCCLUDED) != 0u);
+		else q.hits[L.index] = make_float2(L.best, i2f(L.hitLeaf));
+	}
+};
+
+// gi_trace_device: GiRay batch in, GiHit out (the parity / Mrays/s entry point).
+struct WfBatchIO
+{
+	const F4* rays;
+	float4* hits;
+	uint32_t n;
+	GI_D uint32_t total() const { return n; }
+	GI_D void load(const DScene& s, uint32_t index, WfLane& L, unsigned* cnt) const
+	{
+		const F4 r0 = ld4(rays + 2 * size_t(index)), r1 = ld4(rays + 2 * size_t(index) + 1);
+		wfBegin(L, s, f3(r0.x, r0.y, r0.z), f3(r1.x, r1.y, r1.z), r0.w, (uint32_t(f2i(r1.w)) & 1u) != 0u, index, cnt);
+	}
+	GI_D void finish(const DScene& s, WfLane& L, unsigned* cnt) const
+	{
+		++cnt[(L.flags & WFL_ANY) ? WFC_ANY : WFC_CLOSEST];
+		if (L.flags & WFL_ANY)
+		{
+			hits[L.index] = make_float4(L.tMaxInit, i2f((L.flags & WFL_OCCLUDED) ? 1 : 0), 0.0f, 0.0f);
+			return;
+		}
+		float4 out = make_float4(L.best, i2f(L.hitLeaf), 0.0f, 0.0f);
+		if (L.hitLeaf >= 0)
+		{
+			F3 p0, p1, p2; int valid;
+			loadLeafTri(s, L.hitLeaf, p0, p1, p2, valid);
+			float tt; F3 bary, nn;
+			intersectTriangle(L.o, L.d, p0, p1, p2, tt, bary, nn);
+			out.z = bary.y; out.w = bary.z;
+		}
+		hits[L.index] = out;
+	}
+};
+
+// ------------------------------------------------------------------ path tracer waves (pathtracer.comp:16-110)
+struct WfFrame
+{
+	DFrame f;
+	WfQueues q;
+	WfTune tune;
+	int tilesX, tilesY;      // W/8, H/8 work groups (pathtracer.cpp:50)
+	uint32_t numPaths;
+};
+
+// queue slot -> pixel: 8x8 tiles in row-major tile order, row-major inside the tile (the reference's work-group shape)
+GI_D uint32_t wfSlotToPixel(const WfFrame& w, uint32_t slot)
+{
+	const uint32_t tile = slot >> 6, l = slot & 63u;
+	const uint32_t tx = tile % uint32_t(w.tilesX), ty = tile / uint32_t(w.tilesX);
+	return (tx * 8u + (l & 7u)) + (ty * 8u + (l >> 3)) * uint32_t(w.f.width);
+}
+
+// Shades the hit of one extension ray of bounce `bounce`.  Returns nothing; pushes at most one shadow ray and one
+// extension ray (warp-compacted, so all 32 lanes call this; `valid` masks the tail).
+GI_D void wfShadePT(const WfFrame& w, int bounce, uint32_t slot, bool valid, unsigned* cnt)
+{
+	const DFrame& f = w.f;
+	const WfQueues& q = w.q;
+	bool pushShadow = false, pushRay = false;
+	DirectLightQuery nee;
+	F3 neeValue = f3(0.0f);
+	F3 origin = f3(0.0f), dir = f3(0.0f, 0.0f, 1.0f);
+	F3 color = f3(0.0f), pathThroughput = f3(1.0f);
+	uint32_t seed = 0, id = 0;
+	bool didNEE = false;
+	if (valid)
+	{
+		const F4* rp = q.rays[bounce & 1] + 2 * size_t(slot);
+		const F4 r0 = ld4(rp), r1 = ld4(rp + 1);
+		const float2 hrec = q.hits[slot];
+		const uint32_t word = uint32_t(f2i(r1.w));
+		id = word & WF_ID_MASK;
+		didNEE = (word & WF_FLAG_NEE) != 0u;
+		origin = f3(r0.x, r0.y, r0.z); dir = f3(r1.x, r1.y, r1.z);
+		if (bounce == 0)
+		{
+			seed = initRandomSeed(f.frameSeed, id);
+			random2(seed); // the two draws of the sub-pixel jitter (pathtracer.comp:42)
+		}
+		else
+		{
+			const float4 t = *reinterpret_cast<const float4*>(q.stateT + id);
+			const float4 c = *reinterpret_cast<const float4*>(q.stateC + id);
+			pathThroughput = f3(t.x, t.y, t.z); seed = uint32_t(f2i(t.w));
+			color = f3(c.x, c.y, c.z);
+		}
+		const float tHit = hrec.x;
+		const int leafTri = f2i(hrec.y);
+		bool terminated = true;
+		if (leafTri < 0)
+			color = color + pathThroughput * environmentRadiance(f, dir);
+		else
+		{
+			F3 p0, p1, p2; int tv;
+			loadLeafTri(f.scene, leafTri, p0, p1, p2, tv);
+			float tt; F3 bary, gn;
+			intersectTriangle(origin, dir, p0, p1, p2, tt, bary, gn);
+			const I4 tri = ld4(f.scene.leafTris + leafTri);
+			origin = origin + tHit * dir;
+			F3 hitNormal; F2 tc;
+			getTriangleHitInfo(f.scene, tri, bary, hitNormal, tc);
+			MaterialData md = sampleMaterialData(f.scene, tri.w, tc);
+			++cnt[WFC_SHADED];
+			if (!didNEE) color = color + pathThroughput * md.Emissivity;
+			didNEE = md.Reflectiveness.w < 500.0f;
+			{
+				const int sampleIndex = int(randomUInt(seed) % uint32_t(f.numLightSamples));
+				if (prepareDirectLight(f, origin, hitNormal, sampleIndex, dir, md, didNEE, nee))
+				{
+					pushShadow = true;
+					neeValue = nee.radiance * pathThroughput * float(f.numLightSamples);
+				}
+			}
+			F3 throughput = f3(1.0f);
+			float pdf;
+			dir = sampleBSDF(dir, md, seed, hitNormal, throughput, false, pdf);
+			origin = origin + dir * GI_RAY_HIT_EPSILON;
+			pathThroughput = pathThroughput * throughput;
+			const float cont = saturate(luminance(throughput));
+			if (!(randomFloat(seed) >= cont) && bounce + 1 < f.maxPathLength)
+			{
+				pathThroughput = pathThroughput / cont;
+				terminated = false;
+				pushRay = true;
+			}
+		}
+		if (terminated && !pushShadow)
+		{
+			// pixel-exclusive read-modify-write (pathtracer.comp:107-109), alpha += 0
+			float4* px = reinterpret_cast<float4*>(f.accum) + id;
+			float4 a = *px;
+			a.x += color.x; a.y += color.y; a.z += color.z;
+			*px = a;
+		}
+		else
+			*reinterpret_cast<float4*>(q.stateC + id) = make_float4(color.x, color.y, color.z, 0.0f);
+		if (pushRay) *reinterpret_cast<float4*>(q.stateT + id) = make_float4(pathThroughput.x, pathThroughput.y, pathThroughput.z, i2f(int(seed)));
+	}
+	uint32_t* counts = q.counts + WF_COUNTS_PER_BOUNCE * bounce;
+	const uint32_t sslot = warpPush(counts + 1, pushShadow);
+	if (pushShadow)
+	{
+		++cnt[WFC_ANY];
+		F4* sp = q.shadow + 3 * size_t(sslot);
+		const uint32_t word = id | (pushRay ? 0u : WF_FLAG_TERMINAL);
+		*reinterpret_cast<float4*>(sp) = make_float4(nee.origin.x, nee.origin.y, nee.origin.z, nee.len);
+		*reinterpret_cast<float4*>(sp + 1) = make_float4(nee.dir.x, nee.dir.y, nee.dir.z, i2f(int(word)));
+		*reinterpret_cast<float4*>(sp + 2) = make_float4(neeValue.x, neeValue.y, neeValue.z, 0.0f);
+	}
+	const uint32_t rslot = warpPush(counts + WF_COUNTS_PER_BOUNCE, pushRay);
+	if (pushRay)
+	{
+		++cnt[WFC_CLOSEST];
+		F4* rp = q.rays[(bounce + 1) & 1] + 2 * size_t(rslot);
+		const uint32_t word = id | (didNEE ? WF_FLAG_NEE : 0u);
+		*reinterpret_cast<float4*>(rp) = make_float4(origin.x, origin.y, origin.z, GI_RAY_MAX);
+		*reinterpret_cast<float4*>(rp + 1) = make_float4(dir.x, dir.y, dir.z, i2f(int(word)));
+	}
+}
+
+} // namespace gik

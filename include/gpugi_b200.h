@@ -163,7 +163,15 @@ enum {
 enum {
 	GI_OPT_TRAVERSAL = 0,       /* GI_TRAVERSAL_*                                                */
 	GI_OPT_TEXTURE_FILTER = 1,  /* 0 = hardware bilinear (9-bit weights), 1 = fp32 bilinear      */
-	GI_OPT_SCHEDULER = 2        /* 0 = wavefront (default when available), 1 = megakernel        */
+	GI_OPT_SCHEDULER = 2,       /* GI_SCHEDULER_*                                                */
+	/* tuning of the persistent wavefront trace kernel (defaults are the measured optimum) */
+	GI_OPT_WF_REFILL_THRESHOLD = 3, /* idle lanes per warp that trigger a refill from the ray queue  */
+	GI_OPT_WF_MIN_INNER = 4,        /* keep taking inner-node steps while this many of 32 active lanes are at inner nodes */
+	GI_OPT_WF_BLOCKS_PER_SM = 6     /* resident trace blocks per SM (0 = occupancy maximum)          */
+};
+enum {
+	GI_SCHEDULER_WAVEFRONT = 0, /* HBM ray queues, persistent trace warps, ballot-compacted waves (default; FAST traversal) */
+	GI_SCHEDULER_MEGAKERNEL = 1 /* one thread per path, the reference's launch shape               */
 };
 
 /* Per-iteration parameters: the compile-time #defines and small UBOs of the three renderers. */

@@ -5,6 +5,7 @@
 // (libgpugi_b200.so) fails without a device.
 #include "../../gpugi_b200/csrc/gi_core.h"
 #include "../../gpugi_b200/csrc/gi_layout.h"
+#include "../../gpugi_b200/csrc/gi_lane.h"
 
 #include <cstring>
 #include <vector>
@@ -31,6 +32,7 @@ bool makeScene(const GiSceneDesc* d, EmScene& e, std::string& err)
 	e.s.vertexInfo = e.L.vertexInfo.data();
 	e.s.materials = e.L.materials.data();
 	e.s.texels = e.L.texels.data();
+	e.s.leafNode = e.L.leafNode.data();
 	e.s.textureFilterExact = 1;
 	return true;
 }
@@ -50,7 +52,9 @@ static void addCounters(EmCounters* out, const PathCounters& pc, const TraceStat
 	out->node_tests += st.nodes; out->tri_tests += st.tris;
 }
 
-// k_trace, one "thread" per ray.  mode: GI_TRAVERSAL_*.  Returns 0, or 1 if the scene is rejected.
+#define EM_MODE_LANE 2 // the wavefront lane state machine (gi_lane.h) instead of traceFast()
+
+// k_trace, one "thread" per ray.  mode: GI_TRAVERSAL_* or EM_MODE_LANE.  Returns 0, or 1 if the scene is rejected.
 EM_API int em_trace(const GiSceneDesc* desc, const GiRay* rays, uint32_t n, GiHit* hits, int mode, int* fast_valid, EmCounters* counters)
 {
 	EmScene e; std::string err;
@@ -63,7 +67,29 @@ EM_API int em_trace(const GiSceneDesc* desc, const GiRay* rays, uint32_t n, GiHi
 		TraceStats st = {0, 0};
 		const F3 o = f3(rays[i].origin), d = f3(rays[i].direction);
 		GiHit out;
-		if (rays[i].flags & 1u)
+		if (mode == EM_MODE_LANE)
+		{
+			unsigned cnt[WFC_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+			WfLane L;
+			const bool isAny = (rays[i].flags & 1u) != 0u;
+			wfWalkSingle(L, e.s, o, d, rays[i].t_max, isAny, cnt);
+			if (isAny) { ++pc.anyRays; out.t = rays[i].t_max; out.leaf_tri = (L.flags & WFL_OCCLUDED) ? 1 : 0; out.bary_y = 0.0f; out.bary_z = 0.0f; }
+			else
+			{
+				++pc.closestRays;
+				out.t = L.best; out.leaf_tri = L.hitLeaf; out.bary_y = 0.0f; out.bary_z = 0.0f;
+				if (L.hitLeaf >= 0)
+				{
+					F3 p0, p1, p2; int valid;
+					loadLeafTri(e.s, L.hitLeaf, p0, p1, p2, valid);
+					float tt; F3 bary, nn;
+					intersectTriangle(o, d, p0, p1, p2, tt, bary, nn);
+					out.bary_y = bary.y; out.bary_z = bary.z;
+				}
+			}
+			pc.fallbackRays += cnt[WFC_FALLBACK]; st.nodes += cnt[WFC_NODES]; st.tris += cnt[WFC_TRIS];
+		}
+		else if (rays[i].flags & 1u)
 		{
 			++pc.anyRays;
 			bool occ = traceAny(e.s, mode, o, d, rays[i].t_max, &st);

@@ -8,10 +8,10 @@ import pytest
 from tests.conftest import assert_hits_equal, camera_ray_batch, make_ray_batch
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-FAST, REFERENCE = 0, 1
+FAST, REFERENCE, LANE = 0, 1, 2  # LANE: the per-lane state machine of the wavefront trace kernel (gi_lane.h)
 
 
-@pytest.mark.parametrize("mode", [FAST, REFERENCE])
+@pytest.mark.parametrize("mode", [FAST, REFERENCE, LANE])
 def test_trace_parity_box1(g, orc, emul, scenes, box1, mode):
     C = scenes.BOX1_CAMERA
     rays = np.concatenate([camera_ray_batch(g, orc, box1, C["pos"], C["lookat"], C["fov"], 64, 64, 1), make_ray_batch(g, box1, 20000, 2)])
@@ -22,14 +22,14 @@ def test_trace_parity_box1(g, orc, emul, scenes, box1, mode):
         assert cnt["fallback_rays"] == 0
 
 
-@pytest.mark.parametrize("mode", [FAST, REFERENCE])
+@pytest.mark.parametrize("mode", [FAST, REFERENCE, LANE])
 def test_trace_parity_golden_file(emul, box1, mode):
     z = np.load(os.path.join(GOLDEN, "box1_rays.npz"))
     hits, _ = emul.trace(box1.desc, z["rays"], mode)
     assert_hits_equal(hits, z["hits"], "golden mode %d" % mode)
 
 
-@pytest.mark.parametrize("mode", [FAST, REFERENCE])
+@pytest.mark.parametrize("mode", [FAST, REFERENCE, LANE])
 @pytest.mark.parametrize("build", ["sah", "kd"])
 def test_trace_parity_random_triangles(g, orc, emul, scenes, mode, build):
     """Overlapping slivers: the adversarial case for visit-order dependence."""
@@ -51,9 +51,11 @@ def test_trace_parity_exact_ties(g, orc, emul, box1_coincident):
     d = rng.randn(n, 3); d[:, 1] = -np.abs(d[:, 1]) - 0.2
     rays["direction"] = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
     rays["t_max"] = np.float32(g.RAY_MAX)
-    hits, cnt = emul.trace(box1_coincident.desc, rays, FAST)
-    assert_hits_equal(hits, orc.trace_batch(box1_coincident.desc, rays), "ties")
-    assert cnt["fallback_rays"] > n // 4  # the ties really occur and are resolved by the exact re-trace
+    ref = orc.trace_batch(box1_coincident.desc, rays)
+    for mode in (FAST, LANE):
+        hits, cnt = emul.trace(box1_coincident.desc, rays, mode)
+        assert_hits_equal(hits, ref, "ties mode %d" % mode)
+        assert cnt["fallback_rays"] > n // 4  # the ties really occur and are resolved by the exact re-trace / the collecting pass
 
 
 def test_trace_edges_and_vertices(g, orc, emul, box1):
@@ -81,7 +83,7 @@ def test_trace_edges_and_vertices(g, orc, emul, box1):
     flat["direction"] = (dd / np.linalg.norm(dd, axis=1, keepdims=True)).astype(np.float32)
     flat["t_max"] = np.float32(g.RAY_MAX)
     rays = np.concatenate([rays, flat])
-    for mode in (FAST, REFERENCE):
+    for mode in (FAST, REFERENCE, LANE):
         hits, _ = emul.trace(box1.desc, rays, mode)
         assert_hits_equal(hits, orc.trace_batch(box1.desc, rays), "edges mode %d" % mode)
 
@@ -96,7 +98,7 @@ def test_trace_finite_closest_length(g, orc, emul, box1):
         rays["t_max"][2000:4000] = np.nextafter(t[2000:4000], np.float32(np.inf))
     rays["t_max"][4000:] = t[4000:] * np.float32(0.5)
     rays["t_max"][~np.isfinite(rays["t_max"])] = np.float32(10.0)
-    for mode in (FAST, REFERENCE):
+    for mode in (FAST, REFERENCE, LANE):
         hits, _ = emul.trace(box1.desc, rays, mode)
         assert_hits_equal(hits, orc.trace_batch(box1.desc, rays), "finite length mode %d" % mode)
 
@@ -117,15 +119,28 @@ def test_trace_empty_batch_and_deep_tree(g, orc, emul, scenes):
     deep = g.Scene.from_mesh(pos, np.tile(np.float32([0, 1, 0]), (3 * n, 1)), np.zeros((3 * n, 2), np.float32), tri, np.zeros(n, np.uint32),
                              {"m": scenes.legacy_material()})
     rays = make_ray_batch(g, deep, 3000, 6)
-    hits, cnt = emul.trace(deep.desc, rays, FAST)
-    assert_hits_equal(hits, orc.trace_batch(deep.desc, rays), "deep tree (levels=%d)" % deep.info.num_tree_levels)
+    for mode in (FAST, LANE):
+        hits, cnt = emul.trace(deep.desc, rays, mode)
+        assert_hits_equal(hits, orc.trace_batch(deep.desc, rays), "deep tree (levels=%d) mode %d" % (deep.info.num_tree_levels, mode))
+
+
+def test_lane_parity_sponza_mix(g, orc, emul, scenes, tmp_path):
+    """The wavefront lane logic on the Sponza-shaped scene: primary / secondary / shadow rays, 2^17 rays.  This mix holds
+    leaves whose two triangles are hit at (almost) the same distance with a box entry distance rounded beyond them."""
+    sc = scenes.make_sponza_like(str(tmp_path), texture_size=32)
+    C = scenes.SPONZA_CAMERA
+    rays = camera_ray_batch(g, orc, sc, C["pos"], C["lookat"], C["fov"], 224, 126, 4)
+    rays = np.concatenate([rays, make_ray_batch(g, sc, (1 << 17) - len(rays), 5)])
+    hits, cnt = emul.trace(sc.desc, rays, LANE)
+    assert_hits_equal(hits, orc.trace_batch(sc.desc, rays), "sponza lane")
+    assert cnt["fallback_rays"] > 0
 
 
 def _light_sampler(orc, sc):
     return orc.LightSampler(sc.positions(), sc.triangles(), sc.triangle_materials(), sc.emissivity(), sc.point_lights())
 
 
-@pytest.mark.parametrize("mode", [FAST, REFERENCE])
+@pytest.mark.parametrize("mode", [FAST, REFERENCE, LANE])
 def test_pathtracer_matches_oracle(orc, emul, scenes, box1, mode):
     W = H = 48
     C = scenes.BOX1_CAMERA
