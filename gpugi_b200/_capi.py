@@ -102,7 +102,7 @@ GI_OK = 0
 GI_RENDERER_PT, GI_RENDERER_LPT, GI_RENDERER_BPT = 0, 1, 2
 GI_TRAVERSAL_FAST, GI_TRAVERSAL_REFERENCE = 0, 1
 GI_OPT_TRAVERSAL, GI_OPT_TEXTURE_FILTER, GI_OPT_SCHEDULER = 0, 1, 2
-GI_OPT_WF_REFILL_THRESHOLD, GI_OPT_WF_MIN_INNER, GI_OPT_WF_BLOCKS_PER_SM = 3, 4, 6
+GI_OPT_WF_REFILL_THRESHOLD, GI_OPT_WF_MIN_INNER, GI_OPT_WF_BLOCKS_PER_SM, GI_OPT_COUNT_STEPS = 3, 4, 6, 7
 GI_SCHEDULER_WAVEFRONT, GI_SCHEDULER_MEGAKERNEL = 0, 1
 GI_TEX_SRGB8_ALPHA8, GI_TEX_RGBA8, GI_TEX_RGBA32F = 0, 1, 2
 RAY_MAX = 3.402823466e+38

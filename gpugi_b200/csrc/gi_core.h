@@ -70,6 +70,23 @@ GI_HD float saturate(float x) { return fminf(fmaxf(x, 0.0f), 1.0f); }
 GI_HD F3 saturate(F3 a) { return f3(saturate(a.x), saturate(a.y), saturate(a.z)); }
 GI_HD float sign(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f); }
 
+struct alignas(32) U8 { uint32_t v[8]; };
+
+#if defined(__CUDA_ARCH__)
+// 256-bit global load (sm_100: LDG.E.256): a scattered 32-byte record costs one L1 wavefront per lane instead of two
+// (tools/gpu/micro/gather.cu: 31 vs 70 cycles per warp for an L2-resident table).  p must be 32-byte aligned.
+GI_HD U8 ld8(const void* p)
+{
+	U8 r;
+	asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	             : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+	             : "l"(p));
+	return r;
+}
+#else
+GI_HD U8 ld8(const void* p) { U8 r; __builtin_memcpy(&r, p, 32); return r; }
+#endif
+
 #if defined(__CUDA_ARCH__)
 GI_HD F4 ld4(const F4* p) { float4 v = __ldg(reinterpret_cast<const float4*>(p)); F4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w; return r; }
 GI_HD I4 ld4(const I4* p) { int4 v = __ldg(reinterpret_cast<const int4*>(p)); I4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w; return r; }
@@ -81,6 +98,18 @@ GI_HD I4 ld4(const I4* p) { return *p; }
 GI_HD int f2i(float f) { int i; __builtin_memcpy(&i, &f, 4); return i; }
 GI_HD float i2f(int i) { float f; __builtin_memcpy(&f, &i, 4); return f; }
 #endif
+
+// 96 bytes (6 x F4) with three 256-bit loads
+GI_HD void ld8x3(const F4* p, F4* out)
+{
+	const U8 a = ld8(p), b = ld8(p + 2), c = ld8(p + 4);
+	out[0].x = i2f(int(a.v[0])); out[0].y = i2f(int(a.v[1])); out[0].z = i2f(int(a.v[2])); out[0].w = i2f(int(a.v[3]));
+	out[1].x = i2f(int(a.v[4])); out[1].y = i2f(int(a.v[5])); out[1].z = i2f(int(a.v[6])); out[1].w = i2f(int(a.v[7]));
+	out[2].x = i2f(int(b.v[0])); out[2].y = i2f(int(b.v[1])); out[2].z = i2f(int(b.v[2])); out[2].w = i2f(int(b.v[3]));
+	out[3].x = i2f(int(b.v[4])); out[3].y = i2f(int(b.v[5])); out[3].z = i2f(int(b.v[6])); out[3].w = i2f(int(b.v[7]));
+	out[4].x = i2f(int(c.v[0])); out[4].y = i2f(int(c.v[1])); out[4].z = i2f(int(c.v[2])); out[4].w = i2f(int(c.v[3]));
+	out[5].x = i2f(int(c.v[4])); out[5].y = i2f(int(c.v[5])); out[5].z = i2f(int(c.v[6])); out[5].w = i2f(int(c.v[7]));
+}
 
 // ------------------------------------------------------------------ device scene view (DESIGN.md "HBM layout")
 // Material record: the 64-byte Scene::Material (scene.hpp:79-89) with the bindless handles replaced by
@@ -109,12 +138,17 @@ struct DScene
 	const F4* refNodes;      // 2 x F4 per node: (min.xyz, firstChild bits), (max.xyz, escape bits)
 	// fast layout: one 64-byte record per inner node holding BOTH child boxes
 	const F4* fastNodes;     // 4 x F4: (c0.min.xyz, c0.max.x) (c0.max.yz, c1.min.xy) (c1.min.z, c1.max.xyz) (child0, child1, -, -)
-	const F4* leafPos;       // 6 x F4 per leaf: slot s -> [3s] = (p0.xyz, valid?1:0 as int bits), [3s+1] = (p1.xyz, -), [3s+2] = (p2.xyz, -)
+	const uint32_t* qNodes;  // wavefront walk: 8 words (32 bytes, one 256-bit load) per INNER node: both child boxes on a 16-bit grid over
+	                         // the root box, rounded outwards, min | max << 16 per axis: (c0.x, c0.y, c0.z, c1.x, c1.y, c1.z, child0, child1)
+	float gridLo[3];         // grid origin (root box min) and cell size per axis
+	float gridScale[3];
+	const F4* leafPos;       // 6 x F4 per leaf: slot s -> [3s] = (p0.xyz, .), [3s+1] = (p1.xyz, .), [3s+2] = (p2.xyz, .); an unused slot has
+	                         // p0.x = NaN (vertex positions are checked to be finite at upload).  The six .w hold the leaf node's own box:
+	                         // [0..2].w = box.min.xyz, [3..5].w = box.max.xyz
 	const I4* leafTris;      // GiTriangle per leaf slot (v0, v1, v2, material)
 	const F4* vertexInfo;    // GiVertexInfo per vertex
 	const DMaterial* materials;
 	const DTexel* texels;    // 4 per material, same order as DMaterial::tex (fp32 filter / emulation)
-	const uint32_t* leafNode; // reference node index of every leaf (its own box: the reference's cull test for the leaf)
 	int leafPreorder;        // leaf indices increase in the reference's preorder walk (tie-break order == leaf slot order)
 	uint32_t numNodes;
 	uint32_t numLeafTris;
@@ -184,7 +218,7 @@ GI_HD void loadLeafTri(const DScene& s, int leafTri, F3& p0, F3& p1, F3& p2, int
 	const F4* p = s.leafPos + 3 * size_t(leafTri);
 	F4 a = ld4(p), b = ld4(p + 1), c = ld4(p + 2);
 	p0 = f3(a.x, a.y, a.z); p1 = f3(b.x, b.y, b.z); p2 = f3(c.x, c.y, c.z);
-	valid = f2i(a.w);
+	valid = (a.x == a.x) ? 1 : 0;
 }
 
 // ------------------------------------------------------------------ reference-order traversal (traceray.glsl:25-180)

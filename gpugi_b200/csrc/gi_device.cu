@@ -126,6 +126,9 @@ __global__ void k_reset_counter(uint32_t* lightCacheCount, uint32_t* lightPathLe
 
 // ---- wavefront scheduler (gi_wavefront.cuh) -------------------------------------------------------------
 #define WF_TRACE_THREADS 128
+#ifndef WF_TRACE_MIN_BLOCKS
+#define WF_TRACE_MIN_BLOCKS 8
+#endif
 #define WF_SHADE_THREADS 128
 
 // Camera rays of all W/8 x H/8 work groups (pathtracer.comp:36-46) into the extension queue of bounce 0.
@@ -151,8 +154,8 @@ __global__ void __launch_bounds__(256) k_wf_generate(WfFrame w, unsigned long lo
 }
 
 // trace(b): extension rays of bounce b + shadow rays pushed by shade(b-1); persistent warps, dynamic refill.
-template <bool REFERENCE>
-__global__ void __launch_bounds__(WF_TRACE_THREADS) k_wf_trace(WfFrame w, int bounce, unsigned long long* counters)
+template <bool REFERENCE, bool STEPS>
+__global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MIN_BLOCKS) k_wf_trace(WfFrame w, int bounce, unsigned long long* counters)
 {
 	WfQueueIO io;
 	io.q.rays = w.q.rays[bounce & 1];
@@ -163,23 +166,24 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS) k_wf_trace(WfFrame w, int bo
 	io.q.width = w.f.width; io.q.height = w.f.height;
 	io.q.numClosest = bounce < w.f.maxPathLength ? w.q.counts[WF_COUNTS_PER_BOUNCE * bounce] : 0u;
 	io.q.numShadow = bounce > 0 ? w.q.counts[WF_COUNTS_PER_BOUNCE * (bounce - 1) + 1] : 0u;
-	unsigned cnt[WFC_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+	WfCounters<STEPS> cnt;
 	if (REFERENCE) wfTraceLoopReference(w.f.scene, io, w.q.counts + WF_COUNTS_PER_BOUNCE * bounce + 2, cnt);
 	else wfTraceLoop(w.f.scene, io, w.q.counts + WF_COUNTS_PER_BOUNCE * bounce + 2, w.tune, cnt);
-	flushWarpCounters(counters, cnt, WFC_COUNT);
+	flushWarpCounters(counters, cnt.v, WFC_COUNT);
 }
 
 // gi_trace_device on the same persistent loop.
-__global__ void __launch_bounds__(WF_TRACE_THREADS) k_wf_trace_batch(DScene s, const GiRay* __restrict__ rays, uint32_t n, GiHit* __restrict__ hits, WfTune tune,
+template <bool STEPS>
+__global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MIN_BLOCKS) k_wf_trace_batch(DScene s, const GiRay* __restrict__ rays, uint32_t n, GiHit* __restrict__ hits, WfTune tune,
                                                                       uint32_t* workCounter, unsigned long long* counters)
 {
 	WfBatchIO io;
 	io.rays = reinterpret_cast<const F4*>(rays);
 	io.hits = reinterpret_cast<float4*>(hits);
 	io.n = n;
-	unsigned cnt[WFC_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+	WfCounters<STEPS> cnt;
 	wfTraceLoop(s, io, workCounter, tune, cnt);
-	flushWarpCounters(counters, cnt, WFC_COUNT);
+	flushWarpCounters(counters, cnt.v, WFC_COUNT);
 }
 
 // shade(b) of the path tracer: one lane per hit record, 32 consecutive queue slots per warp and fetch.
@@ -270,6 +274,7 @@ struct GiContext
 	int traversal = GI_TRAVERSAL_FAST;
 	int textureFilterExact = 0;
 	int scheduler = GI_SCHEDULER_WAVEFRONT;
+	int countSteps = 0;              // GI_OPT_COUNT_STEPS
 	WfTune tune = {16, 20, 0};
 
 	// wavefront queues
@@ -407,8 +412,9 @@ static int renderWavefrontPT(GiContext* c, const DFrame& f)
 	};
 	const bool ref = f.traversalMode == GI_TRAVERSAL_REFERENCE;
 	auto trace = [&](int b) {
-		if (ref) k_wf_trace<true><<<traceGrid, WF_TRACE_THREADS, 0, c->stream>>>(w, b, c->counters);
-		else k_wf_trace<false><<<traceGrid, WF_TRACE_THREADS, 0, c->stream>>>(w, b, c->counters);
+		if (ref) k_wf_trace<true, true><<<traceGrid, WF_TRACE_THREADS, 0, c->stream>>>(w, b, c->counters);
+		else if (c->countSteps) k_wf_trace<false, true><<<traceGrid, WF_TRACE_THREADS, 0, c->stream>>>(w, b, c->counters);
+		else k_wf_trace<false, false><<<traceGrid, WF_TRACE_THREADS, 0, c->stream>>>(w, b, c->counters);
 		++c->launches;
 		mark("trace", b);
 	};
@@ -481,7 +487,7 @@ int gi_create(int device, GiContext** out_ctx)
 	if (!ok) { gi_destroy(c); return fail(nullptr, GI_ERR_CUDA, "gi_create: device allocation failed"); }
 	// persistent kernels: one resident wave, grid = SMs x resident blocks per SM
 	c->numSMs = prop.multiProcessorCount;
-	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->traceBlocksPerSM, k_wf_trace<false>, WF_TRACE_THREADS, 0);
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->traceBlocksPerSM, k_wf_trace<false, false>, WF_TRACE_THREADS, 0);
 	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->shadeBlocksPerSM, k_wf_shade_pt, WF_SHADE_THREADS, 0);
 	c->traceBlocksPerSM = std::max(c->traceBlocksPerSM, 1);
 	c->shadeBlocksPerSM = std::max(c->shadeBlocksPerSM, 1);
@@ -524,11 +530,12 @@ int gi_set_option(GiContext* c, int option, int value)
 	case GI_OPT_SCHEDULER:
 		if (value != GI_SCHEDULER_WAVEFRONT && value != GI_SCHEDULER_MEGAKERNEL) return fail(c, GI_ERR_INVALID, "GI_OPT_SCHEDULER: unknown scheduler");
 		c->scheduler = value; return GI_OK;
+	case GI_OPT_COUNT_STEPS: c->countSteps = value ? 1 : 0; return GI_OK;
 	case GI_OPT_WF_REFILL_THRESHOLD: c->tune.refillThreshold = std::min(std::max(value, 1), 32); return GI_OK;
 	case GI_OPT_WF_MIN_INNER: c->tune.minInner = std::min(std::max(value, 1), 32); return GI_OK;
 	case GI_OPT_WF_BLOCKS_PER_SM:
 		if (value > 0) c->traceBlocksPerSM = value;
-		else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->traceBlocksPerSM, k_wf_trace<false>, WF_TRACE_THREADS, 0);
+		else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->traceBlocksPerSM, k_wf_trace<false, false>, WF_TRACE_THREADS, 0);
 		return GI_OK;
 	}
 	return fail(c, GI_ERR_INVALID, "gi_set_option: unknown option");
@@ -604,9 +611,9 @@ int gi_upload_scene(GiContext* c, const GiSceneDesc* d)
 	DScene s = L.scene;
 	GI_CUDA(c, uploadVector(c, L.refNodes, &s.refNodes));
 	GI_CUDA(c, uploadVector(c, L.fastNodes, &s.fastNodes));
+	GI_CUDA(c, uploadVector(c, L.qNodes, &s.qNodes));
 	GI_CUDA(c, uploadVector(c, L.leafPos, &s.leafPos));
 	GI_CUDA(c, uploadVector(c, L.leafTris, &s.leafTris));
-	GI_CUDA(c, uploadVector(c, L.leafNode, &s.leafNode));
 	GI_CUDA(c, uploadVector(c, L.vertexInfo, &s.vertexInfo));
 	GI_CUDA(c, uploadVector(c, L.materials, &s.materials));
 	GI_CUDA(c, uploadVector(c, L.texels, &s.texels));
@@ -816,7 +823,8 @@ int gi_trace_device(GiContext* c, const GiRay* d_rays, uint32_t n, GiHit* d_hits
 	{
 		GI_CUDA(c, cudaMemsetAsync(c->traceWork, 0, sizeof(uint32_t), c->stream));
 		const unsigned grid = std::min(unsigned(c->numSMs * c->traceBlocksPerSM), (n + WF_TRACE_THREADS - 1) / WF_TRACE_THREADS);
-		k_wf_trace_batch<<<grid, WF_TRACE_THREADS, 0, c->stream>>>(s, d_rays, n, d_hits, c->tune, c->traceWork, c->counters);
+		if (c->countSteps) k_wf_trace_batch<true><<<grid, WF_TRACE_THREADS, 0, c->stream>>>(s, d_rays, n, d_hits, c->tune, c->traceWork, c->counters);
+		else k_wf_trace_batch<false><<<grid, WF_TRACE_THREADS, 0, c->stream>>>(s, d_rays, n, d_hits, c->tune, c->traceWork, c->counters);
 		++c->launches;
 	}
 	else

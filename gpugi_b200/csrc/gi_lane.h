@@ -10,6 +10,15 @@ namespace gik {
 // per-thread work counters, flushed per warp at kernel end (order of GiCounters / CNT_* in gi_device.cu)
 enum { WFC_CLOSEST = 0, WFC_ANY, WFC_CAMERA, WFC_LIGHT, WFC_SHADED, WFC_SPLATS, WFC_FALLBACK, WFC_NODES, WFC_TRIS, WFC_COUNT };
 
+// STEPS = false drops the box / triangle test counters (GiCounters::node_tests, triangle_tests) from the hot loop.
+template <bool STEPS>
+struct WfCounters
+{
+	unsigned v[WFC_COUNT];
+	GI_HD WfCounters() { for (int i = 0; i < WFC_COUNT; ++i) v[i] = 0u; }
+	template <int I> GI_HD void add(unsigned n) { if (STEPS || (I != WFC_NODES && I != WFC_TRIS)) v[I] += n; }
+};
+
 // ------------------------------------------------------------------ trace core
 // Per-lane traversal state of the persistent trace kernels.  The arithmetic and the culling rules are those of
 // traceFast() in gi_core.h, cut into single steps so that a warp can interleave rays.
@@ -34,7 +43,13 @@ struct WfCand { float t, first; int leaf; };
 
 struct WfLane
 {
-	F3 o, d, inv;
+	F3 o, d;
+	// conservative inner-node test on the 16-bit grid (wfSlabTest): distance of grid plane q along axis k
+	//   near planes  fma(2^23 + q, cellInv.k, biasNear.k)      far planes  fma(2^23 + q, cellInv.k, biasFar.k)
+	F3 cellInv;      // cell size * (1/d)
+	F3 biasNear;     // (gridLo - o) * (1/d) - 2^23 * cellInv -/+ error bound
+	F3 biasFar;
+	uint32_t selNear[3], selFar[3]; // byte-permute selectors: which 16-bit half of a node word is the near / far plane (sign of d)
 	float tMaxInit, best, second;
 	float limit;     // culling limit for box entry distances
 	int hitLeaf;
@@ -62,32 +77,129 @@ GI_HD void wfPop(WfLane& L, const StackEntry* stack)
 	}
 }
 
-GI_HD void wfBegin(WfLane& L, const DScene& s, F3 o, F3 d, float tMax, bool isAny, uint32_t index, unsigned* cnt)
+// ---- conservative slab test on the quantised child boxes
+// A child box is stored on a 16-bit grid over the root box, rounded outwards: plane q of axis k lies at gridLo.k + q * cell.k
+// (real numbers; checked in double at upload).  Per axis one 32-bit word: min plane in the low half, max plane in the high half.
+// A coordinate becomes a float with ONE byte-permute, no conversion and no mask: bytes (q.lo, q.hi, 0x00, 0x4B) are the float
+// 2^23 + q.  Which half is the ray's near plane depends only on the sign of the direction, so the selector is per-ray state.
+//
+// Error bound (u = 2^-24, all symbols per axis).  True distance of plane q: T = (gridLo + q*cell - o) * inv.  Computed:
+//   S = fl(cell * inv)   B0 = fl(fl(gridLo - o) * inv)   b = fl(B0 - 2^23*S)   b' = fl(b -/+ E)   t = fl((2^23 + q) * S + b')   (one FMA)
+//   |(2^23+q)*S + b - T| <= u*2^16*|S| + 3.02u*|B| + u*(|B0| + 2^23*|S|)      (B = (gridLo - o) * inv)
+//   rounding of b'        <= u*(|B0| + 2^23*|S| + E)
+//   rounding of the FMA   <= u*(|B| + 2^16*|S|) (1 + ...)
+//   the exact-zone value the reference computes for a plane p of the real box, fl(inv * fl(p - o)), differs from its
+//   real-number value by <= 2.01u*(|B| + 2^16*|S|)
+// in total <= 1.016*|S| + 7.04u*|B| + u*E  <  E := 1.02*|S| + 7.5u*|B0|: about one grid cell.  Hence
+//   near.k <= tmin.k and far.k >= tmax.k of IntersectBox (intersectiontests.glsl:12-15) for every box inside its grid box, and
+//   (first <= last && first <= limit)  ==>  wfSlabTest accepts.
+// Rays with a zero / denormal direction component or products near overflow are outside the bound's domain (inf - inf,
+// 0 * inf): they are answered by the stackless reference walk (WFL_OVERFLOW).
+#define WF_SEL_LO 0x7610u
+#define WF_SEL_HI 0x7632u
+
+GI_HD float wfFma(float a, float b, float c)
 {
-	L.o = o; L.d = d; L.inv = invDir(d);
+#if defined(__CUDA_ARCH__)
+	return __fmaf_rn(a, b, c);
+#else
+	return fmaf(a, b, c);
+#endif
+}
+
+GI_HD float wfPlane(uint32_t word, uint32_t sel)
+{
+#if defined(__CUDA_ARCH__)
+	return __uint_as_float(__byte_perm(word, 0x4B000000u, sel));
+#else
+	const uint32_t q = (sel == WF_SEL_LO) ? (word & 0xffffu) : (word >> 16);
+	return i2f(int(0x4B000000u | q));
+#endif
+}
+
+GI_HD float wfMax3(float a, float b, float c)
+{
+#if defined(__CUDA_ARCH__)
+	float r; asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r;
+#else
+	return fmaxf(fmaxf(a, b), c);
+#endif
+}
+GI_HD float wfMin3(float a, float b, float c)
+{
+#if defined(__CUDA_ARCH__)
+	float r; asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r;
+#else
+	return fminf(fminf(a, b), c);
+#endif
+}
+
+// Per-ray constants of the conservative test.  Returns false when the ray is outside the domain of the error bound.
+GI_HD bool wfSlabSetup(WfLane& L, const DScene& s, F3 o, F3 inv)
+{
+	const float u = 5.9604644775390625e-08f; // 2^-24
+	const float S[3] = {s.gridScale[0] * inv.x, s.gridScale[1] * inv.y, s.gridScale[2] * inv.z};
+	const float B0[3] = {(s.gridLo[0] - o.x) * inv.x, (s.gridLo[1] - o.y) * inv.y, (s.gridLo[2] - o.z) * inv.z};
+	float bn[3], bf[3], m = 0.0f;
+	for (int k = 0; k < 3; ++k)
+	{
+		const float b = B0[k] - 8388608.0f * S[k];
+		const float E = 1.02f * fabsf(S[k]) + (7.5f * u) * fabsf(B0[k]) + 1.0e-37f;
+		bn[k] = b - E; bf[k] = b + E;
+		m = fmaxf(m, 16777216.0f * fabsf(S[k]) + fabsf(B0[k]));
+	}
+	L.cellInv = f3(S[0], S[1], S[2]);
+	L.biasNear = f3(bn[0], bn[1], bn[2]);
+	L.biasFar = f3(bf[0], bf[1], bf[2]);
+	L.selNear[0] = inv.x < 0.0f ? WF_SEL_HI : WF_SEL_LO; L.selFar[0] = inv.x < 0.0f ? WF_SEL_LO : WF_SEL_HI;
+	L.selNear[1] = inv.y < 0.0f ? WF_SEL_HI : WF_SEL_LO; L.selFar[1] = inv.y < 0.0f ? WF_SEL_LO : WF_SEL_HI;
+	L.selNear[2] = inv.z < 0.0f ? WF_SEL_HI : WF_SEL_LO; L.selFar[2] = inv.z < 0.0f ? WF_SEL_LO : WF_SEL_HI;
+	return m < 1.0e30f; // false for NaN / inf as well
+}
+
+template <class CNT>
+GI_HD void wfBegin(WfLane& L, const DScene& s, F3 o, F3 d, float tMax, bool isAny, uint32_t index, CNT& cnt)
+{
+	const F3 inv = invDir(d);
+	L.o = o; L.d = d;
 	L.tMaxInit = tMax; L.best = tMax; L.second = GI_INF;
 	L.limit = isAny ? tMax : wfClosestLimit(tMax, s);
 	L.hitLeaf = -1; L.sp = 0; L.index = index;
 	L.flags = isAny ? WFL_ANY : 0u; L.numCand = 0;
+	const bool inDomain = wfSlabSetup(L, s, o, inv);
 	// root box first, as the reference does (traceray.glsl:56-69)
 	F4 a = ld4(s.refNodes), b = ld4(s.refNodes + 1);
 	float f, l;
-	++cnt[WFC_NODES];
-	if (intersectBox(o, L.inv, a.x, a.y, a.z, b.x, b.y, b.z, f, l) && f <= tMax) L.node = s.rootIsLeaf ? ~0 : 0;
+	cnt.template add<WFC_NODES>(1u);
+	if (intersectBox(o, inv, a.x, a.y, a.z, b.x, b.y, b.z, f, l) && f <= tMax) L.node = s.rootIsLeaf ? ~0 : 0;
 	else L.node = WF_NODE_DONE;
+	if (!inDomain && L.node != WF_NODE_DONE) { L.flags |= WFL_OVERFLOW; L.node = WF_NODE_DONE; }
 }
 
-GI_HD void wfInnerStep(WfLane& L, const DScene& s, StackEntry* stack, unsigned* cnt)
+// Conservative accept test of one child box (three words: x, y, z; min plane | max plane << 16): never rejects a box the
+// exact-zone test (first <= last && first <= limit) accepts.  nearLow is a lower bound of the exact-zone entry distance.
+GI_HD bool wfSlabTest(const WfLane& L, uint32_t wx, uint32_t wy, uint32_t wz, float& nearLow)
 {
-	const F4* p = s.fastNodes + 4 * size_t(L.node);
-	const F4 n0 = ld4(p), n1 = ld4(p + 1), n2 = ld4(p + 2), n3 = ld4(p + 3);
-	cnt[WFC_NODES] += 2;
-	float f0, l0, f1, l1;
-	bool h0 = intersectBox(L.o, L.inv, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, f0, l0);
-	bool h1 = intersectBox(L.o, L.inv, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, f1, l1);
-	h0 = h0 && f0 <= L.limit;
-	h1 = h1 && f1 <= L.limit;
-	int c0 = f2i(n3.x), c1 = f2i(n3.y);
+	const float nx = wfFma(wfPlane(wx, L.selNear[0]), L.cellInv.x, L.biasNear.x);
+	const float ny = wfFma(wfPlane(wy, L.selNear[1]), L.cellInv.y, L.biasNear.y);
+	const float nz = wfFma(wfPlane(wz, L.selNear[2]), L.cellInv.z, L.biasNear.z);
+	const float fx = wfFma(wfPlane(wx, L.selFar[0]), L.cellInv.x, L.biasFar.x);
+	const float fy = wfFma(wfPlane(wy, L.selFar[1]), L.cellInv.y, L.biasFar.y);
+	const float fz = wfFma(wfPlane(wz, L.selFar[2]), L.cellInv.z, L.biasFar.z);
+	nearLow = fmaxf(wfMax3(nx, ny, nz), 0.0f);
+	return nearLow <= fminf(wfMin3(fx, fy, fz), L.limit);
+}
+
+template <class CNT>
+GI_HD void wfInnerStep(WfLane& L, const DScene& s, StackEntry* stack, CNT& cnt)
+{
+	// one 32-byte record, one 256-bit load: (c0.x, c0.y, c0.z, c1.x, c1.y, c1.z, child0, child1)
+	const U8 n = ld8(s.qNodes + 8 * size_t(L.node));
+	cnt.template add<WFC_NODES>(2u);
+	float f0, f1;
+	const bool h0 = wfSlabTest(L, n.v[0], n.v[1], n.v[2], f0);
+	const bool h1 = wfSlabTest(L, n.v[3], n.v[4], n.v[5], f1);
+	int c0 = int(n.v[6]), c1 = int(n.v[7]);
 	if (h0 && h1)
 	{
 		if (f1 < f0) { int t = c0; c0 = c1; c1 = t; float tf = f0; f0 = f1; f1 = tf; }
@@ -100,19 +212,26 @@ GI_HD void wfInnerStep(WfLane& L, const DScene& s, StackEntry* stack, unsigned* 
 	else wfPop(L, stack);
 }
 
-GI_HD void wfLeafStep(WfLane& L, const DScene& s, const StackEntry* stack, WfCand* cand, unsigned* cnt)
+template <class CNT>
+GI_HD void wfLeafStep(WfLane& L, const DScene& s, const StackEntry* stack, WfCand* cand, CNT& cnt)
 {
 	const int leaf = ~L.node;
+	// One 96-byte record: both triangles + the leaf node's own box in the .w components; all six loads are issued first.
+	F4 v[6];
+	ld8x3(s.leafPos + 6 * size_t(leaf), v);
+	// the reference's cull test for this leaf: its own node box, exact zone (traceray.glsl:64-69)
+	float leafFirst, leafLast;
+	cnt.template add<WFC_NODES>(1u);
+	if (!(intersectBox(L.o, invDir(L.d), v[0].w, v[1].w, v[2].w, v[3].w, v[4].w, v[5].w, leafFirst, leafLast) && leafFirst <= L.limit)) { wfPop(L, stack); return; }
 #pragma unroll
 	for (int slot = 0; slot < 2; ++slot)
 	{
 		const int lt = 2 * leaf + slot;
-		F3 p0, p1, p2; int valid;
-		loadLeafTri(s, lt, p0, p1, p2, valid);
-		if (!valid) break;
-		++cnt[WFC_TRIS];
+		const F4 q0 = v[3 * slot], q1 = v[3 * slot + 1], q2 = v[3 * slot + 2];
+		if (!(q0.x == q0.x)) break; // unused slot (traceray.glsl:127)
+		cnt.template add<WFC_TRIS>(1u);
 		float t; F3 nb, nn;
-		if (intersectTriangle(L.o, L.d, p0, p1, p2, t, nb, nn) && t < L.tMaxInit)
+		if (intersectTriangle(L.o, L.d, f3(q0.x, q0.y, q0.z), f3(q1.x, q1.y, q1.z), f3(q2.x, q2.y, q2.z), t, nb, nn) && t < L.tMaxInit)
 		{
 			if (L.flags & WFL_ANY) { L.flags |= WFL_OCCLUDED; L.node = WF_NODE_DONE; return; }
 			if (L.flags & WFL_COLLECT)
@@ -124,12 +243,7 @@ GI_HD void wfLeafStep(WfLane& L, const DScene& s, const StackEntry* stack, WfCan
 					if (t > L.best + 0.5f * window) L.flags |= WFL_GUARD;
 					else if (L.numCand < WF_MAX_CAND)
 					{
-						// first of the leaf's own node box (the reference's cull test for this leaf)
-						const uint32_t nodeIdx = s.leafNode[leaf];
-						const F4 a = ld4(s.refNodes + 2 * size_t(nodeIdx)), b = ld4(s.refNodes + 2 * size_t(nodeIdx) + 1);
-						float f, l;
-						intersectBox(L.o, L.inv, a.x, a.y, a.z, b.x, b.y, b.z, f, l);
-						cand[L.numCand].t = t; cand[L.numCand].first = f; cand[L.numCand].leaf = lt;
+						cand[L.numCand].t = t; cand[L.numCand].first = leafFirst; cand[L.numCand].leaf = lt;
 						++L.numCand;
 					}
 					else L.flags |= WFL_OVERFLOW;
@@ -151,7 +265,8 @@ GI_HD void wfLeafStep(WfLane& L, const DScene& s, const StackEntry* stack, WfCan
 
 // Called when a lane's walk ran out of nodes.  Returns true when the ray's result (L.best, L.hitLeaf / WFL_OCCLUDED) is
 // final and equal to the reference's; false when the lane was restarted for the collecting second pass.
-GI_HD bool wfEndOfWalk(WfLane& L, const DScene& s, WfCand* cand, unsigned* cnt)
+template <class CNT>
+GI_HD bool wfEndOfWalk(WfLane& L, const DScene& s, WfCand* cand, CNT& cnt)
 {
 	if (L.flags & WFL_EXACT) return true;
 	TraceStats st = {0, 0};
@@ -179,7 +294,7 @@ GI_HD bool wfEndOfWalk(WfLane& L, const DScene& s, WfCand* cand, unsigned* cnt)
 			}
 			if (ambiguous)
 			{
-				++cnt[WFC_FALLBACK];
+				cnt.template add<WFC_FALLBACK>(1u);
 				if (!walk && s.leafPreorder)
 				{
 					// pass 2: same lane, culling limit fixed at the window of pass 1's result
@@ -221,16 +336,18 @@ GI_HD bool wfEndOfWalk(WfLane& L, const DScene& s, WfCand* cand, unsigned* cnt)
 			walk = true;
 		if (walk)
 		{
+			cnt.template add<WFC_SPLATS>(1u); // DEBUG
 			L.best = L.tMaxInit; L.hitLeaf = -1;
 			traceReference<false>(s, L.o, L.d, L.best, L.hitLeaf, &st);
 		}
 	}
-	cnt[WFC_NODES] += st.nodes; cnt[WFC_TRIS] += st.tris;
+	cnt.template add<WFC_NODES>(st.nodes); cnt.template add<WFC_TRIS>(st.tris);
 	return done;
 }
 
 // One ray from start to end on one lane (what a warp does for 32 rays at once, interleaved with other rays).
-GI_HD void wfWalkSingle(WfLane& L, const DScene& s, F3 o, F3 d, float tMax, bool isAny, unsigned* cnt)
+template <class CNT>
+GI_HD void wfWalkSingle(WfLane& L, const DScene& s, F3 o, F3 d, float tMax, bool isAny, CNT& cnt)
 {
 	StackEntry stack[GI_STACK_SIZE];
 	WfCand cand[WF_MAX_CAND];

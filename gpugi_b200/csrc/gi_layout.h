@@ -8,6 +8,7 @@
 #pragma once
 
 #include "gi_core.h"
+#include "gi_lane.h"
 
 #include <cmath>
 #include <cstring>
@@ -20,6 +21,7 @@ struct HostLayout
 {
 	std::vector<F4> refNodes, fastNodes, leafPos, vertexInfo;
 	std::vector<I4> leafTris;
+	std::vector<uint32_t> qNodes;           // 8 words per inner node (quantised child boxes + child links)
 	std::vector<uint32_t> leafNode;         // leaf -> index of the node that points to it
 	std::vector<DMaterial> materials;
 	std::vector<DTexel> texels;             // 4 per material; .pixels still points at HOST memory here
@@ -79,6 +81,8 @@ inline bool buildHostLayout(const GiSceneDesc* d, HostLayout& L, std::string& er
 		}
 	}
 
+	std::memset(&L.scene, 0, sizeof(L.scene));
+
 	// ---- reference layout
 	L.refNodes.resize(size_t(d->num_nodes) * 2);
 	std::memcpy(L.refNodes.data(), d->nodes, size_t(d->num_nodes) * sizeof(GiNode));
@@ -86,54 +90,6 @@ inline bool buildHostLayout(const GiSceneDesc* d, HostLayout& L, std::string& er
 	std::memcpy(L.leafTris.data(), d->leaf_triangles, size_t(d->num_leaf_triangles) * sizeof(GiTriangle));
 	L.vertexInfo.resize(d->num_vertices);
 	std::memcpy(L.vertexInfo.data(), d->vertex_info, size_t(d->num_vertices) * sizeof(GiVertexInfo));
-
-	// ---- leaf block
-	L.leafPos.resize(size_t(d->num_leaf_triangles) * 3);
-	for (uint32_t i = 0; i < d->num_leaf_triangles; ++i)
-	{
-		const GiTriangle& t = d->leaf_triangles[i];
-		const bool valid = t.v[0] != t.v[1];
-		for (int k = 0; k < 3; ++k)
-		{
-			F4 v = {0.0f, 0.0f, 0.0f, 0.0f};
-			if (valid) { const float* p = d->positions + 3 * size_t(t.v[k]); v.x = p[0]; v.y = p[1]; v.z = p[2]; }
-			if (k == 0) { int flag = valid ? 1 : 0; std::memcpy(&v.w, &flag, 4); }
-			L.leafPos[3 * size_t(i) + k] = v;
-		}
-	}
-
-	// ---- fast layout.  Children of an inner node: firstChild, then its escape (the right sibling),
-	// whose own escape must be the parent's escape (i.e. it is the last child).
-	std::vector<int> fastIndex(d->num_nodes, -1);
-	uint32_t numInner = 0;
-	for (uint32_t i = 0; i < d->num_nodes; ++i)
-		if (!(d->nodes[i].first_child & 0x80000000u)) fastIndex[i] = int(numInner++);
-	L.binary = true;
-	L.fastNodes.assign(size_t(numInner ? numInner : 1) * 4, F4{0.0f, 0.0f, 0.0f, 0.0f});
-	for (uint32_t i = 0; i < d->num_nodes; ++i)
-	{
-		const GiNode& n = d->nodes[i];
-		if (n.first_child & 0x80000000u) continue;
-		const uint32_t left = n.first_child;
-		const uint32_t right = d->nodes[left].escape;
-		if (right == 0 || right >= d->num_nodes || right == n.escape || d->nodes[right].escape != n.escape) { L.binary = false; break; }
-		const GiNode& a = d->nodes[left];
-		const GiNode& b = d->nodes[right];
-		auto encode = [&](uint32_t nodeIdx) -> int {
-			const GiNode& ch = d->nodes[nodeIdx];
-			if (ch.first_child & 0x80000000u) return ~int(ch.first_child & 0x7fffffffu);
-			return fastIndex[nodeIdx];
-		};
-		const int c0 = encode(left), c1 = encode(right);
-		F4* q = &L.fastNodes[size_t(fastIndex[i]) * 4];
-		q[0] = F4{a.min[0], a.min[1], a.min[2], a.max[0]};
-		q[1] = F4{a.max[1], a.max[2], b.min[0], b.min[1]};
-		q[2] = F4{b.min[2], b.max[0], b.max[1], b.max[2]};
-		F4 ch = {0.0f, 0.0f, 0.0f, 0.0f};
-		std::memcpy(&ch.x, &c0, 4);
-		std::memcpy(&ch.y, &c1, 4);
-		q[3] = ch;
-	}
 
 	// ---- leaf -> node map, and whether leaf indices increase along the reference's preorder walk (node -> firstChild,
 	// leaf/skip -> escape; with every box "hit" this enumerates all leaves in tie-break order)
@@ -158,6 +114,117 @@ inline bool buildHostLayout(const GiSceneDesc* d, HostLayout& L, std::string& er
 				node = n.first_child;
 			if (++steps > 2u * d->num_nodes) { preorder = false; break; } // malformed escape chain
 		} while (node != 0);
+	}
+
+	// ---- leaf block: per leaf the gathered vertex positions of both slots + the leaf node's own box in the .w components
+	for (uint32_t v = 0; v < d->num_vertices; ++v)
+		if (!std::isfinite(d->positions[3 * size_t(v)]) || !std::isfinite(d->positions[3 * size_t(v) + 1]) || !std::isfinite(d->positions[3 * size_t(v) + 2]))
+		{
+			err = "vertex " + std::to_string(v) + " has a non-finite position";
+			return false;
+		}
+	L.leafPos.assign(size_t(numLeaves) * 6, F4{0.0f, 0.0f, 0.0f, 0.0f});
+	for (uint32_t leaf = 0; leaf < numLeaves; ++leaf)
+	{
+		F4* rec = &L.leafPos[size_t(leaf) * 6];
+		const GiNode& ln = d->nodes[L.leafNode[leaf]];
+		for (uint32_t slot = 0; slot < 2; ++slot)
+		{
+			const GiTriangle& t = d->leaf_triangles[2 * size_t(leaf) + slot];
+			const bool valid = t.v[0] != t.v[1];
+			for (int k = 0; k < 3; ++k)
+			{
+				F4 v = {0.0f, 0.0f, 0.0f, 0.0f};
+				if (valid) { const float* p = d->positions + 3 * size_t(t.v[k]); v.x = p[0]; v.y = p[1]; v.z = p[2]; }
+				else if (k == 0) v.x = std::nanf("");
+				v.w = slot == 0 ? ln.min[k] : ln.max[k];
+				rec[3 * slot + k] = v;
+			}
+		}
+	}
+
+	// ---- fast layout.  Children of an inner node: firstChild, then its escape (the right sibling),
+	// whose own escape must be the parent's escape (i.e. it is the last child).
+	std::vector<int> fastIndex(d->num_nodes, -1);
+	uint32_t numInner = 0;
+	for (uint32_t i = 0; i < d->num_nodes; ++i)
+		if (!(d->nodes[i].first_child & 0x80000000u)) fastIndex[i] = int(numInner++);
+	L.binary = true;
+	L.fastNodes.assign(size_t(numInner ? numInner : 1) * 4, F4{0.0f, 0.0f, 0.0f, 0.0f});
+	L.qNodes.assign(size_t(numInner ? numInner : 1) * 8, 0u);
+	// 16-bit grid over the root box; cell size rounded up so that 65535 cells cover the box
+	double gridLo[3], gridScale[3];
+	for (int k = 0; k < 3; ++k)
+	{
+		const float lo = d->nodes[0].min[k], hi = d->nodes[0].max[k];
+		float sc = float((double(hi) - double(lo)) / 65535.0 * (1.0 + 1.0e-6));
+		if (!(sc > 1.0e-30f)) sc = 1.0e-30f;
+		L.scene.gridLo[k] = lo; L.scene.gridScale[k] = sc;
+		gridLo[k] = double(lo); gridScale[k] = double(sc);
+	}
+	// outward rounding, verified in double against the decode lo + q * scale the device's slab test stands for
+	auto quantLo = [&](float x, int k) -> uint32_t {
+		double q = std::floor((double(x) - gridLo[k]) / gridScale[k]);
+		if (!(q > 0.0)) q = 0.0;
+		if (q > 65535.0) q = 65535.0;
+		while (q > 0.0 && gridLo[k] + q * gridScale[k] > double(x)) q -= 1.0;
+		return uint32_t(q);
+	};
+	auto quantHi = [&](float x, int k) -> uint32_t {
+		double q = std::ceil((double(x) - gridLo[k]) / gridScale[k]);
+		if (!(q > 0.0)) q = 0.0;
+		if (q > 65535.0) q = 65535.0;
+		while (q < 65535.0 && gridLo[k] + q * gridScale[k] < double(x)) q += 1.0;
+		return uint32_t(q);
+	};
+	for (uint32_t i = 0; i < d->num_nodes; ++i)
+	{
+		const GiNode& n = d->nodes[i];
+		if (n.first_child & 0x80000000u) continue;
+		const uint32_t left = n.first_child;
+		const uint32_t right = d->nodes[left].escape;
+		if (right == 0 || right >= d->num_nodes || right == n.escape || d->nodes[right].escape != n.escape) { L.binary = false; break; }
+		const GiNode& a = d->nodes[left];
+		const GiNode& b = d->nodes[right];
+		// The wavefront walk tests inner nodes conservatively and applies the reference's exact cull test to a leaf's own
+		// box only; that equals the reference's chain of tests iff every child box lies inside its parent's box (the slab
+		// test is monotone in the box).  bim's bottom-up box pass guarantees it; other inputs fall back to the reference walk.
+		for (int k = 0; k < 3; ++k)
+		{
+			const float lo = n.min[k], hi = n.max[k];
+			if (!(lo <= a.min[k] && a.min[k] <= hi && lo <= a.max[k] && a.max[k] <= hi && lo <= b.min[k] && b.min[k] <= hi && lo <= b.max[k] && b.max[k] <= hi))
+				L.binary = false;
+		}
+		if (!L.binary) break;
+		auto encode = [&](uint32_t nodeIdx) -> int {
+			const GiNode& ch = d->nodes[nodeIdx];
+			if (ch.first_child & 0x80000000u) return ~int(ch.first_child & 0x7fffffffu);
+			return fastIndex[nodeIdx];
+		};
+		const int c0 = encode(left), c1 = encode(right);
+		F4* q = &L.fastNodes[size_t(fastIndex[i]) * 4];
+		q[0] = F4{a.min[0], a.min[1], a.min[2], a.max[0]};
+		q[1] = F4{a.max[1], a.max[2], b.min[0], b.min[1]};
+		q[2] = F4{b.min[2], b.max[0], b.max[1], b.max[2]};
+		F4 ch = {0.0f, 0.0f, 0.0f, 0.0f};
+		std::memcpy(&ch.x, &c0, 4);
+		std::memcpy(&ch.y, &c1, 4);
+		q[3] = ch;
+		{
+			uint32_t v[12];
+			for (int k = 0; k < 3; ++k)
+			{
+				v[k] = quantLo(a.min[k], k); v[3 + k] = quantHi(a.max[k], k);
+				v[6 + k] = quantLo(b.min[k], k); v[9 + k] = quantHi(b.max[k], k);
+				// the grid must cover the box (guaranteed for boxes nested in the root box)
+				if (gridLo[k] + double(v[k]) * gridScale[k] > double(a.min[k]) || gridLo[k] + double(v[3 + k]) * gridScale[k] < double(a.max[k]) ||
+				    gridLo[k] + double(v[6 + k]) * gridScale[k] > double(b.min[k]) || gridLo[k] + double(v[9 + k]) * gridScale[k] < double(b.max[k]))
+					L.binary = false;
+			}
+			uint32_t* qn = &L.qNodes[size_t(fastIndex[i]) * 8];
+			for (int k = 0; k < 3; ++k) { qn[k] = v[k] | (v[3 + k] << 16); qn[3 + k] = v[6 + k] | (v[9 + k] << 16); }
+			qn[6] = uint32_t(c0); qn[7] = uint32_t(c1);
+		}
 	}
 
 	// ---- materials
@@ -203,7 +270,6 @@ inline bool buildHostLayout(const GiSceneDesc* d, HostLayout& L, std::string& er
 		L.materials[mi] = dm;
 	}
 
-	std::memset(&L.scene, 0, sizeof(L.scene));
 	L.scene.numNodes = d->num_nodes;
 	L.scene.numLeafTris = d->num_leaf_triangles;
 	L.scene.numMaterials = d->num_materials;

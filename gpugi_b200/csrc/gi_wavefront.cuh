@@ -139,8 +139,8 @@ GI_D void wfFinishShadow(const WfTraceIO& io, uint32_t slot, bool occluded)
 // retired) or idle.  One outer iteration retires finished rays, refills idle lanes, runs ONE leaf step for the lanes
 // waiting at a leaf and then inner-node steps for as long as enough lanes of the warp are at inner nodes (one vote per
 // step), so leaf code, retire/refill code and inner-node code never serialise against each other inside the hot loop.
-template <class IO>
-GI_D void wfTraceLoop(const DScene& s, const IO& io, uint32_t* workCounter, WfTune tune, unsigned* cnt)
+template <class IO, class CNT>
+GI_D void wfTraceLoop(const DScene& s, const IO& io, uint32_t* workCounter, WfTune tune, CNT& cnt)
 {
 	StackEntry stack[GI_STACK_SIZE];
 	WfCand cand[WF_MAX_CAND];
@@ -197,8 +197,8 @@ GI_D void wfTraceLoop(const DScene& s, const IO& io, uint32_t* workCounter, WfTu
 
 // Reference-order variant (GI_TRAVERSAL_REFERENCE): same work distribution, every lane walks its ray with the
 // stackless escape-pointer loop of traceray.glsl from start to end.
-template <class IO>
-GI_D void wfTraceLoopReference(const DScene& s, const IO& io, uint32_t* workCounter, unsigned* cnt)
+template <class IO, class CNT>
+GI_D void wfTraceLoopReference(const DScene& s, const IO& io, uint32_t* workCounter, CNT& cnt)
 {
 	const uint32_t total = io.total();
 	for (;;)
@@ -211,13 +211,13 @@ GI_D void wfTraceLoopReference(const DScene& s, const IO& io, uint32_t* workCoun
 		if (mine < total)
 		{
 			WfLane L;
-			unsigned dummy[WFC_COUNT];
+			WfCounters<false> dummy;
 			io.load(s, mine, L, dummy); // ray + root test (the walk below repeats the root test itself)
 			TraceStats st = {0, 0};
 			float len = L.tMaxInit; int leafTri = -1;
 			if (L.flags & WFL_ANY) { if (traceReference<true>(s, L.o, L.d, len, leafTri, &st)) L.flags |= WFL_OCCLUDED; }
 			else traceReference<false>(s, L.o, L.d, len, leafTri, &st);
-			cnt[WFC_NODES] += st.nodes; cnt[WFC_TRIS] += st.tris;
+			cnt.template add<WFC_NODES>(st.nodes); cnt.template add<WFC_TRIS>(st.tris);
 			L.best = len; L.hitLeaf = leafTri; L.flags |= WFL_EXACT;
 			io.finish(s, L, cnt);
 		}
@@ -228,14 +228,16 @@ struct WfQueueIO
 {
 	WfTraceIO q;
 	GI_D uint32_t total() const { return q.numClosest + q.numShadow; }
-	GI_D void load(const DScene& s, uint32_t index, WfLane& L, unsigned* cnt) const
+	template <class CNT>
+	GI_D void load(const DScene& s, uint32_t index, WfLane& L, CNT& cnt) const
 	{
 		const bool isAny = index >= q.numClosest;
 		const F4* p = isAny ? q.shadow + 3 * size_t(index - q.numClosest) : q.rays + 2 * size_t(index);
 		const F4 r0 = ld4(p), r1 = ld4(p + 1);
 		wfBegin(L, s, f3(r0.x, r0.y, r0.z), f3(r1.x, r1.y, r1.z), r0.w, isAny, index, cnt);
 	}
-	GI_D void finish(const DScene& s, WfLane& L, unsigned* cnt) const
+	template <class CNT>
+	GI_D void finish(const DScene& s, WfLane& L, CNT& cnt) const
 	{
 		if (L.flags & WFL_ANY) wfFinishShadow(q, L.index - q.numClosest, (L.flags & WFL_OCCLUDED) != 0u);
 		else q.hits[L.index] = make_float2(L.best, i2f(L.hitLeaf));
@@ -249,14 +251,16 @@ struct WfBatchIO
 	float4* hits;
 	uint32_t n;
 	GI_D uint32_t total() const { return n; }
-	GI_D void load(const DScene& s, uint32_t index, WfLane& L, unsigned* cnt) const
+	template <class CNT>
+	GI_D void load(const DScene& s, uint32_t index, WfLane& L, CNT& cnt) const
 	{
 		const F4 r0 = ld4(rays + 2 * size_t(index)), r1 = ld4(rays + 2 * size_t(index) + 1);
 		wfBegin(L, s, f3(r0.x, r0.y, r0.z), f3(r1.x, r1.y, r1.z), r0.w, (uint32_t(f2i(r1.w)) & 1u) != 0u, index, cnt);
 	}
-	GI_D void finish(const DScene& s, WfLane& L, unsigned* cnt) const
+	template <class CNT>
+	GI_D void finish(const DScene& s, WfLane& L, CNT& cnt) const
 	{
-		++cnt[(L.flags & WFL_ANY) ? WFC_ANY : WFC_CLOSEST];
+		if (L.flags & WFL_ANY) cnt.template add<WFC_ANY>(1u); else cnt.template add<WFC_CLOSEST>(1u);
 		if (L.flags & WFL_ANY)
 		{
 			hits[L.index] = make_float4(L.tMaxInit, i2f((L.flags & WFL_OCCLUDED) ? 1 : 0), 0.0f, 0.0f);

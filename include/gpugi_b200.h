@@ -167,7 +167,10 @@ enum {
 	/* tuning of the persistent wavefront trace kernel (defaults are the measured optimum) */
 	GI_OPT_WF_REFILL_THRESHOLD = 3, /* idle lanes per warp that trigger a refill from the ray queue  */
 	GI_OPT_WF_MIN_INNER = 4,        /* keep taking inner-node steps while this many of 32 active lanes are at inner nodes */
-	GI_OPT_WF_BLOCKS_PER_SM = 6     /* resident trace blocks per SM (0 = occupancy maximum)          */
+	GI_OPT_WF_BLOCKS_PER_SM = 6,    /* resident trace blocks per SM (0 = occupancy maximum)          */
+	GI_OPT_COUNT_STEPS = 7          /* 1 = the wavefront walk counts its box / triangle tests (GiCounters::node_tests,
+	                                   triangle_tests); off by default: two counters less in the hot loop.  The megakernel and
+	                                   GI_TRAVERSAL_REFERENCE always count. */
 };
 enum {
 	GI_SCHEDULER_WAVEFRONT = 0, /* HBM ray queues, persistent trace warps, ballot-compacted waves (default; FAST traversal) */

@@ -27,12 +27,12 @@ bool makeScene(const GiSceneDesc* d, EmScene& e, std::string& err)
 	e.s = e.L.scene;
 	e.s.refNodes = e.L.refNodes.data();
 	e.s.fastNodes = e.L.fastNodes.data();
+	e.s.qNodes = e.L.qNodes.data();
 	e.s.leafPos = e.L.leafPos.data();
 	e.s.leafTris = e.L.leafTris.data();
 	e.s.vertexInfo = e.L.vertexInfo.data();
 	e.s.materials = e.L.materials.data();
 	e.s.texels = e.L.texels.data();
-	e.s.leafNode = e.L.leafNode.data();
 	e.s.textureFilterExact = 1;
 	return true;
 }
@@ -69,7 +69,7 @@ EM_API int em_trace(const GiSceneDesc* desc, const GiRay* rays, uint32_t n, GiHi
 		GiHit out;
 		if (mode == EM_MODE_LANE)
 		{
-			unsigned cnt[WFC_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+			WfCounters<true> cnt;
 			WfLane L;
 			const bool isAny = (rays[i].flags & 1u) != 0u;
 			wfWalkSingle(L, e.s, o, d, rays[i].t_max, isAny, cnt);
@@ -87,7 +87,7 @@ EM_API int em_trace(const GiSceneDesc* desc, const GiRay* rays, uint32_t n, GiHi
 					out.bary_y = bary.y; out.bary_z = bary.z;
 				}
 			}
-			pc.fallbackRays += cnt[WFC_FALLBACK]; st.nodes += cnt[WFC_NODES]; st.tris += cnt[WFC_TRIS];
+			pc.splats += cnt.v[WFC_SPLATS]; pc.fallbackRays += cnt.v[WFC_FALLBACK]; st.nodes += cnt.v[WFC_NODES]; st.tris += cnt.v[WFC_TRIS];
 		}
 		else if (rays[i].flags & 1u)
 		{
@@ -158,5 +158,47 @@ EM_API int em_render(const GiSceneDesc* desc, const GiCamera* cam, int w, int h,
 		for (int i = 0; i < nls; ++i) showLightCache(f, i, pc, &st);
 	addCounters(counters, pc, st);
 	if (counters) { counters->light_cache_entries = bptCounters[0]; counters->light_path_length_sum = bptCounters[1]; }
+	return 0;
+}
+
+// Conservativeness of the quantised inner-node test (gi_lane.h: wfSlabTest) against the exact-zone test on the real child
+// box (intersectBox): for every ray and every `stride`-th inner node, both children.  out[0] = pairs tested,
+// out[1] = pairs the exact test accepts, out[2] = pairs the conservative test accepts, out[3] = VIOLATIONS (exact accepts
+// with first <= limit but the conservative test rejects, or its entry bound exceeds the exact entry distance),
+// out[4] = rays outside the domain of the bound (answered by the reference walk).
+EM_API int em_slab_check(const GiSceneDesc* desc, const GiRay* rays, uint32_t n, uint32_t stride, uint64_t* out)
+{
+	EmScene e; std::string err;
+	if (!makeScene(desc, e, err)) return 1;
+	if (!e.L.binary) return 2;
+	for (int i = 0; i < 5; ++i) out[i] = 0;
+	std::vector<uint32_t> inner;
+	for (uint32_t i = 0; i < desc->num_nodes; ++i)
+		if (!(desc->nodes[i].first_child & 0x80000000u)) inner.push_back(i);
+	for (uint32_t r = 0; r < n; ++r)
+	{
+		WfLane L;
+		const F3 o = f3(rays[r].origin), d = f3(rays[r].direction);
+		const F3 inv = invDir(d);
+		if (!wfSlabSetup(L, e.s, o, inv)) { ++out[4]; continue; }
+		L.limit = rays[r].t_max;
+		for (size_t fi = r % stride; fi < inner.size(); fi += stride)
+		{
+			const GiNode& nd = desc->nodes[inner[fi]];
+			const uint32_t kids[2] = {nd.first_child, desc->nodes[nd.first_child].escape};
+			const U8 q = ld8(e.s.qNodes + 8 * fi);
+			for (int c = 0; c < 2; ++c)
+			{
+				const GiNode& ch = desc->nodes[kids[c]];
+				float first, last, nearLow;
+				const bool exact = intersectBox(o, inv, ch.min[0], ch.min[1], ch.min[2], ch.max[0], ch.max[1], ch.max[2], first, last) && first <= L.limit;
+				const bool cons = wfSlabTest(L, q.v[3 * c], q.v[3 * c + 1], q.v[3 * c + 2], nearLow);
+				++out[0];
+				if (exact) ++out[1];
+				if (cons) ++out[2];
+				if (exact && (!cons || nearLow > first)) ++out[3];
+			}
+		}
+	}
 	return 0;
 }

@@ -39,6 +39,8 @@ lib.em_trace.restype = C.c_int
 lib.em_trace.argtypes = [vp, vp, u32, vp, C.c_int, C.POINTER(C.c_int), vp]
 lib.em_render.restype = C.c_int
 lib.em_render.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, vp, vp]
+lib.em_slab_check.restype = C.c_int
+lib.em_slab_check.argtypes = [vp, vp, u32, u32, vp]
 
 
 def _p(a):
@@ -74,3 +76,13 @@ def render(scene_desc, cam, w, h, light_samples, renderer, frame_seed, max_len=1
     if st != 0:
         raise RuntimeError("em_render failed: %d" % st)
     return accum, cnt.as_dict()
+
+
+def slab_check(scene_desc, rays, stride=64):
+    """Conservativeness of the quantised inner-node test vs the exact-zone box test (see em_slab_check)."""
+    rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+    out = np.zeros(5, dtype=np.uint64)
+    st = lib.em_slab_check(C.addressof(scene_desc), _p(rays), rays.shape[0], stride, _p(out))
+    if st != 0:
+        raise RuntimeError("em_slab_check failed: %d" % st)
+    return dict(zip(["tested", "exact_accepts", "conservative_accepts", "violations", "out_of_domain"], (int(x) for x in out)))

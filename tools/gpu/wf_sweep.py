@@ -19,6 +19,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--sweep", action="store_true")
+    ap.add_argument("--only-wavefront", action="store_true")
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--texture-size", type=int, default=1024)
@@ -70,6 +71,10 @@ def main():
         return img, res
 
     results = []
+    if args.only_wavefront:
+        run("wavefront default", {g.GI_OPT_SCHEDULER: g.GI_SCHEDULER_WAVEFRONT})
+        dev.close()
+        return
     ref_img, r = run("megakernel", {g.GI_OPT_SCHEDULER: g.GI_SCHEDULER_MEGAKERNEL})
     results.append(r)
     img, r = run("wavefront default", {g.GI_OPT_SCHEDULER: g.GI_SCHEDULER_WAVEFRONT})
