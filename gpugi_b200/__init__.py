@@ -15,7 +15,7 @@ import numpy as np
 from . import _capi as capi
 from ._capi import (GI_RENDERER_PT, GI_RENDERER_LPT, GI_RENDERER_BPT, GI_TRAVERSAL_FAST, GI_TRAVERSAL_REFERENCE,
                     GI_OPT_TRAVERSAL, GI_OPT_TEXTURE_FILTER, GI_OPT_SCHEDULER, GI_OPT_WF_REFILL_THRESHOLD, GI_OPT_WF_MIN_INNER,
-                    GI_OPT_WF_BLOCKS_PER_SM, GI_OPT_COUNT_STEPS, GI_SCHEDULER_WAVEFRONT, GI_SCHEDULER_MEGAKERNEL, RAY_MAX)
+                    GI_OPT_WF_BLOCKS_PER_SM, GI_OPT_COUNT_STEPS, GI_OPT_KERNEL_TIMING, GI_SCHEDULER_WAVEFRONT, GI_SCHEDULER_MEGAKERNEL, RAY_MAX)
 
 RAY_DTYPE = np.dtype([("origin", "<f4", 3), ("t_max", "<f4"), ("direction", "<f4", 3), ("flags", "<u4")])
 HIT_DTYPE = np.dtype([("t", "<f4"), ("leaf_tri", "<i4"), ("bary_y", "<f4"), ("bary_z", "<f4")])
@@ -286,6 +286,13 @@ class Device:
 
     def kernel_launches(self):
         return int(capi.dev.gi_kernel_launches(self._c))
+
+    def kernel_times(self):
+        """gi_get_kernel_times: {class: (ms, launches)} collected while GI_OPT_KERNEL_TIMING is on."""
+        t = capi.GiKernelTimes()
+        self._check(capi.dev.gi_get_kernel_times(self._c, C.byref(t)), "gi_get_kernel_times")
+        names = ["trace", "shade", "generate", "megakernel", "other"]
+        return {n: (float(t.ms[i]), int(t.launches[i])) for i, n in enumerate(names)}
 
 
 # ---------------------------------------------------------------------------------------------------

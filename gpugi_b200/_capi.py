@@ -90,6 +90,10 @@ class GiCounters(C.Structure):
                 ("triangle_tests", u64), ("light_cache_entries", u32), ("light_path_length_sum", u32)]
 
 
+class GiKernelTimes(C.Structure):
+    _fields_ = [("ms", C.c_double * 5), ("launches", u64 * 5)]
+
+
 class GihSceneInfo(C.Structure):
     _fields_ = [("num_triangles", u32), ("num_vertices", u32), ("num_nodes", u32), ("num_leaf_triangles", u32),
                 ("num_materials", u32), ("num_tree_levels", u32), ("num_light_triangles", u32), ("num_point_lights", u32),
@@ -103,6 +107,8 @@ GI_RENDERER_PT, GI_RENDERER_LPT, GI_RENDERER_BPT = 0, 1, 2
 GI_TRAVERSAL_FAST, GI_TRAVERSAL_REFERENCE = 0, 1
 GI_OPT_TRAVERSAL, GI_OPT_TEXTURE_FILTER, GI_OPT_SCHEDULER = 0, 1, 2
 GI_OPT_WF_REFILL_THRESHOLD, GI_OPT_WF_MIN_INNER, GI_OPT_WF_BLOCKS_PER_SM, GI_OPT_COUNT_STEPS = 3, 4, 6, 7
+GI_OPT_KERNEL_TIMING = 8
+GI_KERNEL_TRACE, GI_KERNEL_SHADE, GI_KERNEL_GENERATE, GI_KERNEL_MEGAKERNEL, GI_KERNEL_OTHER, GI_KERNEL_CLASS_COUNT = 0, 1, 2, 3, 4, 5
 GI_SCHEDULER_WAVEFRONT, GI_SCHEDULER_MEGAKERNEL = 0, 1
 GI_TEX_SRGB8_ALPHA8, GI_TEX_RGBA8, GI_TEX_RGBA32F = 0, 1, 2
 RAY_MAX = 3.402823466e+38
@@ -137,6 +143,7 @@ DEVICE_API = {
     "gi_get_counters": (C.c_int, [vp, P(GiCounters)]),
     "gi_reset_counters": (C.c_int, [vp]),
     "gi_kernel_launches": (u64, [vp]),
+    "gi_get_kernel_times": (C.c_int, [vp, P(GiKernelTimes)]),
 }
 
 HOST_API = {

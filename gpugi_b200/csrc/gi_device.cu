@@ -284,7 +284,42 @@ struct GiContext
 	uint32_t* traceWork = nullptr;   // work counter of k_wf_trace_batch
 	int numSMs = 148;
 	int traceBlocksPerSM = 1, shadeBlocksPerSM = 1;
+
+	// GI_OPT_KERNEL_TIMING: CUDA-event duration of every launch of an iteration, summed per kernel class
+	int kernelTiming = 0;
+	double kernelMs[GI_KERNEL_CLASS_COUNT] = {};
+	uint64_t kernelLaunches[GI_KERNEL_CLASS_COUNT] = {};
+	std::vector<cudaEvent_t> timingEvents;   // pool, reused across iterations
+	std::vector<int> timingClass;            // class of the launch that ends at event i+1
+	size_t timingUsed = 0;
 };
+
+// Kernel timing: timingMark(c, cls) after a launch closes the interval since the previous mark and books it to `cls`
+// (cls < 0 opens the first interval); timingCollect() synchronises and sums.  Events sit on the launching stream.
+static void timingMark(GiContext* c, int cls)
+{
+	if (!c->kernelTiming) return;
+	if (c->timingUsed == c->timingEvents.size()) { cudaEvent_t e; cudaEventCreate(&e); c->timingEvents.push_back(e); c->timingClass.push_back(-1); }
+	cudaEventRecord(c->timingEvents[c->timingUsed], c->stream);
+	c->timingClass[c->timingUsed] = cls;
+	++c->timingUsed;
+}
+
+static void timingCollect(GiContext* c)
+{
+	if (!c->kernelTiming || c->timingUsed == 0) return;
+	cudaEventSynchronize(c->timingEvents[c->timingUsed - 1]);
+	for (size_t i = 1; i < c->timingUsed; ++i)
+	{
+		const int cls = c->timingClass[i];
+		if (cls < 0) continue;
+		float ms = 0.0f;
+		cudaEventElapsedTime(&ms, c->timingEvents[i - 1], c->timingEvents[i]);
+		c->kernelMs[cls] += double(ms);
+		++c->kernelLaunches[cls];
+	}
+	c->timingUsed = 0;
+}
 
 static std::string g_createError;
 
@@ -401,51 +436,27 @@ static int renderWavefrontPT(GiContext* c, const DFrame& f)
 	w.tune = c->tune;
 	GI_CUDA(c, cudaMemsetAsync(c->wf.counts, 0, size_t(c->wfCountsLen) * sizeof(uint32_t), c->stream));
 	const unsigned traceGrid = unsigned(c->numSMs * c->traceBlocksPerSM), shadeGrid = unsigned(c->numSMs * c->shadeBlocksPerSM);
-	// GI_WF_PROFILE=1: per-kernel CUDA-event timings of this iteration on stderr (warm caches, unlike an ncu replay)
-	static const bool profile = std::getenv("GI_WF_PROFILE") != nullptr;
-	std::vector<cudaEvent_t> ev;
-	std::vector<std::string> evName;
-	auto mark = [&](const char* what, int b) {
-		if (!profile) return;
-		cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, c->stream);
-		ev.push_back(e); evName.push_back(std::string(what) + "(" + std::to_string(b) + ")");
-	};
 	const bool ref = f.traversalMode == GI_TRAVERSAL_REFERENCE;
 	auto trace = [&](int b) {
 		if (ref) k_wf_trace<true, true><<<traceGrid, WF_TRACE_THREADS, 0, c->stream>>>(w, b, c->counters);
 		else if (c->countSteps) k_wf_trace<false, true><<<traceGrid, WF_TRACE_THREADS, 0, c->stream>>>(w, b, c->counters);
 		else k_wf_trace<false, false><<<traceGrid, WF_TRACE_THREADS, 0, c->stream>>>(w, b, c->counters);
 		++c->launches;
-		mark("trace", b);
+		timingMark(c, GI_KERNEL_TRACE);
 	};
-	mark("start", 0);
+	timingMark(c, -1);
 	k_wf_generate<<<unsigned(c->numSMs) * 8u, 256, 0, c->stream>>>(w, c->counters);
 	++c->launches;
-	mark("generate", 0);
+	timingMark(c, GI_KERNEL_GENERATE);
 	for (int b = 0; b < f.maxPathLength; ++b)
 	{
 		trace(b);
 		k_wf_shade_pt<<<shadeGrid, WF_SHADE_THREADS, 0, c->stream>>>(w, b, c->counters);
 		++c->launches;
-		mark("shade", b);
+		timingMark(c, GI_KERNEL_SHADE);
 	}
 	trace(f.maxPathLength);
-	if (profile)
-	{
-		cudaStreamSynchronize(c->stream);
-		std::vector<uint32_t> h(c->wfCountsLen);
-		cudaMemcpy(h.data(), c->wf.counts, h.size() * 4, cudaMemcpyDeviceToHost);
-		float total = 0.0f;
-		for (size_t i = 1; i < ev.size(); ++i)
-		{
-			float ms = 0.0f; cudaEventElapsedTime(&ms, ev[i - 1], ev[i]); total += ms;
-			std::fprintf(stderr, "[wf] %-10s %8.1f us", evName[i].c_str(), ms * 1e3f);
-			if (evName[i][0] == 't') { int b = int(i - 2) / 2; std::fprintf(stderr, "   closest %8u shadow %8u", h[4 * b], b > 0 ? h[4 * (b - 1) + 1] : 0u); }
-			std::fprintf(stderr, "\n");
-		}
-		std::fprintf(stderr, "[wf] total      %8.1f us\n", total * 1e3f);
-		for (cudaEvent_t e : ev) cudaEventDestroy(e);
-	}
+	timingCollect(c);
 	return GI_OK;
 }
 
@@ -506,6 +517,7 @@ void gi_destroy(GiContext* c)
 	if (c->envTex) cudaDestroyTextureObject(c->envTex);
 	if (c->envArray) cudaFreeArray(c->envArray);
 	cudaFree(c->accum); cudaFree(c->lightSamples); cudaFree(c->lightCache); cudaFree(c->bptCounters); cudaFree(c->counters); cudaFree(c->mseResult);
+	for (cudaEvent_t e : c->timingEvents) cudaEventDestroy(e);
 	if (c->ownStream) cudaStreamDestroy(c->ownStream);
 	delete c;
 }
@@ -531,6 +543,10 @@ int gi_set_option(GiContext* c, int option, int value)
 		if (value != GI_SCHEDULER_WAVEFRONT && value != GI_SCHEDULER_MEGAKERNEL) return fail(c, GI_ERR_INVALID, "GI_OPT_SCHEDULER: unknown scheduler");
 		c->scheduler = value; return GI_OK;
 	case GI_OPT_COUNT_STEPS: c->countSteps = value ? 1 : 0; return GI_OK;
+	case GI_OPT_KERNEL_TIMING:
+		c->kernelTiming = value ? 1 : 0;
+		for (int i = 0; i < GI_KERNEL_CLASS_COUNT; ++i) { c->kernelMs[i] = 0.0; c->kernelLaunches[i] = 0; }
+		return GI_OK;
 	case GI_OPT_WF_REFILL_THRESHOLD: c->tune.refillThreshold = std::min(std::max(value, 1), 32); return GI_OK;
 	case GI_OPT_WF_MIN_INNER: c->tune.minInner = std::min(std::max(value, 1), 32); return GI_OK;
 	case GI_OPT_WF_BLOCKS_PER_SM:
@@ -929,5 +945,12 @@ int gi_reset_counters(GiContext* c)
 }
 
 uint64_t gi_kernel_launches(const GiContext* c) { return c ? c->launches : 0; }
+
+int gi_get_kernel_times(GiContext* c, GiKernelTimes* out)
+{
+	if (!c || !out) return GI_ERR_INVALID;
+	for (int i = 0; i < GI_KERNEL_CLASS_COUNT; ++i) { out->ms[i] = c->kernelMs[i]; out->launches[i] = c->kernelLaunches[i]; }
+	return GI_OK;
+}
 
 } // extern "C"

@@ -171,7 +171,24 @@ enum {
 	GI_OPT_COUNT_STEPS = 7          /* 1 = the wavefront walk counts its box / triangle tests (GiCounters::node_tests,
 	                                   triangle_tests); off by default: two counters less in the hot loop.  The megakernel and
 	                                   GI_TRAVERSAL_REFERENCE always count. */
+	GI_OPT_KERNEL_TIMING = 8        /* 1 = bracket every kernel launch of gi_render_iteration with CUDA events on the launching
+	                                   stream and sum the durations per kernel class (gi_get_kernel_times); setting the option
+	                                   clears the sums.  The iteration call then synchronises -- measurement passes only.
+	                                   Replaces the reference's glFinish + clock() pair (renderersystem.cpp:249-255). */
 };
+/* kernel classes of gi_get_kernel_times */
+enum {
+	GI_KERNEL_TRACE = 0,     /* persistent closest-hit / any-hit traversal waves (k_wf_trace)       */
+	GI_KERNEL_SHADE = 1,     /* shading / bounce waves (k_wf_shade_*)                                */
+	GI_KERNEL_GENERATE = 2,  /* ray generation (k_wf_generate*)                                      */
+	GI_KERNEL_MEGAKERNEL = 3,/* one-thread-per-path kernels (k_pathtrace, k_lighttrace, k_bidir_eye) */
+	GI_KERNEL_OTHER = 4,
+	GI_KERNEL_CLASS_COUNT = 5
+};
+typedef struct GiKernelTimes {
+	double   ms[GI_KERNEL_CLASS_COUNT];       /* summed CUDA-event durations since GI_OPT_KERNEL_TIMING was set */
+	uint64_t launches[GI_KERNEL_CLASS_COUNT];
+} GiKernelTimes;
 enum {
 	GI_SCHEDULER_WAVEFRONT = 0, /* HBM ray queues, persistent trace warps, ballot-compacted waves (default; FAST traversal) */
 	GI_SCHEDULER_MEGAKERNEL = 1 /* one thread per path, the reference's launch shape               */
@@ -310,6 +327,10 @@ GI_API int gi_reset_counters(GiContext* ctx);
 
 /* Number of CUDA kernel launches issued by this context since creation. */
 GI_API uint64_t gi_kernel_launches(const GiContext* ctx);
+
+/* Per-kernel-class device time collected while GI_OPT_KERNEL_TIMING is on (RendererSystem::GetRenderTime's role,
+ * renderersystem.hpp:98, per kernel instead of per Draw). */
+GI_API int gi_get_kernel_times(GiContext* ctx, GiKernelTimes* out);
 
 #ifdef __cplusplus
 }
