@@ -241,6 +241,15 @@ class Device:
                                    warmup=int(warmup))
         self._check(capi.dev.gi_render_iteration(self._c, C.byref(p)), "gi_render_iteration")
 
+    def render_iterations(self, renderer, frame_seeds, max_path_length=16, d_light_samples=0, samples_per_iteration=0, num_rays_per_light_sample=0,
+                          light_cache_capacity=0):
+        """gi_render_iterations: a batch of iterations in one call (PT: overlapped wave by wave, result identical to one by one)."""
+        seeds = np.ascontiguousarray(frame_seeds, dtype=np.uint32)
+        p = capi.GiIterationParams(renderer=int(renderer), frame_seed=0, max_path_length=int(max_path_length),
+                                   num_rays_per_light_sample=int(num_rays_per_light_sample), light_cache_capacity=int(light_cache_capacity), warmup=0)
+        self._check(capi.dev.gi_render_iterations(self._c, C.byref(p), C.cast(_vp(seeds), C.POINTER(C.c_uint32)), seeds.shape[0],
+                                                  C.c_void_p(d_light_samples or None), int(samples_per_iteration)), "gi_render_iterations")
+
     def show_light_caches(self):
         self._check(capi.dev.gi_show_light_caches(self._c), "gi_show_light_caches")
 

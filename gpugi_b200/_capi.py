@@ -133,6 +133,7 @@ DEVICE_API = {
     "gi_clear_accumulator": (C.c_int, [vp]),
     "gi_alloc_light_cache": (C.c_int, [vp, u32]),
     "gi_render_iteration": (C.c_int, [vp, P(GiIterationParams)]),
+    "gi_render_iterations": (C.c_int, [vp, P(GiIterationParams), P(u32), u32, vp, u32]),
     "gi_show_light_caches": (C.c_int, [vp]),
     "gi_trace": (C.c_int, [vp, vp, u32, vp]),
     "gi_trace_device": (C.c_int, [vp, vp, u32, vp]),

@@ -785,10 +785,10 @@ struct DirectLightQuery
 	F3 radiance;      // EstimateDirectLight's result when the ray is free
 };
 
-GI_HD bool prepareDirectLight(const DFrame& f, F3 pos, F3 normal, int lightSampleIndex, F3 viewDir, const MaterialData& md, bool sampleAreaLights,
+GI_HD bool prepareDirectLight(const F4* lightSamples, F3 pos, F3 normal, int lightSampleIndex, F3 viewDir, const MaterialData& md, bool sampleAreaLights,
                               DirectLightQuery& q)
 {
-	F4 l0 = ld4(f.lightSamples + 2 * lightSampleIndex), l1 = ld4(f.lightSamples + 2 * lightSampleIndex + 1);
+	F4 l0 = ld4(lightSamples + 2 * lightSampleIndex), l1 = ld4(lightSamples + 2 * lightSampleIndex + 1);
 	F3 dir = f3(l0.x, l0.y, l0.z) - pos;
 	float lightDistSq = dot(dir, dir) + GI_DIVISOR_EPSILON;
 	float lightDist = sqrtf(lightDistSq);
@@ -823,7 +823,7 @@ GI_HD F3 estimateDirectLight(const DFrame& f, F3 pos, F3 normal, int lightSample
                              PathCounters& pc, TraceStats* st)
 {
 	DirectLightQuery q;
-	if (!prepareDirectLight(f, pos, normal, lightSampleIndex, viewDir, md, sampleAreaLights, q)) return f3(0.0f);
+	if (!prepareDirectLight(f.lightSamples, pos, normal, lightSampleIndex, viewDir, md, sampleAreaLights, q)) return f3(0.0f);
 	++pc.anyRays;
 	if (traceAny(f.scene, f.traversalMode, q.origin, q.dir, q.len, st)) return f3(0.0f);
 	return q.radiance;

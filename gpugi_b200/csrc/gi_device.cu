@@ -131,7 +131,7 @@ __global__ void k_reset_counter(uint32_t* lightCacheCount, uint32_t* lightPathLe
 #endif
 #define WF_SHADE_THREADS 128
 
-// Camera rays of all W/8 x H/8 work groups (pathtracer.comp:36-46) into the extension queue of bounce 0.
+// Camera rays of all W/8 x H/8 work groups (pathtracer.comp:36-46) at the head of this wave's extension queue.
 __global__ void __launch_bounds__(256) k_wf_generate(WfFrame w, unsigned long long* counters)
 {
 	const uint32_t stride = gridDim.x * blockDim.x;
@@ -141,34 +141,34 @@ __global__ void __launch_bounds__(256) k_wf_generate(WfFrame w, unsigned long lo
 		const int gx = int(pixel % uint32_t(w.f.width)), gy = int(pixel / uint32_t(w.f.width));
 		uint32_t seed = initRandomSeed(w.f.frameSeed, pixel);
 		const F3 dir = cameraRayDirection(w.f, seed, gx, gy);
-		F4* rp = w.q.rays[0] + 2 * size_t(slot);
-		*reinterpret_cast<float4*>(rp) = make_float4(w.f.cam.position[0], w.f.cam.position[1], w.f.cam.position[2], GI_RAY_MAX);
+		F4* rp = w.q.rays[w.wave & 1] + 2 * size_t(slot);
+		*reinterpret_cast<float4*>(rp) = make_float4(w.f.cam.position[0], w.f.cam.position[1], w.f.cam.position[2], i2f(0));
 		*reinterpret_cast<float4*>(rp + 1) = make_float4(dir.x, dir.y, dir.z, i2f(int(pixel)));
 	}
 	if (blockIdx.x == 0 && threadIdx.x == 0)
 	{
-		w.q.counts[0] = w.numPaths;
 		atomicAdd(counters + CNT_CLOSEST, (unsigned long long)w.numPaths);
 		atomicAdd(counters + CNT_CAMERA, (unsigned long long)w.numPaths);
 	}
 }
 
-// trace(b): extension rays of bounce b + shadow rays pushed by shade(b-1); persistent warps, dynamic refill.
+// trace(w): extension rays of wave w + shadow rays pushed by shade(w-1); persistent warps, dynamic refill.
 template <bool REFERENCE, bool STEPS>
-__global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MIN_BLOCKS) k_wf_trace(WfFrame w, int bounce, unsigned long long* counters)
+__global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MIN_BLOCKS) k_wf_trace(WfFrame w, unsigned long long* counters)
 {
+	uint32_t* counts = wfCounts(w, w.wave);
 	WfQueueIO io;
-	io.q.rays = w.q.rays[bounce & 1];
+	io.q.rays = w.q.rays[w.wave & 1];
 	io.q.hits = w.q.hits;
 	io.q.shadow = w.q.shadow;
 	io.q.stateC = w.q.stateC;
 	io.q.accum = w.f.accum;
 	io.q.width = w.f.width; io.q.height = w.f.height;
-	io.q.numClosest = bounce < w.f.maxPathLength ? w.q.counts[WF_COUNTS_PER_BOUNCE * bounce] : 0u;
-	io.q.numShadow = bounce > 0 ? w.q.counts[WF_COUNTS_PER_BOUNCE * (bounce - 1) + 1] : 0u;
+	io.q.numClosest = w.numCam + counts[0];
+	io.q.numShadow = counts[1];
 	WfCounters<STEPS> cnt;
-	if (REFERENCE) wfTraceLoopReference(w.f.scene, io, w.q.counts + WF_COUNTS_PER_BOUNCE * bounce + 2, cnt);
-	else wfTraceLoop(w.f.scene, io, w.q.counts + WF_COUNTS_PER_BOUNCE * bounce + 2, w.tune, cnt);
+	if (REFERENCE) wfTraceLoopReference(w.f.scene, io, counts + 2, cnt);
+	else wfTraceLoop(w.f.scene, io, counts + 2, w.tune, cnt);
 	flushWarpCounters(counters, cnt.v, WFC_COUNT);
 }
 
@@ -186,11 +186,11 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MIN_BLOCKS) k_wf_tr
 	flushWarpCounters(counters, cnt.v, WFC_COUNT);
 }
 
-// shade(b) of the path tracer: one lane per hit record, 32 consecutive queue slots per warp and fetch.
-__global__ void __launch_bounds__(WF_SHADE_THREADS) k_wf_shade_pt(WfFrame w, int bounce, unsigned long long* counters)
+// shade(w) of the path tracer: one lane per hit record, 32 consecutive queue slots per warp and fetch.
+__global__ void __launch_bounds__(WF_SHADE_THREADS) k_wf_shade_pt(WfFrame w, unsigned long long* counters)
 {
-	uint32_t* counts = w.q.counts + WF_COUNTS_PER_BOUNCE * bounce;
-	const uint32_t n = counts[0];
+	uint32_t* counts = wfCounts(w, w.wave);
+	const uint32_t n = w.numCam + counts[0];
 	unsigned cnt[WFC_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 	for (;;)
 	{
@@ -199,9 +199,26 @@ __global__ void __launch_bounds__(WF_SHADE_THREADS) k_wf_shade_pt(WfFrame w, int
 		base = __shfl_sync(0xffffffffu, base, 0);
 		if (base >= n) break;
 		const uint32_t slot = base + laneId();
-		wfShadePT(w, bounce, slot, slot < n, cnt);
+		wfShadePT(w, slot, slot < n, cnt);
 	}
 	flushWarpCounters(counters, cnt, WFC_COUNT);
+}
+
+// Final fold: the radiance sums of the iterations still held in state slots join the accumulator, per pixel in
+// iteration order (pathtracer.comp:107-109: Out[px] += vec4(color, 0)).
+__global__ void __launch_bounds__(256) k_wf_fold(float4* __restrict__ accum, const F4* __restrict__ stateC, uint32_t numIds, uint32_t numSlots,
+                                                  uint32_t firstIteration, uint32_t endIteration)
+{
+	for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < numIds; p += gridDim.x * blockDim.x)
+	{
+		float4 a = accum[p];
+		for (uint32_t k = firstIteration; k < endIteration; ++k)
+		{
+			const F4 c = ld4(stateC + size_t(k % numSlots) * numIds + p);
+			a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w;
+		}
+		accum[p] = a;
+	}
 }
 
 // sqerror.frag:16-17 + mean (texturemse.cpp:58-62): per-block partial sums in double.
@@ -280,7 +297,7 @@ struct GiContext
 	// wavefront queues
 	WfQueues wf = {};
 	uint32_t wfCountsLen = 0;
-	uint32_t wfNumIds = 0;
+	uint64_t wfStates = 0;           // allocated path state records (numSlots x numIds)
 	uint32_t* traceWork = nullptr;   // work counter of k_wf_trace_batch
 	int numSMs = 148;
 	int traceBlocksPerSM = 1, shadeBlocksPerSM = 1;
@@ -393,69 +410,100 @@ static void freeWavefront(GiContext* c)
 	cudaFree(c->wf.counts);
 	c->wf = WfQueues{};
 	c->wfCountsLen = 0;
-	c->wfNumIds = 0;
+	c->wfStates = 0;
 }
 
-// capacity: queue slots (paths per iteration); numIds: size of the per-path state arrays, which are indexed by path id
-// (PT/BPT: the pixel index, which is not dense when the frame size is not a multiple of 8).
-static int ensureWavefront(GiContext* c, uint32_t capacity, uint32_t numIds, int maxPathLength)
+// capacity: queue slots; numIds: path ids per iteration (PT/BPT: the pixel index, which is not dense when the frame size is
+// not a multiple of 8); numSlots: iterations in flight; countsLen: wave counters
+static int ensureWavefront(GiContext* c, uint64_t capacity, uint32_t numIds, uint32_t numSlots, uint32_t countsLen)
 {
-	const uint32_t countsLen = WF_COUNTS_PER_BOUNCE * uint32_t(maxPathLength + 2);
-	if (c->wf.capacity >= capacity && c->wfNumIds >= numIds && c->wfCountsLen >= countsLen) return GI_OK;
-	if (capacity > WF_ID_MASK || numIds > WF_ID_MASK) return fail(c, GI_ERR_CAPACITY, "wavefront scheduler: more than 2^30 paths per iteration");
-	GI_CUDA(c, cudaStreamSynchronize(c->stream));
-	const uint32_t cap = std::max(capacity, c->wf.capacity);
-	const uint32_t ids = std::max(numIds, c->wfNumIds);
-	const uint32_t len = std::max(countsLen, c->wfCountsLen);
-	freeWavefront(c);
-	GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->wf.rays[0]), size_t(cap) * 32));
-	GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->wf.rays[1]), size_t(cap) * 32));
-	GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->wf.hits), size_t(cap) * 8));
-	GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->wf.shadow), size_t(cap) * 48));
-	GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->wf.stateT), size_t(ids) * 16));
-	GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->wf.stateC), size_t(ids) * 16));
-	GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->wf.counts), size_t(len) * sizeof(uint32_t)));
-	c->wf.capacity = cap;
-	c->wfNumIds = ids;
-	c->wfCountsLen = len;
+	if (capacity > WF_ID_MASK || uint64_t(numIds) * numSlots > WF_ID_MASK)
+		return fail(c, GI_ERR_CAPACITY, "wavefront scheduler: more than 2^30 queue slots / path states");
+	const uint64_t states = uint64_t(numIds) * numSlots;
+	if (c->wf.capacity < capacity || c->wfStates < states)
+	{
+		GI_CUDA(c, cudaStreamSynchronize(c->stream));
+		const uint64_t cap = std::max<uint64_t>(capacity, c->wf.capacity);
+		const uint64_t st = std::max<uint64_t>(states, c->wfStates);
+		cudaFree(c->wf.rays[0]); cudaFree(c->wf.rays[1]); cudaFree(c->wf.hits); cudaFree(c->wf.shadow); cudaFree(c->wf.stateT); cudaFree(c->wf.stateC);
+		c->wf.rays[0] = c->wf.rays[1] = nullptr; c->wf.hits = nullptr; c->wf.shadow = nullptr; c->wf.stateT = c->wf.stateC = nullptr;
+		c->wf.capacity = 0; c->wfStates = 0;
+		GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->wf.rays[0]), size_t(cap) * 32));
+		GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->wf.rays[1]), size_t(cap) * 32));
+		GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->wf.hits), size_t(cap) * 8));
+		GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->wf.shadow), size_t(cap) * 48));
+		GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->wf.stateT), size_t(st) * 16));
+		GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->wf.stateC), size_t(st) * 16));
+		c->wf.capacity = uint32_t(cap);
+		c->wfStates = st;
+	}
+	if (c->wfCountsLen < countsLen)
+	{
+		GI_CUDA(c, cudaStreamSynchronize(c->stream));
+		cudaFree(c->wf.counts); c->wf.counts = nullptr; c->wfCountsLen = 0;
+		GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->wf.counts), size_t(countsLen) * sizeof(uint32_t)));
+		c->wfCountsLen = countsLen;
+	}
+	c->wf.numIds = numIds;
+	c->wf.numSlots = numSlots;
 	return GI_OK;
 }
 
-// One path-tracer iteration as waves: generate, then trace(b) / shade(b) per bounce, then the shadow rays of the last bounce.
-static int renderWavefrontPT(GiContext* c, const DFrame& f)
+// `count` path-tracer iterations as waves (gi_wavefront.cuh): wave w = generate(iteration w), trace, shade; maxPathLength
+// drain waves; final fold.  seeds[k] = FrameSeed of batch iteration k; its light samples are f.lightSamples + k * lightStride.
+static int renderWavefrontPT(GiContext* c, const DFrame& f, const uint32_t* seeds, uint32_t count, uint32_t lightStride)
 {
 	WfFrame w;
 	std::memset(&w, 0, sizeof(w));
 	w.f = f;
 	w.tilesX = c->width / 8; w.tilesY = c->height / 8; // integer division, pathtracer.cpp:50
 	w.numPaths = uint32_t(w.tilesX) * uint32_t(w.tilesY) * 64u;
-	if (w.numPaths == 0) return GI_OK;
-	int st = ensureWavefront(c, w.numPaths, uint32_t(c->width) * uint32_t(c->height), f.maxPathLength);
+	w.lightStride = lightStride;
+	if (w.numPaths == 0 || count == 0) return GI_OK;
+	const uint32_t maxLen = uint32_t(f.maxPathLength);
+	const uint32_t numSlots = std::min(count, maxLen + 1u);
+	const uint32_t numWaves = count + maxLen; // the last wave carries shadow rays only
+	// worst case (no path ever ends before maxPathLength): maxLen generations of rays share a wave.  Any batch (count > 1)
+	// reserves that much, so that batches of different length never reallocate.
+	int st = ensureWavefront(c, uint64_t(w.numPaths) * (count > 1u ? maxLen : 1u), uint32_t(c->width) * uint32_t(c->height), count > 1u ? maxLen + 1u : 1u,
+	                         WF_COUNTS_PER_WAVE * (numWaves + 1u));
 	if (st != GI_OK) return st;
 	w.q = c->wf;
+	w.q.numSlots = numSlots;
 	w.tune = c->tune;
-	GI_CUDA(c, cudaMemsetAsync(c->wf.counts, 0, size_t(c->wfCountsLen) * sizeof(uint32_t), c->stream));
+	GI_CUDA(c, cudaMemsetAsync(c->wf.counts, 0, size_t(WF_COUNTS_PER_WAVE) * (numWaves + 1u) * sizeof(uint32_t), c->stream));
+	// ids outside the W/8 x H/8 tiles are never written by shade(); the fold reads them
+	if (w.numPaths != w.q.numIds) GI_CUDA(c, cudaMemsetAsync(c->wf.stateC, 0, size_t(numSlots) * w.q.numIds * 16, c->stream));
 	const unsigned traceGrid = unsigned(c->numSMs * c->traceBlocksPerSM), shadeGrid = unsigned(c->numSMs * c->shadeBlocksPerSM);
 	const bool ref = f.traversalMode == GI_TRAVERSAL_REFERENCE;
-	auto trace = [&](int b) {
-		if (ref) k_wf_trace<true, true><<<traceGrid, WF_TRACE_THREADS, 0, c->stream>>>(w, b, c->counters);
-		else if (c->countSteps) k_wf_trace<false, true><<<traceGrid, WF_TRACE_THREADS, 0, c->stream>>>(w, b, c->counters);
-		else k_wf_trace<false, false><<<traceGrid, WF_TRACE_THREADS, 0, c->stream>>>(w, b, c->counters);
+	timingMark(c, -1);
+	for (uint32_t wave = 0; wave < numWaves; ++wave)
+	{
+		w.wave = int(wave);
+		w.numCam = wave < count ? w.numPaths : 0u;
+		w.pushBase = wave + 1u < count ? w.numPaths : 0u;
+		if (wave < count)
+		{
+			w.f.frameSeed = seeds[wave];
+			k_wf_generate<<<unsigned(c->numSMs) * 8u, 256, 0, c->stream>>>(w, c->counters);
+			++c->launches;
+			timingMark(c, GI_KERNEL_GENERATE);
+		}
+		if (ref) k_wf_trace<true, true><<<traceGrid, WF_TRACE_THREADS, 0, c->stream>>>(w, c->counters);
+		else if (c->countSteps) k_wf_trace<false, true><<<traceGrid, WF_TRACE_THREADS, 0, c->stream>>>(w, c->counters);
+		else k_wf_trace<false, false><<<traceGrid, WF_TRACE_THREADS, 0, c->stream>>>(w, c->counters);
 		++c->launches;
 		timingMark(c, GI_KERNEL_TRACE);
-	};
-	timingMark(c, -1);
-	k_wf_generate<<<unsigned(c->numSMs) * 8u, 256, 0, c->stream>>>(w, c->counters);
-	++c->launches;
-	timingMark(c, GI_KERNEL_GENERATE);
-	for (int b = 0; b < f.maxPathLength; ++b)
-	{
-		trace(b);
-		k_wf_shade_pt<<<shadeGrid, WF_SHADE_THREADS, 0, c->stream>>>(w, b, c->counters);
-		++c->launches;
-		timingMark(c, GI_KERNEL_SHADE);
+		if (wave + 1u < numWaves)
+		{
+			k_wf_shade_pt<<<shadeGrid, WF_SHADE_THREADS, 0, c->stream>>>(w, c->counters);
+			++c->launches;
+			timingMark(c, GI_KERNEL_SHADE);
+		}
 	}
-	trace(f.maxPathLength);
+	k_wf_fold<<<unsigned(c->numSMs) * 8u, 256, 0, c->stream>>>(reinterpret_cast<float4*>(c->accum), c->wf.stateC, w.q.numIds, numSlots, count - numSlots, count);
+	++c->launches;
+	timingMark(c, GI_KERNEL_OTHER);
 	timingCollect(c);
 	return GI_OK;
 }
@@ -764,7 +812,7 @@ int gi_render_iteration(GiContext* c, const GiIterationParams* p)
 	case GI_RENDERER_PT:
 		if (c->scheduler == GI_SCHEDULER_WAVEFRONT)
 		{
-			st = renderWavefrontPT(c, f);
+			st = renderWavefrontPT(c, f, &p->frame_seed, 1u, 0u);
 			if (st != GI_OK) return st;
 		}
 		else if (pixelGrid.x && pixelGrid.y)
@@ -811,6 +859,41 @@ int gi_render_iteration(GiContext* c, const GiIterationParams* p)
 	default: return fail(c, GI_ERR_INVALID, "unknown renderer");
 	}
 	GI_CUDA(c, cudaGetLastError());
+	return GI_OK;
+}
+
+int gi_render_iterations(GiContext* c, const GiIterationParams* p, const uint32_t* frame_seeds, uint32_t count, const GiLightSample* d_light_samples,
+                         uint32_t samples_per_iteration)
+{
+	if (!c || !p || (count && !frame_seeds)) return GI_ERR_INVALID;
+	if (count == 0) return GI_OK;
+	if (d_light_samples)
+	{
+		if (samples_per_iteration == 0) return fail(c, GI_ERR_INVALID, "gi_render_iterations: samples_per_iteration must be positive");
+		int st = gi_set_light_samples_device(c, d_light_samples, samples_per_iteration);
+		if (st != GI_OK) return st;
+	}
+	int st = checkRenderState(c);
+	if (st != GI_OK) return st;
+	if (p->max_path_length <= 0) return fail(c, GI_ERR_INVALID, "max_path_length must be positive");
+	GI_CUDA(c, cudaSetDevice(c->device));
+	if (p->renderer == GI_RENDERER_PT && c->scheduler == GI_SCHEDULER_WAVEFRONT)
+	{
+		DFrame f = makeFrame(c, p);
+		st = renderWavefrontPT(c, f, frame_seeds, count, d_light_samples ? 2u * samples_per_iteration : 0u);
+		if (st != GI_OK) return st;
+		GI_CUDA(c, cudaGetLastError());
+		return GI_OK;
+	}
+	// every other renderer / scheduler: one iteration after the other
+	for (uint32_t k = 0; k < count; ++k)
+	{
+		GiIterationParams q = *p;
+		q.frame_seed = frame_seeds[k];
+		if (d_light_samples) c->externalLightSamples = reinterpret_cast<const F4*>(d_light_samples + size_t(k) * samples_per_iteration);
+		st = gi_render_iteration(c, &q);
+		if (st != GI_OK) return st;
+	}
 	return GI_OK;
 }
 

@@ -4,22 +4,30 @@
 // (pathtracer.comp:16-110, lighttracer.comp:49-193, pathtracer_bidir.comp:16-251).  On a GPU without RT cores
 // that shape is divergence-bound: Russian roulette ends most paths after 1-2 bounces while a few run to 16, and
 // inner-node / leaf / shading code serialise inside a warp (profiles/r01_ncu_pathtrace.md: 6.95 of 32 lanes active).
-// Here an iteration is a sequence of waves over HBM-resident queues:
+// Here the work is a sequence of WAVES over HBM-resident queues, and a wave mixes all iterations (sample passes) that are
+// in flight:
 //
-//   generate -> [ trace(b) -> shade(b) ] for b = 0 .. maxPathLength-1 -> trace(maxPathLength)   (shadow rays only)
+//   wave w:  generate(w)   camera rays of iteration w (while w < count)            -> extension queue of wave w
+//            trace(w)      extension rays of wave w + shadow rays pushed by shade(w-1)
+//            shade(w)      one lane per hit: bounce b of iteration w-b             -> extension / shadow queue of wave w+1
 //
-//   trace(b)  persistent warps; every lane owns one ray and refills itself from the extension queue of bounce b
-//             and the shadow queue of bounce b-1 as soon as enough lanes of its warp ran dry (ballot + popc, one
-//             atomicAdd per warp).  Inner-node steps and leaf steps are scheduled per warp by vote so that the two
-//             code paths never serialise against each other.  Same tree, same box/triangle arithmetic, same
-//             ambiguity rule as traceFast() (gi_core.h) -- the result per ray is bit-identical.
-//   shade(b)  one lane per hit: GetTriangleHitInfo, SampleMaterialData, emission, next-event estimation (pushes a
-//             shadow ray carrying its contribution), SampleBSDF, Russian roulette, and a ballot-compacted push of
-//             the surviving ray into the queue of bounce b+1.
+//   trace     persistent warps; every lane owns one ray and refills itself from the queue as soon as enough lanes of its
+//             warp ran dry (ballot + popc, one atomicAdd per warp).  Inner-node steps and leaf steps are scheduled per
+//             warp by vote so that the two code paths never serialise against each other.  Same tree, same box/triangle
+//             arithmetic, same ambiguity rule as traceFast() (gi_core.h) -- the result per ray is bit-identical.
+//   shade     GetTriangleHitInfo, SampleMaterialData, emission, next-event estimation (pushes a shadow ray carrying its
+//             contribution), SampleBSDF, Russian roulette, and a ballot-compacted push of the surviving ray.
 //
-// Every path keeps the reference's private RNG stream and its floating-point operation order (the radiance sum of a
-// path is kept in the path state and added to the accumulator once, at the path's end), so an iteration is a
-// deterministic function of (scene, camera, frame seed, light samples) exactly as in the megakernel.
+// Russian roulette ends most paths after 1-2 bounces while a few run to 16: rendered one iteration at a time, bounces
+// 4..16 are ~30 launches that keep a handful of warps busy (1 ms of a 3.6 ms iteration for 1.5 % of the rays).  With the
+// iterations of a batch overlapped (gi_render_iterations), every wave carries the bounce-0 rays of iteration w, the
+// bounce-1 rays of iteration w-1, ... : constant work per wave, three launches per iteration, and the tail is paid once
+// per batch.  gi_render_iteration is the same code with count = 1.
+//
+// Determinism.  Every path keeps the reference's private RNG stream and its floating-point operation order; the radiance
+// sum of a path lives in its state record (slot = iteration mod S, S = maxPathLength + 1 slots) and is added to the
+// accumulator when the slot is recycled S waves later (or by the final fold), i.e. per pixel in iteration order.  A batch is
+// therefore bit-identical to the same iterations rendered one by one.
 #pragma once
 
 #include "gi_core.h"
@@ -28,27 +36,28 @@
 namespace gik {
 
 // ------------------------------------------------------------------ queues (HBM)
-// ray record      2 x F4: (origin.xyz, tMax) (direction.xyz, path word)
+// ray record      2 x F4: (origin.xyz, bounce bits) (direction.xyz, path word); extension rays always start with RAY_MAX
 // hit record      float2: (t, leafTri bits), leafTri = -1: miss; always the reference's exact answer
 // shadow record   3 x F4: (origin.xyz, rayLength) (direction.xyz, target word) (value.rgb, -)
 // path word       bits 0..29 path id (pixel index / light path index), bit 30 didNEE
-// target word     bits 0..29 path id or pixel index, bit 30 splat (atomic add into the accumulator instead of the
-//                 path's radiance sum), bit 31 terminal (flush the path's radiance sum to the accumulator)
+// target word     bits 0..29 state index (slot * numIds + path id) or pixel index, bit 30 splat (atomic add into the
+//                 accumulator instead of the path's radiance sum)
 #define WF_ID_MASK 0x3fffffffu
 #define WF_FLAG_NEE 0x40000000u
 #define WF_FLAG_SPLAT 0x40000000u
-#define WF_FLAG_TERMINAL 0x80000000u
-#define WF_COUNTS_PER_BOUNCE 4 // [0] extension rays of bounce b, [1] shadow rays pushed by shade(b), [2] trace work counter, [3] shade work counter
+#define WF_COUNTS_PER_WAVE 4 // [0] extension rays pushed by shade(w-1), [1] shadow rays pushed by shade(w-1), [2] trace work counter, [3] shade work counter
 
 struct WfQueues
 {
 	F4* rays[2];
 	float2* hits;
 	F4* shadow;
-	F4* stateT;          // (throughput.xyz, seed bits)
-	F4* stateC;          // (radiance sum.xyz, -)
-	uint32_t* counts;    // WF_COUNTS_PER_BOUNCE x (maxPathLength + 2), zeroed per iteration
+	F4* stateT;          // numSlots x numIds: (throughput.xyz, seed bits)
+	F4* stateC;          // numSlots x numIds: (radiance sum.xyz, alpha increment)
+	uint32_t* counts;    // WF_COUNTS_PER_WAVE x (waves of the batch + 1), zeroed per batch
 	uint32_t capacity;   // slots per queue
+	uint32_t numIds;     // path ids per iteration (PT/BPT: width x height)
+	uint32_t numSlots;   // S iterations in flight
 };
 
 // tuning knobs (uniform kernel arguments so that one build can be swept)
@@ -103,35 +112,20 @@ GI_D void wfSplat(float* accum, int width, int height, uint32_t pixel, F3 v)
 
 GI_D void wfFinishShadow(const WfTraceIO& io, uint32_t slot, bool occluded)
 {
+	if (occluded) return;
 	const F4 s1 = ld4(io.shadow + 3 * size_t(slot) + 1);
+	const F4 v = ld4(io.shadow + 3 * size_t(slot) + 2);
 	const uint32_t word = uint32_t(f2i(s1.w));
 	const uint32_t id = word & WF_ID_MASK;
 	if (word & WF_FLAG_SPLAT)
 	{
-		if (!occluded)
-		{
-			const F4 v = ld4(io.shadow + 3 * size_t(slot) + 2);
-			wfSplat(io.accum, io.width, io.height, id, f3(v.x, v.y, v.z));
-		}
+		wfSplat(io.accum, io.width, io.height, id, f3(v.x, v.y, v.z));
 		return;
 	}
-	const bool terminal = (word & WF_FLAG_TERMINAL) != 0u;
-	if (occluded && !terminal) return;
+	// the path's radiance sum: one shadow ray per path and wave, and shade() is another kernel -> exclusive
 	float4 c = *reinterpret_cast<const float4*>(io.stateC + id);
-	if (!occluded)
-	{
-		const F4 v = ld4(io.shadow + 3 * size_t(slot) + 2);
-		c.x += v.x; c.y += v.y; c.z += v.z;
-	}
-	if (terminal)
-	{
-		float4* px = reinterpret_cast<float4*>(io.accum) + id;
-		float4 a = *px;
-		a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w;
-		*px = a;
-	}
-	else
-		*reinterpret_cast<float4*>(io.stateC + id) = c;
+	c.x += v.x; c.y += v.y; c.z += v.z;
+	*reinterpret_cast<float4*>(io.stateC + id) = c;
 }
 
 // The persistent trace loop.  IO provides: total(), load(index, lane state), finish(lane state).
@@ -234,7 +228,7 @@ struct WfQueueIO
 		const bool isAny = index >= q.numClosest;
 		const F4* p = isAny ? q.shadow + 3 * size_t(index - q.numClosest) : q.rays + 2 * size_t(index);
 		const F4 r0 = ld4(p), r1 = ld4(p + 1);
-		wfBegin(L, s, f3(r0.x, r0.y, r0.z), f3(r1.x, r1.y, r1.z), r0.w, isAny, index, cnt);
+		wfBegin(L, s, f3(r0.x, r0.y, r0.z), f3(r1.x, r1.y, r1.z), isAny ? r0.w : GI_RAY_MAX, isAny, index, cnt);
 	}
 	template <class CNT>
 	GI_D void finish(const DScene& s, WfLane& L, CNT& cnt) const
@@ -282,11 +276,15 @@ struct WfBatchIO
 // ------------------------------------------------------------------ path tracer waves (pathtracer.comp:16-110)
 struct WfFrame
 {
-	DFrame f;
+	DFrame f;                // f.frameSeed: seed of the iteration generated in this wave; f.lightSamples: samples of batch iteration 0
 	WfQueues q;
 	WfTune tune;
 	int tilesX, tilesY;      // W/8, H/8 work groups (pathtracer.cpp:50)
-	uint32_t numPaths;
+	uint32_t numPaths;       // paths per iteration
+	int wave;                // wave index inside the batch; bounce b of this wave belongs to batch iteration wave - b
+	uint32_t numCam;         // freshly generated rays at the head of this wave's extension queue (numPaths or 0)
+	uint32_t pushBase;       // ... of the next wave's extension queue: pushed rays are placed behind them
+	uint32_t lightStride;    // F4 elements between the light samples of consecutive iterations (0: the same set for all)
 };
 
 // queue slot -> pixel: 8x8 tiles in row-major tile order, row-major inside the tile (the reference's work-group shape)
@@ -297,9 +295,11 @@ GI_D uint32_t wfSlotToPixel(const WfFrame& w, uint32_t slot)
 	return (tx * 8u + (l & 7u)) + (ty * 8u + (l >> 3)) * uint32_t(w.f.width);
 }
 
-// Shades the hit of one extension ray of bounce `bounce`.  Returns nothing; pushes at most one shadow ray and one
-// extension ray (warp-compacted, so all 32 lanes call this; `valid` masks the tail).
-GI_D void wfShadePT(const WfFrame& w, int bounce, uint32_t slot, bool valid, unsigned* cnt)
+GI_D uint32_t* wfCounts(const WfFrame& w, int wave) { return w.q.counts + WF_COUNTS_PER_WAVE * size_t(wave); }
+
+// Shades the hit of one extension ray of this wave.  Pushes at most one shadow ray and one extension ray
+// (warp-compacted, so all 32 lanes call this; `valid` masks the tail).
+GI_D void wfShadePT(const WfFrame& w, uint32_t slot, bool valid, unsigned* cnt)
 {
 	const DFrame& f = w.f;
 	const WfQueues& q = w.q;
@@ -307,33 +307,47 @@ GI_D void wfShadePT(const WfFrame& w, int bounce, uint32_t slot, bool valid, uns
 	DirectLightQuery nee;
 	F3 neeValue = f3(0.0f);
 	F3 origin = f3(0.0f), dir = f3(0.0f, 0.0f, 1.0f);
-	F3 color = f3(0.0f), pathThroughput = f3(1.0f);
-	uint32_t seed = 0, id = 0;
+	uint32_t id = 0, sidx = 0;
+	int bounce = 0;
 	bool didNEE = false;
 	if (valid)
 	{
-		const F4* rp = q.rays[bounce & 1] + 2 * size_t(slot);
+		const F4* rp = q.rays[w.wave & 1] + 2 * size_t(slot);
 		const F4 r0 = ld4(rp), r1 = ld4(rp + 1);
 		const float2 hrec = q.hits[slot];
 		const uint32_t word = uint32_t(f2i(r1.w));
 		id = word & WF_ID_MASK;
 		didNEE = (word & WF_FLAG_NEE) != 0u;
+		bounce = f2i(r0.w);
+		const uint32_t iteration = uint32_t(w.wave - bounce);         // batch-relative
+		sidx = (iteration % q.numSlots) * q.numIds + id;
 		origin = f3(r0.x, r0.y, r0.z); dir = f3(r1.x, r1.y, r1.z);
+		F3 color = f3(0.0f), pathThroughput = f3(1.0f);
+		uint32_t seed;
 		if (bounce == 0)
 		{
 			seed = initRandomSeed(f.frameSeed, id);
 			random2(seed); // the two draws of the sub-pixel jitter (pathtracer.comp:42)
+			if (iteration >= q.numSlots)
+			{
+				// the slot is recycled: iteration - S is complete, its radiance joins the accumulator (pathtracer.comp:107-109;
+				// per pixel in iteration order, alpha += 0)
+				const float4 old = *reinterpret_cast<const float4*>(q.stateC + sidx);
+				float4* px = reinterpret_cast<float4*>(f.accum) + id;
+				float4 a = *px;
+				a.x += old.x; a.y += old.y; a.z += old.z;
+				*px = a;
+			}
 		}
 		else
 		{
-			const float4 t = *reinterpret_cast<const float4*>(q.stateT + id);
-			const float4 c = *reinterpret_cast<const float4*>(q.stateC + id);
+			const float4 t = *reinterpret_cast<const float4*>(q.stateT + sidx);
+			const float4 c = *reinterpret_cast<const float4*>(q.stateC + sidx);
 			pathThroughput = f3(t.x, t.y, t.z); seed = uint32_t(f2i(t.w));
 			color = f3(c.x, c.y, c.z);
 		}
 		const float tHit = hrec.x;
 		const int leafTri = f2i(hrec.y);
-		bool terminated = true;
 		if (leafTri < 0)
 			color = color + pathThroughput * environmentRadiance(f, dir);
 		else
@@ -352,7 +366,7 @@ GI_D void wfShadePT(const WfFrame& w, int bounce, uint32_t slot, bool valid, uns
 			didNEE = md.Reflectiveness.w < 500.0f;
 			{
 				const int sampleIndex = int(randomUInt(seed) % uint32_t(f.numLightSamples));
-				if (prepareDirectLight(f, origin, hitNormal, sampleIndex, dir, md, didNEE, nee))
+				if (prepareDirectLight(f.lightSamples + size_t(iteration) * w.lightStride, origin, hitNormal, sampleIndex, dir, md, didNEE, nee))
 				{
 					pushShadow = true;
 					neeValue = nee.radiance * pathThroughput * float(f.numLightSamples);
@@ -367,40 +381,29 @@ GI_D void wfShadePT(const WfFrame& w, int bounce, uint32_t slot, bool valid, uns
 			if (!(randomFloat(seed) >= cont) && bounce + 1 < f.maxPathLength)
 			{
 				pathThroughput = pathThroughput / cont;
-				terminated = false;
 				pushRay = true;
 			}
 		}
-		if (terminated && !pushShadow)
-		{
-			// pixel-exclusive read-modify-write (pathtracer.comp:107-109), alpha += 0
-			float4* px = reinterpret_cast<float4*>(f.accum) + id;
-			float4 a = *px;
-			a.x += color.x; a.y += color.y; a.z += color.z;
-			*px = a;
-		}
-		else
-			*reinterpret_cast<float4*>(q.stateC + id) = make_float4(color.x, color.y, color.z, 0.0f);
-		if (pushRay) *reinterpret_cast<float4*>(q.stateT + id) = make_float4(pathThroughput.x, pathThroughput.y, pathThroughput.z, i2f(int(seed)));
+		*reinterpret_cast<float4*>(q.stateC + sidx) = make_float4(color.x, color.y, color.z, 0.0f);
+		if (pushRay) *reinterpret_cast<float4*>(q.stateT + sidx) = make_float4(pathThroughput.x, pathThroughput.y, pathThroughput.z, i2f(int(seed)));
 	}
-	uint32_t* counts = q.counts + WF_COUNTS_PER_BOUNCE * bounce;
-	const uint32_t sslot = warpPush(counts + 1, pushShadow);
+	uint32_t* next = wfCounts(w, w.wave + 1);
+	const uint32_t sslot = warpPush(next + 1, pushShadow);
 	if (pushShadow)
 	{
 		++cnt[WFC_ANY];
 		F4* sp = q.shadow + 3 * size_t(sslot);
-		const uint32_t word = id | (pushRay ? 0u : WF_FLAG_TERMINAL);
 		*reinterpret_cast<float4*>(sp) = make_float4(nee.origin.x, nee.origin.y, nee.origin.z, nee.len);
-		*reinterpret_cast<float4*>(sp + 1) = make_float4(nee.dir.x, nee.dir.y, nee.dir.z, i2f(int(word)));
+		*reinterpret_cast<float4*>(sp + 1) = make_float4(nee.dir.x, nee.dir.y, nee.dir.z, i2f(int(sidx)));
 		*reinterpret_cast<float4*>(sp + 2) = make_float4(neeValue.x, neeValue.y, neeValue.z, 0.0f);
 	}
-	const uint32_t rslot = warpPush(counts + WF_COUNTS_PER_BOUNCE, pushRay);
+	const uint32_t rslot = w.pushBase + warpPush(next, pushRay);
 	if (pushRay)
 	{
 		++cnt[WFC_CLOSEST];
-		F4* rp = q.rays[(bounce + 1) & 1] + 2 * size_t(rslot);
+		F4* rp = q.rays[(w.wave + 1) & 1] + 2 * size_t(rslot);
 		const uint32_t word = id | (didNEE ? WF_FLAG_NEE : 0u);
-		*reinterpret_cast<float4*>(rp) = make_float4(origin.x, origin.y, origin.z, GI_RAY_MAX);
+		*reinterpret_cast<float4*>(rp) = make_float4(origin.x, origin.y, origin.z, i2f(bounce + 1));
 		*reinterpret_cast<float4*>(rp + 1) = make_float4(dir.x, dir.y, dir.z, i2f(int(word)));
 	}
 }

@@ -168,7 +168,7 @@ enum {
 	GI_OPT_WF_REFILL_THRESHOLD = 3, /* idle lanes per warp that trigger a refill from the ray queue  */
 	GI_OPT_WF_MIN_INNER = 4,        /* keep taking inner-node steps while this many of 32 active lanes are at inner nodes */
 	GI_OPT_WF_BLOCKS_PER_SM = 6,    /* resident trace blocks per SM (0 = occupancy maximum)          */
-	GI_OPT_COUNT_STEPS = 7          /* 1 = the wavefront walk counts its box / triangle tests (GiCounters::node_tests,
+	GI_OPT_COUNT_STEPS = 7,         /* 1 = the wavefront walk counts its box / triangle tests (GiCounters::node_tests,
 	                                   triangle_tests); off by default: two counters less in the hot loop.  The megakernel and
 	                                   GI_TRAVERSAL_REFERENCE always count. */
 	GI_OPT_KERNEL_TIMING = 8        /* 1 = bracket every kernel launch of gi_render_iteration with CUDA events on the launching
@@ -292,6 +292,18 @@ GI_API int gi_alloc_light_cache(GiContext* ctx, uint32_t capacity);
  * BidirectionalPathtracer (bidirectionalpathtracer.cpp:190-200; with params->warmup the
  * warm-up pass of :90-93).  Adds one sample pass into the accumulator.  Asynchronous. */
 GI_API int gi_render_iteration(GiContext* ctx, const GiIterationParams* params);
+
+/* `count` iterations in one call: the application's render loop (application.cpp: `while(...) { Update(); Draw(); }`,
+ * script command `waitIterations N`, scriptprocessing.cpp) handed to the device as a whole.  frame_seeds[k] is
+ * PerIteration.FrameSeed of the k-th iteration (params->frame_seed is ignored); d_light_samples (DEVICE memory, count x
+ * samples_per_iteration records, iteration-major; must stay valid until the call's work has finished) holds the initial
+ * light samples of every iteration, or NULL to use the set installed by gi_set_light_samples for all of them.
+ * PT + wavefront scheduler: the iterations are overlapped wave by wave (bounce b of iteration k runs together with
+ * bounce b+1 of iteration k-1, ...), which removes the per-iteration tail of nearly empty bounces; the accumulator
+ * receives every iteration's radiance per pixel in iteration order, so the result is bit-identical to `count` calls of
+ * gi_render_iteration.  Other renderers / schedulers: the iterations run one after the other. */
+GI_API int gi_render_iterations(GiContext* ctx, const GiIterationParams* params, const uint32_t* frame_seeds, uint32_t count,
+                                const GiLightSample* d_light_samples, uint32_t samples_per_iteration);
 
 /* Replaces RendererSystem::DispatchShowLightCacheShader (renderersystem.cpp:277-281):
  * splats the directly visible initial light samples (showlightcaches.comp). */

@@ -44,7 +44,9 @@ def main():
     ls.seed(4242)
     samples = [ls.generate(128) for _ in range(args.iters + 2)]
 
-    def run(label, opts, iters=args.iters):
+    d_all = torch.from_numpy(np.concatenate(samples).view(np.uint8).reshape(-1)).cuda()
+
+    def run(label, opts, iters=args.iters, batch=False):
         for k, v in opts.items():
             dev.set_option(k, v)
         dev.clear(); dev.reset_counters()
@@ -56,8 +58,11 @@ def main():
         dev.set_light_samples(samples[0])
         dev.synchronize()
         e0.record(stream)
-        for i in range(iters):
-            dev.render_iteration(g.GI_RENDERER_PT, g.wang_hash(i), 16)
+        if batch:
+            dev.render_iterations(g.GI_RENDERER_PT, [g.wang_hash(i) for i in range(iters)], 16)
+        else:
+            for i in range(iters):
+                dev.render_iteration(g.GI_RENDERER_PT, g.wang_hash(i), 16)
         e1.record(stream)
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / iters
@@ -72,13 +77,16 @@ def main():
 
     results = []
     if args.only_wavefront:
-        run("wavefront default", {g.GI_OPT_SCHEDULER: g.GI_SCHEDULER_WAVEFRONT})
+        run("wavefront batch", {g.GI_OPT_SCHEDULER: g.GI_SCHEDULER_WAVEFRONT}, batch=True)
         dev.close()
         return
     ref_img, r = run("megakernel", {g.GI_OPT_SCHEDULER: g.GI_SCHEDULER_MEGAKERNEL})
     results.append(r)
     img, r = run("wavefront default", {g.GI_OPT_SCHEDULER: g.GI_SCHEDULER_WAVEFRONT})
     results.append(r)
+    img_b, r = run("wavefront batch", {g.GI_OPT_SCHEDULER: g.GI_SCHEDULER_WAVEFRONT}, batch=True)
+    results.append(r)
+    print("batch vs sequential wavefront identical=%s" % np.array_equal(img, img_b), flush=True)
     diff = np.abs(img - ref_img)
     rel = diff[..., :3].max(axis=2) / (np.abs(ref_img[..., :3]).max(axis=2) + 1e-6)
     print("wavefront vs megakernel: identical=%s max_abs=%g pixels_rel>1e-3: %.4f%%" % (np.array_equal(img, ref_img), diff.max(), 100 * (rel > 1e-3).mean()), flush=True)
