@@ -886,26 +886,36 @@ GI_HD void pathtracePixel(const DFrame& f, int gx, int gy, PathCounters& pc, Tra
 GI_HD float misHeuristic(float p) { return fminf(1e18f, p); }
 GI_HD float distanceMISHeuristic(float d) { return misHeuristic(d * d); }
 
-// ProjectToScreen, screenreproject.glsl:55-227 (box filter, no CHAINED_MIS)
-GI_HD void projectToScreen(const DFrame& f, F3 pos, F3 inDir, F3 geometryNormal, F3 shadingNormal, const MaterialData& md, F3 pathThroughput, bool computeMIS,
-                           PathCounters& pc, TraceStats* st)
+// ProjectToScreen, screenreproject.glsl:55-227 (box filter, no CHAINED_MIS), split in two like EstimateDirectLight: everything
+// but the any-hit query towards the camera (prepareScreenSplat; the splatted value does not depend on the query), and the
+// query + atomic splat (projectToScreen, the megakernel's form; the wavefront scheduler queues the query instead).
+struct ScreenSplatQuery
+{
+	F3 origin, dir;   // any-hit ray towards the camera
+	float len;
+	int px, py;       // target pixel; round() may yield W or H -> bounds-checked by the consumer
+	F3 value;         // what WriteAtomic adds when the ray is free
+};
+
+GI_HD bool prepareScreenSplat(const DFrame& f, F3 pos, F3 inDir, F3 geometryNormal, F3 shadingNormal, const MaterialData& md, F3 pathThroughput, bool computeMIS,
+                              ScreenSplatQuery& q)
 {
 	const F3 camPos = f3(f.cam.position), camU = f3(f.cam.u), camV = f3(f.cam.v), camW = f3(f.cam.w);
 	F3 toCam = camPos - pos;
 	float camViewDotRay = -dot(camW, toCam);
-	if (!(camViewDotRay > 0.0f)) return;
+	if (!(camViewDotRay > 0.0f)) return false;
 	float sx = -dot(camU, toCam) / camViewDotRay, sy = -dot(camV, toCam) / camViewDotRay;
 	sx /= dot(camU, camU);
 	sy /= dot(camV, camV);
-	if (!(sx >= -1.0f && sx < 1.0f && sy > -1.0f && sy <= 1.0f)) return;
+	if (!(sx >= -1.0f && sx < 1.0f && sy > -1.0f && sy <= 1.0f)) return false;
 	float cameraDistSq = dot(toCam, toCam);
 	float cameraDist = sqrtf(cameraDistSq);
 	toCam = toCam / cameraDist;
-	F3 origin = toCam * GI_RAY_HIT_EPSILON + pos;
-	int pcx = int(roundf((sx * 0.5f + 0.5f) * float(f.width)));
-	int pcy = int(roundf((sy * 0.5f + 0.5f) * float(f.height)));
-	++pc.anyRays;
-	if (traceAny(f.scene, f.traversalMode, origin, toCam, cameraDist, st)) return;
+	q.origin = toCam * GI_RAY_HIT_EPSILON + pos;
+	q.dir = toCam;
+	q.len = cameraDist;
+	q.px = int(roundf((sx * 0.5f + 0.5f) * float(f.width)));
+	q.py = int(roundf((sy * 0.5f + 0.5f) * float(f.height)));
 	float cosAtCamera = saturate(camViewDotRay / cameraDist);
 	float fluxToIrradiance = adjointShadingNormalCorrectedOutDotN(inDir, toCam, geometryNormal, shadingNormal) /
 	                         (cosAtCamera * cosAtCamera * cosAtCamera * f.cam.pixel_area * cameraDistSq);
@@ -917,7 +927,18 @@ GI_HD void projectToScreen(const DFrame& f, F3 pos, F3 inDir, F3 geometryNormal,
 		float lightToEye = misHeuristic(pdf);
 		bsdf = bsdf * (eyeToLight / fmaxf(lightToEye + eyeToLight, GI_DIVISOR_EPSILON));
 	}
-	splatAtomic(f.accum, f.width, f.height, pcx, pcy, pathThroughput * fluxToIrradiance * bsdf, pc);
+	q.value = pathThroughput * fluxToIrradiance * bsdf;
+	return true;
+}
+
+GI_HD void projectToScreen(const DFrame& f, F3 pos, F3 inDir, F3 geometryNormal, F3 shadingNormal, const MaterialData& md, F3 pathThroughput, bool computeMIS,
+                           PathCounters& pc, TraceStats* st)
+{
+	ScreenSplatQuery q;
+	if (!prepareScreenSplat(f, pos, inDir, geometryNormal, shadingNormal, md, pathThroughput, computeMIS, q)) return;
+	++pc.anyRays;
+	if (traceAny(f.scene, f.traversalMode, q.origin, q.dir, q.len, st)) return;
+	splatAtomic(f.accum, f.width, f.height, q.px, q.py, q.value, pc);
 }
 
 // saveLightCache, lighttracer.comp:23-45.  Entry = 4 x F4 (64 bytes):
@@ -1050,6 +1071,85 @@ GI_HD void showLightCache(const DFrame& f, int index, PathCounters& pc, TraceSta
 	splatAtomic(f.accum, f.width, f.height, pcx, pcy, f3(l1.x, l1.y, l1.z) * intensityToRadiance, pc);
 }
 
+// The connection of an eye-path vertex with one random light-cache entry (pathtracer_bidir.comp:97-205), without the any-hit
+// query: returns false when no query is made (combined path too long), else the shadow ray and the radiance the
+// connection adds when the ray is free.  Draws one random number in either case.
+struct ConnectionQuery
+{
+	F3 origin, dir;
+	float len;
+	F3 value;
+};
+
+GI_HD bool prepareConnection(const DFrame& f, uint32_t actualNumEntries, float lightSampleWeight, F3 origin, F3 dir, F3 hitNormal, const MaterialData& md, int i,
+                             float rayHit, float lastConnectionProbability, F3 pathThroughput, uint32_t& seed, ConnectionQuery& q)
+{
+	uint32_t idx = randomUInt(seed) % actualNumEntries;
+	const F4* e = f.lightCache + 4 * size_t(idx);
+	F4 e2 = ld4(e + 2);
+	int pathLength = f2i(e2.w) + i + 1;
+	if (pathLength > f.maxPathLength) return false;
+	F4 e1 = ld4(e + 1);
+	F3 ldir = f3(e1.x, e1.y, e1.z) - origin;
+	float lightDistSq = dot(ldir, ldir);
+	float lightDist = sqrtf(lightDistSq);
+	ldir = ldir / fmaxf(lightDist, GI_DIVISOR_EPSILON);
+	q.origin = GI_RAY_HIT_EPSILON * ldir + origin;
+	q.dir = ldir;
+	q.len = lightDist - GI_RAY_HIT_EPSILON * 2;
+	F4 e0 = ld4(e), e3 = ld4(e + 3);
+	int lightMaterialIndex = f2i(e0.w);
+	F3 lightFlux = f3(e0.x, e0.y, e0.z);
+	F3 lightNormal = f3(0.0f, 1.0f, 0.0f);
+	float lightPathToEye;
+	float cosLight = 0.0f;
+	F3 lightIntensity;
+	float cosCamera = fabsf(dot(ldir, hitNormal));
+	const float normal0 = e1.w, normal1 = e2.z;
+	if (normal1 < 1.5f)
+	{
+		lightNormal = unpackNormalNoSat(normal0, normal1);
+		cosLight = fabsf(dot(ldir, lightNormal));
+	}
+	float pdf;
+	F3 bsdf = BSDF(dir, ldir, md, hitNormal, pdf);
+	float eyeToLight = misHeuristic(pdf);
+	float mis;
+	if (i > 0)
+	{
+		eyeToLight *= distanceMISHeuristic(rayHit);
+		mis = lastConnectionProbability / fmaxf(lastConnectionProbability + eyeToLight, GI_DIVISOR_EPSILON);
+		if (md.Reflectiveness.w >= 100.0f) mis = 1.0f;
+	}
+	else
+		mis = eyeToLight / fmaxf(lastConnectionProbability + eyeToLight, GI_DIVISOR_EPSILON);
+	float misLight = 1.0f;
+	if (normal1 < 1.5f)
+	{
+		if (lightMaterialIndex != -1)
+		{
+			F2 ltc; ltc.x = e2.x; ltc.y = e2.y;
+			MaterialData lmd = sampleMaterialData(f.scene, lightMaterialIndex, ltc);
+			F3 incidentDir = unpackNormal(e3.x, e3.y);
+			F3 lightBSDF = adjointBSDF(ldir, -incidentDir, lmd, lightNormal, pdf);
+			lightIntensity = lightFlux * lightBSDF * cosLight;
+			lightPathToEye = misHeuristic(pdf) * distanceMISHeuristic(lightDist);
+		}
+		else
+		{
+			lightIntensity = lightFlux * (cosLight * GI_PI_2);
+			lightPathToEye = misHeuristic(cosLight / GI_PI) * distanceMISHeuristic(lightDist);
+		}
+		misLight = lightPathToEye / fmaxf(lightPathToEye + eyeToLight, GI_DIVISOR_EPSILON);
+	}
+	else
+		lightIntensity = lightFlux * GI_PI_2;
+	mis *= misLight;
+	F3 irradiance = (mis * lightSampleWeight * cosCamera / lightDistSq) * lightIntensity;
+	q.value = irradiance * pathThroughput * bsdf;
+	return true;
+}
+
 // bidirpathtracer/pathtracer_bidir.comp:16-251, one invocation
 GI_HD void bidirPathtracePixel(const DFrame& f, int gx, int gy, PathCounters& pc, TraceStats* st)
 {
@@ -1082,71 +1182,14 @@ GI_HD void bidirPathtracePixel(const DFrame& f, int gx, int gy, PathCounters& pc
 			mis = (i == 0) ? 1.0f : (lastConnectionProbability / fmaxf(lastConnectionProbability + lightToEye, GI_DIVISOR_EPSILON));
 			color = color + mis * pathThroughput * md.Emissivity;
 		}
-		do
 		{
-			uint32_t idx = randomUInt(seed) % actualNumEntries;
-			const F4* e = f.lightCache + 4 * size_t(idx);
-			F4 e2 = ld4(e + 2);
-			int pathLength = f2i(e2.w) + i + 1;
-			if (pathLength > f.maxPathLength) break;
-			F4 e1 = ld4(e + 1);
-			F3 ldir = f3(e1.x, e1.y, e1.z) - origin;
-			float lightDistSq = dot(ldir, ldir);
-			float lightDist = sqrtf(lightDistSq);
-			ldir = ldir / fmaxf(lightDist, GI_DIVISOR_EPSILON);
-			F3 lorigin = GI_RAY_HIT_EPSILON * ldir + origin;
-			++pc.anyRays;
-			if (traceAny(f.scene, f.traversalMode, lorigin, ldir, lightDist - GI_RAY_HIT_EPSILON * 2, st)) break;
-			F4 e0 = ld4(e), e3 = ld4(e + 3);
-			int lightMaterialIndex = f2i(e0.w);
-			F3 lightFlux = f3(e0.x, e0.y, e0.z);
-			F3 lightNormal = f3(0.0f, 1.0f, 0.0f);
-			float lightPathToEye;
-			float cosLight = 0.0f;
-			F3 lightIntensity;
-			float cosCamera = fabsf(dot(ldir, hitNormal));
-			const float normal0 = e1.w, normal1 = e2.z;
-			if (normal1 < 1.5f)
+			ConnectionQuery cq;
+			if (prepareConnection(f, actualNumEntries, lightSampleWeight, origin, dir, hitNormal, md, i, rayHit, lastConnectionProbability, pathThroughput, seed, cq))
 			{
-				lightNormal = unpackNormalNoSat(normal0, normal1);
-				cosLight = fabsf(dot(ldir, lightNormal));
+				++pc.anyRays;
+				if (!traceAny(f.scene, f.traversalMode, cq.origin, cq.dir, cq.len, st)) color = color + cq.value;
 			}
-			float pdf;
-			F3 bsdf = BSDF(dir, ldir, md, hitNormal, pdf);
-			float eyeToLight = misHeuristic(pdf);
-			if (i > 0)
-			{
-				eyeToLight *= distanceMISHeuristic(rayHit);
-				mis = lastConnectionProbability / fmaxf(lastConnectionProbability + eyeToLight, GI_DIVISOR_EPSILON);
-				if (md.Reflectiveness.w >= 100.0f) mis = 1.0f;
-			}
-			else
-				mis = eyeToLight / fmaxf(lastConnectionProbability + eyeToLight, GI_DIVISOR_EPSILON);
-			float misLight = 1.0f;
-			if (normal1 < 1.5f)
-			{
-				if (lightMaterialIndex != -1)
-				{
-					F2 ltc; ltc.x = e2.x; ltc.y = e2.y;
-					MaterialData lmd = sampleMaterialData(f.scene, lightMaterialIndex, ltc);
-					F3 incidentDir = unpackNormal(e3.x, e3.y);
-					F3 lightBSDF = adjointBSDF(ldir, -incidentDir, lmd, lightNormal, pdf);
-					lightIntensity = lightFlux * lightBSDF * cosLight;
-					lightPathToEye = misHeuristic(pdf) * distanceMISHeuristic(lightDist);
-				}
-				else
-				{
-					lightIntensity = lightFlux * (cosLight * GI_PI_2);
-					lightPathToEye = misHeuristic(cosLight / GI_PI) * distanceMISHeuristic(lightDist);
-				}
-				misLight = lightPathToEye / fmaxf(lightPathToEye + eyeToLight, GI_DIVISOR_EPSILON);
-			}
-			else
-				lightIntensity = lightFlux * GI_PI_2;
-			mis *= misLight;
-			F3 irradiance = (mis * lightSampleWeight * cosCamera / lightDistSq) * lightIntensity;
-			color = color + irradiance * pathThroughput * bsdf;
-		} while (false);
+		}
 		float samplePDF;
 		F3 throughput = f3(1.0f);
 		dir = sampleBSDF(dir, md, seed, hitNormal, throughput, false, samplePDF);

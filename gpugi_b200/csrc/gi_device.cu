@@ -204,6 +204,56 @@ __global__ void __launch_bounds__(WF_SHADE_THREADS) k_wf_shade_pt(WfFrame w, uns
 	flushWarpCounters(counters, cnt, WFC_COUNT);
 }
 
+// generate(w) / shade(w) of the light tracer and shade(w) of the BPT eye pass (gi_shade.h); same work distribution as k_wf_shade_pt.
+__global__ void __launch_bounds__(256) k_wf_generate_light(WfFrame w, unsigned long long* counters)
+{
+	PathCounters pc = {};
+	const uint32_t stride = gridDim.x * blockDim.x;
+	for (uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x; gid < w.numPaths; gid += stride) wfGenerateLight(w, gid, pc);
+	unsigned cnt[WFC_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+	wfAddCounters(cnt, pc);
+	flushWarpCounters(counters, cnt, WFC_COUNT);
+}
+
+__global__ void __launch_bounds__(WF_SHADE_THREADS) k_wf_shade_light(WfFrame w, unsigned long long* counters)
+{
+	uint32_t* counts = wfCounts(w, w.wave);
+	const uint32_t n = w.numCam + counts[0];
+	PathCounters pc = {};
+	for (;;)
+	{
+		uint32_t base = 0;
+		if (laneId() == 0) base = atomicAdd(counts + 3, 32u);
+		base = __shfl_sync(0xffffffffu, base, 0);
+		if (base >= n) break;
+		const uint32_t slot = base + laneId();
+		wfShadeLight(w, slot, slot < n, pc);
+	}
+	unsigned cnt[WFC_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+	wfAddCounters(cnt, pc);
+	flushWarpCounters(counters, cnt, WFC_COUNT);
+}
+
+__global__ void __launch_bounds__(WF_SHADE_THREADS) k_wf_shade_eye(WfFrame w, unsigned long long* counters)
+{
+	uint32_t* counts = wfCounts(w, w.wave);
+	const uint32_t n = w.numCam + counts[0];
+	const uint32_t numEntries = *w.f.lightCacheCount; // complete: the light pass of this iteration ran before the eye waves
+	PathCounters pc = {};
+	for (;;)
+	{
+		uint32_t base = 0;
+		if (laneId() == 0) base = atomicAdd(counts + 3, 32u);
+		base = __shfl_sync(0xffffffffu, base, 0);
+		if (base >= n) break;
+		const uint32_t slot = base + laneId();
+		wfShadeEye(w, slot, slot < n, numEntries, pc);
+	}
+	unsigned cnt[WFC_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+	wfAddCounters(cnt, pc);
+	flushWarpCounters(counters, cnt, WFC_COUNT);
+}
+
 // Final fold: the radiance sums of the iterations still held in state slots join the accumulator, per pixel in
 // iteration order (pathtracer.comp:107-109: Out[px] += vec4(color, 0)).
 __global__ void __launch_bounds__(256) k_wf_fold(float4* __restrict__ accum, const F4* __restrict__ stateC, uint32_t numIds, uint32_t numSlots,
@@ -300,7 +350,7 @@ struct GiContext
 	uint64_t wfStates = 0;           // allocated path state records (numSlots x numIds)
 	uint32_t* traceWork = nullptr;   // work counter of k_wf_trace_batch
 	int numSMs = 148;
-	int traceBlocksPerSM = 1, shadeBlocksPerSM = 1;
+	int traceBlocksPerSM = 1, shadeBlocksPerSM = 1, shadeLightBlocksPerSM = 1, shadeEyeBlocksPerSM = 1;
 
 	// GI_OPT_KERNEL_TIMING: CUDA-event duration of every launch of an iteration, summed per kernel class
 	int kernelTiming = 0;
@@ -406,7 +456,7 @@ static DFrame makeFrame(GiContext* c, const GiIterationParams* p)
 // ---- wavefront queue storage: 2 ray queues, hit records, shadow queue, path state, per-bounce counters
 static void freeWavefront(GiContext* c)
 {
-	cudaFree(c->wf.rays[0]); cudaFree(c->wf.rays[1]); cudaFree(c->wf.hits); cudaFree(c->wf.shadow); cudaFree(c->wf.stateT); cudaFree(c->wf.stateC);
+	cudaFree(c->wf.rays[0]); cudaFree(c->wf.rays[1]); cudaFree(c->wf.hits); cudaFree(c->wf.shadow); cudaFree(c->wf.stateT); cudaFree(c->wf.stateC); cudaFree(c->wf.stateM);
 	cudaFree(c->wf.counts);
 	c->wf = WfQueues{};
 	c->wfCountsLen = 0;
@@ -425,8 +475,8 @@ static int ensureWavefront(GiContext* c, uint64_t capacity, uint32_t numIds, uin
 		GI_CUDA(c, cudaStreamSynchronize(c->stream));
 		const uint64_t cap = std::max<uint64_t>(capacity, c->wf.capacity);
 		const uint64_t st = std::max<uint64_t>(states, c->wfStates);
-		cudaFree(c->wf.rays[0]); cudaFree(c->wf.rays[1]); cudaFree(c->wf.hits); cudaFree(c->wf.shadow); cudaFree(c->wf.stateT); cudaFree(c->wf.stateC);
-		c->wf.rays[0] = c->wf.rays[1] = nullptr; c->wf.hits = nullptr; c->wf.shadow = nullptr; c->wf.stateT = c->wf.stateC = nullptr;
+		cudaFree(c->wf.rays[0]); cudaFree(c->wf.rays[1]); cudaFree(c->wf.hits); cudaFree(c->wf.shadow); cudaFree(c->wf.stateT); cudaFree(c->wf.stateC); cudaFree(c->wf.stateM);
+		c->wf.rays[0] = c->wf.rays[1] = nullptr; c->wf.hits = nullptr; c->wf.shadow = nullptr; c->wf.stateT = c->wf.stateC = nullptr; c->wf.stateM = nullptr;
 		c->wf.capacity = 0; c->wfStates = 0;
 		GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->wf.rays[0]), size_t(cap) * 32));
 		GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->wf.rays[1]), size_t(cap) * 32));
@@ -434,6 +484,7 @@ static int ensureWavefront(GiContext* c, uint64_t capacity, uint32_t numIds, uin
 		GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->wf.shadow), size_t(cap) * 48));
 		GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->wf.stateT), size_t(st) * 16));
 		GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->wf.stateC), size_t(st) * 16));
+		GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->wf.stateM), size_t(st) * 4));
 		c->wf.capacity = uint32_t(cap);
 		c->wfStates = st;
 	}
@@ -449,32 +500,50 @@ static int ensureWavefront(GiContext* c, uint64_t capacity, uint32_t numIds, uin
 	return GI_OK;
 }
 
-// `count` path-tracer iterations as waves (gi_wavefront.cuh): wave w = generate(iteration w), trace, shade; maxPathLength
-// drain waves; final fold.  seeds[k] = FrameSeed of batch iteration k; its light samples are f.lightSamples + k * lightStride.
-static int renderWavefrontPT(GiContext* c, const DFrame& f, const uint32_t* seeds, uint32_t count, uint32_t lightStride)
+// `count` iterations of one pass as waves (gi_wavefront.cuh): wave w = generate(iteration w), trace, shade; maxPathLength drain
+// waves; final fold of the per-path radiance sums (PT, BPT eye pass).  seeds[k] = FrameSeed of batch iteration k; its light
+// samples are f.lightSamples + k * lightStride.
+//   WF_PASS_PT     pathtracer.comp          ids = pixels, W/8 x H/8 tiles
+//   WF_PASS_LIGHT  lighttracer.comp         ids = light paths; lightFlags = WF_LIGHT_SAVE / WF_LIGHT_WARMUP (gi_shade.h)
+//   WF_PASS_EYE    pathtracer_bidir.comp    ids = pixels; count must be 1 (the pass reads the light cache its own light pass filled)
+enum { WF_PASS_PT = 0, WF_PASS_LIGHT, WF_PASS_EYE };
+
+static int renderWavefront(GiContext* c, const DFrame& f, int pass, uint32_t lightFlags, const uint32_t* seeds, uint32_t count, uint32_t lightStride)
 {
 	WfFrame w;
 	std::memset(&w, 0, sizeof(w));
 	w.f = f;
+	w.lightFlags = lightFlags;
 	w.tilesX = c->width / 8; w.tilesY = c->height / 8; // integer division, pathtracer.cpp:50
-	w.numPaths = uint32_t(w.tilesX) * uint32_t(w.tilesY) * 64u;
+	uint32_t numIds;
+	if (pass == WF_PASS_LIGHT)
+	{
+		w.numPaths = (uint32_t(f.numLightSamples) * uint32_t(f.numRaysPerLightSample) / 64u) * 64u; // whole groups of 64, lightpathtracer.cpp:48
+		numIds = w.numPaths;
+	}
+	else
+	{
+		w.numPaths = uint32_t(w.tilesX) * uint32_t(w.tilesY) * 64u;
+		numIds = uint32_t(c->width) * uint32_t(c->height);
+	}
 	w.lightStride = lightStride;
 	if (w.numPaths == 0 || count == 0) return GI_OK;
+	if (pass == WF_PASS_EYE && count != 1u) return fail(c, GI_ERR_INVALID, "wavefront BPT eye pass: one iteration at a time");
 	const uint32_t maxLen = uint32_t(f.maxPathLength);
 	const uint32_t numSlots = std::min(count, maxLen + 1u);
 	const uint32_t numWaves = count + maxLen; // the last wave carries shadow rays only
 	// worst case (no path ever ends before maxPathLength): maxLen generations of rays share a wave.  Any batch (count > 1)
 	// reserves that much, so that batches of different length never reallocate.
-	int st = ensureWavefront(c, uint64_t(w.numPaths) * (count > 1u ? maxLen : 1u), uint32_t(c->width) * uint32_t(c->height), count > 1u ? maxLen + 1u : 1u,
-	                         WF_COUNTS_PER_WAVE * (numWaves + 1u));
+	int st = ensureWavefront(c, uint64_t(w.numPaths) * (count > 1u ? maxLen : 1u), numIds, count > 1u ? maxLen + 1u : 1u, WF_COUNTS_PER_WAVE * (numWaves + 1u));
 	if (st != GI_OK) return st;
 	w.q = c->wf;
 	w.q.numSlots = numSlots;
 	w.tune = c->tune;
 	GI_CUDA(c, cudaMemsetAsync(c->wf.counts, 0, size_t(WF_COUNTS_PER_WAVE) * (numWaves + 1u) * sizeof(uint32_t), c->stream));
 	// ids outside the W/8 x H/8 tiles are never written by shade(); the fold reads them
-	if (w.numPaths != w.q.numIds) GI_CUDA(c, cudaMemsetAsync(c->wf.stateC, 0, size_t(numSlots) * w.q.numIds * 16, c->stream));
-	const unsigned traceGrid = unsigned(c->numSMs * c->traceBlocksPerSM), shadeGrid = unsigned(c->numSMs * c->shadeBlocksPerSM);
+	if (pass != WF_PASS_LIGHT && w.numPaths != w.q.numIds) GI_CUDA(c, cudaMemsetAsync(c->wf.stateC, 0, size_t(numSlots) * w.q.numIds * 16, c->stream));
+	const unsigned traceGrid = unsigned(c->numSMs * c->traceBlocksPerSM);
+	const unsigned shadeGrid = unsigned(c->numSMs * (pass == WF_PASS_PT ? c->shadeBlocksPerSM : pass == WF_PASS_LIGHT ? c->shadeLightBlocksPerSM : c->shadeEyeBlocksPerSM));
 	const bool ref = f.traversalMode == GI_TRAVERSAL_REFERENCE;
 	timingMark(c, -1);
 	for (uint32_t wave = 0; wave < numWaves; ++wave)
@@ -485,7 +554,8 @@ static int renderWavefrontPT(GiContext* c, const DFrame& f, const uint32_t* seed
 		if (wave < count)
 		{
 			w.f.frameSeed = seeds[wave];
-			k_wf_generate<<<unsigned(c->numSMs) * 8u, 256, 0, c->stream>>>(w, c->counters);
+			if (pass == WF_PASS_LIGHT) k_wf_generate_light<<<unsigned(c->numSMs) * 8u, 256, 0, c->stream>>>(w, c->counters);
+			else k_wf_generate<<<unsigned(c->numSMs) * 8u, 256, 0, c->stream>>>(w, c->counters);
 			++c->launches;
 			timingMark(c, GI_KERNEL_GENERATE);
 		}
@@ -496,14 +566,19 @@ static int renderWavefrontPT(GiContext* c, const DFrame& f, const uint32_t* seed
 		timingMark(c, GI_KERNEL_TRACE);
 		if (wave + 1u < numWaves)
 		{
-			k_wf_shade_pt<<<shadeGrid, WF_SHADE_THREADS, 0, c->stream>>>(w, c->counters);
+			if (pass == WF_PASS_PT) k_wf_shade_pt<<<shadeGrid, WF_SHADE_THREADS, 0, c->stream>>>(w, c->counters);
+			else if (pass == WF_PASS_LIGHT) k_wf_shade_light<<<shadeGrid, WF_SHADE_THREADS, 0, c->stream>>>(w, c->counters);
+			else k_wf_shade_eye<<<shadeGrid, WF_SHADE_THREADS, 0, c->stream>>>(w, c->counters);
 			++c->launches;
 			timingMark(c, GI_KERNEL_SHADE);
 		}
 	}
-	k_wf_fold<<<unsigned(c->numSMs) * 8u, 256, 0, c->stream>>>(reinterpret_cast<float4*>(c->accum), c->wf.stateC, w.q.numIds, numSlots, count - numSlots, count);
-	++c->launches;
-	timingMark(c, GI_KERNEL_OTHER);
+	if (pass != WF_PASS_LIGHT)
+	{
+		k_wf_fold<<<unsigned(c->numSMs) * 8u, 256, 0, c->stream>>>(reinterpret_cast<float4*>(c->accum), c->wf.stateC, w.q.numIds, numSlots, count - numSlots, count);
+		++c->launches;
+		timingMark(c, GI_KERNEL_OTHER);
+	}
 	timingCollect(c);
 	return GI_OK;
 }
@@ -550,6 +625,10 @@ int gi_create(int device, GiContext** out_ctx)
 	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->shadeBlocksPerSM, k_wf_shade_pt, WF_SHADE_THREADS, 0);
 	c->traceBlocksPerSM = std::max(c->traceBlocksPerSM, 1);
 	c->shadeBlocksPerSM = std::max(c->shadeBlocksPerSM, 1);
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->shadeLightBlocksPerSM, k_wf_shade_light, WF_SHADE_THREADS, 0);
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->shadeEyeBlocksPerSM, k_wf_shade_eye, WF_SHADE_THREADS, 0);
+	c->shadeLightBlocksPerSM = std::max(c->shadeLightBlocksPerSM, 1);
+	c->shadeEyeBlocksPerSM = std::max(c->shadeEyeBlocksPerSM, 1);
 	*out_ctx = c;
 	return GI_OK;
 }
@@ -812,7 +891,7 @@ int gi_render_iteration(GiContext* c, const GiIterationParams* p)
 	case GI_RENDERER_PT:
 		if (c->scheduler == GI_SCHEDULER_WAVEFRONT)
 		{
-			st = renderWavefrontPT(c, f, &p->frame_seed, 1u, 0u);
+			st = renderWavefront(c, f, WF_PASS_PT, 0u, &p->frame_seed, 1u, 0u);
 			if (st != GI_OK) return st;
 		}
 		else if (pixelGrid.x && pixelGrid.y)
@@ -825,7 +904,12 @@ int gi_render_iteration(GiContext* c, const GiIterationParams* p)
 	{
 		if (p->num_rays_per_light_sample <= 0) return fail(c, GI_ERR_INVALID, "num_rays_per_light_sample must be positive");
 		const unsigned groups = unsigned(c->numLightSamples) * unsigned(p->num_rays_per_light_sample) / 64u; // lightpathtracer.cpp:48
-		if (groups)
+		if (c->scheduler == GI_SCHEDULER_WAVEFRONT)
+		{
+			st = renderWavefront(c, f, WF_PASS_LIGHT, 0u, &p->frame_seed, 1u, 0u);
+			if (st != GI_OK) return st;
+		}
+		else if (groups)
 		{
 			k_lighttrace<false, false><<<groups, 64, 0, c->stream>>>(f, c->counters);
 			++c->launches;
@@ -837,13 +921,19 @@ int gi_render_iteration(GiContext* c, const GiIterationParams* p)
 		if (p->num_rays_per_light_sample <= 0) return fail(c, GI_ERR_INVALID, "num_rays_per_light_sample must be positive");
 		const unsigned numLightPaths = unsigned(c->numLightSamples) * unsigned(p->num_rays_per_light_sample);
 		const unsigned groups = numLightPaths / 64u;
+		const bool wavefront = c->scheduler == GI_SCHEDULER_WAVEFRONT;
 		// resetcounter.comp (bidirectionalpathtracer.cpp:190)
 		k_reset_counter<<<1, 1, 0, c->stream>>>(c->bptCounters, c->bptCounters + 1, numLightPaths);
 		++c->launches;
 		if (p->warmup)
 		{
 			f.lightCacheCapacity = 0x7fffffffu;
-			if (groups) { k_lighttrace<true, true><<<groups, 64, 0, c->stream>>>(f, c->counters); ++c->launches; }
+			if (wavefront)
+			{
+				st = renderWavefront(c, f, WF_PASS_LIGHT, WF_LIGHT_SAVE | WF_LIGHT_WARMUP, &p->frame_seed, 1u, 0u);
+				if (st != GI_OK) return st;
+			}
+			else if (groups) { k_lighttrace<true, true><<<groups, 64, 0, c->stream>>>(f, c->counters); ++c->launches; }
 			break;
 		}
 		if (!c->lightCache) return fail(c, GI_ERR_CAPACITY, "BPT needs gi_alloc_light_cache first");
@@ -852,6 +942,14 @@ int gi_render_iteration(GiContext* c, const GiIterationParams* p)
 		if (uint32_t(p->light_cache_capacity) < numLightPaths)
 			return fail(c, GI_ERR_CAPACITY, "light_cache_capacity is smaller than the number of light paths (their origins occupy the first slots)");
 		f.lightCacheCapacity = uint32_t(p->light_cache_capacity);
+		if (wavefront)
+		{
+			// light pass to completion (fills the cache), then the eye pass (bidirectionalpathtracer.cpp:190-200)
+			st = renderWavefront(c, f, WF_PASS_LIGHT, WF_LIGHT_SAVE, &p->frame_seed, 1u, 0u);
+			if (st == GI_OK) st = renderWavefront(c, f, WF_PASS_EYE, 0u, &p->frame_seed, 1u, 0u);
+			if (st != GI_OK) return st;
+			break;
+		}
 		if (groups) { k_lighttrace<true, false><<<groups, 64, 0, c->stream>>>(f, c->counters); ++c->launches; }
 		if (pixelGrid.x && pixelGrid.y) { k_bidir_eye<<<pixelGrid, 64, 0, c->stream>>>(f, c->counters); ++c->launches; }
 		break;
@@ -877,10 +975,13 @@ int gi_render_iterations(GiContext* c, const GiIterationParams* p, const uint32_
 	if (st != GI_OK) return st;
 	if (p->max_path_length <= 0) return fail(c, GI_ERR_INVALID, "max_path_length must be positive");
 	GI_CUDA(c, cudaSetDevice(c->device));
-	if (p->renderer == GI_RENDERER_PT && c->scheduler == GI_SCHEDULER_WAVEFRONT)
+	if ((p->renderer == GI_RENDERER_PT || p->renderer == GI_RENDERER_LPT) && c->scheduler == GI_SCHEDULER_WAVEFRONT)
 	{
+		// PT / LPT iterations are independent: their waves overlap.  (BPT: the eye pass of an iteration needs its own complete
+		// light cache -> one iteration after the other, below.)
+		if (p->renderer == GI_RENDERER_LPT && p->num_rays_per_light_sample <= 0) return fail(c, GI_ERR_INVALID, "num_rays_per_light_sample must be positive");
 		DFrame f = makeFrame(c, p);
-		st = renderWavefrontPT(c, f, frame_seeds, count, d_light_samples ? 2u * samples_per_iteration : 0u);
+		st = renderWavefront(c, f, p->renderer == GI_RENDERER_PT ? WF_PASS_PT : WF_PASS_LIGHT, 0u, frame_seeds, count, d_light_samples ? 2u * samples_per_iteration : 0u);
 		if (st != GI_OK) return st;
 		GI_CUDA(c, cudaGetLastError());
 		return GI_OK;

@@ -336,7 +336,6 @@ GI_HD bool wfEndOfWalk(WfLane& L, const DScene& s, WfCand* cand, CNT& cnt)
 			walk = true;
 		if (walk)
 		{
-			cnt.template add<WFC_SPLATS>(1u); // DEBUG
 			L.best = L.tMaxInit; L.hitLeaf = -1;
 			traceReference<false>(s, L.o, L.d, L.best, L.hitLeaf, &st);
 		}

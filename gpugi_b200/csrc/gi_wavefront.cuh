@@ -32,6 +32,7 @@
 
 #include "gi_core.h"
 #include "gi_lane.h"
+#include "gi_shade.h"
 
 namespace gik {
 
@@ -54,6 +55,7 @@ struct WfQueues
 	F4* shadow;
 	F4* stateT;          // numSlots x numIds: (throughput.xyz, seed bits)
 	F4* stateC;          // numSlots x numIds: (radiance sum.xyz, alpha increment)
+	float* stateM;       // numSlots x numIds: lastConnectionProbability of a BPT eye path
 	uint32_t* counts;    // WF_COUNTS_PER_WAVE x (waves of the batch + 1), zeroed per batch
 	uint32_t capacity;   // slots per queue
 	uint32_t numIds;     // path ids per iteration (PT/BPT: width x height)
@@ -68,6 +70,7 @@ struct WfTune
 	int reserved;
 };
 
+GI_D F4 f4zero() { F4 r; r.x = r.y = r.z = r.w = 0.0f; return r; }
 GI_D unsigned laneId() { return threadIdx.x & 31u; }
 GI_D unsigned lanemaskLt() { unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
 
@@ -110,7 +113,8 @@ GI_D void wfSplat(float* accum, int width, int height, uint32_t pixel, F3 v)
 	atomicAdd(reinterpret_cast<float4*>(p), make_float4(v.x, v.y, v.z, 0.0f));
 }
 
-GI_D void wfFinishShadow(const WfTraceIO& io, uint32_t slot, bool occluded)
+template <class CNT>
+GI_D void wfFinishShadow(const WfTraceIO& io, uint32_t slot, bool occluded, CNT& cnt)
 {
 	if (occluded) return;
 	const F4 s1 = ld4(io.shadow + 3 * size_t(slot) + 1);
@@ -119,6 +123,7 @@ GI_D void wfFinishShadow(const WfTraceIO& io, uint32_t slot, bool occluded)
 	const uint32_t id = word & WF_ID_MASK;
 	if (word & WF_FLAG_SPLAT)
 	{
+		cnt.template add<WFC_SPLATS>(1u);
 		wfSplat(io.accum, io.width, io.height, id, f3(v.x, v.y, v.z));
 		return;
 	}
@@ -233,7 +238,7 @@ struct WfQueueIO
 	template <class CNT>
 	GI_D void finish(const DScene& s, WfLane& L, CNT& cnt) const
 	{
-		if (L.flags & WFL_ANY) wfFinishShadow(q, L.index - q.numClosest, (L.flags & WFL_OCCLUDED) != 0u);
+		if (L.flags & WFL_ANY) wfFinishShadow(q, L.index - q.numClosest, (L.flags & WFL_OCCLUDED) != 0u, cnt);
 		else q.hits[L.index] = make_float2(L.best, i2f(L.hitLeaf));
 	}
 };
@@ -285,6 +290,7 @@ struct WfFrame
 	uint32_t numCam;         // freshly generated rays at the head of this wave's extension queue (numPaths or 0)
 	uint32_t pushBase;       // ... of the next wave's extension queue: pushed rays are placed behind them
 	uint32_t lightStride;    // F4 elements between the light samples of consecutive iterations (0: the same set for all)
+	uint32_t lightFlags;     // light tracer waves: WF_LIGHT_SAVE / WF_LIGHT_WARMUP (gi_shade.h)
 };
 
 // queue slot -> pixel: 8x8 tiles in row-major tile order, row-major inside the tile (the reference's work-group shape)
@@ -335,7 +341,7 @@ GI_D void wfShadePT(const WfFrame& w, uint32_t slot, bool valid, unsigned* cnt)
 				const float4 old = *reinterpret_cast<const float4*>(q.stateC + sidx);
 				float4* px = reinterpret_cast<float4*>(f.accum) + id;
 				float4 a = *px;
-				a.x += old.x; a.y += old.y; a.z += old.z;
+				a.x += old.x; a.y += old.y; a.z += old.z; a.w += old.w;
 				*px = a;
 			}
 		}
@@ -406,6 +412,99 @@ GI_D void wfShadePT(const WfFrame& w, uint32_t slot, bool valid, unsigned* cnt)
 		*reinterpret_cast<float4*>(rp) = make_float4(origin.x, origin.y, origin.z, i2f(bounce + 1));
 		*reinterpret_cast<float4*>(rp + 1) = make_float4(dir.x, dir.y, dir.z, i2f(int(word)));
 	}
+}
+
+// ------------------------------------------------------------------ light tracer / bidirectional waves (gi_shade.h)
+GI_D void wfAddCounters(unsigned* cnt, const PathCounters& pc)
+{
+	cnt[WFC_CLOSEST] += pc.closestRays; cnt[WFC_ANY] += pc.anyRays; cnt[WFC_CAMERA] += pc.cameraPaths; cnt[WFC_LIGHT] += pc.lightPaths;
+	cnt[WFC_SHADED] += pc.shadedVertices; cnt[WFC_SPLATS] += pc.splats; cnt[WFC_FALLBACK] += pc.fallbackRays;
+}
+
+GI_D F4 ldState(const F4* p) { const float4 v = *reinterpret_cast<const float4*>(p); F4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w; return r; }
+GI_D void stState(F4* p, F4 v) { *reinterpret_cast<float4*>(p) = make_float4(v.x, v.y, v.z, v.w); }
+
+// warp-compacted push of what a shaded vertex produced (all 32 lanes call)
+GI_D void wfPushOut(const WfFrame& w, const WfPush& out, uint32_t shadowTarget, int bounce, uint32_t id)
+{
+	const WfQueues& q = w.q;
+	uint32_t* next = wfCounts(w, w.wave + 1);
+	const uint32_t sslot = warpPush(next + 1, out.shadow);
+	if (out.shadow)
+	{
+		F4* sp = q.shadow + 3 * size_t(sslot);
+		*reinterpret_cast<float4*>(sp) = make_float4(out.sOrigin.x, out.sOrigin.y, out.sOrigin.z, out.sLen);
+		*reinterpret_cast<float4*>(sp + 1) = make_float4(out.sDir.x, out.sDir.y, out.sDir.z, i2f(int(shadowTarget)));
+		*reinterpret_cast<float4*>(sp + 2) = make_float4(out.sValue.x, out.sValue.y, out.sValue.z, 0.0f);
+	}
+	const uint32_t rslot = w.pushBase + warpPush(next, out.ray);
+	if (out.ray)
+	{
+		F4* rp = q.rays[(w.wave + 1) & 1] + 2 * size_t(rslot);
+		*reinterpret_cast<float4*>(rp) = make_float4(out.origin.x, out.origin.y, out.origin.z, i2f(bounce + 1));
+		*reinterpret_cast<float4*>(rp + 1) = make_float4(out.dir.x, out.dir.y, out.dir.z, i2f(int(id)));
+	}
+}
+
+// generate(w) of the light tracer: light path `slot` of iteration w (lighttracer.comp:49-91)
+GI_D void wfGenerateLight(const WfFrame& w, uint32_t gid, PathCounters& pc)
+{
+	DFrame f = w.f;
+	f.lightSamples = w.f.lightSamples + size_t(w.wave) * w.lightStride;
+	F3 origin, dir; F4 T;
+	wfGenerateLightLane(f, w.lightFlags, gid, origin, dir, T, pc);
+	++pc.closestRays;
+	const uint32_t sidx = (uint32_t(w.wave) % w.q.numSlots) * w.q.numIds + gid;
+	stState(w.q.stateT + sidx, T);
+	F4* rp = w.q.rays[w.wave & 1] + 2 * size_t(gid);
+	*reinterpret_cast<float4*>(rp) = make_float4(origin.x, origin.y, origin.z, i2f(0));
+	*reinterpret_cast<float4*>(rp + 1) = make_float4(dir.x, dir.y, dir.z, i2f(int(gid)));
+}
+
+// shade(w) of the light tracer: one lane per hit record of a light path
+GI_D void wfShadeLight(const WfFrame& w, uint32_t slot, bool valid, PathCounters& pc)
+{
+	WfPush out;
+	out.ray = false; out.shadow = false; out.px = 0; out.py = 0;
+	uint32_t id = 0; int bounce = 0;
+	if (valid)
+	{
+		const F4* rp = w.q.rays[w.wave & 1] + 2 * size_t(slot);
+		const F4 r0 = ld4(rp), r1 = ld4(rp + 1);
+		const float2 hrec = w.q.hits[slot];
+		id = uint32_t(f2i(r1.w)) & WF_ID_MASK;
+		bounce = f2i(r0.w);
+		const uint32_t iteration = uint32_t(w.wave - bounce);
+		const uint32_t sidx = (iteration % w.q.numSlots) * w.q.numIds + id;
+		F4 T = ldState(w.q.stateT + sidx);
+		wfShadeLightLane(w.f, w.lightFlags, f3(r0.x, r0.y, r0.z), f3(r1.x, r1.y, r1.z), bounce, hrec.x, f2i(hrec.y), T, out, pc);
+		if (out.ray) stState(w.q.stateT + sidx, T);
+	}
+	wfPushOut(w, out, WF_FLAG_SPLAT | (uint32_t(out.py) * uint32_t(w.f.width) + uint32_t(out.px)), bounce, id);
+}
+
+// shade(w) of the BPT eye pass: one lane per hit record of an eye path
+GI_D void wfShadeEye(const WfFrame& w, uint32_t slot, bool valid, uint32_t numEntries, PathCounters& pc)
+{
+	WfPush out;
+	out.ray = false; out.shadow = false;
+	uint32_t id = 0, sidx = 0; int bounce = 0;
+	if (valid)
+	{
+		const F4* rp = w.q.rays[w.wave & 1] + 2 * size_t(slot);
+		const F4 r0 = ld4(rp), r1 = ld4(rp + 1);
+		const float2 hrec = w.q.hits[slot];
+		id = uint32_t(f2i(r1.w)) & WF_ID_MASK;
+		bounce = f2i(r0.w);
+		const uint32_t iteration = uint32_t(w.wave - bounce);
+		sidx = (iteration % w.q.numSlots) * w.q.numIds + id;
+		F4 T = f4zero(), C = f4zero(); float M = 1.0f;
+		if (bounce > 0) { T = ldState(w.q.stateT + sidx); C = ldState(w.q.stateC + sidx); M = w.q.stateM[sidx]; }
+		wfShadeEyeLane(w.f, numEntries, f3(r0.x, r0.y, r0.z), f3(r1.x, r1.y, r1.z), bounce, id, hrec.x, f2i(hrec.y), T, C, M, out, pc);
+		stState(w.q.stateC + sidx, C);
+		if (out.ray) { stState(w.q.stateT + sidx, T); w.q.stateM[sidx] = M; }
+	}
+	wfPushOut(w, out, sidx, bounce, id);
 }
 
 } // namespace gik

@@ -6,6 +6,7 @@
 #include "../../gpugi_b200/csrc/gi_core.h"
 #include "../../gpugi_b200/csrc/gi_layout.h"
 #include "../../gpugi_b200/csrc/gi_lane.h"
+#include "../../gpugi_b200/csrc/gi_shade.h"
 
 #include <cstring>
 #include <vector>
@@ -158,6 +159,160 @@ EM_API int em_render(const GiSceneDesc* desc, const GiCamera* cam, int w, int h,
 		for (int i = 0; i < nls; ++i) showLightCache(f, i, pc, &st);
 	addCounters(counters, pc, st);
 	if (counters) { counters->light_cache_entries = bptCounters[0]; counters->light_path_length_sum = bptCounters[1]; }
+	return 0;
+}
+
+// ---- the wavefront schedule of the light tracer / BPT (gi_wavefront.cuh) executed sequentially: the same lane functions
+// (gi_shade.h), queues as vectors, one wave after the other.  phase: 0 = whole iteration, 1 = BPT light pass only,
+// 2 = BPT eye pass only (light_cache / cache_count are inputs then).  cache_count: in/out NumLightCacheEntries.
+namespace {
+struct EmRay { F3 o, d; int bounce; uint32_t id; };
+struct EmShadow { F3 o, d; float len; F3 v; uint32_t target; bool splat; };
+
+void emTraceRays(const DFrame& f, const std::vector<EmRay>& rays, std::vector<float>& t, std::vector<int>& leaf, PathCounters& pc, TraceStats& st)
+{
+	t.resize(rays.size()); leaf.resize(rays.size());
+	for (size_t i = 0; i < rays.size(); ++i)
+	{
+		Hit h; bool fb = false;
+		traceClosest(f.scene, f.traversalMode, rays[i].o, rays[i].d, GI_RAY_MAX, h, &st, &fb);
+		if (fb) ++pc.fallbackRays;
+		t[i] = h.t; leaf[i] = h.leafTri;
+	}
+}
+
+void emTraceShadows(const DFrame& f, const std::vector<EmShadow>& sh, std::vector<F4>& stateC, PathCounters& pc, TraceStats& st)
+{
+	for (const EmShadow& r : sh)
+	{
+		if (traceAny(f.scene, f.traversalMode, r.o, r.d, r.len, &st)) continue;
+		if (r.splat) { ++pc.splats; float* p = f.accum + 4 * size_t(r.target); p[0] += r.v.x; p[1] += r.v.y; p[2] += r.v.z; }
+		else { F4& c = stateC[r.target]; c.x += r.v.x; c.y += r.v.y; c.z += r.v.z; }
+	}
+}
+}
+
+EM_API int em_render_wavefront(const GiSceneDesc* desc, const GiCamera* cam, int w, int h, const GiLightSample* ls, int nls, const GiIterationParams* p, int mode,
+                               int phase, void* light_cache, uint32_t* cache_count, float* accum, EmCounters* counters)
+{
+	EmScene e; std::string err;
+	if (!makeScene(desc, e, err)) return 1;
+	if (!e.L.binary) mode = GI_TRAVERSAL_REFERENCE;
+	uint32_t bptCounters[2] = {cache_count ? *cache_count : 0u, 0u};
+	DFrame f;
+	std::memset(&f, 0, sizeof(f));
+	f.scene = e.s; f.cam = *cam; f.width = w; f.height = h;
+	f.lightSamples = reinterpret_cast<const F4*>(ls); f.numLightSamples = nls;
+	f.frameSeed = p->frame_seed; f.maxPathLength = p->max_path_length; f.traversalMode = mode; f.accum = accum;
+	f.envColor = f3(0.0f); f.envCube = 0;
+	f.numRaysPerLightSample = p->num_rays_per_light_sample;
+	f.lightCache = static_cast<F4*>(light_cache);
+	f.lightCacheCapacity = uint32_t(p->light_cache_capacity);
+	f.lightCacheCount = &bptCounters[0]; f.lightPathLengthSum = &bptCounters[1];
+	PathCounters pc; std::memset(&pc, 0, sizeof(pc));
+	TraceStats st = {0, 0};
+	const uint32_t numLightPaths = (uint32_t(nls) * uint32_t(p->num_rays_per_light_sample) / 64u) * 64u;
+	const bool bpt = p->renderer == GI_RENDERER_BPT;
+	if (p->renderer != GI_RENDERER_LPT && !bpt) return 2;
+	std::vector<float> t; std::vector<int> leaf;
+	std::vector<F4> noC;
+	if (phase != 2)
+	{
+		// ---- light pass
+		uint32_t flags = bpt ? WF_LIGHT_SAVE : 0u;
+		if (bpt && p->warmup) { flags |= WF_LIGHT_WARMUP; f.lightCacheCapacity = 0x7fffffffu; }
+		if (bpt) { bptCounters[0] = uint32_t(nls) * uint32_t(p->num_rays_per_light_sample); bptCounters[1] = 0; }
+		std::vector<F4> stateT(numLightPaths);
+		std::vector<EmRay> cur(numLightPaths), next;
+		std::vector<EmShadow> shCur, shNext;
+		for (uint32_t gid = 0; gid < numLightPaths; ++gid)
+		{
+			wfGenerateLightLane(f, flags, gid, cur[gid].o, cur[gid].d, stateT[gid], pc);
+			++pc.closestRays;
+			cur[gid].bounce = 0; cur[gid].id = gid;
+		}
+		for (int wave = 0; wave <= f.maxPathLength; ++wave)
+		{
+			emTraceRays(f, cur, t, leaf, pc, st);
+			emTraceShadows(f, shCur, noC, pc, st);
+			next.clear(); shNext.clear();
+			for (size_t i = 0; i < cur.size(); ++i)
+			{
+				WfPush out;
+				wfShadeLightLane(f, flags, cur[i].o, cur[i].d, cur[i].bounce, t[i], leaf[i], stateT[cur[i].id], out, pc);
+				if (out.shadow) shNext.push_back(EmShadow{out.sOrigin, out.sDir, out.sLen, out.sValue, uint32_t(out.py) * uint32_t(w) + uint32_t(out.px), true});
+				if (out.ray) next.push_back(EmRay{out.origin, out.dir, cur[i].bounce + 1, cur[i].id});
+			}
+			cur.swap(next); shCur.swap(shNext);
+		}
+		if (!cur.empty() || !shCur.empty()) return 3; // the schedule must drain within maxPathLength + 1 waves
+	}
+	if (bpt && !p->warmup && phase != 1)
+	{
+		// ---- eye pass
+		const int gw = w / 8, gh = h / 8;
+		const uint32_t numIds = uint32_t(w) * uint32_t(h);
+		std::vector<F4> stateT(numIds), stateC(numIds);
+		std::vector<float> stateM(numIds, 1.0f);
+		std::memset(stateC.data(), 0, numIds * sizeof(F4));
+		std::vector<EmRay> cur, next;
+		std::vector<EmShadow> shCur, shNext;
+		for (int by = 0; by < gh; ++by) for (int bx = 0; bx < gw; ++bx) for (int l = 0; l < 64; ++l)
+		{
+			const int gx = bx * 8 + (l & 7), gy = by * 8 + (l >> 3);
+			const uint32_t pixel = uint32_t(gx + gy * w);
+			uint32_t seed = initRandomSeed(f.frameSeed, pixel);
+			const F3 dir = cameraRayDirection(f, seed, gx, gy);
+			cur.push_back(EmRay{f3(f.cam.position), dir, 0, pixel});
+			++pc.cameraPaths; ++pc.closestRays;
+		}
+		const uint32_t numEntries = bptCounters[0];
+		for (int wave = 0; wave <= f.maxPathLength; ++wave)
+		{
+			emTraceRays(f, cur, t, leaf, pc, st);
+			emTraceShadows(f, shCur, stateC, pc, st);
+			next.clear(); shNext.clear();
+			for (size_t i = 0; i < cur.size(); ++i)
+			{
+				WfPush out;
+				const uint32_t id = cur[i].id;
+				wfShadeEyeLane(f, numEntries, cur[i].o, cur[i].d, cur[i].bounce, id, t[i], leaf[i], stateT[id], stateC[id], stateM[id], out, pc);
+				if (out.shadow) shNext.push_back(EmShadow{out.sOrigin, out.sDir, out.sLen, out.sValue, id, false});
+				if (out.ray) next.push_back(EmRay{out.origin, out.dir, cur[i].bounce + 1, id});
+			}
+			cur.swap(next); shCur.swap(shNext);
+		}
+		if (!cur.empty() || !shCur.empty()) return 3;
+		for (uint32_t i = 0; i < numIds; ++i) { accum[4 * size_t(i)] += stateC[i].x; accum[4 * size_t(i) + 1] += stateC[i].y; accum[4 * size_t(i) + 2] += stateC[i].z; accum[4 * size_t(i) + 3] += stateC[i].w; }
+	}
+	addCounters(counters, pc, st);
+	if (counters) { counters->light_cache_entries = bptCounters[0]; counters->light_path_length_sum = bptCounters[1]; }
+	if (cache_count) *cache_count = bptCounters[0];
+	return 0;
+}
+
+// k_bidir_eye alone on a given light cache (the megakernel form), for a like-for-like check of the eye waves.
+EM_API int em_bidir_eye(const GiSceneDesc* desc, const GiCamera* cam, int w, int h, const GiIterationParams* p, int mode, void* light_cache, uint32_t cache_count,
+                        float* accum, EmCounters* counters)
+{
+	EmScene e; std::string err;
+	if (!makeScene(desc, e, err)) return 1;
+	if (!e.L.binary) mode = GI_TRAVERSAL_REFERENCE;
+	uint32_t bptCounters[2] = {cache_count, 0u};
+	DFrame f;
+	std::memset(&f, 0, sizeof(f));
+	f.scene = e.s; f.cam = *cam; f.width = w; f.height = h;
+	f.frameSeed = p->frame_seed; f.maxPathLength = p->max_path_length; f.traversalMode = mode; f.accum = accum;
+	f.envColor = f3(0.0f);
+	f.numRaysPerLightSample = p->num_rays_per_light_sample;
+	f.lightCache = static_cast<F4*>(light_cache);
+	f.lightCacheCapacity = uint32_t(p->light_cache_capacity);
+	f.lightCacheCount = &bptCounters[0]; f.lightPathLengthSum = &bptCounters[1];
+	PathCounters pc; std::memset(&pc, 0, sizeof(pc));
+	TraceStats st = {0, 0};
+	for (int by = 0; by < h / 8; ++by) for (int bx = 0; bx < w / 8; ++bx) for (int t = 0; t < 64; ++t)
+		bidirPathtracePixel(f, bx * 8 + (t & 7), by * 8 + (t >> 3), pc, &st);
+	addCounters(counters, pc, st);
 	return 0;
 }
 

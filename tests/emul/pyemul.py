@@ -39,6 +39,10 @@ lib.em_trace.restype = C.c_int
 lib.em_trace.argtypes = [vp, vp, u32, vp, C.c_int, C.POINTER(C.c_int), vp]
 lib.em_render.restype = C.c_int
 lib.em_render.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, vp, vp]
+lib.em_render_wavefront.restype = C.c_int
+lib.em_render_wavefront.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, C.c_int, vp, vp, vp, vp]
+lib.em_bidir_eye.restype = C.c_int
+lib.em_bidir_eye.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_int, vp, u32, vp, vp]
 lib.em_slab_check.restype = C.c_int
 lib.em_slab_check.argtypes = [vp, vp, u32, u32, vp]
 
@@ -61,13 +65,14 @@ def trace(scene_desc, rays, mode=0):
 
 
 def render(scene_desc, cam, w, h, light_samples, renderer, frame_seed, max_len=16, num_rays_per_light_sample=0, capacity=0, warmup=False, mode=0,
-           env_rgb=None, show_light_caches=False, accum=None):
+           env_rgb=None, show_light_caches=False, accum=None, cache=None):
     ls = np.ascontiguousarray(light_samples, dtype=LIGHT_SAMPLE_DTYPE)
     if accum is None:
         accum = np.zeros((h, w, 4), dtype=np.float32)
     p = IterationParams(renderer=renderer, frame_seed=frame_seed & 0xFFFFFFFF, max_path_length=max_len, num_rays_per_light_sample=num_rays_per_light_sample,
                         light_cache_capacity=capacity, warmup=1 if warmup else 0)
-    cache = np.zeros(max(int(capacity), 1) * 16, dtype=np.float32)
+    if cache is None:
+        cache = np.zeros(max(int(capacity), 1) * 16, dtype=np.float32)
     cnt = EmCounters()
     env = np.ascontiguousarray(env_rgb, dtype=np.float32) if env_rgb is not None else None
     camp = _p(cam) if isinstance(cam, np.ndarray) else C.addressof(cam)
@@ -86,3 +91,37 @@ def slab_check(scene_desc, rays, stride=64):
     if st != 0:
         raise RuntimeError("em_slab_check failed: %d" % st)
     return dict(zip(["tested", "exact_accepts", "conservative_accepts", "violations", "out_of_domain"], (int(x) for x in out)))
+
+
+def render_wavefront(scene_desc, cam, w, h, light_samples, renderer, frame_seed, max_len=16, num_rays_per_light_sample=0, capacity=0, warmup=False, mode=0,
+                     phase=0, cache=None, cache_count=0, accum=None):
+    """The wavefront schedule of LPT (renderer 1) / BPT (renderer 2) run sequentially with the product's lane functions (gi_shade.h).
+    phase 0: whole iteration, 1: BPT light pass only, 2: BPT eye pass only on (cache, cache_count).  Returns (accum, counters, cache, count)."""
+    ls = np.ascontiguousarray(light_samples, dtype=LIGHT_SAMPLE_DTYPE)
+    if accum is None:
+        accum = np.zeros((h, w, 4), dtype=np.float32)
+    p = IterationParams(renderer=renderer, frame_seed=frame_seed & 0xFFFFFFFF, max_path_length=max_len, num_rays_per_light_sample=num_rays_per_light_sample,
+                        light_cache_capacity=capacity, warmup=1 if warmup else 0)
+    if cache is None:
+        cache = np.zeros((max(int(capacity), 1), 16), dtype=np.float32)
+    cnt = EmCounters()
+    count = u32(cache_count)
+    camp = _p(cam) if isinstance(cam, np.ndarray) else C.addressof(cam)
+    st = lib.em_render_wavefront(C.addressof(scene_desc), camp, w, h, _p(ls), ls.shape[0], C.addressof(p), mode, phase, _p(cache), C.addressof(count), _p(accum),
+                                 C.addressof(cnt))
+    if st != 0:
+        raise RuntimeError("em_render_wavefront failed: %d" % st)
+    return accum, cnt.as_dict(), cache, int(count.value)
+
+
+def bidir_eye(scene_desc, cam, w, h, frame_seed, cache, cache_count, capacity, max_len=16, num_rays_per_light_sample=64, mode=0):
+    """k_bidir_eye (megakernel form) alone on a given light cache."""
+    accum = np.zeros((h, w, 4), dtype=np.float32)
+    p = IterationParams(renderer=2, frame_seed=frame_seed & 0xFFFFFFFF, max_path_length=max_len, num_rays_per_light_sample=num_rays_per_light_sample,
+                        light_cache_capacity=capacity, warmup=0)
+    cnt = EmCounters()
+    camp = _p(cam) if isinstance(cam, np.ndarray) else C.addressof(cam)
+    st = lib.em_bidir_eye(C.addressof(scene_desc), camp, w, h, C.addressof(p), mode, _p(cache), cache_count, _p(accum), C.addressof(cnt))
+    if st != 0:
+        raise RuntimeError("em_bidir_eye failed: %d" % st)
+    return accum, cnt.as_dict()

@@ -238,6 +238,72 @@ print("ok")
     assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr
 
 
+def test_wavefront_lighttracer_equals_per_path_form(orc, emul, scenes, box1):
+    """The light tracer as waves (gi_shade.h lane functions, the schedule of gi_wavefront.cuh run sequentially) produces the
+    same splats as one invocation per path (lighttracer.comp form); only the summation order inside a pixel differs."""
+    W = H = 48
+    C = scenes.BOX1_CAMERA
+    cam = orc.camera(C["pos"], C["lookat"], C["fov"], W, H)
+    s = _light_sampler(orc, box1).generate(256)
+    for nr, max_len in ((64, 16), (64, 3), (128, 1)):
+        img, ec = emul.render(box1.desc, cam, W, H, s, 1, 5, max_len, num_rays_per_light_sample=nr)
+        wimg, wc, _, _ = emul.render_wavefront(box1.desc, cam, W, H, s, 1, 5, max_len, num_rays_per_light_sample=nr)
+        assert np.allclose(wimg, img, rtol=1e-5, atol=1e-6)
+        for k in ("splats", "light_paths", "shaded_vertices", "closest_rays"):
+            assert wc[k] == ec[k], k
+        # a splat whose pixel rounds to W or H is dropped before its any-hit query instead of after it
+        assert 0 <= ec["any_rays"] - wc["any_rays"] <= ec["any_rays"] // 100 + 2
+
+
+def test_wavefront_bidirectional_equals_per_path_form(orc, emul, scenes, box1):
+    """BPT as waves: (1) warm-up counts, (2) the light cache holds the same entries as the per-path form (as a multiset:
+    the slot order is scheduling dependent in the reference too), (3) the eye waves on a given cache are bit-identical
+    to pathtracer_bidir.comp's one-invocation-per-pixel form on the same cache."""
+    W = H = 40
+    C = scenes.BOX1_CAMERA
+    cam = orc.camera(C["pos"], C["lookat"], C["fov"], W, H)
+    s = _light_sampler(orc, box1).generate(128)
+    nr = 64
+    _, wc = emul.render(box1.desc, cam, W, H, s, 2, 9, 16, num_rays_per_light_sample=nr, warmup=True)
+    _, ww, _, _ = emul.render_wavefront(box1.desc, cam, W, H, s, 2, 9, 16, num_rays_per_light_sample=nr, warmup=True)
+    assert (ww["light_cache_entries"], ww["light_path_length_sum"]) == (wc["light_cache_entries"], wc["light_path_length_sum"])
+    n = wc["light_cache_entries"]
+    cap = n + n // 10
+    # light pass only, as waves
+    acc_l, lc, cache, count = emul.render_wavefront(box1.desc, cam, W, H, s, 2, 9, 16, num_rays_per_light_sample=nr, capacity=cap, phase=1)
+    assert count == n
+    # per-path form of the whole iteration and the wavefront form of the whole iteration agree statistically ...
+    pcache = np.zeros((cap, 16), dtype=np.float32)
+    img, ec = emul.render(box1.desc, cam, W, H, s, 2, 9, 16, num_rays_per_light_sample=nr, capacity=cap, cache=pcache)
+    wimg, wcnt, wcache, wcount = emul.render_wavefront(box1.desc, cam, W, H, s, 2, 9, 16, num_rays_per_light_sample=nr, capacity=cap)
+    assert wcount == n == ec["light_cache_entries"]
+    for k in ("light_paths", "camera_paths", "splats"):
+        assert wcnt[k] == ec[k], k
+    assert abs(wcnt["shaded_vertices"] - ec["shaded_vertices"]) == 0  # eye + light vertices do not depend on the connections
+    assert np.all(wimg[..., 3] == 1.0)
+    assert abs(wimg[..., :3].sum() - img[..., :3].sum()) / img[..., :3].sum() < 0.05
+    # ... the cache entries of the per-path form and of the waves are the same multiset
+    assert np.array_equal(cache.view(np.uint32), wcache.view(np.uint32))  # (bit patterns: the material index -1 reads as NaN)
+    rows = np.ascontiguousarray(pcache[:n]).view(np.uint32).reshape(n, 16)
+    wrows = np.ascontiguousarray(wcache[:n]).view(np.uint32).reshape(n, 16)
+    key = lambda r: r[np.lexsort(r.T[::-1])]
+    assert np.array_equal(key(rows), key(wrows))
+    assert np.array_equal(rows[:128 * nr], wrows[:128 * nr])  # light origins sit in their own slots (lighttracer.comp:56-61)
+    # ... and the eye pass alone, on the same cache, is bit-identical in both forms
+    eye_ref, rc = emul.bidir_eye(box1.desc, cam, W, H, 9, cache, count, cap, 16, nr)
+    eye_wf, ecn, _, _ = emul.render_wavefront(box1.desc, cam, W, H, s, 2, 9, 16, num_rays_per_light_sample=nr, capacity=cap, phase=2, cache=cache, cache_count=count)
+    assert np.array_equal(eye_wf, eye_ref)
+    for k in ("camera_paths", "closest_rays", "any_rays", "shaded_vertices"):
+        assert ecn[k] == rc[k], k
+    # a short path length and a cache that overflows
+    small = n - 500
+    _, _, c2, n2 = emul.render_wavefront(box1.desc, cam, W, H, s, 2, 9, 16, num_rays_per_light_sample=nr, capacity=small, phase=1)
+    assert n2 == n
+    a, _ = emul.bidir_eye(box1.desc, cam, W, H, 9, c2, n2, small, 4, nr)
+    b, _, _, _ = emul.render_wavefront(box1.desc, cam, W, H, s, 2, 9, 4, num_rays_per_light_sample=nr, capacity=small, phase=2, cache=c2, cache_count=n2)
+    assert np.array_equal(a, b)
+
+
 def test_layout_rejects_bad_scenes(g, emul, box1):
     """Scene::SanityCheck equivalents: out-of-range vertex / material / child / escape indices are refused."""
     import ctypes as C

@@ -269,3 +269,107 @@ def test_batched_iterations_are_bit_identical_to_sequential(g, scenes, box1, siz
     two = dev.read_accumulator(W, H)
     assert np.isfinite(two).all() and two[..., :3].sum() > bat[..., :3].sum()
     dev.close()
+
+
+def _device(g, scenes, scene, W, H, cam=None):
+    dev = g.Device(0)
+    dev.upload_scene(scene)
+    dev.set_screen_size(W, H)
+    C = cam or scenes.BOX1_CAMERA
+    dev.set_camera(g.camera_params(C["pos"], C["lookat"], C["fov"], W, H))
+    dev.set_option(g.GI_OPT_TEXTURE_FILTER, 1)
+    return dev
+
+
+@pytest.mark.parametrize("size,nr,path_length", [((128, 128), 64, 16), ((100, 60), 128, 3)])
+def test_lighttracer_wavefront_equals_megakernel(g, scenes, box1, size, nr, path_length):
+    """LPT as waves (default scheduler) vs one thread per light path (the reference's launch shape): the same splats; only the
+    order of the float atomics inside a pixel differs."""
+    W, H = size
+    dev = _device(g, scenes, box1, W, H)
+    samples = g.LightSampler(box1).generate(256)
+    dev.set_light_samples(samples)
+    out = {}
+    for sched in (g.GI_SCHEDULER_MEGAKERNEL, g.GI_SCHEDULER_WAVEFRONT):
+        dev.set_option(g.GI_OPT_SCHEDULER, sched)
+        dev.clear(); dev.reset_counters()
+        dev.render_iteration(g.GI_RENDERER_LPT, g.wang_hash(3), path_length, num_rays_per_light_sample=nr)
+        out[sched] = (dev.read_accumulator(W, H), dev.counters())
+    (a, ca), (b, cb) = out[g.GI_SCHEDULER_MEGAKERNEL], out[g.GI_SCHEDULER_WAVEFRONT]
+    assert a[..., :3].sum() > 0 and np.all(b[..., 3] == 0.0)
+    assert np.allclose(a, b, rtol=1e-4, atol=1e-6)
+    for k in ("light_paths", "splats", "shaded_vertices", "closest_rays"):
+        assert ca[k] == cb[k], k
+    assert 0 <= ca["any_rays"] - cb["any_rays"] <= ca["any_rays"] // 100 + 2  # out-of-frame splats are dropped before their any-hit query
+    dev.close()
+
+
+def test_lighttracer_batched_iterations(g, scenes, box1):
+    """gi_render_iterations for LPT overlaps the iterations wave by wave; same image as one call per iteration."""
+    import torch
+    W = H = 96
+    nr, count = 64, 19
+    dev = _device(g, scenes, box1, W, H)
+    ls = g.LightSampler(box1)
+    samples = [ls.generate(256) for _ in range(count)]
+    seeds = [g.wang_hash(k) for k in range(count)]
+    dev.clear(); dev.reset_counters()
+    for k in range(count):
+        dev.set_light_samples(samples[k])
+        dev.render_iteration(g.GI_RENDERER_LPT, seeds[k], 16, num_rays_per_light_sample=nr)
+    seq, cs = dev.read_accumulator(W, H), dev.counters()
+    d_samples = torch.from_numpy(np.concatenate(samples).view(np.uint8).reshape(-1)).cuda()
+    dev.clear(); dev.reset_counters()
+    dev.render_iterations(g.GI_RENDERER_LPT, seeds, 16, d_samples.data_ptr(), 256, num_rays_per_light_sample=nr)
+    bat, cb = dev.read_accumulator(W, H), dev.counters()
+    assert np.allclose(seq, bat, rtol=1e-4, atol=1e-5)
+    for k in ("light_paths", "splats", "shaded_vertices", "closest_rays", "any_rays"):
+        assert cs[k] == cb[k], k
+    dev.close()
+
+
+def test_bidirectional_wavefront_vs_megakernel(g, scenes, box1):
+    """BPT as waves vs the reference's launch shape.  Deterministic parts are identical (light-cache entry count, light
+    vertices, splats of the light pass); the eye pass picks cache entries by slot, and slot order is scheduling dependent
+    in both, so images are compared statistically (8x8 block means of 16 iterations)."""
+    from gpugi_b200.parallel import rel_mse
+    W = H = 96
+    nr, N = 64, 16
+    dev = _device(g, scenes, box1, W, H)
+    ls = g.LightSampler(box1)
+    samples = [ls.generate(128) for _ in range(N)]
+    # capacity from a warm-up run in both schedulers (counts are order independent)
+    warm = {}
+    for sched in (g.GI_SCHEDULER_MEGAKERNEL, g.GI_SCHEDULER_WAVEFRONT):
+        dev.set_option(g.GI_OPT_SCHEDULER, sched)
+        dev.set_light_samples(samples[0])
+        dev.render_iteration(g.GI_RENDERER_BPT, g.wang_hash(0), 16, num_rays_per_light_sample=nr, warmup=1)
+        c = dev.counters()
+        warm[sched] = (c["light_cache_entries"], c["light_path_length_sum"])
+    assert warm[g.GI_SCHEDULER_MEGAKERNEL] == warm[g.GI_SCHEDULER_WAVEFRONT]
+    n0 = warm[g.GI_SCHEDULER_WAVEFRONT][0]
+    assert n0 - 128 * nr == warm[g.GI_SCHEDULER_WAVEFRONT][1]
+    cap = n0 + n0 // 4
+    dev.alloc_light_cache(cap)
+    out = {}
+    for sched in (g.GI_SCHEDULER_MEGAKERNEL, g.GI_SCHEDULER_WAVEFRONT):
+        dev.set_option(g.GI_OPT_SCHEDULER, sched)
+        dev.clear(); dev.reset_counters()
+        entries = []
+        for k in range(N):
+            dev.set_light_samples(samples[k])
+            dev.render_iteration(g.GI_RENDERER_BPT, g.wang_hash(k), 16, num_rays_per_light_sample=nr, light_cache_capacity=cap)
+            entries.append(dev.counters()["light_cache_entries"])
+        out[sched] = (dev.read_accumulator(W, H), dev.counters(), entries)
+    (a, ca, ea), (b, cb, eb) = out[g.GI_SCHEDULER_MEGAKERNEL], out[g.GI_SCHEDULER_WAVEFRONT]
+    assert ea == eb
+    assert np.all(a[..., 3] == N) and np.all(b[..., 3] == N)
+    for k in ("light_paths", "camera_paths"):
+        assert ca[k] == cb[k], k
+    assert abs(ca["shaded_vertices"] - cb["shaded_vertices"]) == 0
+    am, bm = a[..., :3] / N, b[..., :3] / N
+    assert abs(am.mean() - bm.mean()) / am.mean() < 0.03
+    ab = am.reshape(12, 8, 12, 8, 3).mean(axis=(1, 3))
+    bb = bm.reshape(12, 8, 12, 8, 3).mean(axis=(1, 3))
+    assert rel_mse(ab, bb) < 0.1
+    dev.close()
