@@ -15,7 +15,7 @@ import numpy as np
 from . import _capi as capi
 from ._capi import (GI_RENDERER_PT, GI_RENDERER_LPT, GI_RENDERER_BPT, GI_TRAVERSAL_FAST, GI_TRAVERSAL_REFERENCE,
                     GI_OPT_TRAVERSAL, GI_OPT_TEXTURE_FILTER, GI_OPT_SCHEDULER, GI_OPT_WF_REFILL_THRESHOLD, GI_OPT_WF_MIN_INNER,
-                    GI_OPT_WF_BLOCKS_PER_SM, GI_OPT_COUNT_STEPS, GI_OPT_KERNEL_TIMING, GI_SCHEDULER_WAVEFRONT, GI_SCHEDULER_MEGAKERNEL, RAY_MAX)
+                    GI_OPT_WF_BLOCKS_PER_SM, GI_OPT_COUNT_STEPS, GI_OPT_KERNEL_TIMING, GI_OPT_STREAMING, GI_SCHEDULER_WAVEFRONT, GI_SCHEDULER_MEGAKERNEL, RAY_MAX)
 
 RAY_DTYPE = np.dtype([("origin", "<f4", 3), ("t_max", "<f4"), ("direction", "<f4", 3), ("flags", "<u4")])
 HIT_DTYPE = np.dtype([("t", "<f4"), ("leaf_tri", "<i4"), ("bary_y", "<f4"), ("bary_z", "<f4")])
@@ -274,6 +274,16 @@ class Device:
         self._check(capi.dev.gi_read_accumulator(self._c, _vp(out)), "gi_read_accumulator")
         return out
 
+    def read_accumulator_async(self, out):
+        """gi_read_accumulator_async: snapshot + copy on a second stream, no drain; returns the iterations still in flight.
+        `out` (pinned for a truly asynchronous copy) is complete after wait_reads()."""
+        n = C.c_uint32()
+        self._check(capi.dev.gi_read_accumulator_async(self._c, _vp(out), C.byref(n)), "gi_read_accumulator_async")
+        return n.value
+
+    def wait_reads(self):
+        self._check(capi.dev.gi_wait_reads(self._c), "gi_wait_reads")
+
     def accumulator_device(self):
         ptr, nbytes = C.c_void_p(), C.c_size_t()
         self._check(capi.dev.gi_accumulator_device(self._c, C.byref(ptr), C.byref(nbytes)), "gi_accumulator_device")
@@ -382,6 +392,21 @@ class RendererSystem:
         a, b, c = C.c_int32(), C.c_uint32(), C.c_int32()
         capi.host.gih_rs_renderer_info(self._h, C.byref(a), C.byref(b), C.byref(c))
         return {"num_rays_per_light_sample": a.value, "light_cache_capacity": b.value, "average_light_path_length": c.value}
+
+    def SetStreaming(self, streaming):
+        capi.host.gih_rs_set_streaming(self._h, 1 if streaming else 0)
+
+    def ReadBackbufferAsync(self, out):
+        """Progressive display read: never stalls or drains the renderer.  Returns the number of submitted iterations that
+        are not in the image yet (<= pathLength + 1 while streaming, else 0); `out` is complete after WaitReads()."""
+        n = C.c_uint32()
+        if capi.host.gih_rs_read_backbuffer_async(self._h, _vp(out), C.byref(n)) != 0:
+            raise GpugiError("ReadBackbufferAsync: " + capi.dev.gi_last_error(self.device._c).decode())
+        return n.value
+
+    def WaitReads(self):
+        if capi.host.gih_rs_wait_reads(self._h) != 0:
+            raise GpugiError("WaitReads: " + capi.dev.gi_last_error(self.device._c).decode())
 
     def ReadBackbuffer(self, out=None):
         w, h = self._size

@@ -108,6 +108,7 @@ GI_TRAVERSAL_FAST, GI_TRAVERSAL_REFERENCE = 0, 1
 GI_OPT_TRAVERSAL, GI_OPT_TEXTURE_FILTER, GI_OPT_SCHEDULER = 0, 1, 2
 GI_OPT_WF_REFILL_THRESHOLD, GI_OPT_WF_MIN_INNER, GI_OPT_WF_BLOCKS_PER_SM, GI_OPT_COUNT_STEPS = 3, 4, 6, 7
 GI_OPT_KERNEL_TIMING = 8
+GI_OPT_STREAMING = 9
 GI_KERNEL_TRACE, GI_KERNEL_SHADE, GI_KERNEL_GENERATE, GI_KERNEL_MEGAKERNEL, GI_KERNEL_OTHER, GI_KERNEL_CLASS_COUNT = 0, 1, 2, 3, 4, 5
 GI_SCHEDULER_WAVEFRONT, GI_SCHEDULER_MEGAKERNEL = 0, 1
 GI_TEX_SRGB8_ALPHA8, GI_TEX_RGBA8, GI_TEX_RGBA32F = 0, 1, 2
@@ -139,6 +140,8 @@ DEVICE_API = {
     "gi_trace_device": (C.c_int, [vp, vp, u32, vp]),
     "gi_synchronize": (C.c_int, [vp]),
     "gi_read_accumulator": (C.c_int, [vp, vp]),
+    "gi_read_accumulator_async": (C.c_int, [vp, vp, P(u32)]),
+    "gi_wait_reads": (C.c_int, [vp]),
     "gi_accumulator_device": (C.c_int, [vp, P(vp), P(C.c_size_t)]),
     "gi_compute_mse": (C.c_int, [vp, vp, u32, P(f32)]),
     "gi_get_counters": (C.c_int, [vp, P(GiCounters)]),
@@ -181,6 +184,9 @@ HOST_API = {
     "gih_rs_frame_seed": (u32, [vp]),
     "gih_rs_global_iteration": (u64, [vp]),
     "gih_rs_read_backbuffer": (C.c_int, [vp, vp]),
+    "gih_rs_set_streaming": (None, [vp, C.c_int]),
+    "gih_rs_read_backbuffer_async": (C.c_int, [vp, vp, P(u32)]),
+    "gih_rs_wait_reads": (C.c_int, [vp]),
     "gih_rs_num_light_samples": (u32, [vp]),
     "gih_rs_light_samples": (None, [vp, vp]),
     "gih_rs_camera": (None, [vp, P(GiCamera)]),

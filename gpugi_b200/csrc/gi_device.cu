@@ -166,6 +166,7 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MIN_BLOCKS) k_wf_tr
 	io.q.width = w.f.width; io.q.height = w.f.height;
 	io.q.numClosest = w.numCam + counts[0];
 	io.q.numShadow = counts[1];
+	io.q.rayBase = w.rayBase;
 	WfCounters<STEPS> cnt;
 	if (REFERENCE) wfTraceLoopReference(w.f.scene, io, counts + 2, cnt);
 	else wfTraceLoop(w.f.scene, io, counts + 2, w.tune, cnt);
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(WF_SHADE_THREADS) k_wf_shade_pt(WfFrame w, uns
 		base = __shfl_sync(0xffffffffu, base, 0);
 		if (base >= n) break;
 		const uint32_t slot = base + laneId();
-		wfShadePT(w, slot, slot < n, cnt);
+		wfShadePT(w, w.rayBase + slot, slot < n, cnt);
 	}
 	flushWarpCounters(counters, cnt, WFC_COUNT);
 }
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(WF_SHADE_THREADS) k_wf_shade_light(WfFrame w, 
 		base = __shfl_sync(0xffffffffu, base, 0);
 		if (base >= n) break;
 		const uint32_t slot = base + laneId();
-		wfShadeLight(w, slot, slot < n, pc);
+		wfShadeLight(w, w.rayBase + slot, slot < n, pc);
 	}
 	unsigned cnt[WFC_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 	wfAddCounters(cnt, pc);
@@ -247,7 +248,7 @@ __global__ void __launch_bounds__(WF_SHADE_THREADS) k_wf_shade_eye(WfFrame w, un
 		base = __shfl_sync(0xffffffffu, base, 0);
 		if (base >= n) break;
 		const uint32_t slot = base + laneId();
-		wfShadeEye(w, slot, slot < n, numEntries, pc);
+		wfShadeEye(w, w.rayBase + slot, slot < n, numEntries, pc);
 	}
 	unsigned cnt[WFC_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 	wfAddCounters(cnt, pc);
@@ -297,6 +298,21 @@ __global__ void __launch_bounds__(256) k_mse(const float4* __restrict__ accum, c
 // =====================================================================================================
 // context
 // =====================================================================================================
+enum { WF_PASS_PT = 0, WF_PASS_LIGHT, WF_PASS_EYE };
+#define WF_STREAM_COUNTS_RING 8u
+#define GI_LIGHT_RING 64u            // light-sample sets kept on the device: a stream has up to maxPathLength + 1 iterations in flight
+
+struct WfRun
+{
+	bool open = false, streaming = false;
+	int pass = 0;
+	uint32_t count = 0;      // iterations started
+	uint32_t wave = 0;       // next wave
+	uint32_t maxLen = 0, numSlots = 0;
+	int renderer = 0, numRaysPerLightSample = 0;
+	WfFrame w;
+};
+
 struct GiContext
 {
 	int device = 0;
@@ -345,6 +361,16 @@ struct GiContext
 	WfTune tune = {16, 20, 0};
 
 	// wavefront queues
+	WfRun run;
+	int streamingOption = 0;         // GI_OPT_STREAMING
+	uint32_t lightSlot = 0;          // ring slot of the light-sample set the next iteration uses
+	// asynchronous read-out (gi_read_accumulator_async)
+	cudaStream_t copyStream = nullptr;
+	float* snapshot[2] = {nullptr, nullptr};
+	size_t snapshotBytes = 0;
+	cudaEvent_t snapTaken[2] = {nullptr, nullptr}, snapCopied[2] = {nullptr, nullptr};
+	bool snapUsed[2] = {false, false};
+	int snapNext = 0;
 	WfQueues wf = {};
 	uint32_t wfCountsLen = 0;
 	uint64_t wfStates = 0;           // allocated path state records (numSlots x numIds)
@@ -436,7 +462,7 @@ static DFrame makeFrame(GiContext* c, const GiIterationParams* p)
 	f.scene.textureFilterExact = c->textureFilterExact;
 	f.cam = c->cam;
 	f.width = c->width; f.height = c->height;
-	f.lightSamples = c->externalLightSamples ? c->externalLightSamples : c->lightSamples;
+	f.lightSamples = c->externalLightSamples ? c->externalLightSamples : c->lightSamples + size_t(c->lightSlot) * 2u * size_t(c->numLightSamples);
 	f.numLightSamples = c->numLightSamples;
 	f.frameSeed = p ? p->frame_seed : 0u;
 	f.maxPathLength = p ? p->max_path_length : 16;
@@ -500,17 +526,19 @@ static int ensureWavefront(GiContext* c, uint64_t capacity, uint32_t numIds, uin
 	return GI_OK;
 }
 
-// `count` iterations of one pass as waves (gi_wavefront.cuh): wave w = generate(iteration w), trace, shade; maxPathLength drain
-// waves; final fold of the per-path radiance sums (PT, BPT eye pass).  seeds[k] = FrameSeed of batch iteration k; its light
-// samples are f.lightSamples + k * lightStride.
+// Iterations of one pass as waves (gi_wavefront.cuh): wave w = generate(iteration w), trace, shade; maxPathLength drain
+// waves; final fold of the per-path radiance sums (PT, BPT eye pass).
 //   WF_PASS_PT     pathtracer.comp          ids = pixels, W/8 x H/8 tiles
 //   WF_PASS_LIGHT  lighttracer.comp         ids = light paths; lightFlags = WF_LIGHT_SAVE / WF_LIGHT_WARMUP (gi_shade.h)
-//   WF_PASS_EYE    pathtracer_bidir.comp    ids = pixels; count must be 1 (the pass reads the light cache its own light pass filled)
-enum { WF_PASS_PT = 0, WF_PASS_LIGHT, WF_PASS_EYE };
-
-static int renderWavefront(GiContext* c, const DFrame& f, int pass, uint32_t lightFlags, const uint32_t* seeds, uint32_t count, uint32_t lightStride)
+//   WF_PASS_EYE    pathtracer_bidir.comp    ids = pixels; one iteration (the pass reads the light cache its own light pass filled)
+// A run is opened (wfOpen), fed one iteration per wave (wfStep) and closed (wfClose: drain + fold).  A batch
+// (gi_render_iterations) does all three in one call; a stream (GI_OPT_STREAMING) keeps the run open across
+// gi_render_iteration calls, so that consecutive Draw() calls overlap exactly like the iterations of a batch.
+static int wfOpen(GiContext* c, const DFrame& f, int pass, uint32_t lightFlags, uint32_t expectedCount, bool streaming, uint32_t lightStride, uint32_t lightBase,
+                  uint32_t lightRing)
 {
-	WfFrame w;
+	WfRun& r = c->run;
+	WfFrame& w = r.w;
 	std::memset(&w, 0, sizeof(w));
 	w.f = f;
 	w.lightFlags = lightFlags;
@@ -526,61 +554,118 @@ static int renderWavefront(GiContext* c, const DFrame& f, int pass, uint32_t lig
 		w.numPaths = uint32_t(w.tilesX) * uint32_t(w.tilesY) * 64u;
 		numIds = uint32_t(c->width) * uint32_t(c->height);
 	}
-	w.lightStride = lightStride;
-	if (w.numPaths == 0 || count == 0) return GI_OK;
-	if (pass == WF_PASS_EYE && count != 1u) return fail(c, GI_ERR_INVALID, "wavefront BPT eye pass: one iteration at a time");
-	const uint32_t maxLen = uint32_t(f.maxPathLength);
-	const uint32_t numSlots = std::min(count, maxLen + 1u);
-	const uint32_t numWaves = count + maxLen; // the last wave carries shadow rays only
-	// worst case (no path ever ends before maxPathLength): maxLen generations of rays share a wave.  Any batch (count > 1)
-	// reserves that much, so that batches of different length never reallocate.
-	int st = ensureWavefront(c, uint64_t(w.numPaths) * (count > 1u ? maxLen : 1u), numIds, count > 1u ? maxLen + 1u : 1u, WF_COUNTS_PER_WAVE * (numWaves + 1u));
+	w.lightStride = lightStride; w.lightBase = lightBase; w.lightRing = lightRing ? lightRing : 0x7fffffffu;
+	r.open = false;
+	r.pass = pass; r.streaming = streaming; r.count = 0; r.wave = 0;
+	r.maxLen = uint32_t(f.maxPathLength);
+	if (w.numPaths == 0) return GI_OK;
+	const bool many = streaming || expectedCount > 1u;
+	r.numSlots = streaming ? r.maxLen + 1u : std::min(expectedCount, r.maxLen + 1u);
+	// a batch has one counter entry per wave (zeroed here); a stream cycles through a ring
+	const uint32_t countsRing = streaming ? WF_STREAM_COUNTS_RING : expectedCount + r.maxLen + 1u;
+	// worst case (no path ever ends before maxPathLength): maxLen generations of rays share a wave.  Any batch / stream
+	// reserves that much, so that runs of different length never reallocate.
+	int st = ensureWavefront(c, uint64_t(w.numPaths) * (many ? r.maxLen : 1u), numIds, many ? r.maxLen + 1u : 1u, WF_COUNTS_PER_WAVE * countsRing);
 	if (st != GI_OK) return st;
 	w.q = c->wf;
-	w.q.numSlots = numSlots;
+	w.q.numSlots = r.numSlots;
+	w.q.countsRing = countsRing;
 	w.tune = c->tune;
-	GI_CUDA(c, cudaMemsetAsync(c->wf.counts, 0, size_t(WF_COUNTS_PER_WAVE) * (numWaves + 1u) * sizeof(uint32_t), c->stream));
+	GI_CUDA(c, cudaMemsetAsync(c->wf.counts, 0, size_t(WF_COUNTS_PER_WAVE) * countsRing * sizeof(uint32_t), c->stream));
 	// ids outside the W/8 x H/8 tiles are never written by shade(); the fold reads them
-	if (pass != WF_PASS_LIGHT && w.numPaths != w.q.numIds) GI_CUDA(c, cudaMemsetAsync(c->wf.stateC, 0, size_t(numSlots) * w.q.numIds * 16, c->stream));
+	if (pass != WF_PASS_LIGHT && w.numPaths != w.q.numIds) GI_CUDA(c, cudaMemsetAsync(c->wf.stateC, 0, size_t(r.numSlots) * w.q.numIds * 16, c->stream));
+	r.open = true;
+	timingMark(c, -1);
+	return GI_OK;
+}
+
+// One wave.  generate: iteration r.count starts in this wave (FrameSeed `seed`); nextGenerates: the next wave will start an
+// iteration too (a stream cannot know and always reserves the head of the next queue); shade: false for the very last wave.
+static int wfStep(GiContext* c, bool generate, uint32_t seed, bool nextGenerates, bool shade)
+{
+	WfRun& r = c->run;
+	WfFrame& w = r.w;
+	if (!r.open) return GI_OK;
+	const int pass = r.pass;
+	w.wave = int(r.wave);
+	w.numCam = generate ? w.numPaths : 0u;
+	w.pushBase = (r.streaming || nextGenerates) ? w.numPaths : 0u;
+	w.rayBase = (r.streaming && !generate) ? w.numPaths : 0u;
 	const unsigned traceGrid = unsigned(c->numSMs * c->traceBlocksPerSM);
 	const unsigned shadeGrid = unsigned(c->numSMs * (pass == WF_PASS_PT ? c->shadeBlocksPerSM : pass == WF_PASS_LIGHT ? c->shadeLightBlocksPerSM : c->shadeEyeBlocksPerSM));
-	const bool ref = f.traversalMode == GI_TRAVERSAL_REFERENCE;
-	timingMark(c, -1);
-	for (uint32_t wave = 0; wave < numWaves; ++wave)
+	const bool ref = w.f.traversalMode == GI_TRAVERSAL_REFERENCE;
+	if (r.streaming)
+		GI_CUDA(c, cudaMemsetAsync(c->wf.counts + WF_COUNTS_PER_WAVE * size_t((r.wave + 1u) % w.q.countsRing), 0, WF_COUNTS_PER_WAVE * sizeof(uint32_t), c->stream));
+	if (generate)
 	{
-		w.wave = int(wave);
-		w.numCam = wave < count ? w.numPaths : 0u;
-		w.pushBase = wave + 1u < count ? w.numPaths : 0u;
-		if (wave < count)
-		{
-			w.f.frameSeed = seeds[wave];
-			if (pass == WF_PASS_LIGHT) k_wf_generate_light<<<unsigned(c->numSMs) * 8u, 256, 0, c->stream>>>(w, c->counters);
-			else k_wf_generate<<<unsigned(c->numSMs) * 8u, 256, 0, c->stream>>>(w, c->counters);
-			++c->launches;
-			timingMark(c, GI_KERNEL_GENERATE);
-		}
-		if (ref) k_wf_trace<true, true><<<traceGrid, WF_TRACE_THREADS, 0, c->stream>>>(w, c->counters);
-		else if (c->countSteps) k_wf_trace<false, true><<<traceGrid, WF_TRACE_THREADS, 0, c->stream>>>(w, c->counters);
-		else k_wf_trace<false, false><<<traceGrid, WF_TRACE_THREADS, 0, c->stream>>>(w, c->counters);
+		w.f.frameSeed = seed;
+		if (pass == WF_PASS_LIGHT) k_wf_generate_light<<<unsigned(c->numSMs) * 8u, 256, 0, c->stream>>>(w, c->counters);
+		else k_wf_generate<<<unsigned(c->numSMs) * 8u, 256, 0, c->stream>>>(w, c->counters);
 		++c->launches;
-		timingMark(c, GI_KERNEL_TRACE);
-		if (wave + 1u < numWaves)
-		{
-			if (pass == WF_PASS_PT) k_wf_shade_pt<<<shadeGrid, WF_SHADE_THREADS, 0, c->stream>>>(w, c->counters);
-			else if (pass == WF_PASS_LIGHT) k_wf_shade_light<<<shadeGrid, WF_SHADE_THREADS, 0, c->stream>>>(w, c->counters);
-			else k_wf_shade_eye<<<shadeGrid, WF_SHADE_THREADS, 0, c->stream>>>(w, c->counters);
-			++c->launches;
-			timingMark(c, GI_KERNEL_SHADE);
-		}
+		++r.count;
+		timingMark(c, GI_KERNEL_GENERATE);
 	}
-	if (pass != WF_PASS_LIGHT)
+	if (ref) k_wf_trace<true, true><<<traceGrid, WF_TRACE_THREADS, 0, c->stream>>>(w, c->counters);
+	else if (c->countSteps) k_wf_trace<false, true><<<traceGrid, WF_TRACE_THREADS, 0, c->stream>>>(w, c->counters);
+	else k_wf_trace<false, false><<<traceGrid, WF_TRACE_THREADS, 0, c->stream>>>(w, c->counters);
+	++c->launches;
+	timingMark(c, GI_KERNEL_TRACE);
+	if (shade)
 	{
-		k_wf_fold<<<unsigned(c->numSMs) * 8u, 256, 0, c->stream>>>(reinterpret_cast<float4*>(c->accum), c->wf.stateC, w.q.numIds, numSlots, count - numSlots, count);
+		if (pass == WF_PASS_PT) k_wf_shade_pt<<<shadeGrid, WF_SHADE_THREADS, 0, c->stream>>>(w, c->counters);
+		else if (pass == WF_PASS_LIGHT) k_wf_shade_light<<<shadeGrid, WF_SHADE_THREADS, 0, c->stream>>>(w, c->counters);
+		else k_wf_shade_eye<<<shadeGrid, WF_SHADE_THREADS, 0, c->stream>>>(w, c->counters);
 		++c->launches;
-		timingMark(c, GI_KERNEL_OTHER);
+		timingMark(c, GI_KERNEL_SHADE);
 	}
-	timingCollect(c);
+	++r.wave;
 	return GI_OK;
+}
+
+// Drain: maxPathLength waves without generate (the last one carries shadow rays only), then the fold.
+static int wfClose(GiContext* c)
+{
+	WfRun& r = c->run;
+	if (!r.open) return GI_OK;
+	if (r.count > 0)
+	{
+		for (uint32_t k = 0; k < r.maxLen; ++k)
+		{
+			int st = wfStep(c, false, 0u, false, k + 1u < r.maxLen);
+			if (st != GI_OK) return st;
+		}
+		if (r.pass != WF_PASS_LIGHT)
+		{
+			const uint32_t first = r.count > r.numSlots ? r.count - r.numSlots : 0u;
+			k_wf_fold<<<unsigned(c->numSMs) * 8u, 256, 0, c->stream>>>(reinterpret_cast<float4*>(c->accum), c->wf.stateC, r.w.q.numIds, r.numSlots, first, r.count);
+			++c->launches;
+			timingMark(c, GI_KERNEL_OTHER);
+		}
+	}
+	r.open = false;
+	// a stream leaves the set of the NEXT iteration at ring slot lightBase + count
+	if (r.streaming) c->lightSlot = (r.w.lightBase + r.count) % GI_LIGHT_RING;
+	timingCollect(c);
+	GI_CUDA(c, cudaGetLastError());
+	return GI_OK;
+}
+
+// an open stream must be drained before anything reads or redefines what its iterations depend on
+static int flushStream(GiContext* c)
+{
+	if (c && c->run.open && c->run.streaming) return wfClose(c);
+	return GI_OK;
+}
+
+static int renderWavefront(GiContext* c, const DFrame& f, int pass, uint32_t lightFlags, const uint32_t* seeds, uint32_t count, uint32_t lightStride)
+{
+	if (count == 0) return GI_OK;
+	if (pass == WF_PASS_EYE && count != 1u) return fail(c, GI_ERR_INVALID, "wavefront BPT eye pass: one iteration at a time");
+	int st = wfOpen(c, f, pass, lightFlags, count, false, lightStride, 0u, 0u);
+	for (uint32_t k = 0; st == GI_OK && k < count; ++k) st = wfStep(c, true, seeds[k], k + 1u < count, true);
+	if (st == GI_OK) st = wfClose(c);
+	c->run.open = false;
+	return st;
 }
 
 
@@ -641,6 +726,9 @@ void gi_destroy(GiContext* c)
 	freeScene(c);
 	freeWavefront(c);
 	cudaFree(c->traceWork);
+	cudaFree(c->snapshot[0]); cudaFree(c->snapshot[1]);
+	for (int i = 0; i < 2; ++i) { if (c->snapTaken[i]) cudaEventDestroy(c->snapTaken[i]); if (c->snapCopied[i]) cudaEventDestroy(c->snapCopied[i]); }
+	if (c->copyStream) cudaStreamDestroy(c->copyStream);
 	if (c->envTex) cudaDestroyTextureObject(c->envTex);
 	if (c->envArray) cudaFreeArray(c->envArray);
 	cudaFree(c->accum); cudaFree(c->lightSamples); cudaFree(c->lightCache); cudaFree(c->bptCounters); cudaFree(c->counters); cudaFree(c->mseResult);
@@ -652,6 +740,8 @@ void gi_destroy(GiContext* c)
 int gi_set_stream(GiContext* c, void* cuda_stream)
 {
 	if (!c) return GI_ERR_INVALID;
+	int fst = flushStream(c);
+	if (fst != GI_OK) return fst;
 	GI_CUDA(c, cudaStreamSynchronize(c->stream));
 	c->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->ownStream;
 	return GI_OK;
@@ -660,8 +750,11 @@ int gi_set_stream(GiContext* c, void* cuda_stream)
 int gi_set_option(GiContext* c, int option, int value)
 {
 	if (!c) return GI_ERR_INVALID;
+	int fst = flushStream(c);
+	if (fst != GI_OK) return fst;
 	switch (option)
 	{
+	case GI_OPT_STREAMING: c->streamingOption = value ? 1 : 0; return GI_OK;
 	case GI_OPT_TRAVERSAL:
 		if (value != GI_TRAVERSAL_FAST && value != GI_TRAVERSAL_REFERENCE) return fail(c, GI_ERR_INVALID, "GI_OPT_TRAVERSAL: unknown mode");
 		c->traversal = value; return GI_OK;
@@ -687,6 +780,8 @@ int gi_set_option(GiContext* c, int option, int value)
 int gi_clear_accumulator(GiContext* c)
 {
 	if (!c) return GI_ERR_INVALID;
+	int fst = flushStream(c);
+	if (fst != GI_OK) return fst;
 	if (c->accum) GI_CUDA(c, cudaMemsetAsync(c->accum, 0, size_t(c->width) * c->height * 4 * sizeof(float), c->stream));
 	return GI_OK;
 }
@@ -698,6 +793,8 @@ int gi_upload_scene(GiContext* c, const GiSceneDesc* d)
 	    !d->vertex_info || d->num_vertices == 0 || !d->materials || d->num_materials == 0)
 		return fail(c, GI_ERR_INVALID, "gi_upload_scene: incomplete scene description");
 	GI_CUDA(c, cudaSetDevice(c->device));
+	int fst = flushStream(c);
+	if (fst != GI_OK) return fst;
 	GI_CUDA(c, cudaStreamSynchronize(c->stream));
 	freeScene(c);
 
@@ -770,6 +867,8 @@ int gi_set_environment_map(GiContext* c, int size, const uint8_t* const* faces)
 {
 	if (!c) return GI_ERR_INVALID;
 	GI_CUDA(c, cudaSetDevice(c->device));
+	int fst = flushStream(c);
+	if (fst != GI_OK) return fst;
 	GI_CUDA(c, cudaStreamSynchronize(c->stream));
 	if (c->envTex) { cudaDestroyTextureObject(c->envTex); c->envTex = 0; }
 	if (c->envArray) { cudaFreeArray(c->envArray); c->envArray = nullptr; }
@@ -813,6 +912,8 @@ int gi_set_environment_map(GiContext* c, int size, const uint8_t* const* faces)
 int gi_set_camera(GiContext* c, const GiCamera* cam)
 {
 	if (!c || !cam) return GI_ERR_INVALID;
+	int fst = flushStream(c);
+	if (fst != GI_OK) return fst;
 	c->cam = *cam;
 	c->haveCamera = true;
 	return gi_clear_accumulator(c);
@@ -822,6 +923,9 @@ int gi_set_screen_size(GiContext* c, int width, int height)
 {
 	if (!c || width <= 0 || height <= 0) return fail(c, GI_ERR_INVALID, "gi_set_screen_size: bad size");
 	GI_CUDA(c, cudaSetDevice(c->device));
+	int fst = flushStream(c);
+	if (fst != GI_OK) return fst;
+	if (c->copyStream) GI_CUDA(c, cudaStreamSynchronize(c->copyStream));
 	GI_CUDA(c, cudaStreamSynchronize(c->stream));
 	if (c->accum) { cudaFree(c->accum); c->accum = nullptr; }
 	c->width = width; c->height = height;
@@ -829,21 +933,40 @@ int gi_set_screen_size(GiContext* c, int width, int height)
 	return gi_clear_accumulator(c);
 }
 
+// Light-sample sets live in a ring of GI_LIGHT_RING sets on the device: a stream (GI_OPT_STREAMING) has up to maxPathLength + 1
+// iterations in flight, each shading with its own set.  Outside a stream the ring position does not move.
+static int lightSlotForNextIteration(GiContext* c, uint32_t n, uint32_t* slot)
+{
+	if (c->run.open && c->run.streaming && int(n) != c->numLightSamples)
+	{
+		int st = flushStream(c);
+		if (st != GI_OK) return st;
+	}
+	if (n > c->lightSampleCapacity)
+	{
+		int st = flushStream(c);
+		if (st != GI_OK) return st;
+		GI_CUDA(c, cudaStreamSynchronize(c->stream));
+		if (c->lightSamples) cudaFree(c->lightSamples);
+		c->lightSamples = nullptr;
+		GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->lightSamples), size_t(n) * GI_LIGHT_RING * sizeof(GiLightSample)));
+		c->lightSampleCapacity = n;
+	}
+	*slot = (c->run.open && c->run.streaming) ? (c->run.w.lightBase + c->run.count) % GI_LIGHT_RING : c->lightSlot;
+	return GI_OK;
+}
+
 int gi_set_light_samples(GiContext* c, const GiLightSample* samples, uint32_t n)
 {
 	if (!c || !samples || n == 0) return fail(c, GI_ERR_INVALID, "gi_set_light_samples: no samples");
 	GI_CUDA(c, cudaSetDevice(c->device));
-	if (n > c->lightSampleCapacity)
-	{
-		GI_CUDA(c, cudaStreamSynchronize(c->stream));
-		if (c->lightSamples) cudaFree(c->lightSamples);
-		c->lightSamples = nullptr;
-		GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->lightSamples), size_t(n) * sizeof(GiLightSample)));
-		c->lightSampleCapacity = n;
-	}
+	uint32_t slot = 0;
+	int st = lightSlotForNextIteration(c, n, &slot);
+	if (st != GI_OK) return st;
 	// pageable source: the runtime stages the bytes before returning, so the caller may reuse `samples`;
 	// stream order keeps the previous iteration's reads ahead of this write.
-	GI_CUDA(c, cudaMemcpyAsync(c->lightSamples, samples, size_t(n) * sizeof(GiLightSample), cudaMemcpyHostToDevice, c->stream));
+	GI_CUDA(c, cudaMemcpyAsync(c->lightSamples + size_t(slot) * 2u * n, samples, size_t(n) * sizeof(GiLightSample), cudaMemcpyHostToDevice, c->stream));
+	c->lightSlot = slot;
 	c->externalLightSamples = nullptr;
 	c->numLightSamples = int(n);
 	return GI_OK;
@@ -852,6 +975,19 @@ int gi_set_light_samples(GiContext* c, const GiLightSample* samples, uint32_t n)
 int gi_set_light_samples_device(GiContext* c, const GiLightSample* d_samples, uint32_t n)
 {
 	if (!c || !d_samples || n == 0) return fail(c, GI_ERR_INVALID, "gi_set_light_samples_device: no samples");
+	if (c->streamingOption)
+	{
+		// a stream keeps using the set after this call returns: copy it into the ring
+		GI_CUDA(c, cudaSetDevice(c->device));
+		uint32_t slot = 0;
+		int st = lightSlotForNextIteration(c, n, &slot);
+		if (st != GI_OK) return st;
+		GI_CUDA(c, cudaMemcpyAsync(c->lightSamples + size_t(slot) * 2u * n, d_samples, size_t(n) * sizeof(GiLightSample), cudaMemcpyDeviceToDevice, c->stream));
+		c->lightSlot = slot;
+		c->externalLightSamples = nullptr;
+		c->numLightSamples = int(n);
+		return GI_OK;
+	}
 	c->externalLightSamples = reinterpret_cast<const F4*>(d_samples);
 	c->numLightSamples = int(n);
 	return GI_OK;
@@ -861,6 +997,8 @@ int gi_alloc_light_cache(GiContext* c, uint32_t capacity)
 {
 	if (!c || capacity == 0) return fail(c, GI_ERR_INVALID, "gi_alloc_light_cache: zero capacity");
 	GI_CUDA(c, cudaSetDevice(c->device));
+	int fst = flushStream(c);
+	if (fst != GI_OK) return fst;
 	GI_CUDA(c, cudaStreamSynchronize(c->stream));
 	if (c->lightCache) { cudaFree(c->lightCache); c->lightCache = nullptr; c->lightCacheCapacity = 0; }
 	GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->lightCache), size_t(capacity) * 64));
@@ -884,6 +1022,31 @@ int gi_render_iteration(GiContext* c, const GiIterationParams* p)
 	if (st != GI_OK) return st;
 	if (p->max_path_length <= 0) return fail(c, GI_ERR_INVALID, "max_path_length must be positive");
 	GI_CUDA(c, cudaSetDevice(c->device));
+	if (c->streamingOption && p->renderer == GI_RENDERER_PT && c->scheduler == GI_SCHEDULER_WAVEFRONT && !c->externalLightSamples &&
+	    uint32_t(p->max_path_length) + 1u <= GI_LIGHT_RING)
+	{
+		// GI_OPT_STREAMING: this iteration is one more wave of the open run (opened here if there is none)
+		WfRun& r = c->run;
+		if (r.open && r.streaming && (r.renderer != p->renderer || r.maxLen != uint32_t(p->max_path_length)))
+		{
+			st = flushStream(c);
+			if (st != GI_OK) return st;
+		}
+		if (!(r.open && r.streaming))
+		{
+			DFrame sf = makeFrame(c, p);
+			sf.lightSamples = c->lightSamples; // ring base; iteration i of the stream reads set (lightSlot + i) % GI_LIGHT_RING
+			st = wfOpen(c, sf, WF_PASS_PT, 0u, 0u, true, 2u * uint32_t(c->numLightSamples), c->lightSlot, GI_LIGHT_RING);
+			if (st != GI_OK) return st;
+			r.renderer = p->renderer;
+		}
+		st = wfStep(c, true, p->frame_seed, true, true);
+		if (st != GI_OK) return st;
+		GI_CUDA(c, cudaGetLastError());
+		return GI_OK;
+	}
+	st = flushStream(c);
+	if (st != GI_OK) return st;
 	DFrame f = makeFrame(c, p);
 	const dim3 pixelGrid(unsigned(c->width / 8), unsigned(c->height / 8), 1); // integer division, pathtracer.cpp:50
 	switch (p->renderer)
@@ -965,11 +1128,15 @@ int gi_render_iterations(GiContext* c, const GiIterationParams* p, const uint32_
 {
 	if (!c || !p || (count && !frame_seeds)) return GI_ERR_INVALID;
 	if (count == 0) return GI_OK;
+	{
+		int fst = flushStream(c);
+		if (fst != GI_OK) return fst;
+	}
 	if (d_light_samples)
 	{
 		if (samples_per_iteration == 0) return fail(c, GI_ERR_INVALID, "gi_render_iterations: samples_per_iteration must be positive");
-		int st = gi_set_light_samples_device(c, d_light_samples, samples_per_iteration);
-		if (st != GI_OK) return st;
+		c->externalLightSamples = reinterpret_cast<const F4*>(d_light_samples);
+		c->numLightSamples = int(samples_per_iteration);
 	}
 	int st = checkRenderState(c);
 	if (st != GI_OK) return st;
@@ -1001,6 +1168,10 @@ int gi_render_iterations(GiContext* c, const GiIterationParams* p, const uint32_
 int gi_show_light_caches(GiContext* c)
 {
 	if (!c) return GI_ERR_INVALID;
+	{
+		int fst = flushStream(c);
+		if (fst != GI_OK) return fst;
+	}
 	int st = checkRenderState(c);
 	if (st != GI_OK) return st;
 	GI_CUDA(c, cudaSetDevice(c->device));
@@ -1059,6 +1230,10 @@ int gi_trace(GiContext* c, const GiRay* rays, uint32_t n, GiHit* hits)
 int gi_synchronize(GiContext* c)
 {
 	if (!c) return GI_ERR_INVALID;
+	{
+		int fst = flushStream(c);
+		if (fst != GI_OK) return fst;
+	}
 	GI_CUDA(c, cudaStreamSynchronize(c->stream));
 	return GI_OK;
 }
@@ -1066,15 +1241,70 @@ int gi_synchronize(GiContext* c)
 int gi_read_accumulator(GiContext* c, float* rgba)
 {
 	if (!c || !rgba) return GI_ERR_INVALID;
+	{
+		int fst = flushStream(c);
+		if (fst != GI_OK) return fst;
+	}
 	if (!c->accum) return fail(c, GI_ERR_INVALID, "gi_set_screen_size was not called");
 	GI_CUDA(c, cudaMemcpyAsync(rgba, c->accum, size_t(c->width) * c->height * 4 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
 	GI_CUDA(c, cudaStreamSynchronize(c->stream));
 	return GI_OK;
 }
 
+// Progressive read-out that does not drain an open stream: a device-to-device snapshot of the accumulator in stream order
+// (after the waves submitted so far), copied to the host on a second stream while the next waves run.
+int gi_read_accumulator_async(GiContext* c, float* rgba, uint32_t* iterations_in_flight)
+{
+	if (!c || !rgba) return GI_ERR_INVALID;
+	if (!c->accum) return fail(c, GI_ERR_INVALID, "gi_set_screen_size was not called");
+	GI_CUDA(c, cudaSetDevice(c->device));
+	const size_t bytes = size_t(c->width) * c->height * 4 * sizeof(float);
+	if (!c->copyStream)
+	{
+		GI_CUDA(c, cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
+		for (int i = 0; i < 2; ++i)
+		{
+			GI_CUDA(c, cudaEventCreateWithFlags(&c->snapTaken[i], cudaEventDisableTiming));
+			GI_CUDA(c, cudaEventCreateWithFlags(&c->snapCopied[i], cudaEventDisableTiming));
+		}
+	}
+	if (c->snapshotBytes != bytes)
+	{
+		GI_CUDA(c, cudaStreamSynchronize(c->copyStream));
+		GI_CUDA(c, cudaStreamSynchronize(c->stream));
+		for (int i = 0; i < 2; ++i) { cudaFree(c->snapshot[i]); c->snapshot[i] = nullptr; c->snapUsed[i] = false; }
+		c->snapshotBytes = 0;
+		for (int i = 0; i < 2; ++i) GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->snapshot[i]), bytes));
+		c->snapshotBytes = bytes;
+	}
+	const int i = c->snapNext;
+	c->snapNext ^= 1;
+	if (c->snapUsed[i]) GI_CUDA(c, cudaStreamWaitEvent(c->stream, c->snapCopied[i], 0)); // the read before last has left this buffer
+	GI_CUDA(c, cudaMemcpyAsync(c->snapshot[i], c->accum, bytes, cudaMemcpyDeviceToDevice, c->stream));
+	GI_CUDA(c, cudaEventRecord(c->snapTaken[i], c->stream));
+	GI_CUDA(c, cudaStreamWaitEvent(c->copyStream, c->snapTaken[i], 0));
+	GI_CUDA(c, cudaMemcpyAsync(rgba, c->snapshot[i], bytes, cudaMemcpyDeviceToHost, c->copyStream));
+	GI_CUDA(c, cudaEventRecord(c->snapCopied[i], c->copyStream));
+	c->snapUsed[i] = true;
+	// PT stream: iteration k joins the accumulator when its state slot is recycled, maxPathLength + 1 waves after it started
+	if (iterations_in_flight) *iterations_in_flight = (c->run.open && c->run.streaming) ? std::min(c->run.count, c->run.numSlots) : 0u;
+	return GI_OK;
+}
+
+int gi_wait_reads(GiContext* c)
+{
+	if (!c) return GI_ERR_INVALID;
+	if (c->copyStream) GI_CUDA(c, cudaStreamSynchronize(c->copyStream));
+	return GI_OK;
+}
+
 int gi_accumulator_device(GiContext* c, void** device_ptr, size_t* num_bytes)
 {
 	if (!c || !device_ptr) return GI_ERR_INVALID;
+	{
+		int fst = flushStream(c);
+		if (fst != GI_OK) return fst;
+	}
 	if (!c->accum) return fail(c, GI_ERR_INVALID, "gi_set_screen_size was not called");
 	*device_ptr = c->accum;
 	if (num_bytes) *num_bytes = size_t(c->width) * c->height * 4 * sizeof(float);
@@ -1084,6 +1314,10 @@ int gi_accumulator_device(GiContext* c, void** device_ptr, size_t* num_bytes)
 int gi_compute_mse(GiContext* c, const float* reference_rgb, uint32_t divisor, float* mse)
 {
 	if (!c || !reference_rgb || !mse || divisor == 0) return GI_ERR_INVALID;
+	{
+		int fst = flushStream(c);
+		if (fst != GI_OK) return fst;
+	}
 	if (!c->accum) return fail(c, GI_ERR_INVALID, "gi_set_screen_size was not called");
 	GI_CUDA(c, cudaSetDevice(c->device));
 	const uint32_t numPixels = uint32_t(c->width) * uint32_t(c->height);
@@ -1109,6 +1343,10 @@ int gi_compute_mse(GiContext* c, const float* reference_rgb, uint32_t divisor, f
 int gi_get_counters(GiContext* c, GiCounters* out)
 {
 	if (!c || !out) return GI_ERR_INVALID;
+	{
+		int fst = flushStream(c);
+		if (fst != GI_OK) return fst;
+	}
 	unsigned long long h[CNT_COUNT];
 	uint32_t b[2];
 	GI_CUDA(c, cudaMemcpyAsync(h, c->counters, sizeof(h), cudaMemcpyDeviceToHost, c->stream));

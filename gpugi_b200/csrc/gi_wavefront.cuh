@@ -56,7 +56,9 @@ struct WfQueues
 	F4* stateT;          // numSlots x numIds: (throughput.xyz, seed bits)
 	F4* stateC;          // numSlots x numIds: (radiance sum.xyz, alpha increment)
 	float* stateM;       // numSlots x numIds: lastConnectionProbability of a BPT eye path
-	uint32_t* counts;    // WF_COUNTS_PER_WAVE x (waves of the batch + 1), zeroed per batch
+	uint32_t* counts;    // WF_COUNTS_PER_WAVE x countsRing; wave w uses entry w % countsRing (a batch: one entry per wave, zeroed up front;
+	                     // a stream: a ring, entry w + 1 is zeroed before wave w starts)
+	uint32_t countsRing;
 	uint32_t capacity;   // slots per queue
 	uint32_t numIds;     // path ids per iteration (PT/BPT: width x height)
 	uint32_t numSlots;   // S iterations in flight
@@ -105,6 +107,7 @@ struct WfTraceIO
 	float* accum;
 	int width, height;
 	uint32_t numClosest, numShadow;
+	uint32_t rayBase;   // extension ray i of this wave sits in queue slot rayBase + i
 };
 
 GI_D void wfSplat(float* accum, int width, int height, uint32_t pixel, F3 v)
@@ -231,7 +234,7 @@ struct WfQueueIO
 	GI_D void load(const DScene& s, uint32_t index, WfLane& L, CNT& cnt) const
 	{
 		const bool isAny = index >= q.numClosest;
-		const F4* p = isAny ? q.shadow + 3 * size_t(index - q.numClosest) : q.rays + 2 * size_t(index);
+		const F4* p = isAny ? q.shadow + 3 * size_t(index - q.numClosest) : q.rays + 2 * size_t(q.rayBase + index);
 		const F4 r0 = ld4(p), r1 = ld4(p + 1);
 		wfBegin(L, s, f3(r0.x, r0.y, r0.z), f3(r1.x, r1.y, r1.z), isAny ? r0.w : GI_RAY_MAX, isAny, index, cnt);
 	}
@@ -239,7 +242,7 @@ struct WfQueueIO
 	GI_D void finish(const DScene& s, WfLane& L, CNT& cnt) const
 	{
 		if (L.flags & WFL_ANY) wfFinishShadow(q, L.index - q.numClosest, (L.flags & WFL_OCCLUDED) != 0u, cnt);
-		else q.hits[L.index] = make_float2(L.best, i2f(L.hitLeaf));
+		else q.hits[q.rayBase + L.index] = make_float2(L.best, i2f(L.hitLeaf));
 	}
 };
 
@@ -289,7 +292,10 @@ struct WfFrame
 	int wave;                // wave index inside the batch; bounce b of this wave belongs to batch iteration wave - b
 	uint32_t numCam;         // freshly generated rays at the head of this wave's extension queue (numPaths or 0)
 	uint32_t pushBase;       // ... of the next wave's extension queue: pushed rays are placed behind them
+	uint32_t rayBase;        // first slot of this wave's extension queue that holds a ray (0, or numPaths in a stream wave without generate)
 	uint32_t lightStride;    // F4 elements between the light samples of consecutive iterations (0: the same set for all)
+	uint32_t lightBase;      // iteration i reads light-sample set (lightBase + i) % lightRing
+	uint32_t lightRing;
 	uint32_t lightFlags;     // light tracer waves: WF_LIGHT_SAVE / WF_LIGHT_WARMUP (gi_shade.h)
 };
 
@@ -301,7 +307,10 @@ GI_D uint32_t wfSlotToPixel(const WfFrame& w, uint32_t slot)
 	return (tx * 8u + (l & 7u)) + (ty * 8u + (l >> 3)) * uint32_t(w.f.width);
 }
 
-GI_D uint32_t* wfCounts(const WfFrame& w, int wave) { return w.q.counts + WF_COUNTS_PER_WAVE * size_t(wave); }
+GI_D uint32_t* wfCounts(const WfFrame& w, int wave) { return w.q.counts + WF_COUNTS_PER_WAVE * size_t(uint32_t(wave) % w.q.countsRing); }
+
+// light samples of iteration `iteration` (relative to the start of the batch / stream)
+GI_D const F4* wfLightSamples(const WfFrame& w, uint32_t iteration) { return w.f.lightSamples + size_t((w.lightBase + iteration) % w.lightRing) * w.lightStride; }
 
 // Shades the hit of one extension ray of this wave.  Pushes at most one shadow ray and one extension ray
 // (warp-compacted, so all 32 lanes call this; `valid` masks the tail).
@@ -372,7 +381,7 @@ GI_D void wfShadePT(const WfFrame& w, uint32_t slot, bool valid, unsigned* cnt)
 			didNEE = md.Reflectiveness.w < 500.0f;
 			{
 				const int sampleIndex = int(randomUInt(seed) % uint32_t(f.numLightSamples));
-				if (prepareDirectLight(f.lightSamples + size_t(iteration) * w.lightStride, origin, hitNormal, sampleIndex, dir, md, didNEE, nee))
+				if (prepareDirectLight(wfLightSamples(w, iteration), origin, hitNormal, sampleIndex, dir, md, didNEE, nee))
 				{
 					pushShadow = true;
 					neeValue = nee.radiance * pathThroughput * float(f.numLightSamples);
@@ -450,7 +459,7 @@ GI_D void wfPushOut(const WfFrame& w, const WfPush& out, uint32_t shadowTarget, 
 GI_D void wfGenerateLight(const WfFrame& w, uint32_t gid, PathCounters& pc)
 {
 	DFrame f = w.f;
-	f.lightSamples = w.f.lightSamples + size_t(w.wave) * w.lightStride;
+	f.lightSamples = wfLightSamples(w, uint32_t(w.wave));
 	F3 origin, dir; F4 T;
 	wfGenerateLightLane(f, w.lightFlags, gid, origin, dir, T, pc);
 	++pc.closestRays;

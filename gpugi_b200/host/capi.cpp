@@ -202,6 +202,12 @@ uint64_t gih_rs_render_time_ms(GihRendererSystem* h) { return h->rs->GetRenderTi
 uint32_t gih_rs_frame_seed(GihRendererSystem* h) { return h->rs->GetFrameSeed(); }
 uint64_t gih_rs_global_iteration(GihRendererSystem* h) { return h->rs->GetGlobalIterationIndex(); }
 int gih_rs_read_backbuffer(GihRendererSystem* h, float* rgba) { return h->rs->GetBackbuffer().ReadImage(rgba) ? 0 : 1; }
+void gih_rs_set_streaming(GihRendererSystem* h, int streaming) { h->rs->SetStreaming(streaming != 0); }
+int gih_rs_read_backbuffer_async(GihRendererSystem* h, float* rgba, uint32_t* iterations_in_flight)
+{
+	return h->rs->GetBackbuffer().ReadImageAsync(rgba, iterations_in_flight) ? 0 : 1;
+}
+int gih_rs_wait_reads(GihRendererSystem* h) { return h->rs->GetBackbuffer().WaitReads() ? 0 : 1; }
 uint32_t gih_rs_num_light_samples(GihRendererSystem* h) { return h->rs->GetNumInitialLightSamples(); }
 void gih_rs_light_samples(GihRendererSystem* h, GiLightSample* out)
 {

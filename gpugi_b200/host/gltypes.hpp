@@ -18,6 +18,10 @@ namespace gl
 		void ClearToZero(int = 0) const { gi_clear_accumulator(m_ctx); }
 		/// gl::Texture::ReadImage(RGBA, FLOAT): width*height*4 floats, the un-normalised sum
 		bool ReadImage(float* rgba) const { return gi_read_accumulator(m_ctx, rgba) == GI_OK; }
+		/// Progressive display read (gi_read_accumulator_async): does not stall or drain the renderer; `rgba` is complete
+		/// after WaitReads() / the read after next.  iterationsInFlight: submitted iterations not yet in the image.
+		bool ReadImageAsync(float* rgba, uint32_t* iterationsInFlight) const { return gi_read_accumulator_async(m_ctx, rgba, iterationsInFlight) == GI_OK; }
+		bool WaitReads() const { return gi_wait_reads(m_ctx) == GI_OK; }
 		GiContext* GetDevice() const { return m_ctx; }
 
 	private:

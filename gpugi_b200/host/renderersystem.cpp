@@ -53,6 +53,12 @@ void RendererSystem::SetIterationShard(unsigned int _rank, unsigned int _worldSi
 	PerIterationBufferUpdate(false);
 }
 
+void RendererSystem::SetStreaming(bool _streaming)
+{
+	Check(gi_set_option(m_device, GI_OPT_STREAMING, _streaming ? 1 : 0), "gi_set_option(GI_OPT_STREAMING)");
+	if (_streaming) m_synchronousDraw = false;
+}
+
 void RendererSystem::ResetIterationCount()
 {
 	m_iterationCount = 0;

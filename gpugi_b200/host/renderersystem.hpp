@@ -87,6 +87,10 @@ public:
 	/// If false, Draw() does not synchronise the device (the reference's glFinish, :249,:253);
 	/// GetRenderTime() then only counts host time.
 	void SetSynchronousDraw(bool _sync) { m_synchronousDraw = _sync; }
+	/// Streaming Draw() (GI_OPT_STREAMING): consecutive Draw() calls of the path tracer overlap wave by wave on the device
+	/// instead of running each iteration to its last bounce; the accumulator is exact again after any synchronous read.
+	/// Implies SetSynchronousDraw(false) while on.
+	void SetStreaming(bool _streaming);
 	unsigned int GetWorldSize() const { return m_worldSize; }
 	GiContext* GetDevice() const { return m_device; }
 	const Camera& GetCamera() const { return m_camera; }

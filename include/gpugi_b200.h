@@ -171,10 +171,18 @@ enum {
 	GI_OPT_COUNT_STEPS = 7,         /* 1 = the wavefront walk counts its box / triangle tests (GiCounters::node_tests,
 	                                   triangle_tests); off by default: two counters less in the hot loop.  The megakernel and
 	                                   GI_TRAVERSAL_REFERENCE always count. */
-	GI_OPT_KERNEL_TIMING = 8        /* 1 = bracket every kernel launch of gi_render_iteration with CUDA events on the launching
+	GI_OPT_KERNEL_TIMING = 8,       /* 1 = bracket every kernel launch of gi_render_iteration with CUDA events on the launching
 	                                   stream and sum the durations per kernel class (gi_get_kernel_times); setting the option
 	                                   clears the sums.  The iteration call then synchronises -- measurement passes only.
 	                                   Replaces the reference's glFinish + clock() pair (renderersystem.cpp:249-255). */
+	GI_OPT_STREAMING = 9            /* 1 = consecutive gi_render_iteration(GI_RENDERER_PT) calls form a STREAM: each call submits one
+	                                   wave (generate + trace + shade) of a run that stays open, so the bounces of up to
+	                                   max_path_length + 1 iterations share every wave exactly as in gi_render_iterations -- the
+	                                   reference's one-Draw()-per-iteration loop (renderersystem.cpp:246-256) without its
+	                                   per-iteration tail.  Any call that reads or redefines state (gi_read_accumulator,
+	                                   gi_synchronize, gi_set_camera, gi_clear_accumulator, gi_get_counters, ...) drains the
+	                                   stream first, after which the accumulator equals the one of the same iterations rendered
+	                                   one by one, bit for bit.  gi_read_accumulator_async does NOT drain. */
 };
 /* kernel classes of gi_get_kernel_times */
 enum {
@@ -325,6 +333,17 @@ GI_API int gi_synchronize(GiContext* ctx);
  * copies the width*height*4 float SUM accumulator to host (synchronous).  Division by
  * the iteration count stays with the caller (hdrimage.cpp:21, displayHDR.frag:12). */
 GI_API int gi_read_accumulator(GiContext* ctx, float* rgba);
+
+/* Progressive display read-out (the reference shows the backbuffer every frame, application.cpp:336-343, without ever
+ * stalling the renderer): snapshots the accumulator in stream order and copies it to `rgba` on a second stream; returns at
+ * once.  `rgba` (pinned memory for a truly asynchronous copy) is valid after the next gi_wait_reads / gi_read_accumulator_async
+ * -but-one; at most two reads are in flight.  With GI_OPT_STREAMING the snapshot holds every submitted iteration except the
+ * last *iterations_in_flight ones (<= max_path_length + 1), whose paths are still bouncing; it never holds a partial
+ * iteration.  Does not drain the stream. */
+GI_API int gi_read_accumulator_async(GiContext* ctx, float* rgba, uint32_t* iterations_in_flight);
+
+/* Blocks until every gi_read_accumulator_async copy has landed. */
+GI_API int gi_wait_reads(GiContext* ctx);
 
 /* Device address of the accumulator (for the NCCL sum-reduce across ranks). */
 GI_API int gi_accumulator_device(GiContext* ctx, void** device_ptr, size_t* num_bytes);

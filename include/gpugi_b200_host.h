@@ -71,6 +71,9 @@ GI_API uint64_t gih_rs_render_time_ms(GihRendererSystem* rs);
 GI_API uint32_t gih_rs_frame_seed(GihRendererSystem* rs);
 GI_API uint64_t gih_rs_global_iteration(GihRendererSystem* rs);
 GI_API int gih_rs_read_backbuffer(GihRendererSystem* rs, float* rgba);
+GI_API void gih_rs_set_streaming(GihRendererSystem* rs, int streaming);       /* RendererSystem::SetStreaming (GI_OPT_STREAMING) */
+GI_API int gih_rs_read_backbuffer_async(GihRendererSystem* rs, float* rgba, uint32_t* iterations_in_flight); /* Texture2D::ReadImageAsync */
+GI_API int gih_rs_wait_reads(GihRendererSystem* rs);
 GI_API uint32_t gih_rs_num_light_samples(GihRendererSystem* rs);
 GI_API void gih_rs_light_samples(GihRendererSystem* rs, GiLightSample* out);
 GI_API void gih_rs_camera(GihRendererSystem* rs, GiCamera* out);

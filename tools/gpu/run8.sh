@@ -1,0 +1,3 @@
+#!/bin/bash
+mkdir -p gpurun_out
+(time python -m pytest tests -m gpu -x -q) 2>&1 | tail -25
