@@ -35,6 +35,17 @@ struct WfCounters
 // than WF_MAX_CAND candidates, a stack overflow or a scene whose leaves are not numbered in preorder fall back to the
 // stackless reference walk itself.
 #define WF_NODE_DONE int(0x80000000)
+// build-time switches of the trace loop, A/B measured on B200 (tools/gpu/variants.sh + run_variants.sh, PT batch, ms/iteration):
+// all off 2.221 | raw prmt 2.206 | lazy leaf box 2.332 | top of stack in registers 2.265 -> only the first one is on
+#ifndef WF_RAW_PRMT
+#define WF_RAW_PRMT 1      // prmt.b32 without __byte_perm's selector mask
+#endif
+#ifndef WF_LAZY_LEAF_BOX
+#define WF_LAZY_LEAF_BOX 0 // leaf: triangle tests first, the leaf's own exact box test only when a triangle is hit
+#endif
+#ifndef WF_TOP_IN_REGS
+#define WF_TOP_IN_REGS 0   // most recent stack entry in registers
+#endif
 #define WF_MAX_CAND 8
 
 enum { WFL_ANY = 1u, WFL_OVERFLOW = 2u, WFL_OCCLUDED = 4u, WFL_EXACT = 8u, WFL_COLLECT = 16u, WFL_GUARD = 32u };
@@ -54,6 +65,11 @@ struct WfLane
 	float limit;     // culling limit for box entry distances
 	int hitLeaf;
 	int node;        // >= 0 inner (fast index), < 0 leaf (~leaf), WF_NODE_DONE = finished
+	// traversal stack: the most recent entry lives in registers (topNode, topFirst), the older ones in stack[0 .. sp).  A pop
+	// hands out the register entry at once and refills it with a load whose result is only needed at the NEXT pop or push,
+	// so the walk does not wait on local memory unless the popped entry is culled.  Bottom = sentinel (WF_NODE_DONE, 0).
+	int topNode;
+	float topFirst;
 	int sp;
 	uint32_t index;  // work item index
 	uint32_t flags;  // WFL_*
@@ -66,8 +82,36 @@ GI_HD float wfClosestLimit(float best, const DScene& s)
 	return best * margin + s.ambiguityAbs;
 }
 
+GI_HD void wfStackReset(WfLane& L) { L.sp = 0; L.topNode = WF_NODE_DONE; L.topFirst = 0.0f; }
+
+GI_HD void wfPush(WfLane& L, StackEntry* stack, int node, float first)
+{
+	if (L.sp < GI_STACK_SIZE)
+	{
+#if WF_TOP_IN_REGS
+		stack[L.sp].node = L.topNode; stack[L.sp].first = L.topFirst; ++L.sp;
+		L.topNode = node; L.topFirst = first;
+#else
+		stack[L.sp].node = node; stack[L.sp].first = first; ++L.sp;
+#endif
+	}
+	else L.flags |= WFL_OVERFLOW; // the subtree is skipped; the ray is answered by the stackless reference walk
+}
+
 GI_HD void wfPop(WfLane& L, const StackEntry* stack)
 {
+#if WF_TOP_IN_REGS
+	for (;;)
+	{
+		const int n = L.topNode;
+		const float f = L.topFirst;
+		if (n == WF_NODE_DONE) { L.node = WF_NODE_DONE; return; } // the sentinel stays
+		--L.sp; // >= 0: the sentinel was stored below the first pushed entry
+		const StackEntry e = stack[L.sp];
+		L.topNode = e.node; L.topFirst = e.first;
+		if (f <= L.limit) { L.node = n; return; }
+	}
+#else
 	for (;;)
 	{
 		if (L.sp == 0) { L.node = WF_NODE_DONE; return; }
@@ -75,6 +119,7 @@ GI_HD void wfPop(WfLane& L, const StackEntry* stack)
 		const StackEntry e = stack[L.sp];
 		if (e.first <= L.limit) { L.node = e.node; return; }
 	}
+#endif
 }
 
 // ---- conservative slab test on the quantised child boxes
@@ -110,7 +155,15 @@ GI_HD float wfFma(float a, float b, float c)
 GI_HD float wfPlane(uint32_t word, uint32_t sel)
 {
 #if defined(__CUDA_ARCH__)
+	// prmt.b32 directly: __byte_perm() masks the selector with 0x7777 first (one LOP3 per plane in the hot loop); the two
+	// selectors used here (WF_SEL_LO / WF_SEL_HI) have no mode bits set, so the raw instruction is the same function
+#if WF_RAW_PRMT
+	uint32_t r;
+	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(word), "r"(0x4B000000u), "r"(sel));
+	return __uint_as_float(r);
+#else
 	return __uint_as_float(__byte_perm(word, 0x4B000000u, sel));
+#endif
 #else
 	const uint32_t q = (sel == WF_SEL_LO) ? (word & 0xffffu) : (word >> 16);
 	return i2f(int(0x4B000000u | q));
@@ -164,7 +217,7 @@ GI_HD void wfBegin(WfLane& L, const DScene& s, F3 o, F3 d, float tMax, bool isAn
 	L.o = o; L.d = d;
 	L.tMaxInit = tMax; L.best = tMax; L.second = GI_INF;
 	L.limit = isAny ? tMax : wfClosestLimit(tMax, s);
-	L.hitLeaf = -1; L.sp = 0; L.index = index;
+	L.hitLeaf = -1; wfStackReset(L); L.index = index;
 	L.flags = isAny ? WFL_ANY : 0u; L.numCand = 0;
 	const bool inDomain = wfSlabSetup(L, s, o, inv);
 	// root box first, as the reference does (traceray.glsl:56-69)
@@ -203,8 +256,7 @@ GI_HD void wfInnerStep(WfLane& L, const DScene& s, StackEntry* stack, CNT& cnt)
 	if (h0 && h1)
 	{
 		if (f1 < f0) { int t = c0; c0 = c1; c1 = t; float tf = f0; f0 = f1; f1 = tf; }
-		if (L.sp < GI_STACK_SIZE) { stack[L.sp].node = c1; stack[L.sp].first = f1; ++L.sp; }
-		else L.flags |= WFL_OVERFLOW;
+		wfPush(L, stack, c1, f1);
 		L.node = c0;
 	}
 	else if (h0) L.node = c0;
@@ -219,10 +271,18 @@ GI_HD void wfLeafStep(WfLane& L, const DScene& s, const StackEntry* stack, WfCan
 	// One 96-byte record: both triangles + the leaf node's own box in the .w components; all six loads are issued first.
 	F4 v[6];
 	ld8x3(s.leafPos + 6 * size_t(leaf), v);
-	// the reference's cull test for this leaf: its own node box, exact zone (traceray.glsl:64-69)
-	float leafFirst, leafLast;
+	// The reference visits this leaf iff its own node box passes the exact-zone test with first <= rayLength
+	// (traceray.glsl:64-69); a triangle of an unvisited leaf does not count.  Most leaf visits hit no triangle at all, so the
+	// box test (three IEEE divisions + slab test) is made lazily: at the first triangle hit, with the limit the lane had when it
+	// reached the leaf (L.limit only changes after the gate).
+	float leafFirst = 0.0f, leafLast;
+#if WF_LAZY_LEAF_BOX
+	bool gateKnown = false;
+#else
+	const bool gateKnown = true;
 	cnt.template add<WFC_NODES>(1u);
 	if (!(intersectBox(L.o, invDir(L.d), v[0].w, v[1].w, v[2].w, v[3].w, v[4].w, v[5].w, leafFirst, leafLast) && leafFirst <= L.limit)) { wfPop(L, stack); return; }
+#endif
 #pragma unroll
 	for (int slot = 0; slot < 2; ++slot)
 	{
@@ -233,6 +293,14 @@ GI_HD void wfLeafStep(WfLane& L, const DScene& s, const StackEntry* stack, WfCan
 		float t; F3 nb, nn;
 		if (intersectTriangle(L.o, L.d, f3(q0.x, q0.y, q0.z), f3(q1.x, q1.y, q1.z), f3(q2.x, q2.y, q2.z), t, nb, nn) && t < L.tMaxInit)
 		{
+#if WF_LAZY_LEAF_BOX
+			if (!gateKnown)
+			{
+				gateKnown = true;
+				cnt.template add<WFC_NODES>(1u);
+				if (!(intersectBox(L.o, invDir(L.d), v[0].w, v[1].w, v[2].w, v[3].w, v[4].w, v[5].w, leafFirst, leafLast) && leafFirst <= L.limit)) break;
+			}
+#endif
 			if (L.flags & WFL_ANY) { L.flags |= WFL_OCCLUDED; L.node = WF_NODE_DONE; return; }
 			if (L.flags & WFL_COLLECT)
 			{
@@ -299,7 +367,7 @@ GI_HD bool wfEndOfWalk(WfLane& L, const DScene& s, WfCand* cand, CNT& cnt)
 				{
 					// pass 2: same lane, culling limit fixed at the window of pass 1's result
 					L.flags |= WFL_COLLECT;
-					L.numCand = 0; L.sp = 0;
+					L.numCand = 0; wfStackReset(L);
 					L.limit = wfClosestLimit(L.best, s);
 					L.node = s.rootIsLeaf ? ~0 : 0;
 					done = false;
