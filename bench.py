@@ -38,6 +38,28 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# stdout carries exactly ONE line (the JSON result).  Libraries write there too (NCCL prints its version banner on
+# stdout when NCCL_DEBUG is set on the box), so fd 1 is pointed at stderr for the whole run and the result line goes
+# to the saved descriptor.
+_RESULT_FD = None
+
+
+def capture_stdout():
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 # ----------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
@@ -176,7 +198,7 @@ def run_reference(args, rank, world):
             "config": {"workload": "sponza-shaped atrium PathTracer 1920x1080 (BASELINE config 2), pathLength 16, 262144 triangles", "sample": sample},
             "cpu_baseline": {"value": value, "unit": "Mpaths/s", "cores": orc.num_threads(), "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------- our arm
@@ -380,7 +402,7 @@ def run_ours(args, rank, world, local_rank):
     if world == 1 and not args.no_cpu_baseline:
         base, _ = cpu_baseline(scene)
         line["cpu_baseline"] = base
-    print(json.dumps(line), flush=True)
+    emit(line)
     rs.close()
 
 
@@ -397,6 +419,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     args.warmup = max(args.warmup, 3)
+    capture_stdout()
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
@@ -404,7 +427,7 @@ def main():
         # launched without torchrun: re-exec under torchrun, one rank per GPU
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus), "--master-addr", "127.0.0.1",
                "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:]
-        raise SystemExit(subprocess.call(cmd))
+        raise SystemExit(subprocess.call(cmd, stdout=_RESULT_FD))  # the ranks' stdout is the real one again
     run_ours(args, rank, world, local_rank)
 
 

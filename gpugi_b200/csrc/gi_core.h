@@ -732,6 +732,9 @@ struct DFrame
 	uint32_t lightCacheCapacity;
 	uint32_t* lightCacheCount;         // NumLightCacheEntries
 	uint32_t* lightPathLengthSum;      // LightPathLengthSum
+	// pipelined BPT batches (gi_wavefront.cuh): iteration i uses cache (i % cacheRing) of a ring of caches `lightCacheCapacity`
+	// entries apart, and the counter pair 2 * (i % cacheRing) behind lightCacheCount.  cacheRing <= 1: the single cache above.
+	uint32_t cacheRing;
 };
 
 struct PathCounters
@@ -961,7 +964,8 @@ GI_HD void saveLightCache(const DFrame& f, uint32_t idx, F3 flux, int materialIn
 GI_HD uint32_t allocLightCacheSlot(const DFrame& f, bool warmup)
 {
 #if defined(__CUDA_ARCH__)
-	const unsigned mask = __activemask();
+	// lanes of one warp may belong to different iterations of a pipelined batch (different caches): aggregate per counter
+	const unsigned mask = __match_any_sync(__activemask(), reinterpret_cast<unsigned long long>(f.lightCacheCount));
 	const int leader = __ffs(mask) - 1;
 	const int lane = threadIdx.x & 31;
 	const unsigned count = __popc(mask);

@@ -125,11 +125,16 @@ __global__ void k_reset_counter(uint32_t* lightCacheCount, uint32_t* lightPathLe
 }
 
 // ---- wavefront scheduler (gi_wavefront.cuh) -------------------------------------------------------------
+#ifndef WF_TRACE_THREADS
 #define WF_TRACE_THREADS 128
+#endif
 #ifndef WF_TRACE_MIN_BLOCKS
 #define WF_TRACE_MIN_BLOCKS 8
 #endif
 #define WF_SHADE_THREADS 128
+#ifndef WF_SHADE_MIN_BLOCKS
+#define WF_SHADE_MIN_BLOCKS 8   // k_wf_shade_pt: 64 registers, 8 blocks per SM (B200 A/B, PT batch: 1 -> 2.246, 8 -> 2.195, 10 -> 2.208, 12 -> 2.241 ms/iteration)
+#endif
 
 // Camera rays of all W/8 x H/8 work groups (pathtracer.comp:36-46) at the head of this wave's extension queue.
 __global__ void __launch_bounds__(256) k_wf_generate(WfFrame w, unsigned long long* counters)
@@ -188,7 +193,7 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MIN_BLOCKS) k_wf_tr
 }
 
 // shade(w) of the path tracer: one lane per hit record, 32 consecutive queue slots per warp and fetch.
-__global__ void __launch_bounds__(WF_SHADE_THREADS) k_wf_shade_pt(WfFrame w, unsigned long long* counters)
+__global__ void __launch_bounds__(WF_SHADE_THREADS, WF_SHADE_MIN_BLOCKS) k_wf_shade_pt(WfFrame w, unsigned long long* counters)
 {
 	uint32_t* counts = wfCounts(w, w.wave);
 	const uint32_t n = w.numCam + counts[0];
@@ -239,7 +244,6 @@ __global__ void __launch_bounds__(WF_SHADE_THREADS) k_wf_shade_eye(WfFrame w, un
 {
 	uint32_t* counts = wfCounts(w, w.wave);
 	const uint32_t n = w.numCam + counts[0];
-	const uint32_t numEntries = *w.f.lightCacheCount; // complete: the light pass of this iteration ran before the eye waves
 	PathCounters pc = {};
 	for (;;)
 	{
@@ -248,7 +252,7 @@ __global__ void __launch_bounds__(WF_SHADE_THREADS) k_wf_shade_eye(WfFrame w, un
 		base = __shfl_sync(0xffffffffu, base, 0);
 		if (base >= n) break;
 		const uint32_t slot = base + laneId();
-		wfShadeEye(w, w.rayBase + slot, slot < n, numEntries, pc);
+		wfShadeEye(w, w.rayBase + slot, slot < n, pc);
 	}
 	unsigned cnt[WFC_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 	wfAddCounters(cnt, pc);
@@ -348,6 +352,11 @@ struct GiContext
 	F4* lightCache = nullptr;
 	uint32_t lightCacheCapacity = 0;
 	uint32_t* bptCounters = nullptr; // [0] NumLightCacheEntries, [1] LightPathLengthSum
+	// pipelined BPT batches: a ring of caches + counter pairs, one per iteration in flight (up to 2 x maxPathLength)
+	F4* cacheRing = nullptr;
+	uint64_t cacheRingEntries = 0;   // allocated entries in total
+	uint32_t* ringCounters = nullptr;
+	uint32_t ringCountersLen = 0;
 
 	// counters
 	unsigned long long* counters = nullptr;
@@ -361,7 +370,7 @@ struct GiContext
 	WfTune tune = {16, 20, 0};
 
 	// wavefront queues
-	WfRun run;
+	WfRun run[2];                    // [0]: PT / LPT / BPT light pass / stream, [1]: BPT eye pass of a pipelined batch
 	int streamingOption = 0;         // GI_OPT_STREAMING
 	uint32_t lightSlot = 0;          // ring slot of the light-sample set the next iteration uses
 	// asynchronous read-out (gi_read_accumulator_async)
@@ -371,9 +380,9 @@ struct GiContext
 	cudaEvent_t snapTaken[2] = {nullptr, nullptr}, snapCopied[2] = {nullptr, nullptr};
 	bool snapUsed[2] = {false, false};
 	int snapNext = 0;
-	WfQueues wf = {};
-	uint32_t wfCountsLen = 0;
-	uint64_t wfStates = 0;           // allocated path state records (numSlots x numIds)
+	WfQueues wf[2] = {};
+	uint32_t wfCountsLen[2] = {0, 0};
+	uint64_t wfStates[2] = {0, 0};   // allocated path state records (numSlots x numIds)
 	uint32_t* traceWork = nullptr;   // work counter of k_wf_trace_batch
 	int numSMs = 148;
 	int traceBlocksPerSM = 1, shadeBlocksPerSM = 1, shadeLightBlocksPerSM = 1, shadeEyeBlocksPerSM = 1;
@@ -482,47 +491,51 @@ static DFrame makeFrame(GiContext* c, const GiIterationParams* p)
 // ---- wavefront queue storage: 2 ray queues, hit records, shadow queue, path state, per-bounce counters
 static void freeWavefront(GiContext* c)
 {
-	cudaFree(c->wf.rays[0]); cudaFree(c->wf.rays[1]); cudaFree(c->wf.hits); cudaFree(c->wf.shadow); cudaFree(c->wf.stateT); cudaFree(c->wf.stateC); cudaFree(c->wf.stateM);
-	cudaFree(c->wf.counts);
-	c->wf = WfQueues{};
-	c->wfCountsLen = 0;
-	c->wfStates = 0;
+	for (int set = 0; set < 2; ++set)
+	{
+		WfQueues& q = c->wf[set];
+		cudaFree(q.rays[0]); cudaFree(q.rays[1]); cudaFree(q.hits); cudaFree(q.shadow); cudaFree(q.stateT); cudaFree(q.stateC); cudaFree(q.stateM);
+		cudaFree(q.counts);
+		q = WfQueues{};
+		c->wfCountsLen[set] = 0;
+		c->wfStates[set] = 0;
+	}
 }
 
 // capacity: queue slots; numIds: path ids per iteration (PT/BPT: the pixel index, which is not dense when the frame size is
 // not a multiple of 8); numSlots: iterations in flight; countsLen: wave counters
-static int ensureWavefront(GiContext* c, uint64_t capacity, uint32_t numIds, uint32_t numSlots, uint32_t countsLen)
+static int ensureWavefront(GiContext* c, int set, uint64_t capacity, uint32_t numIds, uint32_t numSlots, uint32_t countsLen)
 {
 	if (capacity > WF_ID_MASK || uint64_t(numIds) * numSlots > WF_ID_MASK)
 		return fail(c, GI_ERR_CAPACITY, "wavefront scheduler: more than 2^30 queue slots / path states");
 	const uint64_t states = uint64_t(numIds) * numSlots;
-	if (c->wf.capacity < capacity || c->wfStates < states)
+	if (c->wf[set].capacity < capacity || c->wfStates[set] < states)
 	{
 		GI_CUDA(c, cudaStreamSynchronize(c->stream));
-		const uint64_t cap = std::max<uint64_t>(capacity, c->wf.capacity);
-		const uint64_t st = std::max<uint64_t>(states, c->wfStates);
-		cudaFree(c->wf.rays[0]); cudaFree(c->wf.rays[1]); cudaFree(c->wf.hits); cudaFree(c->wf.shadow); cudaFree(c->wf.stateT); cudaFree(c->wf.stateC); cudaFree(c->wf.stateM);
-		c->wf.rays[0] = c->wf.rays[1] = nullptr; c->wf.hits = nullptr; c->wf.shadow = nullptr; c->wf.stateT = c->wf.stateC = nullptr; c->wf.stateM = nullptr;
-		c->wf.capacity = 0; c->wfStates = 0;
-		GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->wf.rays[0]), size_t(cap) * 32));
-		GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->wf.rays[1]), size_t(cap) * 32));
-		GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->wf.hits), size_t(cap) * 8));
-		GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->wf.shadow), size_t(cap) * 48));
-		GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->wf.stateT), size_t(st) * 16));
-		GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->wf.stateC), size_t(st) * 16));
-		GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->wf.stateM), size_t(st) * 4));
-		c->wf.capacity = uint32_t(cap);
-		c->wfStates = st;
+		const uint64_t cap = std::max<uint64_t>(capacity, c->wf[set].capacity);
+		const uint64_t st = std::max<uint64_t>(states, c->wfStates[set]);
+		cudaFree(c->wf[set].rays[0]); cudaFree(c->wf[set].rays[1]); cudaFree(c->wf[set].hits); cudaFree(c->wf[set].shadow); cudaFree(c->wf[set].stateT); cudaFree(c->wf[set].stateC); cudaFree(c->wf[set].stateM);
+		c->wf[set].rays[0] = c->wf[set].rays[1] = nullptr; c->wf[set].hits = nullptr; c->wf[set].shadow = nullptr; c->wf[set].stateT = c->wf[set].stateC = nullptr; c->wf[set].stateM = nullptr;
+		c->wf[set].capacity = 0; c->wfStates[set] = 0;
+		GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->wf[set].rays[0]), size_t(cap) * 32));
+		GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->wf[set].rays[1]), size_t(cap) * 32));
+		GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->wf[set].hits), size_t(cap) * 8));
+		GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->wf[set].shadow), size_t(cap) * 48));
+		GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->wf[set].stateT), size_t(st) * 16));
+		GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->wf[set].stateC), size_t(st) * 16));
+		GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->wf[set].stateM), size_t(st) * 4));
+		c->wf[set].capacity = uint32_t(cap);
+		c->wfStates[set] = st;
 	}
-	if (c->wfCountsLen < countsLen)
+	if (c->wfCountsLen[set] < countsLen)
 	{
 		GI_CUDA(c, cudaStreamSynchronize(c->stream));
-		cudaFree(c->wf.counts); c->wf.counts = nullptr; c->wfCountsLen = 0;
-		GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->wf.counts), size_t(countsLen) * sizeof(uint32_t)));
-		c->wfCountsLen = countsLen;
+		cudaFree(c->wf[set].counts); c->wf[set].counts = nullptr; c->wfCountsLen[set] = 0;
+		GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->wf[set].counts), size_t(countsLen) * sizeof(uint32_t)));
+		c->wfCountsLen[set] = countsLen;
 	}
-	c->wf.numIds = numIds;
-	c->wf.numSlots = numSlots;
+	c->wf[set].numIds = numIds;
+	c->wf[set].numSlots = numSlots;
 	return GI_OK;
 }
 
@@ -534,10 +547,10 @@ static int ensureWavefront(GiContext* c, uint64_t capacity, uint32_t numIds, uin
 // A run is opened (wfOpen), fed one iteration per wave (wfStep) and closed (wfClose: drain + fold).  A batch
 // (gi_render_iterations) does all three in one call; a stream (GI_OPT_STREAMING) keeps the run open across
 // gi_render_iteration calls, so that consecutive Draw() calls overlap exactly like the iterations of a batch.
-static int wfOpen(GiContext* c, const DFrame& f, int pass, uint32_t lightFlags, uint32_t expectedCount, bool streaming, uint32_t lightStride, uint32_t lightBase,
+static int wfOpen(GiContext* c, int set, const DFrame& f, int pass, uint32_t lightFlags, uint32_t expectedCount, bool streaming, uint32_t lightStride, uint32_t lightBase,
                   uint32_t lightRing)
 {
-	WfRun& r = c->run;
+	WfRun& r = c->run[set];
 	WfFrame& w = r.w;
 	std::memset(&w, 0, sizeof(w));
 	w.f = f;
@@ -565,15 +578,15 @@ static int wfOpen(GiContext* c, const DFrame& f, int pass, uint32_t lightFlags, 
 	const uint32_t countsRing = streaming ? WF_STREAM_COUNTS_RING : expectedCount + r.maxLen + 1u;
 	// worst case (no path ever ends before maxPathLength): maxLen generations of rays share a wave.  Any batch / stream
 	// reserves that much, so that runs of different length never reallocate.
-	int st = ensureWavefront(c, uint64_t(w.numPaths) * (many ? r.maxLen : 1u), numIds, many ? r.maxLen + 1u : 1u, WF_COUNTS_PER_WAVE * countsRing);
+	int st = ensureWavefront(c, set, uint64_t(w.numPaths) * (many ? r.maxLen : 1u), numIds, many ? r.maxLen + 1u : 1u, WF_COUNTS_PER_WAVE * countsRing);
 	if (st != GI_OK) return st;
-	w.q = c->wf;
+	w.q = c->wf[set];
 	w.q.numSlots = r.numSlots;
 	w.q.countsRing = countsRing;
 	w.tune = c->tune;
-	GI_CUDA(c, cudaMemsetAsync(c->wf.counts, 0, size_t(WF_COUNTS_PER_WAVE) * countsRing * sizeof(uint32_t), c->stream));
+	GI_CUDA(c, cudaMemsetAsync(c->wf[set].counts, 0, size_t(WF_COUNTS_PER_WAVE) * countsRing * sizeof(uint32_t), c->stream));
 	// ids outside the W/8 x H/8 tiles are never written by shade(); the fold reads them
-	if (pass != WF_PASS_LIGHT && w.numPaths != w.q.numIds) GI_CUDA(c, cudaMemsetAsync(c->wf.stateC, 0, size_t(r.numSlots) * w.q.numIds * 16, c->stream));
+	if (pass != WF_PASS_LIGHT && w.numPaths != w.q.numIds) GI_CUDA(c, cudaMemsetAsync(c->wf[set].stateC, 0, size_t(r.numSlots) * w.q.numIds * 16, c->stream));
 	r.open = true;
 	timingMark(c, -1);
 	return GI_OK;
@@ -581,9 +594,9 @@ static int wfOpen(GiContext* c, const DFrame& f, int pass, uint32_t lightFlags, 
 
 // One wave.  generate: iteration r.count starts in this wave (FrameSeed `seed`); nextGenerates: the next wave will start an
 // iteration too (a stream cannot know and always reserves the head of the next queue); shade: false for the very last wave.
-static int wfStep(GiContext* c, bool generate, uint32_t seed, bool nextGenerates, bool shade)
+static int wfStep(GiContext* c, int set, bool generate, uint32_t seed, bool nextGenerates, bool shade)
 {
-	WfRun& r = c->run;
+	WfRun& r = c->run[set];
 	WfFrame& w = r.w;
 	if (!r.open) return GI_OK;
 	const int pass = r.pass;
@@ -595,7 +608,7 @@ static int wfStep(GiContext* c, bool generate, uint32_t seed, bool nextGenerates
 	const unsigned shadeGrid = unsigned(c->numSMs * (pass == WF_PASS_PT ? c->shadeBlocksPerSM : pass == WF_PASS_LIGHT ? c->shadeLightBlocksPerSM : c->shadeEyeBlocksPerSM));
 	const bool ref = w.f.traversalMode == GI_TRAVERSAL_REFERENCE;
 	if (r.streaming)
-		GI_CUDA(c, cudaMemsetAsync(c->wf.counts + WF_COUNTS_PER_WAVE * size_t((r.wave + 1u) % w.q.countsRing), 0, WF_COUNTS_PER_WAVE * sizeof(uint32_t), c->stream));
+		GI_CUDA(c, cudaMemsetAsync(c->wf[set].counts + WF_COUNTS_PER_WAVE * size_t((r.wave + 1u) % w.q.countsRing), 0, WF_COUNTS_PER_WAVE * sizeof(uint32_t), c->stream));
 	if (generate)
 	{
 		w.f.frameSeed = seed;
@@ -623,21 +636,21 @@ static int wfStep(GiContext* c, bool generate, uint32_t seed, bool nextGenerates
 }
 
 // Drain: maxPathLength waves without generate (the last one carries shadow rays only), then the fold.
-static int wfClose(GiContext* c)
+static int wfClose(GiContext* c, int set, bool drain = true)
 {
-	WfRun& r = c->run;
+	WfRun& r = c->run[set];
 	if (!r.open) return GI_OK;
 	if (r.count > 0)
 	{
-		for (uint32_t k = 0; k < r.maxLen; ++k)
+		for (uint32_t k = 0; drain && k < r.maxLen; ++k)
 		{
-			int st = wfStep(c, false, 0u, false, k + 1u < r.maxLen);
+			int st = wfStep(c, set, false, 0u, false, k + 1u < r.maxLen);
 			if (st != GI_OK) return st;
 		}
 		if (r.pass != WF_PASS_LIGHT)
 		{
 			const uint32_t first = r.count > r.numSlots ? r.count - r.numSlots : 0u;
-			k_wf_fold<<<unsigned(c->numSMs) * 8u, 256, 0, c->stream>>>(reinterpret_cast<float4*>(c->accum), c->wf.stateC, r.w.q.numIds, r.numSlots, first, r.count);
+			k_wf_fold<<<unsigned(c->numSMs) * 8u, 256, 0, c->stream>>>(reinterpret_cast<float4*>(c->accum), c->wf[set].stateC, r.w.q.numIds, r.numSlots, first, r.count);
 			++c->launches;
 			timingMark(c, GI_KERNEL_OTHER);
 		}
@@ -653,7 +666,7 @@ static int wfClose(GiContext* c)
 // an open stream must be drained before anything reads or redefines what its iterations depend on
 static int flushStream(GiContext* c)
 {
-	if (c && c->run.open && c->run.streaming) return wfClose(c);
+	if (c && c->run[0].open && c->run[0].streaming) return wfClose(c, 0);
 	return GI_OK;
 }
 
@@ -661,11 +674,86 @@ static int renderWavefront(GiContext* c, const DFrame& f, int pass, uint32_t lig
 {
 	if (count == 0) return GI_OK;
 	if (pass == WF_PASS_EYE && count != 1u) return fail(c, GI_ERR_INVALID, "wavefront BPT eye pass: one iteration at a time");
-	int st = wfOpen(c, f, pass, lightFlags, count, false, lightStride, 0u, 0u);
-	for (uint32_t k = 0; st == GI_OK && k < count; ++k) st = wfStep(c, true, seeds[k], k + 1u < count, true);
-	if (st == GI_OK) st = wfClose(c);
-	c->run.open = false;
+	int st = wfOpen(c, 0, f, pass, lightFlags, count, false, lightStride, 0u, 0u);
+	for (uint32_t k = 0; st == GI_OK && k < count; ++k) st = wfStep(c, 0, true, seeds[k], k + 1u < count, true);
+	if (st == GI_OK) st = wfClose(c, 0);
+	c->run[0].open = false;
 	return st;
+}
+
+
+// A batch of BPT iterations as ONE pipeline of waves.  Global wave w carries
+//   light run (queue set 0):  generate(light paths of iteration w), light bounce b of iteration w - b
+//   eye run   (queue set 1):  generate(camera rays of iteration w - D), eye bounce b of iteration w - D - b,   D = maxPathLength
+// The eye pass of iteration k may only start when its light cache is complete (last light shade: wave k + maxPathLength - 1),
+// hence the offset D; cache k is written in waves k .. k+D-1 and read in waves k+D .. k+2D-1, so 2 D caches (each with its own
+// NumLightCacheEntries counter) are alive at a time: a ring in HBM (C3 at 1080p: 32 x 0.4 GB).  Every wave then has the
+// same amount of work and the per-iteration tails of both passes are paid once per batch.  Returns GI_ERR_CAPACITY without
+// having rendered anything when the ring does not fit the free device memory (the caller then renders one by one).
+static int renderPipelinedBPT(GiContext* c, const GiIterationParams* p, const uint32_t* seeds, uint32_t count, uint32_t lightStride)
+{
+	const uint32_t maxLen = uint32_t(p->max_path_length);
+	const uint32_t D = maxLen;
+	const uint32_t ring = std::min(count, 2u * maxLen);
+	const uint32_t capacity = uint32_t(p->light_cache_capacity);
+	const uint32_t numLightPaths = uint32_t(c->numLightSamples) * uint32_t(p->num_rays_per_light_sample);
+	const uint64_t entries = uint64_t(ring) * capacity;
+	if (c->cacheRingEntries < entries)
+	{
+		GI_CUDA(c, cudaStreamSynchronize(c->stream));
+		cudaFree(c->cacheRing); c->cacheRing = nullptr; c->cacheRingEntries = 0;
+		size_t freeB = 0, totalB = 0;
+		GI_CUDA(c, cudaMemGetInfo(&freeB, &totalB));
+		// the two queue sets of the runs are allocated after this: leave room for them (and 2 GB of slack)
+		const uint64_t numPix = uint64_t(c->width) * c->height;
+		const uint64_t queues = (uint64_t(numLightPaths) + numPix) * (uint64_t(maxLen) * 120u + uint64_t(maxLen + 1u) * 36u);
+		if (entries * 64u + queues + (2ull << 30) > freeB) return fail(c, GI_ERR_CAPACITY, "pipelined BPT: the light-cache ring does not fit the device memory");
+		GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->cacheRing), size_t(entries) * 64u));
+		c->cacheRingEntries = entries;
+	}
+	if (c->ringCountersLen < 2u * ring)
+	{
+		GI_CUDA(c, cudaStreamSynchronize(c->stream));
+		cudaFree(c->ringCounters); c->ringCounters = nullptr; c->ringCountersLen = 0;
+		GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->ringCounters), size_t(2u * ring) * sizeof(uint32_t)));
+		c->ringCountersLen = 2u * ring;
+	}
+	DFrame f = makeFrame(c, p);
+	f.lightCache = c->cacheRing;
+	f.lightCacheCapacity = capacity;
+	f.lightCacheCount = c->ringCounters;
+	f.lightPathLengthSum = c->ringCounters + 1;
+	f.cacheRing = ring;
+	int st = wfOpen(c, 0, f, WF_PASS_LIGHT, WF_LIGHT_SAVE, count, false, lightStride, 0u, 0u);
+	if (st == GI_OK) st = wfOpen(c, 1, f, WF_PASS_EYE, 0u, count, false, 0u, 0u, 0u);
+	if (st != GI_OK) { c->run[0].open = c->run[1].open = false; return st; }
+	const uint32_t runWaves = count + maxLen; // waves of one run; its last wave carries shadow rays only
+	for (uint32_t w = 0; w < runWaves + D && st == GI_OK; ++w)
+	{
+		if (w < runWaves)
+		{
+			if (w < count)
+			{
+				// resetcounter.comp for the cache of iteration w (bidirectionalpathtracer.cpp:190)
+				const uint32_t slot = w % ring;
+				k_reset_counter<<<1, 1, 0, c->stream>>>(c->ringCounters + 2u * slot, c->ringCounters + 2u * slot + 1u, numLightPaths);
+				++c->launches;
+			}
+			st = wfStep(c, 0, w < count, w < count ? seeds[w] : 0u, w + 1u < count, w + 1u < runWaves);
+		}
+		if (st == GI_OK && w >= D)
+		{
+			const uint32_t e = w - D;
+			st = wfStep(c, 1, e < count, e < count ? seeds[e] : 0u, e + 1u < count, e + 1u < runWaves);
+		}
+	}
+	if (st == GI_OK) st = wfClose(c, 0, false);
+	if (st == GI_OK) st = wfClose(c, 1, false);
+	c->run[0].open = c->run[1].open = false;
+	if (st != GI_OK) return st;
+	// GiCounters::light_cache_entries / light_path_length_sum report the last iteration
+	GI_CUDA(c, cudaMemcpyAsync(c->bptCounters, c->ringCounters + 2u * ((count - 1u) % ring), 2 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
+	return GI_OK;
 }
 
 
@@ -731,6 +819,7 @@ void gi_destroy(GiContext* c)
 	if (c->copyStream) cudaStreamDestroy(c->copyStream);
 	if (c->envTex) cudaDestroyTextureObject(c->envTex);
 	if (c->envArray) cudaFreeArray(c->envArray);
+	cudaFree(c->cacheRing); cudaFree(c->ringCounters);
 	cudaFree(c->accum); cudaFree(c->lightSamples); cudaFree(c->lightCache); cudaFree(c->bptCounters); cudaFree(c->counters); cudaFree(c->mseResult);
 	for (cudaEvent_t e : c->timingEvents) cudaEventDestroy(e);
 	if (c->ownStream) cudaStreamDestroy(c->ownStream);
@@ -937,7 +1026,7 @@ int gi_set_screen_size(GiContext* c, int width, int height)
 // iterations in flight, each shading with its own set.  Outside a stream the ring position does not move.
 static int lightSlotForNextIteration(GiContext* c, uint32_t n, uint32_t* slot)
 {
-	if (c->run.open && c->run.streaming && int(n) != c->numLightSamples)
+	if (c->run[0].open && c->run[0].streaming && int(n) != c->numLightSamples)
 	{
 		int st = flushStream(c);
 		if (st != GI_OK) return st;
@@ -952,7 +1041,7 @@ static int lightSlotForNextIteration(GiContext* c, uint32_t n, uint32_t* slot)
 		GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->lightSamples), size_t(n) * GI_LIGHT_RING * sizeof(GiLightSample)));
 		c->lightSampleCapacity = n;
 	}
-	*slot = (c->run.open && c->run.streaming) ? (c->run.w.lightBase + c->run.count) % GI_LIGHT_RING : c->lightSlot;
+	*slot = (c->run[0].open && c->run[0].streaming) ? (c->run[0].w.lightBase + c->run[0].count) % GI_LIGHT_RING : c->lightSlot;
 	return GI_OK;
 }
 
@@ -1026,7 +1115,7 @@ int gi_render_iteration(GiContext* c, const GiIterationParams* p)
 	    uint32_t(p->max_path_length) + 1u <= GI_LIGHT_RING)
 	{
 		// GI_OPT_STREAMING: this iteration is one more wave of the open run (opened here if there is none)
-		WfRun& r = c->run;
+		WfRun& r = c->run[0];
 		if (r.open && r.streaming && (r.renderer != p->renderer || r.maxLen != uint32_t(p->max_path_length)))
 		{
 			st = flushStream(c);
@@ -1036,11 +1125,11 @@ int gi_render_iteration(GiContext* c, const GiIterationParams* p)
 		{
 			DFrame sf = makeFrame(c, p);
 			sf.lightSamples = c->lightSamples; // ring base; iteration i of the stream reads set (lightSlot + i) % GI_LIGHT_RING
-			st = wfOpen(c, sf, WF_PASS_PT, 0u, 0u, true, 2u * uint32_t(c->numLightSamples), c->lightSlot, GI_LIGHT_RING);
+			st = wfOpen(c, 0, sf, WF_PASS_PT, 0u, 0u, true, 2u * uint32_t(c->numLightSamples), c->lightSlot, GI_LIGHT_RING);
 			if (st != GI_OK) return st;
 			r.renderer = p->renderer;
 		}
-		st = wfStep(c, true, p->frame_seed, true, true);
+		st = wfStep(c, 0, true, p->frame_seed, true, true);
 		if (st != GI_OK) return st;
 		GI_CUDA(c, cudaGetLastError());
 		return GI_OK;
@@ -1152,6 +1241,14 @@ int gi_render_iterations(GiContext* c, const GiIterationParams* p, const uint32_
 		if (st != GI_OK) return st;
 		GI_CUDA(c, cudaGetLastError());
 		return GI_OK;
+	}
+	if (p->renderer == GI_RENDERER_BPT && c->scheduler == GI_SCHEDULER_WAVEFRONT && count > 1u && !p->warmup && p->num_rays_per_light_sample > 0 &&
+	    p->light_cache_capacity > 0 && uint64_t(p->light_cache_capacity) >= uint64_t(c->numLightSamples) * uint64_t(p->num_rays_per_light_sample))
+	{
+		// BPT: light and eye passes of consecutive iterations pipelined over a ring of light caches
+		st = renderPipelinedBPT(c, p, frame_seeds, count, d_light_samples ? 2u * samples_per_iteration : 0u);
+		if (st == GI_OK) { GI_CUDA(c, cudaGetLastError()); return GI_OK; }
+		if (st != GI_ERR_CAPACITY) return st;
 	}
 	// every other renderer / scheduler: one iteration after the other
 	for (uint32_t k = 0; k < count; ++k)
@@ -1287,7 +1384,7 @@ int gi_read_accumulator_async(GiContext* c, float* rgba, uint32_t* iterations_in
 	GI_CUDA(c, cudaEventRecord(c->snapCopied[i], c->copyStream));
 	c->snapUsed[i] = true;
 	// PT stream: iteration k joins the accumulator when its state slot is recycled, maxPathLength + 1 waves after it started
-	if (iterations_in_flight) *iterations_in_flight = (c->run.open && c->run.streaming) ? std::min(c->run.count, c->run.numSlots) : 0u;
+	if (iterations_in_flight) *iterations_in_flight = (c->run[0].open && c->run[0].streaming) ? std::min(c->run[0].count, c->run[0].numSlots) : 0u;
 	return GI_OK;
 }
 

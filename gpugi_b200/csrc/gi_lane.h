@@ -82,23 +82,34 @@ GI_HD float wfClosestLimit(float best, const DScene& s)
 	return best * margin + s.ambiguityAbs;
 }
 
+// Storage of the per-lane traversal stack behind a two-function interface, so that the kernel can keep the first entries in
+// shared memory (WfStackShared, gi_wavefront.cuh) while the emulation uses a plain array.
+struct WfStackArray
+{
+	StackEntry* e;
+	GI_HD StackEntry load(int i) const { return e[i]; }
+	GI_HD void store(int i, int node, float first) const { e[i].node = node; e[i].first = first; }
+};
+
 GI_HD void wfStackReset(WfLane& L) { L.sp = 0; L.topNode = WF_NODE_DONE; L.topFirst = 0.0f; }
 
-GI_HD void wfPush(WfLane& L, StackEntry* stack, int node, float first)
+template <class STK>
+GI_HD void wfPush(WfLane& L, const STK& stack, int node, float first)
 {
 	if (L.sp < GI_STACK_SIZE)
 	{
 #if WF_TOP_IN_REGS
-		stack[L.sp].node = L.topNode; stack[L.sp].first = L.topFirst; ++L.sp;
+		stack.store(L.sp, L.topNode, L.topFirst); ++L.sp;
 		L.topNode = node; L.topFirst = first;
 #else
-		stack[L.sp].node = node; stack[L.sp].first = first; ++L.sp;
+		stack.store(L.sp, node, first); ++L.sp;
 #endif
 	}
 	else L.flags |= WFL_OVERFLOW; // the subtree is skipped; the ray is answered by the stackless reference walk
 }
 
-GI_HD void wfPop(WfLane& L, const StackEntry* stack)
+template <class STK>
+GI_HD void wfPop(WfLane& L, const STK& stack)
 {
 #if WF_TOP_IN_REGS
 	for (;;)
@@ -107,7 +118,7 @@ GI_HD void wfPop(WfLane& L, const StackEntry* stack)
 		const float f = L.topFirst;
 		if (n == WF_NODE_DONE) { L.node = WF_NODE_DONE; return; } // the sentinel stays
 		--L.sp; // >= 0: the sentinel was stored below the first pushed entry
-		const StackEntry e = stack[L.sp];
+		const StackEntry e = stack.load(L.sp);
 		L.topNode = e.node; L.topFirst = e.first;
 		if (f <= L.limit) { L.node = n; return; }
 	}
@@ -116,7 +127,7 @@ GI_HD void wfPop(WfLane& L, const StackEntry* stack)
 	{
 		if (L.sp == 0) { L.node = WF_NODE_DONE; return; }
 		--L.sp;
-		const StackEntry e = stack[L.sp];
+		const StackEntry e = stack.load(L.sp);
 		if (e.first <= L.limit) { L.node = e.node; return; }
 	}
 #endif
@@ -243,8 +254,8 @@ GI_HD bool wfSlabTest(const WfLane& L, uint32_t wx, uint32_t wy, uint32_t wz, fl
 	return nearLow <= fminf(wfMin3(fx, fy, fz), L.limit);
 }
 
-template <class CNT>
-GI_HD void wfInnerStep(WfLane& L, const DScene& s, StackEntry* stack, CNT& cnt)
+template <class STK, class CNT>
+GI_HD void wfInnerStep(WfLane& L, const DScene& s, const STK& stack, CNT& cnt)
 {
 	// one 32-byte record, one 256-bit load: (c0.x, c0.y, c0.z, c1.x, c1.y, c1.z, child0, child1)
 	const U8 n = ld8(s.qNodes + 8 * size_t(L.node));
@@ -264,8 +275,8 @@ GI_HD void wfInnerStep(WfLane& L, const DScene& s, StackEntry* stack, CNT& cnt)
 	else wfPop(L, stack);
 }
 
-template <class CNT>
-GI_HD void wfLeafStep(WfLane& L, const DScene& s, const StackEntry* stack, WfCand* cand, CNT& cnt)
+template <class STK, class CNT>
+GI_HD void wfLeafStep(WfLane& L, const DScene& s, const STK& stack, WfCand* cand, CNT& cnt)
 {
 	const int leaf = ~L.node;
 	// One 96-byte record: both triangles + the leaf node's own box in the .w components; all six loads are issued first.
@@ -416,7 +427,8 @@ GI_HD bool wfEndOfWalk(WfLane& L, const DScene& s, WfCand* cand, CNT& cnt)
 template <class CNT>
 GI_HD void wfWalkSingle(WfLane& L, const DScene& s, F3 o, F3 d, float tMax, bool isAny, CNT& cnt)
 {
-	StackEntry stack[GI_STACK_SIZE];
+	StackEntry entries[GI_STACK_SIZE];
+	WfStackArray stack; stack.e = entries;
 	WfCand cand[WF_MAX_CAND];
 	wfBegin(L, s, o, d, tMax, isAny, 0u, cnt);
 	for (;;)

@@ -141,10 +141,44 @@ GI_D void wfFinishShadow(const WfTraceIO& io, uint32_t slot, bool occluded, CNT&
 // retired) or idle.  One outer iteration retires finished rays, refills idle lanes, runs ONE leaf step for the lanes
 // waiting at a leaf and then inner-node steps for as long as enough lanes of the warp are at inner nodes (one vote per
 // step), so leaf code, retire/refill code and inner-node code never serialise against each other inside the hot loop.
+// Traversal stack of a trace lane: entries 0 .. WF_SHARED_STACK-1 in shared memory (entry-major, one 8-byte word per thread and
+// entry: conflict-free, and the hot entries no longer compete with BVH nodes for L1 lines or cost write-through traffic to
+// L2), deeper entries in local memory.
+#ifndef WF_SHARED_STACK
+#define WF_SHARED_STACK 0
+#endif
+#ifndef WF_TRACE_THREADS
+#define WF_TRACE_THREADS 128
+#endif
+struct WfStackShared
+{
+	uint2* sh;          // &smem[threadIdx.x]
+	StackEntry* loc;
+	GI_D StackEntry load(int i) const
+	{
+		StackEntry r;
+		if (i < WF_SHARED_STACK) { const uint2 v = sh[i * WF_TRACE_THREADS]; r.node = int(v.x); r.first = __uint_as_float(v.y); }
+		else r = loc[i - WF_SHARED_STACK];
+		return r;
+	}
+	GI_D void store(int i, int node, float first) const
+	{
+		if (i < WF_SHARED_STACK) sh[i * WF_TRACE_THREADS] = make_uint2(uint32_t(node), __float_as_uint(first));
+		else { loc[i - WF_SHARED_STACK].node = node; loc[i - WF_SHARED_STACK].first = first; }
+	}
+};
+
 template <class IO, class CNT>
 GI_D void wfTraceLoop(const DScene& s, const IO& io, uint32_t* workCounter, WfTune tune, CNT& cnt)
 {
-	StackEntry stack[GI_STACK_SIZE];
+#if WF_SHARED_STACK > 0
+	__shared__ uint2 wfSharedStack[WF_SHARED_STACK * WF_TRACE_THREADS];
+	StackEntry entries[GI_STACK_SIZE - WF_SHARED_STACK];
+	WfStackShared stack; stack.sh = wfSharedStack + threadIdx.x; stack.loc = entries;
+#else
+	StackEntry entries[GI_STACK_SIZE];
+	WfStackArray stack; stack.e = entries;
+#endif
 	WfCand cand[WF_MAX_CAND];
 	WfLane L;
 	L.node = WF_NODE_DONE;
@@ -455,10 +489,23 @@ GI_D void wfPushOut(const WfFrame& w, const WfPush& out, uint32_t shadowTarget, 
 	}
 }
 
+// the light cache + counters of iteration `iteration` in a pipelined BPT batch (DFrame::cacheRing)
+GI_D void wfSelectCache(DFrame& f, uint32_t iteration)
+{
+	if (f.cacheRing > 1u)
+	{
+		const uint32_t slot = iteration % f.cacheRing;
+		f.lightCache += size_t(slot) * f.lightCacheCapacity * 4u;
+		f.lightCacheCount += 2u * slot;
+		f.lightPathLengthSum = f.lightCacheCount + 1;
+	}
+}
+
 // generate(w) of the light tracer: light path `slot` of iteration w (lighttracer.comp:49-91)
 GI_D void wfGenerateLight(const WfFrame& w, uint32_t gid, PathCounters& pc)
 {
 	DFrame f = w.f;
+	wfSelectCache(f, uint32_t(w.wave));
 	f.lightSamples = wfLightSamples(w, uint32_t(w.wave));
 	F3 origin, dir; F4 T;
 	wfGenerateLightLane(f, w.lightFlags, gid, origin, dir, T, pc);
@@ -486,14 +533,16 @@ GI_D void wfShadeLight(const WfFrame& w, uint32_t slot, bool valid, PathCounters
 		const uint32_t iteration = uint32_t(w.wave - bounce);
 		const uint32_t sidx = (iteration % w.q.numSlots) * w.q.numIds + id;
 		F4 T = ldState(w.q.stateT + sidx);
-		wfShadeLightLane(w.f, w.lightFlags, f3(r0.x, r0.y, r0.z), f3(r1.x, r1.y, r1.z), bounce, hrec.x, f2i(hrec.y), T, out, pc);
+		DFrame f = w.f;
+		wfSelectCache(f, iteration);
+		wfShadeLightLane(f, w.lightFlags, f3(r0.x, r0.y, r0.z), f3(r1.x, r1.y, r1.z), bounce, hrec.x, f2i(hrec.y), T, out, pc);
 		if (out.ray) stState(w.q.stateT + sidx, T);
 	}
 	wfPushOut(w, out, WF_FLAG_SPLAT | (uint32_t(out.py) * uint32_t(w.f.width) + uint32_t(out.px)), bounce, id);
 }
 
 // shade(w) of the BPT eye pass: one lane per hit record of an eye path
-GI_D void wfShadeEye(const WfFrame& w, uint32_t slot, bool valid, uint32_t numEntries, PathCounters& pc)
+GI_D void wfShadeEye(const WfFrame& w, uint32_t slot, bool valid, PathCounters& pc)
 {
 	WfPush out;
 	out.ray = false; out.shadow = false;
@@ -507,9 +556,21 @@ GI_D void wfShadeEye(const WfFrame& w, uint32_t slot, bool valid, uint32_t numEn
 		bounce = f2i(r0.w);
 		const uint32_t iteration = uint32_t(w.wave - bounce);
 		sidx = (iteration % w.q.numSlots) * w.q.numIds + id;
+		if (bounce == 0 && iteration >= w.q.numSlots)
+		{
+			// the slot is recycled: iteration - S is complete, its radiance joins the accumulator (pathtracer_bidir.comp:248-250)
+			const float4 old = *reinterpret_cast<const float4*>(w.q.stateC + sidx);
+			float4* px = reinterpret_cast<float4*>(w.f.accum) + id;
+			float4 a = *px;
+			a.x += old.x; a.y += old.y; a.z += old.z; a.w += old.w;
+			*px = a;
+		}
 		F4 T = f4zero(), C = f4zero(); float M = 1.0f;
 		if (bounce > 0) { T = ldState(w.q.stateT + sidx); C = ldState(w.q.stateC + sidx); M = w.q.stateM[sidx]; }
-		wfShadeEyeLane(w.f, numEntries, f3(r0.x, r0.y, r0.z), f3(r1.x, r1.y, r1.z), bounce, id, hrec.x, f2i(hrec.y), T, C, M, out, pc);
+		DFrame f = w.f;
+		wfSelectCache(f, iteration);
+		const uint32_t numEntries = *f.lightCacheCount; // complete: the light pass of this iteration ended before its eye pass began
+		wfShadeEyeLane(f, numEntries, f3(r0.x, r0.y, r0.z), f3(r1.x, r1.y, r1.z), bounce, id, hrec.x, f2i(hrec.y), T, C, M, out, pc);
 		stState(w.q.stateC + sidx, C);
 		if (out.ray) { stState(w.q.stateT + sidx, T); w.q.stateM[sidx] = M; }
 	}

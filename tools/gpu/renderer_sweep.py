@@ -70,7 +70,7 @@ def main():
         images = {}
         for sched_name, sched in (("megakernel", g.GI_SCHEDULER_MEGAKERNEL), ("wavefront", g.GI_SCHEDULER_WAVEFRONT)):
             dev.set_option(g.GI_OPT_SCHEDULER, sched)
-            modes = ["sequential"] + (["batch"] if (sched == g.GI_SCHEDULER_WAVEFRONT and name != "BPT") else [])
+            modes = ["sequential"] + (["batch"] if sched == g.GI_SCHEDULER_WAVEFRONT else [])
             for mode in modes:
                 def run():
                     if mode == "batch":

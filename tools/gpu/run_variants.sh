@@ -7,7 +7,7 @@ for lib in gpugi_b200/variants/libgpugi_b200_*.so; do
   cp $lib gpugi_b200/libgpugi_b200.so
   par=$(python -m pytest tests/test_gpu_parity.py -x -q 2>&1 | tail -1)
   for rep in 1 2; do
-  timeout 300 python tools/gpu/renderer_sweep.py --iters ${ITERS:-24} --renderers ${RENDERERS:-PT} --out gpurun_out/variant_$tag.json 2>&1 | grep '"batch"\|BPT.*wavefront' | python -c "
+  timeout 300 python tools/gpu/renderer_sweep.py --iters ${ITERS:-24} --renderers ${RENDERERS:-PT} --out gpurun_out/variant_$tag.json 2>&1 | grep '"batch"' | python -c "
 import sys, json
 for l in sys.stdin:
     r = json.loads(l)
