@@ -6,8 +6,10 @@ A "step" is one PathTracer sample pass (iteration) over the Sponza-shaped scene 
 262 144 triangles, 25 textured materials, camera + 4 point lights of scenes/cryteksponza.txt, pathLength 16).
   value  whole-job Mpaths/s with every input resident in HBM before the timed region (scene, textures, the light
          samples of all iterations, accumulator); K iterations timed with CUDA events on the launching stream.
-  e2e    the same metric through the Renderer API with HOST buffers: RendererSystem.Draw() (host light sampling +
-         4 KB H2D + kernel) and a D2H read of the full RGBA32F accumulator every step.
+  e2e    the same metric through the Renderer API with HOST buffers: per step RendererSystem.Draw() (host light sampling +
+         4 KB H2D + the iteration's kernels, streaming mode: one wave per call) and a D2H read of the full RGBA32F
+         progressive image into pinned memory (ReadBackbufferAsync), final draining ReadBackbuffer inside the timed
+         region; e2e_sync: plain Draw() + blocking ReadBackbuffer every step.
   --impl reference   the reference's CPU side of this path: the oracle (CPU restatement of the reference shaders,
          kind "port" -- the GLSL/MSVC reference cannot be built here) on all host threads, each step a bounded
          sample (evenly spaced 8-pixel stripes) of the same iteration.
