@@ -367,3 +367,231 @@ def make_furnace(albedo=0.5, emission=1.0, tess=2):
     pos, nrm, uv, tri, mat = mb.arrays()
     mats = {"wall": legacy_material((albedo,) * 3, (0, 0, 0), 1.0, 1.0, (emission,) * 3)}
     return Scene.from_mesh(pos, nrm, uv, tri, mat, mats, "")
+
+
+# --------------------------------------------------------------------------------------------------
+# C3 / C4 / C5 stand-ins: scenes of the named SHAPE for the other BASELINE configs.  Cameras, point lights and
+# the quoted material values are the reference's script / material-table data (input data, not code).
+# --------------------------------------------------------------------------------------------------
+
+BATHROOM_CAMERA = {"pos": (1.315, 1.183, -0.5367), "lookat": (0.389973, 1.086791, -0.904588), "fov": 50.0}           # scenes/bathroom.txt:2-4
+VILLA_CAMERA = {"pos": (11.901048, 3.936197, 6.616631), "lookat": (12.886539, 3.829603, 6.748702), "fov": 47.0}       # scenes/villa-night.txt:4-6
+VILLA_POINT_LIGHTS = [((23.5658, 4.35, 2.46295), (3.0, 3.0, 3.0)), ((21.3179, 4.35, 2.46144), (3.0, 3.0, 3.0)), ((16.8016, 4.18727, 8.15809), (8.0, 8.0, 8.0)),
+                      ((21.2769, 3.96, 7.20042), (1.0, 1.0, 1.0)), ((22.1166, 3.96, 7.18543), (1.0, 1.0, 1.0)), ((23.0586, 3.96, 7.1867), (1.0, 1.0, 1.0))]  # villa-night.txt:10-17
+VILLAGE_CAMERA = {"pos": (99.868530, 41.301537, -84.863884), "lookat": (99.381393, 40.570442, -84.386185), "fov": 67.0}  # scenes/medival.txt:2-4
+# scenes/medival.txt:9-56 (x, y, z, r, g, b)
+VILLAGE_POINT_LIGHTS = [
+    (50.961807, 52.331261, -48.856907, 56.0, 60.0, 74.0),
+    (93.699875, 9.947262, -68.010811, 9.6, 9.0, 8.0),
+    (93.893402, 7.766943, -68.173920, 9.6, 9.0, 8.0),
+    (90.212570, 8.170808, -64.181938, 9.6, 9.0, 8.0),
+    (87.710732, 7.788787, -60.950520, 9.6, 9.0, 8.0),
+    (96.882660, 10.159486, -49.179569, 4.8, 4.5, 4.0),
+    (93.794876, 10.159486, -49.886395, 4.8, 4.5, 4.0),
+    (90.595482, 10.159486, -50.397888, 4.8, 4.5, 4.0),
+    (87.744881, 10.159486, -50.774151, 4.8, 4.5, 4.0),
+    (84.929131, 10.159486, -51.592556, 4.8, 4.5, 4.0),
+    (76.179848, 7.677871, -72.380875, 9.6, 9.0, 8.0),
+    (72.044197, 7.767259, -65.459724, 9.6, 9.0, 8.0),
+    (70.393097, 7.530910, -61.896576, 9.6, 9.0, 8.0),
+    (67.061455, 7.728245, -63.888161, 9.6, 9.0, 8.0),
+    (67.829430, 8.177100, -79.097054, 9.6, 9.0, 8.0),
+    (58.257168, 8.014050, -82.186745, 9.6, 9.0, 8.0),
+    (57.641644, 8.066957, -71.122726, 9.6, 9.0, 8.0),
+    (59.883175, 8.035384, -69.444321, 9.6, 9.0, 8.0),
+    (35.047054, 8.077431, -79.554718, 9.6, 9.0, 8.0),
+    (41.835251, 10.939795, -77.081375, 9.6, 9.0, 8.0),
+    (41.836338, 8.048097, -77.093620, 9.6, 9.0, 8.0),
+    (46.435116, 8.234673, -75.694122, 9.6, 9.0, 8.0),
+    (46.435116, 10.939795, -75.694122, 9.6, 9.0, 8.0),
+    (51.466606, 8.112941, -74.541481, 9.6, 9.0, 8.0),
+    (51.466606, 10.939795, -74.541481, 9.6, 9.0, 8.0),
+    (40.675018, 7.732394, -65.276169, 9.6, 9.0, 8.0),
+    (44.817814, 7.609001, -60.265152, 9.6, 9.0, 8.0),
+    (46.405258, 7.907426, -56.999210, 9.6, 9.0, 8.0),
+    (51.176723, 10.372055, -51.016087, 9.6, 9.0, 8.0),
+    (51.176723, 8.112055, -51.016087, 9.6, 9.0, 8.0),
+    (56.440342, 7.825526, -46.059772, 9.6, 9.0, 8.0),
+    (60.088978, 8.039399, -40.409771, 9.6, 9.0, 8.0),
+    (63.068680, 8.044291, -36.820271, 9.6, 9.0, 8.0),
+    (65.726524, 10.416846, -30.324221, 9.6, 9.0, 8.0),
+    (65.726524, 7.5116846, -30.324221, 9.6, 9.0, 8.0),
+    (83.404610, 10.873559, -42.846710, 9.6, 9.0, 8.0),
+    (83.404610, 7.873559, -42.846710, 9.6, 9.0, 8.0),
+    (83.043175, 10.922251, -38.061066, 9.6, 9.0, 8.0),
+    (83.043175, 7.922251, -38.061066, 9.6, 9.0, 8.0),
+    (82.306511, 8.227152, -31.170267, 9.6, 9.0, 8.0),
+    (80.517807, 8.11138, -25.950634, 9.6, 9.0, 8.0),
+    (79.047409, 8.272710, -20.515154, 9.6, 9.0, 8.0),
+    (88.518288, 10.999722, -19.305355, 9.6, 9.0, 8.0),
+    (88.518288, 7.999722, -19.305355, 9.6, 9.0, 8.0),
+    (96.576538, 8.258466, -24.095053, 9.6, 9.0, 8.0),
+    (98.233070, 8.421268, -33.393890, 9.6, 9.0, 8.0),
+    (99.365128, 8.412631, -37.839222, 9.6, 9.0, 8.0),
+]
+
+
+def _relief(amp, fu, fv):
+    def f(s, t, p, n):
+        d = amp * np.sin(2 * np.pi * fu * s) * np.sin(2 * np.pi * fv * t)
+        return d[..., None] * n[None, None, :], np.broadcast_to(n, p.shape).copy()
+    return f
+
+
+def _fill_to_target(mb, target_triangles, origin, eu, ev, material, displace):
+    """Tops the mesh up to exactly `target_triangles` with a finely tessellated relief panel."""
+    if target_triangles is None:
+        return
+    remaining = target_triangles - mb.num_triangles()
+    if remaining < 0:
+        raise ValueError("base geometry already has %d triangles" % mb.num_triangles())
+    quads = remaining // 2
+    rows = 256 if quads >= 65536 else 16
+    cols = quads // rows
+    if cols > 0:
+        mb.grid(origin, eu, ev, cols, rows, material, (8, 8), displace=displace)
+    rest = quads - rows * cols
+    if rest > 0:
+        eu64, ev64 = np.asarray(eu, dtype=np.float64), np.asarray(ev, dtype=np.float64)
+        nn = np.cross(eu64, ev64)
+        o2 = np.asarray(origin, dtype=np.float64) + 1.0e-3 * nn / np.linalg.norm(nn)
+        mb.grid(o2, eu, ev, rest, 1, material, (8, 1))
+    if target_triangles - mb.num_triangles() == 1:
+        o = np.asarray(origin, dtype=np.float64)
+        mb.add([o, o + 0.01 * np.asarray(eu), o + 0.01 * np.asarray(ev)], [[0, 1, 0]] * 3, [[0, 0], [1, 0], [0, 1]], [[0, 1, 2]], material)
+
+
+def make_bathroom_like(texture_dir, target_triangles=500000, texture_size=512, seed=11, build_method="sah", detail=1.0):
+    """C3: closed interior around the camera of scenes/bathroom.txt, ~0.5 M triangles, two emissive materials
+    (bathroom.json 'light' 13/13/13 and 'low_light' 64/18.1951/1.8709), glossy tub, glass globe, water, a mirror-like
+    drawing (roughness 6.77e-6), 4 textured materials.  Lit by area lights only (BPT's home turf)."""
+
+    def T(n):
+        return max(2, int(round(n * detail)))
+    tex = write_textures(texture_dir, 4, texture_size, seed)
+    materials = {
+        "DefaultMaterial": legacy_material((0.6, 0.6, 0.6)),
+        "bathtube": legacy_material((0.64, 0.64, 0.64), (0.3, 0.3, 0.3), 0.001),
+        "carpet": legacy_material(specular=(0.1, 0.1, 0.1), roughness=0.9, albedo_texture=tex[0]),
+        "ceilling_white": legacy_material((0.8, 0.8, 0.8)),
+        "drawing": legacy_material(specular=(0.0, 0.0, 0.0), roughness=6.77062e-06, albedo_texture=tex[1]),
+        "floor": legacy_material(specular=(0.05, 0.05, 0.05), roughness=0.3, albedo_texture=tex[2]),
+        "wood": legacy_material(specular=(0.04, 0.04, 0.04), roughness=0.5, albedo_texture=tex[3]),
+        "glass_globe": legacy_material((1.0, 1.0, 1.0), (0.04, 0.04, 0.04), 0.0001, 0.0, refraction_index=1.5),
+        "water": legacy_material((0.0, 0.0, 0.0), (0.05, 0.05, 0.05), 1e-6, 0.0, refraction_index=1.33),
+        "light": legacy_material((0.6, 0.6, 0.6), emissivity=(13.0, 13.0, 13.0)),
+        "low_light": legacy_material((0.6, 0.6, 0.6), emissivity=(64.0, 18.1951, 1.8709)),
+        "wall": legacy_material((0.75, 0.72, 0.68), roughness=0.9),
+    }
+    M = {n: i for i, n in enumerate(materials)}
+    mb = MeshBuilder()
+    lo, hi = np.array([-2.2, 0.0, -3.0]), np.array([2.2, 2.6, 1.2])
+    mb.box(lo, hi, [M["wall"], M["wall"], M["floor"], M["ceilling_white"], M["wall"], M["wall"]], tess=T(48), inward=True, uv_scale=(4, 4))
+    mb.grid([-1.0, 0.002, -2.4], [0, 0, 1.6], [1.8, 0, 0], T(64), T(64), M["carpet"], (3, 3))
+    # tub: glossy squashed sphere half sunk into a plinth, water surface inside
+    mb.box([-2.0, 0.0, -2.9], [-0.4, 0.45, -1.9], M["bathtube"], tess=T(16), skip_faces=(2,))
+    mb.sphere([-1.2, 0.55, -2.4], 0.45, M["bathtube"], segments=T(96), rings=T(48), squash=(1.6, 0.5, 1.0))
+    mb.grid([-1.8, 0.62, -2.75], [0, 0, 0.7], [1.2, 0, 0], T(48), T(48), M["water"], displace=_relief(0.004, 6, 5))
+    # glass globe lamp + its low light, mirror-like drawing on the wall, wooden shelf + props
+    mb.sphere([0.6, 1.9, -1.6], 0.22, M["glass_globe"], segments=T(96), rings=T(48))
+    mb.sphere([0.6, 1.9, -1.6], 0.05, M["low_light"], segments=max(6, T(24)), rings=max(3, T(12)))
+    mb.grid([-0.8, 0.9, -2.995], [1.4, 0, 0], [0, 1.0, 0], T(32), T(32), M["drawing"])
+    mb.box([1.2, 0.0, -2.9], [2.1, 0.9, -2.3], M["wood"], tess=T(24), skip_faces=(2,), uv_scale=(2, 2))
+    rng = np.random.RandomState(seed)
+    for i in range(12):
+        x, z = rng.uniform(1.25, 2.05), rng.uniform(-2.85, -2.35)
+        mb.sphere([x, 0.9 + 0.06, z], 0.06, M["bathtube" if i % 2 else "wood"], segments=max(6, T(32)), rings=max(3, T(16)))
+    # ceiling panels (emissive quads facing down)
+    mb.grid([-0.9, 2.59, -2.0], [0.8, 0, 0], [0, 0, 0.8], 4, 4, M["light"])
+    mb.grid([0.6, 2.59, -0.6], [0.6, 0, 0], [0, 0, 0.6], 4, 4, M["light"])
+    _fill_to_target(mb, target_triangles, [2.195, 0.3, 1.1], [0, 0, -3.8], [0, 2.0, 0], M["wall"], _relief(0.004, 60, 40))
+    pos, nrm, uv, tri, mat = mb.arrays()
+    return Scene.from_mesh(pos, nrm, uv, tri, mat, materials, texture_dir, build_method)
+
+
+def make_villa_like(texture_dir, target_triangles=1000000, texture_size=512, seed=13, build_method="sah", detail=1.0):
+    """C4: night-time villa around the camera of scenes/villa-night.txt: terrace + pool (water: opacity 0, roughness 1e-6, villa.json:6-11),
+    window panes (glass: specular 0.14, roughness 1e-4, :46-51), textured boards / walls, ~1 M triangles, the 6 point lights of villa-night.txt:10-17."""
+
+    def T(n):
+        return max(2, int(round(n * detail)))
+    tex = write_textures(texture_dir, 8, texture_size, seed)
+    materials = {
+        "pool water": legacy_material((0.0, 0.0, 0.0), (0.05, 0.05, 0.05), 1e-6, 0.0, refraction_index=1.33),
+        "steel": legacy_material((0.3, 0.3, 0.3), (0.6, 0.6, 0.6), 0.05),
+        "windows/glass": legacy_material((1.0, 1.0, 1.0), (0.14, 0.14, 0.14), 0.0001, 0.0, refraction_index=1.5),
+        "plaster": legacy_material((0.85, 0.85, 0.82), roughness=0.9),
+    }
+    for i in range(8):
+        materials["boards%02d" % i] = legacy_material(specular=(0.04, 0.04, 0.04), roughness=[0.9, 0.6, 0.4, 0.8][i % 4], albedo_texture=tex[i])
+    M = {n: i for i, n in enumerate(materials)}
+    mb = MeshBuilder()
+    # ground + terrace deck, pool basin with a rippled water surface
+    mb.grid([0, 0, -6], [0, 0, 24], [36, 0, 0], T(160), T(160), M["boards00"], (30, 30), displace=_relief(0.03, 9, 7))
+    mb.box([14.0, 0.0, 9.5], [24.0, 3.2, 10.0], M["boards01"], tess=T(48), uv_scale=(8, 3))
+    mb.box([15.0, 0.02, 3.5], [25.0, 0.5, 8.5], M["plaster"], tess=T(40), skip_faces=(2, 3))
+    mb.grid([15.2, 0.45, 3.7], [0, 0, 4.6], [9.6, 0, 0], T(200), T(200), M["pool water"], displace=_relief(0.01, 14, 11))
+    # house: two storeys, glass front, lamella screens
+    mb.box([12.0, 0.0, -4.0], [30.0, 3.3, 2.0], [M["plaster"], M["plaster"], M["boards02"], M["boards03"], M["plaster"], M["plaster"]], tess=T(64), uv_scale=(6, 3))
+    mb.box([14.0, 3.3, -4.0], [28.0, 6.4, 1.0], M["plaster"], tess=T(48), uv_scale=(6, 3))
+    for i in range(10):
+        x = 13.0 + 1.6 * i
+        mb.grid([x, 0.2, 2.03], [1.4, 0, 0], [0, 2.8, 0], T(24), T(24), M["windows/glass"])
+    for i in range(60):
+        x = 12.2 + 0.3 * i
+        mb.box([x, 3.4, 1.05], [x + 0.05, 6.3, 1.25], M["boards04"], tess=T(6))
+    # garden furniture
+    rng = np.random.RandomState(seed)
+    for i in range(20):
+        x, z = rng.uniform(13.0, 26.0), rng.uniform(2.6, 9.0)
+        if 15.0 < x < 25.0 and 3.5 < z < 8.5:
+            continue
+        mb.cylinder([x, 0.0, z], 0.03, 0.45, M["steel"], segments=12, rings=4)
+        mb.box([x - 0.3, 0.45, z - 0.3], [x + 0.3, 0.5, z + 0.3], M["boards05"], tess=T(6))
+    _fill_to_target(mb, target_triangles, [30.5, 0.0, -6.0], [0, 0, 24], [0, 5.0, 0], M["boards06"], _relief(0.02, 80, 30))
+    pos, nrm, uv, tri, mat = mb.arrays()
+    scene = Scene.from_mesh(pos, nrm, uv, tri, mat, materials, texture_dir, build_method)
+    for p, i in VILLA_POINT_LIGHTS:
+        scene.add_point_light(p, i)
+    return scene
+
+
+def make_village_like(target_triangles=4000000, seed=17, build_method="sah", num_lights=48):
+    """C5: large outdoor scene around the camera of scenes/medival.txt: rolling terrain + ~400 houses (boxes with gable roofs) and towers,
+    ~4 M triangles, deep BVH, the two materials of MedivalVillage.json ('DefaultMaterial' opacity 0 -- unused by geometry here -- and
+    'FrontColor' albedo 0.9 roughness 0.6) and the 48 point lights of medival.txt:9-56."""
+    materials = {
+        "DefaultMaterial": legacy_material((0.6, 0.6, 0.6), roughness=1.0, opacity=0.0),
+        "FrontColor": legacy_material((0.9, 0.9, 0.9), roughness=0.6),
+    }
+    F = 1
+    rng = np.random.RandomState(seed)
+    mb = MeshBuilder()
+
+    def hills(s, t, p, n):
+        d = 6.0 * np.sin(2 * np.pi * 1.5 * s) * np.cos(2 * np.pi * 1.2 * t) + 1.5 * np.sin(2 * np.pi * 9 * s + 1.0) * np.sin(2 * np.pi * 7 * t)
+        return d[..., None] * n[None, None, :], np.broadcast_to(n, p.shape).copy()
+
+    scale = max(0.05, min(1.0, (target_triangles or 4000000) / 4000000.0)) ** 0.5
+    g = max(8, int(700 * scale))
+    mb.grid([0, 0, -160], [0, 0, 200], [200, 0, 0], g, g, F, (40, 40), displace=hills)
+    houses = max(4, int(400 * scale * scale))
+    for i in range(houses):
+        x, z = rng.uniform(20, 180), rng.uniform(-140, 20)
+        w, d, h = rng.uniform(4, 9), rng.uniform(4, 9), rng.uniform(3, 7)
+        y0 = -8.0
+        t = max(2, int(12 * scale))
+        mb.box([x, y0, z], [x + w, y0 + 8.0 + h, z + d], F, tess=t, skip_faces=(2,))
+        # gable roof: two sloped grids
+        r = rng.uniform(1.5, 3.5)
+        mb.grid([x - 0.3, y0 + 8.0 + h, z - 0.3], [0, 0, d + 0.6], [w / 2 + 0.3, r, 0], t, t, F)
+        mb.grid([x + w + 0.3, y0 + 8.0 + h, z - 0.3], [-(w / 2 + 0.3), r, 0], [0, 0, d + 0.6], t, t, F)
+    for i in range(max(2, int(24 * scale))):
+        x, z = rng.uniform(30, 170), rng.uniform(-130, 10)
+        mb.cylinder([x, -8.0, z], rng.uniform(2.0, 3.5), rng.uniform(20, 40), F, segments=max(8, int(48 * scale)), rings=max(4, int(40 * scale)))
+    _fill_to_target(mb, target_triangles, [0.0, -20.0, -160.0], [200.0, 0, 0], [0, 0, 200.0], F, _relief(0.5, 90, 70))
+    pos, nrm, uv, tri, mat = mb.arrays()
+    scene = Scene.from_mesh(pos, nrm, uv, tri, mat, materials, "", build_method)
+    for (x, y, z, r, g_, b) in VILLAGE_POINT_LIGHTS[:num_lights]:
+        scene.add_point_light((x, y, z), (r, g_, b))
+    return scene

@@ -469,3 +469,52 @@ def test_bidirectional_pipelined_batch(g, scenes, box1, count, path_length):
     bb = b.reshape(12, 8, 12, 8, 3).mean(axis=(1, 3))
     assert rel_mse(ab, bb) < 0.15
     dev.close()
+
+
+@pytest.mark.parametrize("which", ["bathroom", "villa", "village"])
+def test_stand_in_scenes_match_oracle(g, orc, scenes, tmp_path, which):
+    """The stand-ins of BASELINE configs 3-5 (glass / water refraction, mirror-like and emissive materials, 6 and 47 point
+    lights, textures) at test size: one PT iteration on the GPU against the oracle with the same light samples, and the
+    config's own renderer (BPT / LPT / PT) as waves against the one-thread-per-path form."""
+    if which == "bathroom":
+        sc, cam, renderer = scenes.make_bathroom_like(str(tmp_path), 30000, 64, detail=0.25), scenes.BATHROOM_CAMERA, g.GI_RENDERER_BPT
+    elif which == "villa":
+        sc, cam, renderer = scenes.make_villa_like(str(tmp_path), 60000, 64, detail=0.25), scenes.VILLA_CAMERA, g.GI_RENDERER_LPT
+    else:
+        sc, cam, renderer = scenes.make_village_like(120000), scenes.VILLAGE_CAMERA, g.GI_RENDERER_PT
+    W, H = 160, 96
+    rs = _rs(g, scenes, sc, "PT", W, H, cam=cam)
+    samples, seed, camp = rs.GetInitialLightSamples(), rs.GetFrameSeed(), rs.GetCamera()
+    rs.Draw()
+    img = rs.ReadBackbuffer()
+    ref, _ = orc.render_pt(sc.desc, camp, W, H, samples, seed, 16)
+    assert np.isfinite(img).all() and img[..., :3].mean() > 0
+    assert pixel_mismatch_fraction(img, ref, 1e-2) < 0.03
+    rs.close()
+    if renderer == g.GI_RENDERER_PT:
+        return
+    dev = _device(g, scenes, sc, W, H, cam=cam)
+    nls = 256 if renderer == g.GI_RENDERER_LPT else 128
+    nr = max(64, (W * H // nls // 64) * 64)
+    smp = g.LightSampler(sc).generate(nls)
+    dev.set_light_samples(smp)
+    cap = 0
+    if renderer == g.GI_RENDERER_BPT:
+        dev.render_iteration(renderer, 7, 16, num_rays_per_light_sample=nr, warmup=1)
+        n0 = dev.counters()["light_cache_entries"]
+        cap = n0 + n0 // 4
+        dev.alloc_light_cache(cap)
+    out = {}
+    for sched in (g.GI_SCHEDULER_MEGAKERNEL, g.GI_SCHEDULER_WAVEFRONT):
+        dev.set_option(g.GI_OPT_SCHEDULER, sched)
+        dev.clear(); dev.reset_counters()
+        for k in range(4):
+            dev.render_iteration(renderer, g.wang_hash(k), 16, num_rays_per_light_sample=nr, light_cache_capacity=cap)
+        out[sched] = (dev.read_accumulator(W, H), dev.counters())
+    (a, ca), (b, cb) = out[g.GI_SCHEDULER_MEGAKERNEL], out[g.GI_SCHEDULER_WAVEFRONT]
+    for k in ("light_paths", "camera_paths", "splats", "light_cache_entries"):
+        assert ca[k] == cb[k], k
+    assert np.isfinite(b).all()
+    ea, eb = a[..., :3].sum(), b[..., :3].sum()
+    assert ea > 0 and abs(ea - eb) / ea < (1e-3 if renderer == g.GI_RENDERER_LPT else 0.1)
+    dev.close()
