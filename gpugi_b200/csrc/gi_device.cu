@@ -367,7 +367,7 @@ struct GiContext
 	int textureFilterExact = 0;
 	int scheduler = GI_SCHEDULER_WAVEFRONT;
 	int countSteps = 0;              // GI_OPT_COUNT_STEPS
-	WfTune tune = {16, 20, 0};
+	WfTune tune = {24, 16, 0};     // B200 sweep (tools/gpu/run_variants.sh TUNES=...): refill:minInner 16:20 2.191, 24:20 2.153, 24:16 2.126, 28:16 2.143, 32:16 2.222 ms/iteration
 
 	// wavefront queues
 	WfRun run[2];                    // [0]: PT / LPT / BPT light pass / stream, [1]: BPT eye pass of a pipelined batch

@@ -36,12 +36,15 @@ struct WfCounters
 // stackless reference walk itself.
 #define WF_NODE_DONE int(0x80000000)
 // build-time switches of the trace loop, A/B measured on B200 (tools/gpu/variants.sh + run_variants.sh, PT batch, ms/iteration):
-// all off 2.221 | raw prmt 2.206 | lazy leaf box 2.332 | top of stack in registers 2.265 -> only the first one is on
+// all off 2.221 | raw prmt 2.206 | lazy leaf box 2.332 | top of stack in registers 2.265 | postponed leaf 2.267 vs 2.190 -> only raw prmt is on
 #ifndef WF_RAW_PRMT
 #define WF_RAW_PRMT 1      // prmt.b32 without __byte_perm's selector mask
 #endif
 #ifndef WF_LAZY_LEAF_BOX
 #define WF_LAZY_LEAF_BOX 0 // leaf: triangle tests first, the leaf's own exact box test only when a triangle is hit
+#endif
+#ifndef WF_POSTPONE_LEAF
+#define WF_POSTPONE_LEAF 0 // a lane that reaches a leaf stashes it and keeps stepping inner nodes until the warp's next leaf step
 #endif
 #ifndef WF_TOP_IN_REGS
 #define WF_TOP_IN_REGS 0   // most recent stack entry in registers
@@ -65,6 +68,8 @@ struct WfLane
 	float limit;     // culling limit for box entry distances
 	int hitLeaf;
 	int node;        // >= 0 inner (fast index), < 0 leaf (~leaf), WF_NODE_DONE = finished
+	int pend;        // WF_POSTPONE_LEAF: a reached but not yet tested leaf (~leaf < 0), 0 = none.  A ray is finished when node is
+	                 // WF_NODE_DONE and pend is 0.  Testing a leaf later only delays the shrinking of the culling limit.
 	// traversal stack: the most recent entry lives in registers (topNode, topFirst), the older ones in stack[0 .. sp).  A pop
 	// hands out the register entry at once and refills it with a load whose result is only needed at the NEXT pop or push,
 	// so the walk does not wait on local memory unless the popped entry is culled.  Bottom = sentinel (WF_NODE_DONE, 0).
@@ -91,7 +96,7 @@ struct WfStackArray
 	GI_HD void store(int i, int node, float first) const { e[i].node = node; e[i].first = first; }
 };
 
-GI_HD void wfStackReset(WfLane& L) { L.sp = 0; L.topNode = WF_NODE_DONE; L.topFirst = 0.0f; }
+GI_HD void wfStackReset(WfLane& L) { L.sp = 0; L.topNode = WF_NODE_DONE; L.topFirst = 0.0f; L.pend = 0; }
 
 template <class STK>
 GI_HD void wfPush(WfLane& L, const STK& stack, int node, float first)
@@ -130,6 +135,33 @@ GI_HD void wfPop(WfLane& L, const STK& stack)
 		const StackEntry e = stack.load(L.sp);
 		if (e.first <= L.limit) { L.node = e.node; return; }
 	}
+#endif
+}
+
+// WF_POSTPONE_LEAF: a lane standing at a leaf with an empty stash moves the leaf into the stash and goes on with the next node
+template <class STK>
+GI_HD void wfStash(WfLane& L, const STK& stack)
+{
+#if WF_POSTPONE_LEAF
+	if (L.node < 0 && L.node != WF_NODE_DONE && L.pend == 0) { L.pend = L.node; wfPop(L, stack); }
+#endif
+}
+
+GI_HD bool wfFinished(const WfLane& L)
+{
+#if WF_POSTPONE_LEAF
+	return L.node == WF_NODE_DONE && L.pend == 0;
+#else
+	return L.node == WF_NODE_DONE;
+#endif
+}
+
+GI_HD bool wfAtLeaf(const WfLane& L)
+{
+#if WF_POSTPONE_LEAF
+	return L.pend != 0;
+#else
+	return L.node < 0 && L.node != WF_NODE_DONE;
 #endif
 }
 
@@ -273,12 +305,29 @@ GI_HD void wfInnerStep(WfLane& L, const DScene& s, const STK& stack, CNT& cnt)
 	else if (h0) L.node = c0;
 	else if (h1) L.node = c1;
 	else wfPop(L, stack);
+	wfStash(L, stack);
+}
+
+// what follows a tested leaf: the next stack entry, or (WF_POSTPONE_LEAF) the node the lane already stands at
+template <class STK>
+GI_HD void wfLeafDone(WfLane& L, const STK& stack)
+{
+#if WF_POSTPONE_LEAF
+	wfStash(L, stack);
+#else
+	wfPop(L, stack);
+#endif
 }
 
 template <class STK, class CNT>
 GI_HD void wfLeafStep(WfLane& L, const DScene& s, const STK& stack, WfCand* cand, CNT& cnt)
 {
+#if WF_POSTPONE_LEAF
+	const int leaf = ~L.pend;
+	L.pend = 0;
+#else
 	const int leaf = ~L.node;
+#endif
 	// One 96-byte record: both triangles + the leaf node's own box in the .w components; all six loads are issued first.
 	F4 v[6];
 	ld8x3(s.leafPos + 6 * size_t(leaf), v);
@@ -292,7 +341,7 @@ GI_HD void wfLeafStep(WfLane& L, const DScene& s, const STK& stack, WfCand* cand
 #else
 	const bool gateKnown = true;
 	cnt.template add<WFC_NODES>(1u);
-	if (!(intersectBox(L.o, invDir(L.d), v[0].w, v[1].w, v[2].w, v[3].w, v[4].w, v[5].w, leafFirst, leafLast) && leafFirst <= L.limit)) { wfPop(L, stack); return; }
+	if (!(intersectBox(L.o, invDir(L.d), v[0].w, v[1].w, v[2].w, v[3].w, v[4].w, v[5].w, leafFirst, leafLast) && leafFirst <= L.limit)) { wfLeafDone(L, stack); return; }
 #endif
 #pragma unroll
 	for (int slot = 0; slot < 2; ++slot)
@@ -312,7 +361,7 @@ GI_HD void wfLeafStep(WfLane& L, const DScene& s, const STK& stack, WfCand* cand
 				if (!(intersectBox(L.o, invDir(L.d), v[0].w, v[1].w, v[2].w, v[3].w, v[4].w, v[5].w, leafFirst, leafLast) && leafFirst <= L.limit)) break;
 			}
 #endif
-			if (L.flags & WFL_ANY) { L.flags |= WFL_OCCLUDED; L.node = WF_NODE_DONE; return; }
+			if (L.flags & WFL_ANY) { L.flags |= WFL_OCCLUDED; L.node = WF_NODE_DONE; L.pend = 0; return; }
 			if (L.flags & WFL_COLLECT)
 			{
 				// pass 2: L.best is the result of pass 1 and stays fixed
@@ -339,7 +388,7 @@ GI_HD void wfLeafStep(WfLane& L, const DScene& s, const STK& stack, WfCand* cand
 				L.second = fminf(L.second, t);
 		}
 	}
-	wfPop(L, stack);
+	wfLeafDone(L, stack);
 }
 
 // Called when a lane's walk ran out of nodes.  Returns true when the ray's result (L.best, L.hitLeaf / WFL_OCCLUDED) is
@@ -433,9 +482,16 @@ GI_HD void wfWalkSingle(WfLane& L, const DScene& s, F3 o, F3 d, float tMax, bool
 	wfBegin(L, s, o, d, tMax, isAny, 0u, cnt);
 	for (;;)
 	{
-		if (L.node == WF_NODE_DONE) { if (wfEndOfWalk(L, s, cand, cnt)) return; continue; }
+		wfStash(L, stack);
+		if (wfFinished(L)) { if (wfEndOfWalk(L, s, cand, cnt)) return; continue; }
+#if WF_POSTPONE_LEAF
+		// as late as possible: the stash is only tested when the lane is blocked at a second leaf or has run out of nodes
+		if (L.node >= 0) wfInnerStep(L, s, stack, cnt);
+		else wfLeafStep(L, s, stack, cand, cnt);
+#else
 		if (L.node < 0) wfLeafStep(L, s, stack, cand, cnt);
 		else wfInnerStep(L, s, stack, cnt);
+#endif
 	}
 }
 

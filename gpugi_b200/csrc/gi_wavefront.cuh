@@ -189,7 +189,7 @@ GI_D void wfTraceLoop(const DScene& s, const IO& io, uint32_t* workCounter, WfTu
 	for (;;)
 	{
 		// ---- retire finished rays
-		if (active && L.node == WF_NODE_DONE && wfEndOfWalk(L, s, cand, cnt))
+		if (active && wfFinished(L) && wfEndOfWalk(L, s, cand, cnt))
 		{
 			io.finish(s, L, cnt);
 			active = false;
@@ -218,7 +218,8 @@ GI_D void wfTraceLoop(const DScene& s, const IO& io, uint32_t* workCounter, WfTu
 			continue;
 		}
 		// ---- one leaf step for the lanes waiting at a leaf
-		if (L.node < 0 && L.node != WF_NODE_DONE) wfLeafStep(L, s, stack, cand, cnt);
+		if (active) wfStash(L, stack); // (a freshly loaded / restarted ray may stand at a leaf: single-leaf scenes)
+		if (active && wfAtLeaf(L)) wfLeafStep(L, s, stack, cand, cnt);
 		// ---- inner-node steps while enough lanes are at inner nodes
 		unsigned innerMask = __ballot_sync(0xffffffffu, L.node >= 0);
 		if (innerMask == 0u) continue;

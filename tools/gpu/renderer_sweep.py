@@ -42,6 +42,11 @@ def main():
     ls = g.LightSampler(sc)
     ls.seed(4242)
     results = []
+    # trace-loop tuning from the environment (tools/gpu/run_variants.sh): idle lanes that trigger a refill, inner-step vote threshold
+    if os.environ.get("GPUGI_WF_REFILL"):
+        dev.set_option(g.GI_OPT_WF_REFILL_THRESHOLD, int(os.environ["GPUGI_WF_REFILL"]))
+    if os.environ.get("GPUGI_WF_MIN_INNER"):
+        dev.set_option(g.GI_OPT_WF_MIN_INNER, int(os.environ["GPUGI_WF_MIN_INNER"]))
 
     def timed(fn):
         dev.synchronize()
