@@ -168,6 +168,38 @@ struct WfStackShared
 	}
 };
 
+// Build switch, measured on B200 (PT batch, ms/iteration, refill threshold 24/16/8/4): per-refill atomic + direct loads 2.130/2.162/2.181/2.251;
+// cp.async-prefetched per-warp batches of 32 rays 2.673/2.506/2.431/2.435, of 16 rays 2.877/2.476/2.454/2.435 -- the coarse batches cost more
+// in load balance at the end of every wave than the hidden latency saves.  Off.
+#ifndef WF_PREFETCH
+#define WF_PREFETCH 0
+#endif
+#ifndef WF_PREFETCH_RAYS
+#define WF_PREFETCH_RAYS 32
+#endif
+
+GI_D void wfAsyncCopy16(void* sharedDst, const void* globalSrc)
+{
+	const unsigned d = unsigned(__cvta_generic_to_shared(sharedDst));
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(globalSrc) : "memory");
+}
+// all but the most recent group (= the prefetch of the batch after next) have landed
+GI_D void wfAsyncWaitCurrent() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
+// queue entries base .. base + WF_PREFETCH_RAYS - 1 -> dst (2 x F4 per ray), asynchronously
+template <class IO>
+GI_D void wfPrefetchBatch(const IO& io, F4* dst, uint32_t base, uint32_t total, unsigned lane)
+{
+	for (uint32_t i = lane; i < uint32_t(WF_PREFETCH_RAYS); i += 32u)
+		if (base + i < total)
+		{
+			const F4* src = io.address(base + i);
+			wfAsyncCopy16(dst + 2 * i, src);
+			wfAsyncCopy16(dst + 2 * i + 1, src + 1);
+		}
+	asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
 template <class IO, class CNT>
 GI_D void wfTraceLoop(const DScene& s, const IO& io, uint32_t* workCounter, WfTune tune, CNT& cnt)
 {
@@ -186,6 +218,22 @@ GI_D void wfTraceLoop(const DScene& s, const IO& io, uint32_t* workCounter, WfTu
 	bool poolEmpty = false;
 	const uint32_t total = io.total();
 	const unsigned lane = laneId();
+#if WF_PREFETCH
+	// Work distribution: every warp owns two batches of WF_PREFETCH_RAYS consecutive queue entries, copied to shared memory with
+	// cp.async long before a lane needs them (one atomicAdd per batch).
+	__shared__ F4 wfPrefetchBuf[WF_TRACE_THREADS / 32][2 * 2 * WF_PREFETCH_RAYS];
+	F4* pre = wfPrefetchBuf[threadIdx.x >> 5];
+	uint32_t cur = 0u, curBase, curUsed = 0u, nextBase;
+	{
+		uint32_t b = 0;
+		if (lane == 0) b = atomicAdd(workCounter, uint32_t(2 * WF_PREFETCH_RAYS));
+		b = __shfl_sync(0xffffffffu, b, 0);
+		curBase = b; nextBase = b + uint32_t(WF_PREFETCH_RAYS);
+		wfPrefetchBatch(io, pre, curBase, total, lane);
+		wfPrefetchBatch(io, pre + 2 * WF_PREFETCH_RAYS, nextBase, total, lane);
+		if (curBase >= total) poolEmpty = true;
+	}
+#endif
 	for (;;)
 	{
 		// ---- retire finished rays
@@ -196,6 +244,35 @@ GI_D void wfTraceLoop(const DScene& s, const IO& io, uint32_t* workCounter, WfTu
 		}
 		// ---- refill idle lanes from the queue
 		const unsigned idle = __ballot_sync(0xffffffffu, !active);
+#if WF_PREFETCH
+		if (!poolEmpty && (__popc(idle) >= tune.refillThreshold || idle == 0xffffffffu))
+		{
+			// rays come from the warp's prefetched batch in shared memory: no atomic and no DRAM round trip on this path
+			wfAsyncWaitCurrent();
+			__syncwarp();
+			const uint32_t take = min(uint32_t(__popc(idle)), uint32_t(WF_PREFETCH_RAYS) - curUsed);
+			const uint32_t rank = uint32_t(__popc(idle & lanemaskLt()));
+			const uint32_t mine = curBase + curUsed + rank;
+			if (!active && rank < take && mine < total)
+			{
+				const F4* b = pre + cur * (2 * WF_PREFETCH_RAYS) + 2 * (curUsed + rank);
+				io.begin(s, mine, b[0], b[1], L, cnt);
+				active = true;
+			}
+			curUsed += take;
+			if (curUsed == uint32_t(WF_PREFETCH_RAYS))
+			{
+				// the batch is used up: continue with the other buffer and prefetch a new batch into this one
+				__syncwarp();
+				uint32_t nb = 0;
+				if (lane == 0) nb = atomicAdd(workCounter, uint32_t(WF_PREFETCH_RAYS));
+				nb = __shfl_sync(0xffffffffu, nb, 0);
+				wfPrefetchBatch(io, pre + cur * (2 * WF_PREFETCH_RAYS), nb, total, lane);
+				cur ^= 1u; curBase = nextBase; curUsed = 0u; nextBase = nb;
+			}
+			if (curBase + curUsed >= total) poolEmpty = true;
+		}
+#else
 		if (!poolEmpty && (__popc(idle) >= tune.refillThreshold || idle == 0xffffffffu))
 		{
 			const int n = __popc(idle);
@@ -211,6 +288,7 @@ GI_D void wfTraceLoop(const DScene& s, const IO& io, uint32_t* workCounter, WfTu
 			}
 			if (base + uint32_t(n) >= total) poolEmpty = true;
 		}
+#endif
 		const unsigned activeMask = __ballot_sync(0xffffffffu, active);
 		if (activeMask == 0u)
 		{
@@ -265,13 +343,22 @@ struct WfQueueIO
 {
 	WfTraceIO q;
 	GI_D uint32_t total() const { return q.numClosest + q.numShadow; }
+	// the first two F4 of work item `index`: (origin.xyz, x) (direction.xyz, y)
+	GI_D const F4* address(uint32_t index) const
+	{
+		return index >= q.numClosest ? q.shadow + 3 * size_t(index - q.numClosest) : q.rays + 2 * size_t(q.rayBase + index);
+	}
+	template <class CNT>
+	GI_D void begin(const DScene& s, uint32_t index, F4 r0, F4 r1, WfLane& L, CNT& cnt) const
+	{
+		const bool isAny = index >= q.numClosest;
+		wfBegin(L, s, f3(r0.x, r0.y, r0.z), f3(r1.x, r1.y, r1.z), isAny ? r0.w : GI_RAY_MAX, isAny, index, cnt);
+	}
 	template <class CNT>
 	GI_D void load(const DScene& s, uint32_t index, WfLane& L, CNT& cnt) const
 	{
-		const bool isAny = index >= q.numClosest;
-		const F4* p = isAny ? q.shadow + 3 * size_t(index - q.numClosest) : q.rays + 2 * size_t(q.rayBase + index);
-		const F4 r0 = ld4(p), r1 = ld4(p + 1);
-		wfBegin(L, s, f3(r0.x, r0.y, r0.z), f3(r1.x, r1.y, r1.z), isAny ? r0.w : GI_RAY_MAX, isAny, index, cnt);
+		const F4* p = address(index);
+		begin(s, index, ld4(p), ld4(p + 1), L, cnt);
 	}
 	template <class CNT>
 	GI_D void finish(const DScene& s, WfLane& L, CNT& cnt) const
@@ -288,11 +375,16 @@ struct WfBatchIO
 	float4* hits;
 	uint32_t n;
 	GI_D uint32_t total() const { return n; }
+	GI_D const F4* address(uint32_t index) const { return rays + 2 * size_t(index); }
+	template <class CNT>
+	GI_D void begin(const DScene& s, uint32_t index, F4 r0, F4 r1, WfLane& L, CNT& cnt) const
+	{
+		wfBegin(L, s, f3(r0.x, r0.y, r0.z), f3(r1.x, r1.y, r1.z), r0.w, (uint32_t(f2i(r1.w)) & 1u) != 0u, index, cnt);
+	}
 	template <class CNT>
 	GI_D void load(const DScene& s, uint32_t index, WfLane& L, CNT& cnt) const
 	{
-		const F4 r0 = ld4(rays + 2 * size_t(index)), r1 = ld4(rays + 2 * size_t(index) + 1);
-		wfBegin(L, s, f3(r0.x, r0.y, r0.z), f3(r1.x, r1.y, r1.z), r0.w, (uint32_t(f2i(r1.w)) & 1u) != 0u, index, cnt);
+		begin(s, index, ld4(address(index)), ld4(address(index) + 1), L, cnt);
 	}
 	template <class CNT>
 	GI_D void finish(const DScene& s, WfLane& L, CNT& cnt) const
