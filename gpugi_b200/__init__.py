@@ -417,6 +417,53 @@ class RendererSystem:
         return out
 
 
+class Application:
+    """Headless Application of the host layer (gpugi/application.cpp): runs the reference's command scripts (scenes/*.txt syntax)."""
+
+    def __init__(self, script_path="", device=0):
+        self._h = capi.host.gih_app_create(os.fsencode(script_path) if script_path else None, int(device))
+        if not self._h:
+            raise GpugiError("Application: " + capi.host.gih_last_error().decode())
+
+    def close(self):
+        if self._h:
+            capi.host.gih_app_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def Command(self, line):
+        capi.host.gih_app_command(self._h, line.encode())
+
+    def Run(self, max_iterations=0):
+        capi.host.gih_app_run(self._h, int(max_iterations))
+
+    def GetIterationCount(self):
+        return int(capi.host.gih_app_iteration_count(self._h))
+
+    def HasShutDown(self):
+        return bool(capi.host.gih_app_has_shut_down(self._h))
+
+    def GetLastMSE(self):
+        return float(capi.host.gih_app_last_mse(self._h))
+
+    def GetLastScreenshot(self):
+        return capi.host.gih_app_last_screenshot(self._h).decode()
+
+
+def config_parse(line):
+    """One script line through ScriptProcessing::ParseCommand; True if the processor is asked to stop (wait / pause commands)."""
+    return bool(capi.host.gih_config_parse(line.encode()))
+
+
+def config_get(name):
+    n = capi.host.gih_config_count(name.encode())
+    if n < 0:
+        return None
+    return [capi.host.gih_config_get(name.encode(), i).decode() for i in range(n)]
+
+
 def write_pfm(path, rgba, divisor=1):
     """WritePfm (imageut/hdrimage.cpp:6-33)."""
     rgba = np.ascontiguousarray(rgba, dtype=np.float32)

@@ -191,6 +191,20 @@ HOST_API = {
     "gih_rs_light_samples": (None, [vp, vp]),
     "gih_rs_camera": (None, [vp, P(GiCamera)]),
     "gih_rs_renderer_info": (None, [vp, P(i32), P(u32), P(i32)]),
+    "gih_app_create": (vp, [C.c_char_p, C.c_int]),
+    "gih_app_destroy": (None, [vp]),
+    "gih_app_command": (None, [vp, C.c_char_p]),
+    "gih_app_run": (None, [vp, u64]),
+    "gih_app_iteration_count": (u64, [vp]),
+    "gih_app_has_shut_down": (C.c_int, [vp]),
+    "gih_app_last_mse": (f32, [vp]),
+    "gih_app_last_screenshot": (C.c_char_p, [vp]),
+    "gih_app_device": (vp, [vp]),
+    "gih_config_parse": (C.c_int, [C.c_char_p]),
+    "gih_config_add": (C.c_int, [C.c_char_p, C.c_char_p]),
+    "gih_config_remove": (None, [C.c_char_p]),
+    "gih_config_count": (C.c_int, [C.c_char_p]),
+    "gih_config_get": (C.c_char_p, [C.c_char_p, C.c_int]),
     "gih_write_pfm": (C.c_int, [C.c_char_p, vp, C.c_int, C.c_int, u32]),
     "gih_load_pfm": (C.c_int, [C.c_char_p, vp, C.c_int, P(C.c_int), P(C.c_int)]),
 }

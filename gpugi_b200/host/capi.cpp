@@ -10,7 +10,9 @@
 #include "logger.hpp"
 #include "pathtracer.hpp"
 #include "random.hpp"
+#include "application.hpp"
 #include "renderersystem.hpp"
+#include "scriptprocessing.hpp"
 #include "scene.hpp"
 
 #include <cstring>
@@ -233,6 +235,80 @@ void gih_rs_renderer_info(GihRendererSystem* h, int32_t* num_rays_per_light_samp
 		*light_cache_capacity = b->GetLightCacheCapacity();
 		*avg_light_path_length = b->GetAverageLightPathLength();
 	}
+}
+
+// ---- script front end (application.hpp, scriptprocessing.hpp)
+struct GihApplication { std::unique_ptr<Application> app; };
+
+GihApplication* gih_app_create(const char* script_path, int cuda_device)
+{
+	gi::LastHostError().clear();
+	try
+	{
+		std::unique_ptr<GihApplication> h(new GihApplication());
+		h->app.reset(new Application(script_path ? script_path : "", cuda_device));
+		return h.release();
+	}
+	catch (const std::exception& e)
+	{
+		LOG_ERROR("gih_app_create: " << e.what());
+		return nullptr;
+	}
+}
+void gih_app_destroy(GihApplication* h) { delete h; }
+void gih_app_command(GihApplication* h, const char* line) { h->app->Command(line); }
+void gih_app_run(GihApplication* h, uint64_t max_iterations) { h->app->Run(static_cast<unsigned long>(max_iterations)); }
+uint64_t gih_app_iteration_count(GihApplication* h) { return h->app->GetRendererSystem().GetIterationCount(); }
+int gih_app_has_shut_down(GihApplication* h) { return h->app->HasShutDown() ? 1 : 0; }
+float gih_app_last_mse(GihApplication* h) { return h->app->GetLastMSE(); }
+const char* gih_app_last_screenshot(GihApplication* h) { return h->app->GetLastScreenshot().c_str(); }
+GiContext* gih_app_device(GihApplication* h) { return h->app->GetRendererSystem().GetDevice(); }
+
+// One command line through ScriptProcessing::ParseCommand (script-file rules) against the global parameter table; returns 1 if the
+// command asks the processor to stop (waitSeconds / waitIterations / a registered pause command).
+int gih_config_parse(const char* line)
+{
+	static ScriptProcessing processor;
+	bool stop = false;
+	processor.ParseCommand(line, true, stop);
+	return stop ? 1 : 0;
+}
+int gih_config_add(const char* name, const char* comma_separated_defaults)
+{
+	try
+	{
+		GlobalConfig::ParameterType v;
+		std::string s = comma_separated_defaults ? comma_separated_defaults : "";
+		size_t a = 0;
+		while (!s.empty() && a <= s.size())
+		{
+			size_t b = s.find(',', a);
+			v.push_back(Variant(s.substr(a, b == std::string::npos ? std::string::npos : b - a)));
+			if (b == std::string::npos) break;
+			a = b + 1;
+		}
+		GlobalConfig::AddParameter(name, v);
+		return 0;
+	}
+	catch (const std::invalid_argument& e) { LOG_ERROR(e.what()); return 1; }
+}
+void gih_config_remove(const char* name) { GlobalConfig::RemoveParameter(name); }
+int gih_config_count(const char* name)
+{
+	try { return int(GlobalConfig::GetParameter(name).size()); }
+	catch (const std::invalid_argument&) { return -1; }
+}
+const char* gih_config_get(const char* name, int index)
+{
+	static thread_local std::string out;
+	try
+	{
+		GlobalConfig::ParameterType v = GlobalConfig::GetParameter(name);
+		if (index < 0 || size_t(index) >= v.size()) return nullptr;
+		out = v[size_t(index)].As<std::string>();
+		return out.c_str();
+	}
+	catch (const std::invalid_argument&) { return nullptr; }
 }
 
 // ---- PFM

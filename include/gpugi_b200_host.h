@@ -79,6 +79,24 @@ GI_API void gih_rs_light_samples(GihRendererSystem* rs, GiLightSample* out);
 GI_API void gih_rs_camera(GihRendererSystem* rs, GiCamera* out);
 GI_API void gih_rs_renderer_info(GihRendererSystem* rs, int32_t* num_rays_per_light_sample, uint32_t* light_cache_capacity, int32_t* avg_light_path_length);
 
+/* ---- script front end: Application (gpugi/application.cpp:77-193, 287-344) + ScriptProcessing (gpugi/control/scriptprocessing.cpp) ---- */
+typedef struct GihApplication GihApplication;
+GI_API GihApplication* gih_app_create(const char* script_path, int cuda_device);   /* main.cpp:41 Application(argc, argv); NULL on failure */
+GI_API void gih_app_destroy(GihApplication* app);                                  /* saves a screenshot unless "exit" was run (application.cpp:196-198) */
+GI_API void gih_app_command(GihApplication* app, const char* line);                /* a console line (scriptprocessing.cpp:29-42) */
+GI_API void gih_app_run(GihApplication* app, uint64_t max_iterations);             /* Application::Run; 0 = until "exit" or the script ran out */
+GI_API uint64_t gih_app_iteration_count(GihApplication* app);
+GI_API int gih_app_has_shut_down(GihApplication* app);
+GI_API float gih_app_last_mse(GihApplication* app);
+GI_API const char* gih_app_last_screenshot(GihApplication* app);
+GI_API GiContext* gih_app_device(GihApplication* app);
+/* GlobalConfig (gpugi/control/globalconfig.hpp) through the script syntax "name = v0, v1" */
+GI_API int gih_config_parse(const char* line);
+GI_API int gih_config_add(const char* name, const char* comma_separated_defaults);
+GI_API void gih_config_remove(const char* name);
+GI_API int gih_config_count(const char* name);                                     /* -1: no such parameter */
+GI_API const char* gih_config_get(const char* name, int index);
+
 /* WritePfm / LoadPfm (imageut/hdrimage.cpp:6-60) */
 GI_API int gih_write_pfm(const char* path, const float* rgba, int w, int h, uint32_t divisor);
 GI_API int gih_load_pfm(const char* path, float* rgb, int capacity_pixels, int* w, int* h);

@@ -141,3 +141,20 @@ def assert_hits_equal(a, b, what=""):
 def pixel_mismatch_fraction(img, ref, rel_tol=1e-2):
     rel = np.abs(img[..., :3] - ref[..., :3]) / (np.abs(ref[..., :3]) + 1e-3)
     return float((rel.max(axis=2) > rel_tol).mean())
+
+
+def robust_block_compare(a, b, block=8, clip=20.0):
+    """Two independent noisy estimates of the same image (BPT: the light-cache slot order, hence every connection, is scheduling
+    dependent).  Fireflies make plain (rel)MSE a coin toss at a few iterations, so: clip both at `clip` x the mean, average over
+    block x block pixels, and return (relative difference of the clipped means, median and 90th percentile of the per-block relative
+    differences)."""
+    import numpy as np
+    a = np.asarray(a, dtype=np.float64)[..., :3]
+    b = np.asarray(b, dtype=np.float64)[..., :3]
+    cap = clip * max(b.mean(), 1e-12)
+    a, b = np.minimum(a, cap), np.minimum(b, cap)
+    h, w = (a.shape[0] // block) * block, (a.shape[1] // block) * block
+    ab = a[:h, :w].reshape(h // block, block, w // block, block, 3).mean(axis=(1, 3, 4))
+    bb = b[:h, :w].reshape(h // block, block, w // block, block, 3).mean(axis=(1, 3, 4))
+    rel = np.abs(ab - bb) / (bb + 0.05 * bb.mean())
+    return abs(a.mean() - b.mean()) / b.mean(), float(np.median(rel)), float(np.percentile(rel, 90))

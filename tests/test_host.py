@@ -191,3 +191,33 @@ def test_no_cpu_fallback(g):
     assert "no CPU fallback" in str(e.value) or "CUDA" in str(e.value)
     with pytest.raises(g.GpugiError):
         g.RendererSystem(0)
+
+
+def test_script_syntax_and_global_config(g, capfd):
+    """ScriptProcessing::ParseCommand (scriptprocessing.cpp:66-158) + GlobalConfig (globalconfig.cpp): comments, blanks, value lists,
+    getters, value-count enforcement, unknown names, the two script-only wait commands."""
+    from gpugi_b200 import _capi as c
+    for name in (b"t_vec", b"t_event", b"t_str"):
+        c.host.gih_config_remove(name)
+    assert c.host.gih_config_add(b"t_vec", b"1,2,3") == 0
+    assert c.host.gih_config_add(b"t_vec", b"1") == 1                      # already exists (globalconfig.cpp:20-27)
+    assert c.host.gih_config_add(b"t_event", b"") == 0 and c.host.gih_config_add(b"t_str", b"x") == 0
+    assert g.config_get("t_vec") == ["1", "2", "3"] and g.config_get("t_event") == [] and g.config_get("nope") is None
+    assert not g.config_parse("t_vec = 0.0,\t1.5 ,  2.27   // camera position")
+    assert g.config_get("t_vec") == ["0.0", "1.5", "2.27"]
+    assert not g.config_parse("   # a comment line") and not g.config_parse("") and not g.config_parse("//t_vec = 9,9,9")
+    assert g.config_get("t_vec") == ["0.0", "1.5", "2.27"]
+    assert not g.config_parse("t_str = ../scenes/box1/box1.json")
+    assert g.config_get("t_str") == ["../scenes/box1/box1.json"]
+    assert not g.config_parse("t_vec = 1, 2")                             # wrong value count: error, value kept
+    assert g.config_get("t_vec") == ["0.0", "1.5", "2.27"]
+    assert not g.config_parse("doesNotExist = 3")
+    err = capfd.readouterr().err
+    assert "expects 3 value(s)" in err and "does not exist" in err
+    assert not g.config_parse("t_vec")                                    # getter
+    assert "{0.0, 1.5, 2.27 }" in capfd.readouterr().out
+    assert not g.config_parse("t_event")                                  # an event: empty value list, fires listeners
+    assert g.config_parse("waitIterations = 50") and g.config_parse("waitSeconds = 0.5")  # script-only commands stop the processor
+    assert g.config_get("pathLength") == ["16"]
+    for name in (b"t_vec", b"t_event", b"t_str"):
+        c.host.gih_config_remove(name)
