@@ -70,8 +70,9 @@ class Scene:
         return cls(capi.host.gih_scene_load(os.fsencode(json_path), int(bvh_type)))
 
     @classmethod
-    def from_mesh(cls, positions, normals, texcoords, triangles, tri_materials, materials, texture_dir="", build_method="sah"):
-        """Synthetic scene: mesh arrays + material dict (JSON 'materials' object, order = material index)."""
+    def from_mesh(cls, positions, normals, texcoords, triangles, tri_materials, materials, texture_dir="", build_method="sah", bvh_type=0):
+        """Synthetic scene: mesh arrays + material dict (JSON 'materials' object, order = material index).
+        bvh_type 1: oriented boxes (the reference's second accelerator, GlobalConfig "bvhType")."""
         positions = np.ascontiguousarray(positions, dtype=np.float32)
         normals = np.ascontiguousarray(normals, dtype=np.float32)
         texcoords = np.ascontiguousarray(texcoords, dtype=np.float32)
@@ -79,9 +80,11 @@ class Scene:
         tri_materials = np.ascontiguousarray(tri_materials, dtype=np.uint32)
         assert positions.shape == normals.shape and positions.shape[1] == 3 and texcoords.shape == (positions.shape[0], 2)
         assert triangles.shape[1] == 3 and tri_materials.shape[0] == triangles.shape[0]
-        env = json.dumps({"scene": "", "accelerator": "aabox", "materials": materials, "lights": {}, "cameras": {}})
-        h = capi.host.gih_scene_from_mesh(_vp(positions), _vp(normals), _vp(texcoords), positions.shape[0], _vp(triangles), _vp(tri_materials),
-                                          triangles.shape[0], env.encode(), os.fsencode(texture_dir), 1 if build_method == "kd" else 0)
+        env = json.dumps({"scene": "", "accelerator": "obox" if bvh_type else "aabox", "materials": materials, "lights": {}, "cameras": {}})
+        h = capi.host.gih_scene_from_mesh_bvh(_vp(positions), _vp(normals), _vp(texcoords), positions.shape[0], _vp(triangles), _vp(tri_materials),
+                                              triangles.shape[0], env.encode(), os.fsencode(texture_dir), 1 if build_method == "kd" else 0, int(bvh_type))
+        if not h:
+            raise GpugiError("Scene.from_mesh: " + capi.host.gih_last_error().decode())
         return cls(h)
 
     def __del__(self):
@@ -114,6 +117,14 @@ class Scene:
     def nodes(self):
         d = self.desc
         return np.ctypeslib.as_array(C.cast(d.nodes, C.POINTER(C.c_uint8)), shape=(d.num_nodes * 32,)).view(NODE_DTYPE).copy()
+
+    def obox_nodes(self):
+        """TreeNode<ei::OBox> array (bvh_type 1), else None."""
+        d = self.desc
+        if not d.obox_nodes:
+            return None
+        dt = np.dtype([("center", "<f4", 3), ("first_child", "<u4"), ("sides_half", "<f4", 3), ("escape", "<u4"), ("rotation_inv", "<f4", 4)])
+        return np.ctypeslib.as_array(C.cast(d.obox_nodes, C.POINTER(C.c_uint8)), shape=(d.num_nodes * 48,)).view(dt).copy()
 
     def leaf_triangles(self):
         d = self.desc

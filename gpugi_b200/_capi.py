@@ -58,13 +58,17 @@ class GiMaterial(C.Structure):
                 ("fresnel0", f32 * 3), ("refraction_index_avg", f32), ("fresnel1", f32 * 3), ("padding", f32)]
 
 
+class GiOBoxNode(C.Structure):
+    _fields_ = [("center", f32 * 3), ("first_child", u32), ("sides_half", f32 * 3), ("escape", u32), ("rotation_inv", f32 * 4)]
+
+
 class GiSceneDesc(C.Structure):
     _fields_ = [("nodes", C.POINTER(GiNode)), ("num_nodes", u32),
                 ("leaf_triangles", C.POINTER(GiTriangle)), ("num_leaf_triangles", u32),
                 ("positions", C.POINTER(f32)), ("vertex_info", C.POINTER(GiVertexInfo)), ("num_vertices", u32),
                 ("materials", C.POINTER(GiMaterial)), ("num_materials", u32),
                 ("textures", C.POINTER(GiTexture)), ("num_textures", u32),
-                ("num_tree_levels", u32)]
+                ("num_tree_levels", u32), ("obox_nodes", C.POINTER(GiOBoxNode))]
 
 
 class GiCamera(C.Structure):
@@ -156,6 +160,7 @@ HOST_API = {
     "gih_set_path_length": (None, [C.c_int]),
     "gih_scene_load": (vp, [C.c_char_p, C.c_int]),
     "gih_scene_from_mesh": (vp, [vp, vp, vp, u32, vp, vp, u32, C.c_char_p, C.c_char_p, C.c_int]),
+    "gih_scene_from_mesh_bvh": (vp, [vp, vp, vp, u32, vp, vp, u32, C.c_char_p, C.c_char_p, C.c_int, C.c_int]),
     "gih_scene_destroy": (None, [vp]),
     "gih_scene_store": (C.c_int, [vp, C.c_char_p, C.c_char_p]),
     "gih_scene_desc": (None, [vp, P(GiSceneDesc)]),

@@ -136,6 +136,7 @@ struct DScene
 {
 	// reference layout (escape-pointer walk; exact fallback)
 	const F4* refNodes;      // 2 x F4 per node: (min.xyz, firstChild bits), (max.xyz, escape bits)
+	const F4* oboxNodes;     // bvhType = 1: 3 x F4 per node (center.xyz, firstChild) (sidesHalf.xyz, escape) (rotationInv.xyzw); else null
 	// fast layout: one 64-byte record per inner node holding BOTH child boxes
 	const F4* fastNodes;     // 4 x F4: (c0.min.xyz, c0.max.x) (c0.max.yz, c1.min.xy) (c1.min.z, c1.max.xyz) (child0, child1, -, -)
 	const uint32_t* qNodes;  // wavefront walk: 8 words (32 bytes, one 256-bit load) per INNER node: both child boxes on a 16-bit grid over
@@ -202,6 +203,33 @@ GI_HD bool intersectTriangle(F3 o, F3 d, F3 p0, F3 p1, F3 p2, float& hit, F3& ba
 
 GI_HD F3 invDir(F3 d) { return f3(GI_DIV(1.0f, d.x), GI_DIV(1.0f, d.y), GI_DIV(1.0f, d.z)); }
 
+// rotate(), intersectiontests.glsl:82-88: x rotated by the quaternion q
+GI_HD F3 rotateByQuaternion(F3 x, F4 q)
+{
+	F3 t = crossx(f3(q.x, q.y, q.z), x);
+	return f3(GI_ADD(x.x, GI_MUL(2.0f, GI_SUB(GI_ADD(GI_MUL(q.w, t.x), GI_MUL(q.y, t.z)), GI_MUL(q.z, t.y)))),
+	          GI_ADD(x.y, GI_MUL(2.0f, GI_SUB(GI_ADD(GI_MUL(q.w, t.y), GI_MUL(q.z, t.x)), GI_MUL(q.x, t.z)))),
+	          GI_ADD(x.z, GI_MUL(2.0f, GI_SUB(GI_ADD(GI_MUL(q.w, t.z), GI_MUL(q.x, t.y)), GI_MUL(q.y, t.x)))));
+}
+
+// FetchIntersectBoxNode / FetchIntersectOBoxNode, intersectiontests.glsl:100-128: node test + tree pointers of node `index`
+GI_HD bool fetchIntersectNode(const DScene& s, F3 o, F3 d, F3 inv, int index, float& firstHit, float& lastHit, uint32_t& childCode, int& escape)
+{
+	if (s.oboxNodes)
+	{
+		const F4 a = ld4(s.oboxNodes + 3 * size_t(index)), b = ld4(s.oboxNodes + 3 * size_t(index) + 1), q = ld4(s.oboxNodes + 3 * size_t(index) + 2);
+		childCode = uint32_t(f2i(a.w));
+		escape = f2i(b.w);
+		const F3 ro = rotateByQuaternion(subx(o, f3(a.x, a.y, a.z)), q);
+		const F3 rd = rotateByQuaternion(d, q);
+		return intersectBox(ro, invDir(rd), -b.x, -b.y, -b.z, b.x, b.y, b.z, firstHit, lastHit);
+	}
+	const F4 a = ld4(s.refNodes + 2 * size_t(index)), b = ld4(s.refNodes + 2 * size_t(index) + 1);
+	childCode = uint32_t(f2i(a.w));
+	escape = f2i(b.w);
+	return intersectBox(o, inv, a.x, a.y, a.z, b.x, b.y, b.z, firstHit, lastHit);
+}
+
 struct TraceStats { uint32_t nodes, tris; }; // traversal work actually done by this thread (not the reference counts)
 
 struct Hit
@@ -238,12 +266,10 @@ GI_HD bool traceReference(const DScene& s, F3 o, F3 d, float& rayLength, int& hi
 		if (!nextIsLeafNode)
 		{
 			if (st) ++st->nodes;
-			F4 a = ld4(s.refNodes + 2 * size_t(currentNodeIndex));
-			F4 b = ld4(s.refNodes + 2 * size_t(currentNodeIndex) + 1);
-			uint32_t childCode = uint32_t(f2i(a.w));
-			int escape = f2i(b.w);
+			uint32_t childCode;
+			int escape;
 			float newHit, exitDist;
-			if (intersectBox(o, inv, a.x, a.y, a.z, b.x, b.y, b.z, newHit, exitDist) && newHit <= rayLength)
+			if (fetchIntersectNode(s, o, d, inv, currentNodeIndex, newHit, exitDist, childCode, escape) && newHit <= rayLength)
 			{
 				currentNodeIndex = int(childCode & 0x7FFFFFFFu);
 				nextIsLeafNode = uint32_t(currentNodeIndex) != childCode;

@@ -939,6 +939,7 @@ int gi_upload_scene(GiContext* c, const GiSceneDesc* d)
 	// ---- upload
 	DScene s = L.scene;
 	GI_CUDA(c, uploadVector(c, L.refNodes, &s.refNodes));
+	if (!L.oboxNodes.empty()) GI_CUDA(c, uploadVector(c, L.oboxNodes, &s.oboxNodes));
 	GI_CUDA(c, uploadVector(c, L.fastNodes, &s.fastNodes));
 	GI_CUDA(c, uploadVector(c, L.qNodes, &s.qNodes));
 	GI_CUDA(c, uploadVector(c, L.leafPos, &s.leafPos));

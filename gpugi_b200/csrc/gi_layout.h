@@ -20,6 +20,7 @@ namespace gik {
 struct HostLayout
 {
 	std::vector<F4> refNodes, fastNodes, leafPos, vertexInfo;
+	std::vector<F4> oboxNodes;              // bvhType = 1: GiOBoxNode array as is (3 x F4 per node), else empty
 	std::vector<I4> leafTris;
 	std::vector<uint32_t> qNodes;           // 8 words per inner node (quantised child boxes + child links)
 	std::vector<uint32_t> leafNode;         // leaf -> index of the node that points to it
@@ -274,6 +275,21 @@ inline bool buildHostLayout(const GiSceneDesc* d, HostLayout& L, std::string& er
 	L.scene.numLeafTris = d->num_leaf_triangles;
 	L.scene.numMaterials = d->num_materials;
 	L.scene.rootIsLeaf = (d->nodes[0].first_child & 0x80000000u) ? 1 : 0;
+	if (d->obox_nodes)
+	{
+		// bvhType = 1: the oriented boxes replace the AABoxes in the reference-order walk (intersectiontests.glsl:114-128).  Their tree
+		// pointers must be the ones of `nodes`; the ordered walk (built on the AABoxes) does not apply.
+		for (uint32_t i = 0; i < d->num_nodes; ++i)
+		{
+			const GiOBoxNode& o = d->obox_nodes[i];
+			if (o.first_child != d->nodes[i].first_child || o.escape != d->nodes[i].escape) { err = "obox_nodes: tree pointers differ from nodes"; return false; }
+			for (int k = 0; k < 3; ++k)
+				if (!std::isfinite(o.center[k]) || !std::isfinite(o.sides_half[k]) || o.sides_half[k] < 0.0f) { err = "obox_nodes: non-finite or negative box"; return false; }
+		}
+		L.oboxNodes.resize(size_t(d->num_nodes) * 3);
+		std::memcpy(L.oboxNodes.data(), d->obox_nodes, size_t(d->num_nodes) * sizeof(GiOBoxNode));
+		L.binary = false;
+	}
 	L.scene.fastOrderValid = L.binary ? 1 : 0;
 	L.scene.leafPreorder = preorder ? 1 : 0;
 	{

@@ -151,7 +151,7 @@ void Chunk::setMesh(const Vec3* positions, const Vec3* normals, const Vec2* texc
 	m_triangles.assign(triangles, triangles + numTriangles);
 	if (triangleMaterials) { m_triangleMaterials.assign(triangleMaterials, triangleMaterials + numTriangles); m_properties |= Property::TRIANGLE_MAT; }
 	else m_triangleMaterials.clear();
-	m_hierarchy.clear(); m_hierarchyParents.clear(); m_hierarchyLeaves.clear(); m_aaBoxes.clear();
+	m_hierarchy.clear(); m_hierarchyParents.clear(); m_hierarchyLeaves.clear(); m_aaBoxes.clear(); m_oBoxes.clear();
 	m_numTreeLevels = 0;
 	m_boundingBox = {{1e10f, 1e10f, 1e10f}, {-1e10f, -1e10f, -1e10f}};
 	for (const Vec3& p : m_positions) { m_boundingBox.min = vmin(m_boundingBox.min, p); m_boundingBox.max = vmax(m_boundingBox.max, p); }
@@ -375,7 +375,7 @@ uint32_t Chunk::remapNodePointers(uint32_t root, uint32_t rootParent, uint32_t r
 
 void Chunk::buildHierarchy(BuildMethod method)
 {
-	m_hierarchy.clear(); m_hierarchyParents.clear(); m_hierarchyLeaves.clear(); m_aaBoxes.clear();
+	m_hierarchy.clear(); m_hierarchyParents.clear(); m_hierarchyLeaves.clear(); m_aaBoxes.clear(); m_oBoxes.clear();
 	m_numTrianglesPerLeaf = 2;
 	if (m_triangles.empty()) return;
 	if (method == BuildMethod::KD_TREE) buildBVH_kdtree();
@@ -420,6 +420,135 @@ void Chunk::computeBVHAABoxes()
 		}
 	}
 	m_properties |= Property::AABOX_BVH;
+}
+
+// ---- oriented boxes
+namespace {
+// rotate x by the unit quaternion q (the same formula the traversal uses, intersectiontests.glsl:82-88)
+inline Vec3 qrotate(const Vec3& x, const Quaternion& q)
+{
+	Vec3 t = {q.j * x.z - q.k * x.y, q.k * x.x - q.i * x.z, q.i * x.y - q.j * x.x};
+	return Vec3{x.x + 2.0f * (q.r * t.x + q.j * t.z - q.k * t.y), x.y + 2.0f * (q.r * t.y + q.k * t.x - q.i * t.z), x.z + 2.0f * (q.r * t.z + q.i * t.y - q.j * t.x)};
+}
+inline Quaternion qconj(const Quaternion& q) { return Quaternion{-q.i, -q.j, -q.k, q.r}; }
+
+// unit quaternion of the rotation whose matrix has the orthonormal, right-handed rows a0, a1, a2 (world -> box frame is conj of it)
+Quaternion quaternionFromAxes(const double a[3][3])
+{
+	// columns of the box->world rotation are the axes: R = [a0 a1 a2]
+	const double m00 = a[0][0], m01 = a[1][0], m02 = a[2][0], m10 = a[0][1], m11 = a[1][1], m12 = a[2][1], m20 = a[0][2], m21 = a[1][2], m22 = a[2][2];
+	double qw, qx, qy, qz;
+	const double tr = m00 + m11 + m22;
+	if (tr > 0) { double s = std::sqrt(tr + 1.0) * 2; qw = 0.25 * s; qx = (m21 - m12) / s; qy = (m02 - m20) / s; qz = (m10 - m01) / s; }
+	else if (m00 > m11 && m00 > m22) { double s = std::sqrt(1.0 + m00 - m11 - m22) * 2; qw = (m21 - m12) / s; qx = 0.25 * s; qy = (m01 + m10) / s; qz = (m02 + m20) / s; }
+	else if (m11 > m22) { double s = std::sqrt(1.0 + m11 - m00 - m22) * 2; qw = (m02 - m20) / s; qx = (m01 + m10) / s; qy = 0.25 * s; qz = (m12 + m21) / s; }
+	else { double s = std::sqrt(1.0 + m22 - m00 - m11) * 2; qw = (m10 - m01) / s; qx = (m02 + m20) / s; qy = (m12 + m21) / s; qz = 0.25 * s; }
+	const double n = std::sqrt(qw * qw + qx * qx + qy * qy + qz * qz);
+	return Quaternion{float(qx / n), float(qy / n), float(qz / n), float(qw / n)};
+}
+
+// principal-axis frame of a point set (Jacobi eigen decomposition of the covariance), rows = axes, right-handed
+void principalFrame(const Vec3* p, size_t n, double axes[3][3])
+{
+	double mean[3] = {0, 0, 0};
+	for (size_t i = 0; i < n; ++i) { mean[0] += p[i].x; mean[1] += p[i].y; mean[2] += p[i].z; }
+	for (double& m : mean) m /= double(n);
+	double c[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+	for (size_t i = 0; i < n; ++i)
+	{
+		const double d[3] = {p[i].x - mean[0], p[i].y - mean[1], p[i].z - mean[2]};
+		for (int r = 0; r < 3; ++r) for (int k = 0; k < 3; ++k) c[r][k] += d[r] * d[k];
+	}
+	double v[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+	for (int sweep = 0; sweep < 32; ++sweep)
+	{
+		double off = std::fabs(c[0][1]) + std::fabs(c[0][2]) + std::fabs(c[1][2]);
+		if (off < 1e-30) break;
+		for (int a = 0; a < 2; ++a) for (int b = a + 1; b < 3; ++b)
+		{
+			if (std::fabs(c[a][b]) < 1e-300) continue;
+			const double theta = (c[b][b] - c[a][a]) / (2.0 * c[a][b]);
+			const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+			const double cs = 1.0 / std::sqrt(t * t + 1.0), sn = t * cs;
+			for (int k = 0; k < 3; ++k) { const double ca = c[k][a], cb = c[k][b]; c[k][a] = cs * ca - sn * cb; c[k][b] = sn * ca + cs * cb; }
+			for (int k = 0; k < 3; ++k) { const double ca = c[a][k], cb = c[b][k]; c[a][k] = cs * ca - sn * cb; c[b][k] = sn * ca + cs * cb; }
+			for (int k = 0; k < 3; ++k) { const double va = v[k][a], vb = v[k][b]; v[k][a] = cs * va - sn * vb; v[k][b] = sn * va + cs * vb; }
+		}
+	}
+	for (int a = 0; a < 3; ++a) for (int k = 0; k < 3; ++k) axes[a][k] = v[k][a]; // eigenvectors are the columns of v
+	// right-handed: a2 = a0 x a1
+	axes[2][0] = axes[0][1] * axes[1][2] - axes[0][2] * axes[1][1];
+	axes[2][1] = axes[0][2] * axes[1][0] - axes[0][0] * axes[1][2];
+	axes[2][2] = axes[0][0] * axes[1][1] - axes[0][1] * axes[1][0];
+}
+}
+
+void Chunk::computeBVHOBoxes()
+{
+	m_oBoxes.assign(m_hierarchy.size(), OBox{{0, 0, 0}, {0, 0, 0}, {0, 0, 0, 1}});
+	if (m_hierarchy.empty()) return;
+	// bim_hierarchy.cpp:54-85: depth-first, every node fits its box to the vertices collected below it (explicit stack instead of recursion)
+	std::vector<Vec3> points;
+	struct Frame { uint32_t node; size_t firstPoint; uint32_t nextChild; };
+	std::vector<Frame> stack;
+	stack.push_back(Frame{0u, 0u, 0xffffffffu});
+	while (!stack.empty())
+	{
+		Frame& f = stack.back();
+		const uint32_t child = m_hierarchy[f.node].firstChild;
+		bool fit = false;
+		if (child & 0x80000000u)
+		{
+			size_t leafIdx = size_t(child & 0x7fffffffu) * m_numTrianglesPerLeaf;
+			for (uint32_t i = 0; i < m_numTrianglesPerLeaf; ++i)
+			{
+				const UVec4& t = m_hierarchyLeaves[leafIdx + i];
+				if (t.x == t.y) break;
+				points.push_back(m_positions[t.x]); points.push_back(m_positions[t.y]); points.push_back(m_positions[t.z]);
+			}
+			fit = true;
+		}
+		else if (f.nextChild == 0xffffffffu)
+		{
+			f.nextChild = m_hierarchy[child].escape;
+			stack.push_back(Frame{child, points.size(), 0xffffffffu});
+		}
+		else if (f.nextChild != 0 && m_hierarchyParents[f.nextChild] == f.node)
+		{
+			const uint32_t c = f.nextChild;
+			f.nextChild = m_hierarchy[c].escape;
+			stack.push_back(Frame{c, points.size(), 0xffffffffu});
+		}
+		else
+			fit = true;
+		if (!fit) continue;
+		const Frame done = stack.back();
+		stack.pop_back();
+		const Vec3* p = points.data() + done.firstPoint;
+		const size_t n = points.size() - done.firstPoint;
+		double axes[3][3];
+		principalFrame(p, n, axes);
+		OBox box;
+		box.orientation = quaternionFromAxes(axes);
+		// ei::OBox(orientation, points, n), 3dtypes.cpp:205-225, in the arithmetic of the traversal; padded by a few ulp so that
+		// the float rotation of a contained vertex can never land outside
+		const Quaternion inv = qconj(box.orientation);
+		Vec3 mn = qrotate(p[0], inv), mx = mn;
+		for (size_t i = 1; i < n; ++i)
+		{
+			const Vec3 q = qrotate(p[i], inv);
+			mn = Vec3{std::min(mn.x, q.x), std::min(mn.y, q.y), std::min(mn.z, q.z)};
+			mx = Vec3{std::max(mx.x, q.x), std::max(mx.y, q.y), std::max(mx.z, q.z)};
+		}
+		const Vec3 mid = {(mn.x + mx.x) * 0.5f, (mn.y + mx.y) * 0.5f, (mn.z + mx.z) * 0.5f};
+		box.center = qrotate(mid, box.orientation);
+		const float scale = std::max(std::max(std::fabs(mn.x), std::fabs(mx.x)), std::max(std::max(std::fabs(mn.y), std::fabs(mx.y)), std::max(std::fabs(mn.z), std::fabs(mx.z))));
+		const float pad = 8.0f * 1.1920929e-07f * scale + 1e-30f;
+		box.halfSides = Vec3{(mx.x - mn.x) * 0.5f + pad, (mx.y - mn.y) * 0.5f + pad, (mx.z - mn.z) * 0.5f + pad};
+		m_oBoxes[done.node] = box;
+		// (the reference reduces the collected points to their convex set before going up; the plain list gives the same box here)
+	}
+	m_properties |= Property::OBOX_BVH;
 }
 
 // ------------------------------------------------------------------ file format
@@ -577,6 +706,7 @@ bool BinaryModel::load(const std::string& envFile, std::string* error)
 				case HIERARCHY_PARENTS: ok = readSection(f, s, c.m_hierarchyParents); break;
 				case HIERARCHY_LEAVES: ok = readSection(f, s, c.m_hierarchyLeaves); break;
 				case Property::AABOX_BVH: ok = readSection(f, s, c.m_aaBoxes); c.m_properties |= Property::AABOX_BVH; break;
+				case Property::OBOX_BVH: ok = readSection(f, s, c.m_oBoxes); c.m_properties |= Property::OBOX_BVH; break;
 				default: f.seekg(std::streamoff(s.size), std::ios::cur); // tangents, qormals, OBoxes, SGGX, ...: not consumed
 				}
 				if (!ok) { if (error) *error = "Error in chunk decompression."; return false; }
@@ -667,6 +797,7 @@ bool BinaryModel::store(const std::string& envFile, const std::string& bimFileNa
 		ok = ok && writeSection(f, HIERARCHY_LEAVES, c.m_hierarchyLeaves);
 	}
 	if (c.m_properties & Property::AABOX_BVH) ok = ok && writeSection(f, Property::AABOX_BVH, c.m_aaBoxes);
+	if (c.m_properties & Property::OBOX_BVH) ok = ok && writeSection(f, Property::OBOX_BVH, c.m_oBoxes);
 	std::streamoff endPos = f.tellp();
 	h = {CHUNK_SECTION, 0, uint64_t(endPos - chunkHeaderPos) - sizeof(SectionHeader), 0};
 	f.seekp(chunkHeaderPos);

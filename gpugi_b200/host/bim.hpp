@@ -28,6 +28,8 @@ struct Vec3 { float x, y, z; };
 struct UVec3 { uint32_t x, y, z; };
 struct UVec4 { uint32_t x, y, z, w; };
 struct Box { Vec3 min, max; };
+struct Quaternion { float i, j, k, r; };                                   // ei::TQuaternion: imaginary part first (vector.hpp:867)
+struct OBox { Vec3 center; Vec3 halfSides; Quaternion orientation; };      // ei::OBox (3dtypes.hpp:126-131), 40 bytes, the OBOX_BVH section element
 
 // chunk.hpp:9-37 (subset + the extra section ids of bim_io.cpp:44-49)
 namespace Property {
@@ -110,6 +112,7 @@ public:
 	const Node* getHierarchy() const { return m_hierarchy.data(); }
 	const uint32_t* getHierarchyParents() const { return m_hierarchyParents.data(); }
 	const Box* getHierarchyAABoxes() const { return m_aaBoxes.data(); }
+	const OBox* getHierarchyOBoxes() const { return m_oBoxes.empty() ? nullptr : m_oBoxes.data(); }
 	const UVec4* getLeafNodes() const { return m_hierarchyLeaves.data(); }
 	uint32_t getNumTrianglesPerLeaf() const { return m_numTrianglesPerLeaf; }
 	const Box& getBoundingBox() const { return m_boundingBox; }
@@ -123,6 +126,11 @@ public:
 	void buildHierarchy(BuildMethod method);
 	/// Chunk::computeBVHAABoxes (bim_hierarchy.cpp:45-50)
 	void computeBVHAABoxes();
+	/// Chunk::computeBVHOBoxes (bim_hierarchy.cpp:54-96): one oriented box per node around all vertices below it, same recursion.
+	/// The reference fits each box by brute force over all vertex triples (ei::OBox(points, n), O(n^4) on the convex set); here the
+	/// orientation is the principal-axis frame of the vertices and the extent is ei::OBox(orientation, points, n) (3dtypes.cpp:205-225).
+	/// Files written by the reference's tools carry their own boxes and are used as stored.
+	void computeBVHOBoxes();
 
 private:
 	friend class BinaryModel;
@@ -136,6 +144,7 @@ private:
 	std::vector<uint32_t> m_hierarchyParents;
 	std::vector<UVec4> m_hierarchyLeaves;
 	std::vector<Box> m_aaBoxes;
+	std::vector<OBox> m_oBoxes;
 	uint32_t m_numTrianglesPerLeaf = 2; // bim.cpp:14; BinaryModel::setNumTrianglesPerLeaf is a no-op (bim.hpp:91)
 	uint32_t m_numTreeLevels = 0;
 

@@ -45,6 +45,12 @@ GihScene* gih_scene_load(const char* json_path, int bvh_type)
 GihScene* gih_scene_from_mesh(const float* positions, const float* normals, const float* texcoords, uint32_t num_vertices, const uint32_t* triangles,
                               const uint32_t* tri_materials, uint32_t num_triangles, const char* env_json, const char* texture_dir, int build_method)
 {
+	return gih_scene_from_mesh_bvh(positions, normals, texcoords, num_vertices, triangles, tri_materials, num_triangles, env_json, texture_dir, build_method, 0);
+}
+
+GihScene* gih_scene_from_mesh_bvh(const float* positions, const float* normals, const float* texcoords, uint32_t num_vertices, const uint32_t* triangles,
+                                  const uint32_t* tri_materials, uint32_t num_triangles, const char* env_json, const char* texture_dir, int build_method, int bvh_type)
+{
 	gi::LastHostError().clear();
 	std::unique_ptr<BinaryModel> model(new BinaryModel());
 	std::string err;
@@ -56,7 +62,7 @@ GihScene* gih_scene_from_mesh(const float* positions, const float* normals, cons
 	model->chunk().buildHierarchy(build_method == 1 ? Chunk::BuildMethod::KD_TREE : Chunk::BuildMethod::SAH);
 	model->chunk().computeBVHAABoxes();
 	std::unique_ptr<GihScene> h(new GihScene());
-	h->scene = std::make_shared<Scene>(std::move(model), texture_dir ? texture_dir : "", ei::Types3D::BOX);
+	h->scene = std::make_shared<Scene>(std::move(model), texture_dir ? texture_dir : "", bvh_type == 0 ? ei::Types3D::BOX : ei::Types3D::OBOX);
 	if (!h->scene->IsValid()) return nullptr;
 	return h.release();
 }

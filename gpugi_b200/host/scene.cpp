@@ -39,9 +39,9 @@ Scene::~Scene() {}
 
 void Scene::Init()
 {
-	if (m_bvhType != ei::Types3D::BOX)
+	if (m_bvhType != ei::Types3D::BOX && m_bvhType != ei::Types3D::OBOX)
 	{
-		LOG_ERROR("Only the AABox BVH (bvhType=0) is supported; oriented boxes are a next-row item (SURVEY 8f-2).");
+		LOG_ERROR("Only AABox (bvhType=0) and OBox (bvhType=1) hierarchies exist (scene.cpp:95-118).");
 		return;
 	}
 	Chunk& chunk = m_model->chunk();
@@ -51,6 +51,8 @@ void Scene::Init()
 		chunk.buildHierarchy(Chunk::BuildMethod::SAH);
 	if (!(chunk.getProperties() & Property::AABOX_BVH) || chunk.getHierarchyAABoxes() == nullptr)
 		chunk.computeBVHAABoxes();
+	if (m_bvhType == ei::Types3D::OBOX && (!(chunk.getProperties() & Property::OBOX_BVH) || chunk.getHierarchyOBoxes() == nullptr))
+		chunk.computeBVHOBoxes();
 	UploadGeometry();
 	UploadHierarchy(m_bvhType);
 	for (uint32_t i = 0; i < m_model->getNumUsedMaterials(); ++i)
@@ -111,9 +113,25 @@ void Scene::UploadGeometry()
 }
 
 // scene.cpp:92-130 (AABox branch; written through resize())
-void Scene::UploadHierarchy(ei::Types3D)
+void Scene::UploadHierarchy(ei::Types3D _bvhType)
 {
 	const Chunk& chunk = m_model->chunk();
+	m_oboxHierarchy.clear();
+	if (_bvhType == ei::Types3D::OBOX)
+	{
+		// scene.cpp:107-118: center, sidesHalf, rotationInv = conjugate(orientation) + the tree pointers
+		m_oboxHierarchy.resize(chunk.getNumNodes());
+		for (uint32_t i = 0; i < chunk.getNumNodes(); ++i)
+		{
+			const gi::bim::OBox& b = chunk.getHierarchyOBoxes()[i];
+			GiOBoxNode& n = m_oboxHierarchy[i];
+			n.center[0] = b.center.x; n.center[1] = b.center.y; n.center[2] = b.center.z;
+			n.sides_half[0] = b.halfSides.x; n.sides_half[1] = b.halfSides.y; n.sides_half[2] = b.halfSides.z;
+			n.rotation_inv[0] = -b.orientation.i; n.rotation_inv[1] = -b.orientation.j; n.rotation_inv[2] = -b.orientation.k; n.rotation_inv[3] = b.orientation.r;
+			n.escape = chunk.getHierarchy()[i].escape;
+			n.first_child = chunk.getHierarchy()[i].firstChild;
+		}
+	}
 	m_hierarchy.resize(chunk.getNumNodes());
 	for (uint32_t i = 0; i < chunk.getNumNodes(); ++i)
 	{
@@ -347,5 +365,6 @@ GiSceneDesc Scene::GetSceneDesc() const
 	d.materials = m_materials.data(); d.num_materials = uint32_t(m_materials.size());
 	d.textures = m_textures.data(); d.num_textures = uint32_t(m_textures.size());
 	d.num_tree_levels = m_valid ? m_model->chunk().getNumTreeLevels() : 0;
+	d.obox_nodes = m_oboxHierarchy.empty() ? nullptr : m_oboxHierarchy.data();
 	return d;
 }

@@ -44,6 +44,7 @@ public:
 	const std::vector<GiVertexInfo>& GetVertexInfo() const { return m_vertexInfo; }
 	const std::vector<GiTriangle>& GetTriangles() const { return m_leafTriangles; }
 	const std::vector<GiNode>& GetHierarchy() const { return m_hierarchy; }
+	const std::vector<GiOBoxNode>& GetOBoxHierarchy() const { return m_oboxHierarchy; }
 	const std::vector<GiMaterial>& GetMaterials() const { return m_materials; }
 	/// Everything gi_upload_scene needs; pointers stay valid while the Scene lives.
 	GiSceneDesc GetSceneDesc() const;
@@ -84,6 +85,7 @@ private:
 	std::vector<GiVertexInfo> m_vertexInfo;
 	std::vector<GiTriangle> m_leafTriangles;
 	std::vector<GiNode> m_hierarchy;
+	std::vector<GiOBoxNode> m_oboxHierarchy; // bvhType = 1: TreeNode<ei::OBox> (scene.hpp:40-49), else empty
 
 	std::vector<LightTriangle> m_lightTriangles;
 	std::vector<PointLight> m_pointLights;

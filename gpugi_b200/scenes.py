@@ -216,7 +216,7 @@ def box1_materials():
     }
 
 
-def make_box1(tess=4, build_method="sah", coincident_faces=False):
+def make_box1(tess=4, build_method="sah", coincident_faces=False, bvh_type=0):
     """Closed room x in [-1.5,1.5], y in [0,3], z in [-3,2.3] + a white box, a glass box and two emissive quads.
     coincident_faces=True keeps the boxes' bottom faces, which lie exactly in the floor plane: a
     deliberate exact-tie case for the traversal parity tests."""
@@ -232,7 +232,7 @@ def make_box1(tess=4, build_method="sah", coincident_faces=False):
     mb.grid([0.35, 2.98, -1.9], [0.6, 0, 0], [0, 0, 0.6], 2, 2, M["LightR"])
     mb.grid([-0.95, 2.98, -1.9], [0.6, 0, 0], [0, 0, 0.6], 2, 2, M["LightL"])
     pos, nrm, uv, tri, mat = mb.arrays()
-    return Scene.from_mesh(pos, nrm, uv, tri, mat, box1_materials(), "", build_method)
+    return Scene.from_mesh(pos, nrm, uv, tri, mat, box1_materials(), "", build_method, bvh_type=bvh_type)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -347,7 +347,7 @@ def make_sponza_like(texture_dir, target_triangles=262144, texture_size=1024, nu
 # --------------------------------------------------------------------------------------------------
 
 
-def make_random_triangles(n, seed=0, extent=10.0, size=1.0, build_method="sah"):
+def make_random_triangles(n, seed=0, extent=10.0, size=1.0, build_method="sah", bvh_type=0):
     """n random triangles in a cube: the adversarial case for traversal parity (overlaps, slivers)."""
     rng = np.random.RandomState(seed)
     c = rng.uniform(-extent, extent, size=(n, 1, 3))
@@ -357,7 +357,7 @@ def make_random_triangles(n, seed=0, extent=10.0, size=1.0, build_method="sah"):
     tri = np.arange(3 * n, dtype=np.uint32).reshape(n, 3)
     mat = (np.arange(n) % 2).astype(np.uint32)
     mats = {"a": legacy_material((0.7, 0.7, 0.7)), "b": legacy_material((0.3, 0.5, 0.7), (0.04, 0.04, 0.04), 0.3)}
-    return Scene.from_mesh(p, nrm, uv, tri, mat, mats, "", build_method)
+    return Scene.from_mesh(p, nrm, uv, tri, mat, mats, "", build_method, bvh_type=bvh_type)
 
 
 def make_furnace(albedo=0.5, emission=1.0, tess=2):

@@ -110,6 +110,16 @@ typedef struct GiMaterial {
 /* Everything Scene::UploadGeometry / UploadHierarchy / LoadMaterial hand to GL
  * (scene.cpp:75-130,132-180) and RendererSystem::SetScene binds
  * (renderersystem.cpp:132-152).                                              */
+/* Scene::TreeNode<ei::OBox> (scene.hpp:40-49) as assembled by Scene::UploadHierarchy for bvhType = 1 (scene.cpp:107-118): three 16-byte
+ * texels per node, read by FetchIntersectOBoxNode (intersectiontests.glsl:114-128). */
+typedef struct GiOBoxNode {
+	float    center[3];
+	uint32_t first_child;      /* same coding as GiNode */
+	float    sides_half[3];
+	uint32_t escape;
+	float    rotation_inv[4];  /* conjugate(orientation), (x, y, z, w) */
+} GiOBoxNode;
+
 typedef struct GiSceneDesc {
 	const GiNode*       nodes;
 	uint32_t            num_nodes;
@@ -123,6 +133,9 @@ typedef struct GiSceneDesc {
 	const GiTexture*    textures;
 	uint32_t            num_textures;
 	uint32_t            num_tree_levels;     /* Chunk::getNumTreeLevels, 0 = unknown */
+	const GiOBoxNode*   obox_nodes;          /* bvhType = 1 (OBOX_BVH): num_nodes oriented boxes, tested INSTEAD of the AABoxes of `nodes`
+	                                            (which stay mandatory: upload validation and the leaf records use them); the walk is then
+	                                            always the reference-order one.  NULL = bvhType 0. */
 } GiSceneDesc;
 
 /* Camera UBO, gpugi/shader/globaluniforms.glsl:7-15, filled by

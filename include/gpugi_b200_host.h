@@ -38,6 +38,10 @@ GI_API GihScene* gih_scene_load(const char* json_path, int bvh_type);
 GI_API GihScene* gih_scene_from_mesh(const float* positions, const float* normals, const float* texcoords, uint32_t num_vertices,
                                      const uint32_t* triangles, const uint32_t* tri_materials, uint32_t num_triangles, const char* env_json,
                                      const char* texture_dir, int build_method);
+/* same with bvh_type: 0 = AABoxes, 1 = OBoxes (GlobalConfig "bvhType", application.cpp:136; oriented boxes are fitted by Chunk::computeBVHOBoxes) */
+GI_API GihScene* gih_scene_from_mesh_bvh(const float* positions, const float* normals, const float* texcoords, uint32_t num_vertices,
+                                     const uint32_t* triangles, const uint32_t* tri_materials, uint32_t num_triangles, const char* env_json,
+                                     const char* texture_dir, int build_method, int bvh_type);
 GI_API void gih_scene_destroy(GihScene* s);
 /* BinaryModel::storeEnvironmentFile/storeBinaryHeader/storeChunk: writes <json_path> and <dir>/<bim_name>. */
 GI_API int gih_scene_store(GihScene* s, const char* json_path, const char* bim_name);

@@ -166,6 +166,7 @@ struct Texture
 struct Scene
 {
 	const GiNode* nodes;
+	const GiOBoxNode* oboxNodes; // bvhType = 1 (Scene::TreeNode<ei::OBox>), else null
 	uint32_t numNodes;
 	const GiTriangle* leafTris;
 	uint32_t numLeafTris;
@@ -196,6 +197,7 @@ Scene makeScene(const GiSceneDesc* d)
 	initSrgb();
 	Scene s;
 	s.nodes = d->nodes; s.numNodes = d->num_nodes;
+	s.oboxNodes = d->obox_nodes;
 	s.leafTris = d->leaf_triangles; s.numLeafTris = d->num_leaf_triangles;
 	s.positions = d->positions; s.vinfo = d->vertex_info; s.numVertices = d->num_vertices;
 	s.materials = d->materials; s.numMaterials = d->num_materials;
@@ -282,6 +284,35 @@ inline bool IntersectTriangle(const Ray& ray, V3 p0, V3 p1, V3 p2, float& hit, V
 
 struct TraceCounters { uint64_t boxes, tris; };
 
+// intersectiontests.glsl:82-88
+inline V3 rotate(V3 x, const float q[4])
+{
+	V3 t = cross(v3(q[0], q[1], q[2]), x);
+	return x + 2.0f * v3(q[3] * t.x + q[1] * t.z - q[2] * t.y,
+	                     q[3] * t.y + q[2] * t.x - q[0] * t.z,
+	                     q[3] * t.z + q[0] * t.y - q[1] * t.x);
+}
+
+// FetchIntersectBoxNode (intersectiontests.glsl:100-111) / FetchIntersectOBoxNode (:114-128), selected by the scene's bvhType
+// (the AABOX_BVH / OBOX_BVH define of traceray.glsl:62-66)
+inline bool FetchIntersectNode(const Scene& s, const Ray& ray, V3 invRayDir, int nodeIdx, float& firstHit, float& lastHit, uint32_t& childCode, int& escape)
+{
+	if (s.oboxNodes)
+	{
+		const GiOBoxNode& n = s.oboxNodes[nodeIdx];
+		childCode = n.first_child;
+		escape = int(n.escape);
+		V3 bbSidesHalf = v3(n.sides_half);
+		V3 rayOrigin = rotate(ray.Origin - v3(n.center), n.rotation_inv);
+		V3 rayDir = rotate(ray.Direction, n.rotation_inv);
+		return IntersectBox(rayOrigin, v3(1.0f) / rayDir, -bbSidesHalf, bbSidesHalf, firstHit, lastHit);
+	}
+	const GiNode& n = s.nodes[nodeIdx];
+	childCode = n.first_child;
+	escape = int(n.escape);
+	return IntersectBox(ray.Origin, invRayDir, v3(n.min), v3(n.max), firstHit, lastHit);
+}
+
 inline uint32_t fbits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 
 // traceray.glsl:25-180 without ANY_HIT; HIT_INDEX_OUTPUT + TRINORMAL_OUTPUT always on.
@@ -300,11 +331,9 @@ void TraceRay(const Scene& s, const Ray& ray, float& rayLength, int hitIndex[2],
 		{
 			if (cnt) ++cnt->boxes;
 			float newHit, exitDist;
-			// FetchIntersectBoxNode, intersectiontests.glsl:100-111
-			const GiNode& n = s.nodes[currentNodeIndex];
-			uint32_t childCode = n.first_child;
-			int escape = int(n.escape);
-			if (IntersectBox(ray.Origin, invRayDir, v3(n.min), v3(n.max), newHit, exitDist) && newHit <= rayLength)
+			uint32_t childCode;
+			int escape;
+			if (FetchIntersectNode(s, ray, invRayDir, currentNodeIndex, newHit, exitDist, childCode, escape) && newHit <= rayLength)
 			{
 				lastNodeIndex = currentNodeIndex;
 				currentNodeIndex = int(childCode & 0x7FFFFFFFu);
@@ -359,10 +388,9 @@ bool TraceRayAnyHit(const Scene& s, const Ray& ray, float rayLength, TraceCounte
 		{
 			if (cnt) ++cnt->boxes;
 			float newHit, exitDist;
-			const GiNode& n = s.nodes[currentNodeIndex];
-			uint32_t childCode = n.first_child;
-			int escape = int(n.escape);
-			if (IntersectBox(ray.Origin, invRayDir, v3(n.min), v3(n.max), newHit, exitDist) && newHit <= rayLength)
+			uint32_t childCode;
+			int escape;
+			if (FetchIntersectNode(s, ray, invRayDir, currentNodeIndex, newHit, exitDist, childCode, escape) && newHit <= rayLength)
 			{
 				currentNodeIndex = int(childCode & 0x7FFFFFFFu);
 				nextIsLeafNode = uint32_t(currentNodeIndex) != childCode;

@@ -27,6 +27,7 @@ bool makeScene(const GiSceneDesc* d, EmScene& e, std::string& err)
 	if (!buildHostLayout(d, e.L, err)) return false;
 	e.s = e.L.scene;
 	e.s.refNodes = e.L.refNodes.data();
+	e.s.oboxNodes = e.L.oboxNodes.empty() ? nullptr : e.L.oboxNodes.data();
 	e.s.fastNodes = e.L.fastNodes.data();
 	e.s.qNodes = e.L.qNodes.data();
 	e.s.leafPos = e.L.leafPos.data();

@@ -329,3 +329,51 @@ def test_layout_rejects_bad_scenes(g, emul, box1):
     badn = nodes.copy(); badn["first_child"][0] = d.num_nodes + 5
     with pytest.raises(RuntimeError):
         emul.trace(with_arrays(badn, lt), rays)
+
+
+def test_obox_hierarchy_traversal(g, orc, emul, scenes, tmp_path):
+    """bvhType = 1: FetchIntersectOBoxNode (intersectiontests.glsl:114-128) in the reference-order walk.  The product's
+    device logic (host build) equals the oracle bit for bit on an oriented-box hierarchy; the boxes contain their geometry, so the hits
+    equal those of the AABox hierarchy of the same tree; the OBOX_BVH section survives a .bim round trip."""
+    sc0 = scenes.make_random_triangles(400, seed=5)
+    sc1 = scenes.make_random_triangles(400, seed=5, bvh_type=1)
+    ob, nodes = sc1.obox_nodes(), sc1.nodes()
+    assert sc0.obox_nodes() is None and ob.shape[0] == nodes.shape[0]
+    assert np.array_equal(ob["first_child"], nodes["first_child"]) and np.array_equal(ob["escape"], nodes["escape"])
+    assert np.allclose(np.linalg.norm(ob["rotation_inv"], axis=1), 1.0, atol=1e-5) and (ob["sides_half"] >= 0).all()
+
+    def rotate(x, q):  # intersectiontests.glsl:82-88
+        t = np.cross(q[:3], x)
+        return x + 2 * np.stack([q[3] * t[:, 0] + q[1] * t[:, 2] - q[2] * t[:, 1], q[3] * t[:, 1] + q[2] * t[:, 0] - q[0] * t[:, 2],
+                                 q[3] * t[:, 2] + q[0] * t[:, 1] - q[1] * t[:, 0]], 1)
+    P = sc1.positions().astype(np.float64)
+    # the root box holds every vertex; every leaf box holds the vertices of its triangles
+    assert (np.abs(rotate(P - ob[0]["center"], ob[0]["rotation_inv"].astype(np.float64))) <= ob[0]["sides_half"] * (1 + 1e-6) + 1e-6).all()
+    lt = sc1.leaf_triangles()
+    for i in np.nonzero(nodes["first_child"] & 0x80000000)[0][:200]:
+        leaf = int(nodes["first_child"][i] & 0x7fffffff)
+        for t in lt[2 * leaf: 2 * leaf + 2]:
+            if t["v"][0] == t["v"][1]:
+                break
+            local = rotate(P[t["v"]] - ob[i]["center"], ob[i]["rotation_inv"].astype(np.float64))
+            assert (np.abs(local) <= ob[i]["sides_half"] * (1 + 1e-6) + 1e-6).all()
+    rng = np.random.RandomState(2)
+    rays = np.zeros(30000, dtype=g.RAY_DTYPE)
+    rays["origin"] = rng.uniform(-12, 12, (30000, 3))
+    d = rng.randn(30000, 3)
+    rays["direction"] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    rays["t_max"] = g.RAY_MAX
+    rays["flags"][:8000] = 1
+    rays["t_max"][:8000] = rng.rand(8000) * 20
+    ref = orc.trace_batch(sc1.desc, rays)
+    for mode in (0, 1, 2):  # fast / lane requests fall back to the reference-order walk: the ordered walk is built on AABoxes
+        hits, cnt = emul.trace(sc1.desc, rays, mode=mode)
+        assert cnt["fast_valid"] == 0
+        assert np.array_equal(hits["leaf_tri"], ref["leaf_tri"]) and np.array_equal(hits["t"].view(np.uint32), ref["t"].view(np.uint32))
+    aabox = orc.trace_batch(sc0.desc, rays)
+    assert (aabox["leaf_tri"] == ref["leaf_tri"]).mean() > 0.9995
+    # .bim round trip (OBOX_BVH = 0x02000000, 40-byte ei::OBox elements)
+    sc1.store(str(tmp_path / "ob.json"), "ob.bim")
+    sc2 = g.Scene.load(str(tmp_path / "ob.json"), bvh_type=1)
+    assert sc2.obox_nodes().tobytes() == ob.tobytes()
+    assert g.Scene.load(str(tmp_path / "ob.json"), bvh_type=0).obox_nodes() is None

@@ -173,3 +173,45 @@ def test_error_behaviour(g, dev, box1):
     with pytest.raises(g.GpugiError):
         g.Device(99)
     d.close()
+
+
+def test_obox_hierarchy_on_device(g, orc, scenes):
+    """bvhType = 1: the oriented-box walk on the GPU (gi_trace, both schedulers) equals the oracle bit for bit, and a PT iteration on the
+    OBox hierarchy matches the oracle's and -- the boxes being conservative -- the AABox image of the same tree."""
+    sc = scenes.make_random_triangles(3000, seed=9, extent=6.0, size=1.2, bvh_type=1)
+    rng = np.random.RandomState(4)
+    n = 200000
+    rays = np.zeros(n, dtype=g.RAY_DTYPE)
+    rays["origin"] = rng.uniform(-8, 8, (n, 3))
+    d = rng.randn(n, 3)
+    rays["direction"] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    rays["t_max"] = g.RAY_MAX
+    rays["flags"][: n // 4] = 1
+    rays["t_max"][: n // 4] = rng.rand(n // 4) * 12
+    ref = orc.trace_batch(sc.desc, rays)
+    dev = g.Device(0)
+    dev.upload_scene(sc)
+    for sched in (g.GI_SCHEDULER_WAVEFRONT, g.GI_SCHEDULER_MEGAKERNEL):
+        dev.set_option(g.GI_OPT_SCHEDULER, sched)
+        hits = dev.trace(rays)
+        assert np.array_equal(hits["leaf_tri"], ref["leaf_tri"])
+        assert np.array_equal(hits["t"].view(np.uint32), ref["t"].view(np.uint32))
+    dev.close()
+    from tests.conftest import pixel_mismatch_fraction
+    imgs = {}
+    for bvh in (0, 1):
+        box = scenes.make_box1(tess=4, bvh_type=bvh)
+        W = H = 128
+        rs = g.RendererSystem(0)
+        rs.SetScene(box); rs.SetScreenSize(W, H)
+        C = scenes.BOX1_CAMERA
+        rs.SetCamera(C["pos"], C["lookat"], C["fov"]); rs.SetRenderer("PT")
+        rs.device.set_option(g.GI_OPT_TEXTURE_FILTER, 1)
+        samples, seed, cam = rs.GetInitialLightSamples(), rs.GetFrameSeed(), rs.GetCamera()
+        rs.Draw()
+        imgs[bvh] = rs.ReadBackbuffer()
+        if bvh == 1:
+            ref_img, _ = orc.render_pt(box.desc, cam, W, H, samples, seed, 16)
+            assert pixel_mismatch_fraction(imgs[1], ref_img, 1e-2) < 0.02
+        rs.close()
+    assert pixel_mismatch_fraction(imgs[1], imgs[0], 1e-2) < 0.01
