@@ -317,6 +317,18 @@ struct WfRun
 	WfFrame w;
 };
 
+// pipelined BPT (renderPipelinedBPT / streaming Draw of the bidirectional path tracer)
+struct BptPipe
+{
+	bool open = false, streaming = false;
+	uint32_t count = 0;      // iterations submitted
+	uint32_t wave = 0;       // next global wave
+	uint32_t expected = 0;   // batch: total iterations
+	uint32_t ring = 0, D = 0, maxLen = 0, capacity = 0, numLightPaths = 0;
+	int numRaysPerLightSample = 0;
+	std::vector<uint32_t> seeds; // FrameSeed of iteration k at [k % size]: its eye pass starts D waves later
+};
+
 struct GiContext
 {
 	int device = 0;
@@ -370,6 +382,7 @@ struct GiContext
 	WfTune tune = {24, 16, 0};     // B200 sweep (tools/gpu/run_variants.sh TUNES=...): refill:minInner 16:20 2.191, 24:20 2.153, 24:16 2.126, 28:16 2.143, 32:16 2.222 ms/iteration
 
 	// wavefront queues
+	BptPipe bpt;
 	WfRun run[2];                    // [0]: PT / LPT / BPT light pass / stream, [1]: BPT eye pass of a pipelined batch
 	int streamingOption = 0;         // GI_OPT_STREAMING
 	uint32_t lightSlot = 0;          // ring slot of the light-sample set the next iteration uses
@@ -663,9 +676,12 @@ static int wfClose(GiContext* c, int set, bool drain = true)
 	return GI_OK;
 }
 
+static int bptClose(GiContext* c);
+
 // an open stream must be drained before anything reads or redefines what its iterations depend on
 static int flushStream(GiContext* c)
 {
+	if (c && c->bpt.open && c->bpt.streaming) return bptClose(c);
 	if (c && c->run[0].open && c->run[0].streaming) return wfClose(c, 0);
 	return GI_OK;
 }
@@ -690,11 +706,13 @@ static int renderWavefront(GiContext* c, const DFrame& f, int pass, uint32_t lig
 // NumLightCacheEntries counter) are alive at a time: a ring in HBM (C3 at 1080p: 32 x 0.4 GB).  Every wave then has the
 // same amount of work and the per-iteration tails of both passes are paid once per batch.  Returns GI_ERR_CAPACITY without
 // having rendered anything when the ring does not fit the free device memory (the caller then renders one by one).
-static int renderPipelinedBPT(GiContext* c, const GiIterationParams* p, const uint32_t* seeds, uint32_t count, uint32_t lightStride)
+// bptOpen: allocate the ring (expectedCount = 0: a stream, which always needs the full 2 D caches) and open both runs.
+static int bptOpen(GiContext* c, const GiIterationParams* p, uint32_t expectedCount, uint32_t lightStride, uint32_t lightBase, uint32_t lightRing)
 {
+	BptPipe& b = c->bpt;
+	const bool streaming = expectedCount == 0u;
 	const uint32_t maxLen = uint32_t(p->max_path_length);
-	const uint32_t D = maxLen;
-	const uint32_t ring = std::min(count, 2u * maxLen);
+	const uint32_t ring = streaming ? 2u * maxLen : std::min(expectedCount, 2u * maxLen);
 	const uint32_t capacity = uint32_t(p->light_cache_capacity);
 	const uint32_t numLightPaths = uint32_t(c->numLightSamples) * uint32_t(p->num_rays_per_light_sample);
 	const uint64_t entries = uint64_t(ring) * capacity;
@@ -719,41 +737,84 @@ static int renderPipelinedBPT(GiContext* c, const GiIterationParams* p, const ui
 		c->ringCountersLen = 2u * ring;
 	}
 	DFrame f = makeFrame(c, p);
+	if (streaming) f.lightSamples = c->lightSamples; // ring base (see gi_render_iteration)
 	f.lightCache = c->cacheRing;
 	f.lightCacheCapacity = capacity;
 	f.lightCacheCount = c->ringCounters;
 	f.lightPathLengthSum = c->ringCounters + 1;
 	f.cacheRing = ring;
-	int st = wfOpen(c, 0, f, WF_PASS_LIGHT, WF_LIGHT_SAVE, count, false, lightStride, 0u, 0u);
-	if (st == GI_OK) st = wfOpen(c, 1, f, WF_PASS_EYE, 0u, count, false, 0u, 0u, 0u);
+	int st = wfOpen(c, 0, f, WF_PASS_LIGHT, WF_LIGHT_SAVE, expectedCount, streaming, lightStride, lightBase, lightRing);
+	if (st == GI_OK) st = wfOpen(c, 1, f, WF_PASS_EYE, 0u, expectedCount, streaming, 0u, 0u, 0u);
 	if (st != GI_OK) { c->run[0].open = c->run[1].open = false; return st; }
-	const uint32_t runWaves = count + maxLen; // waves of one run; its last wave carries shadow rays only
-	for (uint32_t w = 0; w < runWaves + D && st == GI_OK; ++w)
+	b.open = true; b.streaming = streaming;
+	b.count = 0; b.wave = 0; b.expected = expectedCount;
+	b.ring = ring; b.D = maxLen; b.maxLen = maxLen; b.capacity = capacity; b.numLightPaths = numLightPaths;
+	b.numRaysPerLightSample = p->num_rays_per_light_sample;
+	b.seeds.assign(size_t(maxLen) + 2u, 0u);
+	return GI_OK;
+}
+
+// One global wave.  submit: a new iteration (FrameSeed `seed`) starts its light pass in this wave; otherwise the wave belongs to the
+// drain of a pipeline that got `finalCount` iterations.
+static int bptWave(GiContext* c, bool submit, uint32_t seed)
+{
+	BptPipe& b = c->bpt;
+	const uint32_t w = b.wave, D = b.D, maxLen = b.maxLen;
+	if (submit) { b.seeds[b.count % b.seeds.size()] = seed; ++b.count; }
+	const uint32_t C = submit ? (b.streaming ? 0xffffffffu : b.expected) : b.count; // total iterations, if known
+	const uint32_t runWaves = C == 0xffffffffu ? 0xffffffffu : C + maxLen;           // waves of one run; its last wave carries shadow rays only
+	int st = GI_OK;
+	if (w < runWaves)
 	{
-		if (w < runWaves)
+		if (submit)
 		{
-			if (w < count)
-			{
-				// resetcounter.comp for the cache of iteration w (bidirectionalpathtracer.cpp:190)
-				const uint32_t slot = w % ring;
-				k_reset_counter<<<1, 1, 0, c->stream>>>(c->ringCounters + 2u * slot, c->ringCounters + 2u * slot + 1u, numLightPaths);
-				++c->launches;
-			}
-			st = wfStep(c, 0, w < count, w < count ? seeds[w] : 0u, w + 1u < count, w + 1u < runWaves);
+			// resetcounter.comp for the cache of this iteration (bidirectionalpathtracer.cpp:190)
+			const uint32_t slot = w % b.ring;
+			k_reset_counter<<<1, 1, 0, c->stream>>>(c->ringCounters + 2u * slot, c->ringCounters + 2u * slot + 1u, b.numLightPaths);
+			++c->launches;
 		}
-		if (st == GI_OK && w >= D)
-		{
-			const uint32_t e = w - D;
-			st = wfStep(c, 1, e < count, e < count ? seeds[e] : 0u, e + 1u < count, e + 1u < runWaves);
-		}
+		st = wfStep(c, 0, submit, seed, submit && w + 1u < C, runWaves == 0xffffffffu || w + 1u < runWaves);
+	}
+	if (st == GI_OK && w >= D)
+	{
+		const uint32_t e = w - D; // the eye pass of iteration e starts D waves after its light pass
+		const bool gen = e < b.count;
+		if (gen || e < runWaves)
+			st = wfStep(c, 1, gen, gen ? b.seeds[e % b.seeds.size()] : 0u, e + 1u < (C == 0xffffffffu ? b.count + 1u : C), runWaves == 0xffffffffu || e + 1u < runWaves);
+	}
+	++b.wave;
+	return st;
+}
+
+// Drain (maxPathLength + D more waves), fold, publish the last iteration's counters.
+static int bptClose(GiContext* c)
+{
+	BptPipe& b = c->bpt;
+	if (!b.open) return GI_OK;
+	int st = GI_OK;
+	if (b.count > 0)
+	{
+		const uint32_t end = b.count + b.maxLen + b.D;
+		while (st == GI_OK && b.wave < end) st = bptWave(c, false, 0u);
 	}
 	if (st == GI_OK) st = wfClose(c, 0, false);
 	if (st == GI_OK) st = wfClose(c, 1, false);
 	c->run[0].open = c->run[1].open = false;
+	b.open = false;
 	if (st != GI_OK) return st;
-	// GiCounters::light_cache_entries / light_path_length_sum report the last iteration
-	GI_CUDA(c, cudaMemcpyAsync(c->bptCounters, c->ringCounters + 2u * ((count - 1u) % ring), 2 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
+	if (b.count > 0)
+		GI_CUDA(c, cudaMemcpyAsync(c->bptCounters, c->ringCounters + 2u * ((b.count - 1u) % b.ring), 2 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
 	return GI_OK;
+}
+
+static int renderPipelinedBPT(GiContext* c, const GiIterationParams* p, const uint32_t* seeds, uint32_t count, uint32_t lightStride)
+{
+	int st = bptOpen(c, p, count, lightStride, 0u, 0u);
+	if (st != GI_OK) return st;
+	for (uint32_t k = 0; st == GI_OK && k < count; ++k) st = bptWave(c, true, seeds[k]);
+	if (st == GI_OK) st = bptClose(c);
+	c->bpt.open = false; c->run[0].open = c->run[1].open = false;
+	return st;
 }
 
 
@@ -1112,12 +1173,12 @@ int gi_render_iteration(GiContext* c, const GiIterationParams* p)
 	if (st != GI_OK) return st;
 	if (p->max_path_length <= 0) return fail(c, GI_ERR_INVALID, "max_path_length must be positive");
 	GI_CUDA(c, cudaSetDevice(c->device));
-	if (c->streamingOption && p->renderer == GI_RENDERER_PT && c->scheduler == GI_SCHEDULER_WAVEFRONT && !c->externalLightSamples &&
-	    uint32_t(p->max_path_length) + 1u <= GI_LIGHT_RING)
+	const bool canStream = c->streamingOption && c->scheduler == GI_SCHEDULER_WAVEFRONT && !c->externalLightSamples && uint32_t(p->max_path_length) + 1u <= GI_LIGHT_RING;
+	if (canStream && p->renderer == GI_RENDERER_PT)
 	{
 		// GI_OPT_STREAMING: this iteration is one more wave of the open run (opened here if there is none)
 		WfRun& r = c->run[0];
-		if (r.open && r.streaming && (r.renderer != p->renderer || r.maxLen != uint32_t(p->max_path_length)))
+		if (c->bpt.open || (r.open && r.streaming && (r.renderer != p->renderer || r.maxLen != uint32_t(p->max_path_length))))
 		{
 			st = flushStream(c);
 			if (st != GI_OK) return st;
@@ -1134,6 +1195,31 @@ int gi_render_iteration(GiContext* c, const GiIterationParams* p)
 		if (st != GI_OK) return st;
 		GI_CUDA(c, cudaGetLastError());
 		return GI_OK;
+	}
+	if (canStream && p->renderer == GI_RENDERER_BPT && !p->warmup && p->num_rays_per_light_sample > 0 && p->light_cache_capacity > 0 &&
+	    uint64_t(p->light_cache_capacity) >= uint64_t(c->numLightSamples) * uint64_t(p->num_rays_per_light_sample))
+	{
+		// streaming BPT: one global wave of the light / eye pipeline per call (renderPipelinedBPT's schedule, kept open)
+		BptPipe& b = c->bpt;
+		if ((c->run[0].open && c->run[0].streaming && !b.open) ||
+		    (b.open && (b.maxLen != uint32_t(p->max_path_length) || b.capacity != uint32_t(p->light_cache_capacity) || b.numRaysPerLightSample != p->num_rays_per_light_sample)))
+		{
+			st = flushStream(c);
+			if (st != GI_OK) return st;
+		}
+		if (!b.open)
+		{
+			st = bptOpen(c, p, 0u, 2u * uint32_t(c->numLightSamples), c->lightSlot, GI_LIGHT_RING);
+			if (st != GI_OK && st != GI_ERR_CAPACITY) return st;
+		}
+		if (b.open)
+		{
+			st = bptWave(c, true, p->frame_seed);
+			if (st != GI_OK) return st;
+			GI_CUDA(c, cudaGetLastError());
+			return GI_OK;
+		}
+		// the ring does not fit: one iteration at a time, below
 	}
 	st = flushStream(c);
 	if (st != GI_OK) return st;
@@ -1385,7 +1471,11 @@ int gi_read_accumulator_async(GiContext* c, float* rgba, uint32_t* iterations_in
 	GI_CUDA(c, cudaEventRecord(c->snapCopied[i], c->copyStream));
 	c->snapUsed[i] = true;
 	// PT stream: iteration k joins the accumulator when its state slot is recycled, maxPathLength + 1 waves after it started
-	if (iterations_in_flight) *iterations_in_flight = (c->run[0].open && c->run[0].streaming) ? std::min(c->run[0].count, c->run[0].numSlots) : 0u;
+	if (iterations_in_flight)
+	{
+		if (c->bpt.open && c->bpt.streaming) *iterations_in_flight = std::min(c->bpt.count, c->bpt.D + c->bpt.maxLen + 1u); // eye pass starts D waves late
+		else *iterations_in_flight = (c->run[0].open && c->run[0].streaming) ? std::min(c->run[0].count, c->run[0].numSlots) : 0u;
+	}
 	return GI_OK;
 }
 

@@ -188,14 +188,17 @@ enum {
 	                                   stream and sum the durations per kernel class (gi_get_kernel_times); setting the option
 	                                   clears the sums.  The iteration call then synchronises -- measurement passes only.
 	                                   Replaces the reference's glFinish + clock() pair (renderersystem.cpp:249-255). */
-	GI_OPT_STREAMING = 9            /* 1 = consecutive gi_render_iteration(GI_RENDERER_PT) calls form a STREAM: each call submits one
+	GI_OPT_STREAMING = 9            /* 1 = consecutive gi_render_iteration(GI_RENDERER_PT or _BPT) calls form a STREAM: each call submits one
 	                                   wave (generate + trace + shade) of a run that stays open, so the bounces of up to
 	                                   max_path_length + 1 iterations share every wave exactly as in gi_render_iterations -- the
 	                                   reference's one-Draw()-per-iteration loop (renderersystem.cpp:246-256) without its
 	                                   per-iteration tail.  Any call that reads or redefines state (gi_read_accumulator,
 	                                   gi_synchronize, gi_set_camera, gi_clear_accumulator, gi_get_counters, ...) drains the
 	                                   stream first, after which the accumulator equals the one of the same iterations rendered
-	                                   one by one, bit for bit.  gi_read_accumulator_async does NOT drain. */
+	                                   one by one, bit for bit (PT; BPT: as for a pipelined batch, up to the scheduling-dependent order of
+	                                   light-cache slots, and 2 x max_path_length + 1 iterations deep over a ring of light caches; one
+	                                   iteration at a time if the ring does not fit the device memory).  gi_read_accumulator_async
+	                                   does NOT drain. */
 };
 /* kernel classes of gi_get_kernel_times */
 enum {

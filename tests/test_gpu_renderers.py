@@ -565,3 +565,34 @@ def test_script_front_end_runs_a_reference_style_script(g, scenes, box1, tmp_pat
     cli = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpugi_b200", "gpugi_b200_cli")
     out = subprocess.run([cli, str(script)], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "Wrote screenshot" in out.stdout, out.stdout + out.stderr
+
+
+def test_streaming_bidirectional(g, scenes, box1):
+    """GI_OPT_STREAMING for the bidirectional path tracer: Draw() submits one global wave of the light / eye pipeline (the eye pass of an
+    iteration starts pathLength waves after its light pass, on its own cache of the ring).  After the drain: alpha == iterations, every
+    deterministic counter equals plain Draw() calls, the images agree statistically; the asynchronous read reports the pipeline depth."""
+    import torch
+    W = H = 96
+    N, path_length = 40, 16
+    out = {}
+    for streaming in (False, True):
+        rs = _rs(g, scenes, box1, "BPT", W, H)
+        rs.SetStreaming(streaming)
+        buf = torch.empty((H, W, 4), dtype=torch.float32, pin_memory=True).numpy()
+        rs.device.reset_counters()
+        for k in range(N):
+            rs.Draw()
+            if streaming and k in (0, 5, 36, 39):
+                assert rs.ReadBackbufferAsync(buf) == min(k + 1, 2 * path_length + 1)
+                rs.WaitReads()
+                assert np.all(buf[..., 3] == max(0, k + 1 - (2 * path_length + 1)))   # whole iterations only
+        img = rs.ReadBackbuffer()
+        out[streaming] = (img, rs.device.counters(), rs.GetRendererInfo())
+        assert rs.GetIterationCount() == N and np.all(img[..., 3] == N)
+        rs.close()
+    (a, ca, ia), (b, cb, ib) = out[False], out[True]
+    assert ia == ib
+    for k in ("light_paths", "camera_paths", "shaded_vertices", "closest_rays", "splats", "light_cache_entries"):
+        assert ca[k] == cb[k], k
+    mean_diff, med, p90 = robust_block_compare(b / N, a / N)
+    assert mean_diff < 0.05 and med < 0.15 and p90 < 0.5, (mean_diff, med, p90)
