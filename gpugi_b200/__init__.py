@@ -72,7 +72,8 @@ class Scene:
     @classmethod
     def from_mesh(cls, positions, normals, texcoords, triangles, tri_materials, materials, texture_dir="", build_method="sah", bvh_type=0):
         """Synthetic scene: mesh arrays + material dict (JSON 'materials' object, order = material index).
-        bvh_type 1: oriented boxes (the reference's second accelerator, GlobalConfig "bvhType")."""
+        bvh_type 1: oriented boxes (the reference's second accelerator, GlobalConfig "bvhType").
+        build_method: "sah" (bim_sahspilt.cpp sweep, host), "kd" (bim_kdtree.cpp median, host), "lbvh" (gi_build_hierarchy: on the GPU)."""
         positions = np.ascontiguousarray(positions, dtype=np.float32)
         normals = np.ascontiguousarray(normals, dtype=np.float32)
         texcoords = np.ascontiguousarray(texcoords, dtype=np.float32)
@@ -82,7 +83,7 @@ class Scene:
         assert triangles.shape[1] == 3 and tri_materials.shape[0] == triangles.shape[0]
         env = json.dumps({"scene": "", "accelerator": "obox" if bvh_type else "aabox", "materials": materials, "lights": {}, "cameras": {}})
         h = capi.host.gih_scene_from_mesh_bvh(_vp(positions), _vp(normals), _vp(texcoords), positions.shape[0], _vp(triangles), _vp(tri_materials),
-                                              triangles.shape[0], env.encode(), os.fsencode(texture_dir), 1 if build_method == "kd" else 0, int(bvh_type))
+                                              triangles.shape[0], env.encode(), os.fsencode(texture_dir), {"sah": 0, "kd": 1, "lbvh": 2}[build_method], int(bvh_type))
         if not h:
             raise GpugiError("Scene.from_mesh: " + capi.host.gih_last_error().decode())
         return cls(h)
@@ -245,6 +246,21 @@ class Device:
 
     def alloc_light_cache(self, capacity):
         self._check(capi.dev.gi_alloc_light_cache(self._c, int(capacity)), "gi_alloc_light_cache")
+
+    def build_hierarchy(self, positions, triangles, tri_materials=None):
+        """gi_build_hierarchy: LBVH on the device in the reference's layout -> (nodes, leaf_triangles, parents, num_tree_levels)."""
+        positions = np.ascontiguousarray(positions, dtype=np.float32)
+        triangles = np.ascontiguousarray(triangles, dtype=np.uint32)
+        mats = None if tri_materials is None else np.ascontiguousarray(tri_materials, dtype=np.uint32)
+        T = triangles.shape[0]
+        L = (T + 1) // 2
+        nodes = np.zeros(2 * L - 1, dtype=NODE_DTYPE)
+        leaves = np.zeros(2 * L, dtype=TRIANGLE_DTYPE)
+        parents = np.zeros(2 * L - 1, dtype=np.uint32)
+        n, lv = C.c_uint32(), C.c_uint32()
+        self._check(capi.dev.gi_build_hierarchy(self._c, _vp(positions), positions.shape[0], _vp(triangles), _vp(mats) if mats is not None else None, T,
+                                                _vp(nodes), _vp(leaves), _vp(parents), C.byref(n), C.byref(lv)), "gi_build_hierarchy")
+        return nodes[: n.value], leaves, parents[: n.value], lv.value
 
     def render_iteration(self, renderer, frame_seed, max_path_length=16, num_rays_per_light_sample=0, light_cache_capacity=0, warmup=0):
         p = capi.GiIterationParams(renderer=int(renderer), frame_seed=int(frame_seed) & 0xFFFFFFFF, max_path_length=int(max_path_length),

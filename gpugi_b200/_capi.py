@@ -146,6 +146,7 @@ DEVICE_API = {
     "gi_read_accumulator": (C.c_int, [vp, vp]),
     "gi_read_accumulator_async": (C.c_int, [vp, vp, P(u32)]),
     "gi_wait_reads": (C.c_int, [vp]),
+    "gi_build_hierarchy": (C.c_int, [vp, vp, u32, vp, vp, u32, vp, vp, vp, P(u32), P(u32)]),
     "gi_accumulator_device": (C.c_int, [vp, P(vp), P(C.c_size_t)]),
     "gi_compute_mse": (C.c_int, [vp, vp, u32, P(f32)]),
     "gi_get_counters": (C.c_int, [vp, P(GiCounters)]),

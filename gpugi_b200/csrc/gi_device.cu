@@ -5,6 +5,7 @@
 #include "gi_core.h"
 #include "gi_layout.h"
 #include "gi_wavefront.cuh"
+#include "gi_lbvh.cuh"
 
 #include <cuda_runtime.h>
 
@@ -1409,6 +1410,107 @@ int gi_trace(GiContext* c, const GiRay* rays, uint32_t n, GiHit* hits)
 	cudaFree(dr); cudaFree(dh);
 	if (e != cudaSuccess) return fail(c, GI_ERR_CUDA, std::string("gi_trace: ") + cudaGetErrorString(e));
 	return st;
+}
+
+// Device-side hierarchy build (gi_lbvh.cuh).  Host buffers in and out; the result is in the reference's layout.
+int gi_build_hierarchy(GiContext* c, const float* positions, uint32_t num_vertices, const uint32_t* triangles, const uint32_t* triangle_materials,
+                       uint32_t num_triangles, GiNode* out_nodes, GiTriangle* out_leaf_triangles, uint32_t* out_parents, uint32_t* out_num_nodes,
+                       uint32_t* out_num_tree_levels)
+{
+	if (!c || !positions || !triangles || !out_nodes || !out_leaf_triangles || !out_parents || !out_num_nodes || !out_num_tree_levels) return GI_ERR_INVALID;
+	if (num_vertices == 0 || num_triangles == 0) return fail(c, GI_ERR_INVALID, "gi_build_hierarchy: empty mesh");
+	if (num_triangles > 0x7ffffff0u) return fail(c, GI_ERR_CAPACITY, "gi_build_hierarchy: too many triangles");
+	for (size_t i = 0; i < size_t(num_triangles) * 3; ++i)
+		if (triangles[i] >= num_vertices) return fail(c, GI_ERR_INVALID, "gi_build_hierarchy: vertex index out of range");
+	GI_CUDA(c, cudaSetDevice(c->device));
+	const uint32_t T = num_triangles, L = (T + 1u) / 2u, N = 2u * L - 1u, I = L - 1u;
+	cudaStream_t st = c->stream;
+	std::vector<void*> allocs;
+	auto dalloc = [&](size_t bytes) -> void* { void* p = nullptr; if (cudaMalloc(&p, std::max<size_t>(bytes, 16)) != cudaSuccess) return nullptr; allocs.push_back(p); return p; };
+	auto freeAll = [&]() { for (void* p : allocs) cudaFree(p); };
+	float* dPos = static_cast<float*>(dalloc(size_t(num_vertices) * 12));
+	uint32_t* dTri = static_cast<uint32_t*>(dalloc(size_t(T) * 12));
+	uint32_t* dMat = triangle_materials ? static_cast<uint32_t*>(dalloc(size_t(T) * 4)) : nullptr;
+	unsigned* dBounds = static_cast<unsigned*>(dalloc(6 * 4));
+	unsigned long long* dCodes = static_cast<unsigned long long*>(dalloc(size_t(T) * 8));
+	unsigned long long* dCodesSorted = static_cast<unsigned long long*>(dalloc(size_t(T) * 8));
+	uint32_t* dIds = static_cast<uint32_t*>(dalloc(size_t(T) * 4));
+	uint32_t* dIdsSorted = static_cast<uint32_t*>(dalloc(size_t(T) * 4));
+	unsigned long long* dLeafCodes = static_cast<unsigned long long*>(dalloc(size_t(L) * 8));
+	I4* dLeafTris = static_cast<I4*>(dalloc(size_t(L) * 2 * 16));
+	LbvhTree tr;
+	tr.left = static_cast<uint32_t*>(dalloc(size_t(I) * 4)); tr.right = static_cast<uint32_t*>(dalloc(size_t(I) * 4));
+	tr.parent = static_cast<uint32_t*>(dalloc(size_t(I) * 4)); tr.first = static_cast<uint32_t*>(dalloc(size_t(I) * 4)); tr.last = static_cast<uint32_t*>(dalloc(size_t(I) * 4));
+	tr.leafParent = static_cast<uint32_t*>(dalloc(size_t(L) * 4));
+	tr.boxMin = static_cast<float*>(dalloc(size_t(I) * 12)); tr.boxMax = static_cast<float*>(dalloc(size_t(I) * 12));
+	tr.leafMin = static_cast<float*>(dalloc(size_t(L) * 12)); tr.leafMax = static_cast<float*>(dalloc(size_t(L) * 12));
+	tr.visits = static_cast<uint32_t*>(dalloc(size_t(I) * 4));
+	uint32_t* dPreInner = static_cast<uint32_t*>(dalloc(size_t(I) * 4));
+	uint32_t* dPreLeaf = static_cast<uint32_t*>(dalloc(size_t(L) * 4));
+	uint32_t* dDepth = static_cast<uint32_t*>(dalloc(4));
+	F4* dNodes = static_cast<F4*>(dalloc(size_t(N) * 32));
+	uint32_t* dParents = static_cast<uint32_t*>(dalloc(size_t(N) * 4));
+	size_t sortBytes = 0;
+	cub::DeviceRadixSort::SortPairs(nullptr, sortBytes, dCodes, dCodesSorted, dIds, dIdsSorted, int(T), 0, 63, st);
+	void* dSortTmp = dalloc(sortBytes);
+	bool ok = dPos && dTri && (!triangle_materials || dMat) && dBounds && dCodes && dCodesSorted && dIds && dIdsSorted && dLeafCodes && dLeafTris && tr.left && tr.right &&
+	          tr.parent && tr.first && tr.last && tr.leafParent && tr.boxMin && tr.boxMax && tr.leafMin && tr.leafMax && tr.visits && dPreInner && dPreLeaf && dDepth && dNodes &&
+	          dParents && dSortTmp;
+	if (!ok) { freeAll(); return fail(c, GI_ERR_CUDA, "gi_build_hierarchy: device allocation failed"); }
+	cudaError_t e = cudaSuccess;
+	auto step = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+	step(cudaMemcpyAsync(dPos, positions, size_t(num_vertices) * 12, cudaMemcpyHostToDevice, st));
+	step(cudaMemcpyAsync(dTri, triangles, size_t(T) * 12, cudaMemcpyHostToDevice, st));
+	if (dMat) step(cudaMemcpyAsync(dMat, triangle_materials, size_t(T) * 4, cudaMemcpyHostToDevice, st));
+	const unsigned initBounds[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+	step(cudaMemcpyAsync(dBounds, initBounds, sizeof(initBounds), cudaMemcpyHostToDevice, st));
+	step(cudaMemsetAsync(tr.visits, 0, std::max<size_t>(size_t(I) * 4, 4), st));
+	step(cudaMemsetAsync(dDepth, 0, 4, st));
+	if (e == cudaSuccess)
+	{
+		const unsigned B = 256;
+		k_lbvh_bounds<<<unsigned(c->numSMs) * 4u, B, 0, st>>>(dPos, num_vertices, dBounds);
+		k_lbvh_morton<<<(T + B - 1) / B, B, 0, st>>>(dPos, dTri, T, dBounds, dCodes, dIds);
+		step(cub::DeviceRadixSort::SortPairs(dSortTmp, sortBytes, dCodes, dCodesSorted, dIds, dIdsSorted, int(T), 0, 63, st));
+		k_lbvh_leaves<<<(L + B - 1) / B, B, 0, st>>>(dPos, dTri, dMat, dIdsSorted, dCodesSorted, T, L, dLeafTris, dLeafCodes, tr);
+		c->launches += 4;
+		if (I > 0)
+		{
+			k_lbvh_tree<<<(I + B - 1) / B, B, 0, st>>>(dLeafCodes, int(L), tr);
+			k_lbvh_boxes<<<(L + B - 1) / B, B, 0, st>>>(int(L), tr);
+			k_lbvh_preorder<<<(N + B - 1) / B, B, 0, st>>>(int(L), tr, dPreInner, dPreLeaf, dDepth);
+			k_lbvh_emit<<<(N + B - 1) / B, B, 0, st>>>(int(L), tr, dPreInner, dPreLeaf, dNodes, dParents);
+			c->launches += 4;
+		}
+		step(cudaGetLastError());
+	}
+	uint32_t depth = 1;
+	if (I > 0)
+	{
+		step(cudaMemcpyAsync(out_nodes, dNodes, size_t(N) * 32, cudaMemcpyDeviceToHost, st));
+		step(cudaMemcpyAsync(out_parents, dParents, size_t(N) * 4, cudaMemcpyDeviceToHost, st));
+		step(cudaMemcpyAsync(&depth, dDepth, 4, cudaMemcpyDeviceToHost, st));
+	}
+	step(cudaMemcpyAsync(out_leaf_triangles, dLeafTris, size_t(L) * 2 * 16, cudaMemcpyDeviceToHost, st));
+	float leafBox[6];
+	if (I == 0)
+	{
+		step(cudaMemcpyAsync(leafBox, tr.leafMin, 12, cudaMemcpyDeviceToHost, st));
+		step(cudaMemcpyAsync(leafBox + 3, tr.leafMax, 12, cudaMemcpyDeviceToHost, st));
+	}
+	step(cudaStreamSynchronize(st));
+	freeAll();
+	if (e != cudaSuccess) return fail(c, GI_ERR_CUDA, std::string("gi_build_hierarchy: ") + cudaGetErrorString(e));
+	if (I == 0)
+	{
+		// one leaf: the root is a leaf node (bim_sahspilt.cpp:36)
+		std::memcpy(out_nodes[0].min, leafBox, 12); std::memcpy(out_nodes[0].max, leafBox + 3, 12);
+		out_nodes[0].first_child = 0x80000000u; out_nodes[0].escape = 0u;
+		out_parents[0] = 0u;
+	}
+	*out_num_nodes = N;
+	*out_num_tree_levels = depth;
+	return GI_OK;
 }
 
 int gi_synchronize(GiContext* c)

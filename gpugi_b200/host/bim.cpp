@@ -384,6 +384,19 @@ void Chunk::buildHierarchy(BuildMethod method)
 	m_properties |= Property::HIERARCHY;
 }
 
+void Chunk::setHierarchy(const Node* nodes, const uint32_t* parents, const Box* boxes, uint32_t numNodes, const UVec4* leaves, uint32_t numLeafSlots, uint32_t numTreeLevels)
+{
+	m_numTrianglesPerLeaf = 2;
+	m_hierarchy.assign(nodes, nodes + numNodes);
+	m_hierarchyParents.assign(parents, parents + numNodes);
+	m_aaBoxes.assign(boxes, boxes + numNodes);
+	m_hierarchyLeaves.assign(leaves, leaves + numLeafSlots);
+	m_oBoxes.clear();
+	m_numTreeLevels = numTreeLevels;
+	m_properties |= Property::HIERARCHY | Property::AABOX_BVH;
+	m_properties &= ~uint32_t(Property::OBOX_BVH);
+}
+
 // bim_hierarchy.cpp:8-50: leaf box = union of its (valid) triangles, inner box = union of children.
 // Nodes are in preorder, so a reverse sweep sees every child before its parent.
 void Chunk::computeBVHAABoxes()

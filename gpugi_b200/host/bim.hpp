@@ -124,6 +124,9 @@ public:
 
 	/// Chunk::buildHierarchy (bim_chunk.cpp:227-242)
 	void buildHierarchy(BuildMethod method);
+	/// Install a hierarchy built elsewhere (the device LBVH, gi_build_hierarchy) in the chunk's own format: nodes in preorder with
+	/// child / escape links, parents, 2 slots per leaf, boxes, tree levels.
+	void setHierarchy(const Node* nodes, const uint32_t* parents, const Box* boxes, uint32_t numNodes, const UVec4* leaves, uint32_t numLeafSlots, uint32_t numTreeLevels);
 	/// Chunk::computeBVHAABoxes (bim_hierarchy.cpp:45-50)
 	void computeBVHAABoxes();
 	/// Chunk::computeBVHOBoxes (bim_hierarchy.cpp:54-96): one oriented box per node around all vertices below it, same recursion.

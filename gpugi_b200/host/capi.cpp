@@ -16,6 +16,7 @@
 #include "scene.hpp"
 
 #include <cstring>
+#include <vector>
 #include <memory>
 #include <stdexcept>
 
@@ -59,8 +60,34 @@ GihScene* gih_scene_from_mesh_bvh(const float* positions, const float* normals, 
 	                       reinterpret_cast<const gi::bim::Vec2*>(texcoords), num_vertices, reinterpret_cast<const gi::bim::UVec3*>(triangles), tri_materials,
 	                       num_triangles);
 	model->useJsonMaterialOrder(); // TRIANGLE_MAT indices follow the order of the JSON "materials" object
-	model->chunk().buildHierarchy(build_method == 1 ? Chunk::BuildMethod::KD_TREE : Chunk::BuildMethod::SAH);
-	model->chunk().computeBVHAABoxes();
+	if (build_method == 2)
+	{
+		// device-side LBVH (gi_build_hierarchy): same layout as the host builders, built on the GPU
+		GiContext* ctx = nullptr;
+		if (gi_create(0, &ctx) != GI_OK) { LOG_ERROR("device hierarchy build: " << gi_last_error(nullptr)); return nullptr; }
+		const uint32_t L = (num_triangles + 1u) / 2u, N = 2u * L - 1u;
+		std::vector<GiNode> nodes(N);
+		std::vector<GiTriangle> leaves(size_t(L) * 2);
+		std::vector<uint32_t> parents(N);
+		uint32_t numNodes = 0, levels = 0;
+		int st = gi_build_hierarchy(ctx, positions, num_vertices, triangles, tri_materials, num_triangles, nodes.data(), leaves.data(), parents.data(), &numNodes, &levels);
+		if (st != GI_OK) { LOG_ERROR("device hierarchy build: " << gi_last_error(ctx)); gi_destroy(ctx); return nullptr; }
+		gi_destroy(ctx);
+		std::vector<gi::bim::Node> hn(numNodes);
+		std::vector<gi::bim::Box> hb(numNodes);
+		for (uint32_t i = 0; i < numNodes; ++i)
+		{
+			hn[i].firstChild = nodes[i].first_child; hn[i].escape = nodes[i].escape;
+			hb[i].min = {nodes[i].min[0], nodes[i].min[1], nodes[i].min[2]}; hb[i].max = {nodes[i].max[0], nodes[i].max[1], nodes[i].max[2]};
+		}
+		static_assert(sizeof(GiTriangle) == sizeof(gi::bim::UVec4), "leaf slot layout");
+		model->chunk().setHierarchy(hn.data(), parents.data(), hb.data(), numNodes, reinterpret_cast<const gi::bim::UVec4*>(leaves.data()), uint32_t(leaves.size()), levels);
+	}
+	else
+	{
+		model->chunk().buildHierarchy(build_method == 1 ? Chunk::BuildMethod::KD_TREE : Chunk::BuildMethod::SAH);
+		model->chunk().computeBVHAABoxes();
+	}
 	std::unique_ptr<GihScene> h(new GihScene());
 	h->scene = std::make_shared<Scene>(std::move(model), texture_dir ? texture_dir : "", bvh_type == 0 ? ei::Types3D::BOX : ei::Types3D::OBOX);
 	if (!h->scene->IsValid()) return nullptr;

@@ -340,6 +340,16 @@ GI_API int gi_trace(GiContext* ctx, const GiRay* rays, uint32_t n, GiHit* hits);
 /* Same, on device-resident buffers (asynchronous on the context stream). */
 GI_API int gi_trace_device(GiContext* ctx, const GiRay* d_rays, uint32_t n, GiHit* d_hits);
 
+/* Device-side replacement of Chunk::buildHierarchy + remapNodePointers + computeBVHAABoxes (bim_chunk.cpp:227-242, bim_sahspilt.cpp:27-151,
+ * bim_hierarchy.cpp:8-50,238-252) for a mesh that comes without a hierarchy: an LBVH (Morton order of the triangle centroids, consecutive
+ * pairs per leaf, Karras' binary radix tree, bottom-up boxes) written in the REFERENCE'S layout -- preorder GiNode array with child / escape
+ * links, 2 slots per leaf (unused slot all-zero), parents, tree levels -- so that gi_upload_scene, both walks and the .bim writer take it
+ * unchanged.  Host buffers in and out: out_nodes / out_parents hold 2*ceil(T/2)-1 entries, out_leaf_triangles 2*ceil(T/2).
+ * triangle_materials may be NULL (material 0). */
+GI_API int gi_build_hierarchy(GiContext* ctx, const float* positions, uint32_t num_vertices, const uint32_t* triangles, const uint32_t* triangle_materials,
+                              uint32_t num_triangles, GiNode* out_nodes, GiTriangle* out_leaf_triangles, uint32_t* out_parents, uint32_t* out_num_nodes,
+                              uint32_t* out_num_tree_levels);
+
 /* Replaces glFinish (renderersystem.cpp:249,253). */
 GI_API int gi_synchronize(GiContext* ctx);
 
