@@ -241,6 +241,14 @@ class Device:
         arr = (C.c_void_p * 6)(*[face.ctypes.data] * 6)
         self._check(capi.dev.gi_set_environment_map(self._c, 1, arr), "gi_set_environment_map")
 
+    def set_environment_cube(self, faces):
+        """6 (size, size, 4) uint8 sRGB faces in the order -X,+X,-Y,+Y,-Z,+Z (RendererSystem::SetEnvironmentMap, renderersystem.cpp:173-186)."""
+        arrs = [np.ascontiguousarray(f, dtype=np.uint8) for f in faces]
+        size = arrs[0].shape[0]
+        assert all(a.shape == (size, size, 4) for a in arrs) and len(arrs) == 6
+        ptrs = (C.c_void_p * 6)(*[a.ctypes.data for a in arrs])
+        self._check(capi.dev.gi_set_environment_map(self._c, size, ptrs), "gi_set_environment_map")
+
     def clear(self):
         self._check(capi.dev.gi_clear_accumulator(self._c), "gi_clear_accumulator")
 

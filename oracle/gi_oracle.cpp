@@ -673,9 +673,34 @@ inline V3 cameraRayDirection(const Frame& f, uint32_t& seed, int gx, int gy)
 	return normalize(sc.x * v3(f.cam.u) + sc.y * v3(f.cam.v) + v3(f.cam.w));
 }
 
+// textureLod(EnvironmentMap, vec4(dir, 0), 0) (pathtracer.comp:57) for a size x size SRGB8 cube (renderersystem.cpp:173-186): face
+// selection and (s, t) of the GL 4.5 specification, table 8.19 / section 8.13; linear filter inside the selected face with
+// clamp-to-edge (no seamless filtering), texels decoded from sRGB before filtering.  Faces in the order -X,+X,-Y,+Y,-Z,+Z, RGBA8.
+struct EnvCube { const uint8_t* const* faces; int size; };
+
+inline V3 sampleCube(const EnvCube& e, V3 r)
+{
+	const float ax = fabsf(r.x), ay = fabsf(r.y), az = fabsf(r.z);
+	int face; float sc, tc, ma;
+	if (ax >= ay && ax >= az) { ma = ax; if (r.x > 0) { face = 1; sc = -r.z; tc = -r.y; } else { face = 0; sc = r.z; tc = -r.y; } }
+	else if (ay >= az) { ma = ay; if (r.y > 0) { face = 3; sc = r.x; tc = r.z; } else { face = 2; sc = r.x; tc = -r.z; } }
+	else { ma = az; if (r.z > 0) { face = 5; sc = r.x; tc = -r.y; } else { face = 4; sc = -r.x; tc = -r.y; } }
+	const float s = 0.5f * (sc / ma + 1.0f), t = 0.5f * (tc / ma + 1.0f);
+	const float fu = s * float(e.size) - 0.5f, fv = t * float(e.size) - 0.5f;
+	const float iu = floorf(fu), iv = floorf(fv);
+	const float a = fu - iu, b = fv - iv;
+	auto clampi = [&](int i) { return i < 0 ? 0 : (i >= e.size ? e.size - 1 : i); };
+	const int i0 = clampi(int(iu)), i1 = clampi(int(iu) + 1), j0 = clampi(int(iv)), j1 = clampi(int(iv) + 1);
+	auto tex = [&](int i, int j) { const uint8_t* p = e.faces[face] + 4 * (size_t(j) * e.size + i); return v3(g_srgbLut[p[0]], g_srgbLut[p[1]], g_srgbLut[p[2]]); };
+	const V3 t00 = tex(i0, j0), t10 = tex(i1, j0), t01 = tex(i0, j1), t11 = tex(i1, j1);
+	const float w00 = (1.0f - a) * (1.0f - b), w10 = a * (1.0f - b), w01 = (1.0f - a) * b, w11 = a * b;
+	return v3(t00.x * w00 + t10.x * w10 + t01.x * w01 + t11.x * w11, t00.y * w00 + t10.y * w10 + t01.y * w01 + t11.y * w11,
+	          t00.z * w00 + t10.z * w10 + t01.z * w01 + t11.z * w11);
+}
+
 // pathtracer.comp:16-110, one invocation. envColor: textureLod(EnvironmentMap,..) of the
 // default 1x1 cube (renderersystem.cpp:39-47) generalised to a constant colour.
-void PathtracerPixel(const Frame& f, int gx, int gy, V3 envColor, Counters& c, TraceCounters& tc)
+void PathtracerPixel(const Frame& f, int gx, int gy, V3 envColor, Counters& c, TraceCounters& tc, const EnvCube* cube = nullptr)
 {
 	const Scene& s = *f.scene;
 	const float lightSampleWeight = float(f.numLightSamples) / 1;
@@ -694,7 +719,7 @@ void PathtracerPixel(const Frame& f, int gx, int gy, V3 envColor, Counters& c, T
 		TraceRay(s, ray, rayHit, hitIndex, bary, triangle, geometryNormal, &tc);
 		if (rayHit == RAY_MAX)
 		{
-			color += pathThroughput * envColor;
+			color += pathThroughput * (cube ? sampleCube(*cube, ray.Direction) : envColor);
 			break;
 		}
 		geometryNormal = normalize(geometryNormal);
@@ -1201,9 +1226,16 @@ static Frame makeFrame(const Scene& s, const GiCamera* cam, int w, int h, const 
 
 // Pathtracer::Draw (pathtracer.cpp:47-50): (W/8) x (H/8) groups of 8x8 => pixels beyond the last
 // full group are not rendered.
+static const uint8_t* const* g_envFaces = nullptr;
+static int g_envSize = 0;
+// Environment cube for the following or_render_pt calls (size 0 / NULL: back to the constant colour argument).
+OR_API void or_set_environment_cube(int size, const uint8_t* const* faces) { g_envFaces = size > 0 ? faces : nullptr; g_envSize = size > 0 ? size : 0; }
+
 OR_API int or_render_pt(const GiSceneDesc* desc, const GiCamera* cam, int w, int h, const GiLightSample* ls, int nls, uint32_t frameSeed, int maxLen,
                         const float env_rgb[3], const OrRegion* region, float* accum, OrCounters* counters)
 {
+	EnvCube cubeStorage = {g_envFaces, g_envSize};
+	const EnvCube* cube = g_envFaces ? &cubeStorage : nullptr;
 	Scene s = makeScene(desc);
 	Frame f = makeFrame(s, cam, w, h, ls, nls, frameSeed, maxLen, accum);
 	V3 env = env_rgb ? v3(env_rgb) : v3(0.0f);
@@ -1224,7 +1256,7 @@ OR_API int or_render_pt(const GiSceneDesc* desc, const GiCamera* cam, int w, int
 				{
 					int gx = tx * 8 + lx, gy = ty * 8 + ly;
 					if (gx < x0 || gx >= x1 || gy < y0 || gy >= y1) continue;
-					PathtracerPixel(f, gx, gy, env, c, tc);
+					PathtracerPixel(f, gx, gy, env, c, tc, cube);
 				}
 		}
 		addCounters(counters, c, tc);

@@ -149,6 +149,22 @@ def render_pt(scene_desc, cam, w, h, light_samples, frame_seed, max_len=16, env_
     return accum, cnt.as_dict()
 
 
+def set_environment_cube(faces):
+    """faces: None, or 6 (size, size, 4) uint8 sRGB arrays in the order -X,+X,-Y,+Y,-Z,+Z, used by the following render_pt calls."""
+    global _env_keep
+    if faces is None:
+        lib.or_set_environment_cube(0, None)
+        _env_keep = None
+        return
+    arrs = [np.ascontiguousarray(f, dtype=np.uint8) for f in faces]
+    ptrs = (C.c_void_p * 6)(*[a.ctypes.data for a in arrs])
+    _env_keep = (arrs, ptrs)
+    lib.or_set_environment_cube(arrs[0].shape[0], ptrs)
+
+
+_env_keep = None
+
+
 def render_lpt(scene_desc, cam, w, h, light_samples, frame_seed, num_rays_per_light_sample, max_len=16, first_path=0, num_paths=0, show_light_caches=True,
                accum=None):
     ls = np.ascontiguousarray(light_samples, dtype=LIGHT_SAMPLE_DTYPE)
