@@ -431,6 +431,9 @@ class RendererSystem:
     def SetStreaming(self, streaming):
         capi.host.gih_rs_set_streaming(self._h, 1 if streaming else 0)
 
+    def SetDeviceLightSampling(self, on_device):
+        capi.host.gih_rs_set_device_light_sampling(self._h, 1 if on_device else 0)
+
     def ReadBackbufferAsync(self, out):
         """Progressive display read: never stalls or drains the renderer.  Returns the number of submitted iterations that
         are not in the image yet (<= pathLength + 1 while streaming, else 0); `out` is complete after WaitReads()."""

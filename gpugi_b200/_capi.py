@@ -146,6 +146,9 @@ DEVICE_API = {
     "gi_read_accumulator": (C.c_int, [vp, vp]),
     "gi_read_accumulator_async": (C.c_int, [vp, vp, P(u32)]),
     "gi_wait_reads": (C.c_int, [vp]),
+    "gi_set_light_tables": (C.c_int, [vp, vp]),
+    "gi_generate_light_samples": (C.c_int, [vp, P(u64), u32, f32]),
+    "gi_get_light_samples": (C.c_int, [vp, vp, u32]),
     "gi_build_hierarchy": (C.c_int, [vp, vp, u32, vp, vp, u32, vp, vp, vp, P(u32), P(u32)]),
     "gi_accumulator_device": (C.c_int, [vp, P(vp), P(C.c_size_t)]),
     "gi_compute_mse": (C.c_int, [vp, vp, u32, P(f32)]),
@@ -191,6 +194,7 @@ HOST_API = {
     "gih_rs_global_iteration": (u64, [vp]),
     "gih_rs_read_backbuffer": (C.c_int, [vp, vp]),
     "gih_rs_set_streaming": (None, [vp, C.c_int]),
+    "gih_rs_set_device_light_sampling": (None, [vp, C.c_int]),
     "gih_rs_read_backbuffer_async": (C.c_int, [vp, vp, P(u32)]),
     "gih_rs_wait_reads": (C.c_int, [vp]),
     "gih_rs_num_light_samples": (u32, [vp]),

@@ -125,6 +125,90 @@ __global__ void k_reset_counter(uint32_t* lightCacheCount, uint32_t* lightPathLe
 	*lightPathLengthSum = 0u;
 }
 
+// LightSampler::GenerateRandomSamples (lightsampler.cpp:18-95) for one iteration.  The xorshift64* recurrence of utilities/random.cpp:25-43
+// stores the multiplied value back into its state, so the stream has no jump-ahead: thread 0 draws the 3 * numArea + numPoint numbers
+// of the iteration into shared memory, then one thread per sample does the rest.  Every float operation is the host's (no contraction).
+struct DLightTables
+{
+	const float* tri;        // 12 floats per light triangle: v0, v1, v2, luminance
+	const float* summedArea;
+	uint32_t numTri;
+	float areaSum;
+	const float* pointPos; const float* pointInt; const float* pointSummedFlux;
+	uint32_t numPoint;
+	float areaFlux, pointFlux;  // totals
+};
+
+__device__ __forceinline__ uint32_t lowerBound(const float* table, uint32_t n, float key)
+{
+	uint32_t lo = 0, hi = n;
+	while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (table[mid] < key) lo = mid + 1; else hi = mid; }
+	return lo;
+}
+
+__global__ void __launch_bounds__(256) k_light_samples(DLightTables t, unsigned long long state, uint32_t n, float positionBias, F4* __restrict__ out)
+{
+	extern __shared__ float draws[];
+	if (t.areaFlux + t.pointFlux == 0.0f)
+	{
+		for (uint32_t s = threadIdx.x; s < 2u * n; s += blockDim.x) *reinterpret_cast<float4*>(out + s) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+		return;
+	}
+	const float pointLightPercentage = __fdiv_rn(t.pointFlux, __fadd_rn(t.areaFlux, t.pointFlux));
+	const uint32_t numPoint = uint32_t(__fmul_rn(pointLightPercentage, float(n)));
+	const uint32_t numArea = n - numPoint;
+	if (threadIdx.x == 0)
+	{
+		const uint32_t numDraws = 3u * numArea + numPoint;
+		for (uint32_t i = 0; i < numDraws; ++i)
+		{
+			state ^= state >> 12; state ^= state << 25; state ^= state >> 27;
+			state *= 2685821657736338717ull;
+			draws[i] = __fdiv_rn(float(state % 8388593ull), 8388593.0f);
+		}
+	}
+	__syncthreads();
+	for (uint32_t s = threadIdx.x; s < n; s += blockDim.x)
+	{
+		float4 a, b;
+		if (s < numArea)
+		{
+			const float sampleWeight = __fdiv_rn(t.areaSum, float(numArea));
+			const float pick = draws[3u * s];
+			float xi0 = draws[3u * s + 1u];
+			const float xi1 = draws[3u * s + 2u];
+			const uint32_t ti = min(lowerBound(t.summedArea, t.numTri, pick), t.numTri - 1u);
+			xi0 = __fsqrt_rn(xi0);
+			const float alpha = __fsub_rn(1.0f, xi0), beta = __fmul_rn(xi0, __fsub_rn(1.0f, xi1)), gamma = __fmul_rn(xi0, xi1);
+			const float* v = t.tri + 12 * size_t(ti);
+			float pos[3], e1[3], e2[3];
+			for (int k = 0; k < 3; ++k)
+			{
+				pos[k] = __fadd_rn(__fadd_rn(__fmul_rn(v[k], alpha), __fmul_rn(v[3 + k], beta)), __fmul_rn(v[6 + k], gamma));
+				e1[k] = __fsub_rn(v[k], v[3 + k]); e2[k] = __fsub_rn(v[k], v[6 + k]);
+			}
+			float nrm[3] = {__fsub_rn(__fmul_rn(e1[1], e2[2]), __fmul_rn(e1[2], e2[1])), __fsub_rn(__fmul_rn(e1[2], e2[0]), __fmul_rn(e1[0], e2[2])),
+			                __fsub_rn(__fmul_rn(e1[0], e2[1]), __fmul_rn(e1[1], e2[0]))};
+			const float len = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(nrm[0], nrm[0]), __fmul_rn(nrm[1], nrm[1])), __fmul_rn(nrm[2], nrm[2])));
+			for (int k = 0; k < 3; ++k) { nrm[k] = __fdiv_rn(nrm[k], len); pos[k] = __fadd_rn(pos[k], __fmul_rn(nrm[k], positionBias)); }
+			a = make_float4(pos[0], pos[1], pos[2], atan2f(nrm[1], nrm[0]));
+			b = make_float4(__fmul_rn(v[9], sampleWeight), __fmul_rn(v[10], sampleWeight), __fmul_rn(v[11], sampleWeight), nrm[2]);
+		}
+		else
+		{
+			const float pick = draws[3u * numArea + (s - numArea)];
+			const uint32_t li = min(lowerBound(t.pointSummedFlux, t.numPoint, pick), t.numPoint - 1u);
+			float w = t.pointSummedFlux[li];
+			if (li > 0) w = __fsub_rn(w, t.pointSummedFlux[li - 1]);
+			const float div = __fmul_rn(float(numPoint), w);
+			a = make_float4(t.pointPos[3 * li], t.pointPos[3 * li + 1], t.pointPos[3 * li + 2], 0.0f);
+			b = make_float4(__fdiv_rn(t.pointInt[3 * li], div), __fdiv_rn(t.pointInt[3 * li + 1], div), __fdiv_rn(t.pointInt[3 * li + 2], div), 2.0f);
+		}
+		*reinterpret_cast<float4*>(out + 2 * size_t(s)) = a;
+		*reinterpret_cast<float4*>(out + 2 * size_t(s) + 1) = b;
+	}
+}
+
 // ---- wavefront scheduler (gi_wavefront.cuh) -------------------------------------------------------------
 #ifndef WF_TRACE_THREADS
 #define WF_TRACE_THREADS 128
@@ -360,6 +444,10 @@ struct GiContext
 	const F4* externalLightSamples = nullptr; // gi_set_light_samples_device
 	uint32_t lightSampleCapacity = 0;
 	int numLightSamples = 0;
+
+	// device-side light sampling (gi_set_light_tables)
+	DLightTables lightTables = {};
+	std::vector<void*> lightTableAllocs;
 
 	// light cache
 	F4* lightCache = nullptr;
@@ -882,6 +970,7 @@ void gi_destroy(GiContext* c)
 	if (c->envTex) cudaDestroyTextureObject(c->envTex);
 	if (c->envArray) cudaFreeArray(c->envArray);
 	cudaFree(c->cacheRing); cudaFree(c->ringCounters);
+	for (void* p : c->lightTableAllocs) cudaFree(p);
 	cudaFree(c->accum); cudaFree(c->lightSamples); cudaFree(c->lightCache); cudaFree(c->bptCounters); cudaFree(c->counters); cudaFree(c->mseResult);
 	for (cudaEvent_t e : c->timingEvents) cudaEventDestroy(e);
 	if (c->ownStream) cudaStreamDestroy(c->ownStream);
@@ -1142,6 +1231,80 @@ int gi_set_light_samples_device(GiContext* c, const GiLightSample* d_samples, ui
 	}
 	c->externalLightSamples = reinterpret_cast<const F4*>(d_samples);
 	c->numLightSamples = int(n);
+	return GI_OK;
+}
+
+int gi_set_light_tables(GiContext* c, const GiLightTables* t)
+{
+	if (!c || !t) return GI_ERR_INVALID;
+	if ((t->num_light_triangles && (!t->light_triangles || !t->summed_area)) || (t->num_point_lights && (!t->point_positions || !t->point_intensities || !t->point_summed_flux)))
+		return fail(c, GI_ERR_INVALID, "gi_set_light_tables: incomplete tables");
+	GI_CUDA(c, cudaSetDevice(c->device));
+	int fst = flushStream(c);
+	if (fst != GI_OK) return fst;
+	GI_CUDA(c, cudaStreamSynchronize(c->stream));
+	for (void* p : c->lightTableAllocs) cudaFree(p);
+	c->lightTableAllocs.clear();
+	c->lightTables = DLightTables{};
+	auto up = [&](const void* src, size_t bytes, const float** dst) -> cudaError_t
+	{
+		void* d = nullptr;
+		cudaError_t e = cudaMalloc(&d, std::max<size_t>(bytes, 16));
+		if (e != cudaSuccess) return e;
+		c->lightTableAllocs.push_back(d);
+		if (bytes) e = cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, c->stream);
+		*dst = static_cast<const float*>(d);
+		return e;
+	};
+	DLightTables d = {};
+	GI_CUDA(c, up(t->light_triangles, size_t(t->num_light_triangles) * sizeof(GiLightTriangle), &d.tri));
+	GI_CUDA(c, up(t->summed_area, size_t(t->num_light_triangles) * 4, &d.summedArea));
+	GI_CUDA(c, up(t->point_positions, size_t(t->num_point_lights) * 12, &d.pointPos));
+	GI_CUDA(c, up(t->point_intensities, size_t(t->num_point_lights) * 12, &d.pointInt));
+	GI_CUDA(c, up(t->point_summed_flux, size_t(t->num_point_lights) * 4, &d.pointSummedFlux));
+	d.numTri = t->num_light_triangles; d.areaSum = t->light_area_sum; d.numPoint = t->num_point_lights;
+	d.areaFlux = t->num_light_triangles ? t->total_area_flux : 0.0f;
+	d.pointFlux = t->num_point_lights ? t->total_point_flux : 0.0f;
+	GI_CUDA(c, cudaStreamSynchronize(c->stream));
+	c->lightTables = d;
+	return GI_OK;
+}
+
+int gi_generate_light_samples(GiContext* c, uint64_t* rng_state, uint32_t n, float position_bias)
+{
+	if (!c || !rng_state || n == 0) return fail(c, GI_ERR_INVALID, "gi_generate_light_samples: no samples");
+	if (n > 8192u) return fail(c, GI_ERR_CAPACITY, "gi_generate_light_samples: more than 8192 samples per iteration");
+	GI_CUDA(c, cudaSetDevice(c->device));
+	uint32_t slot = 0;
+	int st = lightSlotForNextIteration(c, n, &slot);
+	if (st != GI_OK) return st;
+	const DLightTables& t = c->lightTables;
+	k_light_samples<<<1, 256, size_t(3u * n) * sizeof(float), c->stream>>>(t, (unsigned long long)*rng_state, n, position_bias, c->lightSamples + size_t(slot) * 2u * n);
+	++c->launches;
+	GI_CUDA(c, cudaGetLastError());
+	// the host copy of the stream advances exactly as the kernel's (lightsampler.cpp:33-35: 3 draws per area sample, 1 per point sample)
+	if (t.areaFlux + t.pointFlux != 0.0f)
+	{
+		const float pointLightPercentage = t.pointFlux / (t.areaFlux + t.pointFlux);
+		const uint32_t numPoint = uint32_t(pointLightPercentage * float(n));
+		const uint32_t numDraws = 3u * (n - numPoint) + numPoint;
+		uint64_t s = *rng_state;
+		for (uint32_t i = 0; i < numDraws; ++i) { s ^= s >> 12; s ^= s << 25; s ^= s >> 27; s *= 2685821657736338717ull; }
+		*rng_state = s;
+	}
+	c->lightSlot = slot;
+	c->externalLightSamples = nullptr;
+	c->numLightSamples = int(n);
+	return GI_OK;
+}
+
+int gi_get_light_samples(GiContext* c, GiLightSample* out, uint32_t n)
+{
+	if (!c || !out) return GI_ERR_INVALID;
+	if (int(n) != c->numLightSamples || n == 0) return fail(c, GI_ERR_INVALID, "gi_get_light_samples: n differs from the current set");
+	const F4* src = c->externalLightSamples ? c->externalLightSamples : c->lightSamples + size_t(c->lightSlot) * 2u * n;
+	GI_CUDA(c, cudaMemcpyAsync(out, src, size_t(n) * sizeof(GiLightSample), cudaMemcpyDeviceToHost, c->stream));
+	GI_CUDA(c, cudaStreamSynchronize(c->stream));
 	return GI_OK;
 }
 

@@ -238,6 +238,7 @@ uint32_t gih_rs_frame_seed(GihRendererSystem* h) { return h->rs->GetFrameSeed();
 uint64_t gih_rs_global_iteration(GihRendererSystem* h) { return h->rs->GetGlobalIterationIndex(); }
 int gih_rs_read_backbuffer(GihRendererSystem* h, float* rgba) { return h->rs->GetBackbuffer().ReadImage(rgba) ? 0 : 1; }
 void gih_rs_set_streaming(GihRendererSystem* h, int streaming) { h->rs->SetStreaming(streaming != 0); }
+void gih_rs_set_device_light_sampling(GihRendererSystem* h, int on_device) { h->rs->SetDeviceLightSampling(on_device != 0); }
 int gih_rs_read_backbuffer_async(GihRendererSystem* h, float* rgba, uint32_t* iterations_in_flight)
 {
 	return h->rs->GetBackbuffer().ReadImageAsync(rgba, iterations_in_flight) ? 0 : 1;

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <vector>
 
 LightSampler::LightSampler() : m_randomSeed(123) {}
 
@@ -65,4 +66,36 @@ void LightSampler::GenerateRandomSamples(LightSample* dst, unsigned int _numSamp
 		ei::Vec3 intensity = lights[lightIdx].intensity / (numPointSamples * sampleWeight);
 		dst->intensity[0] = intensity.x; dst->intensity[1] = intensity.y; dst->intensity[2] = intensity.z;
 	}
+}
+
+bool LightSampler::GenerateRandomSamplesOnDevice(GiContext* _device, unsigned int _numSamples, float _positionBias)
+{
+	if (!m_scene || !_device) return false;
+	if (m_tablesDevice != _device || m_tablesScene != m_scene.get() || m_tablesVersion != m_scene->GetLightTablesVersion())
+	{
+		static_assert(sizeof(Scene::LightTriangle) == sizeof(GiLightTriangle), "LightTriangle layout");
+		std::vector<float> pos, inten;
+		for (const Scene::PointLight& l : m_scene->GetPointLightsRef())
+		{
+			pos.push_back(l.position.x); pos.push_back(l.position.y); pos.push_back(l.position.z);
+			inten.push_back(l.intensity.x); inten.push_back(l.intensity.y); inten.push_back(l.intensity.z);
+		}
+		GiLightTables t;
+		std::memset(&t, 0, sizeof(t));
+		t.light_triangles = reinterpret_cast<const GiLightTriangle*>(m_scene->GetLightTriangles());
+		t.summed_area = m_scene->GetLightSummedAreaTable();
+		t.num_light_triangles = m_scene->GetNumLightTriangles();
+		t.light_area_sum = m_scene->GetLightAreaSum();
+		t.point_positions = pos.data(); t.point_intensities = inten.data();
+		t.point_summed_flux = m_scene->GetPointLightSummedFluxTable();
+		t.num_point_lights = uint32_t(m_scene->GetPointLightsRef().size());
+		t.total_area_flux = m_scene->GetTotalAreaLightFlux();
+		t.total_point_flux = m_scene->GetTotalPointLightFlux();
+		if (gi_set_light_tables(_device, &t) != GI_OK) return false;
+		m_tablesDevice = _device; m_tablesScene = m_scene.get(); m_tablesVersion = m_scene->GetLightTablesVersion();
+	}
+	uint64_t state = m_randomSeed;
+	if (gi_generate_light_samples(_device, &state, _numSamples, _positionBias) != GI_OK) return false;
+	m_randomSeed = state;
+	return true;
 }

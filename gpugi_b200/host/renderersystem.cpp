@@ -59,6 +59,13 @@ void RendererSystem::SetStreaming(bool _streaming)
 	if (_streaming) m_synchronousDraw = false;
 }
 
+const std::vector<LightSampler::LightSample>& RendererSystem::GetInitialLightSamples()
+{
+	if (m_deviceLightSampling && !m_lightSamples.empty())
+		Check(gi_get_light_samples(m_device, m_lightSamples.data(), uint32_t(m_lightSamples.size())), "gi_get_light_samples");
+	return m_lightSamples;
+}
+
 void RendererSystem::ResetIterationCount()
 {
 	m_iterationCount = 0;
@@ -80,6 +87,8 @@ void RendererSystem::PerIterationBufferUpdate(bool _iterationIncrement)
 			uint64_t seed = Mix64(global) ^ 123ull;
 			m_lightSampler.SetSeed(seed ? seed : 123ull);
 		}
+		if (m_deviceLightSampling && m_lightSampler.GenerateRandomSamplesOnDevice(m_device, m_numInitialLightSamples))
+			return;
 		m_lightSampler.GenerateRandomSamples(m_lightSamples.data(), m_numInitialLightSamples);
 		Check(gi_set_light_samples(m_device, m_lightSamples.data(), m_numInitialLightSamples), "gi_set_light_samples");
 	}

@@ -91,10 +91,13 @@ public:
 	/// instead of running each iteration to its last bounce; the accumulator is exact again after any synchronous read.
 	/// Implies SetSynchronousDraw(false) while on.
 	void SetStreaming(bool _streaming);
+	/// Light samples of every iteration are drawn on the device (LightSampler::GenerateRandomSamplesOnDevice) instead of on the host
+	/// + 4 KB upload; GetInitialLightSamples() then reads them back on demand.
+	void SetDeviceLightSampling(bool _onDevice) { m_deviceLightSampling = _onDevice; }
 	unsigned int GetWorldSize() const { return m_worldSize; }
 	GiContext* GetDevice() const { return m_device; }
 	const Camera& GetCamera() const { return m_camera; }
-	const std::vector<LightSampler::LightSample>& GetInitialLightSamples() const { return m_lightSamples; }
+	const std::vector<LightSampler::LightSample>& GetInitialLightSamples();
 
 private:
 	GiContext* m_device;
@@ -114,6 +117,7 @@ private:
 
 	unsigned int m_rank, m_worldSize;
 	bool m_synchronousDraw;
+	bool m_deviceLightSampling = false;
 
 	Renderer* m_activeRenderer;
 

@@ -299,6 +299,7 @@ int32_t Scene::GetBindlessHandle(const ei::Vec4& _data, bool _hdr)
 // scene.cpp:244-293
 void Scene::LoadLightSources()
 {
+	++m_lightTablesVersion;
 	const Chunk& chunk = m_model->chunk();
 	m_totalAreaLightFlux = 0.0f;
 	m_lightTriangles.clear();
@@ -335,6 +336,7 @@ void Scene::LoadLightSources()
 // scene.cpp:295-307
 void Scene::ComputePointLightTable()
 {
+	++m_lightTablesVersion;
 	m_totalPointLightFlux = 0.0f;
 	m_pointLightSummedFlux.clear();
 	for (auto& light : m_pointLights)

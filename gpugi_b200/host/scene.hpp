@@ -67,6 +67,9 @@ public:
 	float GetLightAreaSum() const { return m_lightAreaSum; }
 	float GetTotalAreaLightFlux() const { return m_totalAreaLightFlux; }
 	float GetTotalPointLightFlux() const { return m_totalPointLightFlux; }
+	/// Changes whenever the light tables do (LoadLightSources, ComputePointLightTable): device copies are refreshed lazily.
+	unsigned GetLightTablesVersion() const { return m_lightTablesVersion; }
+	const std::vector<PointLight>& GetPointLightsRef() const { return m_pointLights; }
 	ei::Box GetBoundingBox() const;
 
 	void AddPointLight(const PointLight& _light) { m_pointLights.push_back(_light); ComputePointLightTable(); }
@@ -87,6 +90,7 @@ private:
 	std::vector<GiNode> m_hierarchy;
 	std::vector<GiOBoxNode> m_oboxHierarchy; // bvhType = 1: TreeNode<ei::OBox> (scene.hpp:40-49), else empty
 
+	unsigned m_lightTablesVersion = 0;
 	std::vector<LightTriangle> m_lightTriangles;
 	std::vector<PointLight> m_pointLights;
 	std::vector<float> m_lightSummedArea;

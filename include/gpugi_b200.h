@@ -340,6 +340,31 @@ GI_API int gi_trace(GiContext* ctx, const GiRay* rays, uint32_t n, GiHit* hits);
 /* Same, on device-resident buffers (asynchronous on the context stream). */
 GI_API int gi_trace_device(GiContext* ctx, const GiRay* d_rays, uint32_t n, GiHit* d_hits);
 
+/* Device-side light sampling: what LightSampler::GenerateRandomSamples (lightsampler.cpp:18-95) needs from the scene,
+ * uploaded once per scene / point-light change (Scene::LoadLightSources, ComputePointLightTable, scene.cpp:244-307). */
+typedef struct GiLightTriangle { float v0[3], v1[3], v2[3], luminance[3]; } GiLightTriangle;
+typedef struct GiLightTables {
+	const GiLightTriangle* light_triangles;   /* emissive triangles                                       */
+	const float*           summed_area;       /* normalised running sum of their areas (lower_bound key)   */
+	uint32_t               num_light_triangles;
+	float                  light_area_sum;
+	const float*           point_positions;   /* 3 floats per point light                                  */
+	const float*           point_intensities; /* 3 floats per point light                                  */
+	const float*           point_summed_flux; /* normalised running sum of log(1 + 4 pi luminance)         */
+	uint32_t               num_point_lights;
+	float                  total_area_flux;
+	float                  total_point_flux;
+} GiLightTables;
+GI_API int gi_set_light_tables(GiContext* ctx, const GiLightTables* tables);
+
+/* LightSampler::GenerateRandomSamples on the device: the `n` light samples of the NEXT iteration, written straight into the context's
+ * light-sample ring (what gi_set_light_samples does with host data).  rng_state is the sampler's xorshift64* state (utilities/random.cpp:
+ * 25-43, seed 123 at start); it is advanced exactly as the host sampler would advance it (the recurrence is sequential: one thread
+ * draws, n threads build the samples).  Same records as the host sampler up to the last bit of atan2. */
+GI_API int gi_generate_light_samples(GiContext* ctx, uint64_t* rng_state, uint32_t n, float position_bias);
+/* The current light-sample set (host or device generated), for inspection. */
+GI_API int gi_get_light_samples(GiContext* ctx, GiLightSample* out, uint32_t n);
+
 /* Device-side replacement of Chunk::buildHierarchy + remapNodePointers + computeBVHAABoxes (bim_chunk.cpp:227-242, bim_sahspilt.cpp:27-151,
  * bim_hierarchy.cpp:8-50,238-252) for a mesh that comes without a hierarchy: an LBVH (Morton order of the triangle centroids, consecutive
  * pairs per leaf, Karras' binary radix tree, bottom-up boxes) written in the REFERENCE'S layout -- preorder GiNode array with child / escape

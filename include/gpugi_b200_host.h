@@ -76,6 +76,7 @@ GI_API uint32_t gih_rs_frame_seed(GihRendererSystem* rs);
 GI_API uint64_t gih_rs_global_iteration(GihRendererSystem* rs);
 GI_API int gih_rs_read_backbuffer(GihRendererSystem* rs, float* rgba);
 GI_API void gih_rs_set_streaming(GihRendererSystem* rs, int streaming);       /* RendererSystem::SetStreaming (GI_OPT_STREAMING) */
+GI_API void gih_rs_set_device_light_sampling(GihRendererSystem* rs, int on_device); /* RendererSystem::SetDeviceLightSampling (gi_generate_light_samples) */
 GI_API int gih_rs_read_backbuffer_async(GihRendererSystem* rs, float* rgba, uint32_t* iterations_in_flight); /* Texture2D::ReadImageAsync */
 GI_API int gih_rs_wait_reads(GihRendererSystem* rs);
 GI_API uint32_t gih_rs_num_light_samples(GihRendererSystem* rs);

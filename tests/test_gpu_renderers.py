@@ -635,3 +635,35 @@ def test_environment_cube_map(g, orc, scenes):
         assert pixel_mismatch_fraction(img, ref, 3e-2) < 0.03
         assert abs(img[..., :3].mean() - ref[..., :3].mean()) / ref[..., :3].mean() < 5e-3
     dev.close()
+
+
+@pytest.mark.parametrize("scene_kind", ["box1", "box1+points", "points"])
+def test_device_light_sampling(g, scenes, scene_kind, tmp_path):
+    """gi_generate_light_samples (SURVEY 8f-1): LightSampler::GenerateRandomSamples on the device.  Same stream, same triangle / light
+    picks, same records as the host sampler (positions and intensities bit for bit, the packed normal angle up to atan2's last bits),
+    over many iterations, for area lights, point lights and both; rendering with it gives the host-sampled image."""
+    if scene_kind == "points":
+        sc = scenes.make_random_triangles(300, seed=8)
+        lights = [((0.0, 8.0, 0.0), (50.0, 40.0, 30.0)), ((4.0, 6.0, -2.0), (5.0, 5.0, 25.0)), ((-5.0, 3.0, 1.0), (1.0, 9.0, 1.0))]
+    else:
+        sc = scenes.make_box1(tess=4)
+        lights = [((0.5, 1.0, 0.0), (3.0, 2.0, 1.0)), ((-0.7, 2.0, -1.0), (0.5, 0.5, 4.0))] if scene_kind == "box1+points" else []
+    for p, i in lights:
+        sc.add_point_light(p, i)
+    W = H = 64
+    cam = scenes.BOX1_CAMERA if scene_kind != "points" else {"pos": (0.0, 0.0, 14.0), "lookat": (0.0, 0.0, 0.0), "fov": 60.0}
+    host, devs = _rs(g, scenes, sc, "PT", W, H, cam=cam), g.RendererSystem(0)
+    devs.SetDeviceLightSampling(True)
+    devs.SetScene(sc); devs.SetScreenSize(W, H); devs.SetCamera(cam["pos"], cam["lookat"], cam["fov"]); devs.SetRenderer("PT")
+    devs.device.set_option(g.GI_OPT_TEXTURE_FILTER, 1)
+    for it in range(12):
+        a, b = host.GetInitialLightSamples(), devs.GetInitialLightSamples()
+        assert a.shape == b.shape == (128,)
+        assert np.array_equal(a["position"], b["position"]) and np.array_equal(a["intensity"], b["intensity"]), "iteration %d" % it
+        assert np.array_equal(a["normal_theta_cos"], b["normal_theta_cos"])
+        assert np.allclose(a["normal_phi"], b["normal_phi"], rtol=0, atol=2e-6)
+        host.Draw(); devs.Draw()
+    ia, ib = host.ReadBackbuffer(), devs.ReadBackbuffer()
+    assert ia[..., :3].mean() > 0
+    assert pixel_mismatch_fraction(ib, ia, 1e-3) < 0.01
+    host.close(); devs.close()
