@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(256) k_light_samples(DLightTables t, unsigned 
 #define WF_TRACE_THREADS 128
 #endif
 #ifndef WF_TRACE_MIN_BLOCKS
-#define WF_TRACE_MIN_BLOCKS 8
+#define WF_TRACE_MIN_BLOCKS 7   // 72 registers, 7 x 4 warps per SM (B200 A/B at refill 24 / vote 16: 6 -> 2.378*, 7 -> 2.137, 8 -> 2.168, 9 -> 2.255*, 10 -> 2.269* ms per PT iteration; * at 16/20)
 #endif
 #define WF_SHADE_THREADS 128
 #ifndef WF_SHADE_MIN_BLOCKS
