@@ -262,9 +262,9 @@ class Device:
         mats = None if tri_materials is None else np.ascontiguousarray(tri_materials, dtype=np.uint32)
         T = triangles.shape[0]
         L = (T + 1) // 2
-        nodes = np.zeros(2 * L - 1, dtype=NODE_DTYPE)
-        leaves = np.zeros(2 * L, dtype=TRIANGLE_DTYPE)
-        parents = np.zeros(2 * L - 1, dtype=np.uint32)
+        nodes = np.zeros(max(2 * L - 1, 1), dtype=NODE_DTYPE)
+        leaves = np.zeros(max(2 * L, 2), dtype=TRIANGLE_DTYPE)
+        parents = np.zeros(max(2 * L - 1, 1), dtype=np.uint32)
         n, lv = C.c_uint32(), C.c_uint32()
         self._check(capi.dev.gi_build_hierarchy(self._c, _vp(positions), positions.shape[0], _vp(triangles), _vp(mats) if mats is not None else None, T,
                                                 _vp(nodes), _vp(leaves), _vp(parents), C.byref(n), C.byref(lv)), "gi_build_hierarchy")

@@ -24,12 +24,14 @@
 #endif
 
 #if defined(__CUDA_ARCH__)
+#define GI_UNROLL _Pragma("unroll")
 #define GI_MUL(a, b) __fmul_rn((a), (b))
 #define GI_ADD(a, b) __fadd_rn((a), (b))
 #define GI_SUB(a, b) __fsub_rn((a), (b))
 #define GI_DIV(a, b) __fdiv_rn((a), (b))
 #else
 // host emulation: compiled with -ffp-contract=off, so each operator is one rounded operation
+#define GI_UNROLL
 #define GI_MUL(a, b) ((a) * (b))
 #define GI_ADD(a, b) ((a) + (b))
 #define GI_SUB(a, b) ((a) - (b))
@@ -369,7 +371,7 @@ GI_HD bool traceFast(const DScene& s, F3 o, F3 d, float& rayLength, int& hitLeaf
 		{
 			// leaf: two triangle slots (TRIANGLES_PER_LEAF 2, scenedata.glsl:5)
 			const int leaf = ~node;
-#pragma unroll
+GI_UNROLL
 			for (int slot = 0; slot < 2; ++slot)
 			{
 				const int lt = 2 * leaf + slot;

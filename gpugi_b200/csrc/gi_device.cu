@@ -22,8 +22,7 @@ using namespace gik;
 // kernels
 // =====================================================================================================
 
-// 64-bit device counters (GiCounters order, first 7 entries)
-static_assert(true, "");
+// 64-bit device counters (GiCounters order)
 enum { CNT_CLOSEST = 0, CNT_ANY, CNT_CAMERA, CNT_LIGHT, CNT_SHADED, CNT_SPLATS, CNT_FALLBACK, CNT_NODES, CNT_TRIS, CNT_COUNT };
 
 __device__ __forceinline__ void flushCounters(unsigned long long* counters, const PathCounters& pc, const TraceStats& st)

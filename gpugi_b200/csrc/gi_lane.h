@@ -261,7 +261,7 @@ GI_HD void wfBegin(WfLane& L, const DScene& s, F3 o, F3 d, float tMax, bool isAn
 	L.tMaxInit = tMax; L.best = tMax; L.second = GI_INF;
 	L.limit = isAny ? tMax : wfClosestLimit(tMax, s);
 	L.hitLeaf = -1; wfStackReset(L); L.index = index;
-	L.flags = isAny ? WFL_ANY : 0u; L.numCand = 0;
+	L.flags = isAny ? uint32_t(WFL_ANY) : 0u; L.numCand = 0;
 	const bool inDomain = wfSlabSetup(L, s, o, inv);
 	// root box first, as the reference does (traceray.glsl:56-69)
 	F4 a = ld4(s.refNodes), b = ld4(s.refNodes + 1);
@@ -339,11 +339,10 @@ GI_HD void wfLeafStep(WfLane& L, const DScene& s, const STK& stack, WfCand* cand
 #if WF_LAZY_LEAF_BOX
 	bool gateKnown = false;
 #else
-	const bool gateKnown = true;
 	cnt.template add<WFC_NODES>(1u);
 	if (!(intersectBox(L.o, invDir(L.d), v[0].w, v[1].w, v[2].w, v[3].w, v[4].w, v[5].w, leafFirst, leafLast) && leafFirst <= L.limit)) { wfLeafDone(L, stack); return; }
 #endif
-#pragma unroll
+GI_UNROLL
 	for (int slot = 0; slot < 2; ++slot)
 	{
 		const int lt = 2 * leaf + slot;

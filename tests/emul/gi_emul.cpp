@@ -220,7 +220,7 @@ EM_API int em_render_wavefront(const GiSceneDesc* desc, const GiCamera* cam, int
 	if (phase != 2)
 	{
 		// ---- light pass
-		uint32_t flags = bpt ? WF_LIGHT_SAVE : 0u;
+		uint32_t flags = bpt ? uint32_t(WF_LIGHT_SAVE) : 0u;
 		if (bpt && p->warmup) { flags |= WF_LIGHT_WARMUP; f.lightCacheCapacity = 0x7fffffffu; }
 		if (bpt) { bptCounters[0] = uint32_t(nls) * uint32_t(p->num_rays_per_light_sample); bptCounters[1] = 0; }
 		std::vector<F4> stateT(numLightPaths);

@@ -172,6 +172,36 @@ def test_error_behaviour(g, dev, box1):
         d.render_iteration(g.GI_RENDERER_PT, 1)
     with pytest.raises(g.GpugiError):
         g.Device(99)
+    # the other renderers' preconditions, option values, the device builders' inputs
+    from gpugi_b200 import scenes as _scenes
+    d.set_camera(g.camera_params(_scenes.BOX1_CAMERA["pos"], _scenes.BOX1_CAMERA["lookat"], _scenes.BOX1_CAMERA["fov"], 64, 64))
+    with pytest.raises(g.GpugiError, match="gi_set_light_samples"):
+        d.render_iteration(g.GI_RENDERER_PT, 1)
+    d.set_light_samples(g.LightSampler(box1).generate(128))
+    with pytest.raises(g.GpugiError, match="max_path_length"):
+        d.render_iteration(g.GI_RENDERER_PT, 1, 0)
+    with pytest.raises(g.GpugiError, match="num_rays_per_light_sample"):
+        d.render_iteration(g.GI_RENDERER_LPT, 1)
+    with pytest.raises(g.GpugiError, match="gi_alloc_light_cache"):
+        d.render_iteration(g.GI_RENDERER_BPT, 1, 16, num_rays_per_light_sample=64, light_cache_capacity=100000)
+    d.alloc_light_cache(100000)
+    with pytest.raises(g.GpugiError, match="smaller than the number of light paths"):
+        d.render_iteration(g.GI_RENDERER_BPT, 1, 16, num_rays_per_light_sample=64, light_cache_capacity=128 * 64 - 1)
+    with pytest.raises(g.GpugiError, match="exceeds the allocated"):
+        d.render_iteration(g.GI_RENDERER_BPT, 1, 16, num_rays_per_light_sample=64, light_cache_capacity=100001)
+    with pytest.raises(g.GpugiError, match="unknown renderer"):
+        d.render_iteration(7, 1)
+    for opt, val in ((g.GI_OPT_TRAVERSAL, 5), (g.GI_OPT_SCHEDULER, 9), (1234, 0)):
+        with pytest.raises(g.GpugiError):
+            d.set_option(opt, val)
+    d.render_iterations(g.GI_RENDERER_PT, [], 16)                      # an empty batch is a no-op
+    with pytest.raises(g.GpugiError, match="out of range"):
+        d.build_hierarchy(np.zeros((3, 3), np.float32), np.array([[0, 1, 3]], np.uint32))
+    with pytest.raises(g.GpugiError, match="empty mesh"):
+        d.build_hierarchy(np.zeros((3, 3), np.float32), np.zeros((0, 3), np.uint32))
+    # after all these refusals the context still renders
+    d.render_iteration(g.GI_RENDERER_PT, g.wang_hash(0), 16)
+    assert d.read_accumulator(64, 64)[..., :3].sum() > 0
     d.close()
 
 
