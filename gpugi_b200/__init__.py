@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 from . import _capi as capi
-from ._capi import (GI_RENDERER_PT, GI_RENDERER_LPT, GI_RENDERER_BPT, GI_TRAVERSAL_FAST, GI_TRAVERSAL_REFERENCE,
+from ._capi import (GI_RENDERER_PT, GI_RENDERER_LPT, GI_RENDERER_BPT, GI_RENDERER_WHITTED, GI_TRAVERSAL_FAST, GI_TRAVERSAL_REFERENCE,
                     GI_OPT_TRAVERSAL, GI_OPT_TEXTURE_FILTER, GI_OPT_SCHEDULER, GI_OPT_WF_REFILL_THRESHOLD, GI_OPT_WF_MIN_INNER,
                     GI_OPT_WF_BLOCKS_PER_SM, GI_OPT_COUNT_STEPS, GI_OPT_KERNEL_TIMING, GI_OPT_STREAMING, GI_SCHEDULER_WAVEFRONT, GI_SCHEDULER_MEGAKERNEL, RAY_MAX)
 
@@ -23,7 +23,7 @@ LIGHT_SAMPLE_DTYPE = np.dtype([("position", "<f4", 3), ("normal_phi", "<f4"), ("
 NODE_DTYPE = np.dtype([("min", "<f4", 3), ("first_child", "<u4"), ("max", "<f4", 3), ("escape", "<u4")])
 TRIANGLE_DTYPE = np.dtype([("v", "<u4", 3), ("material", "<u4")])
 
-RENDERERS = {"PT": GI_RENDERER_PT, "LPT": GI_RENDERER_LPT, "BPT": GI_RENDERER_BPT}
+RENDERERS = {"PT": GI_RENDERER_PT, "LPT": GI_RENDERER_LPT, "BPT": GI_RENDERER_BPT, "WPT": GI_RENDERER_WHITTED}
 
 
 class GpugiError(RuntimeError):

@@ -107,7 +107,7 @@ class GihSceneInfo(C.Structure):
 
 
 GI_OK = 0
-GI_RENDERER_PT, GI_RENDERER_LPT, GI_RENDERER_BPT = 0, 1, 2
+GI_RENDERER_PT, GI_RENDERER_LPT, GI_RENDERER_BPT, GI_RENDERER_WHITTED = 0, 1, 2, 3
 GI_TRAVERSAL_FAST, GI_TRAVERSAL_REFERENCE = 0, 1
 GI_OPT_TRAVERSAL, GI_OPT_TEXTURE_FILTER, GI_OPT_SCHEDULER = 0, 1, 2
 GI_OPT_WF_REFILL_THRESHOLD, GI_OPT_WF_MIN_INNER, GI_OPT_WF_BLOCKS_PER_SM, GI_OPT_COUNT_STEPS = 3, 4, 6, 7

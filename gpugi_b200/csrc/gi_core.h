@@ -641,7 +641,8 @@ GI_HD void bsdfDecisionProbabilities(const MaterialData& md, F3& preflect, F3& p
 }
 
 // __SampleBSDF, materials.glsl:118-277 (rejection loop disabled :232 => counter == 1)
-GI_HD F3 sampleBSDF(F3 incident, const MaterialData& md, uint32_t& seed, F3 N, F3& throughput, bool adjoint, float& pdf)
+// stopOnDiffuse = the STOP_ON_DIFFUSE_BOUNCE build of the Whitted ray tracer (:164-167): the diffuse decision ends the path
+GI_HD F3 sampleBSDF(F3 incident, const MaterialData& md, uint32_t& seed, F3 N, F3& throughput, bool adjoint, float& pdf, bool stopOnDiffuse = false)
 {
 	float cosTheta = dot(N, incident);
 	float cosThetaAbs = saturate(fabsf(cosTheta));
@@ -655,6 +656,7 @@ GI_HD F3 sampleBSDF(F3 incident, const MaterialData& md, uint32_t& seed, F3 N, F
 	float decision = randomFloat(seed);
 	if (avgPDiffuse > decision)
 	{
+		if (stopOnDiffuse) { throughput = f3(-1.0f, 0.0f, 0.0f); pdf = 0.0f; return f3(0.0f); }
 		throughput = throughput * ((md.Diffuse * pdiffuse) / avgPDiffuse);
 		if (cosTheta > 0.0f) N = -N;
 		F3 U, V;
@@ -688,7 +690,8 @@ GI_HD F3 sampleBSDF(F3 incident, const MaterialData& md, uint32_t& seed, F3 N, F
 }
 
 // __BSDF, materials.glsl:306-391
-GI_HD F3 evalBSDF(F3 incident, F3 excident, const MaterialData& md, F3 N, float& pdf, bool adjoint)
+// stopOnDiffuse: STOP_ON_DIFFUSE_BOUNCE, :355-358 (no refractive next event estimation)
+GI_HD F3 evalBSDF(F3 incident, F3 excident, const MaterialData& md, F3 N, float& pdf, bool adjoint, bool stopOnDiffuse = false)
 {
 	float cosTheta = dot(N, incident);
 	float cosThetaAbs = saturate(fabsf(cosTheta));
@@ -709,6 +712,7 @@ GI_HD F3 evalBSDF(F3 incident, F3 excident, const MaterialData& md, F3 N, float&
 		bsdf = bsdf + pdiffuse * md.Diffuse / GI_PI;
 		pdf += avg(pdiffuse) * saturate(cosThetaOut) / GI_PI;
 	}
+	if (stopOnDiffuse) return bsdf;
 	float eta = cosTheta < 0.0f ? 1.0f / md.RefractionIndexAvg : md.RefractionIndexAvg;
 	float etaSq = eta * eta;
 	float sinTheta2Sq = etaSq * (1.0f - cosTheta * cosTheta);
@@ -817,7 +821,7 @@ struct DirectLightQuery
 };
 
 GI_HD bool prepareDirectLight(const F4* lightSamples, F3 pos, F3 normal, int lightSampleIndex, F3 viewDir, const MaterialData& md, bool sampleAreaLights,
-                              DirectLightQuery& q)
+                              DirectLightQuery& q, bool stopOnDiffuse = false)
 {
 	F4 l0 = ld4(lightSamples + 2 * lightSampleIndex), l1 = ld4(lightSamples + 2 * lightSampleIndex + 1);
 	F3 dir = f3(l0.x, l0.y, l0.z) - pos;
@@ -844,17 +848,17 @@ GI_HD bool prepareDirectLight(const F4* lightSamples, F3 pos, F3 normal, int lig
 	q.dir = dir;
 	q.len = lightDist - GI_RAY_HIT_EPSILON * 2;
 	float pdf;
-	F3 bsdf = BSDF(viewDir, dir, md, normal, pdf);
+	F3 bsdf = evalBSDF(viewDir, dir, md, normal, pdf, false, stopOnDiffuse);
 	F3 irradiance = (surfaceCos / lightDistSq) * intensity;
 	q.radiance = irradiance * bsdf;
 	return true;
 }
 
 GI_HD F3 estimateDirectLight(const DFrame& f, F3 pos, F3 normal, int lightSampleIndex, F3 viewDir, const MaterialData& md, bool sampleAreaLights,
-                             PathCounters& pc, TraceStats* st)
+                             PathCounters& pc, TraceStats* st, bool stopOnDiffuse = false)
 {
 	DirectLightQuery q;
-	if (!prepareDirectLight(f.lightSamples, pos, normal, lightSampleIndex, viewDir, md, sampleAreaLights, q)) return f3(0.0f);
+	if (!prepareDirectLight(f.lightSamples, pos, normal, lightSampleIndex, viewDir, md, sampleAreaLights, q, stopOnDiffuse)) return f3(0.0f);
 	++pc.anyRays;
 	if (traceAny(f.scene, f.traversalMode, q.origin, q.dir, q.len, st)) return f3(0.0f);
 	return q.radiance;
@@ -910,6 +914,62 @@ GI_HD void pathtracePixel(const DFrame& f, int gx, int gy, PathCounters& pc, Tra
 	*reinterpret_cast<float4*>(px) = v;
 #else
 	px[0] += color.x; px[1] += color.y; px[2] += color.z;
+#endif
+}
+
+// whittedraytracer.comp:16-133 (STOP_ON_DIFFUSE_BOUNCE build, whittedraytracer.cpp:38-49), one invocation: specular chain from the camera,
+// two next-event samples at the first diffuse decision, alpha += 1
+GI_HD void whittedPixel(const DFrame& f, int gx, int gy, PathCounters& pc, TraceStats* st)
+{
+	const int NUM_LIGHT_SAMPLES = 2;
+	const float lightSampleWeight = float(f.numLightSamples) / float(NUM_LIGHT_SAMPLES);
+	uint32_t seed = wanghash(f.frameSeed); // InitCoherentRandomSeed (random.glsl:23-28): one stream for all pixels
+	F2 r = random2(seed);
+	float sx = (r.x + float(gx)) / float(f.width) * 2.0f - 1.0f;
+	float sy = (r.y + float(gy)) / float(f.height) * 2.0f - 1.0f;
+	F3 origin = f3(f.cam.position);
+	F3 dir = normalize(sx * f3(f.cam.u) + sy * f3(f.cam.v) + f3(f.cam.w));
+	++pc.cameraPaths;
+	F3 color = f3(0.0f), pathThroughput = f3(1.0f);
+	for (int i = 0; i < f.maxPathLength; ++i)
+	{
+		Hit h; bool fb = false;
+		++pc.closestRays;
+		traceClosest(f.scene, f.traversalMode, origin, dir, GI_RAY_MAX, h, st, &fb);
+		if (fb) ++pc.fallbackRays;
+		if (h.t == GI_RAY_MAX) break;
+		origin = origin + h.t * dir;
+		F3 hitNormal; F2 tc;
+		getTriangleHitInfo(f.scene, h.triangle, h.bary, hitNormal, tc);
+		MaterialData md = sampleMaterialData(f.scene, h.triangle.w, tc);
+		++pc.shadedVertices;
+		color = color + pathThroughput * md.Emissivity;
+		F3 pdiffuse = (f3(1.0f) - saturate(md.Fresnel0)) * md.Opacity; // GetDiffuseProbability, materials.glsl:96-101
+		float pdiffuseAvg = luminance(pdiffuse);
+		F3 throughput = f3(1.0f);
+		float pdf;
+		F3 sampleDirection = sampleBSDF(dir, md, seed, hitNormal, throughput, false, pdf, true);
+		if (throughput.x == -1.0f)
+		{
+			for (int ls = 0; ls < NUM_LIGHT_SAMPLES; ++ls)
+			{
+				int sampleIndex = int(randomUInt(seed) % uint32_t(f.numLightSamples));
+				F3 radiance = estimateDirectLight(f, origin, hitNormal, sampleIndex, dir, md, true, pc, st, true);
+				color = color + radiance * pathThroughput * (lightSampleWeight / (pdiffuseAvg + GI_DIVISOR_EPSILON));
+			}
+			break;
+		}
+		dir = sampleDirection;
+		origin = origin + dir * GI_RAY_HIT_EPSILON;
+		pathThroughput = pathThroughput * (throughput / (luminance(throughput) + GI_DIVISOR_EPSILON));
+	}
+	float* px = f.accum + 4 * (size_t(gy) * f.width + gx);
+#if defined(__CUDA_ARCH__)
+	float4 v = *reinterpret_cast<float4*>(px);
+	v.x += color.x; v.y += color.y; v.z += color.z; v.w += 1.0f;
+	*reinterpret_cast<float4*>(px) = v;
+#else
+	px[0] += color.x; px[1] += color.y; px[2] += color.z; px[3] += 1.0f;
 #endif
 }
 

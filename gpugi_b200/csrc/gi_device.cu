@@ -85,6 +85,17 @@ __global__ void __launch_bounds__(64) k_pathtrace(DFrame f, unsigned long long* 
 	flushCounters(counters, pc, st);
 }
 
+// whittedraytracer.comp: same launch shape (whittedraytracer.cpp:31-36).
+__global__ void __launch_bounds__(64) k_whitted(DFrame f, unsigned long long* counters)
+{
+	const int gx = blockIdx.x * 8 + (threadIdx.x & 7);
+	const int gy = blockIdx.y * 8 + (threadIdx.x >> 3);
+	PathCounters pc = {};
+	TraceStats st = {0, 0};
+	whittedPixel(f, gx, gy, pc, &st);
+	flushCounters(counters, pc, st);
+}
+
 // pathtracer_bidir.comp: same launch shape (bidirectionalpathtracer.cpp:200).
 __global__ void __launch_bounds__(64) k_bidir_eye(DFrame f, unsigned long long* counters)
 {
@@ -1456,6 +1467,13 @@ int gi_render_iteration(GiContext* c, const GiIterationParams* p)
 		if (pixelGrid.x && pixelGrid.y) { k_bidir_eye<<<pixelGrid, 64, 0, c->stream>>>(f, c->counters); ++c->launches; }
 		break;
 	}
+	case GI_RENDERER_WHITTED:
+		if (pixelGrid.x && pixelGrid.y)
+		{
+			k_whitted<<<pixelGrid, 64, 0, c->stream>>>(f, c->counters);
+			++c->launches;
+		}
+		break;
 	default: return fail(c, GI_ERR_INVALID, "unknown renderer");
 	}
 	GI_CUDA(c, cudaGetLastError());

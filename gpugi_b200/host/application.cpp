@@ -6,6 +6,7 @@
 #include "lightpathtracer.hpp"
 #include "logger.hpp"
 #include "pathtracer.hpp"
+#include "whittedraytracer.hpp"
 #include "scene.hpp"
 
 #include <cmath>
@@ -79,7 +80,7 @@ void Application::RegisterScriptCommands()
 	GlobalConfig::AddListener("cameraLookAt", "update renderer cam", updateCamera);
 	GlobalConfig::AddListener("cameraFOV", "update renderer cam", updateCamera);
 
-	GlobalConfig::AddParameter("renderer", {0}, "Change this value to change the active renderer (resets previous results!).\n0: Pathtracer\n1: LightPathtracer\n2: BidirectionalPathtracer");
+	GlobalConfig::AddParameter("renderer", {0}, "Change this value to change the active renderer (resets previous results!).\n0: Pathtracer\n1: LightPathtracer\n2: BidirectionalPathtracer\n4: Whitted Pathtracer");
 	GlobalConfig::AddListener("renderer", "ChangeRenderer", [this](const GlobalConfig::ParameterType& p) { SwitchRenderer(p); });
 	GlobalConfig::AddParameter("debugrenderer", {-1}, "Debug renderers are not part of this library; only -1 (off) is accepted.");
 	GlobalConfig::AddListener("debugrenderer", "Renderer", [](const GlobalConfig::ParameterType& p) { if (p[0].As<int>() != -1) LOG_ERROR("debug renderers are not part of gpugi_b200"); });
@@ -153,7 +154,8 @@ void Application::SwitchRenderer(const GlobalConfig::ParameterType& p)
 	case 0: m_rendererSystem->SetRenderer<Pathtracer>(); break;
 	case 1: m_rendererSystem->SetRenderer<LightPathtracer>(); break;
 	case 2: m_rendererSystem->SetRenderer<BidirectionalPathtracer>(); break;
-	default: LOG_ERROR("renderer " << p[0].As<int>() << " is not part of gpugi_b200 (0: Pathtracer, 1: LightPathtracer, 2: BidirectionalPathtracer)"); return;
+	case 4: m_rendererSystem->SetRenderer<WhittedRayTracer>(); break;
+	default: LOG_ERROR("renderer " << p[0].As<int>() << " is not part of gpugi_b200 (0: Pathtracer, 1: LightPathtracer, 2: BidirectionalPathtracer, 4: Whitted)"); return;
 	}
 }
 

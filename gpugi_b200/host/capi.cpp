@@ -9,6 +9,7 @@
 #include "lightpathtracer.hpp"
 #include "logger.hpp"
 #include "pathtracer.hpp"
+#include "whittedraytracer.hpp"
 #include "random.hpp"
 #include "application.hpp"
 #include "renderersystem.hpp"
@@ -219,8 +220,9 @@ int gih_rs_set_renderer(GihRendererSystem* h, int renderer)
 	case GI_RENDERER_PT: h->rs->SetRenderer<Pathtracer>(); return 0;
 	case GI_RENDERER_LPT: h->rs->SetRenderer<LightPathtracer>(); return 0;
 	case GI_RENDERER_BPT: h->rs->SetRenderer<BidirectionalPathtracer>(); return 0;
+	case GI_RENDERER_WHITTED: h->rs->SetRenderer<WhittedRayTracer>(); return 0;
 	}
-	LOG_ERROR("Unknown renderer index " << renderer << " (0 PT, 1 LPT, 2 BPT)");
+	LOG_ERROR("Unknown renderer index " << renderer << " (0 PT, 1 LPT, 2 BPT, 3 Whitted)");
 	return 1;
 }
 const char* gih_rs_renderer_name(GihRendererSystem* h)

@@ -166,7 +166,8 @@ typedef struct GiHit {
 } GiHit;
 
 /* Renderer selection = Application::SwitchRenderer cases 0,1,2 (application.cpp:233-241). */
-enum { GI_RENDERER_PT = 0, GI_RENDERER_LPT = 1, GI_RENDERER_BPT = 2 };
+enum { GI_RENDERER_PT = 0, GI_RENDERER_LPT = 1, GI_RENDERER_BPT = 2,
+       GI_RENDERER_WHITTED = 3 /* whittedraytracer.comp; one thread per pixel, the reference's launch shape, in either scheduler */ };
 
 /* gi_trace / gi_set_option modes */
 enum {

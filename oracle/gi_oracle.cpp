@@ -486,7 +486,7 @@ inline V3 GetDiffuseProbability(const MaterialData& md, float /*cosThetaAbs*/)
 // materials.glsl:118-277 (__SampleBSDF); rejection loop disabled by `plausible = true` (:232),
 // so counter == 1; Fresnel corrections return vec3(1.0) (:70-83).
 V3 SampleBSDFImpl(V3 incidentDirection, const MaterialData& md, uint32_t& seed, V3 N, V3& pathThroughput, bool adjoint, float& pdf,
-                  bool& isReflectedDiffuse)
+                  bool& isReflectedDiffuse, bool stopOnDiffuseBounce = false /* STOP_ON_DIFFUSE_BOUNCE, materials.glsl:164-167 */)
 {
 	float cosTheta = dot(N, incidentDirection);
 	float cosThetaAbs = saturate(fabsf(cosTheta));
@@ -502,6 +502,7 @@ V3 SampleBSDFImpl(V3 incidentDirection, const MaterialData& md, uint32_t& seed, 
 	float pathDecisionVar = Random(seed);
 	if (avgPDiffuse > pathDecisionVar)
 	{
+		if (stopOnDiffuseBounce) { pathThroughput = v3(-1.0f, 0.0f, 0.0f); return v3(0.0f); }
 		isReflectedDiffuse = true;
 		pathThroughput *= (md.Diffuse * pdiffuse) / avgPDiffuse;
 		if (cosTheta > 0.0f) N = -N;
@@ -541,7 +542,8 @@ V3 SampleBSDFImpl(V3 incidentDirection, const MaterialData& md, uint32_t& seed, 
 }
 
 // materials.glsl:306-391 (__BSDF)
-V3 BSDFImpl(V3 incidentDirection, V3 excidentDirection, const MaterialData& md, V3 N, float& pdf, bool adjoint, bool specularOnly)
+V3 BSDFImpl(V3 incidentDirection, V3 excidentDirection, const MaterialData& md, V3 N, float& pdf, bool adjoint, bool specularOnly,
+           bool stopOnDiffuseBounce = false /* materials.glsl:355-358: no refractive next event estimation */)
 {
 	V3 bsdf = v3(0.0f);
 	float cosTheta = dot(N, incidentDirection);
@@ -564,6 +566,7 @@ V3 BSDFImpl(V3 incidentDirection, V3 excidentDirection, const MaterialData& md, 
 			bsdf += pdiffuse * md.Diffuse / PI;
 			pdf += Avg(pdiffuse) * saturate(cosThetaOut) / PI;
 		}
+	if (stopOnDiffuseBounce) return bsdf;
 	float eta = cosTheta < 0.0f ? 1.0f / md.RefractionIndexAvg : md.RefractionIndexAvg;
 	float etaSq = eta * eta;
 	float sinTheta2Sq = etaSq * (1.0f - cosTheta * cosTheta);
@@ -619,7 +622,7 @@ struct Frame
 
 // lightsource.glsl:3-93 (EstimateDirectLight, no TRACERAY_IMPORTANCE_BREAK / CACHE_DIRECT_DIFFUSE)
 V3 EstimateDirectLight(const Frame& f, V3 pos, V3 normal, int lightSampleIndex, V3 viewDir, const MaterialData& md, bool sampleAreaLights, Counters& c,
-                       TraceCounters& tc)
+                       TraceCounters& tc, bool stopOnDiffuseBounce = false)
 {
 	const GiLightSample& ls = f.lightSamples[lightSampleIndex];
 	Ray lightRay;
@@ -637,7 +640,7 @@ V3 EstimateDirectLight(const Frame& f, V3 pos, V3 normal, int lightSampleIndex, 
 		{
 			V3 irradiance = (surfaceCos / lightDistSq) * v3(ls.intensity);
 			float pdf;
-			V3 bsdf = BSDF(viewDir, lightRay.Direction, md, normal, pdf);
+			V3 bsdf = BSDFImpl(viewDir, lightRay.Direction, md, normal, pdf, false, false, stopOnDiffuseBounce);
 			return irradiance * bsdf;
 		}
 	}
@@ -653,7 +656,7 @@ V3 EstimateDirectLight(const Frame& f, V3 pos, V3 normal, int lightSampleIndex, 
 			{
 				float pdf;
 				V3 lightSampleIntensity = v3(ls.intensity) * lightSampleIntensityFactor;
-				V3 bsdf = BSDF(viewDir, lightRay.Direction, md, normal, pdf);
+				V3 bsdf = BSDFImpl(viewDir, lightRay.Direction, md, normal, pdf, false, false, stopOnDiffuseBounce);
 				V3 irradiance = (surfaceCos / lightDistSq) * lightSampleIntensity;
 				return irradiance * bsdf;
 			}
@@ -1259,6 +1262,77 @@ OR_API int or_render_pt(const GiSceneDesc* desc, const GiCamera* cam, int w, int
 					PathtracerPixel(f, gx, gy, env, c, tc, cube);
 				}
 		}
+		addCounters(counters, c, tc);
+	}
+	return 0;
+}
+
+// whittedraytracer.comp:16-133 (compiled with STOP_ON_DIFFUSE_BOUNCE, whittedraytracer.cpp:38-49), one invocation
+void WhittedPixel(const Frame& f, int gx, int gy, Counters& c, TraceCounters& tc)
+{
+	const int NUM_LIGHT_SAMPLES = 2;
+	const float lightSampleWeight = float(f.numLightSamples) / NUM_LIGHT_SAMPLES;
+	const Scene& s = *f.scene;
+	uint32_t randomSeed = wanghash(f.frameSeed); // InitCoherentRandomSeed, random.glsl:23-28: the same stream for every pixel
+	V2 r = Random2(randomSeed);
+	float sx = (r.x + float(gx)) / float(f.width) * 2.0f - 1.0f;
+	float sy = (r.y + float(gy)) / float(f.height) * 2.0f - 1.0f;
+	Ray ray;
+	ray.Origin = v3(f.cam.position);
+	ray.Direction = normalize(sx * v3(f.cam.u) + sy * v3(f.cam.v) + v3(f.cam.w));
+	++c.camera_paths;
+	V3 color = v3(0.0f), pathThroughput = v3(1.0f);
+	for (int i = 0; i < f.maxPathLength; ++i)
+	{
+		GiTriangle triangle; V3 bary, geometryNormal;
+		float rayHit = RAY_MAX;
+		int hitIndex[2];
+		++c.closest_rays;
+		TraceRay(s, ray, rayHit, hitIndex, bary, triangle, geometryNormal, &tc);
+		if (rayHit == RAY_MAX) break;
+		ray.Origin = ray.Origin + rayHit * ray.Direction;
+		V3 hitNormal; V2 hitTexcoord;
+		GetTriangleHitInfo(s, triangle, bary, hitNormal, hitTexcoord);
+		MaterialData md = SampleMaterialData(s, int(triangle.material), hitTexcoord);
+		++c.shaded_vertices;
+		color += pathThroughput * md.Emissivity;
+		// GetDiffuseProbability, materials.glsl:96-101 (constant reflection: preflect = Fresnel0)
+		V3 pdiffuse = (v3(1.0f) - saturate(md.Fresnel0)) * md.Opacity;
+		float pdiffuseAvg = GetLuminance(pdiffuse);
+		V3 throughput = v3(1.0f);
+		float pdf; bool dummy;
+		V3 sampleDirection = SampleBSDFImpl(ray.Direction, md, randomSeed, hitNormal, throughput, false, pdf, dummy, true);
+		if (throughput.x == -1.0f)
+		{
+			for (int lightSample = 0; lightSample < NUM_LIGHT_SAMPLES; ++lightSample)
+			{
+				int sampleIndex = int(RandomUInt(randomSeed) % uint32_t(f.numLightSamples));
+				V3 radiance = EstimateDirectLight(f, ray.Origin, hitNormal, sampleIndex, ray.Direction, md, true, c, tc, true);
+				color += radiance * pathThroughput * (lightSampleWeight / (pdiffuseAvg + DIVISOR_EPSILON));
+			}
+			break;
+		}
+		ray.Direction = sampleDirection;
+		ray.Origin += ray.Direction * RAY_HIT_EPSILON;
+		pathThroughput *= throughput / (GetLuminance(throughput) + DIVISOR_EPSILON);
+	}
+	float* px = f.accum + 4 * (size_t(gy) * f.width + gx);
+	px[0] += color.x; px[1] += color.y; px[2] += color.z; px[3] += 1.0f; // vec4(color, 1.0) (:130-132)
+}
+
+// WhittedRayTracer::Draw (whittedraytracer.cpp:31-36): (W/8) x (H/8) groups of 8x8
+OR_API int or_render_whitted(const GiSceneDesc* desc, const GiCamera* cam, int w, int h, const GiLightSample* ls, int nls, uint32_t frameSeed, int maxLen,
+                             float* accum, OrCounters* counters)
+{
+	Scene s = makeScene(desc);
+	Frame f = makeFrame(s, cam, w, h, ls, nls, frameSeed, maxLen, accum);
+	const int gw = w / 8, gh = h / 8;
+#pragma omp parallel
+	{
+		Counters c; memset(&c, 0, sizeof(c)); TraceCounters tc = {0, 0};
+#pragma omp for schedule(dynamic, 1)
+		for (int t = 0; t < gw * gh; ++t)
+			for (int l = 0; l < 64; ++l) WhittedPixel(f, (t % gw) * 8 + (l & 7), (t / gw) * 8 + (l >> 3), c, tc);
 		addCounters(counters, c, tc);
 	}
 	return 0;

@@ -50,6 +50,10 @@ lib.or_intersect_box.restype = C.c_int
 lib.or_intersect_box.argtypes = [vp, vp, vp, vp, C.POINTER(f32), C.POINTER(f32)]
 lib.or_intersect_triangle.restype = C.c_int
 lib.or_intersect_triangle.argtypes = [vp, vp, vp, vp, vp, C.POINTER(f32), vp, vp]
+lib.or_render_whitted.restype = C.c_int
+lib.or_render_whitted.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_int, u32, C.c_int, vp, vp]
+lib.or_set_environment_cube.restype = None
+lib.or_set_environment_cube.argtypes = [C.c_int, vp]
 lib.or_render_pt.restype = C.c_int
 lib.or_render_pt.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_int, u32, C.c_int, vp, vp, vp, vp]
 lib.or_render_lpt.restype = C.c_int
@@ -146,6 +150,15 @@ def render_pt(scene_desc, cam, w, h, light_samples, frame_seed, max_len=16, env_
     reg = _region(region)
     lib.or_render_pt(C.addressof(scene_desc), _cam_ptr(cam), w, h, _p(ls), ls.shape[0], frame_seed & 0xFFFFFFFF, max_len, _p(env) if env is not None else None,
                      C.addressof(reg) if reg is not None else None, _p(accum), C.addressof(cnt))
+    return accum, cnt.as_dict()
+
+
+def render_whitted(scene_desc, cam, w, h, light_samples, frame_seed, max_len=16, accum=None):
+    ls = np.ascontiguousarray(light_samples, dtype=LIGHT_SAMPLE_DTYPE)
+    if accum is None:
+        accum = np.zeros((h, w, 4), dtype=np.float32)
+    cnt = OrCounters()
+    lib.or_render_whitted(C.addressof(scene_desc), _cam_ptr(cam), w, h, _p(ls), ls.shape[0], frame_seed & 0xFFFFFFFF, max_len, _p(accum), C.addressof(cnt))
     return accum, cnt.as_dict()
 
 

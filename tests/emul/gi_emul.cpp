@@ -139,6 +139,10 @@ EM_API int em_render(const GiSceneDesc* desc, const GiCamera* cam, int w, int h,
 		for (int by = 0; by < gh; ++by) for (int bx = 0; bx < gw; ++bx) for (int t = 0; t < 64; ++t)
 			pathtracePixel(f, bx * 8 + (t & 7), by * 8 + (t >> 3), pc, &st);
 		break;
+	case GI_RENDERER_WHITTED:
+		for (int by = 0; by < gh; ++by) for (int bx = 0; bx < gw; ++bx) for (int t = 0; t < 64; ++t)
+			whittedPixel(f, bx * 8 + (t & 7), by * 8 + (t >> 3), pc, &st);
+		break;
 	case GI_RENDERER_LPT:
 		for (uint32_t gid = 0; gid < (numLightPaths / 64u) * 64u; ++gid) lighttracePath<false, false>(f, gid, pc, &st);
 		break;

@@ -377,3 +377,22 @@ def test_obox_hierarchy_traversal(g, orc, emul, scenes, tmp_path):
     sc2 = g.Scene.load(str(tmp_path / "ob.json"), bvh_type=1)
     assert sc2.obox_nodes().tobytes() == ob.tobytes()
     assert g.Scene.load(str(tmp_path / "ob.json"), bvh_type=0).obox_nodes() is None
+
+
+def test_whitted_matches_oracle(orc, emul, scenes, box1):
+    """whittedraytracer.comp: STOP_ON_DIFFUSE_BOUNCE sampling, coherent seed, two light samples at the diffuse stop,
+    alpha += 1 -- the device logic (host build) against the oracle, bit for bit with one thread."""
+    os.environ["OMP_NUM_THREADS"] = "1"
+    W = H = 48
+    C = scenes.BOX1_CAMERA
+    cam = orc.camera(C["pos"], C["lookat"], C["fov"], W, H)
+    s = _light_sampler(orc, box1).generate(128)
+    for seed, max_len in ((3, 16), (11, 2)):
+        ref, rc = orc.render_whitted(box1.desc, cam, W, H, s, seed, max_len)
+        img, ec = emul.render(box1.desc, cam, W, H, s, 3, seed, max_len, mode=1)
+        assert np.array_equal(img, ref)
+        assert np.all(img[..., 3] == 1.0) and img[..., :3].sum() > 0
+        for k in ("camera_paths", "closest_rays", "any_rays", "shaded_vertices"):
+            assert ec[k] == rc[k], k
+        fast, _ = emul.render(box1.desc, cam, W, H, s, 3, seed, max_len, mode=0)
+        assert np.array_equal(fast, ref)

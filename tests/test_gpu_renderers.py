@@ -667,3 +667,20 @@ def test_device_light_sampling(g, scenes, scene_kind, tmp_path):
     assert ia[..., :3].mean() > 0
     assert pixel_mismatch_fraction(ib, ia, 1e-3) < 0.01
     host.close(); devs.close()
+
+
+def test_whitted_raytracer_matches_oracle(g, orc, scenes, box1, sponza_small):
+    """WhittedRayTracer (renderer 4 of the reference's list) through the Renderer API against the oracle."""
+    for sc, cam, W, H in ((box1, scenes.BOX1_CAMERA, 128, 128), (sponza_small, scenes.SPONZA_CAMERA, 160, 96)):
+        rs = _rs(g, scenes, sc, "WPT", W, H, cam=cam)
+        assert rs.GetRendererName() == "WPT" and rs.GetNumInitialLightSamples() == 128
+        samples, seed, camp = rs.GetInitialLightSamples(), rs.GetFrameSeed(), rs.GetCamera()
+        rs.Draw()
+        img = rs.ReadBackbuffer()
+        ref, rc = orc.render_whitted(sc.desc, camp, W, H, samples, seed, 16)
+        assert np.all(img[..., 3] == 1.0) and img[..., :3].sum() > 0
+        assert pixel_mismatch_fraction(img, ref, 1e-2) < 0.03
+        cnt = rs.device.counters()
+        assert cnt["camera_paths"] == (W // 8) * (H // 8) * 64
+        assert abs(cnt["closest_rays"] - rc["closest_rays"]) / rc["closest_rays"] < 0.01
+        rs.close()
