@@ -15,7 +15,7 @@ import numpy as np
 from . import _capi as capi
 from ._capi import (GI_RENDERER_PT, GI_RENDERER_LPT, GI_RENDERER_BPT, GI_RENDERER_WHITTED, GI_TRAVERSAL_FAST, GI_TRAVERSAL_REFERENCE,
                     GI_OPT_TRAVERSAL, GI_OPT_TEXTURE_FILTER, GI_OPT_SCHEDULER, GI_OPT_WF_REFILL_THRESHOLD, GI_OPT_WF_MIN_INNER,
-                    GI_OPT_WF_BLOCKS_PER_SM, GI_OPT_COUNT_STEPS, GI_OPT_KERNEL_TIMING, GI_OPT_STREAMING, GI_SCHEDULER_WAVEFRONT, GI_SCHEDULER_MEGAKERNEL, RAY_MAX)
+                    GI_OPT_WF_BLOCKS_PER_SM, GI_OPT_COUNT_STEPS, GI_OPT_KERNEL_TIMING, GI_OPT_STREAMING, GI_OPT_DEVICE_BUILDER, GI_BUILDER_LBVH, GI_BUILDER_PLOC, GI_SCHEDULER_WAVEFRONT, GI_SCHEDULER_MEGAKERNEL, RAY_MAX)
 
 RAY_DTYPE = np.dtype([("origin", "<f4", 3), ("t_max", "<f4"), ("direction", "<f4", 3), ("flags", "<u4")])
 HIT_DTYPE = np.dtype([("t", "<f4"), ("leaf_tri", "<i4"), ("bary_y", "<f4"), ("bary_z", "<f4")])
@@ -73,7 +73,7 @@ class Scene:
     def from_mesh(cls, positions, normals, texcoords, triangles, tri_materials, materials, texture_dir="", build_method="sah", bvh_type=0):
         """Synthetic scene: mesh arrays + material dict (JSON 'materials' object, order = material index).
         bvh_type 1: oriented boxes (the reference's second accelerator, GlobalConfig "bvhType").
-        build_method: "sah" (bim_sahspilt.cpp sweep, host), "kd" (bim_kdtree.cpp median, host), "lbvh" (gi_build_hierarchy: on the GPU)."""
+        build_method: "sah" (bim_sahspilt.cpp sweep, host), "kd" (bim_kdtree.cpp median, host), "lbvh" / "ploc" (gi_build_hierarchy: on the GPU, Karras radix tree / PLOC clustering)."""
         positions = np.ascontiguousarray(positions, dtype=np.float32)
         normals = np.ascontiguousarray(normals, dtype=np.float32)
         texcoords = np.ascontiguousarray(texcoords, dtype=np.float32)
@@ -83,7 +83,7 @@ class Scene:
         assert triangles.shape[1] == 3 and tri_materials.shape[0] == triangles.shape[0]
         env = json.dumps({"scene": "", "accelerator": "obox" if bvh_type else "aabox", "materials": materials, "lights": {}, "cameras": {}})
         h = capi.host.gih_scene_from_mesh_bvh(_vp(positions), _vp(normals), _vp(texcoords), positions.shape[0], _vp(triangles), _vp(tri_materials),
-                                              triangles.shape[0], env.encode(), os.fsencode(texture_dir), {"sah": 0, "kd": 1, "lbvh": 2}[build_method], int(bvh_type))
+                                              triangles.shape[0], env.encode(), os.fsencode(texture_dir), {"sah": 0, "kd": 1, "lbvh": 2, "ploc": 3}[build_method], int(bvh_type))
         if not h:
             raise GpugiError("Scene.from_mesh: " + capi.host.gih_last_error().decode())
         return cls(h)
@@ -261,14 +261,13 @@ class Device:
         triangles = np.ascontiguousarray(triangles, dtype=np.uint32)
         mats = None if tri_materials is None else np.ascontiguousarray(tri_materials, dtype=np.uint32)
         T = triangles.shape[0]
-        L = (T + 1) // 2
-        nodes = np.zeros(max(2 * L - 1, 1), dtype=NODE_DTYPE)
-        leaves = np.zeros(max(2 * L, 2), dtype=TRIANGLE_DTYPE)
-        parents = np.zeros(max(2 * L - 1, 1), dtype=np.uint32)
+        nodes = np.zeros(max(2 * T - 1, 1), dtype=NODE_DTYPE)
+        leaves = np.zeros(max(2 * T, 2), dtype=TRIANGLE_DTYPE)
+        parents = np.zeros(max(2 * T - 1, 1), dtype=np.uint32)
         n, lv = C.c_uint32(), C.c_uint32()
         self._check(capi.dev.gi_build_hierarchy(self._c, _vp(positions), positions.shape[0], _vp(triangles), _vp(mats) if mats is not None else None, T,
                                                 _vp(nodes), _vp(leaves), _vp(parents), C.byref(n), C.byref(lv)), "gi_build_hierarchy")
-        return nodes[: n.value], leaves, parents[: n.value], lv.value
+        return nodes[: n.value], leaves[: n.value + 1], parents[: n.value], lv.value
 
     def render_iteration(self, renderer, frame_seed, max_path_length=16, num_rays_per_light_sample=0, light_cache_capacity=0, warmup=0):
         p = capi.GiIterationParams(renderer=int(renderer), frame_seed=int(frame_seed) & 0xFFFFFFFF, max_path_length=int(max_path_length),

@@ -113,6 +113,8 @@ GI_OPT_TRAVERSAL, GI_OPT_TEXTURE_FILTER, GI_OPT_SCHEDULER = 0, 1, 2
 GI_OPT_WF_REFILL_THRESHOLD, GI_OPT_WF_MIN_INNER, GI_OPT_WF_BLOCKS_PER_SM, GI_OPT_COUNT_STEPS = 3, 4, 6, 7
 GI_OPT_KERNEL_TIMING = 8
 GI_OPT_STREAMING = 9
+GI_OPT_DEVICE_BUILDER = 10
+GI_BUILDER_LBVH, GI_BUILDER_PLOC = 0, 1
 GI_KERNEL_TRACE, GI_KERNEL_SHADE, GI_KERNEL_GENERATE, GI_KERNEL_MEGAKERNEL, GI_KERNEL_OTHER, GI_KERNEL_CLASS_COUNT = 0, 1, 2, 3, 4, 5
 GI_SCHEDULER_WAVEFRONT, GI_SCHEDULER_MEGAKERNEL = 0, 1
 GI_TEX_SRGB8_ALPHA8, GI_TEX_RGBA8, GI_TEX_RGBA32F = 0, 1, 2

@@ -484,6 +484,7 @@ struct GiContext
 	BptPipe bpt;
 	WfRun run[2];                    // [0]: PT / LPT / BPT light pass / stream, [1]: BPT eye pass of a pipelined batch
 	int streamingOption = 0;         // GI_OPT_STREAMING
+	int deviceBuilder = GI_BUILDER_PLOC; // GI_OPT_DEVICE_BUILDER
 	uint32_t lightSlot = 0;          // ring slot of the light-sample set the next iteration uses
 	// asynchronous read-out (gi_read_accumulator_async)
 	cudaStream_t copyStream = nullptr;
@@ -1005,6 +1006,9 @@ int gi_set_option(GiContext* c, int option, int value)
 	switch (option)
 	{
 	case GI_OPT_STREAMING: c->streamingOption = value ? 1 : 0; return GI_OK;
+	case GI_OPT_DEVICE_BUILDER:
+		if (value != GI_BUILDER_LBVH && value != GI_BUILDER_PLOC) return fail(c, GI_ERR_INVALID, "GI_OPT_DEVICE_BUILDER: unknown builder");
+		c->deviceBuilder = value; return GI_OK;
 	case GI_OPT_TRAVERSAL:
 		if (value != GI_TRAVERSAL_FAST && value != GI_TRAVERSAL_REFERENCE) return fail(c, GI_ERR_INVALID, "GI_OPT_TRAVERSAL: unknown mode");
 		c->traversal = value; return GI_OK;
@@ -1603,7 +1607,10 @@ int gi_build_hierarchy(GiContext* c, const float* positions, uint32_t num_vertic
 	for (size_t i = 0; i < size_t(num_triangles) * 3; ++i)
 		if (triangles[i] >= num_vertices) return fail(c, GI_ERR_INVALID, "gi_build_hierarchy: vertex index out of range");
 	GI_CUDA(c, cudaSetDevice(c->device));
-	const uint32_t T = num_triangles, L = (T + 1u) / 2u, N = 2u * L - 1u, I = L - 1u;
+	const uint32_t T = num_triangles;
+	const bool ploc = c->deviceBuilder == GI_BUILDER_PLOC;
+	const uint32_t Lcap = ploc ? T : (T + 1u) / 2u;   // PLOC: leaves by mutual nearest neighbours, anything between T/2 and T of them
+	uint32_t L = (T + 1u) / 2u, N = 2u * L - 1u, I = L - 1u;
 	cudaStream_t st = c->stream;
 	std::vector<void*> allocs;
 	auto dalloc = [&](size_t bytes) -> void* { void* p = nullptr; if (cudaMalloc(&p, std::max<size_t>(bytes, 16)) != cudaSuccess) return nullptr; allocs.push_back(p); return p; };
@@ -1616,20 +1623,20 @@ int gi_build_hierarchy(GiContext* c, const float* positions, uint32_t num_vertic
 	unsigned long long* dCodesSorted = static_cast<unsigned long long*>(dalloc(size_t(T) * 8));
 	uint32_t* dIds = static_cast<uint32_t*>(dalloc(size_t(T) * 4));
 	uint32_t* dIdsSorted = static_cast<uint32_t*>(dalloc(size_t(T) * 4));
-	unsigned long long* dLeafCodes = static_cast<unsigned long long*>(dalloc(size_t(L) * 8));
-	I4* dLeafTris = static_cast<I4*>(dalloc(size_t(L) * 2 * 16));
+	unsigned long long* dLeafCodes = static_cast<unsigned long long*>(dalloc(size_t(Lcap) * 8));
+	I4* dLeafTris = static_cast<I4*>(dalloc(size_t(Lcap) * 2 * 16));
 	LbvhTree tr;
-	tr.left = static_cast<uint32_t*>(dalloc(size_t(I) * 4)); tr.right = static_cast<uint32_t*>(dalloc(size_t(I) * 4));
-	tr.parent = static_cast<uint32_t*>(dalloc(size_t(I) * 4)); tr.first = static_cast<uint32_t*>(dalloc(size_t(I) * 4)); tr.last = static_cast<uint32_t*>(dalloc(size_t(I) * 4));
-	tr.leafParent = static_cast<uint32_t*>(dalloc(size_t(L) * 4));
-	tr.boxMin = static_cast<float*>(dalloc(size_t(I) * 12)); tr.boxMax = static_cast<float*>(dalloc(size_t(I) * 12));
-	tr.leafMin = static_cast<float*>(dalloc(size_t(L) * 12)); tr.leafMax = static_cast<float*>(dalloc(size_t(L) * 12));
-	tr.visits = static_cast<uint32_t*>(dalloc(size_t(I) * 4));
-	uint32_t* dPreInner = static_cast<uint32_t*>(dalloc(size_t(I) * 4));
-	uint32_t* dPreLeaf = static_cast<uint32_t*>(dalloc(size_t(L) * 4));
+	tr.left = static_cast<uint32_t*>(dalloc(size_t(Lcap) * 4)); tr.right = static_cast<uint32_t*>(dalloc(size_t(Lcap) * 4));
+	tr.parent = static_cast<uint32_t*>(dalloc(size_t(Lcap) * 4)); tr.first = static_cast<uint32_t*>(dalloc(size_t(Lcap) * 4)); tr.last = static_cast<uint32_t*>(dalloc(size_t(Lcap) * 4));
+	tr.leafParent = static_cast<uint32_t*>(dalloc(size_t(Lcap) * 4));
+	tr.boxMin = static_cast<float*>(dalloc(size_t(Lcap) * 12)); tr.boxMax = static_cast<float*>(dalloc(size_t(Lcap) * 12));
+	tr.leafMin = static_cast<float*>(dalloc(size_t(Lcap) * 12)); tr.leafMax = static_cast<float*>(dalloc(size_t(Lcap) * 12));
+	tr.visits = static_cast<uint32_t*>(dalloc(size_t(Lcap) * 4));
+	uint32_t* dPreInner = static_cast<uint32_t*>(dalloc(size_t(Lcap) * 4));
+	uint32_t* dPreLeaf = static_cast<uint32_t*>(dalloc(size_t(Lcap) * 4));
 	uint32_t* dDepth = static_cast<uint32_t*>(dalloc(4));
-	F4* dNodes = static_cast<F4*>(dalloc(size_t(N) * 32));
-	uint32_t* dParents = static_cast<uint32_t*>(dalloc(size_t(N) * 4));
+	F4* dNodes = static_cast<F4*>(dalloc(size_t(2u * Lcap) * 32));
+	uint32_t* dParents = static_cast<uint32_t*>(dalloc(size_t(2u * Lcap) * 4));
 	size_t sortBytes = 0;
 	cub::DeviceRadixSort::SortPairs(nullptr, sortBytes, dCodes, dCodesSorted, dIds, dIdsSorted, int(T), 0, 63, st);
 	void* dSortTmp = dalloc(sortBytes);
@@ -1644,7 +1651,7 @@ int gi_build_hierarchy(GiContext* c, const float* positions, uint32_t num_vertic
 	if (dMat) step(cudaMemcpyAsync(dMat, triangle_materials, size_t(T) * 4, cudaMemcpyHostToDevice, st));
 	const unsigned initBounds[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
 	step(cudaMemcpyAsync(dBounds, initBounds, sizeof(initBounds), cudaMemcpyHostToDevice, st));
-	step(cudaMemsetAsync(tr.visits, 0, std::max<size_t>(size_t(I) * 4, 4), st));
+	step(cudaMemsetAsync(tr.visits, 0, std::max<size_t>(size_t(Lcap) * 4, 4), st));
 	step(cudaMemsetAsync(dDepth, 0, 4, st));
 	if (e == cudaSuccess)
 	{
@@ -1652,15 +1659,95 @@ int gi_build_hierarchy(GiContext* c, const float* positions, uint32_t num_vertic
 		k_lbvh_bounds<<<unsigned(c->numSMs) * 4u, B, 0, st>>>(dPos, num_vertices, dBounds);
 		k_lbvh_morton<<<(T + B - 1) / B, B, 0, st>>>(dPos, dTri, T, dBounds, dCodes, dIds);
 		step(cub::DeviceRadixSort::SortPairs(dSortTmp, sortBytes, dCodes, dCodesSorted, dIds, dIdsSorted, int(T), 0, 63, st));
-		k_lbvh_leaves<<<(L + B - 1) / B, B, 0, st>>>(dPos, dTri, dMat, dIdsSorted, dCodesSorted, T, L, dLeafTris, dLeafCodes, tr);
+		if (!ploc)
+			k_lbvh_leaves<<<(L + B - 1) / B, B, 0, st>>>(dPos, dTri, dMat, dIdsSorted, dCodesSorted, T, L, dLeafTris, dLeafCodes, tr);
+		else
+		{
+			// leaves by mutual nearest neighbours (gi_lbvh.cuh); scratch: the not yet used tree arrays
+			float* tmn = static_cast<float*>(dalloc(size_t(T) * 12)); float* tmx = static_cast<float*>(dalloc(size_t(T) * 12));
+			uint32_t* pNearest = static_cast<uint32_t*>(dalloc(size_t(T) * 4)); uint32_t* pValid = static_cast<uint32_t*>(dalloc(size_t(T) * 4));
+			uint32_t* pOffset = static_cast<uint32_t*>(dalloc(size_t(T) * 4)); uint32_t* pCount = static_cast<uint32_t*>(dalloc(4));
+			size_t pScanBytes = 0;
+			cub::DeviceScan::ExclusiveSum(nullptr, pScanBytes, pValid, pOffset, int(T), st);
+			void* pScanTmp = dalloc(pScanBytes);
+			if (!(tmn && tmx && pNearest && pValid && pOffset && pCount && pScanTmp)) { freeAll(); return fail(c, GI_ERR_CUDA, "gi_build_hierarchy: device allocation failed"); }
+			PlocTree view = {};
+			view.boxMin = tmn; view.boxMax = tmx;
+			k_pair_boxes<<<(T + B - 1) / B, B, 0, st>>>(dPos, dTri, dIdsSorted, T, tmn, tmx);
+			k_ploc_nearest<<<(T + B - 1) / B, B, 0, st>>>(T, nullptr, view, pNearest);
+			k_pair_flags<<<(T + B - 1) / B, B, 0, st>>>(T, pNearest, pValid);
+			step(cub::DeviceScan::ExclusiveSum(pScanTmp, pScanBytes, pValid, pOffset, int(T), st));
+			k_pair_emit<<<(T + B - 1) / B, B, 0, st>>>(T, dTri, dMat, dIdsSorted, dCodesSorted, pNearest, pValid, pOffset, tmn, tmx, dLeafTris, dLeafCodes, tr, pCount);
+			c->launches += 4;
+			step(cudaMemcpyAsync(&L, pCount, 4, cudaMemcpyDeviceToHost, st));
+			step(cudaStreamSynchronize(st));
+			if (e == cudaSuccess) { N = 2u * L - 1u; I = L - 1u; }
+		}
 		c->launches += 4;
-		if (I > 0)
+		if (I > 0 && c->deviceBuilder == GI_BUILDER_LBVH)
 		{
 			k_lbvh_tree<<<(I + B - 1) / B, B, 0, st>>>(dLeafCodes, int(L), tr);
 			k_lbvh_boxes<<<(L + B - 1) / B, B, 0, st>>>(int(L), tr);
 			k_lbvh_preorder<<<(N + B - 1) / B, B, 0, st>>>(int(L), tr, dPreInner, dPreLeaf, dDepth);
 			k_lbvh_emit<<<(N + B - 1) / B, B, 0, st>>>(int(L), tr, dPreInner, dPreLeaf, dNodes, dParents);
 			c->launches += 4;
+		}
+		else if (I > 0)
+		{
+			// PLOC over the Morton-ordered leaves (gi_lbvh.cuh)
+			PlocTree pt;
+			pt.boxMin = static_cast<float*>(dalloc(size_t(N) * 12)); pt.boxMax = static_cast<float*>(dalloc(size_t(N) * 12));
+			pt.left = static_cast<uint32_t*>(dalloc(size_t(N) * 4)); pt.right = static_cast<uint32_t*>(dalloc(size_t(N) * 4));
+			pt.parent = static_cast<uint32_t*>(dalloc(size_t(N) * 4)); pt.size = static_cast<uint32_t*>(dalloc(size_t(N) * 4)); pt.leaves = static_cast<uint32_t*>(dalloc(size_t(N) * 4));
+			uint32_t* clA = static_cast<uint32_t*>(dalloc(size_t(L) * 4)); uint32_t* clB = static_cast<uint32_t*>(dalloc(size_t(L) * 4));
+			uint32_t* dNearest = static_cast<uint32_t*>(dalloc(size_t(L) * 4)); uint32_t* dMerged = static_cast<uint32_t*>(dalloc(size_t(L) * 4));
+			uint32_t* dValid = static_cast<uint32_t*>(dalloc(size_t(L) * 4)); uint32_t* dOffset = static_cast<uint32_t*>(dalloc(size_t(L) * 4));
+			uint32_t* dCounters = static_cast<uint32_t*>(dalloc(8)); // [0] next inner node id, [1] cluster count after the pass
+			uint32_t* dPre = static_cast<uint32_t*>(dalloc(size_t(N) * 4)); uint32_t* dLeafIndex = static_cast<uint32_t*>(dalloc(size_t(L) * 4));
+			I4* dLeafTrisOut = static_cast<I4*>(dalloc(size_t(L) * 2 * 16));
+			size_t scanBytes = 0;
+			cub::DeviceScan::ExclusiveSum(nullptr, scanBytes, dValid, dOffset, int(L), st);
+			void* dScanTmp = dalloc(scanBytes);
+			if (!(pt.boxMin && pt.boxMax && pt.left && pt.right && pt.parent && pt.size && pt.leaves && clA && clB && dNearest && dMerged && dValid && dOffset && dCounters &&
+			      dPre && dLeafIndex && dLeafTrisOut && dScanTmp))
+			{
+				freeAll();
+				return fail(c, GI_ERR_CUDA, "gi_build_hierarchy: device allocation failed");
+			}
+			const uint32_t initCounters[2] = {L, L};
+			step(cudaMemcpyAsync(dCounters, initCounters, 8, cudaMemcpyHostToDevice, st));
+			k_ploc_init<<<(L + B - 1) / B, B, 0, st>>>(L, tr, pt, clA);
+			++c->launches;
+			uint32_t n = L;
+			auto pass = [&](bool forced)
+			{
+				const unsigned g = (n + B - 1) / B;
+				if (forced) k_ploc_force_pairs<<<g, B, 0, st>>>(n, dNearest);
+				else k_ploc_nearest<<<g, B, 0, st>>>(n, clA, pt, dNearest);
+				k_ploc_merge<<<g, B, 0, st>>>(n, clA, dNearest, pt, dCounters, dMerged, dValid);
+				step(cub::DeviceScan::ExclusiveSum(dScanTmp, scanBytes, dValid, dOffset, int(n), st));
+				k_ploc_compact<<<g, B, 0, st>>>(n, dMerged, dValid, dOffset, clB, dCounters + 1);
+				c->launches += 3;
+				uint32_t next = n;
+				step(cudaMemcpyAsync(&next, dCounters + 1, 4, cudaMemcpyDeviceToHost, st));
+				step(cudaStreamSynchronize(st));
+				return next;
+			};
+			while (n > 1u && e == cudaSuccess)
+			{
+				uint32_t next = pass(false);
+				if (next >= n && e == cudaSuccess) next = pass(true); // (never taken with the tie rule of k_ploc_nearest)
+				if (next >= n) { if (e == cudaSuccess) e = cudaErrorUnknown; break; }
+				std::swap(clA, clB);
+				n = next;
+			}
+			if (e == cudaSuccess)
+			{
+				k_ploc_preorder<<<(N + B - 1) / B, B, 0, st>>>(N, L, pt, dPre, dLeafIndex, dDepth);
+				k_ploc_emit<<<(N + B - 1) / B, B, 0, st>>>(N, L, pt, dPre, dLeafIndex, dLeafTris, dNodes, dParents, dLeafTrisOut);
+				c->launches += 2;
+				dLeafTris = dLeafTrisOut; // leaves renumbered in preorder
+			}
 		}
 		step(cudaGetLastError());
 	}

@@ -61,14 +61,15 @@ GihScene* gih_scene_from_mesh_bvh(const float* positions, const float* normals, 
 	                       reinterpret_cast<const gi::bim::Vec2*>(texcoords), num_vertices, reinterpret_cast<const gi::bim::UVec3*>(triangles), tri_materials,
 	                       num_triangles);
 	model->useJsonMaterialOrder(); // TRIANGLE_MAT indices follow the order of the JSON "materials" object
-	if (build_method == 2)
+	if (build_method == 2 || build_method == 3)
 	{
 		// device-side LBVH (gi_build_hierarchy): same layout as the host builders, built on the GPU
 		GiContext* ctx = nullptr;
 		if (gi_create(0, &ctx) != GI_OK) { LOG_ERROR("device hierarchy build: " << gi_last_error(nullptr)); return nullptr; }
-		const uint32_t L = (num_triangles + 1u) / 2u, N = 2u * L - 1u;
+		gi_set_option(ctx, GI_OPT_DEVICE_BUILDER, build_method == 2 ? GI_BUILDER_LBVH : GI_BUILDER_PLOC);
+		const uint32_t N = 2u * num_triangles - 1u; // worst case: one triangle per leaf
 		std::vector<GiNode> nodes(N);
-		std::vector<GiTriangle> leaves(size_t(L) * 2);
+		std::vector<GiTriangle> leaves(size_t(num_triangles) * 2);
 		std::vector<uint32_t> parents(N);
 		uint32_t numNodes = 0, levels = 0;
 		int st = gi_build_hierarchy(ctx, positions, num_vertices, triangles, tri_materials, num_triangles, nodes.data(), leaves.data(), parents.data(), &numNodes, &levels);
@@ -82,7 +83,7 @@ GihScene* gih_scene_from_mesh_bvh(const float* positions, const float* normals, 
 			hb[i].min = {nodes[i].min[0], nodes[i].min[1], nodes[i].min[2]}; hb[i].max = {nodes[i].max[0], nodes[i].max[1], nodes[i].max[2]};
 		}
 		static_assert(sizeof(GiTriangle) == sizeof(gi::bim::UVec4), "leaf slot layout");
-		model->chunk().setHierarchy(hn.data(), parents.data(), hb.data(), numNodes, reinterpret_cast<const gi::bim::UVec4*>(leaves.data()), uint32_t(leaves.size()), levels);
+		model->chunk().setHierarchy(hn.data(), parents.data(), hb.data(), numNodes, reinterpret_cast<const gi::bim::UVec4*>(leaves.data()), numNodes + 1u, levels);
 	}
 	else
 	{

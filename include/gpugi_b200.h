@@ -189,7 +189,7 @@ enum {
 	                                   stream and sum the durations per kernel class (gi_get_kernel_times); setting the option
 	                                   clears the sums.  The iteration call then synchronises -- measurement passes only.
 	                                   Replaces the reference's glFinish + clock() pair (renderersystem.cpp:249-255). */
-	GI_OPT_STREAMING = 9            /* 1 = consecutive gi_render_iteration(GI_RENDERER_PT or _BPT) calls form a STREAM: each call submits one
+	GI_OPT_STREAMING = 9,           /* 1 = consecutive gi_render_iteration(GI_RENDERER_PT or _BPT) calls form a STREAM: each call submits one
 	                                   wave (generate + trace + shade) of a run that stays open, so the bounces of up to
 	                                   max_path_length + 1 iterations share every wave exactly as in gi_render_iterations -- the
 	                                   reference's one-Draw()-per-iteration loop (renderersystem.cpp:246-256) without its
@@ -200,6 +200,11 @@ enum {
 	                                   light-cache slots, and 2 x max_path_length + 1 iterations deep over a ring of light caches; one
 	                                   iteration at a time if the ring does not fit the device memory).  gi_read_accumulator_async
 	                                   does NOT drain. */
+	GI_OPT_DEVICE_BUILDER = 10      /* GI_BUILDER_*: what gi_build_hierarchy builds */
+};
+enum {
+	GI_BUILDER_LBVH = 0,        /* Karras' binary radix tree over the Morton-ordered leaves: fastest build, Morton-bit splits       */
+	GI_BUILDER_PLOC = 1         /* parallel locally-ordered clustering over the same leaves (default): close to the host SAH sweep   */
 };
 /* kernel classes of gi_get_kernel_times */
 enum {
@@ -370,7 +375,8 @@ GI_API int gi_get_light_samples(GiContext* ctx, GiLightSample* out, uint32_t n);
  * bim_hierarchy.cpp:8-50,238-252) for a mesh that comes without a hierarchy: an LBVH (Morton order of the triangle centroids, consecutive
  * pairs per leaf, Karras' binary radix tree, bottom-up boxes) written in the REFERENCE'S layout -- preorder GiNode array with child / escape
  * links, 2 slots per leaf (unused slot all-zero), parents, tree levels -- so that gi_upload_scene, both walks and the .bim writer take it
- * unchanged.  Host buffers in and out: out_nodes / out_parents hold 2*ceil(T/2)-1 entries, out_leaf_triangles 2*ceil(T/2).
+ * unchanged.  Host buffers in and out, sized for the worst case of one triangle per leaf: out_nodes / out_parents 2*T-1 entries,
+ * out_leaf_triangles 2*T; *out_num_nodes = N tells how much was written (N nodes, N+1 leaf slots).
  * triangle_materials may be NULL (material 0). */
 GI_API int gi_build_hierarchy(GiContext* ctx, const float* positions, uint32_t num_vertices, const uint32_t* triangles, const uint32_t* triangle_materials,
                               uint32_t num_triangles, GiNode* out_nodes, GiTriangle* out_leaf_triangles, uint32_t* out_parents, uint32_t* out_num_nodes,

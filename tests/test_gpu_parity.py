@@ -247,9 +247,10 @@ def test_obox_hierarchy_on_device(g, orc, scenes):
     assert pixel_mismatch_fraction(imgs[1], imgs[0], 1e-2) < 0.01
 
 
+@pytest.mark.parametrize("method", ["lbvh", "ploc"])
 @pytest.mark.parametrize("which", ["random", "box1", "odd", "tiny"])
-def test_device_hierarchy_build(g, orc, scenes, which):
-    """gi_build_hierarchy: the LBVH built on the GPU is a valid hierarchy in the reference's layout (every triangle once,
+def test_device_hierarchy_build(g, orc, scenes, which, method):
+    """gi_build_hierarchy: the hierarchy built on the GPU (Karras radix tree / PLOC clustering) is a valid hierarchy in the reference's layout (every triangle once,
     preorder child / escape links, exact boxes, parents), the GPU walks on it equal the oracle's walk on the same nodes bit for bit, and
     -- the closest hit being a property of the geometry, not of the tree -- the hit distances equal those found through the host-built
     SAH tree."""
@@ -262,10 +263,10 @@ def test_device_hierarchy_build(g, orc, scenes, which):
         mk = lambda m: scenes.make_random_triangles(333, seed=2, build_method=m)
     else:
         mk = lambda m: scenes.make_random_triangles(2, seed=1, build_method=m)
-    dev_sc, sah_sc = mk("lbvh"), mk("sah")
+    dev_sc, sah_sc = mk(method), mk("sah")
     _check_hierarchy(dev_sc)
     info = dev_sc.info
-    assert info.num_nodes == 2 * ((info.num_leaf_triangles + 1) // 2) - 1 or info.num_nodes == info.num_leaf_triangles - 1
+    assert info.num_nodes == info.num_leaf_triangles - 1    # N nodes, (N + 1) / 2 leaves, 2 slots each
     lo, hi = np.array(info.bbox_min), np.array(info.bbox_max)
     rng = np.random.RandomState(6)
     n = 100000

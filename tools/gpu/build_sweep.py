@@ -30,14 +30,15 @@ def main():
     results = []
     dev0 = g.Device(0)  # context creation out of the timings
     for label, (mk, C, W, H) in cases.items():
-        for method in ("sah", "lbvh"):
+        for method in ("sah", "lbvh", "ploc"):
             t0 = time.time()
             sc = mk(method)
             total_s = time.time() - t0
             # the build alone, on the final mesh
             pos, tri, mat = sc.positions(), sc.triangles(), sc.triangle_materials()
             build_ms = None
-            if method == "lbvh":
+            if method != "sah":
+                dev0.set_option(g.GI_OPT_DEVICE_BUILDER, g.GI_BUILDER_LBVH if method == "lbvh" else g.GI_BUILDER_PLOC)
                 dev0.build_hierarchy(pos, tri, mat)
                 t1 = time.time(); dev0.build_hierarchy(pos, tri, mat); build_ms = (time.time() - t1) * 1e3
             dev = g.Device(0)
