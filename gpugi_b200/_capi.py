@@ -163,6 +163,10 @@ DEVICE_API = {
 HOST_API = {
     "gih_last_error": (C.c_char_p, []),
     "gih_wanghash": (u32, [u32]),
+    "gih_xorshift32": (u32, [u32]),
+    "gih_xorshift64": (C.c_uint64, [C.c_uint64]),
+    "gih_xorshift_f": (f32, [P(C.c_uint64)]),
+    "gih_xorshift_d": (C.c_double, [P(C.c_uint64)]),
     "gih_set_path_length": (None, [C.c_int]),
     "gih_scene_load": (vp, [C.c_char_p, C.c_int]),
     "gih_scene_from_mesh": (vp, [vp, vp, vp, u32, vp, vp, u32, C.c_char_p, C.c_char_p, C.c_int]),

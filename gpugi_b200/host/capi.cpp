@@ -32,6 +32,11 @@ extern "C" {
 const char* gih_last_error(void) { return gi::LastHostError().c_str(); }
 
 uint32_t gih_wanghash(uint32_t x) { return WangHash(x); }
+// the host generators of utilities/random.cpp:15-43, exported for the known-answer tests against the reference's own object code
+uint32_t gih_xorshift32(uint32_t x) { return Xorshift(x); }
+uint64_t gih_xorshift64(uint64_t x) { return Xorshift(x); }
+float gih_xorshift_f(uint64_t* state) { return XorshiftF(*state); }
+double gih_xorshift_d(uint64_t* state) { return XorshiftD(*state); }
 
 void gih_set_path_length(int n) { GlobalConfig::SetParameter("pathLength", {Variant(n)}); }
 

@@ -30,6 +30,10 @@ typedef struct GihSceneInfo {
 
 GI_API const char* gih_last_error(void);
 GI_API uint32_t gih_wanghash(uint32_t x);                         /* utilities/random.cpp:5-13     */
+GI_API uint32_t gih_xorshift32(uint32_t x);                       /* utilities/random.cpp:15-22    */
+GI_API uint64_t gih_xorshift64(uint64_t x);                       /* utilities/random.cpp:25-31    */
+GI_API float gih_xorshift_f(uint64_t* state);                     /* utilities/random.cpp:39-43 (the light sampler's generator) */
+GI_API double gih_xorshift_d(uint64_t* state);                    /* utilities/random.cpp:33-37    */
 GI_API void gih_set_path_length(int n);                           /* GlobalConfig "pathLength"      */
 
 /* Scene::Scene(file, bvhType), scene.cpp:15-59.  NULL on failure (gih_last_error).                */

@@ -1172,6 +1172,11 @@ OR_API int or_num_threads(void)
 }
 
 OR_API uint32_t or_wanghash(uint32_t x) { return wanghash(x); }
+// the remaining scalar generators, exported so that tests can pin them against oracle/_ref (the reference's own utilities/random.cpp,
+// compiled where it lies) and the golden vectors generated from it: random.glsl:11-19 == random.cpp:15-22 (xorshift32), random.cpp:25-43
+OR_API uint32_t or_xorshift32(uint32_t s) { uint32_t t = s; return RandomUInt(t); }
+OR_API uint64_t or_xorshift64(uint64_t s) { return Xorshift64(s); }
+OR_API float or_xorshift_f(uint64_t* state) { return XorshiftF(*state); }
 
 // TraceRay / TraceRayAnyHit over a batch.  node_visits / tri_visits (optional, per ray) are the
 // TRACERAY_DEBUG_VARS counters (traceray.glsl:59-61,131-133) that define the algorithmic bytes.

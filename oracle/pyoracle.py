@@ -44,6 +44,12 @@ class OrRegion(C.Structure):
 lib.or_num_threads.restype = C.c_int
 lib.or_wanghash.restype = u32
 lib.or_wanghash.argtypes = [u32]
+lib.or_xorshift32.restype = u32
+lib.or_xorshift32.argtypes = [u32]
+lib.or_xorshift64.restype = C.c_uint64
+lib.or_xorshift64.argtypes = [C.c_uint64]
+lib.or_xorshift_f.restype = C.c_float
+lib.or_xorshift_f.argtypes = [C.POINTER(C.c_uint64)]
 lib.or_trace_batch.restype = C.c_int
 lib.or_trace_batch.argtypes = [vp, vp, u32, vp, vp, vp]
 lib.or_intersect_box.restype = C.c_int

@@ -171,3 +171,56 @@ def test_pt_lpt_bpt_agree(orc, scenes, box1):
     # loose: catches unit errors (a factor pi, 1/N, pixel area), not noise or the integrators' different path sets
     assert abs(m_bpt - m_pt) / m_pt < 0.25, (m_pt, m_bpt)
     assert abs(m_lpt - m_pt) / m_pt < 0.35, (m_pt, m_lpt)
+
+
+# ---------------------------------------------------------------- vectors from the reference's own object code
+def _stream_f(fn, seed, n):
+    import ctypes as C
+    st = C.c_uint64(int(seed))
+    vals = np.array([fn(C.byref(st)) for _ in range(n)], dtype=np.float32)
+    return vals, st.value
+
+
+def test_rng_matches_reference_golden_vectors(orc, g):
+    """tests/golden/ref_rng.npz was produced by the REFERENCE'S utilities/random.cpp (compiled where it lies into oracle/_ref, see
+    tests/golden/make_golden_rng.py): WangHash, xorshift32, xorshift64*, the XorshiftF stream from the light sampler's seed 123 and
+    the FrameSeed sequence.  The oracle (or_*) and the host layer (gih_*) must reproduce every value bit for bit."""
+    import ctypes as C
+    z = np.load(os.path.join(GOLDEN, "ref_rng.npz"))
+    host = g.capi.host
+    for x, y in zip(z["wang_in"], z["wang_out"]):
+        assert orc.lib.or_wanghash(int(x)) == int(y) == host.gih_wanghash(int(x))
+    for x, y in zip(z["xs32_in"], z["xs32_out"]):
+        assert orc.lib.or_xorshift32(int(x)) == int(y) == host.gih_xorshift32(int(x))
+    for x, y in zip(z["xs64_in"], z["xs64_out"]):
+        assert orc.lib.or_xorshift64(int(x)) == int(y) == host.gih_xorshift64(int(x))
+    for i, y in enumerate(z["frame_seeds"]):
+        assert g.wang_hash(i) == int(y) == orc.wanghash(i)
+    n = len(z["f_out"])
+    for fn in (orc.lib.or_xorshift_f, host.gih_xorshift_f):
+        vals, state = _stream_f(fn, z["f_seed"], n)
+        assert np.array_equal(vals.view(np.uint32), z["f_out"].view(np.uint32)) and state == int(z["f_state"])
+    st = C.c_uint64(int(z["f_seed"]))
+    d = np.array([host.gih_xorshift_d(C.byref(st)) for _ in range(len(z["d_out"]))], dtype=np.float64)
+    assert np.array_equal(d.view(np.uint64), z["d_out"].view(np.uint64))
+
+
+def test_rng_matches_reference_object_live(orc, g):
+    """Where oracle/_ref/libref_random.so exists (built in the container that holds /root/reference, shipped prebuilt to the GPU box):
+    fresh random inputs through the reference's object code, the oracle and the host layer."""
+    import pytest
+    path = os.path.join(os.path.dirname(GOLDEN), "..", "oracle", "_ref", "libref_random.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref not built here (needs /root/reference); the committed golden vectors cover the same functions")
+    from tests.golden.make_golden_rng import load_ref
+    ref, host = load_ref(), g.capi.host
+    rng = np.random.RandomState(7)
+    for x in rng.randint(0, 2**32, 20000, dtype=np.uint64):
+        x = int(x)
+        assert ref.ref_wanghash(x) == orc.lib.or_wanghash(x) == host.gih_wanghash(x)
+        assert ref.ref_xorshift32(x) == orc.lib.or_xorshift32(x) == host.gih_xorshift32(x)
+    for seed in [1, 123, 123 ^ 77, 2**64 - 1, 0x9E3779B97F4A7C15]:
+        a, sa = _stream_f(ref.ref_xorshift_f, seed, 5000)
+        b, sb = _stream_f(orc.lib.or_xorshift_f, seed, 5000)
+        c, sc = _stream_f(host.gih_xorshift_f, seed, 5000)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and np.array_equal(a.view(np.uint32), c.view(np.uint32)) and sa == sb == sc
