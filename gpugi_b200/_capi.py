@@ -114,6 +114,8 @@ GI_OPT_WF_REFILL_THRESHOLD, GI_OPT_WF_MIN_INNER, GI_OPT_WF_BLOCKS_PER_SM, GI_OPT
 GI_OPT_KERNEL_TIMING = 8
 GI_OPT_STREAMING = 9
 GI_OPT_DEVICE_BUILDER = 10
+GI_OPT_UPLOAD_TOPOLOGY = 11
+GI_TOPOLOGY_REFERENCE, GI_TOPOLOGY_PLOC = 0, 1
 GI_BUILDER_LBVH, GI_BUILDER_PLOC = 0, 1
 GI_KERNEL_TRACE, GI_KERNEL_SHADE, GI_KERNEL_GENERATE, GI_KERNEL_MEGAKERNEL, GI_KERNEL_OTHER, GI_KERNEL_CLASS_COUNT = 0, 1, 2, 3, 4, 5
 GI_SCHEDULER_WAVEFRONT, GI_SCHEDULER_MEGAKERNEL = 0, 1
@@ -157,6 +159,7 @@ DEVICE_API = {
     "gi_get_counters": (C.c_int, [vp, P(GiCounters)]),
     "gi_reset_counters": (C.c_int, [vp]),
     "gi_kernel_launches": (u64, [vp]),
+    "gi_scene_topology": (C.c_int, [vp, P(C.c_double)]),
     "gi_get_kernel_times": (C.c_int, [vp, P(GiKernelTimes)]),
 }
 

@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <chrono>
 #include <vector>
 
 using namespace gik;
@@ -485,6 +486,9 @@ struct GiContext
 	WfRun run[2];                    // [0]: PT / LPT / BPT light pass / stream, [1]: BPT eye pass of a pipelined batch
 	int streamingOption = 0;         // GI_OPT_STREAMING
 	int deviceBuilder = GI_BUILDER_PLOC; // GI_OPT_DEVICE_BUILDER
+	int uploadTopology = GI_TOPOLOGY_PLOC; // GI_OPT_UPLOAD_TOPOLOGY (what the next gi_upload_scene builds)
+	int sceneTopology = GI_TOPOLOGY_REFERENCE; // what the uploaded scene's ordered layout is built on
+	double topologyBuildMs = 0.0;
 	uint32_t lightSlot = 0;          // ring slot of the light-sample set the next iteration uses
 	// asynchronous read-out (gi_read_accumulator_async)
 	cudaStream_t copyStream = nullptr;
@@ -1009,6 +1013,9 @@ int gi_set_option(GiContext* c, int option, int value)
 	case GI_OPT_DEVICE_BUILDER:
 		if (value != GI_BUILDER_LBVH && value != GI_BUILDER_PLOC) return fail(c, GI_ERR_INVALID, "GI_OPT_DEVICE_BUILDER: unknown builder");
 		c->deviceBuilder = value; return GI_OK;
+	case GI_OPT_UPLOAD_TOPOLOGY:
+		if (value != GI_TOPOLOGY_REFERENCE && value != GI_TOPOLOGY_PLOC) return fail(c, GI_ERR_INVALID, "GI_OPT_UPLOAD_TOPOLOGY: unknown topology");
+		c->uploadTopology = value; return GI_OK;
 	case GI_OPT_TRAVERSAL:
 		if (value != GI_TRAVERSAL_FAST && value != GI_TRAVERSAL_REFERENCE) return fail(c, GI_ERR_INVALID, "GI_OPT_TRAVERSAL: unknown mode");
 		c->traversal = value; return GI_OK;
@@ -1040,6 +1047,105 @@ int gi_clear_accumulator(GiContext* c)
 	return GI_OK;
 }
 
+// GI_OPT_UPLOAD_TOPOLOGY = GI_TOPOLOGY_PLOC: re-cluster the reference's leaves on the device (gi_lbvh.cuh: Morton order of the leaf
+// boxes + PLOC passes) and hand the tree back to the host encoder (gi_layout.h: applyLeafTree).  GI_OK with t.numLeaves == 0 when the
+// scene has fewer than two leaves.
+static int buildLeafTreeOnDevice(GiContext* c, const GiSceneDesc* d, const HostLayout& L, LeafTree& t)
+{
+	const uint32_t nl = d->num_leaf_triangles / 2u;
+	t = LeafTree();
+	if (nl < 2u) return GI_OK;
+	const uint32_t N = 2u * nl - 1u;
+	std::vector<float> hMin(size_t(nl) * 3), hMax(size_t(nl) * 3);
+	for (uint32_t l = 0; l < nl; ++l)
+	{
+		const GiNode& ln = d->nodes[L.leafNode[l]];
+		std::memcpy(&hMin[size_t(l) * 3], ln.min, 12); std::memcpy(&hMax[size_t(l) * 3], ln.max, 12);
+	}
+	cudaStream_t st = c->stream;
+	std::vector<void*> allocs;
+	auto dalloc = [&](size_t bytes) -> void* { void* p = nullptr; if (cudaMalloc(&p, std::max<size_t>(bytes, 16)) != cudaSuccess) return nullptr; allocs.push_back(p); return p; };
+	auto freeAll = [&]() { for (void* p : allocs) cudaFree(p); };
+	float* dLeafMin = static_cast<float*>(dalloc(size_t(nl) * 12)); float* dLeafMax = static_cast<float*>(dalloc(size_t(nl) * 12));
+	unsigned long long* dCodes = static_cast<unsigned long long*>(dalloc(size_t(nl) * 8));
+	unsigned long long* dCodesSorted = static_cast<unsigned long long*>(dalloc(size_t(nl) * 8));
+	uint32_t* dIds = static_cast<uint32_t*>(dalloc(size_t(nl) * 4)); uint32_t* dIdsSorted = static_cast<uint32_t*>(dalloc(size_t(nl) * 4));
+	PlocTree pt;
+	pt.boxMin = static_cast<float*>(dalloc(size_t(N) * 12)); pt.boxMax = static_cast<float*>(dalloc(size_t(N) * 12));
+	pt.left = static_cast<uint32_t*>(dalloc(size_t(N) * 4)); pt.right = static_cast<uint32_t*>(dalloc(size_t(N) * 4));
+	pt.parent = static_cast<uint32_t*>(dalloc(size_t(N) * 4)); pt.size = static_cast<uint32_t*>(dalloc(size_t(N) * 4)); pt.leaves = static_cast<uint32_t*>(dalloc(size_t(N) * 4));
+	uint32_t* clA = static_cast<uint32_t*>(dalloc(size_t(nl) * 4)); uint32_t* clB = static_cast<uint32_t*>(dalloc(size_t(nl) * 4));
+	uint32_t* dNearest = static_cast<uint32_t*>(dalloc(size_t(nl) * 4)); uint32_t* dMerged = static_cast<uint32_t*>(dalloc(size_t(nl) * 4));
+	uint32_t* dValid = static_cast<uint32_t*>(dalloc(size_t(nl) * 4)); uint32_t* dOffset = static_cast<uint32_t*>(dalloc(size_t(nl) * 4));
+	uint32_t* dCounters = static_cast<uint32_t*>(dalloc(8)); // [0] next inner node id, [1] cluster count after the pass
+	size_t sortBytes = 0, scanBytes = 0;
+	cub::DeviceRadixSort::SortPairs(nullptr, sortBytes, dCodes, dCodesSorted, dIds, dIdsSorted, int(nl), 0, 63, st);
+	cub::DeviceScan::ExclusiveSum(nullptr, scanBytes, dValid, dOffset, int(nl), st);
+	void* dSortTmp = dalloc(sortBytes); void* dScanTmp = dalloc(scanBytes);
+	if (!(dLeafMin && dLeafMax && dCodes && dCodesSorted && dIds && dIdsSorted && pt.boxMin && pt.boxMax && pt.left && pt.right && pt.parent && pt.size && pt.leaves && clA && clB &&
+	      dNearest && dMerged && dValid && dOffset && dCounters && dSortTmp && dScanTmp))
+	{
+		freeAll();
+		return fail(c, GI_ERR_CUDA, "gi_upload_scene: device allocation failed (topology build)");
+	}
+	cudaError_t e = cudaSuccess;
+	auto step = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+	step(cudaMemcpyAsync(dLeafMin, hMin.data(), size_t(nl) * 12, cudaMemcpyHostToDevice, st));
+	step(cudaMemcpyAsync(dLeafMax, hMax.data(), size_t(nl) * 12, cudaMemcpyHostToDevice, st));
+	const uint32_t initCounters[2] = {nl, nl};
+	step(cudaMemcpyAsync(dCounters, initCounters, 8, cudaMemcpyHostToDevice, st));
+	const unsigned B = 256;
+	if (e == cudaSuccess)
+	{
+		k_leafbox_morton<<<(nl + B - 1) / B, B, 0, st>>>(dLeafMin, dLeafMax, nl, f3(d->nodes[0].min), f3(d->nodes[0].max), dCodes, dIds);
+		step(cub::DeviceRadixSort::SortPairs(dSortTmp, sortBytes, dCodes, dCodesSorted, dIds, dIdsSorted, int(nl), 0, 63, st));
+		k_ploc_init_gather<<<(nl + B - 1) / B, B, 0, st>>>(nl, dIdsSorted, dLeafMin, dLeafMax, pt, clA);
+		c->launches += 2;
+		uint32_t n = nl;
+		auto pass = [&](bool forced)
+		{
+			const unsigned g = (n + B - 1) / B;
+			if (forced) k_ploc_force_pairs<<<g, B, 0, st>>>(n, dNearest);
+			else k_ploc_nearest<<<g, B, 0, st>>>(n, clA, pt, dNearest);
+			k_ploc_merge<<<g, B, 0, st>>>(n, clA, dNearest, pt, dCounters, dMerged, dValid);
+			step(cub::DeviceScan::ExclusiveSum(dScanTmp, scanBytes, dValid, dOffset, int(n), st));
+			k_ploc_compact<<<g, B, 0, st>>>(n, dMerged, dValid, dOffset, clB, dCounters + 1);
+			c->launches += 3;
+			uint32_t next = n;
+			step(cudaMemcpyAsync(&next, dCounters + 1, 4, cudaMemcpyDeviceToHost, st));
+			step(cudaStreamSynchronize(st));
+			return next;
+		};
+		while (n > 1u && e == cudaSuccess)
+		{
+			uint32_t next = pass(false);
+			if (next >= n && e == cudaSuccess) next = pass(true);
+			if (next >= n) { if (e == cudaSuccess) e = cudaErrorUnknown; break; }
+			std::swap(clA, clB);
+			n = next;
+		}
+		step(cudaGetLastError());
+	}
+	uint32_t counters[2] = {0, 0};
+	if (e == cudaSuccess)
+	{
+		t.left.resize(N); t.right.resize(N); t.boxMin.resize(size_t(N) * 3); t.boxMax.resize(size_t(N) * 3); t.leafOf.resize(nl);
+		step(cudaMemcpyAsync(t.left.data(), pt.left, size_t(N) * 4, cudaMemcpyDeviceToHost, st));
+		step(cudaMemcpyAsync(t.right.data(), pt.right, size_t(N) * 4, cudaMemcpyDeviceToHost, st));
+		step(cudaMemcpyAsync(t.boxMin.data(), pt.boxMin, size_t(N) * 12, cudaMemcpyDeviceToHost, st));
+		step(cudaMemcpyAsync(t.boxMax.data(), pt.boxMax, size_t(N) * 12, cudaMemcpyDeviceToHost, st));
+		step(cudaMemcpyAsync(t.leafOf.data(), dIdsSorted, size_t(nl) * 4, cudaMemcpyDeviceToHost, st));
+		step(cudaMemcpyAsync(counters, dCounters, 8, cudaMemcpyDeviceToHost, st));
+		step(cudaStreamSynchronize(st));
+	}
+	freeAll();
+	if (e != cudaSuccess) return fail(c, GI_ERR_CUDA, std::string("gi_upload_scene (topology build): ") + cudaGetErrorString(e));
+	if (counters[0] != N) return fail(c, GI_ERR_CUDA, "gi_upload_scene (topology build): the clustering did not end in one root");
+	t.numLeaves = nl;
+	t.root = N - 1u; // the last merge
+	return GI_OK;
+}
+
 int gi_upload_scene(GiContext* c, const GiSceneDesc* d)
 {
 	if (!c || !d) return GI_ERR_INVALID;
@@ -1057,6 +1163,18 @@ int gi_upload_scene(GiContext* c, const GiSceneDesc* d)
 	std::string lerr;
 	if (!buildHostLayout(d, L, lerr)) return fail(c, GI_ERR_INVALID, "gi_upload_scene: " + lerr);
 	c->fastValid = L.binary;
+	c->sceneTopology = GI_TOPOLOGY_REFERENCE;
+	c->topologyBuildMs = 0.0;
+	if (L.binary && c->uploadTopology == GI_TOPOLOGY_PLOC && d->num_leaf_triangles >= 4u)
+	{
+		const auto t0 = std::chrono::steady_clock::now();
+		LeafTree tree;
+		const int tst = buildLeafTreeOnDevice(c, d, L, tree);
+		if (tst != GI_OK) return tst;
+		std::string why;
+		if (applyLeafTree(d, L, tree, why)) c->sceneTopology = GI_TOPOLOGY_PLOC; // else: the reference's own topology stays (always valid)
+		c->topologyBuildMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+	}
 
 	// ---- textures: CUDA arrays + texture objects (hardware filter) and a linear copy (fp32 filter)
 	std::vector<cudaTextureObject_t> objOfTexture(d->num_textures, 0);
@@ -1778,6 +1896,13 @@ int gi_build_hierarchy(GiContext* c, const float* positions, uint32_t num_vertic
 	*out_num_nodes = N;
 	*out_num_tree_levels = depth;
 	return GI_OK;
+}
+
+int gi_scene_topology(const GiContext* c, double* build_ms)
+{
+	if (!c || !c->haveScene) return -1;
+	if (build_ms) *build_ms = c->topologyBuildMs;
+	return c->sceneTopology;
 }
 
 int gi_synchronize(GiContext* c)

@@ -31,6 +31,75 @@ struct HostLayout
 	DScene scene = {};                      // counts, flags, ambiguity window (pointers unset)
 };
 
+// Encoder of the two inner-node records (fastNodes: the reference's floats; qNodes: 16-bit grid over the root box, rounded outwards and
+// verified in double against the decode lo + q * scale the device's slab test stands for).
+struct FastEmitter
+{
+	double gridLo[3], gridScale[3];
+
+	void init(const float rootMin[3], const float rootMax[3], HostLayout& L)
+	{
+		// cell size rounded up so that 65535 cells cover the box
+		for (int k = 0; k < 3; ++k)
+		{
+			const float lo = rootMin[k], hi = rootMax[k];
+			float sc = float((double(hi) - double(lo)) / 65535.0 * (1.0 + 1.0e-6));
+			if (!(sc > 1.0e-30f)) sc = 1.0e-30f;
+			L.scene.gridLo[k] = lo; L.scene.gridScale[k] = sc;
+			gridLo[k] = double(lo); gridScale[k] = double(sc);
+		}
+	}
+	static bool nested(const float pmin[3], const float pmax[3], const float cmin[3], const float cmax[3])
+	{
+		for (int k = 0; k < 3; ++k)
+			if (!(pmin[k] <= cmin[k] && cmin[k] <= pmax[k] && pmin[k] <= cmax[k] && cmax[k] <= pmax[k])) return false;
+		return true;
+	}
+	uint32_t quantLo(float x, int k) const
+	{
+		double q = std::floor((double(x) - gridLo[k]) / gridScale[k]);
+		if (!(q > 0.0)) q = 0.0;
+		if (q > 65535.0) q = 65535.0;
+		while (q > 0.0 && gridLo[k] + q * gridScale[k] > double(x)) q -= 1.0;
+		return uint32_t(q);
+	}
+	uint32_t quantHi(float x, int k) const
+	{
+		double q = std::ceil((double(x) - gridLo[k]) / gridScale[k]);
+		if (!(q > 0.0)) q = 0.0;
+		if (q > 65535.0) q = 65535.0;
+		while (q < 65535.0 && gridLo[k] + q * gridScale[k] < double(x)) q += 1.0;
+		return uint32_t(q);
+	}
+	// inner node `index` with the child boxes a, b and the child links c0, c1 (inner index >= 0, leaf = ~leafIndex).
+	// false: the grid does not cover a box (cannot happen for boxes nested in the root box).
+	bool emit(HostLayout& L, uint32_t index, const float amin[3], const float amax[3], const float bmin[3], const float bmax[3], int c0, int c1) const
+	{
+		F4* q = &L.fastNodes[size_t(index) * 4];
+		q[0] = F4{amin[0], amin[1], amin[2], amax[0]};
+		q[1] = F4{amax[1], amax[2], bmin[0], bmin[1]};
+		q[2] = F4{bmin[2], bmax[0], bmax[1], bmax[2]};
+		F4 ch = {0.0f, 0.0f, 0.0f, 0.0f};
+		std::memcpy(&ch.x, &c0, 4);
+		std::memcpy(&ch.y, &c1, 4);
+		q[3] = ch;
+		bool covered = true;
+		uint32_t v[12];
+		for (int k = 0; k < 3; ++k)
+		{
+			v[k] = quantLo(amin[k], k); v[3 + k] = quantHi(amax[k], k);
+			v[6 + k] = quantLo(bmin[k], k); v[9 + k] = quantHi(bmax[k], k);
+			if (gridLo[k] + double(v[k]) * gridScale[k] > double(amin[k]) || gridLo[k] + double(v[3 + k]) * gridScale[k] < double(amax[k]) ||
+			    gridLo[k] + double(v[6 + k]) * gridScale[k] > double(bmin[k]) || gridLo[k] + double(v[9 + k]) * gridScale[k] < double(bmax[k]))
+				covered = false;
+		}
+		uint32_t* qn = &L.qNodes[size_t(index) * 8];
+		for (int k = 0; k < 3; ++k) { qn[k] = v[k] | (v[3 + k] << 16); qn[3 + k] = v[6 + k] | (v[9 + k] << 16); }
+		qn[6] = uint32_t(c0); qn[7] = uint32_t(c1);
+		return covered;
+	}
+};
+
 inline float srgbDecodeHost(uint8_t v)
 {
 	float c = float(v) / 255.0f;
@@ -153,31 +222,8 @@ inline bool buildHostLayout(const GiSceneDesc* d, HostLayout& L, std::string& er
 	L.binary = true;
 	L.fastNodes.assign(size_t(numInner ? numInner : 1) * 4, F4{0.0f, 0.0f, 0.0f, 0.0f});
 	L.qNodes.assign(size_t(numInner ? numInner : 1) * 8, 0u);
-	// 16-bit grid over the root box; cell size rounded up so that 65535 cells cover the box
-	double gridLo[3], gridScale[3];
-	for (int k = 0; k < 3; ++k)
-	{
-		const float lo = d->nodes[0].min[k], hi = d->nodes[0].max[k];
-		float sc = float((double(hi) - double(lo)) / 65535.0 * (1.0 + 1.0e-6));
-		if (!(sc > 1.0e-30f)) sc = 1.0e-30f;
-		L.scene.gridLo[k] = lo; L.scene.gridScale[k] = sc;
-		gridLo[k] = double(lo); gridScale[k] = double(sc);
-	}
-	// outward rounding, verified in double against the decode lo + q * scale the device's slab test stands for
-	auto quantLo = [&](float x, int k) -> uint32_t {
-		double q = std::floor((double(x) - gridLo[k]) / gridScale[k]);
-		if (!(q > 0.0)) q = 0.0;
-		if (q > 65535.0) q = 65535.0;
-		while (q > 0.0 && gridLo[k] + q * gridScale[k] > double(x)) q -= 1.0;
-		return uint32_t(q);
-	};
-	auto quantHi = [&](float x, int k) -> uint32_t {
-		double q = std::ceil((double(x) - gridLo[k]) / gridScale[k]);
-		if (!(q > 0.0)) q = 0.0;
-		if (q > 65535.0) q = 65535.0;
-		while (q < 65535.0 && gridLo[k] + q * gridScale[k] < double(x)) q += 1.0;
-		return uint32_t(q);
-	};
+	FastEmitter em;
+	em.init(d->nodes[0].min, d->nodes[0].max, L);
 	for (uint32_t i = 0; i < d->num_nodes; ++i)
 	{
 		const GiNode& n = d->nodes[i];
@@ -190,42 +236,13 @@ inline bool buildHostLayout(const GiSceneDesc* d, HostLayout& L, std::string& er
 		// The wavefront walk tests inner nodes conservatively and applies the reference's exact cull test to a leaf's own
 		// box only; that equals the reference's chain of tests iff every child box lies inside its parent's box (the slab
 		// test is monotone in the box).  bim's bottom-up box pass guarantees it; other inputs fall back to the reference walk.
-		for (int k = 0; k < 3; ++k)
-		{
-			const float lo = n.min[k], hi = n.max[k];
-			if (!(lo <= a.min[k] && a.min[k] <= hi && lo <= a.max[k] && a.max[k] <= hi && lo <= b.min[k] && b.min[k] <= hi && lo <= b.max[k] && b.max[k] <= hi))
-				L.binary = false;
-		}
-		if (!L.binary) break;
+		if (!FastEmitter::nested(n.min, n.max, a.min, a.max) || !FastEmitter::nested(n.min, n.max, b.min, b.max)) { L.binary = false; break; }
 		auto encode = [&](uint32_t nodeIdx) -> int {
 			const GiNode& ch = d->nodes[nodeIdx];
 			if (ch.first_child & 0x80000000u) return ~int(ch.first_child & 0x7fffffffu);
 			return fastIndex[nodeIdx];
 		};
-		const int c0 = encode(left), c1 = encode(right);
-		F4* q = &L.fastNodes[size_t(fastIndex[i]) * 4];
-		q[0] = F4{a.min[0], a.min[1], a.min[2], a.max[0]};
-		q[1] = F4{a.max[1], a.max[2], b.min[0], b.min[1]};
-		q[2] = F4{b.min[2], b.max[0], b.max[1], b.max[2]};
-		F4 ch = {0.0f, 0.0f, 0.0f, 0.0f};
-		std::memcpy(&ch.x, &c0, 4);
-		std::memcpy(&ch.y, &c1, 4);
-		q[3] = ch;
-		{
-			uint32_t v[12];
-			for (int k = 0; k < 3; ++k)
-			{
-				v[k] = quantLo(a.min[k], k); v[3 + k] = quantHi(a.max[k], k);
-				v[6 + k] = quantLo(b.min[k], k); v[9 + k] = quantHi(b.max[k], k);
-				// the grid must cover the box (guaranteed for boxes nested in the root box)
-				if (gridLo[k] + double(v[k]) * gridScale[k] > double(a.min[k]) || gridLo[k] + double(v[3 + k]) * gridScale[k] < double(a.max[k]) ||
-				    gridLo[k] + double(v[6 + k]) * gridScale[k] > double(b.min[k]) || gridLo[k] + double(v[9 + k]) * gridScale[k] < double(b.max[k]))
-					L.binary = false;
-			}
-			uint32_t* qn = &L.qNodes[size_t(fastIndex[i]) * 8];
-			for (int k = 0; k < 3; ++k) { qn[k] = v[k] | (v[3 + k] << 16); qn[3 + k] = v[6 + k] | (v[9 + k] << 16); }
-			qn[6] = uint32_t(c0); qn[7] = uint32_t(c1);
-		}
+		if (!em.emit(L, uint32_t(fastIndex[i]), a.min, a.max, b.min, b.max, encode(left), encode(right))) L.binary = false;
 	}
 
 	// ---- materials
@@ -297,6 +314,83 @@ inline bool buildHostLayout(const GiSceneDesc* d, HostLayout& L, std::string& er
 		float dx = r.max[0] - r.min[0], dy = r.max[1] - r.min[1], dz = r.max[2] - r.min[2];
 		L.scene.ambiguityAbs = 1.0e-6f * sqrtf(dx * dx + dy * dy + dz * dz);
 	}
+	return true;
+}
+
+// ---- a second topology over the SAME leaves (GI_OPT_UPLOAD_TOPOLOGY).  The ordered walks only need a binary tree whose inner boxes
+// contain their children's and whose leaves are the reference's leaves with the reference leaf node's own box (the exact gate of
+// DESIGN.md 4): the reference visits a leaf iff the slab test of every ancestor passes, which -- the test being monotone in the box and
+// bim's boxes being nested -- it does iff the test of the leaf's own box passes.  So ANY such tree returns the reference's answer; the
+// hit ids stay reference leaf indices, ties and near-ties still go to the reference-order re-trace on refNodes.
+// Node ids: 0 .. L-1 = leaves (position p holds reference leaf leafOf[p]), L .. 2L-2 = inner nodes.
+struct LeafTree
+{
+	uint32_t numLeaves = 0, root = 0;
+	std::vector<uint32_t> left, right;      // per node id (entries of leaves unused)
+	std::vector<float> boxMin, boxMax;      // 3 per node id
+	std::vector<uint32_t> leafOf;           // per leaf position
+};
+
+// Rewrites fastNodes / qNodes from `t`, inner nodes numbered in preorder (the memory order the walks like).  Leaves L untouched and
+// returns false (with the reason) if `t` is not a valid tree over the reference's leaves with nested boxes.
+inline bool applyLeafTree(const GiSceneDesc* d, HostLayout& L, const LeafTree& t, std::string& why)
+{
+	const uint32_t nl = d->num_leaf_triangles / 2;
+	if (!L.binary || nl < 2 || t.numLeaves != nl) { why = "no ordered layout to replace or leaf count mismatch"; return false; }
+	const uint32_t numNodes = 2u * nl - 1u;
+	if (t.left.size() < numNodes || t.right.size() < numNodes || t.boxMin.size() < size_t(numNodes) * 3 || t.boxMax.size() < size_t(numNodes) * 3 ||
+	    t.leafOf.size() < nl || t.root < nl || t.root >= numNodes)
+	{ why = "incomplete tree"; return false; }
+	// leaves: a permutation of the reference's leaves carrying exactly the reference leaf node's box
+	{
+		std::vector<uint8_t> seen(nl, 0);
+		for (uint32_t p = 0; p < nl; ++p)
+		{
+			const uint32_t leaf = t.leafOf[p];
+			if (leaf >= nl || seen[leaf]) { why = "leaf list is not a permutation"; return false; }
+			seen[leaf] = 1;
+			const GiNode& ln = d->nodes[L.leafNode[leaf]];
+			if (std::memcmp(&t.boxMin[size_t(p) * 3], ln.min, 12) != 0 || std::memcmp(&t.boxMax[size_t(p) * 3], ln.max, 12) != 0) { why = "leaf box differs from the reference's"; return false; }
+		}
+	}
+	// preorder numbering of the inner nodes (iterative), every node reached exactly once
+	std::vector<uint32_t> rank(numNodes, 0xffffffffu);
+	std::vector<uint32_t> order; order.reserve(nl - 1);
+	{
+		std::vector<uint8_t> seen(numNodes, 0);
+		std::vector<uint32_t> stack; stack.push_back(t.root);
+		uint32_t leavesSeen = 0;
+		while (!stack.empty())
+		{
+			const uint32_t x = stack.back(); stack.pop_back();
+			if (x >= numNodes || seen[x]) { why = "child link out of range or node reached twice"; return false; }
+			seen[x] = 1;
+			if (x < nl) { ++leavesSeen; continue; }
+			rank[x] = uint32_t(order.size()); order.push_back(x);
+			stack.push_back(t.right[x]); stack.push_back(t.left[x]);
+		}
+		if (leavesSeen != nl || order.size() != size_t(nl - 1)) { why = "tree does not span all leaves"; return false; }
+	}
+	// root box must lie inside the reference's root box (the quantisation grid) and every child inside its parent
+	if (!FastEmitter::nested(d->nodes[0].min, d->nodes[0].max, &t.boxMin[size_t(t.root) * 3], &t.boxMax[size_t(t.root) * 3])) { why = "root box outside the reference's"; return false; }
+	for (uint32_t x : order)
+		for (uint32_t ch : {t.left[x], t.right[x]})
+			if (!FastEmitter::nested(&t.boxMin[size_t(x) * 3], &t.boxMax[size_t(x) * 3], &t.boxMin[size_t(ch) * 3], &t.boxMax[size_t(ch) * 3])) { why = "child box not inside its parent's"; return false; }
+	// encode into fresh vectors, swap in on success
+	HostLayout tmp;
+	tmp.fastNodes.assign(size_t(nl - 1) * 4, F4{0.0f, 0.0f, 0.0f, 0.0f});
+	tmp.qNodes.assign(size_t(nl - 1) * 8, 0u);
+	FastEmitter em;
+	em.init(d->nodes[0].min, d->nodes[0].max, tmp);
+	auto link = [&](uint32_t ch) -> int { return ch < nl ? ~int(t.leafOf[ch]) : int(rank[ch]); };
+	for (uint32_t x : order)
+	{
+		const uint32_t a = t.left[x], b = t.right[x];
+		if (!em.emit(tmp, rank[x], &t.boxMin[size_t(a) * 3], &t.boxMax[size_t(a) * 3], &t.boxMin[size_t(b) * 3], &t.boxMax[size_t(b) * 3], link(a), link(b)))
+		{ why = "quantisation grid does not cover a box"; return false; }
+	}
+	L.fastNodes.swap(tmp.fastNodes);
+	L.qNodes.swap(tmp.qNodes);
 	return true;
 }
 

@@ -441,4 +441,35 @@ __global__ void __launch_bounds__(256) k_ploc_emit(uint32_t numNodes, uint32_t n
 	parents[p] = t.parent[x] == 0xffffffffu ? 0u : pre[t.parent[x]];
 }
 
+// ---- re-clustering of an existing hierarchy's leaves (GI_OPT_UPLOAD_TOPOLOGY, gi_layout.h: applyLeafTree): Morton codes of the leaf
+// boxes' centres over the root box, then the PLOC passes above over the sorted leaves
+__global__ void __launch_bounds__(256) k_leafbox_morton(const float* __restrict__ leafMin, const float* __restrict__ leafMax, uint32_t numLeaves, F3 rootLo, F3 rootHi,
+                                                         unsigned long long* __restrict__ codes, uint32_t* __restrict__ ids)
+{
+	const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+	if (l >= numLeaves) return;
+	const float lo[3] = {rootLo.x, rootLo.y, rootLo.z}, hi[3] = {rootHi.x, rootHi.y, rootHi.z};
+	float c[3];
+	for (int k = 0; k < 3; ++k)
+	{
+		const float p = 0.5f * leafMin[3 * size_t(l) + k] + 0.5f * leafMax[3 * size_t(l) + k];
+		const float ext = hi[k] - lo[k];
+		c[k] = ext > 0.0f ? fminf(fmaxf((p - lo[k]) / ext, 0.0f), 1.0f) : 0.0f; // (fminf / fmaxf drop a NaN)
+	}
+	const unsigned long long x = (unsigned long long)(c[0] * 2097151.0f), y = (unsigned long long)(c[1] * 2097151.0f), z = (unsigned long long)(c[2] * 2097151.0f);
+	codes[l] = (expandBits21(x) << 2) | (expandBits21(y) << 1) | expandBits21(z);
+	ids[l] = l;
+}
+
+__global__ void __launch_bounds__(256) k_ploc_init_gather(uint32_t numLeaves, const uint32_t* __restrict__ sortedIds, const float* __restrict__ leafMin,
+                                                           const float* __restrict__ leafMax, PlocTree t, uint32_t* __restrict__ clusters)
+{
+	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= numLeaves) return;
+	const uint32_t l = sortedIds[p];
+	for (int a = 0; a < 3; ++a) { t.boxMin[3 * size_t(p) + a] = leafMin[3 * size_t(l) + a]; t.boxMax[3 * size_t(p) + a] = leafMax[3 * size_t(l) + a]; }
+	t.parent[p] = 0xffffffffu; t.size[p] = 1u; t.leaves[p] = 1u; t.left[p] = 0u; t.right[p] = 0u;
+	clusters[p] = p;
+}
+
 } // namespace gik

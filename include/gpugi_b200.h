@@ -200,7 +200,17 @@ enum {
 	                                   light-cache slots, and 2 x max_path_length + 1 iterations deep over a ring of light caches; one
 	                                   iteration at a time if the ring does not fit the device memory).  gi_read_accumulator_async
 	                                   does NOT drain. */
-	GI_OPT_DEVICE_BUILDER = 10      /* GI_BUILDER_*: what gi_build_hierarchy builds */
+	GI_OPT_DEVICE_BUILDER = 10,     /* GI_BUILDER_*: what gi_build_hierarchy builds */
+	GI_OPT_UPLOAD_TOPOLOGY = 11     /* GI_TOPOLOGY_*: the tree the ORDERED walks of the next gi_upload_scene run on.  Results do not depend on it
+	                                   (bit-exact either way, see GI_TOPOLOGY_PLOC); refNodes / the reference-order walk are never touched. */
+};
+enum {
+	GI_TOPOLOGY_REFERENCE = 0,  /* the bim hierarchy's own topology (Scene::UploadHierarchy, scene.cpp:95-118)                                  */
+	GI_TOPOLOGY_PLOC = 1        /* (default) the reference's LEAVES -- same triangle pairs, same leaf boxes, same ids -- re-clustered on the device
+	                               by PLOC at upload.  The reference reaches a leaf iff the slab test of the leaf node's own box passes (the test is
+	                               monotone in the box and bim's boxes are nested), so any tree over those leaves finds the same candidates; ties
+	                               and near-ties go to the reference-order re-trace as before.  Falls back to GI_TOPOLOGY_REFERENCE by itself when
+	                               the input's boxes are not nested. */
 };
 enum {
 	GI_BUILDER_LBVH = 0,        /* Karras' binary radix tree over the Morton-ordered leaves: fastest build, Morton-bit splits       */
@@ -384,6 +394,10 @@ GI_API int gi_build_hierarchy(GiContext* ctx, const float* positions, uint32_t n
 
 /* Replaces glFinish (renderersystem.cpp:249,253). */
 GI_API int gi_synchronize(GiContext* ctx);
+
+/* Which GI_TOPOLOGY_* the uploaded scene's ordered layout stands on (-1: no scene); *build_ms (may be NULL) = time the re-clustering
+ * added to gi_upload_scene. */
+GI_API int gi_scene_topology(const GiContext* ctx, double* build_ms);
 
 /* ------------------------------------------------------------------ read-out */
 

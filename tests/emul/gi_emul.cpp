@@ -8,6 +8,8 @@
 #include "../../gpugi_b200/csrc/gi_lane.h"
 #include "../../gpugi_b200/csrc/gi_shade.h"
 
+#include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <vector>
 
@@ -22,9 +24,88 @@ struct EmScene
 	DScene s;
 };
 
+// em_set_topology: 0 = the reference's topology, 1 = median split of the leaf centres, 2 = random balanced pairing (a terrible tree: the
+// exactness of the ordered walks must not depend on tree quality).  Host stand-ins for the device's PLOC pass, fed to the same
+// applyLeafTree encoder gi_upload_scene uses.
+int g_topology = 0;
+uint32_t g_topologySeed = 1;
+int g_topologyApplied = 0;
+
+uint32_t emRand(uint32_t& s) { s ^= s << 13; s ^= s >> 17; s ^= s << 5; return s; }
+
+void uniteBoxes(LeafTree& t, uint32_t id, uint32_t a, uint32_t b)
+{
+	for (int k = 0; k < 3; ++k)
+	{
+		t.boxMin[size_t(id) * 3 + k] = std::fmin(t.boxMin[size_t(a) * 3 + k], t.boxMin[size_t(b) * 3 + k]);
+		t.boxMax[size_t(id) * 3 + k] = std::fmax(t.boxMax[size_t(a) * 3 + k], t.boxMax[size_t(b) * 3 + k]);
+	}
+	t.left[id] = a; t.right[id] = b;
+}
+
+// median split over positions [lo, hi) of the (reordered) leaf list; returns the node id of the subtree
+uint32_t medianSplit(LeafTree& t, std::vector<uint32_t>& pos, uint32_t lo, uint32_t hi, uint32_t& nextInner)
+{
+	if (hi - lo == 1) return pos[lo];
+	float mn[3] = {GI_INF, GI_INF, GI_INF}, mx[3] = {-GI_INF, -GI_INF, -GI_INF};
+	auto centre = [&](uint32_t p, int k) { return 0.5f * t.boxMin[size_t(p) * 3 + k] + 0.5f * t.boxMax[size_t(p) * 3 + k]; };
+	for (uint32_t i = lo; i < hi; ++i)
+		for (int k = 0; k < 3; ++k) { mn[k] = std::fmin(mn[k], centre(pos[i], k)); mx[k] = std::fmax(mx[k], centre(pos[i], k)); }
+	int axis = 0;
+	if (mx[1] - mn[1] > mx[axis] - mn[axis]) axis = 1;
+	if (mx[2] - mn[2] > mx[axis] - mn[axis]) axis = 2;
+	const uint32_t mid = lo + (hi - lo) / 2;
+	std::nth_element(pos.begin() + lo, pos.begin() + mid, pos.begin() + hi, [&](uint32_t a, uint32_t b) { return centre(a, axis) < centre(b, axis); });
+	const uint32_t a = medianSplit(t, pos, lo, mid, nextInner), b = medianSplit(t, pos, mid, hi, nextInner);
+	const uint32_t id = nextInner++;
+	uniteBoxes(t, id, a, b);
+	return id;
+}
+
+bool applyTestTopology(const GiSceneDesc* d, HostLayout& L)
+{
+	const uint32_t nl = d->num_leaf_triangles / 2;
+	if (!L.binary || nl < 2) return false;
+	const uint32_t N = 2 * nl - 1;
+	LeafTree t;
+	t.numLeaves = nl; t.left.assign(N, 0); t.right.assign(N, 0); t.boxMin.assign(size_t(N) * 3, 0.0f); t.boxMax.assign(size_t(N) * 3, 0.0f); t.leafOf.resize(nl);
+	uint32_t seed = g_topologySeed ? g_topologySeed : 1u;
+	for (uint32_t p = 0; p < nl; ++p) t.leafOf[p] = p;
+	for (uint32_t p = nl - 1; p > 0; --p) std::swap(t.leafOf[p], t.leafOf[emRand(seed) % (p + 1)]);
+	for (uint32_t p = 0; p < nl; ++p)
+	{
+		const GiNode& ln = d->nodes[L.leafNode[t.leafOf[p]]];
+		std::memcpy(&t.boxMin[size_t(p) * 3], ln.min, 12); std::memcpy(&t.boxMax[size_t(p) * 3], ln.max, 12);
+	}
+	uint32_t nextInner = nl;
+	if (g_topology == 1)
+	{
+		std::vector<uint32_t> pos(nl);
+		for (uint32_t p = 0; p < nl; ++p) pos[p] = p;
+		t.root = medianSplit(t, pos, 0, nl, nextInner);
+	}
+	else
+	{
+		std::vector<uint32_t> cur(nl), nxt;
+		for (uint32_t p = 0; p < nl; ++p) cur[p] = p;
+		while (cur.size() > 1)
+		{
+			nxt.clear();
+			for (size_t i = 0; i + 1 < cur.size(); i += 2) { const uint32_t id = nextInner++; uniteBoxes(t, id, cur[i], cur[i + 1]); nxt.push_back(id); }
+			if (cur.size() & 1) nxt.push_back(cur.back());
+			cur.swap(nxt);
+		}
+		t.root = cur[0];
+	}
+	std::string why;
+	return applyLeafTree(d, L, t, why);
+}
+
 bool makeScene(const GiSceneDesc* d, EmScene& e, std::string& err)
 {
 	if (!buildHostLayout(d, e.L, err)) return false;
+	g_topologyApplied = 0;
+	if (g_topology != 0 && applyTestTopology(d, e.L)) g_topologyApplied = 1;
 	e.s = e.L.scene;
 	e.s.refNodes = e.L.refNodes.data();
 	e.s.oboxNodes = e.L.oboxNodes.empty() ? nullptr : e.L.oboxNodes.data();
@@ -39,6 +120,9 @@ bool makeScene(const GiSceneDesc* d, EmScene& e, std::string& err)
 	return true;
 }
 }
+
+EM_API void em_set_topology(int kind, uint32_t seed) { g_topology = kind; g_topologySeed = seed; }
+EM_API int em_topology_applied(void) { return g_topologyApplied; }
 
 struct EmCounters
 {

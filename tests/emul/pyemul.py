@@ -47,6 +47,23 @@ lib.em_slab_check.restype = C.c_int
 lib.em_slab_check.argtypes = [vp, vp, u32, u32, vp]
 
 
+lib.em_set_topology.restype = None
+lib.em_set_topology.argtypes = [C.c_int, u32]
+lib.em_topology_applied.restype = C.c_int
+lib.em_topology_applied.argtypes = []
+TOPOLOGY_REFERENCE, TOPOLOGY_MEDIAN, TOPOLOGY_RANDOM = 0, 1, 2
+
+
+def set_topology(kind, seed=1):
+    """Tree the ordered walks of the following calls run on (gi_layout.h applyLeafTree): the reference's, a median split of its leaves,
+    or a random balanced pairing of them."""
+    lib.em_set_topology(int(kind), int(seed))
+
+
+def topology_applied():
+    return bool(lib.em_topology_applied())
+
+
 def _p(a):
     return a.ctypes.data_as(vp)
 

@@ -396,3 +396,57 @@ def test_whitted_matches_oracle(orc, emul, scenes, box1):
             assert ec[k] == rc[k], k
         fast, _ = emul.render(box1.desc, cam, W, H, s, 3, seed, max_len, mode=0)
         assert np.array_equal(fast, ref)
+
+
+# ---------------------------------------------------------------- GI_OPT_UPLOAD_TOPOLOGY: another tree over the reference's leaves
+@pytest.fixture
+def alt_topology(emul):
+    yield emul
+    emul.set_topology(emul.TOPOLOGY_REFERENCE)
+
+
+@pytest.mark.parametrize("kind", [1, 2])
+@pytest.mark.parametrize("mode", [FAST, LANE])
+def test_retopologised_trace_is_exact(g, orc, alt_topology, scenes, box1, box1_coincident, kind, mode):
+    """The ordered walks on a DIFFERENT binary tree over the same leaves (median split; random pairing = a terrible tree) return the
+    reference's hit flag, triangle id, t and barycentrics bit for bit -- overlapping slivers, exact ties, finite lengths, camera rays.
+    This is the property gi_upload_scene's device-side PLOC re-clustering rests on (gi_layout.h: applyLeafTree)."""
+    emul = alt_topology
+    emul.set_topology(kind, seed=3 + kind)
+    C = scenes.BOX1_CAMERA
+    cases = []
+    cases.append((box1, np.concatenate([camera_ray_batch(g, orc, box1, C["pos"], C["lookat"], C["fov"], 48, 48, 1), make_ray_batch(g, box1, 12000, 2)])))
+    sliver = scenes.make_random_triangles(1500, seed=7, build_method="sah")
+    cases.append((sliver, make_ray_batch(g, sliver, 15000, 3)))
+    odd = scenes.make_random_triangles(333, seed=2, build_method="kd")
+    cases.append((odd, make_ray_batch(g, odd, 8000, 4)))
+    rng = np.random.RandomState(5)
+    n = 3000
+    rays = np.zeros(n, dtype=g.RAY_DTYPE)
+    lo, hi = np.array([0.25, 0.05, -1.3]), np.array([1.05, 0.7, -0.5])
+    rays["origin"] = (lo + rng.rand(n, 3) * (hi - lo)).astype(np.float32)
+    d = rng.randn(n, 3); d[:, 1] = -np.abs(d[:, 1]) - 0.2
+    rays["direction"] = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    rays["t_max"] = np.float32(g.RAY_MAX)
+    cases.append((box1_coincident, rays))
+    for sc, batch in cases:
+        hits, cnt = emul.trace(sc.desc, batch, mode)
+        assert emul.topology_applied() and cnt["fast_valid"] == 1
+        assert_hits_equal(hits, orc.trace_batch(sc.desc, batch), "topology %d mode %d" % (kind, mode))
+
+
+@pytest.mark.parametrize("mode", [FAST, LANE])
+def test_retopologised_pathtracer_matches_oracle(orc, alt_topology, scenes, box1, mode):
+    """A whole PT iteration on the median-split topology equals the oracle's bit for bit (as on the reference topology)."""
+    emul = alt_topology
+    emul.set_topology(emul.TOPOLOGY_MEDIAN, seed=9)
+    W = H = 40
+    C = scenes.BOX1_CAMERA
+    cam = orc.camera(C["pos"], C["lookat"], C["fov"], W, H)
+    s = _light_sampler(orc, box1).generate(128)
+    ref, rc = orc.render_pt(box1.desc, cam, W, H, s, orc.wanghash(3), 16)
+    img, ec = emul.render(box1.desc, cam, W, H, s, 0, orc.wanghash(3), 16, mode=mode)
+    assert emul.topology_applied()
+    assert np.array_equal(img, ref)
+    for k in ("closest_rays", "any_rays", "camera_paths", "shaded_vertices"):
+        assert ec[k] == rc[k]

@@ -287,3 +287,53 @@ def test_device_hierarchy_build(g, orc, scenes, which, method):
     same_t = hits["t"].view(np.uint32) == sah["t"].view(np.uint32)
     assert same_t[n // 4:].mean() > 0.9999                       # closest hits: the same distance bits (ties aside)
     assert np.array_equal(hits["leaf_tri"][: n // 4], sah["leaf_tri"][: n // 4])   # any-hit: occluded or not
+
+
+def test_upload_topology_is_exact(g, orc, scenes, box1, box1_coincident, tmp_path):
+    """GI_OPT_UPLOAD_TOPOLOGY (default GI_TOPOLOGY_PLOC): the ordered walks run on a tree the device re-clustered over the REFERENCE'S
+    leaves at upload.  Hit flag, triangle id, distance and barycentrics must equal the oracle's bit for bit on both topologies (camera
+    rays, secondaries, finite shadow rays, overlapping slivers, exact ties), and a PT iteration must be bit-identical between them."""
+    C = scenes.BOX1_CAMERA
+    sponza = scenes.make_sponza_like(str(tmp_path), texture_size=32)
+    S = scenes.SPONZA_CAMERA
+    sliver = scenes.make_random_triangles(20000, seed=7, build_method="sah")
+    rng = np.random.RandomState(5)
+    n = 50000
+    ties = np.zeros(n, dtype=g.RAY_DTYPE)
+    lo, hi = np.array([0.25, 0.05, -1.3]), np.array([1.05, 0.7, -0.5])
+    ties["origin"] = (lo + rng.rand(n, 3) * (hi - lo)).astype(np.float32)
+    d = rng.randn(n, 3); d[:, 1] = -np.abs(d[:, 1]) - 0.2
+    ties["direction"] = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    ties["t_max"] = np.float32(g.RAY_MAX)
+    cases = [
+        (box1, np.concatenate([camera_ray_batch(g, orc, box1, C["pos"], C["lookat"], C["fov"], 128, 128, 1), make_ray_batch(g, box1, 200000, 2)])),
+        (sponza, np.concatenate([camera_ray_batch(g, orc, sponza, S["pos"], S["lookat"], S["fov"], 320, 180, 4), make_ray_batch(g, sponza, 300000, 5)])),
+        (sliver, make_ray_batch(g, sliver, 300000, 3)),
+        (box1_coincident, ties),
+    ]
+    for topo in (g.GI_TOPOLOGY_PLOC, g.GI_TOPOLOGY_REFERENCE):
+        dev = g.Device(0)
+        dev.set_option(g.GI_OPT_UPLOAD_TOPOLOGY, topo)
+        for sc, rays in cases:
+            dev.upload_scene(sc)
+            active, ms = dev.scene_topology()
+            assert active == topo, "the re-clustered tree was rejected (boxes not nested?)"
+            dev.reset_counters()
+            hits = dev.trace(rays)
+            assert_hits_equal(hits, orc.trace_batch(sc.desc, rays), "topology %d" % topo)
+            assert dev.counters()["exact_fallback_rays"] < len(rays) // 2 or sc is box1_coincident
+        dev.close()
+    imgs = []
+    for topo in (g.GI_TOPOLOGY_PLOC, g.GI_TOPOLOGY_REFERENCE):
+        rs = g.RendererSystem(0)
+        rs.device.set_option(g.GI_OPT_UPLOAD_TOPOLOGY, topo)
+        rs.SetScene(sponza)
+        rs.SetScreenSize(320, 184)
+        rs.SetCamera(S["pos"], S["lookat"], S["fov"])
+        rs.SetRenderer("PT")
+        for _ in range(3):
+            rs.Draw()
+        imgs.append(rs.ReadBackbuffer().copy())
+        assert rs.device.scene_topology()[0] == topo
+        rs.close()
+    assert np.array_equal(imgs[0].view(np.uint32), imgs[1].view(np.uint32)), "PT images differ between the two topologies"
