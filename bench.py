@@ -224,7 +224,10 @@ def run_ours(args, rank, world, local_rank):
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     dev.set_stream(stream.cuda_stream)
+    if args.topology == "reference":
+        dev.set_option(g.GI_OPT_UPLOAD_TOPOLOGY, g.GI_TOPOLOGY_REFERENCE)
     rs.SetScene(scene)
+    topo_active, topo_ms = dev.scene_topology()
     rs.SetScreenSize(WIDTH, HEIGHT)
     rs.SetCamera(C["pos"], C["lookat"], C["fov"])
     rs.SetRenderer("PT")
@@ -384,7 +387,9 @@ def run_ours(args, rank, world, local_rank):
                                "complete iterations, D2H on a second stream), final draining ReadBackbuffer inside the timed region; e2e_sync: Draw() + "
                                "blocking ReadBackbuffer per step",
                    "l2": "no flush between iterations: resident inputs ~%.0f MB (BVH + leaf block + textures + accumulator) exceed the 126 MB L2" % scene_mb,
-                   "traversal": "fast (ordered short stack + exact fallback)", "scene_build_s": build_s, "mean_radiance": mean_lum},
+                   "traversal": "fast (ordered short stack + exact fallback)",
+                   "upload_topology": ("ploc: the bim hierarchy's leaves re-clustered on the device at upload (%.0f ms), hit ids / images bit-identical to the bim topology" % topo_ms)
+                   if topo_active == g.GI_TOPOLOGY_PLOC else "reference: the bim hierarchy as stored", "scene_build_s": build_s, "mean_radiance": mean_lum},
         "e2e": {"value": e2e_value, "unit": "Mpaths/s", "h2d_bytes_per_step": 128 * 32, "d2h_bytes_per_step": WIDTH * HEIGHT * 16},
         "e2e_sync": {"value": e2e_sync_value, "unit": "Mpaths/s", "h2d_bytes_per_step": 128 * 32, "d2h_bytes_per_step": WIDTH * HEIGHT * 16},
         "gpu_launches": int(launches),
@@ -416,6 +421,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--texture-size", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--topology", default="ploc", choices=["ploc", "reference"], help="GI_OPT_UPLOAD_TOPOLOGY of the ordered walks (results identical)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

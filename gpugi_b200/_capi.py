@@ -115,6 +115,7 @@ GI_OPT_KERNEL_TIMING = 8
 GI_OPT_STREAMING = 9
 GI_OPT_DEVICE_BUILDER = 10
 GI_OPT_UPLOAD_TOPOLOGY = 11
+GI_OPT_PLOC_RADIUS = 12
 GI_TOPOLOGY_REFERENCE, GI_TOPOLOGY_PLOC = 0, 1
 GI_BUILDER_LBVH, GI_BUILDER_PLOC = 0, 1
 GI_KERNEL_TRACE, GI_KERNEL_SHADE, GI_KERNEL_GENERATE, GI_KERNEL_MEGAKERNEL, GI_KERNEL_OTHER, GI_KERNEL_CLASS_COUNT = 0, 1, 2, 3, 4, 5

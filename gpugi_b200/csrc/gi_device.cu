@@ -489,6 +489,7 @@ struct GiContext
 	int uploadTopology = GI_TOPOLOGY_PLOC; // GI_OPT_UPLOAD_TOPOLOGY (what the next gi_upload_scene builds)
 	int sceneTopology = GI_TOPOLOGY_REFERENCE; // what the uploaded scene's ordered layout is built on
 	double topologyBuildMs = 0.0;
+	int plocRadius = 4; // GI_OPT_PLOC_RADIUS (clustering passes of the upload topology; B200 sweep: 4 beats 1..3 and 6..64 on C2, 2..4 on C5)
 	uint32_t lightSlot = 0;          // ring slot of the light-sample set the next iteration uses
 	// asynchronous read-out (gi_read_accumulator_async)
 	cudaStream_t copyStream = nullptr;
@@ -1013,6 +1014,7 @@ int gi_set_option(GiContext* c, int option, int value)
 	case GI_OPT_DEVICE_BUILDER:
 		if (value != GI_BUILDER_LBVH && value != GI_BUILDER_PLOC) return fail(c, GI_ERR_INVALID, "GI_OPT_DEVICE_BUILDER: unknown builder");
 		c->deviceBuilder = value; return GI_OK;
+	case GI_OPT_PLOC_RADIUS: c->plocRadius = std::min(std::max(value, 1), PLOC_MAX_RADIUS); return GI_OK;
 	case GI_OPT_UPLOAD_TOPOLOGY:
 		if (value != GI_TOPOLOGY_REFERENCE && value != GI_TOPOLOGY_PLOC) return fail(c, GI_ERR_INVALID, "GI_OPT_UPLOAD_TOPOLOGY: unknown topology");
 		c->uploadTopology = value; return GI_OK;
@@ -1106,7 +1108,7 @@ static int buildLeafTreeOnDevice(GiContext* c, const GiSceneDesc* d, const HostL
 		{
 			const unsigned g = (n + B - 1) / B;
 			if (forced) k_ploc_force_pairs<<<g, B, 0, st>>>(n, dNearest);
-			else k_ploc_nearest<<<g, B, 0, st>>>(n, clA, pt, dNearest);
+			else k_ploc_nearest<<<g, B, 0, st>>>(n, clA, pt, dNearest, c->plocRadius);
 			k_ploc_merge<<<g, B, 0, st>>>(n, clA, dNearest, pt, dCounters, dMerged, dValid);
 			step(cub::DeviceScan::ExclusiveSum(dScanTmp, scanBytes, dValid, dOffset, int(n), st));
 			k_ploc_compact<<<g, B, 0, st>>>(n, dMerged, dValid, dOffset, clB, dCounters + 1);

@@ -233,7 +233,8 @@ __global__ void __launch_bounds__(256) k_lbvh_emit(int numLeaves, LbvhTree tr, c
 // splits by Morton bits only), at a few more milliseconds of build time.
 // Node ids: leaves 0 .. L-1, inner nodes L .. 2L-2 (allocated at merge time).  Per node: box, children, parent, subtree sizes.
 // ====================================================================================================================================
-#define PLOC_RADIUS 16
+#define PLOC_RADIUS 16      // window of the triangle-pairing pass and default of the clustering passes
+#define PLOC_MAX_RADIUS 64  // the clustering passes take the radius as an argument (GI_OPT_PLOC_RADIUS)
 
 struct PlocTree
 {
@@ -262,11 +263,11 @@ GI_D float plocUnionArea(const float* amn, const float* amx, const float* bmn, c
 }
 
 // nearest neighbour of every cluster inside the window; ties go to the smaller position, so that mutual pairs always exist
-__global__ void __launch_bounds__(256) k_ploc_nearest(uint32_t n, const uint32_t* __restrict__ clusters, PlocTree t, uint32_t* __restrict__ nearest)
+__global__ void __launch_bounds__(256) k_ploc_nearest(uint32_t n, const uint32_t* __restrict__ clusters, PlocTree t, uint32_t* __restrict__ nearest, int radius = PLOC_RADIUS)
 {
-	__shared__ float smn[256 + 2 * PLOC_RADIUS][3], smx[256 + 2 * PLOC_RADIUS][3];
-	const int base = int(blockIdx.x * blockDim.x) - PLOC_RADIUS;
-	for (int k = threadIdx.x; k < 256 + 2 * PLOC_RADIUS; k += blockDim.x)
+	__shared__ float smn[256 + 2 * PLOC_MAX_RADIUS][3], smx[256 + 2 * PLOC_MAX_RADIUS][3];
+	const int base = int(blockIdx.x * blockDim.x) - radius;
+	for (int k = threadIdx.x; k < 256 + 2 * radius; k += blockDim.x)
 	{
 		const int j = base + k;
 		if (j >= 0 && j < int(n))
@@ -278,9 +279,9 @@ __global__ void __launch_bounds__(256) k_ploc_nearest(uint32_t n, const uint32_t
 	__syncthreads();
 	const int i = int(blockIdx.x * blockDim.x + threadIdx.x);
 	if (i >= int(n)) return;
-	const int self = int(threadIdx.x) + PLOC_RADIUS;
+	const int self = int(threadIdx.x) + radius;
 	float best = GI_INF; int bestJ = -1;
-	for (int o = -PLOC_RADIUS; o <= PLOC_RADIUS; ++o)
+	for (int o = -radius; o <= radius; ++o)
 	{
 		const int j = i + o;
 		if (o == 0 || j < 0 || j >= int(n)) continue;

@@ -201,6 +201,7 @@ enum {
 	                                   iteration at a time if the ring does not fit the device memory).  gi_read_accumulator_async
 	                                   does NOT drain. */
 	GI_OPT_DEVICE_BUILDER = 10,     /* GI_BUILDER_*: what gi_build_hierarchy builds */
+	GI_OPT_PLOC_RADIUS = 12,        /* neighbour window (1..64, default 4) of the clustering passes behind GI_TOPOLOGY_PLOC: tree quality vs upload time */
 	GI_OPT_UPLOAD_TOPOLOGY = 11     /* GI_TOPOLOGY_*: the tree the ORDERED walks of the next gi_upload_scene run on.  Results do not depend on it
 	                                   (bit-exact either way, see GI_TOPOLOGY_PLOC); refNodes / the reference-order walk are never touched. */
 };

@@ -31,6 +31,8 @@ int g_topology = 0;
 uint32_t g_topologySeed = 1;
 int g_topologyApplied = 0;
 
+LeafTree g_userTree;
+
 uint32_t emRand(uint32_t& s) { s ^= s << 13; s ^= s >> 17; s ^= s << 5; return s; }
 
 void uniteBoxes(LeafTree& t, uint32_t id, uint32_t a, uint32_t b)
@@ -78,7 +80,29 @@ bool applyTestTopology(const GiSceneDesc* d, HostLayout& L)
 		std::memcpy(&t.boxMin[size_t(p) * 3], ln.min, 12); std::memcpy(&t.boxMax[size_t(p) * 3], ln.max, 12);
 	}
 	uint32_t nextInner = nl;
-	if (g_topology == 1)
+	if (g_topology == 3)
+	{
+		// tree handed in by em_set_tree (experiments with builders in Python): leaf positions as given, boxes bottom-up
+		if (g_userTree.numLeaves != nl) return false;
+		t.leafOf = g_userTree.leafOf; t.left = g_userTree.left; t.right = g_userTree.right; t.root = g_userTree.root;
+		for (uint32_t p = 0; p < nl; ++p)
+		{
+			if (t.leafOf[p] >= nl) return false;
+			const GiNode& ln = d->nodes[L.leafNode[t.leafOf[p]]];
+			std::memcpy(&t.boxMin[size_t(p) * 3], ln.min, 12); std::memcpy(&t.boxMax[size_t(p) * 3], ln.max, 12);
+		}
+		std::vector<std::pair<uint32_t, int>> stack; stack.push_back({t.root, 0});
+		size_t guard = 0;
+		while (!stack.empty())
+		{
+			auto [x, state] = stack.back(); stack.pop_back();
+			if (x >= N || ++guard > size_t(4) * N) return false;
+			if (x < nl) continue;
+			if (state == 0) { stack.push_back({x, 1}); stack.push_back({t.left[x], 0}); stack.push_back({t.right[x], 0}); }
+			else uniteBoxes(t, x, t.left[x], t.right[x]);
+		}
+	}
+	else if (g_topology == 1)
 	{
 		std::vector<uint32_t> pos(nl);
 		for (uint32_t p = 0; p < nl; ++p) pos[p] = p;
@@ -122,6 +146,14 @@ bool makeScene(const GiSceneDesc* d, EmScene& e, std::string& err)
 }
 
 EM_API void em_set_topology(int kind, uint32_t seed) { g_topology = kind; g_topologySeed = seed; }
+EM_API void em_set_tree(uint32_t num_leaves, const uint32_t* left, const uint32_t* right, const uint32_t* leaf_of, uint32_t root)
+{
+	const uint32_t N = 2 * num_leaves - 1;
+	g_userTree = LeafTree();
+	g_userTree.numLeaves = num_leaves; g_userTree.root = root;
+	g_userTree.left.assign(left, left + N); g_userTree.right.assign(right, right + N); g_userTree.leafOf.assign(leaf_of, leaf_of + num_leaves);
+	g_topology = 3;
+}
 EM_API int em_topology_applied(void) { return g_topologyApplied; }
 
 struct EmCounters

@@ -60,6 +60,17 @@ def set_topology(kind, seed=1):
     lib.em_set_topology(int(kind), int(seed))
 
 
+lib.em_set_tree.restype = None
+lib.em_set_tree.argtypes = [u32, vp, vp, vp, u32]
+
+
+def set_tree(left, right, leaf_of, root):
+    """Ordered walks of the following calls run on this tree over the reference's leaves (node ids: leaf positions 0..L-1, inner L..2L-2)."""
+    left = np.ascontiguousarray(left, dtype=np.uint32); right = np.ascontiguousarray(right, dtype=np.uint32)
+    leaf_of = np.ascontiguousarray(leaf_of, dtype=np.uint32)
+    lib.em_set_tree(len(leaf_of), _p(left), _p(right), _p(leaf_of), int(root))
+
+
 def topology_applied():
     return bool(lib.em_topology_applied())
 

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--out", default="gpurun_out/config_sweep.json")
     ap.add_argument("--topologies", default="ploc", help="comma list of ploc,reference (GI_OPT_UPLOAD_TOPOLOGY): every config is measured on each")
     ap.add_argument("--modes", default="sequential,batch")
+    ap.add_argument("--radii", default="4", help="comma list of GI_OPT_PLOC_RADIUS values tried for the ploc topology")
     args = ap.parse_args()
     import torch
     import gpugi_b200 as g
@@ -42,12 +43,13 @@ def main():
         t0 = time.time()
         sc = build()
         build_s = time.time() - t0
-        for topo in args.topologies.split(","):
+        for topo, radius in [(t, int(r)) for t in args.topologies.split(",") for r in (args.radii.split(",") if t == "ploc" else ["4"])]:
             dev = g.Device(0)
             stream = torch.cuda.Stream()
             torch.cuda.set_stream(stream)
             dev.set_stream(stream.cuda_stream)
             dev.set_option(g.GI_OPT_UPLOAD_TOPOLOGY, g.GI_TOPOLOGY_PLOC if topo == "ploc" else g.GI_TOPOLOGY_REFERENCE)
+            dev.set_option(g.GI_OPT_PLOC_RADIUS, radius)
             t1 = time.time()
             dev.upload_scene(sc)
             upload_s = time.time() - t1
@@ -86,7 +88,7 @@ def main():
                 img = dev.read_accumulator(W, H)
                 paths = cnt["camera_paths"] + cnt["light_paths"]
                 rays = cnt["closest_rays"] + cnt["any_rays"]
-                r = {"config": key, "workload": label, "mode": mode, "topology": topo, "topology_active": active, "topology_build_ms": topo_ms, "upload_s": upload_s, "iterations": args.iters, "triangles": int(sc.info.num_leaf_triangles), "scene_build_s": build_s,
+                r = {"config": key, "workload": label, "mode": mode, "topology": topo, "ploc_radius": radius, "topology_active": active, "topology_build_ms": topo_ms, "upload_s": upload_s, "iterations": args.iters, "triangles": int(sc.info.num_leaf_triangles), "scene_build_s": build_s,
                      "ms_per_iteration": ms / args.iters, "mpaths_per_s": paths / ms / 1e3, "mrays_per_s": rays / ms / 1e3, "rays_per_path": rays / max(paths, 1),
                      "mean_radiance": float(img[..., :3].mean() / args.iters), "finite": bool(np.isfinite(img).all()), "light_cache_capacity": cap,
                      "num_rays_per_light_sample": nr, "free_gb_after": torch.cuda.mem_get_info()[0] / 2**30}
