@@ -49,6 +49,9 @@ struct WfCounters
 #ifndef WF_TOP_IN_REGS
 #define WF_TOP_IN_REGS 0   // most recent stack entry in registers
 #endif
+#ifndef WF_WIDE4
+#define WF_WIDE4 0         // 4-wide inner nodes (gi_layout.h: emitWide4): 64-byte records, two 256-bit loads, up to three pushes per step
+#endif
 #define WF_MAX_CAND 8
 
 enum { WFL_ANY = 1u, WFL_OVERFLOW = 2u, WFL_OCCLUDED = 4u, WFL_EXACT = 8u, WFL_COLLECT = 16u, WFL_GUARD = 32u };
@@ -286,6 +289,37 @@ GI_HD bool wfSlabTest(const WfLane& L, uint32_t wx, uint32_t wy, uint32_t wz, fl
 	return nearLow <= fminf(wfMin3(fx, fy, fz), L.limit);
 }
 
+#if WF_WIDE4
+// 4-wide inner node: words 0..11 = child k, axis a at 3k + a (min plane | max plane << 16), words 12..15 = child links (wide index >= 0,
+// leaf = ~leafIndex).  An unused slot carries the empty box (min 65535, max 0 on every axis), which the conservative test rejects for
+// every ray inside its domain.  The accepted children are visited nearest first; the others go to the stack, farthest first.
+template <class STK, class CNT>
+GI_HD void wfInnerStep(WfLane& L, const DScene& s, const STK& stack, CNT& cnt)
+{
+	const U8 a = ld8(s.qNodes + 16 * size_t(L.node));
+	const U8 b = ld8(s.qNodes + 16 * size_t(L.node) + 8);
+	cnt.template add<WFC_NODES>(4u);
+	float f0, f1, f2, f3v;
+	if (!wfSlabTest(L, a.v[0], a.v[1], a.v[2], f0)) f0 = GI_INF;
+	if (!wfSlabTest(L, a.v[3], a.v[4], a.v[5], f1)) f1 = GI_INF;
+	if (!wfSlabTest(L, a.v[6], a.v[7], b.v[0], f2)) f2 = GI_INF;
+	if (!wfSlabTest(L, b.v[1], b.v[2], b.v[3], f3v)) f3v = GI_INF;
+	int c0 = int(b.v[4]), c1 = int(b.v[5]), c2 = int(b.v[6]), c3 = int(b.v[7]);
+	// sorting network (0,1)(2,3)(0,2)(1,3)(1,2): ascending entry distance, rejected children (inf) last
+#define WF_CSWAP(fa, ca, fb, cb) { if (fb < fa) { const float tf = fa; fa = fb; fb = tf; const int tc = ca; ca = cb; cb = tc; } }
+	WF_CSWAP(f0, c0, f1, c1) WF_CSWAP(f2, c2, f3v, c3) WF_CSWAP(f0, c0, f2, c2) WF_CSWAP(f1, c1, f3v, c3) WF_CSWAP(f1, c1, f2, c2)
+#undef WF_CSWAP
+	if (f0 < GI_INF)
+	{
+		if (f3v < GI_INF) wfPush(L, stack, c3, f3v);
+		if (f2 < GI_INF) wfPush(L, stack, c2, f2);
+		if (f1 < GI_INF) wfPush(L, stack, c1, f1);
+		L.node = c0;
+	}
+	else wfPop(L, stack);
+	wfStash(L, stack);
+}
+#else
 template <class STK, class CNT>
 GI_HD void wfInnerStep(WfLane& L, const DScene& s, const STK& stack, CNT& cnt)
 {
@@ -307,6 +341,8 @@ GI_HD void wfInnerStep(WfLane& L, const DScene& s, const STK& stack, CNT& cnt)
 	else wfPop(L, stack);
 	wfStash(L, stack);
 }
+
+#endif
 
 // what follows a tested leaf: the next stack entry, or (WF_POSTPONE_LEAF) the node the lane already stands at
 template <class STK>

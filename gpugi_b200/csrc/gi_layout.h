@@ -27,6 +27,9 @@ struct HostLayout
 	std::vector<DMaterial> materials;
 	std::vector<DTexel> texels;             // 4 per material; .pixels still points at HOST memory here
 	std::vector<int32_t> materialTexture;   // 4 per material: index into GiSceneDesc::textures
+	struct ChildBox { uint32_t word; float mn[3], mx[3]; }; // test hook: where in qNodes an encoded child box starts (3 words) + the exact box
+	bool keepChildBoxes = false;            // set by the test emulator before the build
+	std::vector<ChildBox> childBoxes;
 	bool binary = false;                    // strictly binary tree => fastNodes usable
 	DScene scene = {};                      // counts, flags, ambiguity window (pointers unset)
 };
@@ -71,6 +74,25 @@ struct FastEmitter
 		while (q < 65535.0 && gridLo[k] + q * gridScale[k] < double(x)) q += 1.0;
 		return uint32_t(q);
 	}
+	// one box -> three words (min plane | max plane << 16 per axis); false if the grid does not cover it
+	bool quantBox(const float bmin[3], const float bmax[3], uint32_t out[3]) const
+	{
+		bool covered = true;
+		for (int k = 0; k < 3; ++k)
+		{
+			const uint32_t lo = quantLo(bmin[k], k), hi = quantHi(bmax[k], k);
+			if (gridLo[k] + double(lo) * gridScale[k] > double(bmin[k]) || gridLo[k] + double(hi) * gridScale[k] < double(bmax[k])) covered = false;
+			out[k] = lo | (hi << 16);
+		}
+		return covered;
+	}
+	static void noteChildBox(HostLayout& L, size_t word, const float bmin[3], const float bmax[3])
+	{
+		if (!L.keepChildBoxes) return;
+		HostLayout::ChildBox cb; cb.word = uint32_t(word);
+		for (int k = 0; k < 3; ++k) { cb.mn[k] = bmin[k]; cb.mx[k] = bmax[k]; }
+		L.childBoxes.push_back(cb);
+	}
 	// inner node `index` with the child boxes a, b and the child links c0, c1 (inner index >= 0, leaf = ~leafIndex).
 	// false: the grid does not cover a box (cannot happen for boxes nested in the root box).
 	bool emit(HostLayout& L, uint32_t index, const float amin[3], const float amax[3], const float bmin[3], const float bmax[3], int c0, int c1) const
@@ -96,9 +118,108 @@ struct FastEmitter
 		uint32_t* qn = &L.qNodes[size_t(index) * 8];
 		for (int k = 0; k < 3; ++k) { qn[k] = v[k] | (v[3 + k] << 16); qn[3 + k] = v[6 + k] | (v[9 + k] << 16); }
 		qn[6] = uint32_t(c0); qn[7] = uint32_t(c1);
+		noteChildBox(L, size_t(index) * 8, amin, amax); noteChildBox(L, size_t(index) * 8 + 3, bmin, bmax);
 		return covered;
 	}
 };
+
+// ---- a second topology over the SAME leaves (GI_OPT_UPLOAD_TOPOLOGY).  The ordered walks only need a binary tree whose inner boxes
+// contain their children's and whose leaves are the reference's leaves with the reference leaf node's own box (the exact gate of
+// DESIGN.md 4): the reference visits a leaf iff the slab test of every ancestor passes, which -- the test being monotone in the box and
+// bim's boxes being nested -- it does iff the test of the leaf's own box passes.  So ANY such tree returns the reference's answer; the
+// hit ids stay reference leaf indices, ties and near-ties still go to the reference-order re-trace on refNodes.
+// Node ids: 0 .. L-1 = leaves (position p holds reference leaf leafOf[p]), L .. 2L-2 = inner nodes.
+struct LeafTree
+{
+	uint32_t numLeaves = 0, root = 0;
+	std::vector<uint32_t> left, right;      // per node id (entries of leaves unused)
+	std::vector<float> boxMin, boxMax;      // 3 per node id
+	std::vector<uint32_t> leafOf;           // per leaf position
+};
+
+// WF_WIDE4: the ordered wavefront walk runs on 4-wide nodes collapsed from the binary tree `t` (repeatedly replace the inner child with
+// the largest surface area by its two children until the node has four children or only leaves).  Wide nodes are numbered in preorder;
+// 16 words each (gi_lane.h: wfInnerStep).  The exactness argument is that of the binary layout: a collapsed node's children are
+// descendants of the binary node, their boxes nested in its box.
+inline bool emitWide4(const GiSceneDesc* d, HostLayout& L, const LeafTree& t, std::string& why)
+{
+	const uint32_t nl = t.numLeaves;
+	FastEmitter em;
+	HostLayout gridOnly;
+	em.init(d->nodes[0].min, d->nodes[0].max, gridOnly);
+	std::vector<uint32_t> q;
+	q.reserve(size_t(nl) * 8);
+	if (L.keepChildBoxes) L.childBoxes.clear();
+	auto areaOf = [&](uint32_t x) {
+		const float* mn = &t.boxMin[size_t(x) * 3]; const float* mx = &t.boxMax[size_t(x) * 3];
+		const double dx = double(mx[0]) - mn[0], dy = double(mx[1]) - mn[1], dz = double(mx[2]) - mn[2];
+		return dx * dy + dy * dz + dz * dx;
+	};
+	struct Item { uint32_t node; uint32_t parentWord; }; // parentWord: index into q of the link to patch (0xffffffff for the root)
+	std::vector<Item> stack;
+	stack.push_back({t.root, 0xffffffffu});
+	while (!stack.empty())
+	{
+		const Item it = stack.back(); stack.pop_back();
+		const uint32_t index = uint32_t(q.size() / 16);
+		if (it.parentWord != 0xffffffffu) q[it.parentWord] = index;
+		uint32_t kids[4] = {t.left[it.node], t.right[it.node], 0, 0};
+		int n = 2;
+		while (n < 4)
+		{
+			int pick = -1; double best = -1.0;
+			for (int k = 0; k < n; ++k)
+				if (kids[k] >= nl) { const double a = areaOf(kids[k]); if (a > best) { best = a; pick = k; } }
+			if (pick < 0) break;
+			const uint32_t x = kids[pick];
+			for (int k = n; k > pick + 1; --k) kids[k] = kids[k - 1];
+			kids[pick] = t.left[x]; kids[pick + 1] = t.right[x];
+			++n;
+		}
+		const size_t base = q.size();
+		q.resize(base + 16, 0u);
+		for (int k = 0; k < 4; ++k)
+		{
+			uint32_t w[3] = {0x0000ffffu, 0x0000ffffu, 0x0000ffffu}; // empty box: min 65535, max 0
+			uint32_t link = uint32_t(WF_NODE_DONE);
+			if (k < n)
+			{
+				const float* mn = &t.boxMin[size_t(kids[k]) * 3]; const float* mx = &t.boxMax[size_t(kids[k]) * 3];
+				if (!em.quantBox(mn, mx, w)) { why = "quantisation grid does not cover a box"; return false; }
+				FastEmitter::noteChildBox(L, base + 3 * size_t(k), mn, mx);
+				if (kids[k] < nl) link = uint32_t(~int(t.leafOf[kids[k]]));
+			}
+			q[base + 3 * size_t(k)] = w[0]; q[base + 3 * size_t(k) + 1] = w[1]; q[base + 3 * size_t(k) + 2] = w[2];
+			q[base + 12 + size_t(k)] = link;
+		}
+		for (int k = n - 1; k >= 0; --k) // reverse push: the first child gets the next preorder index
+			if (kids[k] >= nl) stack.push_back({kids[k], uint32_t(base + 12 + size_t(k))});
+	}
+	L.qNodes.swap(q);
+	return true;
+}
+
+// the reference's own (binary, validated) topology as a LeafTree: leaf position = leaf index, inner id = numLeaves + preorder inner index
+inline void referenceLeafTree(const GiSceneDesc* d, const std::vector<int>& fastIndex, LeafTree& t)
+{
+	const uint32_t nl = d->num_leaf_triangles / 2, N = 2u * nl - 1u;
+	t = LeafTree();
+	t.numLeaves = nl; t.root = nl;
+	t.left.assign(N, 0u); t.right.assign(N, 0u); t.boxMin.assign(size_t(N) * 3, 0.0f); t.boxMax.assign(size_t(N) * 3, 0.0f); t.leafOf.resize(nl);
+	for (uint32_t p = 0; p < nl; ++p) t.leafOf[p] = p;
+	auto idOf = [&](uint32_t nodeIdx) -> uint32_t {
+		const GiNode& n = d->nodes[nodeIdx];
+		return (n.first_child & 0x80000000u) ? (n.first_child & 0x7fffffffu) : nl + uint32_t(fastIndex[nodeIdx]);
+	};
+	for (uint32_t i = 0; i < d->num_nodes; ++i)
+	{
+		const GiNode& n = d->nodes[i];
+		const uint32_t id = idOf(i);
+		if (id >= N) continue;
+		std::memcpy(&t.boxMin[size_t(id) * 3], n.min, 12); std::memcpy(&t.boxMax[size_t(id) * 3], n.max, 12);
+		if (!(n.first_child & 0x80000000u)) { t.left[id] = idOf(n.first_child); t.right[id] = idOf(d->nodes[n.first_child].escape); }
+	}
+}
 
 inline float srgbDecodeHost(uint8_t v)
 {
@@ -244,6 +365,15 @@ inline bool buildHostLayout(const GiSceneDesc* d, HostLayout& L, std::string& er
 		};
 		if (!em.emit(L, uint32_t(fastIndex[i]), a.min, a.max, b.min, b.max, encode(left), encode(right))) L.binary = false;
 	}
+#if WF_WIDE4
+	if (L.binary && numInner > 0)
+	{
+		LeafTree rt;
+		referenceLeafTree(d, fastIndex, rt);
+		std::string why;
+		if (!emitWide4(d, L, rt, why)) L.binary = false;
+	}
+#endif
 
 	// ---- materials
 	L.materials.resize(d->num_materials);
@@ -317,20 +447,6 @@ inline bool buildHostLayout(const GiSceneDesc* d, HostLayout& L, std::string& er
 	return true;
 }
 
-// ---- a second topology over the SAME leaves (GI_OPT_UPLOAD_TOPOLOGY).  The ordered walks only need a binary tree whose inner boxes
-// contain their children's and whose leaves are the reference's leaves with the reference leaf node's own box (the exact gate of
-// DESIGN.md 4): the reference visits a leaf iff the slab test of every ancestor passes, which -- the test being monotone in the box and
-// bim's boxes being nested -- it does iff the test of the leaf's own box passes.  So ANY such tree returns the reference's answer; the
-// hit ids stay reference leaf indices, ties and near-ties still go to the reference-order re-trace on refNodes.
-// Node ids: 0 .. L-1 = leaves (position p holds reference leaf leafOf[p]), L .. 2L-2 = inner nodes.
-struct LeafTree
-{
-	uint32_t numLeaves = 0, root = 0;
-	std::vector<uint32_t> left, right;      // per node id (entries of leaves unused)
-	std::vector<float> boxMin, boxMax;      // 3 per node id
-	std::vector<uint32_t> leafOf;           // per leaf position
-};
-
 // Rewrites fastNodes / qNodes from `t`, inner nodes numbered in preorder (the memory order the walks like).  Leaves L untouched and
 // returns false (with the reason) if `t` is not a valid tree over the reference's leaves with nested boxes.
 inline bool applyLeafTree(const GiSceneDesc* d, HostLayout& L, const LeafTree& t, std::string& why)
@@ -378,6 +494,7 @@ inline bool applyLeafTree(const GiSceneDesc* d, HostLayout& L, const LeafTree& t
 			if (!FastEmitter::nested(&t.boxMin[size_t(x) * 3], &t.boxMax[size_t(x) * 3], &t.boxMin[size_t(ch) * 3], &t.boxMax[size_t(ch) * 3])) { why = "child box not inside its parent's"; return false; }
 	// encode into fresh vectors, swap in on success
 	HostLayout tmp;
+	tmp.keepChildBoxes = L.keepChildBoxes;
 	tmp.fastNodes.assign(size_t(nl - 1) * 4, F4{0.0f, 0.0f, 0.0f, 0.0f});
 	tmp.qNodes.assign(size_t(nl - 1) * 8, 0u);
 	FastEmitter em;
@@ -389,6 +506,18 @@ inline bool applyLeafTree(const GiSceneDesc* d, HostLayout& L, const LeafTree& t
 		if (!em.emit(tmp, rank[x], &t.boxMin[size_t(a) * 3], &t.boxMax[size_t(a) * 3], &t.boxMin[size_t(b) * 3], &t.boxMax[size_t(b) * 3], link(a), link(b)))
 		{ why = "quantisation grid does not cover a box"; return false; }
 	}
+#if WF_WIDE4
+	{
+		HostLayout wide;
+		wide.keepChildBoxes = L.keepChildBoxes;
+		if (!emitWide4(d, wide, t, why)) return false;
+		L.fastNodes.swap(tmp.fastNodes);
+		L.qNodes.swap(wide.qNodes);
+		L.childBoxes.swap(wide.childBoxes);
+		return true;
+	}
+#endif
+	if (L.keepChildBoxes) L.childBoxes.swap(tmp.childBoxes);
 	L.fastNodes.swap(tmp.fastNodes);
 	L.qNodes.swap(tmp.qNodes);
 	return true;

@@ -125,8 +125,9 @@ bool applyTestTopology(const GiSceneDesc* d, HostLayout& L)
 	return applyLeafTree(d, L, t, why);
 }
 
-bool makeScene(const GiSceneDesc* d, EmScene& e, std::string& err)
+bool makeScene(const GiSceneDesc* d, EmScene& e, std::string& err, bool keepChildBoxes = false)
 {
+	e.L.keepChildBoxes = keepChildBoxes;
 	if (!buildHostLayout(d, e.L, err)) return false;
 	g_topologyApplied = 0;
 	if (g_topology != 0 && applyTestTopology(d, e.L)) g_topologyApplied = 1;
@@ -445,12 +446,11 @@ EM_API int em_bidir_eye(const GiSceneDesc* desc, const GiCamera* cam, int w, int
 EM_API int em_slab_check(const GiSceneDesc* desc, const GiRay* rays, uint32_t n, uint32_t stride, uint64_t* out)
 {
 	EmScene e; std::string err;
-	if (!makeScene(desc, e, err)) return 1;
+	if (!makeScene(desc, e, err, true)) return 1;
 	if (!e.L.binary) return 2;
 	for (int i = 0; i < 5; ++i) out[i] = 0;
-	std::vector<uint32_t> inner;
-	for (uint32_t i = 0; i < desc->num_nodes; ++i)
-		if (!(desc->nodes[i].first_child & 0x80000000u)) inner.push_back(i);
+	// every child box the layout encoded (binary or 4-wide nodes, reference or re-clustered topology), with its exact floats
+	const std::vector<HostLayout::ChildBox>& boxes = e.L.childBoxes;
 	for (uint32_t r = 0; r < n; ++r)
 	{
 		WfLane L;
@@ -458,22 +458,17 @@ EM_API int em_slab_check(const GiSceneDesc* desc, const GiRay* rays, uint32_t n,
 		const F3 inv = invDir(d);
 		if (!wfSlabSetup(L, e.s, o, inv)) { ++out[4]; continue; }
 		L.limit = rays[r].t_max;
-		for (size_t fi = r % stride; fi < inner.size(); fi += stride)
+		for (size_t bi = r % stride; bi < boxes.size(); bi += stride)
 		{
-			const GiNode& nd = desc->nodes[inner[fi]];
-			const uint32_t kids[2] = {nd.first_child, desc->nodes[nd.first_child].escape};
-			const U8 q = ld8(e.s.qNodes + 8 * fi);
-			for (int c = 0; c < 2; ++c)
-			{
-				const GiNode& ch = desc->nodes[kids[c]];
-				float first, last, nearLow;
-				const bool exact = intersectBox(o, inv, ch.min[0], ch.min[1], ch.min[2], ch.max[0], ch.max[1], ch.max[2], first, last) && first <= L.limit;
-				const bool cons = wfSlabTest(L, q.v[3 * c], q.v[3 * c + 1], q.v[3 * c + 2], nearLow);
-				++out[0];
-				if (exact) ++out[1];
-				if (cons) ++out[2];
-				if (exact && (!cons || nearLow > first)) ++out[3];
-			}
+			const HostLayout::ChildBox& cb = boxes[bi];
+			const uint32_t* q = e.s.qNodes + cb.word;
+			float first, last, nearLow;
+			const bool exact = intersectBox(o, inv, cb.mn[0], cb.mn[1], cb.mn[2], cb.mx[0], cb.mx[1], cb.mx[2], first, last) && first <= L.limit;
+			const bool cons = wfSlabTest(L, q[0], q[1], q[2], nearLow);
+			++out[0];
+			if (exact) ++out[1];
+			if (cons) ++out[2];
+			if (exact && (!cons || nearLow > first)) ++out[3];
 		}
 	}
 	return 0;

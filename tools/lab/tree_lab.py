@@ -76,6 +76,45 @@ def ploc(bmin, bmax, order, radius, radius_schedule=None):
     return left, right, int(clusters[0]), mn, mx, p
 
 
+def sah_sweep(bmin, bmax):
+    """Top-down full-sweep SAH over the leaves, all three axes (the quality yardstick).  Returns left, right, leaf_of, root, mn, mx."""
+    nl = len(bmin)
+    N = 2 * nl - 1
+    mn = np.zeros((N, 3), np.float32); mx = np.zeros((N, 3), np.float32)
+    mn[:nl] = bmin; mx[:nl] = bmax
+    left = np.zeros(N, np.uint32); right = np.zeros(N, np.uint32)
+    cen = 0.5 * bmin + 0.5 * bmax
+    nxt = [nl]
+
+    def alloc():
+        i = nxt[0]; nxt[0] += 1
+        return i
+    root = alloc()
+    stack = [(np.arange(nl), root)]
+    while stack:
+        ids, node = stack.pop()
+        n = len(ids)
+        mn[node] = bmin[ids].min(axis=0); mx[node] = bmax[ids].max(axis=0)
+        best = (np.inf, None, None)
+        for ax in range(3):
+            o = ids[np.argsort(cen[ids, ax], kind="stable")]
+            lmn = np.minimum.accumulate(bmin[o], axis=0); lmx = np.maximum.accumulate(bmax[o], axis=0)
+            rmn = np.minimum.accumulate(bmin[o][::-1], axis=0)[::-1]; rmx = np.maximum.accumulate(bmax[o][::-1], axis=0)[::-1]
+            k = np.arange(1, n)
+            cost = area(lmn[:-1], lmx[:-1]) * k + area(rmn[1:], rmx[1:]) * (n - k)
+            i = int(np.argmin(cost))
+            if cost[i] < best[0]:
+                best = (float(cost[i]), o, i + 1)
+        _, o, split = best
+        for part, side in ((o[:split], left), (o[split:], right)):
+            if len(part) == 1:
+                side[node] = part[0]
+            else:
+                c = alloc(); side[node] = c
+                stack.append((part, c))
+    return left, right, np.arange(nl, dtype=np.uint32), root, mn, mx
+
+
 def tree_stats(left, right, root, mn, mx, nl):
     depth = np.zeros(len(left), np.int32)
     stack = [(root, 1)]
@@ -132,11 +171,14 @@ def main():
                 # radius grows as the cluster list shrinks: small windows at the bottom, wide at the top
                 lo_r, hi_r = [int(x) for x in v[5:].split("_")]
                 left, right, root, mn, mx, passes = ploc(bmin, bmax, order, lo_r, lambda p, n: hi_r if n < nl // 64 else lo_r)
+            elif v == "sah":
+                left, right, order_v, root, mn, mx = sah_sweep(bmin, bmax)
+                passes = 0
             else:
                 raise SystemExit("unknown variant " + v)
             stats = tree_stats(left, right, root, mn, mx, nl)
             stats["passes"] = passes
-            emul.set_tree(left, right, order, root)
+            emul.set_tree(left, right, order_v if v == "sah" else order, root)
         tb = time.time() - t0
         hits, cnt = emul.trace(sc.desc, rays, 2)
         assert v == "ref" or emul.topology_applied()
