@@ -175,6 +175,9 @@ def run_reference(args, rank, world):
         return
     from gpugi_b200 import scenes
     from oracle import pyoracle as orc
+    if world > 1:
+        # torchrun exports OMP_NUM_THREADS=1 to every rank; rank 0 alone runs this arm and is meant to use every host core it may run on
+        orc.set_num_threads(len(os.sched_getaffinity(0)))
     scene, build_s = build_scene(args.texture_size)
     C = scenes.SPONZA_CAMERA
     cam = orc.camera(C["pos"], C["lookat"], C["fov"], WIDTH, HEIGHT)
@@ -257,6 +260,13 @@ def run_ours(args, rank, world, local_rank):
     seeds = [g.wang_hash(parallel.global_iteration(j, rank, world)) for j in range(n_iter)]
     dev.clear(); dev.reset_counters()
     dev.render_iterations(g.GI_RENDERER_PT, seeds[:Wm], PATH_LENGTH, d_samples.data_ptr(), 128)
+    if dist is not None:
+        # the warm-up covers the read-out collective as well: NCCL sets up its channels / NVLS buffers for a message size at first use
+        # (8 ranks: tens of ms), which is not part of a steady-state step.  Same call, same shape, on a scratch image.
+        scratch = torch.zeros_like(acc_t)
+        for _ in range(2):
+            parallel.reduce_accumulator(scratch, Wm, dist)
+        del scratch
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()

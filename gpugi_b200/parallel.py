@@ -37,7 +37,12 @@ def init_process_group(backend=None):
         if backend is None:
             import torch
             backend = "nccl" if torch.cuda.is_available() else "gloo"
-        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+        if backend == "nccl":
+            import torch
+            # device_id: the communicator is created here (eagerly, on this rank's GPU) instead of inside the first collective
+            dist.init_process_group(backend=backend, rank=rank, world_size=world, device_id=torch.device("cuda", torch.cuda.current_device()))
+        else:
+            dist.init_process_group(backend=backend, rank=rank, world_size=world)
     return dist
 
 

@@ -1171,6 +1171,14 @@ OR_API int or_num_threads(void)
 #endif
 }
 
+// launchers such as torchrun export OMP_NUM_THREADS=1 to every rank; the CPU baseline is meant to use all host cores
+OR_API void or_set_num_threads(int n)
+{
+#ifdef _OPENMP
+	if (n > 0) omp_set_num_threads(n);
+#endif
+}
+
 OR_API uint32_t or_wanghash(uint32_t x) { return wanghash(x); }
 // the remaining scalar generators, exported so that tests can pin them against oracle/_ref (the reference's own utilities/random.cpp,
 // compiled where it lies) and the golden vectors generated from it: random.glsl:11-19 == random.cpp:15-22 (xorshift32), random.cpp:25-43

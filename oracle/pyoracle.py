@@ -90,6 +90,14 @@ def _f3(v):
     return np.ascontiguousarray(v, dtype=np.float32)
 
 
+lib.or_set_num_threads.restype = None
+lib.or_set_num_threads.argtypes = [C.c_int]
+
+
+def set_num_threads(n):
+    lib.or_set_num_threads(int(n))
+
+
 def num_threads():
     return int(lib.or_num_threads())
 
