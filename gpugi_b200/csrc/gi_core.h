@@ -141,8 +141,9 @@ struct DScene
 	const F4* oboxNodes;     // bvhType = 1: 3 x F4 per node (center.xyz, firstChild) (sidesHalf.xyz, escape) (rotationInv.xyzw); else null
 	// fast layout: one 64-byte record per inner node holding BOTH child boxes
 	const F4* fastNodes;     // 4 x F4: (c0.min.xyz, c0.max.x) (c0.max.yz, c1.min.xy) (c1.min.z, c1.max.xyz) (child0, child1, -, -)
-	const uint32_t* qNodes;  // wavefront walk: 8 words (32 bytes, one 256-bit load) per INNER node: both child boxes on a 16-bit grid over
-	                         // the root box, rounded outwards, min | max << 16 per axis: (c0.x, c0.y, c0.z, c1.x, c1.y, c1.z, child0, child1)
+	const uint32_t* qNodes;  // wavefront walk: child boxes on a 16-bit grid over the root box, rounded outwards, min | max << 16 per axis.
+	                         // WF_WIDE4 (default): 16 words (64 bytes, two 256-bit loads) per 4-wide node -- 4 x (x, y, z) + 4 child links,
+	                         // unused slot = empty box; WF_WIDE4=0: 8 words per binary inner node (c0.xyz, c1.xyz, child0, child1)
 	float gridLo[3];         // grid origin (root box min) and cell size per axis
 	float gridScale[3];
 	const F4* leafPos;       // 6 x F4 per leaf: slot s -> [3s] = (p0.xyz, .), [3s+1] = (p1.xyz, .), [3s+2] = (p2.xyz, .); an unused slot has

@@ -50,8 +50,8 @@ struct WfCounters
 #define WF_TOP_IN_REGS 0   // most recent stack entry in registers
 #endif
 #ifndef WF_WIDE4
-#define WF_WIDE4 0         // 4-wide inner nodes (gi_layout.h: emitWide4): 64-byte records, two 256-bit loads, up to three pushes per step
-#endif
+#define WF_WIDE4 1         // 4-wide inner nodes (gi_layout.h: emitWide4): 64-byte records, two 256-bit loads, up to three pushes per step.
+#endif                     // B200 A/B against the binary nodes (0), ms per iteration: C2 PT 1.810 -> 1.765, C3 BPT 8.82 -> 8.38, C4 LPT 4K 8.06 -> 7.32, C5 PT 4K 17.77 -> 15.42
 #define WF_MAX_CAND 8
 
 enum { WFL_ANY = 1u, WFL_OVERFLOW = 2u, WFL_OCCLUDED = 4u, WFL_EXACT = 8u, WFL_COLLECT = 16u, WFL_GUARD = 32u };

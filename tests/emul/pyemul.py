@@ -6,7 +6,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# GI_EMUL_VARIANT=wide4 selects the build with the 4-wide inner nodes (WF_WIDE4) -- same tests, other build switch
+# GI_EMUL_VARIANT=bin2 selects the build with binary inner nodes (WF_WIDE4=0) -- same tests, other build switch
 LIB_PATH = os.path.join(_HERE, "libgi_emul_%s.so" % os.environ["GI_EMUL_VARIANT"] if os.environ.get("GI_EMUL_VARIANT") else "libgi_emul.so")
 
 

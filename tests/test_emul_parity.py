@@ -450,3 +450,31 @@ def test_retopologised_pathtracer_matches_oracle(orc, alt_topology, scenes, box1
     assert np.array_equal(img, ref)
     for k in ("closest_rays", "any_rays", "camera_paths", "shaded_vertices"):
         assert ec[k] == rc[k]
+
+
+def test_quantised_child_boxes_are_conservative(g, emul, scenes, box1):
+    """Every child box the layout encodes (4-wide nodes; reference and re-clustered topologies) against random rays: whenever the exact
+    slab test with first <= limit accepts, the quantised test accepts too and its entry distance is a lower bound (em_slab_check)."""
+    sliver = scenes.make_random_triangles(1500, seed=7, build_method="sah")
+    try:
+        for kind in (emul.TOPOLOGY_REFERENCE, emul.TOPOLOGY_MEDIAN, emul.TOPOLOGY_RANDOM):
+            emul.set_topology(kind, seed=5)
+            for sc, seed in ((box1, 2), (sliver, 3)):
+                r = emul.slab_check(sc.desc, make_ray_batch(g, sc, 3000, seed), stride=7)
+                assert r["tested"] > 50000 and r["exact_accepts"] > 1000
+                assert r["violations"] == 0, r
+                assert r["conservative_accepts"] >= r["exact_accepts"]
+    finally:
+        emul.set_topology(emul.TOPOLOGY_REFERENCE)
+
+
+def test_binary_node_build_switch():
+    """The A/B alternative of the wavefront walk (WF_WIDE4=0: binary inner nodes, tests/emul/libgi_emul_bin2.so) passes the same
+    traversal parity tests; run in a child process because the emulator library is chosen at import."""
+    import subprocess
+    import sys
+    env = dict(os.environ, GI_EMUL_VARIANT="bin2")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_emul_parity.py"), "-x", "-q", "-p", "no:cacheprovider",
+                        "-k", "trace_parity or retopologised or exact_ties or conservative"], cwd=root, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
