@@ -315,7 +315,9 @@ GI_HD bool traceReference(const DScene& s, F3 o, F3 d, float& rayLength, int& hi
 // result when two candidate triangles have (nearly) the same distance; those rays are detected
 // (second-closest hit inside a relative+absolute window of the closest, or a stack overflow) and
 // re-traced with traceReference().  DESIGN.md "Why the fast traversal is exact" has the argument.
+#ifndef GI_STACK_SIZE
 #define GI_STACK_SIZE 48
+#endif
 #define GI_AMBIGUITY_REL 1.0e-4f
 
 struct StackEntry { int node; float first; };
