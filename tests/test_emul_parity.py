@@ -478,3 +478,18 @@ def test_binary_node_build_switch():
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_emul_parity.py"), "-x", "-q", "-p", "no:cacheprovider",
                         "-k", "trace_parity or retopologised or exact_ties or conservative"], cwd=root, env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("ntri", [2, 3, 4, 5, 7, 9])
+def test_small_trees_all_layouts(g, orc, alt_topology, scenes, ntri):
+    """1 .. 5 leaves: wide nodes with two or three children and unused slots, single-leaf scenes without any inner node; on the
+    reference's topology and on the two alternative ones."""
+    emul = alt_topology
+    sc = scenes.make_random_triangles(ntri, seed=ntri, build_method="sah")
+    rays = make_ray_batch(g, sc, 4000, 11)
+    ref = orc.trace_batch(sc.desc, rays)
+    for kind in (emul.TOPOLOGY_REFERENCE, emul.TOPOLOGY_MEDIAN, emul.TOPOLOGY_RANDOM):
+        emul.set_topology(kind, seed=2)
+        for mode in (FAST, LANE):
+            hits, cnt = emul.trace(sc.desc, rays, mode)
+            assert_hits_equal(hits, ref, "%d triangles topology %d mode %d" % (ntri, kind, mode))

@@ -337,3 +337,19 @@ def test_upload_topology_is_exact(g, orc, scenes, box1, box1_coincident, tmp_pat
         assert rs.device.scene_topology()[0] == topo
         rs.close()
     assert np.array_equal(imgs[0].view(np.uint32), imgs[1].view(np.uint32)), "PT images differ between the two topologies"
+
+
+@pytest.mark.parametrize("ntri", [2, 3, 4, 5, 7, 9, 33])
+def test_upload_topology_small_scenes(g, orc, scenes, ntri):
+    """1 .. 17 leaves through the device re-clustering: single-leaf scenes (nothing to cluster), one merge, wide nodes with unused slots."""
+    sc = scenes.make_random_triangles(ntri, seed=ntri, build_method="sah")
+    rays = make_ray_batch(g, sc, 50000, 11)
+    ref = orc.trace_batch(sc.desc, rays)
+    for topo in (g.GI_TOPOLOGY_PLOC, g.GI_TOPOLOGY_REFERENCE):
+        dev = g.Device(0)
+        dev.set_option(g.GI_OPT_UPLOAD_TOPOLOGY, topo)
+        dev.upload_scene(sc)
+        nleaves = sc.info.num_leaf_triangles // 2
+        assert dev.scene_topology()[0] == (topo if nleaves >= 2 else g.GI_TOPOLOGY_REFERENCE)
+        assert_hits_equal(dev.trace(rays), ref, "%d triangles topology %d" % (ntri, topo))
+        dev.close()
