@@ -52,6 +52,9 @@ struct WfCounters
 #ifndef WF_WIDE4
 #define WF_WIDE4 1         // 4-wide inner nodes (gi_layout.h: emitWide4): 64-byte records, two 256-bit loads, up to three pushes per step.
 #endif                     // B200 A/B against the binary nodes (0), ms per iteration: C2 PT 1.810 -> 1.765, C3 BPT 8.82 -> 8.38, C4 LPT 4K 8.06 -> 7.32, C5 PT 4K 17.77 -> 15.42
+#ifndef WF_SORT_EXCHANGES
+#define WF_SORT_EXCHANGES 5 // 4-wide step: 5 = children fully sorted by entry distance, 3 = nearest exact, the pushed ones roughly ordered
+#endif
 #ifndef WF_CACHE_INV
 #define WF_CACHE_INV 1     // 1/d kept in the lane state for the leaf gate instead of three IEEE divisions per leaf step (B200: 1.712 -> 1.692 ms)
 #endif
@@ -325,6 +328,7 @@ GI_HD void wfInnerStep(WfLane& L, const DScene& s, const STK& stack, CNT& cnt)
 	int c0 = int(b.v[4]), c1 = int(b.v[5]), c2 = int(b.v[6]), c3 = int(b.v[7]);
 	// sorting network (0,1)(2,3)(0,2)(1,3)(1,2): ascending entry distance, rejected children (inf) last
 #define WF_CSWAP(fa, ca, fb, cb) { if (fb < fa) { const float tf = fa; fa = fb; fb = tf; const int tc = ca; ca = cb; cb = tc; } }
+#if WF_SORT_EXCHANGES >= 5
 	WF_CSWAP(f0, c0, f1, c1) WF_CSWAP(f2, c2, f3v, c3) WF_CSWAP(f0, c0, f2, c2) WF_CSWAP(f1, c1, f3v, c3) WF_CSWAP(f1, c1, f2, c2)
 #undef WF_CSWAP
 	if (f0 < GI_INF)
@@ -335,6 +339,20 @@ GI_HD void wfInnerStep(WfLane& L, const DScene& s, const STK& stack, CNT& cnt)
 		L.node = c0;
 	}
 	else wfPop(L, stack);
+#else
+	// three exchanges: the nearest child is exact (slot 0), slot 2 holds the loser of the final and is pushed last (popped first);
+	// the order of the stack is a heuristic only -- every entry carries its own entry distance for the cull at pop time
+	WF_CSWAP(f0, c0, f1, c1) WF_CSWAP(f2, c2, f3v, c3) WF_CSWAP(f0, c0, f2, c2)
+#undef WF_CSWAP
+	if (f0 < GI_INF)
+	{
+		if (f3v < GI_INF) wfPush(L, stack, c3, f3v);
+		if (f1 < GI_INF) wfPush(L, stack, c1, f1);
+		if (f2 < GI_INF) wfPush(L, stack, c2, f2);
+		L.node = c0;
+	}
+	else wfPop(L, stack);
+#endif
 	wfStash(L, stack);
 }
 #else
