@@ -52,6 +52,13 @@ struct WfCounters
 #ifndef WF_WIDE4
 #define WF_WIDE4 1         // 4-wide inner nodes (gi_layout.h: emitWide4): 64-byte records, two 256-bit loads, up to three pushes per step.
 #endif                     // B200 A/B against the binary nodes (0), ms per iteration: C2 PT 1.810 -> 1.765, C3 BPT 8.82 -> 8.38, C4 LPT 4K 8.06 -> 7.32, C5 PT 4K 17.77 -> 15.42
+#ifndef WF_FLOAT_PLANES
+#define WF_FLOAT_PLANES 0  // 4-wide nodes with the child boxes as FLOATS, grouped per axis (min x4 | max x4): 128-byte records, the near / far planes
+#endif                     // are picked by the load address (sign of the direction), no decode and no select in the slab test (needs WF_WIDE4)
+#if WF_FLOAT_PLANES && !WF_WIDE4
+#error "WF_FLOAT_PLANES needs WF_WIDE4"
+#endif
+#define WF_NODE_WORDS (WF_FLOAT_PLANES ? 32 : (WF_WIDE4 ? 16 : 8)) // words per record of DScene::qNodes
 #ifndef WF_SORT_EXCHANGES
 #define WF_SORT_EXCHANGES 5 // 4-wide step: 5 = children fully sorted by entry distance, 3 = nearest exact, the pushed ones roughly ordered
 #endif
@@ -70,12 +77,20 @@ struct WfLane
 #if WF_CACHE_INV
 	F3 inv;          // invDir(d), the same three IEEE quotients the leaf gate would recompute
 #endif
+#if WF_FLOAT_PLANES
+	// conservative inner-node test on float planes: distance of plane p along axis k = fma(p, cellInv.k, biasNear.k / biasFar.k)
+	F3 cellInv;      // 1/d
+	F3 biasNear;     // -o * (1/d) -/+ error bound
+	F3 biasFar;
+	uint32_t offNear[3]; // word offset of the four near planes of axis k inside a node record (8k, or 8k + 4 for a negative direction); far = ^ 4
+#else
 	// conservative inner-node test on the 16-bit grid (wfSlabTest): distance of grid plane q along axis k
 	//   near planes  fma(2^23 + q, cellInv.k, biasNear.k)      far planes  fma(2^23 + q, cellInv.k, biasFar.k)
 	F3 cellInv;      // cell size * (1/d)
 	F3 biasNear;     // (gridLo - o) * (1/d) - 2^23 * cellInv -/+ error bound
 	F3 biasFar;
 	uint32_t selNear[3], selFar[3]; // byte-permute selectors: which 16-bit half of a node word is the near / far plane (sign of d)
+#endif
 	float tMaxInit, best, second;
 	float limit;     // culling limit for box entry distances
 	int hitLeaf;
@@ -251,6 +266,35 @@ GI_HD float wfMin3(float a, float b, float c)
 #endif
 }
 
+#if WF_FLOAT_PLANES
+// Float planes.  Reference (exact zone): t_ref = fl(inv * fl(p - o)), |t_ref - T| <= 2.01u |T| with T = (p - o) * inv and |T| <= (|p| + |o|) |inv|.
+// Here: c = fl(-o * inv), c' = fl(c -/+ E), t = fl(p * inv + c') (one FMA):
+//   |c - (-o inv)| <= u |o inv|,   |c' - (c -/+ E)| <= u (|c| + E),   |t - (p inv + c')| <= u (|p inv| + |c| + E)
+//   => |t +/- E - T| <= u (3.01 |o| + 1.01 |p|) |inv| + 2.01 u E, and with the reference's own rounding the planes are bracketed as soon as
+//   E (1 - 2.01u) >= u |inv| (5.02 |o| + 3.02 |p|).   E := 8u |inv| (|o| + P), P = max |coordinate| of the root box >= |p|, satisfies it.
+// Hence near.k <= tmin.k and far.k >= tmax.k of IntersectBox for every box inside the root box, and
+//   (first <= last && first <= limit)  ==>  the conservative test accepts.
+// Zero / denormal direction components and products near overflow are outside the domain (answered by the reference walk).
+GI_HD bool wfSlabSetup(WfLane& L, const DScene& s, F3 o, F3 inv)
+{
+	const float u = 5.9604644775390625e-08f; // 2^-24
+	const float iv[3] = {inv.x, inv.y, inv.z}, ov[3] = {o.x, o.y, o.z};
+	float bn[3], bf[3], m = 0.0f;
+	for (int k = 0; k < 3; ++k)
+	{
+		const float c = -(ov[k] * iv[k]);
+		const float reach = (fabsf(ov[k]) + s.gridAbsMax[k]) * fabsf(iv[k]);
+		const float E = (8.0f * u) * reach + 1.0e-37f;
+		bn[k] = c - E; bf[k] = c + E;
+		m = fmaxf(m, reach);
+		L.offNear[k] = uint32_t(8 * k) + (iv[k] < 0.0f ? 4u : 0u);
+	}
+	L.cellInv = inv;
+	L.biasNear = f3(bn[0], bn[1], bn[2]);
+	L.biasFar = f3(bf[0], bf[1], bf[2]);
+	return m < 1.0e30f; // false for NaN / inf as well
+}
+#else
 // Per-ray constants of the conservative test.  Returns false when the ray is outside the domain of the error bound.
 GI_HD bool wfSlabSetup(WfLane& L, const DScene& s, F3 o, F3 inv)
 {
@@ -274,6 +318,8 @@ GI_HD bool wfSlabSetup(WfLane& L, const DScene& s, F3 o, F3 inv)
 	return m < 1.0e30f; // false for NaN / inf as well
 }
 
+#endif
+
 template <class CNT>
 GI_HD void wfBegin(WfLane& L, const DScene& s, F3 o, F3 d, float tMax, bool isAny, uint32_t index, CNT& cnt)
 {
@@ -296,6 +342,7 @@ GI_HD void wfBegin(WfLane& L, const DScene& s, F3 o, F3 d, float tMax, bool isAn
 	if (!inDomain && L.node != WF_NODE_DONE) { L.flags |= WFL_OVERFLOW; L.node = WF_NODE_DONE; }
 }
 
+#if !WF_FLOAT_PLANES
 // Conservative accept test of one child box (three words: x, y, z; min plane | max plane << 16): never rejects a box the
 // exact-zone test (first <= last && first <= limit) accepts.  nearLow is a lower bound of the exact-zone entry distance.
 GI_HD bool wfSlabTest(const WfLane& L, uint32_t wx, uint32_t wy, uint32_t wz, float& nearLow)
@@ -309,8 +356,54 @@ GI_HD bool wfSlabTest(const WfLane& L, uint32_t wx, uint32_t wy, uint32_t wz, fl
 	nearLow = fmaxf(wfMax3(nx, ny, nz), 0.0f);
 	return nearLow <= fminf(wfMin3(fx, fy, fz), L.limit);
 }
+#endif
 
-#if WF_WIDE4
+#if WF_FLOAT_PLANES
+// conservative test of the four children at once is in wfInnerStep; this is the same test for ONE child of the record at `node` (test hook)
+GI_HD bool wfSlabTestChild(const WfLane& L, const uint32_t* node, int child, float& nearLow)
+{
+	const float* f = reinterpret_cast<const float*>(node);
+	const float nx = wfFma(f[L.offNear[0] + child], L.cellInv.x, L.biasNear.x), fx = wfFma(f[(L.offNear[0] ^ 4u) + child], L.cellInv.x, L.biasFar.x);
+	const float ny = wfFma(f[L.offNear[1] + child], L.cellInv.y, L.biasNear.y), fy = wfFma(f[(L.offNear[1] ^ 4u) + child], L.cellInv.y, L.biasFar.y);
+	const float nz = wfFma(f[L.offNear[2] + child], L.cellInv.z, L.biasNear.z), fz = wfFma(f[(L.offNear[2] ^ 4u) + child], L.cellInv.z, L.biasFar.z);
+	nearLow = fmaxf(wfMax3(nx, ny, nz), 0.0f);
+	return nearLow <= fminf(wfMin3(fx, fy, fz), L.limit);
+}
+
+// 4-wide inner node with float planes: six 128-bit loads (near / far planes of the four children per axis, the address picks the side) + the links
+template <class STK, class CNT>
+GI_HD void wfInnerStep(WfLane& L, const DScene& s, const STK& stack, CNT& cnt)
+{
+	const uint32_t* nb = s.qNodes + 32 * size_t(L.node);
+	const F4 nx = ld4(reinterpret_cast<const F4*>(nb + L.offNear[0])), fx = ld4(reinterpret_cast<const F4*>(nb + (L.offNear[0] ^ 4u)));
+	const F4 ny = ld4(reinterpret_cast<const F4*>(nb + L.offNear[1])), fy = ld4(reinterpret_cast<const F4*>(nb + (L.offNear[1] ^ 4u)));
+	const F4 nz = ld4(reinterpret_cast<const F4*>(nb + L.offNear[2])), fz = ld4(reinterpret_cast<const F4*>(nb + (L.offNear[2] ^ 4u)));
+	const F4 lk = ld4(reinterpret_cast<const F4*>(nb + 24));
+	cnt.template add<WFC_NODES>(4u);
+#define WF_CHILD(m, out) { \
+		const float nn = fmaxf(wfMax3(wfFma(nx.m, L.cellInv.x, L.biasNear.x), wfFma(ny.m, L.cellInv.y, L.biasNear.y), wfFma(nz.m, L.cellInv.z, L.biasNear.z)), 0.0f); \
+		const float ff = fminf(wfMin3(wfFma(fx.m, L.cellInv.x, L.biasFar.x), wfFma(fy.m, L.cellInv.y, L.biasFar.y), wfFma(fz.m, L.cellInv.z, L.biasFar.z)), L.limit); \
+		out = nn <= ff ? nn : GI_INF; }
+	float f0, f1, f2, f3v;
+	WF_CHILD(x, f0) WF_CHILD(y, f1) WF_CHILD(z, f2) WF_CHILD(w, f3v)
+#undef WF_CHILD
+	int c0 = f2i(lk.x), c1 = f2i(lk.y), c2 = f2i(lk.z), c3 = f2i(lk.w);
+#define WF_CSWAP(fa, ca, fb, cb) { if (fb < fa) { const float tf = fa; fa = fb; fb = tf; const int tc = ca; ca = cb; cb = tc; } }
+	WF_CSWAP(f0, c0, f1, c1) WF_CSWAP(f2, c2, f3v, c3) WF_CSWAP(f0, c0, f2, c2) WF_CSWAP(f1, c1, f3v, c3) WF_CSWAP(f1, c1, f2, c2)
+#undef WF_CSWAP
+	if (f0 < GI_INF)
+	{
+		if (f3v < GI_INF) wfPush(L, stack, c3, f3v);
+		if (f2 < GI_INF) wfPush(L, stack, c2, f2);
+		if (f1 < GI_INF) wfPush(L, stack, c1, f1);
+		L.node = c0;
+	}
+	else wfPop(L, stack);
+	wfStash(L, stack);
+}
+#elif WF_WIDE4
+GI_HD bool wfSlabTestChild(const WfLane& L, const uint32_t* node, int child, float& nearLow) { return wfSlabTest(L, node[3 * child], node[3 * child + 1], node[3 * child + 2], nearLow); }
+
 // 4-wide inner node: words 0..11 = child k, axis a at 3k + a (min plane | max plane << 16), words 12..15 = child links (wide index >= 0,
 // leaf = ~leafIndex).  An unused slot carries the empty box (min 65535, max 0 on every axis), which the conservative test rejects for
 // every ray inside its domain.  The accepted children are visited nearest first; the others go to the stack, farthest first.
@@ -356,6 +449,8 @@ GI_HD void wfInnerStep(WfLane& L, const DScene& s, const STK& stack, CNT& cnt)
 	wfStash(L, stack);
 }
 #else
+GI_HD bool wfSlabTestChild(const WfLane& L, const uint32_t* node, int child, float& nearLow) { return wfSlabTest(L, node[3 * child], node[3 * child + 1], node[3 * child + 2], nearLow); }
+
 template <class STK, class CNT>
 GI_HD void wfInnerStep(WfLane& L, const DScene& s, const STK& stack, CNT& cnt)
 {

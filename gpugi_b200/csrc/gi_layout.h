@@ -27,7 +27,7 @@ struct HostLayout
 	std::vector<DMaterial> materials;
 	std::vector<DTexel> texels;             // 4 per material; .pixels still points at HOST memory here
 	std::vector<int32_t> materialTexture;   // 4 per material: index into GiSceneDesc::textures
-	struct ChildBox { uint32_t word; float mn[3], mx[3]; }; // test hook: where in qNodes an encoded child box starts (3 words) + the exact box
+	struct ChildBox { uint32_t word; uint32_t child; float mn[3], mx[3]; }; // test hook: first word of the node record in qNodes, child slot, the exact box
 	bool keepChildBoxes = false;            // set by the test emulator before the build
 	std::vector<ChildBox> childBoxes;
 	bool binary = false;                    // strictly binary tree => fastNodes usable
@@ -49,6 +49,7 @@ struct FastEmitter
 			float sc = float((double(hi) - double(lo)) / 65535.0 * (1.0 + 1.0e-6));
 			if (!(sc > 1.0e-30f)) sc = 1.0e-30f;
 			L.scene.gridLo[k] = lo; L.scene.gridScale[k] = sc;
+			L.scene.gridAbsMax[k] = std::fmax(std::fabs(lo), std::fabs(hi));
 			gridLo[k] = double(lo); gridScale[k] = double(sc);
 		}
 	}
@@ -86,10 +87,10 @@ struct FastEmitter
 		}
 		return covered;
 	}
-	static void noteChildBox(HostLayout& L, size_t word, const float bmin[3], const float bmax[3])
+	static void noteChildBox(HostLayout& L, size_t word, uint32_t child, const float bmin[3], const float bmax[3])
 	{
 		if (!L.keepChildBoxes) return;
-		HostLayout::ChildBox cb; cb.word = uint32_t(word);
+		HostLayout::ChildBox cb; cb.word = uint32_t(word); cb.child = child;
 		for (int k = 0; k < 3; ++k) { cb.mn[k] = bmin[k]; cb.mx[k] = bmax[k]; }
 		L.childBoxes.push_back(cb);
 	}
@@ -118,7 +119,7 @@ struct FastEmitter
 		uint32_t* qn = &L.qNodes[size_t(index) * 8];
 		for (int k = 0; k < 3; ++k) { qn[k] = v[k] | (v[3 + k] << 16); qn[3 + k] = v[6 + k] | (v[9 + k] << 16); }
 		qn[6] = uint32_t(c0); qn[7] = uint32_t(c1);
-		noteChildBox(L, size_t(index) * 8, amin, amax); noteChildBox(L, size_t(index) * 8 + 3, bmin, bmax);
+		noteChildBox(L, size_t(index) * 8, 0u, amin, amax); noteChildBox(L, size_t(index) * 8, 1u, bmin, bmax);
 		return covered;
 	}
 };
@@ -161,7 +162,7 @@ inline bool emitWide4(const GiSceneDesc* d, HostLayout& L, const LeafTree& t, st
 	while (!stack.empty())
 	{
 		const Item it = stack.back(); stack.pop_back();
-		const uint32_t index = uint32_t(q.size() / 16);
+		const uint32_t index = uint32_t(q.size() / WF_NODE_WORDS);
 		if (it.parentWord != 0xffffffffu) q[it.parentWord] = index;
 		uint32_t kids[4] = {t.left[it.node], t.right[it.node], 0, 0};
 		int n = 2;
@@ -177,6 +178,34 @@ inline bool emitWide4(const GiSceneDesc* d, HostLayout& L, const LeafTree& t, st
 			++n;
 		}
 		const size_t base = q.size();
+#if WF_FLOAT_PLANES
+		// 32 words: axis a at 8a: (min of the four children | max of the four children) as floats, links at 24..27; an unused slot
+		// carries min = +3e38, max = -3e38, which no ray inside the domain of the error bound accepts
+		q.resize(base + 32, 0u);
+		for (int k = 0; k < 4; ++k)
+		{
+			float mnv[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mxv[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+			uint32_t link = uint32_t(WF_NODE_DONE);
+			if (k < n)
+			{
+				const float* mn = &t.boxMin[size_t(kids[k]) * 3]; const float* mx = &t.boxMax[size_t(kids[k]) * 3];
+				for (int a = 0; a < 3; ++a)
+				{
+					mnv[a] = mn[a]; mxv[a] = mx[a];
+					if (!(std::fabs(mn[a]) <= gridOnly.scene.gridAbsMax[a] && std::fabs(mx[a]) <= gridOnly.scene.gridAbsMax[a])) { why = "box outside the root box"; return false; }
+				}
+				FastEmitter::noteChildBox(L, base, uint32_t(k), mn, mx);
+				if (kids[k] < nl) link = uint32_t(~int(t.leafOf[kids[k]]));
+			}
+			for (int a = 0; a < 3; ++a)
+			{
+				std::memcpy(&q[base + 8 * size_t(a) + size_t(k)], &mnv[a], 4);
+				std::memcpy(&q[base + 8 * size_t(a) + 4 + size_t(k)], &mxv[a], 4);
+			}
+			q[base + 24 + size_t(k)] = link;
+		}
+		const size_t linkBase = base + 24;
+#else
 		q.resize(base + 16, 0u);
 		for (int k = 0; k < 4; ++k)
 		{
@@ -186,14 +215,16 @@ inline bool emitWide4(const GiSceneDesc* d, HostLayout& L, const LeafTree& t, st
 			{
 				const float* mn = &t.boxMin[size_t(kids[k]) * 3]; const float* mx = &t.boxMax[size_t(kids[k]) * 3];
 				if (!em.quantBox(mn, mx, w)) { why = "quantisation grid does not cover a box"; return false; }
-				FastEmitter::noteChildBox(L, base + 3 * size_t(k), mn, mx);
+				FastEmitter::noteChildBox(L, base, uint32_t(k), mn, mx);
 				if (kids[k] < nl) link = uint32_t(~int(t.leafOf[kids[k]]));
 			}
 			q[base + 3 * size_t(k)] = w[0]; q[base + 3 * size_t(k) + 1] = w[1]; q[base + 3 * size_t(k) + 2] = w[2];
 			q[base + 12 + size_t(k)] = link;
 		}
+		const size_t linkBase = base + 12;
+#endif
 		for (int k = n - 1; k >= 0; --k) // reverse push: the first child gets the next preorder index
-			if (kids[k] >= nl) stack.push_back({kids[k], uint32_t(base + 12 + size_t(k))});
+			if (kids[k] >= nl) stack.push_back({kids[k], uint32_t(linkBase + size_t(k))});
 	}
 	L.qNodes.swap(q);
 	return true;

@@ -461,10 +461,9 @@ EM_API int em_slab_check(const GiSceneDesc* desc, const GiRay* rays, uint32_t n,
 		for (size_t bi = r % stride; bi < boxes.size(); bi += stride)
 		{
 			const HostLayout::ChildBox& cb = boxes[bi];
-			const uint32_t* q = e.s.qNodes + cb.word;
 			float first, last, nearLow;
 			const bool exact = intersectBox(o, inv, cb.mn[0], cb.mn[1], cb.mn[2], cb.mx[0], cb.mx[1], cb.mx[2], first, last) && first <= L.limit;
-			const bool cons = wfSlabTest(L, q[0], q[1], q[2], nearLow);
+			const bool cons = wfSlabTestChild(L, e.s.qNodes + cb.word, int(cb.child), nearLow);
 			++out[0];
 			if (exact) ++out[1];
 			if (cons) ++out[2];
