@@ -1,9 +1,13 @@
 // gi_layout.h -- host-side half of gi_upload_scene(): validates a GiSceneDesc (the reference's
 // Scene::SanityCheck) and re-lays the bim hierarchy out for the device (DESIGN.md "HBM layout"):
 //   refNodes   the 32-byte TreeNode<Box> array as is (reference-order walk / exact fallback)
-//   fastNodes  one 64-byte record per INNER node carrying both child boxes + child links
-//   leafPos    vertex positions gathered per leaf triangle slot (3 x 16 B), validity flag in .w
+//   fastNodes  one 64-byte record per binary INNER node carrying both child boxes + child links (one-thread-per-path kernels)
+//   qNodes     the wavefront walk's records: 4-wide nodes (emitWide4) with the child boxes on a 16-bit grid over the root box;
+//              build switches: binary records (WF_WIDE4=0), float planes (WF_FLOAT_PLANES)
+//   leafPos    vertex positions gathered per leaf triangle slot (3 x 16 B) + the leaf node's own box in the .w components
 //   materials  Scene::Material with 1x1 constant textures folded into the record
+// fastNodes / qNodes stand on the reference's topology (buildHostLayout) or on any other binary tree over the reference's leaves
+// (applyLeafTree: gi_upload_scene hands in the tree the device clustered, GI_OPT_UPLOAD_TOPOLOGY).
 // Pure host C++ (no CUDA calls); gi_device.cu uploads the vectors and patches in texture objects.
 #pragma once
 
