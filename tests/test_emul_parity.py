@@ -468,15 +468,17 @@ def test_quantised_child_boxes_are_conservative(g, emul, scenes, box1):
         emul.set_topology(emul.TOPOLOGY_REFERENCE)
 
 
-def test_binary_node_build_switch():
-    """The A/B alternative of the wavefront walk (WF_WIDE4=0: binary inner nodes, tests/emul/libgi_emul_bin2.so) passes the same
-    traversal parity tests; run in a child process because the emulator library is chosen at import."""
+@pytest.mark.parametrize("variant", ["bin2", "sort3", "fplanes"])
+def test_build_switches_of_the_wavefront_walk(variant):
+    """The measured-and-switched-off alternatives of the wavefront walk stay exact: binary inner nodes (WF_WIDE4=0), three sort exchanges
+    (WF_SORT_EXCHANGES=3), float planes (WF_FLOAT_PLANES=1) -- tests/emul/libgi_emul_<variant>.so passes the same traversal parity tests;
+    run in a child process because the emulator library is chosen at import."""
     import subprocess
     import sys
-    env = dict(os.environ, GI_EMUL_VARIANT="bin2")
+    env = dict(os.environ, GI_EMUL_VARIANT=variant)
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_emul_parity.py"), "-x", "-q", "-p", "no:cacheprovider",
-                        "-k", "trace_parity or retopologised or exact_ties or conservative"], cwd=root, env=env, capture_output=True, text=True, timeout=900)
+                        "-k", "trace_parity or retopologised or exact_ties or conservative or small_trees"], cwd=root, env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
