@@ -174,6 +174,9 @@ struct WfStackShared
 #ifndef WF_PREFETCH
 #define WF_PREFETCH 0
 #endif
+#ifndef WF_SHADE_HOIST
+#define WF_SHADE_HOIST 0  // k_wf_shade_pt: leaf record + triangle requested before the path state
+#endif
 #ifndef WF_BATCH_RETIRE
 #define WF_BATCH_RETIRE 1 // finished lanes are retired together when the refill is due (B200: 1.699 -> 1.680 ms per PT iteration)
 #endif
@@ -488,6 +491,18 @@ GI_D void wfShadePT(const WfFrame& w, uint32_t slot, bool valid, unsigned* cnt)
 		origin = f3(r0.x, r0.y, r0.z); dir = f3(r1.x, r1.y, r1.z);
 		F3 color = f3(0.0f), pathThroughput = f3(1.0f);
 		uint32_t seed;
+#if WF_SHADE_HOIST
+		// the hit's leaf record and triangle are requested BEFORE the path state is read: both gathers depend on the queue entry only,
+		// so their latencies overlap instead of adding up (the compiler does not hoist loads across the branches below)
+		const int leafTriEarly = f2i(hrec.y);
+		F3 hp0 = f3(0.0f), hp1 = f3(0.0f), hp2 = f3(0.0f); int hvalid = 0;
+		I4 htri; htri.x = htri.y = htri.z = htri.w = 0;
+		if (leafTriEarly >= 0)
+		{
+			loadLeafTri(f.scene, leafTriEarly, hp0, hp1, hp2, hvalid);
+			htri = ld4(f.scene.leafTris + leafTriEarly);
+		}
+#endif
 		if (bounce == 0)
 		{
 			seed = initRandomSeed(f.frameSeed, id);
@@ -516,11 +531,16 @@ GI_D void wfShadePT(const WfFrame& w, uint32_t slot, bool valid, unsigned* cnt)
 			color = color + pathThroughput * environmentRadiance(f, dir);
 		else
 		{
+#if WF_SHADE_HOIST
+			const F3 p0 = hp0, p1 = hp1, p2 = hp2;
+			const I4 tri = htri;
+#else
 			F3 p0, p1, p2; int tv;
 			loadLeafTri(f.scene, leafTri, p0, p1, p2, tv);
+			const I4 tri = ld4(f.scene.leafTris + leafTri);
+#endif
 			float tt; F3 bary, gn;
 			intersectTriangle(origin, dir, p0, p1, p2, tt, bary, gn);
-			const I4 tri = ld4(f.scene.leafTris + leafTri);
 			origin = origin + tHit * dir;
 			F3 hitNormal; F2 tc;
 			getTriangleHitInfo(f.scene, tri, bary, hitNormal, tc);
