@@ -1118,11 +1118,16 @@ static int buildLeafTreeOnDevice(GiContext* c, const GiSceneDesc* d, const HostL
 			step(cudaStreamSynchronize(st));
 			return next;
 		};
+		// A pass normally merges 35-45 % of the clusters.  Many coincident boxes (duplicated geometry) can leave a single mutual pair per pass;
+		// a pass that removed less than 1/16 of the list is therefore followed by a forced pairing of neighbours, which halves the list.
+		bool forceNext = false;
 		while (n > 1u && e == cudaSuccess)
 		{
-			uint32_t next = pass(false);
+			uint32_t next = pass(forceNext);
+			forceNext = false;
 			if (next >= n && e == cudaSuccess) next = pass(true);
 			if (next >= n) { if (e == cudaSuccess) e = cudaErrorUnknown; break; }
+			if (uint64_t(n - next) * 16u < uint64_t(n)) forceNext = true;
 			std::swap(clA, clB);
 			n = next;
 		}
@@ -1853,11 +1858,14 @@ int gi_build_hierarchy(GiContext* c, const float* positions, uint32_t num_vertic
 				step(cudaStreamSynchronize(st));
 				return next;
 			};
+			bool forceNext = false; // (see buildLeafTreeOnDevice: coincident boxes must not cost one pass per cluster)
 			while (n > 1u && e == cudaSuccess)
 			{
-				uint32_t next = pass(false);
+				uint32_t next = pass(forceNext);
+				forceNext = false;
 				if (next >= n && e == cudaSuccess) next = pass(true); // (never taken with the tie rule of k_ploc_nearest)
 				if (next >= n) { if (e == cudaSuccess) e = cudaErrorUnknown; break; }
+				if (uint64_t(n - next) * 16u < uint64_t(n)) forceNext = true;
 				std::swap(clA, clB);
 				n = next;
 			}

@@ -353,3 +353,29 @@ def test_upload_topology_small_scenes(g, orc, scenes, ntri):
         assert dev.scene_topology()[0] == (topo if nleaves >= 2 else g.GI_TOPOLOGY_REFERENCE)
         assert_hits_equal(dev.trace(rays), ref, "%d triangles topology %d" % (ntri, topo))
         dev.close()
+
+
+def test_upload_topology_coincident_geometry(g, orc, scenes):
+    """4000 copies of the same two triangles: every leaf box is identical, so the clustering finds one mutual pair per pass -- the forced
+    pairing must keep the number of passes logarithmic (the upload finishes at once) and the walk exact (every hit is a 4000-fold tie)."""
+    import time
+    base_pos = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0]], dtype=np.float32)
+    n = 4000
+    pos = np.tile(base_pos, (n, 1))
+    tri = np.concatenate([np.array([[0, 1, 2], [1, 3, 2]], dtype=np.uint32) + 4 * i for i in range(n)])
+    nrm = np.tile(np.array([[0, 0, 1]], dtype=np.float32), (4 * n, 1))
+    uv = np.zeros((4 * n, 2), dtype=np.float32)
+    sc = g.Scene.from_mesh(pos, nrm, uv, tri, np.zeros(len(tri), dtype=np.uint32), {"m": {"albedo": [0.5, 0.5, 0.5]}}, build_method="kd")
+    rng = np.random.RandomState(3)
+    rays = np.zeros(20000, dtype=g.RAY_DTYPE)
+    rays["origin"] = np.concatenate([rng.rand(len(rays), 2) * 1.2 - 0.1, np.full((len(rays), 1), 2.0)], axis=1).astype(np.float32)
+    d = rng.randn(len(rays), 3) * 0.2; d[:, 2] = -1.0
+    rays["direction"] = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    rays["t_max"] = np.float32(g.RAY_MAX)
+    dev = g.Device(0)
+    t0 = time.time()
+    dev.upload_scene(sc)
+    assert time.time() - t0 < 5.0
+    assert dev.scene_topology()[0] == g.GI_TOPOLOGY_PLOC
+    assert_hits_equal(dev.trace(rays), orc.trace_batch(sc.desc, rays), "coincident geometry")
+    dev.close()
