@@ -1119,7 +1119,7 @@ static int buildLeafTreeOnDevice(GiContext* c, const GiSceneDesc* d, const HostL
 			return next;
 		};
 		// A pass normally merges 35-45 % of the clusters.  Many coincident boxes (duplicated geometry) can leave a single mutual pair per pass;
-		// a pass that removed less than 1/16 of the list is therefore followed by a forced pairing of neighbours, which halves the list.
+		// a pass that removed less than 1/16 of a list of more than 1024 clusters is therefore followed by a forced pairing of neighbours, which halves the list.
 		bool forceNext = false;
 		while (n > 1u && e == cudaSuccess)
 		{
@@ -1127,7 +1127,7 @@ static int buildLeafTreeOnDevice(GiContext* c, const GiSceneDesc* d, const HostL
 			forceNext = false;
 			if (next >= n && e == cudaSuccess) next = pass(true);
 			if (next >= n) { if (e == cudaSuccess) e = cudaErrorUnknown; break; }
-			if (uint64_t(n - next) * 16u < uint64_t(n)) forceNext = true;
+			if (n > 1024u && uint64_t(n - next) * 16u < uint64_t(n)) forceNext = true; // (short lists near the root always merge slowly: leave them to the area rule)
 			std::swap(clA, clB);
 			n = next;
 		}
@@ -1865,7 +1865,7 @@ int gi_build_hierarchy(GiContext* c, const float* positions, uint32_t num_vertic
 				forceNext = false;
 				if (next >= n && e == cudaSuccess) next = pass(true); // (never taken with the tie rule of k_ploc_nearest)
 				if (next >= n) { if (e == cudaSuccess) e = cudaErrorUnknown; break; }
-				if (uint64_t(n - next) * 16u < uint64_t(n)) forceNext = true;
+				if (n > 1024u && uint64_t(n - next) * 16u < uint64_t(n)) forceNext = true; // (short lists near the root always merge slowly: leave them to the area rule)
 				std::swap(clA, clB);
 				n = next;
 			}

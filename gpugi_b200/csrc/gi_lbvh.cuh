@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(256) k_ploc_force_pairs(uint32_t n, uint32_t* 
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	const uint32_t partner = i ^ 1u;
-	nearest[i] = partner < n ? partner : i;
+	nearest[i] = partner < n ? partner : 0xffffffffu; // the last cluster of an odd list stays as it is (k_ploc_merge: no partner)
 }
 
 // ---- leaves by mutual nearest neighbours: one clustering pass over the single triangles.  Two Morton-neighbouring triangles share a leaf
