@@ -495,3 +495,43 @@ def test_small_trees_all_layouts(g, orc, alt_topology, scenes, ntri):
         for mode in (FAST, LANE):
             hits, cnt = emul.trace(sc.desc, rays, mode)
             assert_hits_equal(hits, ref, "%d triangles topology %d mode %d" % (ntri, kind, mode))
+
+
+def test_invalid_leaf_trees_are_rejected(g, orc, alt_topology, scenes):
+    """applyLeafTree must refuse anything that is not a binary tree over exactly the reference's leaves (the device clustering is checked, not
+    trusted): a leaf reached twice, a cycle, a leaf list that is not a permutation, an out-of-range link.  The layout then keeps the
+    reference's topology and the walk stays exact."""
+    emul = alt_topology
+    sc = scenes.make_random_triangles(40, seed=4, build_method="sah")
+    nl = sc.info.num_leaf_triangles // 2
+    assert nl >= 8
+    N = 2 * nl - 1
+    rays = make_ray_batch(g, sc, 3000, 5)
+    ref = orc.trace_batch(sc.desc, rays)
+
+    def chain():
+        # a valid (list-like) tree: inner node nl + k joins leaf k + 1 with the subtree so far
+        left = np.zeros(N, np.uint32); right = np.zeros(N, np.uint32)
+        left[nl], right[nl] = 0, 1
+        for k in range(1, nl - 1):
+            left[nl + k], right[nl + k] = nl + k - 1, k + 1
+        return left, right, np.arange(nl, dtype=np.uint32), N - 1
+
+    left, right, leaf_of, root = chain()
+    emul.set_tree(left, right, leaf_of, root)
+    hits, _ = emul.trace(sc.desc, rays, LANE)
+    assert emul.topology_applied()
+    assert_hits_equal(hits, ref, "valid chain")
+
+    broken = []
+    l, r, lo, rt = chain(); r[nl + 3] = 0; broken.append(("leaf reached twice", l, r, lo, rt))
+    l, r, lo, rt = chain(); l[nl + 2] = nl + 5; broken.append(("cycle", l, r, lo, rt))
+    l, r, lo, rt = chain(); lo[1] = lo[0]; broken.append(("not a permutation", l, r, lo, rt))
+    l, r, lo, rt = chain(); r[nl + 1] = N + 7; broken.append(("link out of range", l, r, lo, rt))
+    l, r, lo, rt = chain(); broken.append(("root is a leaf", l, r, lo, 0))
+    for name, l, r, lo, rt in broken:
+        emul.set_tree(l, r, lo, rt)
+        hits, cnt = emul.trace(sc.desc, rays, LANE)
+        assert not emul.topology_applied(), name
+        assert cnt["fast_valid"] == 1
+        assert_hits_equal(hits, ref, name)
