@@ -377,9 +377,12 @@ def run_ours(args, rank, world, local_rank):
     k_ms = trace_ms / max(trace_launches, 1)
     achieved = bytes_per_launch / (k_ms * 1e-3) / 1e9
     step_ms = sum(v[0] for v in ktimes.values()) / K
-    traffic = None
+    traffic = l2_bytes = l2_gbs = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_wf_trace_dram_bytes_per_launch")
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tj.get("k_wf_trace_dram_bytes_per_launch")
+        l2_bytes = tj.get("k_wf_trace_l2_bytes_per_launch") or None
+        l2_gbs = tj.get("k_wf_trace_l2_gbs_in_capture")
     except Exception:
         pass
     scene_mb = (info.num_nodes * 32 + (info.num_nodes // 2) * 64 + info.num_leaf_triangles * 64 + info.num_vertices * 28 + 25 * args.texture_size ** 2 * 8
@@ -405,6 +408,7 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": int(launches),
         "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"]},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "l2_traffic": l2_bytes, "l2_gbs_in_capture": l2_gbs,  # L2 bytes and L2 GB/s of the captured steady-state launch (ncu; SURVEY 8d: the scene is L2-resident)
                      "kernel": "k_wf_trace", "kernel_ms": k_ms, "launches_timed": trace_launches, "algorithmic_bytes_per_launch": bytes_per_launch,
                      "peak_source": peak_src, "share_of_step": trace_ms / K / step_ms,
                      "kernel_ms_per_step": {k: v[0] / K for k, v in ktimes.items() if v[1]},

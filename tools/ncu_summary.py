@@ -15,7 +15,7 @@ WANT = [
     "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
     "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
     "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "l1tex__throughput.avg.pct_of_peak_sustained_active",
-    "lts__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum",
+    "lts__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum", "lts__t_sectors.sum",
     "sass__inst_executed_local_loads", "sass__inst_executed_local_stores",
     "smsp__average_warp_latency_per_inst_issued.ratio",
 ]

@@ -55,12 +55,21 @@ def main():
     for l in open(md):
         if l.startswith("## "):
             kernel = "trace" if "k_wf_trace" in l else "shade"
+        if l.startswith("| gpu__time_duration.sum |"):
+            p = [x.strip() for x in l.strip().strip("|").split("|")]
+            vals[kernel + "_ms"] = float(p[1]) * {"ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3}.get(p[2], 1.0)
+        if l.startswith("| lts__t_sectors.sum |"):
+            p = [x.strip() for x in l.strip().strip("|").split("|")]
+            vals[kernel + "_l2"] = float(p[1]) * 32.0  # 32-byte sectors through the L2 tag stage
         if l.startswith("| dram__bytes_"):
             p = [x.strip() for x in l.strip().strip("|").split("|")]
             scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[p[2]]
             vals[kernel] = vals.get(kernel, 0.0) + float(p[1]) * scale
     json.dump({"k_wf_trace_dram_bytes_per_launch": int(vals["trace"]), "k_wf_shade_pt_dram_bytes_per_launch": int(vals["shade"]),
-               "source": "profiles/r01_ncu_wavefront_%s.md (ncu --set full, steady-state wave of a 24-iteration batch: dram__bytes_read.sum + dram__bytes_write.sum)" % tag},
+               "k_wf_trace_l2_bytes_per_launch": int(vals.get("trace_l2", 0)), "k_wf_shade_pt_l2_bytes_per_launch": int(vals.get("shade_l2", 0)),
+               "k_wf_trace_ncu_launch_ms": vals.get("trace_ms"), "k_wf_shade_pt_ncu_launch_ms": vals.get("shade_ms"),
+               "k_wf_trace_l2_gbs_in_capture": (vals.get("trace_l2", 0) / (vals["trace_ms"] * 1e-3) / 1e9) if vals.get("trace_ms") else None,
+               "source": "profiles/r01_ncu_wavefront_%s.md (ncu --set full, steady-state wave of a 24-iteration batch: dram__bytes_read.sum + dram__bytes_write.sum; L2: lts__t_sectors.sum x 32 B)" % tag},
               open(os.path.join(pr, "traffic.json"), "w"), indent=1)
     print("\n".join(out[4:]))
     print({k: b[k] for k in ("value", "ms_per_step", "e2e", "gpu_launches")}, b["roofline"]["achieved"], b["roofline"]["frac"], b["roofline"]["kernel_ms"])
