@@ -25,10 +25,18 @@
 
 #if defined(__CUDA_ARCH__)
 #define GI_UNROLL _Pragma("unroll")
+#ifndef GI_USE_FRCP
+#define GI_USE_FRCP 0
+#endif
 #define GI_MUL(a, b) __fmul_rn((a), (b))
 #define GI_ADD(a, b) __fadd_rn((a), (b))
 #define GI_SUB(a, b) __fsub_rn((a), (b))
 #define GI_DIV(a, b) __fdiv_rn((a), (b))
+#if GI_USE_FRCP
+#define GI_RCP(a) __frcp_rn((a))          // correctly rounded reciprocal == the IEEE quotient 1.0f / a, a shorter instruction sequence than div.rn
+#else
+#define GI_RCP(a) __fdiv_rn(1.0f, (a))
+#endif
 #else
 // host emulation: compiled with -ffp-contract=off, so each operator is one rounded operation
 #define GI_UNROLL
@@ -36,6 +44,7 @@
 #define GI_ADD(a, b) ((a) + (b))
 #define GI_SUB(a, b) ((a) - (b))
 #define GI_DIV(a, b) ((a) / (b))
+#define GI_RCP(a) (1.0f / (a))
 #endif
 
 namespace gik {
@@ -194,7 +203,7 @@ GI_HD bool intersectTriangle(F3 o, F3 d, F3 p0, F3 p1, F3 p2, float& hit, F3& ba
 	F3 e0 = subx(p1, p0);
 	F3 e1 = subx(p0, p2);
 	n = crossx(e1, e0);
-	float r = GI_DIV(1.0f, dotx(n, d));
+	float r = GI_RCP(dotx(n, d));
 	F3 po = subx(p0, o);
 	F3 e2 = f3(GI_MUL(r, po.x), GI_MUL(r, po.y), GI_MUL(r, po.z));
 	F3 i = crossx(d, e2);
@@ -205,7 +214,7 @@ GI_HD bool intersectTriangle(F3 o, F3 d, F3 p0, F3 p1, F3 p2, float& hit, F3& ba
 	return (hit > GI_INTERSECT_EPSILON) && (bary.x >= 0.0f) && (bary.y >= 0.0f) && (bary.z >= 0.0f);
 }
 
-GI_HD F3 invDir(F3 d) { return f3(GI_DIV(1.0f, d.x), GI_DIV(1.0f, d.y), GI_DIV(1.0f, d.z)); }
+GI_HD F3 invDir(F3 d) { return f3(GI_RCP(d.x), GI_RCP(d.y), GI_RCP(d.z)); }
 
 // rotate(), intersectiontests.glsl:82-88: x rotated by the quaternion q
 GI_HD F3 rotateByQuaternion(F3 x, F4 q)
