@@ -10,8 +10,11 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-DEVICE_LIB_PATH = os.path.join(_HERE, "libgpugi_b200.so")
-HOST_LIB_PATH = os.path.join(_HERE, "libgpugi_b200_host.so")
+# GPUGI_B200_LIBDIR: directory holding an A/B build of BOTH libraries (tools/gpu/variants.sh writes gpugi_b200/variants/<tag>/); the
+# product libraries next to this file are never overwritten by an experiment.
+_LIBDIR = os.environ.get("GPUGI_B200_LIBDIR") or _HERE
+DEVICE_LIB_PATH = os.path.join(_LIBDIR, "libgpugi_b200.so")
+HOST_LIB_PATH = os.path.join(_LIBDIR, "libgpugi_b200_host.so")
 
 
 class GpugiBuildError(ImportError):
