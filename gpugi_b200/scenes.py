@@ -216,10 +216,8 @@ def box1_materials():
     }
 
 
-def make_box1(tess=4, build_method="sah", coincident_faces=False, bvh_type=0):
-    """Closed room x in [-1.5,1.5], y in [0,3], z in [-3,2.3] + a white box, a glass box and two emissive quads.
-    coincident_faces=True keeps the boxes' bottom faces, which lie exactly in the floor plane: a
-    deliberate exact-tie case for the traversal parity tests."""
+def box1_mesh(tess=4, coincident_faces=False):
+    """The box1 mesh as arrays (positions, normals, texcoords, triangles, triangle materials)."""
     M = {n: i for i, n in enumerate(BOX1_MATERIAL_NAMES)}
     mb = MeshBuilder()
     lo, hi = np.array([-1.5, 0.0, -3.0]), np.array([1.5, 3.0, 2.3])
@@ -231,7 +229,14 @@ def make_box1(tess=4, build_method="sah", coincident_faces=False, bvh_type=0):
     # emissive quads just below the ceiling, facing down (normal -y): eu x ev must point to -y
     mb.grid([0.35, 2.98, -1.9], [0.6, 0, 0], [0, 0, 0.6], 2, 2, M["LightR"])
     mb.grid([-0.95, 2.98, -1.9], [0.6, 0, 0], [0, 0, 0.6], 2, 2, M["LightL"])
-    pos, nrm, uv, tri, mat = mb.arrays()
+    return mb.arrays()
+
+
+def make_box1(tess=4, build_method="sah", coincident_faces=False, bvh_type=0):
+    """Closed room x in [-1.5,1.5], y in [0,3], z in [-3,2.3] + a white box, a glass box and two emissive quads.
+    coincident_faces=True keeps the boxes' bottom faces, which lie exactly in the floor plane: a
+    deliberate exact-tie case for the traversal parity tests."""
+    pos, nrm, uv, tri, mat = box1_mesh(tess, coincident_faces)
     return Scene.from_mesh(pos, nrm, uv, tri, mat, box1_materials(), "", build_method, bvh_type=bvh_type)
 
 
