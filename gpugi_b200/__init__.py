@@ -235,6 +235,18 @@ class Device:
         """gi_set_light_samples_device: samples already resident in device memory (no copy)."""
         self._check(capi.dev.gi_set_light_samples_device(self._c, C.c_void_p(d_ptr), int(n)), "gi_set_light_samples_device")
 
+    def generate_light_samples(self, rng_state, n, position_bias=1.0e-4):
+        """gi_generate_light_samples: the next iteration's set drawn on the device (needs gi_set_light_tables, which
+        RendererSystem.SetDeviceLightSampling uploads); returns the advanced xorshift64* state."""
+        st = C.c_uint64(int(rng_state))
+        self._check(capi.dev.gi_generate_light_samples(self._c, C.byref(st), int(n), float(position_bias)), "gi_generate_light_samples")
+        return int(st.value)
+
+    def get_light_samples(self, n):
+        out = np.zeros(int(n), dtype=LIGHT_SAMPLE_DTYPE)
+        self._check(capi.dev.gi_get_light_samples(self._c, C.cast(_vp(out), C.POINTER(capi.GiLightSample)), int(n)), "gi_get_light_samples")
+        return out
+
     def set_environment_constant(self, srgb8):
         """1x1 cube with the same sRGB8 colour on all faces (the reference default is black)."""
         face = np.array([srgb8[0], srgb8[1], srgb8[2], 255], dtype=np.uint8)

@@ -211,6 +211,7 @@ HOST_API = {
     "gih_rs_read_backbuffer_async": (C.c_int, [vp, vp, P(u32)]),
     "gih_rs_wait_reads": (C.c_int, [vp]),
     "gih_rs_num_light_samples": (u32, [vp]),
+    "gih_rs_set_num_light_samples": (None, [vp, u32]),
     "gih_rs_light_samples": (None, [vp, vp]),
     "gih_rs_camera": (None, [vp, P(GiCamera)]),
     "gih_rs_renderer_info": (None, [vp, P(i32), P(u32), P(i32)]),

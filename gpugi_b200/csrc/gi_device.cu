@@ -138,7 +138,9 @@ __global__ void k_reset_counter(uint32_t* lightCacheCount, uint32_t* lightPathLe
 
 // LightSampler::GenerateRandomSamples (lightsampler.cpp:18-95) for one iteration.  The xorshift64* recurrence of utilities/random.cpp:25-43
 // stores the multiplied value back into its state, so the stream has no jump-ahead: thread 0 draws the 3 * numArea + numPoint numbers
-// of the iteration into shared memory, then one thread per sample does the rest.  Every float operation is the host's (no contraction).
+// of the iteration into shared memory, then one thread per sample does the rest.  Every +, -, *, /, sqrt is the host's (no contraction);
+// two things are not: atan2f is the device's (normal_phi may differ from the host's libm in the last bit), and the table index is clamped
+// to the last entry where the host asserts (a pick of exactly 1.0 on a table whose last entry rounds below 1).
 struct DLightTables
 {
 	const float* tri;        // 12 floats per light triangle: v0, v1, v2, luminance
@@ -268,6 +270,8 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MIN_BLOCKS) k_wf_tr
 	io.q.numClosest = w.numCam + counts[0];
 	io.q.numShadow = counts[1];
 	io.q.rayBase = w.rayBase;
+	io.q.splatBase = w.splatBase;
+	io.q.splatStride = size_t(w.f.width) * size_t(w.f.height) * 4u;
 	WfCounters<STEPS> cnt;
 	if (REFERENCE) wfTraceLoopReference(w.f.scene, io, counts + 2, cnt);
 	else wfTraceLoop(w.f.scene, io, counts + 2, w.tune, cnt);
@@ -372,6 +376,23 @@ __global__ void __launch_bounds__(256) k_wf_fold(float4* __restrict__ accum, con
 	}
 }
 
+// A stream of light paths keeps the splats of every iteration in flight in that iteration's own image; when the iteration is complete the
+// image joins the accumulator and is cleared for the iteration that takes the ring slot next.
+__global__ void __launch_bounds__(256) k_wf_fold_splats(float4* __restrict__ accum, float4* __restrict__ image, uint32_t numPixels)
+{
+	for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < numPixels; p += gridDim.x * blockDim.x)
+	{
+		const float4 s = image[p];
+		if (s.x != 0.0f || s.y != 0.0f || s.z != 0.0f || s.w != 0.0f)
+		{
+			float4 a = accum[p];
+			a.x += s.x; a.y += s.y; a.z += s.z; a.w += s.w;
+			accum[p] = a;
+			image[p] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+		}
+	}
+}
+
 // sqerror.frag:16-17 + mean (texturemse.cpp:58-62): per-block partial sums in double.
 __global__ void __launch_bounds__(256) k_mse(const float4* __restrict__ accum, const float* __restrict__ ref, uint32_t numPixels, float invDivisor,
                                               double* result)
@@ -410,6 +431,9 @@ struct WfRun
 	uint32_t wave = 0;       // next wave
 	uint32_t maxLen = 0, numSlots = 0;
 	int renderer = 0, numRaysPerLightSample = 0;
+	// splat ring of a light-path stream: iteration k splats into image k % splatSlots and is folded into the accumulator after the trace of
+	// wave k + foldDelay (LPT: its last camera connection is traced in wave k + maxLen; BPT: together with the eye radiance of iteration k)
+	uint32_t splatSlots = 0, foldDelay = 0, splatFolded = 0;
 	WfFrame w;
 };
 
@@ -491,6 +515,10 @@ struct GiContext
 	double topologyBuildMs = 0.0;
 	int plocRadius = 4; // GI_OPT_PLOC_RADIUS (clustering passes of the upload topology; B200 sweep: 4 beats 1..3 and 6..64 on C2, 2..4 on C5)
 	uint32_t lightSlot = 0;          // ring slot of the light-sample set the next iteration uses
+	uint32_t lightSetIteration = 0;  // stream iteration (run[0].count at the time) whose ring slot holds a set installed by the caller
+	float* splatRing = nullptr;      // per-iteration splat images of an open LPT / BPT stream
+	uint32_t splatRingSlots = 0;
+	size_t splatRingStride = 0;      // floats per image
 	// asynchronous read-out (gi_read_accumulator_async)
 	cudaStream_t copyStream = nullptr;
 	float* snapshot[2] = {nullptr, nullptr};
@@ -665,8 +693,32 @@ static int ensureWavefront(GiContext* c, int set, uint64_t capacity, uint32_t nu
 // A run is opened (wfOpen), fed one iteration per wave (wfStep) and closed (wfClose: drain + fold).  A batch
 // (gi_render_iterations) does all three in one call; a stream (GI_OPT_STREAMING) keeps the run open across
 // gi_render_iteration calls, so that consecutive Draw() calls overlap exactly like the iterations of a batch.
+static int ensureSplatRing(GiContext* c, uint32_t slots)
+{
+	const size_t stride = size_t(c->width) * size_t(c->height) * 4u;
+	if (c->splatRingSlots < slots || c->splatRingStride != stride)
+	{
+		GI_CUDA(c, cudaStreamSynchronize(c->stream));
+		cudaFree(c->splatRing); c->splatRing = nullptr; c->splatRingSlots = 0; c->splatRingStride = 0;
+		GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->splatRing), size_t(slots) * stride * sizeof(float)));
+		c->splatRingSlots = slots; c->splatRingStride = stride;
+	}
+	GI_CUDA(c, cudaMemsetAsync(c->splatRing, 0, size_t(slots) * stride * sizeof(float), c->stream));
+	return GI_OK;
+}
+
+// the splat image of stream iteration k joins the accumulator
+static int foldSplatImage(GiContext* c, WfRun& r, uint32_t iteration)
+{
+	float* image = c->splatRing + size_t(iteration % r.splatSlots) * c->splatRingStride;
+	k_wf_fold_splats<<<unsigned(c->numSMs) * 8u, 256, 0, c->stream>>>(reinterpret_cast<float4*>(c->accum), reinterpret_cast<float4*>(image), uint32_t(c->width) * uint32_t(c->height));
+	++c->launches;
+	timingMark(c, GI_KERNEL_OTHER);
+	return GI_OK;
+}
+
 static int wfOpen(GiContext* c, int set, const DFrame& f, int pass, uint32_t lightFlags, uint32_t expectedCount, bool streaming, uint32_t lightStride, uint32_t lightBase,
-                  uint32_t lightRing)
+                  uint32_t lightRing, uint32_t splatSlots = 0u, uint32_t foldDelay = 0u)
 {
 	WfRun& r = c->run[set];
 	WfFrame& w = r.w;
@@ -689,7 +741,15 @@ static int wfOpen(GiContext* c, int set, const DFrame& f, int pass, uint32_t lig
 	r.open = false;
 	r.pass = pass; r.streaming = streaming; r.count = 0; r.wave = 0;
 	r.maxLen = uint32_t(f.maxPathLength);
+	r.splatSlots = 0u; r.foldDelay = foldDelay; r.splatFolded = 0u;
 	if (w.numPaths == 0) return GI_OK;
+	if (splatSlots)
+	{
+		int sst = ensureSplatRing(c, splatSlots);
+		if (sst != GI_OK) return sst;
+		r.splatSlots = splatSlots;
+		w.splatBase = c->splatRing; w.splatSlots = splatSlots;
+	}
 	const bool many = streaming || expectedCount > 1u;
 	r.numSlots = streaming ? r.maxLen + 1u : std::min(expectedCount, r.maxLen + 1u);
 	// a batch has one counter entry per wave (zeroed here); a stream cycles through a ring
@@ -741,6 +801,13 @@ static int wfStep(GiContext* c, int set, bool generate, uint32_t seed, bool next
 	else k_wf_trace<false, false><<<traceGrid, WF_TRACE_THREADS, 0, c->stream>>>(w, c->counters);
 	++c->launches;
 	timingMark(c, GI_KERNEL_TRACE);
+	if (r.splatSlots && r.wave >= r.foldDelay && r.wave - r.foldDelay < r.count && r.splatFolded == r.wave - r.foldDelay)
+	{
+		// every splat of iteration wave - foldDelay has landed in its image
+		int fst = foldSplatImage(c, r, r.splatFolded);
+		if (fst != GI_OK) return fst;
+		++r.splatFolded;
+	}
 	if (shade)
 	{
 		if (pass == WF_PASS_PT) k_wf_shade_pt<<<shadeGrid, WF_SHADE_THREADS, 0, c->stream>>>(w, c->counters);
@@ -764,6 +831,12 @@ static int wfClose(GiContext* c, int set, bool drain = true)
 		{
 			int st = wfStep(c, set, false, 0u, false, k + 1u < r.maxLen);
 			if (st != GI_OK) return st;
+		}
+		while (r.splatSlots && r.splatFolded < r.count)
+		{
+			int fst = foldSplatImage(c, r, r.splatFolded);
+			if (fst != GI_OK) return fst;
+			++r.splatFolded;
 		}
 		if (r.pass != WF_PASS_LIGHT)
 		{
@@ -848,7 +921,9 @@ static int bptOpen(GiContext* c, const GiIterationParams* p, uint32_t expectedCo
 	f.lightCacheCount = c->ringCounters;
 	f.lightPathLengthSum = c->ringCounters + 1;
 	f.cacheRing = ring;
-	int st = wfOpen(c, 0, f, WF_PASS_LIGHT, WF_LIGHT_SAVE, expectedCount, streaming, lightStride, lightBase, lightRing);
+	// a stream can be read while it runs (gi_read_accumulator_async): the camera-connection splats of iteration k wait in their own image
+	// until the eye radiance of iteration k joins the accumulator (global wave k + D + maxLen + 1), so a snapshot never holds half an iteration
+	int st = wfOpen(c, 0, f, WF_PASS_LIGHT, WF_LIGHT_SAVE, expectedCount, streaming, lightStride, lightBase, lightRing, streaming ? 2u * maxLen + 2u : 0u, 2u * maxLen + 1u);
 	if (st == GI_OK) st = wfOpen(c, 1, f, WF_PASS_EYE, 0u, expectedCount, streaming, 0u, 0u, 0u);
 	if (st != GI_OK) { c->run[0].open = c->run[1].open = false; return st; }
 	b.open = true; b.streaming = streaming;
@@ -968,6 +1043,8 @@ int gi_create(int device, GiContext** out_ctx)
 	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->shadeEyeBlocksPerSM, k_wf_shade_eye, WF_SHADE_THREADS, 0);
 	c->shadeLightBlocksPerSM = std::max(c->shadeLightBlocksPerSM, 1);
 	c->shadeEyeBlocksPerSM = std::max(c->shadeEyeBlocksPerSM, 1);
+	// k_light_samples keeps up to 3 x 8192 draws in dynamic shared memory: above 48 KB a kernel has to opt in
+	cudaFuncSetAttribute(k_light_samples, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 8192 * int(sizeof(float)));
 	*out_ctx = c;
 	return GI_OK;
 }
@@ -985,7 +1062,7 @@ void gi_destroy(GiContext* c)
 	if (c->copyStream) cudaStreamDestroy(c->copyStream);
 	if (c->envTex) cudaDestroyTextureObject(c->envTex);
 	if (c->envArray) cudaFreeArray(c->envArray);
-	cudaFree(c->cacheRing); cudaFree(c->ringCounters);
+	cudaFree(c->cacheRing); cudaFree(c->ringCounters); cudaFree(c->splatRing);
 	for (void* p : c->lightTableAllocs) cudaFree(p);
 	cudaFree(c->accum); cudaFree(c->lightSamples); cudaFree(c->lightCache); cudaFree(c->bptCounters); cudaFree(c->counters); cudaFree(c->mseResult);
 	for (cudaEvent_t e : c->timingEvents) cudaEventDestroy(e);
@@ -1336,6 +1413,23 @@ static int lightSlotForNextIteration(GiContext* c, uint32_t n, uint32_t* slot)
 	return GI_OK;
 }
 
+// Streams: the set just installed belongs to the iteration the next gi_render_iteration call submits.
+static void markLightSet(GiContext* c) { c->lightSetIteration = (c->run[0].open && c->run[0].streaming) ? c->run[0].count : 0u; }
+
+// A caller who installs ONE set and then renders many iterations gets that set for all of them outside a stream (the ring position does not
+// move).  Inside a stream every iteration reads its own ring slot: when no set was installed for the iteration about to be submitted, the
+// previous iteration's set is copied forward (device to device, stream ordered), so both modes render the same thing.
+static int carryLightSetForward(GiContext* c)
+{
+	const WfRun& r = c->run[0];
+	if (!(r.open && r.streaming) || r.count == 0u || c->lightSetIteration == r.count) return GI_OK;
+	const size_t setElems = 2u * size_t(c->numLightSamples);
+	const uint32_t src = (r.w.lightBase + r.count - 1u) % GI_LIGHT_RING, dst = (r.w.lightBase + r.count) % GI_LIGHT_RING;
+	GI_CUDA(c, cudaMemcpyAsync(c->lightSamples + size_t(dst) * setElems, c->lightSamples + size_t(src) * setElems, setElems * sizeof(F4), cudaMemcpyDeviceToDevice, c->stream));
+	c->lightSetIteration = r.count;
+	return GI_OK;
+}
+
 int gi_set_light_samples(GiContext* c, const GiLightSample* samples, uint32_t n)
 {
 	if (!c || !samples || n == 0) return fail(c, GI_ERR_INVALID, "gi_set_light_samples: no samples");
@@ -1349,6 +1443,7 @@ int gi_set_light_samples(GiContext* c, const GiLightSample* samples, uint32_t n)
 	c->lightSlot = slot;
 	c->externalLightSamples = nullptr;
 	c->numLightSamples = int(n);
+	markLightSet(c);
 	return GI_OK;
 }
 
@@ -1366,6 +1461,7 @@ int gi_set_light_samples_device(GiContext* c, const GiLightSample* d_samples, ui
 		c->lightSlot = slot;
 		c->externalLightSamples = nullptr;
 		c->numLightSamples = int(n);
+		markLightSet(c);
 		return GI_OK;
 	}
 	c->externalLightSamples = reinterpret_cast<const F4*>(d_samples);
@@ -1412,7 +1508,7 @@ int gi_set_light_tables(GiContext* c, const GiLightTables* t)
 int gi_generate_light_samples(GiContext* c, uint64_t* rng_state, uint32_t n, float position_bias)
 {
 	if (!c || !rng_state || n == 0) return fail(c, GI_ERR_INVALID, "gi_generate_light_samples: no samples");
-	if (n > 8192u) return fail(c, GI_ERR_CAPACITY, "gi_generate_light_samples: more than 8192 samples per iteration");
+	if (n > 8192u) return fail(c, GI_ERR_CAPACITY, "gi_generate_light_samples: more than 8192 samples per iteration"); // 3 draws x 4 B x 8192 = 96 KB of shared memory (opted in at gi_create)
 	GI_CUDA(c, cudaSetDevice(c->device));
 	uint32_t slot = 0;
 	int st = lightSlotForNextIteration(c, n, &slot);
@@ -1434,6 +1530,7 @@ int gi_generate_light_samples(GiContext* c, uint64_t* rng_state, uint32_t n, flo
 	c->lightSlot = slot;
 	c->externalLightSamples = nullptr;
 	c->numLightSamples = int(n);
+	markLightSet(c);
 	return GI_OK;
 }
 
@@ -1476,12 +1573,23 @@ int gi_render_iteration(GiContext* c, const GiIterationParams* p)
 	if (st != GI_OK) return st;
 	if (p->max_path_length <= 0) return fail(c, GI_ERR_INVALID, "max_path_length must be positive");
 	GI_CUDA(c, cudaSetDevice(c->device));
+	// Streams and the light-sample ring (GI_LIGHT_RING sets): iteration k reads its set in the waves that shade it with next-event estimation (PT:
+	// waves k .. k + maxPathLength) or that start its light paths (LPT / BPT: generate wave k only -- light vertices carry their flux, and the BPT
+	// eye pass takes its light vertices from the cache, never from InitialLightSamples).  maxPathLength + 1 <= GI_LIGHT_RING therefore covers all
+	// three, although a BPT stream keeps 2 x maxPathLength + 1 iterations in flight.
 	const bool canStream = c->streamingOption && c->scheduler == GI_SCHEDULER_WAVEFRONT && !c->externalLightSamples && uint32_t(p->max_path_length) + 1u <= GI_LIGHT_RING;
-	if (canStream && p->renderer == GI_RENDERER_PT)
+	// the wave index is an int inside the kernels: a stream that has been open for 2^30 waves is drained and reopened
+	if (canStream && ((c->run[0].open && c->run[0].streaming && c->run[0].wave >= 0x40000000u) || (c->bpt.open && c->bpt.wave >= 0x40000000u)))
+	{
+		st = flushStream(c);
+		if (st != GI_OK) return st;
+	}
+	if (canStream && (p->renderer == GI_RENDERER_PT || (p->renderer == GI_RENDERER_LPT && p->num_rays_per_light_sample > 0)))
 	{
 		// GI_OPT_STREAMING: this iteration is one more wave of the open run (opened here if there is none)
 		WfRun& r = c->run[0];
-		if (c->bpt.open || (r.open && r.streaming && (r.renderer != p->renderer || r.maxLen != uint32_t(p->max_path_length))))
+		if (c->bpt.open || (r.open && r.streaming && (r.renderer != p->renderer || r.maxLen != uint32_t(p->max_path_length) ||
+		                                              (p->renderer == GI_RENDERER_LPT && r.numRaysPerLightSample != p->num_rays_per_light_sample))))
 		{
 			st = flushStream(c);
 			if (st != GI_OK) return st;
@@ -1490,10 +1598,17 @@ int gi_render_iteration(GiContext* c, const GiIterationParams* p)
 		{
 			DFrame sf = makeFrame(c, p);
 			sf.lightSamples = c->lightSamples; // ring base; iteration i of the stream reads set (lightSlot + i) % GI_LIGHT_RING
-			st = wfOpen(c, 0, sf, WF_PASS_PT, 0u, 0u, true, 2u * uint32_t(c->numLightSamples), c->lightSlot, GI_LIGHT_RING);
+			// LPT: the splats of every iteration in flight go to that iteration's own image and join the accumulator when its last camera
+			// connection has been traced (wave k + maxPathLength), so that a progressive read-out only ever sees complete iterations
+			if (p->renderer == GI_RENDERER_PT) st = wfOpen(c, 0, sf, WF_PASS_PT, 0u, 0u, true, 2u * uint32_t(c->numLightSamples), c->lightSlot, GI_LIGHT_RING);
+			else st = wfOpen(c, 0, sf, WF_PASS_LIGHT, 0u, 0u, true, 2u * uint32_t(c->numLightSamples), c->lightSlot, GI_LIGHT_RING, uint32_t(p->max_path_length) + 1u, uint32_t(p->max_path_length));
 			if (st != GI_OK) return st;
 			r.renderer = p->renderer;
+			r.numRaysPerLightSample = p->num_rays_per_light_sample;
+			c->lightSetIteration = 0u;
 		}
+		st = carryLightSetForward(c);
+		if (st != GI_OK) return st;
 		st = wfStep(c, 0, true, p->frame_seed, true, true);
 		if (st != GI_OK) return st;
 		GI_CUDA(c, cudaGetLastError());
@@ -1514,9 +1629,12 @@ int gi_render_iteration(GiContext* c, const GiIterationParams* p)
 		{
 			st = bptOpen(c, p, 0u, 2u * uint32_t(c->numLightSamples), c->lightSlot, GI_LIGHT_RING);
 			if (st != GI_OK && st != GI_ERR_CAPACITY) return st;
+			if (st == GI_OK) c->lightSetIteration = 0u;
 		}
 		if (b.open)
 		{
+			st = carryLightSetForward(c);
+			if (st != GI_OK) return st;
 			st = bptWave(c, true, p->frame_seed);
 			if (st != GI_OK) return st;
 			GI_CUDA(c, cudaGetLastError());
@@ -1662,6 +1780,21 @@ int gi_render_iterations(GiContext* c, const GiIterationParams* p, const uint32_
 int gi_show_light_caches(GiContext* c)
 {
 	if (!c) return GI_ERR_INVALID;
+	const WfRun& r0 = c->run[0];
+	if (r0.open && r0.streaming && r0.pass == WF_PASS_LIGHT && r0.splatSlots && !c->bpt.open && r0.count > 0u && c->haveScene)
+	{
+		// LightPathtracer::Draw (lightpathtracer.cpp:45-50) shows the light samples of the iteration it has just started: inside a stream that is
+		// iteration count - 1, whose splats are collected in its own image and whose samples sit in its own ring slot -- no drain
+		GI_CUDA(c, cudaSetDevice(c->device));
+		DFrame f = makeFrame(c, nullptr);
+		const uint32_t k = r0.count - 1u;
+		f.accum = c->splatRing + size_t(k % r0.splatSlots) * c->splatRingStride;
+		f.lightSamples = c->lightSamples + size_t((r0.w.lightBase + k) % GI_LIGHT_RING) * 2u * size_t(c->numLightSamples);
+		k_show_light_caches<<<(c->numLightSamples + 63) / 64, 64, 0, c->stream>>>(f, c->counters);
+		++c->launches;
+		GI_CUDA(c, cudaGetLastError());
+		return GI_OK;
+	}
 	{
 		int fst = flushStream(c);
 		if (fst != GI_OK) return fst;
@@ -1977,7 +2110,9 @@ int gi_read_accumulator_async(GiContext* c, float* rgba, uint32_t* iterations_in
 	// PT stream: iteration k joins the accumulator when its state slot is recycled, maxPathLength + 1 waves after it started
 	if (iterations_in_flight)
 	{
-		if (c->bpt.open && c->bpt.streaming) *iterations_in_flight = std::min(c->bpt.count, c->bpt.D + c->bpt.maxLen + 1u); // eye pass starts D waves late
+		// BPT: the eye pass starts D waves late; the light-pass splats of an iteration wait in its splat image until its eye radiance is folded
+		if (c->bpt.open && c->bpt.streaming) *iterations_in_flight = std::min(c->bpt.count, c->bpt.D + c->bpt.maxLen + 1u);
+		else if (c->run[0].open && c->run[0].streaming && c->run[0].pass == WF_PASS_LIGHT) *iterations_in_flight = c->run[0].count - c->run[0].splatFolded;
 		else *iterations_in_flight = (c->run[0].open && c->run[0].streaming) ? std::min(c->run[0].count, c->run[0].numSlots) : 0u;
 	}
 	return GI_OK;

@@ -108,6 +108,8 @@ struct WfTraceIO
 	int width, height;
 	uint32_t numClosest, numShadow;
 	uint32_t rayBase;   // extension ray i of this wave sits in queue slot rayBase + i
+	float* splatBase;   // streams of light paths: ring of per-iteration splat images (nullptr: splats go straight into accum)
+	size_t splatStride; // floats per image
 };
 
 GI_D void wfSplat(float* accum, int width, int height, uint32_t pixel, F3 v)
@@ -127,7 +129,9 @@ GI_D void wfFinishShadow(const WfTraceIO& io, uint32_t slot, bool occluded, CNT&
 	if (word & WF_FLAG_SPLAT)
 	{
 		cnt.template add<WFC_SPLATS>(1u);
-		wfSplat(io.accum, io.width, io.height, id, f3(v.x, v.y, v.z));
+		// a stream keeps the splats of an iteration in that iteration's own image (ring slot in v.w) until the iteration is complete
+		float* image = io.splatBase ? io.splatBase + size_t(uint32_t(f2i(v.w))) * io.splatStride : io.accum;
+		wfSplat(image, io.width, io.height, id, f3(v.x, v.y, v.z));
 		return;
 	}
 	// the path's radiance sum: one shadow ray per path and wave, and shade() is another kernel -> exclusive
@@ -449,6 +453,8 @@ struct WfFrame
 	uint32_t lightBase;      // iteration i reads light-sample set (lightBase + i) % lightRing
 	uint32_t lightRing;
 	uint32_t lightFlags;     // light tracer waves: WF_LIGHT_SAVE / WF_LIGHT_WARMUP (gi_shade.h)
+	float* splatBase;        // streams of light paths: ring of splatSlots images, iteration i splats into image i % splatSlots (nullptr: into f.accum)
+	uint32_t splatSlots;
 };
 
 // queue slot -> pixel: 8x8 tiles in row-major tile order, row-major inside the tile (the reference's work-group shape)
@@ -603,7 +609,7 @@ GI_D F4 ldState(const F4* p) { const float4 v = *reinterpret_cast<const float4*>
 GI_D void stState(F4* p, F4 v) { *reinterpret_cast<float4*>(p) = make_float4(v.x, v.y, v.z, v.w); }
 
 // warp-compacted push of what a shaded vertex produced (all 32 lanes call)
-GI_D void wfPushOut(const WfFrame& w, const WfPush& out, uint32_t shadowTarget, int bounce, uint32_t id)
+GI_D void wfPushOut(const WfFrame& w, const WfPush& out, uint32_t shadowTarget, int bounce, uint32_t id, uint32_t splatSlot = 0u)
 {
 	const WfQueues& q = w.q;
 	uint32_t* next = wfCounts(w, w.wave + 1);
@@ -613,7 +619,7 @@ GI_D void wfPushOut(const WfFrame& w, const WfPush& out, uint32_t shadowTarget, 
 		F4* sp = q.shadow + 3 * size_t(sslot);
 		*reinterpret_cast<float4*>(sp) = make_float4(out.sOrigin.x, out.sOrigin.y, out.sOrigin.z, out.sLen);
 		*reinterpret_cast<float4*>(sp + 1) = make_float4(out.sDir.x, out.sDir.y, out.sDir.z, i2f(int(shadowTarget)));
-		*reinterpret_cast<float4*>(sp + 2) = make_float4(out.sValue.x, out.sValue.y, out.sValue.z, 0.0f);
+		*reinterpret_cast<float4*>(sp + 2) = make_float4(out.sValue.x, out.sValue.y, out.sValue.z, i2f(int(splatSlot)));
 	}
 	const uint32_t rslot = w.pushBase + warpPush(next, out.ray);
 	if (out.ray)
@@ -657,7 +663,7 @@ GI_D void wfShadeLight(const WfFrame& w, uint32_t slot, bool valid, PathCounters
 {
 	WfPush out;
 	out.ray = false; out.shadow = false; out.px = 0; out.py = 0;
-	uint32_t id = 0; int bounce = 0;
+	uint32_t id = 0, splatSlot = 0; int bounce = 0;
 	if (valid)
 	{
 		const F4* rp = w.q.rays[w.wave & 1] + 2 * size_t(slot);
@@ -666,6 +672,7 @@ GI_D void wfShadeLight(const WfFrame& w, uint32_t slot, bool valid, PathCounters
 		id = uint32_t(f2i(r1.w)) & WF_ID_MASK;
 		bounce = f2i(r0.w);
 		const uint32_t iteration = uint32_t(w.wave - bounce);
+		if (w.splatSlots) splatSlot = iteration % w.splatSlots;
 		const uint32_t sidx = (iteration % w.q.numSlots) * w.q.numIds + id;
 		F4 T = ldState(w.q.stateT + sidx);
 		DFrame f = w.f;
@@ -673,7 +680,7 @@ GI_D void wfShadeLight(const WfFrame& w, uint32_t slot, bool valid, PathCounters
 		wfShadeLightLane(f, w.lightFlags, f3(r0.x, r0.y, r0.z), f3(r1.x, r1.y, r1.z), bounce, hrec.x, f2i(hrec.y), T, out, pc);
 		if (out.ray) stState(w.q.stateT + sidx, T);
 	}
-	wfPushOut(w, out, WF_FLAG_SPLAT | (uint32_t(out.py) * uint32_t(w.f.width) + uint32_t(out.px)), bounce, id);
+	wfPushOut(w, out, WF_FLAG_SPLAT | (uint32_t(out.py) * uint32_t(w.f.width) + uint32_t(out.px)), bounce, id, splatSlot);
 }
 
 // shade(w) of the BPT eye pass: one lane per hit record of an eye path

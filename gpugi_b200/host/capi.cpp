@@ -253,6 +253,7 @@ int gih_rs_read_backbuffer_async(GihRendererSystem* h, float* rgba, uint32_t* it
 }
 int gih_rs_wait_reads(GihRendererSystem* h) { return h->rs->GetBackbuffer().WaitReads() ? 0 : 1; }
 uint32_t gih_rs_num_light_samples(GihRendererSystem* h) { return h->rs->GetNumInitialLightSamples(); }
+void gih_rs_set_num_light_samples(GihRendererSystem* h, uint32_t n) { h->rs->SetNumInitialLightSamples(n); }
 void gih_rs_light_samples(GihRendererSystem* h, GiLightSample* out)
 {
 	const auto& v = h->rs->GetInitialLightSamples();

@@ -189,7 +189,7 @@ enum {
 	                                   stream and sum the durations per kernel class (gi_get_kernel_times); setting the option
 	                                   clears the sums.  The iteration call then synchronises -- measurement passes only.
 	                                   Replaces the reference's glFinish + clock() pair (renderersystem.cpp:249-255). */
-	GI_OPT_STREAMING = 9,           /* 1 = consecutive gi_render_iteration(GI_RENDERER_PT or _BPT) calls form a STREAM: each call submits one
+	GI_OPT_STREAMING = 9,           /* 1 = consecutive gi_render_iteration(GI_RENDERER_PT, _LPT or _BPT) calls form a STREAM: each call submits one
 	                                   wave (generate + trace + shade) of a run that stays open, so the bounces of up to
 	                                   max_path_length + 1 iterations share every wave exactly as in gi_render_iterations -- the
 	                                   reference's one-Draw()-per-iteration loop (renderersystem.cpp:246-256) without its
@@ -198,8 +198,12 @@ enum {
 	                                   stream first, after which the accumulator equals the one of the same iterations rendered
 	                                   one by one, bit for bit (PT; BPT: as for a pipelined batch, up to the scheduling-dependent order of
 	                                   light-cache slots, and 2 x max_path_length + 1 iterations deep over a ring of light caches; one
-	                                   iteration at a time if the ring does not fit the device memory).  gi_read_accumulator_async
-	                                   does NOT drain. */
+	                                   iteration at a time if the ring does not fit the device memory; LPT: up to the order of the float
+	                                   atomics inside a pixel).  gi_read_accumulator_async and, in an LPT stream, gi_show_light_caches do
+	                                   NOT drain.  LPT / BPT streams collect the splats of every iteration in flight in that iteration's own
+	                                   image (a ring of max_path_length + 1, BPT: 2 x max_path_length + 2, RGBA32F images) and add it to the
+	                                   accumulator when the iteration is complete.  Light samples: an iteration for which no set was
+	                                   installed since the previous one renders with the previous set, as outside a stream. */
 	GI_OPT_DEVICE_BUILDER = 10,     /* GI_BUILDER_*: what gi_build_hierarchy builds */
 	GI_OPT_PLOC_RADIUS = 12,        /* neighbour window (1..64, default 4) of the clustering passes behind GI_TOPOLOGY_PLOC: tree quality vs upload time */
 	GI_OPT_UPLOAD_TOPOLOGY = 11     /* GI_TOPOLOGY_*: the tree the ORDERED walks of the next gi_upload_scene run on.  Results do not depend on it
@@ -311,7 +315,9 @@ GI_API int gi_set_screen_size(GiContext* ctx, int width, int height);
 
 /* Replaces the light-sample half of RendererSystem::PerIterationBufferUpdate
  * (renderersystem.cpp:106-111) and SetNumInitialLightSamples (:118-130): the next
- * iteration uses these `n` initial light samples.  Copied at call time. */
+ * iteration -- and every later one, until another set is installed -- uses these `n`
+ * initial light samples.  Copied at call time.  (Inside a GI_OPT_STREAMING stream every
+ * iteration in flight keeps the set it started with.) */
 GI_API int gi_set_light_samples(GiContext* ctx, const GiLightSample* samples, uint32_t n);
 
 /* Same, but the samples already live in device memory (caller-owned, must stay valid until the
@@ -347,7 +353,8 @@ GI_API int gi_render_iterations(GiContext* ctx, const GiIterationParams* params,
                                 const GiLightSample* d_light_samples, uint32_t samples_per_iteration);
 
 /* Replaces RendererSystem::DispatchShowLightCacheShader (renderersystem.cpp:277-281):
- * splats the directly visible initial light samples (showlightcaches.comp). */
+ * splats the directly visible initial light samples (showlightcaches.comp).  In an LPT stream: those of the iteration
+ * submitted last, into that iteration's splat image. */
 GI_API int gi_show_light_caches(GiContext* ctx);
 
 /* Replaces TraceRay / TraceRayAnyHit (traceray.glsl:19-180) for a host ray batch:
@@ -411,8 +418,10 @@ GI_API int gi_read_accumulator(GiContext* ctx, float* rgba);
  * stalling the renderer): snapshots the accumulator in stream order and copies it to `rgba` on a second stream; returns at
  * once.  `rgba` (pinned memory for a truly asynchronous copy) is valid after the next gi_wait_reads / gi_read_accumulator_async
  * -but-one; at most two reads are in flight.  With GI_OPT_STREAMING the snapshot holds every submitted iteration except the
- * last *iterations_in_flight ones (<= max_path_length + 1), whose paths are still bouncing; it never holds a partial
- * iteration.  Does not drain the stream. */
+ * last *iterations_in_flight ones (PT, LPT: <= max_path_length + 1; BPT: <= 2 x max_path_length + 1), whose paths are still
+ * bouncing; it never holds a partial iteration: per-path radiance sums wait in the path state, light-path splats (LPT, and the
+ * camera connections of a BPT light pass) in the iteration's own splat image, and both join the accumulator together when the
+ * iteration is complete.  Does not drain the stream. */
 GI_API int gi_read_accumulator_async(GiContext* ctx, float* rgba, uint32_t* iterations_in_flight);
 
 /* Blocks until every gi_read_accumulator_async copy has landed. */

@@ -84,6 +84,7 @@ GI_API void gih_rs_set_device_light_sampling(GihRendererSystem* rs, int on_devic
 GI_API int gih_rs_read_backbuffer_async(GihRendererSystem* rs, float* rgba, uint32_t* iterations_in_flight); /* Texture2D::ReadImageAsync */
 GI_API int gih_rs_wait_reads(GihRendererSystem* rs);
 GI_API uint32_t gih_rs_num_light_samples(GihRendererSystem* rs);
+GI_API void gih_rs_set_num_light_samples(GihRendererSystem* rs, uint32_t n);   /* RendererSystem::SetNumInitialLightSamples (renderersystem.hpp:124) */
 GI_API void gih_rs_light_samples(GihRendererSystem* rs, GiLightSample* out);
 GI_API void gih_rs_camera(GihRendererSystem* rs, GiCamera* out);
 GI_API void gih_rs_renderer_info(GihRendererSystem* rs, int32_t* num_rays_per_light_sample, uint32_t* light_cache_capacity, int32_t* avg_light_path_length);

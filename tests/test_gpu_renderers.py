@@ -684,3 +684,155 @@ def test_whitted_raytracer_matches_oracle(g, orc, scenes, box1, sponza_small):
         assert cnt["camera_paths"] == (W // 8) * (H // 8) * 64
         assert abs(cnt["closest_rays"] - rc["closest_rays"]) / rc["closest_rays"] < 0.01
         rs.close()
+
+
+# ------------------------------------------------------------------------------------------------- round 2: streams
+def test_stream_with_one_light_sample_set_equals_plain_iterations(g, scenes, box1):
+    """C-ABI contract of gi_set_light_samples under GI_OPT_STREAMING: a caller who installs ONE set and renders N iterations gets that set
+    for every iteration in both modes (inside a stream the previous set is carried forward into the next ring slot).  PT: bit-identical."""
+    W = H = 96
+    N = 25
+    samples = g.LightSampler(box1).generate(128)
+    imgs = {}
+    for streaming in (0, 1):
+        dev = _device(g, scenes, box1, W, H)
+        dev.set_option(g.GI_OPT_STREAMING, streaming)
+        dev.set_light_samples(samples)
+        for k in range(N):
+            dev.render_iteration(g.GI_RENDERER_PT, g.wang_hash(k), 16)
+        imgs[streaming] = dev.read_accumulator(W, H)
+        dev.close()
+    assert imgs[0][..., :3].sum() > 0
+    assert np.array_equal(imgs[0], imgs[1])
+    # a set replaced in mid-stream is used from the next iteration on, and carried forward after that
+    other = g.LightSampler(box1)
+    other.seed(77)
+    samples2 = other.generate(128)
+    for streaming in (0, 1):
+        dev = _device(g, scenes, box1, W, H)
+        dev.set_option(g.GI_OPT_STREAMING, streaming)
+        dev.set_light_samples(samples)
+        for k in range(N):
+            if k == 7:
+                dev.set_light_samples(samples2)
+            dev.render_iteration(g.GI_RENDERER_PT, g.wang_hash(k), 16)
+        imgs[streaming] = dev.read_accumulator(W, H)
+        dev.close()
+    assert np.array_equal(imgs[0], imgs[1])
+
+
+@pytest.mark.parametrize("size,path_length", [((96, 96), 16), ((100, 60), 3)])
+def test_streaming_lighttracer(g, scenes, box1, size, path_length):
+    """GI_OPT_STREAMING for the light tracer (one wave per Draw, iterations overlap): the splats of an iteration wait in its own image until
+    its last camera connection is traced, so the asynchronous read shows whole iterations only -- equal (up to the order of the float
+    atomics) to plain Draw() calls of exactly those iterations -- and the drained image equals plain Draw() calls of all of them.
+    DispatchShowLightCacheShader runs inside the stream without draining it."""
+    import torch
+    W, H = size
+    N = 2 * path_length + 5
+    g.set_path_length(path_length)
+    try:
+        rs = _rs(g, scenes, box1, "LPT", W, H)
+        partial = [np.zeros((H, W, 4), np.float32)]
+        for _ in range(N):
+            rs.Draw()
+            partial.append(rs.ReadBackbuffer())
+        plain_counters = rs.device.counters()
+        rs.close()
+        rs = _rs(g, scenes, box1, "LPT", W, H)
+        rs.SetStreaming(True)
+        buf = torch.empty((H, W, 4), dtype=torch.float32, pin_memory=True).numpy()
+        launches0 = rs.device.kernel_launches()
+        for k in range(N):
+            rs.Draw()
+            in_flight = rs.ReadBackbufferAsync(buf)
+            assert in_flight == min(k + 1, path_length + 1), (k, in_flight)
+            rs.WaitReads()
+            assert np.allclose(buf, partial[k + 1 - in_flight], rtol=2e-4, atol=1e-5), "snapshot after Draw %d" % k
+        # generate + trace + shade + show-light-caches (+ one fold once the pipeline is full) per Draw: the stream was never drained
+        assert rs.device.kernel_launches() - launches0 <= 5 * N
+        final = rs.ReadBackbuffer()
+        assert np.allclose(final, partial[N], rtol=2e-4, atol=1e-5)
+        cnt = rs.device.counters()
+        for key in ("light_paths", "splats", "shaded_vertices", "closest_rays", "any_rays"):
+            assert cnt[key] == plain_counters[key], key
+        rs.close()
+    finally:
+        g.set_path_length(16)
+
+
+def test_streaming_bidirectional_snapshot_holds_whole_iterations(g, scenes, box1):
+    """gi_read_accumulator_async on a BPT stream: the light pass's camera-connection splats of an iteration in flight must not be visible
+    before its eye radiance is (they used to be added to the accumulator at once, which over-weighted the light-tracer part of up to
+    2 x pathLength + 1 iterations).  With the per-iteration splat images a snapshot divided by its own iteration count is an unbiased
+    image: its mean agrees with the converged one."""
+    import torch
+    W = H = 64
+    path_length = 4
+    g.set_path_length(path_length)
+    try:
+        rs = _rs(g, scenes, box1, "BPT", W, H)
+        rs.SetStreaming(True)
+        buf = torch.empty((H, W, 4), dtype=torch.float32, pin_memory=True).numpy()
+        depth = 2 * path_length + 1
+        means = []
+        for k in range(200):
+            rs.Draw()
+            if k + 1 in (depth, depth + 1, depth + 3, 60, 200):
+                in_flight = rs.ReadBackbufferAsync(buf)
+                rs.WaitReads()
+                done = k + 1 - in_flight
+                assert in_flight == depth
+                assert np.all(buf[..., 3] == done)
+                if done == 0:
+                    assert not buf[..., :3].any(), "splats of iterations in flight leaked into the snapshot"
+                else:
+                    means.append((done, float(buf[..., :3].mean()) / done))
+        final = rs.ReadBackbuffer()
+        ref = float(final[..., :3].mean()) / 200
+        rs.close()
+        for done, m in means:
+            tol = 0.5 if done < 4 else (0.15 if done < 100 else 0.05)
+            assert abs(m - ref) <= tol * ref, (done, m, ref)
+    finally:
+        g.set_path_length(16)
+
+
+@pytest.mark.parametrize("n", [4097, 8192])
+def test_device_light_sampling_large_sets(g, scenes, n):
+    """gi_generate_light_samples up to the advertised 8192 samples (3 draws x 4 B each in dynamic shared memory: above 48 KB the kernel
+    opts in).  Two RendererSystems make the same sequence of sampler calls, one on the host and one on the device: same records."""
+    from gpugi_b200 import _capi as capi
+    sc = scenes.make_box1(tess=4)
+    sc.add_point_light((0.5, 1.0, 0.0), (3.0, 2.0, 1.0))
+    systems = []
+    for on_device in (False, True):
+        rs = g.RendererSystem(0)
+        rs.SetDeviceLightSampling(on_device)
+        rs.SetScene(sc); rs.SetScreenSize(32, 32); rs.SetCamera(scenes.BOX1_CAMERA["pos"], scenes.BOX1_CAMERA["lookat"], scenes.BOX1_CAMERA["fov"])
+        rs.SetRenderer("PT")
+        capi.host.gih_rs_set_num_light_samples(rs._h, n)   # RendererSystem::SetNumInitialLightSamples (renderersystem.hpp:124)
+        systems.append(rs)
+    for it in range(3):
+        a, b = systems[0].GetInitialLightSamples(), systems[1].GetInitialLightSamples()
+        assert a.shape == b.shape == (n,)
+        assert np.array_equal(a["position"], b["position"]) and np.array_equal(a["intensity"], b["intensity"]), "iteration %d" % it
+        assert np.allclose(a["normal_phi"], b["normal_phi"], rtol=0, atol=2e-6)
+        for rs in systems:
+            rs.Draw()
+    assert pixel_mismatch_fraction(systems[1].ReadBackbuffer(), systems[0].ReadBackbuffer(), 1e-3) < 0.02
+    # the C-ABI entry point itself (no host fallback in between): state in, n samples out, state advanced like the host's stream
+    dev = systems[1].device
+    launches = dev.kernel_launches()
+    state = dev.generate_light_samples(123, n)
+    assert dev.kernel_launches() == launches + 1
+    got = dev.get_light_samples(n)
+    host = g.LightSampler(sc)
+    host.seed(123)
+    want = host.generate(n)
+    assert np.array_equal(want["position"], got["position"]) and np.array_equal(want["intensity"], got["intensity"])
+    nxt = host.generate(16)
+    dev.generate_light_samples(state, 16)
+    assert np.array_equal(nxt["position"], dev.get_light_samples(16)["position"])
+    for rs in systems:
+        rs.close()
