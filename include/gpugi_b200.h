@@ -418,7 +418,7 @@ GI_API int gi_read_accumulator(GiContext* ctx, float* rgba);
  * stalling the renderer): snapshots the accumulator in stream order and copies it to `rgba` on a second stream; returns at
  * once.  `rgba` (pinned memory for a truly asynchronous copy) is valid after the next gi_wait_reads / gi_read_accumulator_async
  * -but-one; at most two reads are in flight.  With GI_OPT_STREAMING the snapshot holds every submitted iteration except the
- * last *iterations_in_flight ones (PT, LPT: <= max_path_length + 1; BPT: <= 2 x max_path_length + 1), whose paths are still
+ * last *iterations_in_flight ones (PT: <= max_path_length + 1; LPT: <= max_path_length; BPT: <= 2 x max_path_length + 1), whose paths are still
  * bouncing; it never holds a partial iteration: per-path radiance sums wait in the path state, light-path splats (LPT, and the
  * camera connections of a BPT light pass) in the iteration's own splat image, and both join the accumulator together when the
  * iteration is complete.  Does not drain the stream. */
