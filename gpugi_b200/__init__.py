@@ -330,6 +330,31 @@ class Device:
     def wait_reads(self):
         self._check(capi.dev.gi_wait_reads(self._c), "gi_wait_reads")
 
+    # ---- multi-GPU read-out (gi_comm_*): one process per GPU, see parallel.connect_ranks for the rendezvous
+    def comm_create(self, rank, world):
+        """gi_comm_create -> this rank's 64-byte exchange-block handle (bytes)."""
+        h = (C.c_ubyte * 64)()
+        self._check(capi.dev.gi_comm_create(self._c, int(rank), int(world), h), "gi_comm_create")
+        return bytes(h)
+
+    def comm_connect(self, handles):
+        """gi_comm_connect: handles = the 64-byte handles of all ranks, in rank order."""
+        buf = (C.c_ubyte * (64 * len(handles))).from_buffer_copy(b"".join(handles))
+        self._check(capi.dev.gi_comm_connect(self._c, buf), "gi_comm_connect")
+
+    def comm_destroy(self):
+        self._check(capi.dev.gi_comm_destroy(self._c), "gi_comm_destroy")
+
+    def read_accumulator_reduced(self, out_rows):
+        """gi_read_accumulator_reduced (collective): sum over all ranks, this rank's rows (comm_slice) into out_rows; drains + waits."""
+        self._check(capi.dev.gi_read_accumulator_reduced(self._c, _vp(out_rows)), "gi_read_accumulator_reduced")
+        return out_rows
+
+    def read_accumulator_reduced_async(self, out_rows):
+        n = C.c_uint32()
+        self._check(capi.dev.gi_read_accumulator_reduced_async(self._c, _vp(out_rows), C.byref(n)), "gi_read_accumulator_reduced_async")
+        return n.value
+
     def accumulator_device(self):
         ptr, nbytes = C.c_void_p(), C.c_size_t()
         self._check(capi.dev.gi_accumulator_device(self._c, C.byref(ptr), C.byref(nbytes)), "gi_accumulator_device")
@@ -462,6 +487,18 @@ class RendererSystem:
         if capi.host.gih_rs_wait_reads(self._h) != 0:
             raise GpugiError("WaitReads: " + capi.dev.gi_last_error(self.device._c).decode())
 
+    def ReadBackbufferReduced(self, out_rows):
+        """Multi-GPU: sum of all ranks' backbuffers, this rank's rows (comm_slice) -- collective, drains and waits."""
+        if capi.host.gih_rs_read_backbuffer_reduced(self._h, _vp(out_rows)) != 0:
+            raise GpugiError("ReadBackbufferReduced: " + capi.dev.gi_last_error(self.device._c).decode())
+        return out_rows
+
+    def ReadBackbufferReducedAsync(self, out_rows):
+        n = C.c_uint32()
+        if capi.host.gih_rs_read_backbuffer_reduced_async(self._h, _vp(out_rows), C.byref(n)) != 0:
+            raise GpugiError("ReadBackbufferReducedAsync: " + capi.dev.gi_last_error(self.device._c).decode())
+        return n.value
+
     def ReadBackbuffer(self, out=None):
         w, h = self._size
         if out is None:
@@ -504,6 +541,14 @@ class Application:
 
     def GetLastScreenshot(self):
         return capi.host.gih_app_last_screenshot(self._h).decode()
+
+
+def comm_slice(height, rank, world):
+    """gi_comm_slice: (first_row, num_rows) of the summed image that `rank` of `world` reduces and copies out."""
+    a, b = C.c_uint32(), C.c_uint32()
+    if capi.dev.gi_comm_slice(int(height), int(rank), int(world), C.byref(a), C.byref(b)) != capi.GI_OK:
+        raise GpugiError("gi_comm_slice: bad arguments")
+    return a.value, b.value
 
 
 def config_parse(line):

@@ -154,6 +154,12 @@ DEVICE_API = {
     "gi_read_accumulator": (C.c_int, [vp, vp]),
     "gi_read_accumulator_async": (C.c_int, [vp, vp, P(u32)]),
     "gi_wait_reads": (C.c_int, [vp]),
+    "gi_comm_slice": (C.c_int, [C.c_int, C.c_int, C.c_int, P(u32), P(u32)]),
+    "gi_comm_create": (C.c_int, [vp, C.c_int, C.c_int, vp]),
+    "gi_comm_connect": (C.c_int, [vp, vp]),
+    "gi_comm_destroy": (C.c_int, [vp]),
+    "gi_read_accumulator_reduced": (C.c_int, [vp, vp]),
+    "gi_read_accumulator_reduced_async": (C.c_int, [vp, vp, P(u32)]),
     "gi_set_light_tables": (C.c_int, [vp, vp]),
     "gi_generate_light_samples": (C.c_int, [vp, P(u64), u32, f32]),
     "gi_get_light_samples": (C.c_int, [vp, vp, u32]),
@@ -210,6 +216,8 @@ HOST_API = {
     "gih_rs_set_device_light_sampling": (None, [vp, C.c_int]),
     "gih_rs_read_backbuffer_async": (C.c_int, [vp, vp, P(u32)]),
     "gih_rs_wait_reads": (C.c_int, [vp]),
+    "gih_rs_read_backbuffer_reduced": (C.c_int, [vp, vp]),
+    "gih_rs_read_backbuffer_reduced_async": (C.c_int, [vp, vp, P(u32)]),
     "gih_rs_num_light_samples": (u32, [vp]),
     "gih_rs_set_num_light_samples": (None, [vp, u32]),
     "gih_rs_light_samples": (None, [vp, vp]),

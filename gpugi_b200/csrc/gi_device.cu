@@ -6,6 +6,7 @@
 #include "gi_layout.h"
 #include "gi_wavefront.cuh"
 #include "gi_lbvh.cuh"
+#include "gi_comm.cuh"
 
 #include <cuda_runtime.h>
 
@@ -533,6 +534,18 @@ struct GiContext
 	int numSMs = 148;
 	int traceBlocksPerSM = 1, shadeBlocksPerSM = 1, shadeLightBlocksPerSM = 1, shadeEyeBlocksPerSM = 1;
 
+	// multi-GPU read-out (gi_comm.cuh): exchange block shared with the peer ranks over CUDA IPC
+	int commRank = 0, commWorld = 0;          // world 0: no communicator
+	bool commConnected = false;
+	unsigned char* commBlock = nullptr;       // own exchange block
+	unsigned char* commPeer[GI_COMM_MAX_WORLD] = {};
+	int commWidth = 0, commHeight = 0;
+	uint32_t commEpoch = 0;
+	float* commOut[2] = {nullptr, nullptr};   // this rank's rows of the summed image
+	uint32_t* commWords = nullptr;            // [0] arrival counter of k_comm_snapshot, [1] of k_comm_reduce, [2] status (0 = ok)
+	cudaEvent_t commSnapped[2] = {nullptr, nullptr}, commReduced[2] = {nullptr, nullptr};
+	bool commUsed[2] = {false, false};
+
 	// GI_OPT_KERNEL_TIMING: CUDA-event duration of every launch of an iteration, summed per kernel class
 	int kernelTiming = 0;
 	double kernelMs[GI_KERNEL_CLASS_COUNT] = {};
@@ -1054,6 +1067,7 @@ void gi_destroy(GiContext* c)
 	if (!c) return;
 	cudaSetDevice(c->device);
 	cudaDeviceSynchronize();
+	gi_comm_destroy(c); // (uses the copy stream: before it is destroyed)
 	freeScene(c);
 	freeWavefront(c);
 	cudaFree(c->traceWork);
@@ -2118,11 +2132,169 @@ int gi_read_accumulator_async(GiContext* c, float* rgba, uint32_t* iterations_in
 	return GI_OK;
 }
 
+static int commCheckStatus(GiContext* c);
+
 int gi_wait_reads(GiContext* c)
 {
 	if (!c) return GI_ERR_INVALID;
 	if (c->copyStream) GI_CUDA(c, cudaStreamSynchronize(c->copyStream));
+	return commCheckStatus(c);
+}
+
+// ---- multi-GPU read-out (gi_comm.cuh)
+int gi_comm_slice(int height, int rank, int world, uint32_t* first_row, uint32_t* num_rows)
+{
+	if (height <= 0 || world <= 0 || rank < 0 || rank >= world || !first_row || !num_rows) return GI_ERR_INVALID;
+	const uint64_t a = uint64_t(height) * uint64_t(rank) / uint64_t(world), b = uint64_t(height) * uint64_t(rank + 1) / uint64_t(world);
+	*first_row = uint32_t(a); *num_rows = uint32_t(b - a);
 	return GI_OK;
+}
+
+int gi_comm_destroy(GiContext* c)
+{
+	if (!c) return GI_ERR_INVALID;
+	if (c->commWorld == 0) return GI_OK;
+	cudaSetDevice(c->device);
+	if (c->copyStream) cudaStreamSynchronize(c->copyStream);
+	cudaStreamSynchronize(c->stream);
+	for (int r = 0; r < c->commWorld; ++r)
+		if (r != c->commRank && c->commPeer[r]) cudaIpcCloseMemHandle(c->commPeer[r]);
+	for (int r = 0; r < GI_COMM_MAX_WORLD; ++r) c->commPeer[r] = nullptr;
+	cudaFree(c->commBlock); c->commBlock = nullptr;
+	cudaFree(c->commOut[0]); cudaFree(c->commOut[1]); c->commOut[0] = c->commOut[1] = nullptr;
+	cudaFree(c->commWords); c->commWords = nullptr;
+	for (int i = 0; i < 2; ++i)
+	{
+		if (c->commSnapped[i]) cudaEventDestroy(c->commSnapped[i]);
+		if (c->commReduced[i]) cudaEventDestroy(c->commReduced[i]);
+		c->commSnapped[i] = c->commReduced[i] = nullptr; c->commUsed[i] = false;
+	}
+	c->commWorld = 0; c->commConnected = false; c->commEpoch = 0;
+	return GI_OK;
+}
+
+int gi_comm_create(GiContext* c, int rank, int world, GiCommHandle* out_handle)
+{
+	if (!c || !out_handle) return GI_ERR_INVALID;
+	if (world < 1 || world > GI_COMM_MAX_WORLD || rank < 0 || rank >= world) return fail(c, GI_ERR_INVALID, "gi_comm_create: rank / world out of range (1..16 ranks)");
+	if (!c->accum) return fail(c, GI_ERR_INVALID, "gi_comm_create: gi_set_screen_size was not called");
+	static_assert(sizeof(GiCommHandle) >= sizeof(cudaIpcMemHandle_t), "GiCommHandle holds a cudaIpcMemHandle_t");
+	GI_CUDA(c, cudaSetDevice(c->device));
+	gi_comm_destroy(c);
+	const size_t imageBytes = size_t(c->width) * size_t(c->height) * 16u;
+	uint32_t firstRow = 0, rows = 0;
+	gi_comm_slice(c->height, rank, world, &firstRow, &rows);
+	GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->commBlock), GI_COMM_FLAG_BYTES + 2u * imageBytes));
+	GI_CUDA(c, cudaMemset(c->commBlock, 0, GI_COMM_FLAG_BYTES));
+	for (int i = 0; i < 2; ++i) GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->commOut[i]), std::max<size_t>(size_t(rows) * size_t(c->width) * 16u, 16u)));
+	GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->commWords), 4 * sizeof(uint32_t)));
+	GI_CUDA(c, cudaMemset(c->commWords, 0, 4 * sizeof(uint32_t)));
+	for (int i = 0; i < 2; ++i)
+	{
+		GI_CUDA(c, cudaEventCreateWithFlags(&c->commSnapped[i], cudaEventDisableTiming));
+		GI_CUDA(c, cudaEventCreateWithFlags(&c->commReduced[i], cudaEventDisableTiming));
+	}
+	std::memset(out_handle, 0, sizeof(*out_handle));
+	cudaIpcMemHandle_t h;
+	if (world > 1)
+	{
+		GI_CUDA(c, cudaIpcGetMemHandle(&h, c->commBlock));
+		std::memcpy(out_handle, &h, sizeof(h));
+	}
+	c->commRank = rank; c->commWorld = world; c->commWidth = c->width; c->commHeight = c->height;
+	c->commPeer[rank] = c->commBlock;
+	c->commConnected = world == 1;
+	c->commEpoch = 0;
+	return GI_OK;
+}
+
+int gi_comm_connect(GiContext* c, const GiCommHandle* handles)
+{
+	if (!c || !handles) return GI_ERR_INVALID;
+	if (c->commWorld == 0) return fail(c, GI_ERR_INVALID, "gi_comm_connect: gi_comm_create was not called");
+	GI_CUDA(c, cudaSetDevice(c->device));
+	for (int r = 0; r < c->commWorld; ++r)
+	{
+		if (r == c->commRank || c->commPeer[r]) continue;
+		cudaIpcMemHandle_t h;
+		std::memcpy(&h, handles + r, sizeof(h));
+		void* p = nullptr;
+		cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+		if (e != cudaSuccess)
+			return fail(c, GI_ERR_CUDA, std::string("gi_comm_connect: cannot map the exchange block of rank ") + std::to_string(r) + " (" + cudaGetErrorString(e) +
+			                                "); the ranks must be processes on GPUs of one NVLink / PCIe peer group");
+		c->commPeer[r] = static_cast<unsigned char*>(p);
+	}
+	c->commConnected = true;
+	return GI_OK;
+}
+
+static int commRead(GiContext* c, float* rgba_rows, uint32_t* iterations_in_flight, bool drain)
+{
+	if (!c || !rgba_rows) return GI_ERR_INVALID;
+	if (c->commWorld == 0 || !c->commConnected) return fail(c, GI_ERR_INVALID, "reduced read-out: gi_comm_create / gi_comm_connect first");
+	if (!c->accum || c->commWidth != c->width || c->commHeight != c->height) return fail(c, GI_ERR_INVALID, "reduced read-out: the screen size changed since gi_comm_create");
+	GI_CUDA(c, cudaSetDevice(c->device));
+	if (drain)
+	{
+		int fst = flushStream(c);
+		if (fst != GI_OK) return fst;
+	}
+	if (!c->copyStream) GI_CUDA(c, cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
+	const uint32_t epoch = c->commEpoch++;
+	const int i = int(epoch & 1u);
+	const uint32_t numPixels = uint32_t(c->width) * uint32_t(c->height);
+	const size_t imageBytes = size_t(numPixels) * 16u;
+	uint32_t firstRow = 0, rows = 0;
+	gi_comm_slice(c->height, c->commRank, c->commWorld, &firstRow, &rows);
+	CommPeers peers;
+	for (int r = 0; r < GI_COMM_MAX_WORLD; ++r) peers.block[r] = c->commPeer[r];
+	peers.world = c->commWorld; peers.rank = c->commRank;
+	// snapshot e & 1 is still being read by this rank's own reduce of read-out e - 2 until commReduced[i]
+	if (c->commUsed[i]) GI_CUDA(c, cudaStreamWaitEvent(c->stream, c->commReduced[i], 0));
+	k_comm_snapshot<<<unsigned(c->numSMs) * 2u, 256, 0, c->stream>>>(reinterpret_cast<const float4*>(c->accum), peers, epoch, numPixels, imageBytes, c->commWords, c->commWords + 2);
+	++c->launches;
+	GI_CUDA(c, cudaEventRecord(c->commSnapped[i], c->stream));
+	GI_CUDA(c, cudaStreamWaitEvent(c->copyStream, c->commSnapped[i], 0));
+	// a small grid: the kernel may sit next to the persistent trace kernel while it waits for the slowest peer
+	k_comm_reduce<<<unsigned(c->numSMs) / 2u, 256, 0, c->copyStream>>>(peers, epoch, firstRow * uint32_t(c->width), rows * uint32_t(c->width), imageBytes,
+	                                                                   reinterpret_cast<float4*>(c->commOut[i]), c->commWords + 1, c->commWords + 2);
+	++c->launches;
+	GI_CUDA(c, cudaEventRecord(c->commReduced[i], c->copyStream));
+	c->commUsed[i] = true;
+	if (rows) GI_CUDA(c, cudaMemcpyAsync(rgba_rows, c->commOut[i], size_t(rows) * size_t(c->width) * 16u, cudaMemcpyDeviceToHost, c->copyStream));
+	GI_CUDA(c, cudaGetLastError());
+	if (iterations_in_flight)
+	{
+		if (c->bpt.open && c->bpt.streaming) *iterations_in_flight = std::min(c->bpt.count, c->bpt.D + c->bpt.maxLen + 1u);
+		else if (c->run[0].open && c->run[0].streaming && c->run[0].pass == WF_PASS_LIGHT) *iterations_in_flight = c->run[0].count - c->run[0].splatFolded;
+		else *iterations_in_flight = (c->run[0].open && c->run[0].streaming) ? std::min(c->run[0].count, c->run[0].numSlots) : 0u;
+	}
+	return GI_OK;
+}
+
+static int commCheckStatus(GiContext* c)
+{
+	if (c->commWorld == 0 || !c->commWords) return GI_OK;
+	uint32_t status = 0;
+	GI_CUDA(c, cudaMemcpy(&status, c->commWords + 2, sizeof(status), cudaMemcpyDeviceToHost));
+	if (status != 0u)
+	{
+		cudaMemset(c->commWords + 2, 0, sizeof(uint32_t));
+		return fail(c, GI_ERR_CUDA, status == 1u ? "reduced read-out: a peer rank did not publish its snapshot within 4 s (ranks must issue the same sequence of reduced reads)"
+		                                         : "reduced read-out: a peer rank did not finish reading within 4 s");
+	}
+	return GI_OK;
+}
+
+int gi_read_accumulator_reduced_async(GiContext* c, float* rgba_rows, uint32_t* iterations_in_flight) { return commRead(c, rgba_rows, iterations_in_flight, false); }
+
+int gi_read_accumulator_reduced(GiContext* c, float* rgba_rows)
+{
+	int st = commRead(c, rgba_rows, nullptr, true);
+	if (st != GI_OK) return st;
+	GI_CUDA(c, cudaStreamSynchronize(c->copyStream));
+	return commCheckStatus(c);
 }
 
 int gi_accumulator_device(GiContext* c, void** device_ptr, size_t* num_bytes)

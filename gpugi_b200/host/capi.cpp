@@ -252,6 +252,11 @@ int gih_rs_read_backbuffer_async(GihRendererSystem* h, float* rgba, uint32_t* it
 	return h->rs->GetBackbuffer().ReadImageAsync(rgba, iterations_in_flight) ? 0 : 1;
 }
 int gih_rs_wait_reads(GihRendererSystem* h) { return h->rs->GetBackbuffer().WaitReads() ? 0 : 1; }
+int gih_rs_read_backbuffer_reduced(GihRendererSystem* h, float* rgba_rows) { return h->rs->GetBackbuffer().ReadImageReduced(rgba_rows) ? 0 : 1; }
+int gih_rs_read_backbuffer_reduced_async(GihRendererSystem* h, float* rgba_rows, uint32_t* iterations_in_flight)
+{
+	return h->rs->GetBackbuffer().ReadImageReducedAsync(rgba_rows, iterations_in_flight) ? 0 : 1;
+}
 uint32_t gih_rs_num_light_samples(GihRendererSystem* h) { return h->rs->GetNumInitialLightSamples(); }
 void gih_rs_set_num_light_samples(GihRendererSystem* h, uint32_t n) { h->rs->SetNumInitialLightSamples(n); }
 void gih_rs_light_samples(GihRendererSystem* h, GiLightSample* out)

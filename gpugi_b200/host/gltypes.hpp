@@ -22,6 +22,9 @@ namespace gl
 		/// after WaitReads() / the read after next.  iterationsInFlight: submitted iterations not yet in the image.
 		bool ReadImageAsync(float* rgba, uint32_t* iterationsInFlight) const { return gi_read_accumulator_async(m_ctx, rgba, iterationsInFlight) == GI_OK; }
 		bool WaitReads() const { return gi_wait_reads(m_ctx) == GI_OK; }
+		/// Multi-GPU read-out (gi_comm_*): the sum of all ranks' backbuffers, this rank's rows only (gi_comm_slice) -- collective.
+		bool ReadImageReduced(float* rgbaRows) const { return gi_read_accumulator_reduced(m_ctx, rgbaRows) == GI_OK; }
+		bool ReadImageReducedAsync(float* rgbaRows, uint32_t* iterationsInFlight) const { return gi_read_accumulator_reduced_async(m_ctx, rgbaRows, iterationsInFlight) == GI_OK; }
 		GiContext* GetDevice() const { return m_ctx; }
 
 	private:

@@ -46,6 +46,30 @@ def init_process_group(backend=None):
     return dist
 
 
+def exchange_handles(handle, dist=None):
+    """All ranks' 64-byte exchange-block handles in rank order (the transport gi_comm_connect leaves to the caller): one all_gather_object.
+    Works on any backend (gloo on CPU for the tests, nccl on the GPU box -- object collectives go through the process group's store / CPU)."""
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return [bytes(handle)]
+    out = [None] * dist.get_world_size()
+    dist.all_gather_object(out, bytes(handle))
+    assert all(isinstance(h, bytes) and len(h) == 64 for h in out)
+    return out
+
+
+def connect_ranks(device_obj, dist=None):
+    """gi_comm_create + handle exchange + gi_comm_connect for this rank's context; after it, Device.read_accumulator_reduced[_async] /
+    RendererSystem.ReadBackbufferReduced[Async] are available.  Call after the screen size is set.  Returns (rank, world)."""
+    rank, world, _ = env_rank_world()
+    if dist is None or not dist.is_initialized():
+        rank, world = 0, 1
+    handle = device_obj.comm_create(rank, world)
+    device_obj.comm_connect(exchange_handles(handle, dist))
+    if world > 1:
+        dist.barrier()   # every rank has mapped every block before anyone issues the first reduced read
+    return rank, world
+
+
 def reduce_accumulator(accum_tensor, iteration_count, dist=None):
     """Sum-reduce the RGBA32F accumulators and the iteration counts over all ranks, in place.
 

@@ -427,7 +427,38 @@ GI_API int gi_read_accumulator_async(GiContext* ctx, float* rgba, uint32_t* iter
 /* Blocks until every gi_read_accumulator_async copy has landed. */
 GI_API int gi_wait_reads(GiContext* ctx);
 
-/* Device address of the accumulator (for the NCCL sum-reduce across ranks). */
+/* ------------------------------------------------------------------ multi-GPU read-out
+ * One process per GPU; rank r of W renders the iterations k = r (mod W) (FrameSeed = WangHash(k), renderersystem.cpp:101) into its own
+ * accumulator, and the accumulators only meet at read-out: Application::SaveImage's glGetTextureImage of ONE backbuffer (application.cpp:411,
+ * renderersystem.cpp:224) becomes a reduce-scatter over NVLink peer memory in which every rank sums and copies out 1/W of the image
+ * (csrc/gi_comm.cuh).  The ranks' exchange blocks are plain device allocations shared through CUDA IPC handles; HOW the 64-byte handles
+ * travel between the processes is the caller's business (MPI, a pipe, torch.distributed -- gpugi_b200/parallel.py uses all_gather). */
+typedef struct GiCommHandle { unsigned char opaque[64]; } GiCommHandle;
+
+/* Rows [*first_row, *first_row + *num_rows) of a `height`-row image belong to `rank` of `world`.  Pure function, no context. */
+GI_API int gi_comm_slice(int height, int rank, int world, uint32_t* first_row, uint32_t* num_rows);
+
+/* Allocates this rank's exchange block (two snapshots of the current screen size + flags) and returns its handle.  Call after
+ * gi_set_screen_size; a later size change needs a new communicator.  world == 1 is allowed (no peer, the handle is unused). */
+GI_API int gi_comm_create(GiContext* ctx, int rank, int world, GiCommHandle* out_handle);
+
+/* Maps the peers' exchange blocks: handles[r] = the handle rank r got from gi_comm_create (world entries; the own entry is ignored). */
+GI_API int gi_comm_connect(GiContext* ctx, const GiCommHandle* handles);
+
+/* COLLECTIVE (every rank issues the same sequence of reduced reads): the sum over all ranks of the accumulators, this rank's rows only,
+ * width * num_rows * 4 floats to `rgba_rows` (host memory).  Summation runs in rank order on every rank: the result equals the sequential
+ * sum rank 0 + rank 1 + ... of the per-rank images bit for bit.  Drains an open stream first and returns when the rows are on the host. */
+GI_API int gi_read_accumulator_reduced(GiContext* ctx, float* rgba_rows);
+
+/* The same without draining or waiting (the multi-GPU gi_read_accumulator_async): snapshot in stream order, reduce + copy on the second
+ * stream while the next waves run; `rgba_rows` (pinned) is valid after gi_wait_reads, which also reports a peer that never arrived.
+ * *iterations_in_flight as for gi_read_accumulator_async (the same on every rank when all ranks submit in lockstep). */
+GI_API int gi_read_accumulator_reduced_async(GiContext* ctx, float* rgba_rows, uint32_t* iterations_in_flight);
+
+/* Unmaps the peers and frees the exchange block (also done by gi_destroy). */
+GI_API int gi_comm_destroy(GiContext* ctx);
+
+/* Device address of the accumulator (for callers that bring their own collective, e.g. an NCCL all-reduce). */
 GI_API int gi_accumulator_device(GiContext* ctx, void** device_ptr, size_t* num_bytes);
 
 /* Replaces TextureMSE::ComputeCurrentMSE (texturemse.cpp:39-66, sqerror.frag:16-17):

@@ -83,6 +83,10 @@ GI_API void gih_rs_set_streaming(GihRendererSystem* rs, int streaming);       /*
 GI_API void gih_rs_set_device_light_sampling(GihRendererSystem* rs, int on_device); /* RendererSystem::SetDeviceLightSampling (gi_generate_light_samples) */
 GI_API int gih_rs_read_backbuffer_async(GihRendererSystem* rs, float* rgba, uint32_t* iterations_in_flight); /* Texture2D::ReadImageAsync */
 GI_API int gih_rs_wait_reads(GihRendererSystem* rs);
+/* multi-GPU: Texture2D::ReadImageReduced / ReadImageReducedAsync = gi_read_accumulator_reduced[_async] on the backbuffer (collective; the
+   communicator is set up on the device context: gi_comm_create / gi_comm_connect through gih_rs_device) */
+GI_API int gih_rs_read_backbuffer_reduced(GihRendererSystem* rs, float* rgba_rows);
+GI_API int gih_rs_read_backbuffer_reduced_async(GihRendererSystem* rs, float* rgba_rows, uint32_t* iterations_in_flight);
 GI_API uint32_t gih_rs_num_light_samples(GihRendererSystem* rs);
 GI_API void gih_rs_set_num_light_samples(GihRendererSystem* rs, uint32_t n);   /* RendererSystem::SetNumInitialLightSamples (renderersystem.hpp:124) */
 GI_API void gih_rs_light_samples(GihRendererSystem* rs, GiLightSample* out);
