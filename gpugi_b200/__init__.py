@@ -247,6 +247,13 @@ class Device:
         self._check(capi.dev.gi_get_light_samples(self._c, C.cast(_vp(out), C.POINTER(capi.GiLightSample)), int(n)), "gi_get_light_samples")
         return out
 
+    def get_light_cache(self, capacity):
+        """gi_get_light_cache -> (entries as (capacity, 16) float32, NumLightCacheEntries counter)."""
+        out = np.zeros((int(capacity), 16), dtype=np.float32)
+        n = C.c_uint32()
+        self._check(capi.dev.gi_get_light_cache(self._c, _vp(out), int(capacity), C.byref(n)), "gi_get_light_cache")
+        return out, int(n.value)
+
     def set_environment_constant(self, srgb8):
         """1x1 cube with the same sRGB8 colour on all faces (the reference default is black)."""
         face = np.array([srgb8[0], srgb8[1], srgb8[2], 255], dtype=np.uint8)

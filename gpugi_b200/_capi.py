@@ -94,7 +94,7 @@ class GiIterationParams(C.Structure):
 class GiCounters(C.Structure):
     _fields_ = [("closest_rays", u64), ("any_rays", u64), ("camera_paths", u64), ("light_paths", u64),
                 ("shaded_vertices", u64), ("splats", u64), ("exact_fallback_rays", u64), ("node_tests", u64),
-                ("triangle_tests", u64), ("light_cache_entries", u32), ("light_path_length_sum", u32)]
+                ("triangle_tests", u64), ("light_cache_entries", u32), ("light_path_length_sum", u32), ("inner_node_steps", u64), ("leaf_steps", u64)]
 
 
 class GiKernelTimes(C.Structure):
@@ -163,6 +163,7 @@ DEVICE_API = {
     "gi_set_light_tables": (C.c_int, [vp, vp]),
     "gi_generate_light_samples": (C.c_int, [vp, P(u64), u32, f32]),
     "gi_get_light_samples": (C.c_int, [vp, vp, u32]),
+    "gi_get_light_cache": (C.c_int, [vp, vp, u32, P(u32)]),
     "gi_build_hierarchy": (C.c_int, [vp, vp, u32, vp, vp, u32, vp, vp, vp, P(u32), P(u32)]),
     "gi_accumulator_device": (C.c_int, [vp, P(vp), P(C.c_size_t)]),
     "gi_compute_mse": (C.c_int, [vp, vp, u32, P(f32)]),

@@ -25,13 +25,14 @@ using namespace gik;
 // =====================================================================================================
 
 // 64-bit device counters (GiCounters order)
-enum { CNT_CLOSEST = 0, CNT_ANY, CNT_CAMERA, CNT_LIGHT, CNT_SHADED, CNT_SPLATS, CNT_FALLBACK, CNT_NODES, CNT_TRIS, CNT_COUNT };
+enum { CNT_CLOSEST = 0, CNT_ANY, CNT_CAMERA, CNT_LIGHT, CNT_SHADED, CNT_SPLATS, CNT_FALLBACK, CNT_NODES, CNT_TRIS, CNT_INNER_STEPS, CNT_LEAF_STEPS, CNT_COUNT };
+static_assert(int(CNT_COUNT) == int(WFC_COUNT), "device counter slots = per-warp counter slots");
 
 __device__ __forceinline__ void flushCounters(unsigned long long* counters, const PathCounters& pc, const TraceStats& st)
 {
 	// warp-aggregate, one atomic per warp and counter
 	const unsigned mask = __activemask();
-	unsigned v[CNT_COUNT] = {pc.closestRays, pc.anyRays, pc.cameraPaths, pc.lightPaths, pc.shadedVertices, pc.splats, pc.fallbackRays, st.nodes, st.tris};
+	unsigned v[CNT_COUNT] = {pc.closestRays, pc.anyRays, pc.cameraPaths, pc.lightPaths, pc.shadedVertices, pc.splats, pc.fallbackRays, st.nodes, st.tris, 0u, 0u};
 	const int lane = threadIdx.x & 31;
 	const int leader = __ffs(mask) - 1;
 #pragma unroll
@@ -298,7 +299,7 @@ __global__ void __launch_bounds__(WF_SHADE_THREADS, WF_SHADE_MIN_BLOCKS) k_wf_sh
 {
 	uint32_t* counts = wfCounts(w, w.wave);
 	const uint32_t n = w.numCam + counts[0];
-	unsigned cnt[WFC_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+	unsigned cnt[WFC_COUNT] = {};
 	for (;;)
 	{
 		uint32_t base = 0;
@@ -317,7 +318,7 @@ __global__ void __launch_bounds__(256) k_wf_generate_light(WfFrame w, unsigned l
 	PathCounters pc = {};
 	const uint32_t stride = gridDim.x * blockDim.x;
 	for (uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x; gid < w.numPaths; gid += stride) wfGenerateLight(w, gid, pc);
-	unsigned cnt[WFC_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+	unsigned cnt[WFC_COUNT] = {};
 	wfAddCounters(cnt, pc);
 	flushWarpCounters(counters, cnt, WFC_COUNT);
 }
@@ -336,7 +337,7 @@ __global__ void __launch_bounds__(WF_SHADE_THREADS) k_wf_shade_light(WfFrame w, 
 		const uint32_t slot = base + laneId();
 		wfShadeLight(w, w.rayBase + slot, slot < n, pc);
 	}
-	unsigned cnt[WFC_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+	unsigned cnt[WFC_COUNT] = {};
 	wfAddCounters(cnt, pc);
 	flushWarpCounters(counters, cnt, WFC_COUNT);
 }
@@ -355,7 +356,7 @@ __global__ void __launch_bounds__(WF_SHADE_THREADS) k_wf_shade_eye(WfFrame w, un
 		const uint32_t slot = base + laneId();
 		wfShadeEye(w, w.rayBase + slot, slot < n, pc);
 	}
-	unsigned cnt[WFC_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+	unsigned cnt[WFC_COUNT] = {};
 	wfAddCounters(cnt, pc);
 	flushWarpCounters(counters, cnt, WFC_COUNT);
 }
@@ -1558,6 +1559,26 @@ int gi_get_light_samples(GiContext* c, GiLightSample* out, uint32_t n)
 	return GI_OK;
 }
 
+int gi_get_light_cache(GiContext* c, void* entries, uint32_t max_entries, uint32_t* num_entries)
+{
+	if (!c || !num_entries) return GI_ERR_INVALID;
+	int fst = flushStream(c);
+	if (fst != GI_OK) return fst;
+	if (!c->lightCache) return fail(c, GI_ERR_INVALID, "gi_get_light_cache: no light cache allocated");
+	GI_CUDA(c, cudaSetDevice(c->device));
+	uint32_t counters[2] = {0u, 0u};
+	GI_CUDA(c, cudaMemcpyAsync(counters, c->bptCounters, sizeof(counters), cudaMemcpyDeviceToHost, c->stream));
+	GI_CUDA(c, cudaStreamSynchronize(c->stream));
+	*num_entries = counters[0];
+	const uint32_t n = std::min(std::min(counters[0], c->lightCacheCapacity), max_entries);
+	if (entries && n)
+	{
+		GI_CUDA(c, cudaMemcpyAsync(entries, c->lightCache, size_t(n) * 64u, cudaMemcpyDeviceToHost, c->stream));
+		GI_CUDA(c, cudaStreamSynchronize(c->stream));
+	}
+	return GI_OK;
+}
+
 int gi_alloc_light_cache(GiContext* c, uint32_t capacity)
 {
 	if (!c || capacity == 0) return fail(c, GI_ERR_INVALID, "gi_alloc_light_cache: zero capacity");
@@ -2354,6 +2375,7 @@ int gi_get_counters(GiContext* c, GiCounters* out)
 	out->closest_rays = h[CNT_CLOSEST]; out->any_rays = h[CNT_ANY]; out->camera_paths = h[CNT_CAMERA]; out->light_paths = h[CNT_LIGHT];
 	out->shaded_vertices = h[CNT_SHADED]; out->splats = h[CNT_SPLATS]; out->exact_fallback_rays = h[CNT_FALLBACK];
 	out->node_tests = h[CNT_NODES]; out->triangle_tests = h[CNT_TRIS];
+	out->inner_node_steps = h[CNT_INNER_STEPS]; out->leaf_steps = h[CNT_LEAF_STEPS];
 	out->light_cache_entries = b[0]; out->light_path_length_sum = b[1];
 	return GI_OK;
 }

@@ -8,7 +8,7 @@
 namespace gik {
 
 // per-thread work counters, flushed per warp at kernel end (order of GiCounters / CNT_* in gi_device.cu)
-enum { WFC_CLOSEST = 0, WFC_ANY, WFC_CAMERA, WFC_LIGHT, WFC_SHADED, WFC_SPLATS, WFC_FALLBACK, WFC_NODES, WFC_TRIS, WFC_COUNT };
+enum { WFC_CLOSEST = 0, WFC_ANY, WFC_CAMERA, WFC_LIGHT, WFC_SHADED, WFC_SPLATS, WFC_FALLBACK, WFC_NODES, WFC_TRIS, WFC_INNER_STEPS, WFC_LEAF_STEPS, WFC_COUNT };
 
 // STEPS = false drops the box / triangle test counters (GiCounters::node_tests, triangle_tests) from the hot loop.
 template <bool STEPS>
@@ -16,7 +16,7 @@ struct WfCounters
 {
 	unsigned v[WFC_COUNT];
 	GI_HD WfCounters() { for (int i = 0; i < WFC_COUNT; ++i) v[i] = 0u; }
-	template <int I> GI_HD void add(unsigned n) { if (STEPS || (I != WFC_NODES && I != WFC_TRIS)) v[I] += n; }
+	template <int I> GI_HD void add(unsigned n) { if (STEPS || (I != WFC_NODES && I != WFC_TRIS && I != WFC_INNER_STEPS && I != WFC_LEAF_STEPS)) v[I] += n; }
 };
 
 // ------------------------------------------------------------------ trace core
@@ -396,7 +396,7 @@ GI_HD void wfInnerStep(WfLane& L, const DScene& s, const STK& stack, CNT& cnt)
 	const F4 ny = ld4(reinterpret_cast<const F4*>(nb + L.offNear[1])), fy = ld4(reinterpret_cast<const F4*>(nb + (L.offNear[1] ^ 4u)));
 	const F4 nz = ld4(reinterpret_cast<const F4*>(nb + L.offNear[2])), fz = ld4(reinterpret_cast<const F4*>(nb + (L.offNear[2] ^ 4u)));
 	const F4 lk = ld4(reinterpret_cast<const F4*>(nb + 24));
-	cnt.template add<WFC_NODES>(4u);
+	cnt.template add<WFC_NODES>(4u); cnt.template add<WFC_INNER_STEPS>(1u);
 #define WF_CHILD(m, out) { \
 		const float nn = fmaxf(wfMax3(wfFma(nx.m, L.cellInv.x, L.biasNear.x), wfFma(ny.m, L.cellInv.y, L.biasNear.y), wfFma(nz.m, L.cellInv.z, L.biasNear.z)), 0.0f); \
 		const float ff = fminf(wfMin3(wfFma(fx.m, L.cellInv.x, L.biasFar.x), wfFma(fy.m, L.cellInv.y, L.biasFar.y), wfFma(fz.m, L.cellInv.z, L.biasFar.z)), L.limit); \
@@ -434,7 +434,7 @@ GI_HD void wfInnerStep(WfLane& L, const DScene& s, const STK& stack, CNT& cnt)
 {
 	const U8 a = ld8(s.qNodes + 16 * size_t(L.node));
 	const U8 b = ld8(s.qNodes + 16 * size_t(L.node) + 8);
-	cnt.template add<WFC_NODES>(4u);
+	cnt.template add<WFC_NODES>(4u); cnt.template add<WFC_INNER_STEPS>(1u);
 	float f0, f1, f2, f3v;
 	if (!wfSlabTest(L, a.v[0], a.v[1], a.v[2], f0)) f0 = GI_INF;
 	if (!wfSlabTest(L, a.v[3], a.v[4], a.v[5], f1)) f1 = GI_INF;
@@ -491,7 +491,7 @@ GI_HD void wfInnerStep(WfLane& L, const DScene& s, const STK& stack, CNT& cnt)
 {
 	// one 32-byte record, one 256-bit load: (c0.x, c0.y, c0.z, c1.x, c1.y, c1.z, child0, child1)
 	const U8 n = ld8(s.qNodes + 8 * size_t(L.node));
-	cnt.template add<WFC_NODES>(2u);
+	cnt.template add<WFC_NODES>(2u); cnt.template add<WFC_INNER_STEPS>(1u);
 	float f0, f1;
 	const bool h0 = wfSlabTest(L, n.v[0], n.v[1], n.v[2], f0);
 	const bool h1 = wfSlabTest(L, n.v[3], n.v[4], n.v[5], f1);
@@ -533,6 +533,7 @@ GI_HD void wfLeafStep(WfLane& L, const DScene& s, const STK& stack, WfCand* cand
 	// One 96-byte record: both triangles + the leaf node's own box in the .w components; all six loads are issued first.
 	F4 v[6];
 	ld8x3(s.leafPos + 6 * size_t(leaf), v);
+	cnt.template add<WFC_LEAF_STEPS>(1u);
 	// The reference visits this leaf iff its own node box passes the exact-zone test with first <= rayLength
 	// (traceray.glsl:64-69); a triangle of an unvisited leaf does not count.  Most leaf visits hit no triangle at all, so the
 	// box test (three IEEE divisions + slab test) is made lazily: at the first triangle hit, with the limit the lane had when it

@@ -264,6 +264,9 @@ typedef struct GiCounters {
 	uint64_t triangle_tests;     /* triangle tests actually executed                       */
 	uint32_t light_cache_entries;/* NumLightCacheEntries after the last light pass         */
 	uint32_t light_path_length_sum; /* LightPathLengthSum (warm-up)                        */
+	/* with GI_OPT_COUNT_STEPS, the record loads of the wavefront walk (DESIGN.md "Data layout"): what the kernel's own layout touches */
+	uint64_t inner_node_steps;   /* inner-node records fetched: 64 B each (one 4-wide node = 4 of the node_tests)                   */
+	uint64_t leaf_steps;         /* leaf records fetched: 96 B each (both triangles + the leaf's own box = 1 of the node_tests)     */
 } GiCounters;
 
 /* ------------------------------------------------------------------ lifecycle */
@@ -388,6 +391,11 @@ GI_API int gi_set_light_tables(GiContext* ctx, const GiLightTables* tables);
 GI_API int gi_generate_light_samples(GiContext* ctx, uint64_t* rng_state, uint32_t n, float position_bias);
 /* The current light-sample set (host or device generated), for inspection. */
 GI_API int gi_get_light_samples(GiContext* ctx, GiLightSample* out, uint32_t n);
+
+/* The light cache as the last non-streamed BPT iteration left it (LightCacheEntry records of 64 bytes, lightcache.glsl:1-16: the SSBO of
+ * bidirectionalpathtracer.cpp:116-131) and its NumLightCacheEntries counter, for inspection: copies min(counter, capacity, max_entries)
+ * entries to `entries` (host) and stores the counter (which may exceed the capacity: later vertices were dropped) in *num_entries. */
+GI_API int gi_get_light_cache(GiContext* ctx, void* entries, uint32_t max_entries, uint32_t* num_entries);
 
 /* Device-side replacement of Chunk::buildHierarchy + remapNodePointers + computeBVHAABoxes (bim_chunk.cpp:227-242, bim_sahspilt.cpp:27-151,
  * bim_hierarchy.cpp:8-50,238-252) for a mesh that comes without a hierarchy: an LBVH (Morton order of the triangle centroids, consecutive

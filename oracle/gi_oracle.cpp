@@ -1382,9 +1382,32 @@ OR_API int or_render_lpt(const GiSceneDesc* desc, const GiCamera* cam, int w, in
 // SAVE_LIGHT_CACHE, eye pass.  warmup != 0 runs only the SAVE_LIGHT_CACHE_WARMUP light pass (:90-93).
 // cache: capacity * 64 bytes scratch (may be NULL for warm-up).  out_counts[0] = NumLightCacheEntries,
 // out_counts[1] = LightPathLengthSum.
+static int renderBpt(const GiSceneDesc* desc, const GiCamera* cam, int w, int h, const GiLightSample* ls, int nls, uint32_t frameSeed, int maxLen,
+                     int numRaysPerLightSample, uint32_t capacity, void* cache, int warmup, const OrRegion* region, float* accum, uint32_t out_counts[2],
+                     OrCounters* counters, const void* eyeCache, uint32_t eyeCacheEntries);
+
 OR_API int or_render_bpt(const GiSceneDesc* desc, const GiCamera* cam, int w, int h, const GiLightSample* ls, int nls, uint32_t frameSeed, int maxLen,
                          int numRaysPerLightSample, uint32_t capacity, void* cache, int warmup, const OrRegion* region, float* accum, uint32_t out_counts[2],
                          OrCounters* counters)
+{
+	return renderBpt(desc, cam, w, h, ls, nls, frameSeed, maxLen, numRaysPerLightSample, capacity, cache, warmup, region, accum, out_counts, counters, nullptr, 0u);
+}
+
+// The same iteration, but the eye pass connects to a light cache GIVEN by the caller (capacity x 64 bytes in LightCacheEntry layout, lightcache.glsl:1-16,
+// + the NumLightCacheEntries counter that goes with it) instead of the one the light pass above just wrote.  The light pass still runs (its
+// camera-connection splats belong to the image).  Which slot a light vertex lands in depends on the scheduling of the atomic counter
+// (lighttracer.comp:23-45), so two implementations only produce the same eye pass when they read the same cache: this is the deterministic
+// half of the BPT parity test.
+OR_API int or_render_bpt_with_cache(const GiSceneDesc* desc, const GiCamera* cam, int w, int h, const GiLightSample* ls, int nls, uint32_t frameSeed, int maxLen,
+                                    int numRaysPerLightSample, uint32_t capacity, void* cache, const void* eye_cache, uint32_t eye_cache_entries,
+                                    const OrRegion* region, float* accum, uint32_t out_counts[2], OrCounters* counters)
+{
+	return renderBpt(desc, cam, w, h, ls, nls, frameSeed, maxLen, numRaysPerLightSample, capacity, cache, 0, region, accum, out_counts, counters, eye_cache, eye_cache_entries);
+}
+
+static int renderBpt(const GiSceneDesc* desc, const GiCamera* cam, int w, int h, const GiLightSample* ls, int nls, uint32_t frameSeed, int maxLen,
+                     int numRaysPerLightSample, uint32_t capacity, void* cache, int warmup, const OrRegion* region, float* accum, uint32_t out_counts[2],
+                     OrCounters* counters, const void* eyeCache, uint32_t eyeCacheEntries)
 {
 	Scene s = makeScene(desc);
 	Frame f = makeFrame(s, cam, w, h, ls, nls, frameSeed, maxLen, accum);
@@ -1406,6 +1429,11 @@ OR_API int or_render_bpt(const GiSceneDesc* desc, const GiCamera* cam, int w, in
 	}
 	if (out_counts) { out_counts[0] = lc.numEntries; out_counts[1] = lc.pathLengthSum; }
 	if (warmup) return 0;
+	if (eyeCache)
+	{
+		lc.entries = static_cast<LightCacheEntry*>(const_cast<void*>(eyeCache));
+		lc.numEntries = eyeCacheEntries;
+	}
 	int gw = w / 8, gh = h / 8;
 	int x0 = 0, y0 = 0, x1 = gw * 8, y1 = gh * 8;
 	if (region && (region->x1 > region->x0)) { x0 = std::max(x0, region->x0); y0 = std::max(y0, region->y0); x1 = std::min(x1, region->x1); y1 = std::min(y1, region->y1); }

@@ -66,6 +66,8 @@ lib.or_render_lpt.restype = C.c_int
 lib.or_render_lpt.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_int, u32, C.c_int, C.c_int, u32, u32, C.c_int, vp, vp]
 lib.or_render_bpt.restype = C.c_int
 lib.or_render_bpt.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_int, u32, C.c_int, C.c_int, u32, vp, C.c_int, vp, vp, vp, vp]
+lib.or_render_bpt_with_cache.restype = C.c_int
+lib.or_render_bpt_with_cache.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_int, u32, C.c_int, C.c_int, u32, vp, vp, u32, vp, vp, vp, vp]
 lib.or_camera.restype = None
 lib.or_camera.argtypes = [vp, vp, vp, f32, f32, C.c_int, C.c_int, vp]
 lib.or_light_sampler_create.restype = vp
@@ -203,7 +205,8 @@ def render_lpt(scene_desc, cam, w, h, light_samples, frame_seed, num_rays_per_li
     return accum, cnt.as_dict()
 
 
-def render_bpt(scene_desc, cam, w, h, light_samples, frame_seed, num_rays_per_light_sample, capacity, max_len=16, warmup=False, region=None, accum=None):
+def render_bpt(scene_desc, cam, w, h, light_samples, frame_seed, num_rays_per_light_sample, capacity, max_len=16, warmup=False, region=None, accum=None,
+               return_cache=False):
     ls = np.ascontiguousarray(light_samples, dtype=LIGHT_SAMPLE_DTYPE)
     if accum is None:
         accum = np.zeros((h, w, 4), dtype=np.float32)
@@ -214,6 +217,27 @@ def render_bpt(scene_desc, cam, w, h, light_samples, frame_seed, num_rays_per_li
     lib.or_render_bpt(C.addressof(scene_desc), _cam_ptr(cam), w, h, _p(ls), ls.shape[0], frame_seed & 0xFFFFFFFF, max_len, int(num_rays_per_light_sample),
                       int(capacity), _p(cache) if cache is not None else None, 1 if warmup else 0, C.addressof(reg) if reg is not None else None, _p(accum),
                       _p(counts), C.addressof(cnt))
+    if return_cache:
+        return accum, cnt.as_dict(), (int(counts[0]), int(counts[1])), cache.reshape(-1, 16)
+    return accum, cnt.as_dict(), (int(counts[0]), int(counts[1]))
+
+
+def render_bpt_with_cache(scene_desc, cam, w, h, light_samples, frame_seed, num_rays_per_light_sample, capacity, eye_cache, eye_cache_entries, max_len=16,
+                          region=None, accum=None):
+    """One BPT iteration whose eye pass reads `eye_cache` (capacity x 16 floats, LightCacheEntry layout) with `eye_cache_entries` as its
+    NumLightCacheEntries counter -- e.g. the cache another implementation's light pass wrote."""
+    ls = np.ascontiguousarray(light_samples, dtype=LIGHT_SAMPLE_DTYPE)
+    if accum is None:
+        accum = np.zeros((h, w, 4), dtype=np.float32)
+    cnt = OrCounters()
+    counts = np.zeros(2, dtype=np.uint32)
+    own = np.zeros(int(capacity) * 16, dtype=np.float32)
+    given = np.ascontiguousarray(eye_cache, dtype=np.float32).reshape(-1)
+    assert given.size >= int(capacity) * 16
+    reg = _region(region)
+    lib.or_render_bpt_with_cache(C.addressof(scene_desc), _cam_ptr(cam), w, h, _p(ls), ls.shape[0], frame_seed & 0xFFFFFFFF, max_len, int(num_rays_per_light_sample),
+                                 int(capacity), _p(own), _p(given), int(eye_cache_entries), C.addressof(reg) if reg is not None else None, _p(accum), _p(counts),
+                                 C.addressof(cnt))
     return accum, cnt.as_dict(), (int(counts[0]), int(counts[1]))
 
 

@@ -1,0 +1,242 @@
+"""Parity at the BASELINE.json configurations (round 2; VERDICT r1 "next" item 1): the config's OWN renderer against the oracle on the
+stand-in scenes, the deterministic half of the bidirectional path tracer (eye pass on a given light cache), C1 at its stated size
+(box1 512x512, 64 iterations), one 1080p C2 iteration on 64 stripes, and the 2^22-ray batch of SURVEY 8d on the full-size Sponza-shaped scene.
+All through the C ABI / the Renderer mirror; the oracle is only the checker."""
+import numpy as np
+import pytest
+
+from tests.conftest import make_ray_batch, pixel_mismatch_fraction
+
+pytestmark = pytest.mark.gpu
+
+
+def _device(g, scene, W, H, cam):
+    dev = g.Device(0)
+    dev.upload_scene(scene)
+    dev.set_screen_size(W, H)
+    dev.set_camera(g.camera_params(cam["pos"], cam["lookat"], cam["fov"], W, H))
+    dev.set_option(g.GI_OPT_TEXTURE_FILTER, 1)
+    return dev
+
+
+def _bpt_iteration_vs_oracle_on_the_same_cache(g, orc, scene, cam, W, H, seed_index, path_length=16, scheduler=None):
+    """One BPT iteration on the GPU; its light cache is read back and handed to the oracle's eye pass.  Everything in the image is then a
+    deterministic function of (scene, camera, light samples, FrameSeed, cache): compared at the path tracer's tolerance."""
+    dev = _device(g, scene, W, H, cam)
+    if scheduler is not None:
+        dev.set_option(g.GI_OPT_SCHEDULER, scheduler)
+    nls = 128
+    nr = max(64, (W * H // nls // 64) * 64)
+    samples = g.LightSampler(scene).generate(nls)
+    dev.set_light_samples(samples)
+    dev.render_iteration(g.GI_RENDERER_BPT, 7, path_length, num_rays_per_light_sample=nr, warmup=1)
+    n0 = dev.counters()["light_cache_entries"]
+    cap = n0 + n0 // 4
+    dev.alloc_light_cache(cap)
+    seed = g.wang_hash(seed_index)
+    dev.clear(); dev.reset_counters()
+    dev.render_iteration(g.GI_RENDERER_BPT, seed, path_length, num_rays_per_light_sample=nr, light_cache_capacity=cap)
+    img = dev.read_accumulator(W, H)
+    cnt = dev.counters()
+    cache, entries = dev.get_light_cache(cap)
+    assert entries == cnt["light_cache_entries"] and nls * nr < entries <= cap
+    camp = np.frombuffer(g.camera_params(cam["pos"], cam["lookat"], cam["fov"], W, H), dtype=np.float32)
+    ref, rc, (ref_entries, _) = orc.render_bpt_with_cache(scene.desc, camp, W, H, samples, seed, nr, cap, cache, entries, path_length)
+    dev.close()
+    # the light pass is deterministic: same number of light vertices, same splats
+    assert ref_entries == entries
+    assert cnt["light_paths"] == rc["light_paths"] and cnt["camera_paths"] == rc["camera_paths"]
+    assert abs(cnt["splats"] - rc["splats"]) <= rc["splats"] // 100 + 2
+    # the GPU's cache holds the same light vertices as the oracle's own, in another order: compare as multisets of (position, flux)
+    return img, ref, cache, entries
+
+
+@pytest.mark.parametrize("scheduler", ["wavefront", "megakernel"])
+def test_bidirectional_eye_pass_on_the_gpu_cache_matches_oracle(g, orc, scenes, box1, scheduler):
+    """pathtracer_bidir.comp:16-251 (MIS weights, connection, emissive term, reverse pdf): GPU vs oracle on the SAME light cache, box1 96x96."""
+    W = H = 96
+    sched = g.GI_SCHEDULER_WAVEFRONT if scheduler == "wavefront" else g.GI_SCHEDULER_MEGAKERNEL
+    for k in (0, 5):
+        img, ref, cache, entries = _bpt_iteration_vs_oracle_on_the_same_cache(g, orc, box1, scenes.BOX1_CAMERA, W, H, k, scheduler=sched)
+        assert np.all(img[..., 3] == 1.0) and img[..., :3].sum() > 0
+        bad = pixel_mismatch_fraction(img, ref, 1e-2)
+        assert bad < 0.02, "iteration %d: %.2f %% of the pixels differ by more than 1 %%" % (k, 100 * bad)
+        e_img, e_ref = float(img[..., :3].sum()), float(ref[..., :3].sum())
+        assert abs(e_img - e_ref) <= 2e-3 * e_ref
+
+
+def test_bidirectional_cache_holds_the_oracles_light_vertices(g, orc, scenes, box1):
+    """The light pass (lighttracer.comp:49-193 with SAVE_LIGHT_CACHE): the GPU's cache is the oracle's cache up to the order of the slots."""
+    W = H = 64
+    cam = scenes.BOX1_CAMERA
+    dev = _device(g, box1, W, H, cam)
+    nls, nr = 128, max(64, (W * H // 128 // 64) * 64)
+    samples = g.LightSampler(box1).generate(nls)
+    dev.set_light_samples(samples)
+    cap = nls * nr * 4
+    dev.alloc_light_cache(cap)
+    seed = g.wang_hash(3)
+    dev.render_iteration(g.GI_RENDERER_BPT, seed, 16, num_rays_per_light_sample=nr, light_cache_capacity=cap)
+    cache, entries = dev.get_light_cache(cap)
+    dev.close()
+    camp = np.frombuffer(g.camera_params(cam["pos"], cam["lookat"], cam["fov"], W, H), dtype=np.float32)
+    _, _, counts, own = orc.render_bpt(box1.desc, camp, W, H, samples, seed, nr, cap, 16, return_cache=True)
+    assert counts[0] == entries and nls * nr < entries < cap
+    # the first nls * nr slots are the light origins, written by path index: identical in place (lighttracer.comp:56-61, resetcounter.comp:10)
+    n0 = nls * nr
+    assert np.allclose(cache[:n0], own[:n0], rtol=1e-6, atol=1e-7)
+    # the others are the same light vertices in a scheduling-dependent order: every column has the same multiset of values (up to the last
+    # bits of the transcendentals in the flux)
+    a, b = np.sort(cache[n0:entries], axis=0), np.sort(own[n0:entries], axis=0)
+    assert np.allclose(a, b, rtol=2e-4, atol=1e-6)
+
+
+def test_c3_stand_in_bidirectional_vs_oracle(g, orc, scenes, tmp_path):
+    """BASELINE config 3's renderer on its stand-in scene (bathroom-like: glass, mirror, 2 emissive materials, textures), 160x96."""
+    sc = scenes.make_bathroom_like(str(tmp_path), 30000, 64, detail=0.25)
+    W, H = 160, 96
+    img, ref, cache, entries = _bpt_iteration_vs_oracle_on_the_same_cache(g, orc, sc, scenes.BATHROOM_CAMERA, W, H, 1)
+    assert np.isfinite(img).all() and img[..., :3].mean() > 0
+    bad = pixel_mismatch_fraction(img, ref, 1e-2)
+    assert bad < 0.03, "%.2f %% of the pixels differ by more than 1 %%" % (100 * bad)
+    e_img, e_ref = float(img[..., :3].sum()), float(ref[..., :3].sum())
+    assert abs(e_img - e_ref) <= 5e-3 * e_ref
+
+
+def test_c4_stand_in_lighttracer_vs_oracle(g, orc, scenes, tmp_path):
+    """BASELINE config 4's renderer on its stand-in scene (villa-like: glass + water refraction, 6 point lights), 160x96, through the
+    Renderer mirror incl. DispatchShowLightCacheShader: same light paths, same splats; only the order of the float atomics differs."""
+    from tests.test_gpu_renderers import _rs
+    sc = scenes.make_villa_like(str(tmp_path), 60000, 64, detail=0.25)
+    W, H = 160, 96
+    rs = _rs(g, scenes, sc, "LPT", W, H, cam=scenes.VILLA_CAMERA)
+    info = rs.GetRendererInfo()
+    nr = info["num_rays_per_light_sample"]
+    acc = np.zeros((H, W, 4), np.float32)
+    rc_tot = {}
+    N = 3
+    for k in range(N):
+        samples, seed, cam = rs.GetInitialLightSamples(), rs.GetFrameSeed(), rs.GetCamera()
+        rs.Draw()
+        acc, rc = orc.render_lpt(sc.desc, cam, W, H, samples, seed, nr, 16, show_light_caches=True, accum=acc)
+        for key, v in rc.items():
+            rc_tot[key] = rc_tot.get(key, 0) + v
+    img = rs.ReadBackbuffer()
+    cnt = rs.device.counters()
+    rs.close()
+    assert cnt["light_paths"] == rc_tot["light_paths"] == N * 256 * nr
+    assert cnt["shaded_vertices"] == rc_tot["shaded_vertices"]
+    assert abs(cnt["splats"] - rc_tot["splats"]) <= rc_tot["splats"] // 200 + 2
+    e_img, e_ref = float(img[..., :3].sum()), float(acc[..., :3].sum())
+    assert e_ref > 0 and abs(e_img - e_ref) <= 5e-3 * e_ref
+    assert pixel_mismatch_fraction(img, acc, 1e-2) < 0.03
+
+
+def test_c1_box1_at_stated_size(g, orc, scenes):
+    """BASELINE config 1 at its stated size: box1, PathTracer 512x512, 64 iterations (box1.txt), through RendererSystem.Draw() in streaming
+    mode, against the oracle rendering the same 64 iterations with the same light-sample stream."""
+    from gpugi_b200.parallel import rel_mse
+    from tests.test_gpu_renderers import _rs
+    W = H = 512
+    N = 64
+    sc = scenes.make_box1(tess=4)
+    rs = _rs(g, scenes, sc, "PT", W, H)
+    rs.SetStreaming(True)
+    ref = np.zeros((H, W, 4), np.float32)
+    for k in range(N):
+        samples, seed, cam = rs.GetInitialLightSamples(), rs.GetFrameSeed(), rs.GetCamera()
+        rs.Draw()
+        ref, _ = orc.render_pt(sc.desc, cam, W, H, samples, seed, 16, accum=ref)
+    img = rs.ReadBackbuffer()
+    assert rs.GetIterationCount() == N
+    rs.close()
+    x, r = img[..., :3] / N, ref[..., :3] / N
+    assert r.mean() > 0
+    value = rel_mse(x, r)
+    assert value <= 1e-3, "relMSE %.3g of the 64-iteration image against the oracle" % value
+    assert pixel_mismatch_fraction(img, ref, 1e-2) < 0.01
+
+
+@pytest.fixture(scope="module")
+def sponza_full(scenes, tmp_path_factory):
+    d = tmp_path_factory.mktemp("sponza_full")
+    return scenes.make_sponza_like(str(d), target_triangles=262144, texture_size=256, num_materials=25, seed=7)
+
+
+def test_c2_one_iteration_at_1080p_on_64_stripes(g, orc, scenes, sponza_full):
+    """BASELINE config 2 at its stated size: one PathTracer iteration at 1920x1080 on the 262 144-triangle scene against the oracle on 64 evenly
+    spaced 8-pixel stripes (983 040 of the 2 073 600 paths)."""
+    from gpugi_b200.parallel import rel_mse
+    from tests.test_gpu_renderers import _rs
+    W, H = 1920, 1080
+    rs = _rs(g, scenes, sponza_full, "PT", W, H, cam=scenes.SPONZA_CAMERA)
+    samples, seed, cam = rs.GetInitialLightSamples(), rs.GetFrameSeed(), rs.GetCamera()
+    rs.Draw()
+    img = rs.ReadBackbuffer()
+    rs.close()
+    ref = np.zeros((H, W, 4), np.float32)
+    rows = np.zeros(H, dtype=bool)
+    for i in range(64):
+        y = int(H * (i + 0.5) / 64) // 8 * 8
+        ref, _ = orc.render_pt(sponza_full.desc, cam, W, H, samples, seed, 16, region=(0, y, W, y + 8), accum=ref)
+        rows[y:y + 8] = True
+    assert rows.sum() == 512 and ref[rows][..., :3].mean() > 0
+    assert pixel_mismatch_fraction(img[rows], ref[rows], 1e-2) < 0.02
+    assert rel_mse(img[rows][..., :3], ref[rows][..., :3]) <= 2e-3
+
+
+def test_ray_batch_2_22_on_the_full_size_scene(g, orc, scenes, sponza_full):
+    """SURVEY 8d's ray batch at its stated size: 2^22 rays on the 262 144-triangle scene -- 50 % primary camera rays, 25 % cosine-hemisphere
+    secondaries from first hits, 25 % finite-length shadow rays -- hit flag, triangle id and distance bit-exact against the oracle."""
+    n = 1 << 22
+    W, H = 1920, 1080
+    cam = np.frombuffer(g.camera_params(scenes.SPONZA_CAMERA["pos"], scenes.SPONZA_CAMERA["lookat"], scenes.SPONZA_CAMERA["fov"], W, H), dtype=np.float32)
+    rng = np.random.RandomState(22)
+    rays = np.zeros(n, dtype=g.RAY_DTYPE)
+    rays["t_max"] = np.float32(g.RAY_MAX)
+    # primary rays through jittered pixel positions (pathtracer.comp:39-46)
+    half = n // 2
+    px = rng.randint(0, W, half); py = rng.randint(0, H, half)
+    jit = rng.rand(half, 2).astype(np.float32) - np.float32(0.5)
+    sx = ((px + jit[:, 0]) / np.float32(W) * 2 - 1).astype(np.float32); sy = ((py + jit[:, 1]) / np.float32(H) * 2 - 1).astype(np.float32)
+    U, V, Wd = cam[3:6], cam[6:9], cam[9:12]
+    d = sx[:, None] * U[None, :] + sy[:, None] * V[None, :] + Wd[None, :]
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    rays["origin"][:half] = cam[0:3]
+    rays["direction"][:half] = d
+    dev = g.Device(0)
+    dev.upload_scene(sponza_full)
+    first = dev.trace(rays[:half])
+    hit = first["leaf_tri"] >= 0
+    assert hit.mean() > 0.9
+    # secondaries: from the first hits, cosine-ish directions around the flipped ray direction (any direction will do for a parity batch)
+    q = n // 4
+    src = np.flatnonzero(hit)[:q]
+    p = rays["origin"][src] + first["t"][src, None] * rays["direction"][src]
+    nd = rng.randn(q, 3)
+    nd = (nd / np.linalg.norm(nd, axis=1, keepdims=True)).astype(np.float32)
+    nd = np.where((nd * rays["direction"][src]).sum(1, keepdims=True) > 0, -nd, nd)
+    rays["origin"][half:half + q] = (p + np.float32(1e-3) * nd).astype(np.float32)
+    rays["direction"][half:half + q] = nd
+    # shadow rays: from hit points to the scene's point lights, finite length, any-hit
+    lights = np.array([l[0] for l in scenes.SPONZA_POINT_LIGHTS], dtype=np.float32)
+    src2 = np.flatnonzero(hit)[q:2 * q]
+    p2 = rays["origin"][src2] + first["t"][src2, None] * rays["direction"][src2]
+    tgt = lights[rng.randint(0, len(lights), q)]
+    v = tgt - p2
+    dist = np.linalg.norm(v, axis=1).astype(np.float32)
+    rays["origin"][half + q:] = p2
+    rays["direction"][half + q:] = (v / dist[:, None]).astype(np.float32)
+    rays["t_max"][half + q:] = dist
+    rays["flags"][half + q:] = 1
+    hits = dev.trace(rays)
+    cnt = dev.counters()
+    dev.close()
+    ref = orc.trace_batch(sponza_full.desc, rays)
+    assert np.array_equal(hits["leaf_tri"], ref["leaf_tri"]), "%d of %d ids differ" % ((hits["leaf_tri"] != ref["leaf_tri"]).sum(), n)
+    assert np.array_equal(hits["t"].view(np.uint32), ref["t"].view(np.uint32))
+    closest = rays["flags"] == 0
+    assert np.array_equal(hits["bary_y"][closest].view(np.uint32), ref["bary_y"][closest].view(np.uint32))
+    occ = hits["leaf_tri"][~closest]
+    assert 0.05 < occ.mean() < 0.95   # both outcomes of the any-hit query are exercised
+    assert cnt["exact_fallback_rays"] > 0  # ties / near-ties went through the exact path
