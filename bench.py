@@ -549,6 +549,9 @@ def run_ours(args, rank, world, local_rank):
 
     if rank != 0:
         rs.close()
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
         return
     if shm_path:
         try:
@@ -633,6 +636,9 @@ def run_ours(args, rank, world, local_rank):
         line["relmse"] = relmse_vs_oracle(cfg, dev, g, sets, oracle_acc, its, regions, nr, cap)
     emit(line)
     rs.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def main():
