@@ -117,6 +117,7 @@ GI_OPT_WF_REFILL_THRESHOLD, GI_OPT_WF_MIN_INNER, GI_OPT_WF_BLOCKS_PER_SM, GI_OPT
 GI_OPT_KERNEL_TIMING = 8
 GI_OPT_STREAMING = 9
 GI_OPT_DEVICE_BUILDER = 10
+GI_OPT_WF_SHADE_BLOCKS_PER_SM = 13
 GI_OPT_UPLOAD_TOPOLOGY = 11
 GI_OPT_PLOC_RADIUS = 12
 GI_TOPOLOGY_REFERENCE, GI_TOPOLOGY_PLOC = 0, 1

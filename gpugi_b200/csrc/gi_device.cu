@@ -236,6 +236,13 @@ __global__ void __launch_bounds__(256) k_light_samples(DLightTables t, unsigned 
 #define WF_SHADE_MIN_BLOCKS 8   // k_wf_shade_pt: 64 registers, 8 blocks per SM (B200 A/B, PT batch: 1 -> 2.246, 8 -> 2.195, 10 -> 2.208, 12 -> 2.241 ms/iteration)
 #endif
 
+#ifndef WF_SHADE_LIGHT_MIN_BLOCKS
+#define WF_SHADE_LIGHT_MIN_BLOCKS 8   // B200 A/B (ms per iteration, 4 / 5 / 6 / 8 / 10 blocks per SM = 118 / 96 / 80 / 64 / 48 registers): C4 LPT 4K 6.92 / 6.78 / 6.62 / 6.49 / 6.62
+#endif
+#ifndef WF_SHADE_EYE_MIN_BLOCKS
+#define WF_SHADE_EYE_MIN_BLOCKS 8     // C3 BPT 1080p 7.64 / 7.55 / 7.46 / 7.43 / 7.64 (both kernels bounded together)
+#endif
+
 // Camera rays of all W/8 x H/8 work groups (pathtracer.comp:36-46) at the head of this wave's extension queue.
 __global__ void __launch_bounds__(256) k_wf_generate(WfFrame w, unsigned long long* counters)
 {
@@ -323,7 +330,7 @@ __global__ void __launch_bounds__(256) k_wf_generate_light(WfFrame w, unsigned l
 	flushWarpCounters(counters, cnt, WFC_COUNT);
 }
 
-__global__ void __launch_bounds__(WF_SHADE_THREADS) k_wf_shade_light(WfFrame w, unsigned long long* counters)
+__global__ void __launch_bounds__(WF_SHADE_THREADS, WF_SHADE_LIGHT_MIN_BLOCKS) k_wf_shade_light(WfFrame w, unsigned long long* counters)
 {
 	uint32_t* counts = wfCounts(w, w.wave);
 	const uint32_t n = w.numCam + counts[0];
@@ -342,7 +349,7 @@ __global__ void __launch_bounds__(WF_SHADE_THREADS) k_wf_shade_light(WfFrame w, 
 	flushWarpCounters(counters, cnt, WFC_COUNT);
 }
 
-__global__ void __launch_bounds__(WF_SHADE_THREADS) k_wf_shade_eye(WfFrame w, unsigned long long* counters)
+__global__ void __launch_bounds__(WF_SHADE_THREADS, WF_SHADE_EYE_MIN_BLOCKS) k_wf_shade_eye(WfFrame w, unsigned long long* counters)
 {
 	uint32_t* counts = wfCounts(w, w.wave);
 	const uint32_t n = w.numCam + counts[0];
@@ -1124,6 +1131,15 @@ int gi_set_option(GiContext* c, int option, int value)
 		return GI_OK;
 	case GI_OPT_WF_REFILL_THRESHOLD: c->tune.refillThreshold = std::min(std::max(value, 1), 32); return GI_OK;
 	case GI_OPT_WF_MIN_INNER: c->tune.minInner = std::min(std::max(value, 1), 32); return GI_OK;
+	case GI_OPT_WF_SHADE_BLOCKS_PER_SM:
+		if (value > 0) c->shadeBlocksPerSM = c->shadeLightBlocksPerSM = c->shadeEyeBlocksPerSM = value;
+		else
+		{
+			cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->shadeBlocksPerSM, k_wf_shade_pt, WF_SHADE_THREADS, 0);
+			cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->shadeLightBlocksPerSM, k_wf_shade_light, WF_SHADE_THREADS, 0);
+			cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->shadeEyeBlocksPerSM, k_wf_shade_eye, WF_SHADE_THREADS, 0);
+		}
+		return GI_OK;
 	case GI_OPT_WF_BLOCKS_PER_SM:
 		if (value > 0) c->traceBlocksPerSM = value;
 		else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->traceBlocksPerSM, k_wf_trace<false, false>, WF_TRACE_THREADS, 0);

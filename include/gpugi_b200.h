@@ -182,6 +182,7 @@ enum {
 	GI_OPT_WF_REFILL_THRESHOLD = 3, /* idle lanes per warp that trigger a refill from the ray queue  */
 	GI_OPT_WF_MIN_INNER = 4,        /* keep taking inner-node steps while this many of 32 active lanes are at inner nodes */
 	GI_OPT_WF_BLOCKS_PER_SM = 6,    /* resident trace blocks per SM (0 = occupancy maximum)          */
+	GI_OPT_WF_SHADE_BLOCKS_PER_SM = 13, /* resident shade blocks per SM (0 = occupancy maximum)          */
 	GI_OPT_COUNT_STEPS = 7,         /* 1 = the wavefront walk counts its box / triangle tests (GiCounters::node_tests,
 	                                   triangle_tests); off by default: two counters less in the hot loop.  The megakernel and
 	                                   GI_TRAVERSAL_REFERENCE always count. */
