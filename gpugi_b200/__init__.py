@@ -15,7 +15,7 @@ import numpy as np
 from . import _capi as capi
 from ._capi import (GI_RENDERER_PT, GI_RENDERER_LPT, GI_RENDERER_BPT, GI_RENDERER_WHITTED, GI_TRAVERSAL_FAST, GI_TRAVERSAL_REFERENCE,
                     GI_OPT_TRAVERSAL, GI_OPT_TEXTURE_FILTER, GI_OPT_SCHEDULER, GI_OPT_WF_REFILL_THRESHOLD, GI_OPT_WF_MIN_INNER,
-                    GI_OPT_WF_BLOCKS_PER_SM, GI_OPT_COUNT_STEPS, GI_OPT_KERNEL_TIMING, GI_OPT_STREAMING, GI_OPT_DEVICE_BUILDER, GI_BUILDER_LBVH, GI_BUILDER_PLOC, GI_OPT_UPLOAD_TOPOLOGY, GI_OPT_PLOC_RADIUS, GI_TOPOLOGY_REFERENCE, GI_TOPOLOGY_PLOC, GI_SCHEDULER_WAVEFRONT, GI_SCHEDULER_MEGAKERNEL, RAY_MAX)
+                    GI_OPT_WF_BLOCKS_PER_SM, GI_OPT_WF_SHADE_BLOCKS_PER_SM, GI_OPT_RECONSTRUCTION_FILTER, GI_OPT_CHAINED_MIS, GI_OPT_COUNT_STEPS, GI_OPT_KERNEL_TIMING, GI_OPT_STREAMING, GI_OPT_DEVICE_BUILDER, GI_BUILDER_LBVH, GI_BUILDER_PLOC, GI_OPT_UPLOAD_TOPOLOGY, GI_OPT_PLOC_RADIUS, GI_TOPOLOGY_REFERENCE, GI_TOPOLOGY_PLOC, GI_SCHEDULER_WAVEFRONT, GI_SCHEDULER_MEGAKERNEL, RAY_MAX)
 
 RAY_DTYPE = np.dtype([("origin", "<f4", 3), ("t_max", "<f4"), ("direction", "<f4", 3), ("flags", "<u4")])
 HIT_DTYPE = np.dtype([("t", "<f4"), ("leaf_tri", "<i4"), ("bary_y", "<f4"), ("bary_z", "<f4")])

@@ -118,6 +118,8 @@ GI_OPT_KERNEL_TIMING = 8
 GI_OPT_STREAMING = 9
 GI_OPT_DEVICE_BUILDER = 10
 GI_OPT_WF_SHADE_BLOCKS_PER_SM = 13
+GI_OPT_RECONSTRUCTION_FILTER = 14
+GI_OPT_CHAINED_MIS = 15
 GI_OPT_UPLOAD_TOPOLOGY = 11
 GI_OPT_PLOC_RADIUS = 12
 GI_TOPOLOGY_REFERENCE, GI_TOPOLOGY_PLOC = 0, 1

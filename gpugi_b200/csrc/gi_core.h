@@ -780,6 +780,9 @@ struct DFrame
 	// pipelined BPT batches (gi_wavefront.cuh): iteration i uses cache (i % cacheRing) of a ring of caches `lightCacheCapacity`
 	// entries apart, and the counter pair 2 * (i % cacheRing) behind lightCacheCount.  cacheRing <= 1: the single cache above.
 	uint32_t cacheRing;
+	// shader #define variants (off by default, as in the reference's build): RECONSTRUCTION_FILTER (screenreproject.glsl:14-17) and CHAINED_MIS
+	int reconFilter;                   // 0 box, 1 Mitchell 1/3 1/3, 2 cone, 3 B-spline
+	int chainedMIS;                    // one-thread-per-path kernels only (the eye path carries g_mis[MAX_PATHLENGTH])
 };
 
 struct PathCounters
@@ -990,7 +993,68 @@ GI_HD void whittedPixel(const DFrame& f, int gx, int gy, PathCounters& pc, Trace
 GI_HD float misHeuristic(float p) { return fminf(1e18f, p); }
 GI_HD float distanceMISHeuristic(float d) { return misHeuristic(d * d); }
 
-// ProjectToScreen, screenreproject.glsl:55-227 (box filter, no CHAINED_MIS), split in two like EstimateDirectLight: everything
+// bidirpathtracer/chained_mis.glsl:1-34 (g_mis: the eye path's array of per-segment MIS weights)
+#define GI_MAX_PATHLENGTH 64
+GI_HD void updateQuality(float& prevQuality, float mis) { prevQuality = prevQuality * (mis + 1.0f); }
+GI_HD float qualityWeightedMIS_NEE(float mis_nee, float quality_nee, float quality_trace)
+{
+	return mis_nee * quality_nee / fmaxf(mis_nee * quality_nee + (1.0f - mis_nee) * quality_trace, GI_DIVISOR_EPSILON);
+}
+GI_HD float qualityWeightedMIS_Trace(float mis_trace, float quality_nee, float quality_trace)
+{
+	return mis_trace * quality_trace / fmaxf((1.0f - mis_trace) * quality_nee + mis_trace * quality_trace, GI_DIVISOR_EPSILON);
+}
+// cmisPathThroughputWeight with g_mis[pathSegment - 1] taken from `last` (the shader writes it into the array right before the call)
+GI_HD float cmisPathThroughputWeight(const float* gMis, float last, int pathSegment, float quality_nee, float quality_trace)
+{
+	float w = 1.0f;
+	for (int i = pathSegment - 1; i >= 0; --i)
+	{
+		const float m = (i == pathSegment - 1) ? last : gMis[i];
+		w *= qualityWeightedMIS_Trace(m, quality_nee, quality_trace);
+		updateQuality(quality_nee, m);
+		updateQuality(quality_trace, 1.0f - m);
+	}
+	return w;
+}
+
+// reconstruction filter kernels of screenreproject.glsl:186-223 over the distance to the pixel centre
+GI_HD float reconstructionFilterValue(int filter, float d)
+{
+	float v = 0.0f;
+	if (filter == 1)
+	{
+		if (d < 1.0f) v = (7.0f * d * d * d - 12.0f * d * d + 16.0f / 3.0f) / 6.0f;
+		else if (d < 2.0f) v = (-7.0f / 3.0f * d * d * d + 12.0f * d * d - 20.0f * d + 32.0f / 3.0f) / 6.0f;
+	}
+	else if (filter == 2)
+	{
+		if (d < 1.5f) v = 1.0f - d / 1.5f;
+	}
+	else if (filter == 3)
+	{
+		if (d < 1.0f) v = (3.0f * d * d * d - 6.0f * d * d + 4.0f) / 6.0f;
+		else if (d < 2.0f) v = (-d * d * d + 6.0f * d * d - 12.0f * d + 8.0f) / 6.0f;
+	}
+	return v;
+}
+
+// the splat of one camera connection: one pixel (box) or the 5 x 5 pixels around the rounded position weighted by their distance to it
+GI_HD void splatFiltered(float* accum, int width, int height, int filter, float posX, float posY, F3 v, PathCounters& pc)
+{
+	const int pcx = int(roundf(posX)), pcy = int(roundf(posY));
+	if (filter == 0) { splatAtomic(accum, width, height, pcx, pcy, v, pc); return; }
+	for (int y = -2; y <= 2; ++y)
+		for (int x = -2; x <= 2; ++x)
+		{
+			const int px = pcx + x, py = pcy + y;
+			const float dx = posX - float(px), dy = posY - float(py);
+			const float w = reconstructionFilterValue(filter, sqrtf(dx * dx + dy * dy));
+			if (w != 0.0f) splatAtomic(accum, width, height, px, py, w * v, pc);
+		}
+}
+
+// ProjectToScreen, screenreproject.glsl:55-227, split in two like EstimateDirectLight: everything
 // but the any-hit query towards the camera (prepareScreenSplat; the splatted value does not depend on the query), and the
 // query + atomic splat (projectToScreen, the megakernel's form; the wavefront scheduler queues the query instead).
 struct ScreenSplatQuery
@@ -998,11 +1062,13 @@ struct ScreenSplatQuery
 	F3 origin, dir;   // any-hit ray towards the camera
 	float len;
 	int px, py;       // target pixel; round() may yield W or H -> bounds-checked by the consumer
+	float posX, posY; // pixelPos before rounding (the reconstruction filters weight by the distance to it)
 	F3 value;         // what WriteAtomic adds when the ray is free
 };
 
+// cmisQualityN .. lastDistMIS: the CHAINED_MIS arguments of screenreproject.glsl:64-69, read only when f.chainedMIS && computeMIS
 GI_HD bool prepareScreenSplat(const DFrame& f, F3 pos, F3 inDir, F3 geometryNormal, F3 shadingNormal, const MaterialData& md, F3 pathThroughput, bool computeMIS,
-                              ScreenSplatQuery& q)
+                              ScreenSplatQuery& q, float cmisQualityN = 1.0f, float cmisQualityT = 1.0f, float lastConnectionProbability = 0.0f, float lastDistMIS = 0.0f)
 {
 	const F3 camPos = f3(f.cam.position), camU = f3(f.cam.u), camV = f3(f.cam.v), camW = f3(f.cam.w);
 	F3 toCam = camPos - pos;
@@ -1018,8 +1084,10 @@ GI_HD bool prepareScreenSplat(const DFrame& f, F3 pos, F3 inDir, F3 geometryNorm
 	q.origin = toCam * GI_RAY_HIT_EPSILON + pos;
 	q.dir = toCam;
 	q.len = cameraDist;
-	q.px = int(roundf((sx * 0.5f + 0.5f) * float(f.width)));
-	q.py = int(roundf((sy * 0.5f + 0.5f) * float(f.height)));
+	q.posX = (sx * 0.5f + 0.5f) * float(f.width);
+	q.posY = (sy * 0.5f + 0.5f) * float(f.height);
+	q.px = int(roundf(q.posX));
+	q.py = int(roundf(q.posY));
 	float cosAtCamera = saturate(camViewDotRay / cameraDist);
 	float fluxToIrradiance = adjointShadingNormalCorrectedOutDotN(inDir, toCam, geometryNormal, shadingNormal) /
 	                         (cosAtCamera * cosAtCamera * cosAtCamera * f.cam.pixel_area * cameraDistSq);
@@ -1029,20 +1097,39 @@ GI_HD bool prepareScreenSplat(const DFrame& f, F3 pos, F3 inDir, F3 geometryNorm
 	{
 		float eyeToLight = 1.0f; // InitialMIS()
 		float lightToEye = misHeuristic(pdf);
-		bsdf = bsdf * (eyeToLight / fmaxf(lightToEye + eyeToLight, GI_DIVISOR_EPSILON));
+		float mis = eyeToLight / fmaxf(lightToEye + eyeToLight, GI_DIVISOR_EPSILON);
+		if (f.chainedMIS)
+		{
+			// screenreproject.glsl:160-170
+			float lastPTmis = lastConnectionProbability / fmaxf(lastConnectionProbability + lightToEye * lastDistMIS, GI_DIVISOR_EPSILON);
+			updateQuality(cmisQualityN, lastPTmis);
+			updateQuality(cmisQualityT, 1.0f - lastPTmis);
+			mis = qualityWeightedMIS_NEE(mis, cmisQualityN, cmisQualityT);
+		}
+		bsdf = bsdf * mis;
 	}
 	q.value = pathThroughput * fluxToIrradiance * bsdf;
 	return true;
 }
 
 GI_HD void projectToScreen(const DFrame& f, F3 pos, F3 inDir, F3 geometryNormal, F3 shadingNormal, const MaterialData& md, F3 pathThroughput, bool computeMIS,
-                           PathCounters& pc, TraceStats* st)
+                           PathCounters& pc, TraceStats* st, float cmisQualityN = 1.0f, float cmisQualityT = 1.0f, float lastConnectionProbability = 0.0f,
+                           float lastDistMIS = 0.0f)
 {
 	ScreenSplatQuery q;
-	if (!prepareScreenSplat(f, pos, inDir, geometryNormal, shadingNormal, md, pathThroughput, computeMIS, q)) return;
+	if (!prepareScreenSplat(f, pos, inDir, geometryNormal, shadingNormal, md, pathThroughput, computeMIS, q, cmisQualityN, cmisQualityT, lastConnectionProbability, lastDistMIS))
+		return;
 	++pc.anyRays;
 	if (traceAny(f.scene, f.traversalMode, q.origin, q.dir, q.len, st)) return;
-	splatAtomic(f.accum, f.width, f.height, q.px, q.py, q.value, pc);
+	splatFiltered(f.accum, f.width, f.height, f.reconFilter, q.posX, q.posY, q.value, pc);
+}
+
+// CHAINED_MIS: the two quality weights of a stored light vertex (lighttracer.comp:67-68,174-177)
+GI_HD void setLightCacheQuality(const DFrame& f, uint32_t idx, float weightN, float weightT)
+{
+	if (idx >= f.lightCacheCapacity) return;
+	F4* e = f.lightCache + 4 * size_t(idx) + 3;
+	e->z = weightN; e->w = weightT;
 }
 
 // saveLightCache, lighttracer.comp:23-45.  Entry = 4 x F4 (64 bytes):
@@ -1100,6 +1187,10 @@ GI_HD void lighttracePath(const DFrame& f, uint32_t gid, PathCounters& pc, Trace
 		F2 z; z.x = 0.0f; z.y = 0.0f;
 		saveLightCache(f, gid, intensity / GI_PI_2 / float(f.numRaysPerLightSample), -1, f3(l0.x, l0.y, l0.z), pn, z, f3(0.0f), 0);
 	}
+	// CHAINED_MIS state of the light path (lighttracer.comp:62-69)
+	const bool cmis = SAVE && !WARMUP && f.chainedMIS != 0;
+	float lastConnectionProbability = 0.0f, lastCosAbs = 1.0f, chainedMISWeightN = 1.0f, chainedMISWeightT = 1.0f;
+	if (cmis) setLightCacheQuality(f, gid, chainedMISWeightN, chainedMISWeightT);
 	F3 pathThroughput = intensity * (GI_PI / float(f.numRaysPerLightSample));
 	F3 origin = f3(l0.x, l0.y, l0.z), dir;
 	if (l1.w > 1.5f)
@@ -1113,6 +1204,11 @@ GI_HD void lighttracePath(const DFrame& f, uint32_t gid, PathCounters& pc, Trace
 		F3 U, V;
 		createONB(normal, U, V);
 		dir = sampleHemisphereCosine(random2(seed), U, V, normal);
+		if (cmis)
+		{
+			lastCosAbs = saturate(dot(normal, dir)); // lighttracer.comp:89-92
+			lastConnectionProbability = misHeuristic(lastCosAbs / GI_PI);
+		}
 	}
 	for (int i = 0; i < f.maxPathLength; ++i)
 	{
@@ -1126,20 +1222,40 @@ GI_HD void lighttracePath(const DFrame& f, uint32_t gid, PathCounters& pc, Trace
 		getTriangleHitInfo(f.scene, h.triangle, h.bary, shadingNormal, tc);
 		MaterialData md = sampleMaterialData(f.scene, h.triangle.w, tc);
 		++pc.shadedVertices;
+		uint32_t slot = 0xffffffffu;
 		if (SAVE)
 		{
 			if (md.Reflectiveness.w < 100.0f)
 			{
-				uint32_t slot = allocLightCacheSlot(f, WARMUP);
+				slot = allocLightCacheSlot(f, WARMUP);
 				if (!WARMUP) saveLightCache(f, slot, pathThroughput, h.triangle.w, origin, packNormal(shadingNormal), tc, dir, i + 1);
 			}
 		}
-		if (!WARMUP) projectToScreen(f, origin, dir, h.normal, shadingNormal, md, pathThroughput, SAVE, pc, st);
+		if (!WARMUP)
+		{
+			if (cmis) // lighttracer.comp:141-144
+				projectToScreen(f, origin, dir, h.normal, shadingNormal, md, pathThroughput, true, pc, st, chainedMISWeightN, chainedMISWeightT, lastConnectionProbability,
+				                distanceMISHeuristic(h.t));
+			else
+				projectToScreen(f, origin, dir, h.normal, shadingNormal, md, pathThroughput, SAVE, pc, st);
+		}
 		F3 throughput = f3(1.0f);
 		float samplePDF;
 		F3 newDir = sampleBSDF(dir, md, seed, shadingNormal, throughput, true, samplePDF);
 		throughput = throughput * adjointShadingNormalCorrection(dir, newDir, h.normal, shadingNormal);
 		pathThroughput = pathThroughput * throughput;
+		if (cmis)
+		{
+			// lighttracer.comp:165-181
+			float reverseProb = misHeuristic(samplePDF);
+			float distMIS = distanceMISHeuristic(h.t);
+			float mis = lastConnectionProbability / fmaxf(lastConnectionProbability + distMIS * reverseProb, GI_DIVISOR_EPSILON);
+			updateQuality(chainedMISWeightN, mis);
+			updateQuality(chainedMISWeightT, 1.0f - mis);
+			if (slot != 0xffffffffu) setLightCacheQuality(f, slot, chainedMISWeightN, chainedMISWeightT);
+			lastConnectionProbability = reverseProb;
+			lastCosAbs = fabsf(dot(dir, h.normal)); // (the old direction and the un-normalised geometry normal, as written)
+		}
 		float cont = saturate(luminance(throughput));
 		if (randomFloat(seed) >= cont) break;
 		pathThroughput = pathThroughput / cont;
@@ -1187,7 +1303,7 @@ struct ConnectionQuery
 };
 
 GI_HD bool prepareConnection(const DFrame& f, uint32_t actualNumEntries, float lightSampleWeight, F3 origin, F3 dir, F3 hitNormal, const MaterialData& md, int i,
-                             float rayHit, float lastConnectionProbability, F3 pathThroughput, uint32_t& seed, ConnectionQuery& q)
+                             float rayHit, float lastConnectionProbability, F3 pathThroughput, uint32_t& seed, ConnectionQuery& q, const float* gMis = nullptr)
 {
 	uint32_t idx = randomUInt(seed) % actualNumEntries;
 	const F4* e = f.lightCache + 4 * size_t(idx);
@@ -1249,6 +1365,15 @@ GI_HD bool prepareConnection(const DFrame& f, uint32_t actualNumEntries, float l
 	}
 	else
 		lightIntensity = lightFlux * GI_PI_2;
+	if (gMis)
+	{
+		// CHAINED_MIS, pathtracer_bidir.comp:187-199 (g_mis[i] = mis is visible inside this block only: the end of the loop body overwrites it)
+		float quality_nee = e3.z, quality_trace = e3.w;
+		misLight = qualityWeightedMIS_NEE(misLight, quality_nee, quality_trace);
+		updateQuality(quality_nee, 1.0f - misLight);
+		updateQuality(quality_trace, misLight);
+		mis = cmisPathThroughputWeight(gMis, mis, i + 1, quality_nee, quality_trace);
+	}
 	mis *= misLight;
 	F3 irradiance = (mis * lightSampleWeight * cosCamera / lightDistSq) * lightIntensity;
 	q.value = irradiance * pathThroughput * bsdf;
@@ -1268,6 +1393,9 @@ GI_HD void bidirPathtracePixel(const DFrame& f, int gx, int gy, PathCounters& pc
 	float lightSampleWeight = float(actualNumEntries);
 	float lastConnectionProbability = 1.0f; // InitialMIS()
 	float mis = 0.0f;
+	const bool cmis = f.chainedMIS != 0;
+	float gMis[GI_MAX_PATHLENGTH];
+	if (cmis) for (int i = 0; i < GI_MAX_PATHLENGTH; ++i) gMis[i] = 0.0f; // pathtracer_bidir.comp:49-52
 	for (int i = 0; i < f.maxPathLength; ++i)
 	{
 		Hit h; bool fb = false;
@@ -1285,11 +1413,17 @@ GI_HD void bidirPathtracePixel(const DFrame& f, int gx, int gy, PathCounters& pc
 			float incidentCosSat = saturate(-dot(hitNormal, dir));
 			float lightToEye = distanceMISHeuristic(rayHit) * misHeuristic(incidentCosSat / GI_PI);
 			mis = (i == 0) ? 1.0f : (lastConnectionProbability / fmaxf(lastConnectionProbability + lightToEye, GI_DIVISOR_EPSILON));
+			if (cmis)
+			{
+				gMis[i] = mis; // pathtracer_bidir.comp:85-89
+				mis = cmisPathThroughputWeight(gMis, mis, i + 1, 1.0f, 1.0f);
+			}
 			color = color + mis * pathThroughput * md.Emissivity;
 		}
 		{
 			ConnectionQuery cq;
-			if (prepareConnection(f, actualNumEntries, lightSampleWeight, origin, dir, hitNormal, md, i, rayHit, lastConnectionProbability, pathThroughput, seed, cq))
+			if (prepareConnection(f, actualNumEntries, lightSampleWeight, origin, dir, hitNormal, md, i, rayHit, lastConnectionProbability, pathThroughput, seed, cq,
+			                      cmis ? gMis : nullptr))
 			{
 				++pc.anyRays;
 				if (!traceAny(f.scene, f.traversalMode, cq.origin, cq.dir, cq.len, st)) color = color + cq.value;
@@ -1313,7 +1447,8 @@ GI_HD void bidirPathtracePixel(const DFrame& f, int gx, int gy, PathCounters& pc
 			mis = lastConnectionProbability / fmaxf(lastConnectionProbability + distMIS * reverseProb, GI_DIVISOR_EPSILON);
 			if (md.Reflectiveness.w >= 100.0f) mis = 1.0f;
 		}
-		pathThroughput = pathThroughput * mis;
+		if (cmis) gMis[i] = mis; // pathtracer_bidir.comp:236-242: the weight changes with the future of the path
+		else pathThroughput = pathThroughput * mis;
 		lastConnectionProbability = reverseProb;
 	}
 	float* px = f.accum + 4 * (size_t(gy) * f.width + gx);

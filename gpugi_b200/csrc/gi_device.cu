@@ -281,6 +281,8 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MIN_BLOCKS) k_wf_tr
 	io.q.rayBase = w.rayBase;
 	io.q.splatBase = w.splatBase;
 	io.q.splatStride = size_t(w.f.width) * size_t(w.f.height) * 4u;
+	io.q.shadowPos = w.q.shadowPos;
+	io.q.reconFilter = w.q.shadowPos ? w.f.reconFilter : 0;
 	WfCounters<STEPS> cnt;
 	if (REFERENCE) wfTraceLoopReference(w.f.scene, io, counts + 2, cnt);
 	else wfTraceLoop(w.f.scene, io, counts + 2, w.tune, cnt);
@@ -512,6 +514,8 @@ struct GiContext
 	int textureFilterExact = 0;
 	int scheduler = GI_SCHEDULER_WAVEFRONT;
 	int countSteps = 0;              // GI_OPT_COUNT_STEPS
+	int reconFilter = 0;             // GI_OPT_RECONSTRUCTION_FILTER
+	int chainedMIS = 0;              // GI_OPT_CHAINED_MIS
 	WfTune tune = {24, 16, 0};     // B200 sweep (tools/gpu/run_variants.sh TUNES=...): refill:minInner 16:20 2.191, 24:20 2.153, 24:16 2.126, 28:16 2.143, 32:16 2.222 ms/iteration
 
 	// wavefront queues
@@ -651,6 +655,8 @@ static DFrame makeFrame(GiContext* c, const GiIterationParams* p)
 	f.lightCacheCapacity = 0;
 	f.lightCacheCount = c->bptCounters;
 	f.lightPathLengthSum = c->bptCounters + 1;
+	f.reconFilter = c->reconFilter;
+	f.chainedMIS = c->chainedMIS;
 	return f;
 }
 
@@ -661,7 +667,7 @@ static void freeWavefront(GiContext* c)
 	for (int set = 0; set < 2; ++set)
 	{
 		WfQueues& q = c->wf[set];
-		cudaFree(q.rays[0]); cudaFree(q.rays[1]); cudaFree(q.hits); cudaFree(q.shadow); cudaFree(q.stateT); cudaFree(q.stateC); cudaFree(q.stateM);
+		cudaFree(q.rays[0]); cudaFree(q.rays[1]); cudaFree(q.hits); cudaFree(q.shadow); cudaFree(q.shadowPos); cudaFree(q.stateT); cudaFree(q.stateC); cudaFree(q.stateM);
 		cudaFree(q.counts);
 		q = WfQueues{};
 		c->wfCountsLen[set] = 0;
@@ -676,18 +682,20 @@ static int ensureWavefront(GiContext* c, int set, uint64_t capacity, uint32_t nu
 	if (capacity > WF_ID_MASK || uint64_t(numIds) * numSlots > WF_ID_MASK)
 		return fail(c, GI_ERR_CAPACITY, "wavefront scheduler: more than 2^30 queue slots / path states");
 	const uint64_t states = uint64_t(numIds) * numSlots;
-	if (c->wf[set].capacity < capacity || c->wfStates[set] < states)
+	const bool needPos = c->reconFilter != 0;
+	if (c->wf[set].capacity < capacity || c->wfStates[set] < states || (needPos && !c->wf[set].shadowPos))
 	{
 		GI_CUDA(c, cudaStreamSynchronize(c->stream));
 		const uint64_t cap = std::max<uint64_t>(capacity, c->wf[set].capacity);
 		const uint64_t st = std::max<uint64_t>(states, c->wfStates[set]);
-		cudaFree(c->wf[set].rays[0]); cudaFree(c->wf[set].rays[1]); cudaFree(c->wf[set].hits); cudaFree(c->wf[set].shadow); cudaFree(c->wf[set].stateT); cudaFree(c->wf[set].stateC); cudaFree(c->wf[set].stateM);
-		c->wf[set].rays[0] = c->wf[set].rays[1] = nullptr; c->wf[set].hits = nullptr; c->wf[set].shadow = nullptr; c->wf[set].stateT = c->wf[set].stateC = nullptr; c->wf[set].stateM = nullptr;
+		cudaFree(c->wf[set].rays[0]); cudaFree(c->wf[set].rays[1]); cudaFree(c->wf[set].hits); cudaFree(c->wf[set].shadow); cudaFree(c->wf[set].shadowPos); cudaFree(c->wf[set].stateT); cudaFree(c->wf[set].stateC); cudaFree(c->wf[set].stateM);
+		c->wf[set].rays[0] = c->wf[set].rays[1] = nullptr; c->wf[set].hits = nullptr; c->wf[set].shadow = nullptr; c->wf[set].shadowPos = nullptr; c->wf[set].stateT = c->wf[set].stateC = nullptr; c->wf[set].stateM = nullptr;
 		c->wf[set].capacity = 0; c->wfStates[set] = 0;
 		GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->wf[set].rays[0]), size_t(cap) * 32));
 		GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->wf[set].rays[1]), size_t(cap) * 32));
 		GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->wf[set].hits), size_t(cap) * 8));
 		GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->wf[set].shadow), size_t(cap) * 48));
+		if (needPos) GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->wf[set].shadowPos), size_t(cap) * 8));
 		GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->wf[set].stateT), size_t(st) * 16));
 		GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->wf[set].stateC), size_t(st) * 16));
 		GI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->wf[set].stateM), size_t(st) * 4));
@@ -1125,6 +1133,10 @@ int gi_set_option(GiContext* c, int option, int value)
 		if (value != GI_SCHEDULER_WAVEFRONT && value != GI_SCHEDULER_MEGAKERNEL) return fail(c, GI_ERR_INVALID, "GI_OPT_SCHEDULER: unknown scheduler");
 		c->scheduler = value; return GI_OK;
 	case GI_OPT_COUNT_STEPS: c->countSteps = value ? 1 : 0; return GI_OK;
+	case GI_OPT_RECONSTRUCTION_FILTER:
+		if (value < 0 || value > 3) return fail(c, GI_ERR_INVALID, "GI_OPT_RECONSTRUCTION_FILTER: 0 (box) .. 3");
+		c->reconFilter = value; return GI_OK;
+	case GI_OPT_CHAINED_MIS: c->chainedMIS = value ? 1 : 0; return GI_OK;
 	case GI_OPT_KERNEL_TIMING:
 		c->kernelTiming = value ? 1 : 0;
 		for (int i = 0; i < GI_KERNEL_CLASS_COUNT; ++i) { c->kernelMs[i] = 0.0; c->kernelLaunches[i] = 0; }
@@ -1623,6 +1635,8 @@ int gi_render_iteration(GiContext* c, const GiIterationParams* p)
 	int st = checkRenderState(c);
 	if (st != GI_OK) return st;
 	if (p->max_path_length <= 0) return fail(c, GI_ERR_INVALID, "max_path_length must be positive");
+	if (c->chainedMIS && p->renderer == GI_RENDERER_BPT && p->max_path_length > GI_MAX_PATHLENGTH)
+		return fail(c, GI_ERR_INVALID, "GI_OPT_CHAINED_MIS: max_path_length must not exceed 64");
 	GI_CUDA(c, cudaSetDevice(c->device));
 	// Streams and the light-sample ring (GI_LIGHT_RING sets): iteration k reads its set in the waves that shade it with next-event estimation (PT:
 	// waves k .. k + maxPathLength) or that start its light paths (LPT / BPT: generate wave k only -- light vertices carry their flux, and the BPT
@@ -1665,7 +1679,7 @@ int gi_render_iteration(GiContext* c, const GiIterationParams* p)
 		GI_CUDA(c, cudaGetLastError());
 		return GI_OK;
 	}
-	if (canStream && p->renderer == GI_RENDERER_BPT && !p->warmup && p->num_rays_per_light_sample > 0 && p->light_cache_capacity > 0 &&
+	if (canStream && !c->chainedMIS && p->renderer == GI_RENDERER_BPT && !p->warmup && p->num_rays_per_light_sample > 0 && p->light_cache_capacity > 0 &&
 	    uint64_t(p->light_cache_capacity) >= uint64_t(c->numLightSamples) * uint64_t(p->num_rays_per_light_sample))
 	{
 		// streaming BPT: one global wave of the light / eye pipeline per call (renderPipelinedBPT's schedule, kept open)
@@ -1732,7 +1746,8 @@ int gi_render_iteration(GiContext* c, const GiIterationParams* p)
 		if (p->num_rays_per_light_sample <= 0) return fail(c, GI_ERR_INVALID, "num_rays_per_light_sample must be positive");
 		const unsigned numLightPaths = unsigned(c->numLightSamples) * unsigned(p->num_rays_per_light_sample);
 		const unsigned groups = numLightPaths / 64u;
-		const bool wavefront = c->scheduler == GI_SCHEDULER_WAVEFRONT;
+		// CHAINED_MIS keeps g_mis[MAX_PATHLENGTH] per eye path and two more weights per light path: the one-thread-per-path kernels carry them
+		const bool wavefront = c->scheduler == GI_SCHEDULER_WAVEFRONT && !(c->chainedMIS && !p->warmup);
 		// resetcounter.comp (bidirectionalpathtracer.cpp:190)
 		k_reset_counter<<<1, 1, 0, c->stream>>>(c->bptCounters, c->bptCounters + 1, numLightPaths);
 		++c->launches;
@@ -1808,7 +1823,7 @@ int gi_render_iterations(GiContext* c, const GiIterationParams* p, const uint32_
 		GI_CUDA(c, cudaGetLastError());
 		return GI_OK;
 	}
-	if (p->renderer == GI_RENDERER_BPT && c->scheduler == GI_SCHEDULER_WAVEFRONT && count > 1u && !p->warmup && p->num_rays_per_light_sample > 0 &&
+	if (p->renderer == GI_RENDERER_BPT && c->scheduler == GI_SCHEDULER_WAVEFRONT && !c->chainedMIS && count > 1u && !p->warmup && p->num_rays_per_light_sample > 0 &&
 	    p->light_cache_capacity > 0 && uint64_t(p->light_cache_capacity) >= uint64_t(c->numLightSamples) * uint64_t(p->num_rays_per_light_sample))
 	{
 		// BPT: light and eye passes of consecutive iterations pipelined over a ring of light caches

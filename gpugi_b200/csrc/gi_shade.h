@@ -21,7 +21,8 @@ struct WfPush
 	F3 sOrigin, sDir;
 	float sLen;
 	F3 sValue;
-	int px, py;          // light tracer: target pixel of the splat (already bounds-checked)
+	int px, py;          // light tracer: target pixel of the splat (already bounds-checked; with a reconstruction filter: the centre pixel, which may lie up to 2 pixels outside)
+	float posX, posY;    // ... and the unrounded position the filter weights refer to
 };
 
 // Path state records (HBM): T = (pathThroughput.xyz, RNG state bits), C = (radiance sum.xyz, alpha increment),
@@ -92,12 +93,15 @@ GI_HD void wfShadeLightLane(const DFrame& f, uint32_t lightFlags, F3 origin, F3 
 	if (!warmup)
 	{
 		ScreenSplatQuery q;
-		if (prepareScreenSplat(f, origin, dir, gn, shadingNormal, md, pathThroughput, save, q) && q.px >= 0 && q.py >= 0 && q.px < f.width && q.py < f.height)
+		// (a filtered splat whose centre lies just outside the frame still reaches pixels inside)
+		const int border = f.reconFilter ? 2 : 0;
+		if (prepareScreenSplat(f, origin, dir, gn, shadingNormal, md, pathThroughput, save, q) && q.px >= -border && q.py >= -border && q.px < f.width + border &&
+		    q.py < f.height + border)
 		{
 			++pc.anyRays;
 			out.shadow = true;
 			out.sOrigin = q.origin; out.sDir = q.dir; out.sLen = q.len; out.sValue = q.value;
-			out.px = q.px; out.py = q.py;
+			out.px = q.px; out.py = q.py; out.posX = q.posX; out.posY = q.posY;
 		}
 	}
 	F3 throughput = f3(1.0f);

@@ -53,6 +53,7 @@ struct WfQueues
 	F4* rays[2];
 	float2* hits;
 	F4* shadow;
+	float2* shadowPos;   // reconstruction filters only (else nullptr): unrounded pixel position of a splat, one per shadow-queue slot
 	F4* stateT;          // numSlots x numIds: (throughput.xyz, seed bits)
 	F4* stateC;          // numSlots x numIds: (radiance sum.xyz, alpha increment)
 	float* stateM;       // numSlots x numIds: lastConnectionProbability of a BPT eye path
@@ -110,6 +111,8 @@ struct WfTraceIO
 	uint32_t rayBase;   // extension ray i of this wave sits in queue slot rayBase + i
 	float* splatBase;   // streams of light paths: ring of per-iteration splat images (nullptr: splats go straight into accum)
 	size_t splatStride; // floats per image
+	const float2* shadowPos; // RECONSTRUCTION_FILTER != 0: where each splat falls before rounding
+	int reconFilter;
 };
 
 GI_D void wfSplat(float* accum, int width, int height, uint32_t pixel, F3 v)
@@ -131,6 +134,14 @@ GI_D void wfFinishShadow(const WfTraceIO& io, uint32_t slot, bool occluded, CNT&
 		cnt.template add<WFC_SPLATS>(1u);
 		// a stream keeps the splats of an iteration in that iteration's own image (ring slot in v.w) until the iteration is complete
 		float* image = io.splatBase ? io.splatBase + size_t(uint32_t(f2i(v.w))) * io.splatStride : io.accum;
+		if (io.reconFilter)
+		{
+			// screenreproject.glsl:186-223: 5 x 5 weighted splats around the rounded position
+			const float2 pos = io.shadowPos[slot];
+			PathCounters dummy = {};
+			splatFiltered(image, io.width, io.height, io.reconFilter, pos.x, pos.y, f3(v.x, v.y, v.z), dummy);
+			return;
+		}
 		wfSplat(image, io.width, io.height, id, f3(v.x, v.y, v.z));
 		return;
 	}
@@ -620,6 +631,7 @@ GI_D void wfPushOut(const WfFrame& w, const WfPush& out, uint32_t shadowTarget, 
 		*reinterpret_cast<float4*>(sp) = make_float4(out.sOrigin.x, out.sOrigin.y, out.sOrigin.z, out.sLen);
 		*reinterpret_cast<float4*>(sp + 1) = make_float4(out.sDir.x, out.sDir.y, out.sDir.z, i2f(int(shadowTarget)));
 		*reinterpret_cast<float4*>(sp + 2) = make_float4(out.sValue.x, out.sValue.y, out.sValue.z, i2f(int(splatSlot)));
+		if (q.shadowPos && (shadowTarget & WF_FLAG_SPLAT)) q.shadowPos[sslot] = make_float2(out.posX, out.posY);
 	}
 	const uint32_t rslot = w.pushBase + warpPush(next, out.ray);
 	if (out.ray)
@@ -680,7 +692,9 @@ GI_D void wfShadeLight(const WfFrame& w, uint32_t slot, bool valid, PathCounters
 		wfShadeLightLane(f, w.lightFlags, f3(r0.x, r0.y, r0.z), f3(r1.x, r1.y, r1.z), bounce, hrec.x, f2i(hrec.y), T, out, pc);
 		if (out.ray) stState(w.q.stateT + sidx, T);
 	}
-	wfPushOut(w, out, WF_FLAG_SPLAT | (uint32_t(out.py) * uint32_t(w.f.width) + uint32_t(out.px)), bounce, id, splatSlot);
+	// (with a reconstruction filter the centre pixel may lie outside the frame: the target word then only carries the flag, the position is in shadowPos)
+	const bool inside = out.px >= 0 && out.py >= 0 && out.px < w.f.width && out.py < w.f.height;
+	wfPushOut(w, out, WF_FLAG_SPLAT | (inside ? uint32_t(out.py) * uint32_t(w.f.width) + uint32_t(out.px) : 0u), bounce, id, splatSlot);
 }
 
 // shade(w) of the BPT eye pass: one lane per hit record of an eye path

@@ -183,6 +183,13 @@ enum {
 	GI_OPT_WF_MIN_INNER = 4,        /* keep taking inner-node steps while this many of 32 active lanes are at inner nodes */
 	GI_OPT_WF_BLOCKS_PER_SM = 6,    /* resident trace blocks per SM (0 = occupancy maximum)          */
 	GI_OPT_WF_SHADE_BLOCKS_PER_SM = 13, /* resident shade blocks per SM (0 = occupancy maximum)          */
+	GI_OPT_RECONSTRUCTION_FILTER = 14,  /* RECONSTRUCTION_FILTER of screenreproject.glsl:14-17,186-223 for every camera-connection splat (LPT, the BPT light
+	                                       pass): 0 = box (default, the reference's build), 1 = Mitchell-Netravali 1/3 1/3, 2 = cone, 3 = B-spline; 5 x 5 pixels
+	                                       around the rounded position, weighted by the distance to the unrounded one */
+	GI_OPT_CHAINED_MIS = 15,            /* 1 = CHAINED_MIS (bidirpathtracer/chained_mis.glsl; hooks lighttracer.comp:62-69,89-92,141-144,165-181,
+	                                       screenreproject.glsl:160-170, pathtracer_bidir.comp:49-52,85-89,187-199,236-242): quality-weighted MIS along the
+	                                       light and eye paths of the bidirectional path tracer.  Off in the reference's build (bidirectionalpathtracer.cpp:142).
+	                                       BPT iterations then run one thread per path (the eye path carries g_mis[MAX_PATHLENGTH]); max_path_length <= 64. */
 	GI_OPT_COUNT_STEPS = 7,         /* 1 = the wavefront walk counts its box / triangle tests (GiCounters::node_tests,
 	                                   triangle_tests); off by default: two counters less in the hot loop.  The megakernel and
 	                                   GI_TRAVERSAL_REFERENCE always count. */

@@ -618,6 +618,8 @@ struct Frame
 	uint32_t frameSeed;
 	int maxPathLength;
 	float* accum; // RGBA32F sum image
+	int reconFilter; // RECONSTRUCTION_FILTER (screenreproject.glsl:14-17): 0 box, 1 Mitchell 1/3 1/3, 2 cone, 3 B-spline
+	bool chainedMIS; // CHAINED_MIS (bidirpathtracer/chained_mis.glsl)
 };
 
 // lightsource.glsl:3-93 (EstimateDirectLight, no TRACERAY_IMPORTANCE_BREAK / CACHE_DIRECT_DIFFUSE)
@@ -773,9 +775,55 @@ inline float MISHeuristic(float p) { return fminf(1e18f, p); }
 inline float InitialMIS() { return 1.0f; }
 inline float DistanceMISHeuristic(float d, float /*c*/) { return MISHeuristic(d * d); }
 
-// screenreproject.glsl:55-227 (ProjectToScreen, RECONSTRUCTION_FILTER off, no CHAINED_MIS)
+// bidirpathtracer/chained_mis.glsl:1-34.  g_mis is the shader's global array, here owned by the eye path.
+#define OR_MAX_PATHLENGTH 64
+inline void updateQuality(float& prevQuality, float mis) { prevQuality = prevQuality * (mis + 1.0f); }
+inline float qualityWeightedMIS_NEE(float mis_nee, float quality_nee, float quality_trace)
+{
+	return mis_nee * quality_nee / fmaxf(mis_nee * quality_nee + (1 - mis_nee) * quality_trace, DIVISOR_EPSILON);
+}
+inline float qualityWeightedMIS_Trace(float mis_trace, float quality_nee, float quality_trace)
+{
+	return mis_trace * quality_trace / fmaxf((1 - mis_trace) * quality_nee + mis_trace * quality_trace, DIVISOR_EPSILON);
+}
+inline float cmisPathThroughputWeight(const float* g_mis, int pathSegment, float quality_nee, float quality_trace)
+{
+	float w = 1.0f; // (chained_mis.glsl:25-26: the first assignment is dead)
+	for (int i = pathSegment - 1; i >= 0; --i)
+	{
+		w *= qualityWeightedMIS_Trace(g_mis[i], quality_nee, quality_trace);
+		updateQuality(quality_nee, g_mis[i]);
+		updateQuality(quality_trace, 1.0f - g_mis[i]);
+	}
+	return w;
+}
+
+// the reconstruction filter kernels of screenreproject.glsl:186-223, as a function of the distance to the pixel centre
+inline float reconstructionFilterValue(int filter, float d)
+{
+	float filterValue = 0.0f;
+	if (filter == 1)
+	{
+		if (d < 1.0f) filterValue = (7.0f * d * d * d - 12.0f * d * d + 16.0f / 3.0f) / 6.0f;
+		else if (d < 2.0f) filterValue = (-7.0f / 3.0f * d * d * d + 12.0f * d * d - 20.0f * d + 32.0f / 3.0f) / 6.0f;
+	}
+	else if (filter == 2)
+	{
+		if (d < 1.5f) filterValue = 1.0f - d / 1.5f;
+	}
+	else if (filter == 3)
+	{
+		if (d < 1.0f) filterValue = (3.0f * d * d * d - 6.0f * d * d + 4.0f) / 6.0f;
+		else if (d < 2.0f) filterValue = (-d * d * d + 6.0f * d * d - 12.0f * d + 8.0f) / 6.0f;
+	}
+	return filterValue;
+}
+
+// screenreproject.glsl:55-227 (ProjectToScreen).  f.reconFilter selects RECONSTRUCTION_FILTER, f.chainedMIS the CHAINED_MIS variant, whose four
+// extra arguments (:64-69) are ignored otherwise.
 void ProjectToScreen(const Frame& f, const Ray& ray, V3 geometryNormal, V3 shadingNormal, const MaterialData& md, V3 pathThroughput, bool computeFullBSDF,
-                     bool computeMIS, Counters& c, TraceCounters& tc)
+                     bool computeMIS, Counters& c, TraceCounters& tc, float cmisQualityN = 1.0f, float cmisQualityT = 1.0f, float lastConnectionProbability = 0.0f,
+                     float lastDistMIS = 0.0f)
 {
 	V3 CameraPosition = v3(f.cam.position), CameraU = v3(f.cam.u), CameraV = v3(f.cam.v), CameraW = v3(f.cam.w);
 	Ray cameraRay;
@@ -811,6 +859,14 @@ void ProjectToScreen(const Frame& f, const Ray& ray, V3 geometryNormal, V3 shadi
 						float connectionEyeToLightPath = InitialMIS();
 						float connectionLightPathToEye = MISHeuristic(pdf);
 						float mis = connectionEyeToLightPath / fmaxf(connectionLightPathToEye + connectionEyeToLightPath, DIVISOR_EPSILON);
+						if (f.chainedMIS)
+						{
+							// screenreproject.glsl:160-170
+							float lastPTmis = lastConnectionProbability / fmaxf(lastConnectionProbability + connectionLightPathToEye * lastDistMIS, DIVISOR_EPSILON);
+							updateQuality(cmisQualityN, lastPTmis);
+							updateQuality(cmisQualityT, 1.0f - lastPTmis);
+							mis = qualityWeightedMIS_NEE(mis, cmisQualityN, cmisQualityT);
+						}
 						bsdf *= mis;
 					}
 				}
@@ -826,7 +882,21 @@ void ProjectToScreen(const Frame& f, const Ray& ray, V3 geometryNormal, V3 shadi
 					else bsdf = v3(0.0f);
 				}
 				V3 color = pathThroughput * fluxToIrradiance * bsdf;
-				WriteAtomic(f, color, pcx, pcy, c);
+				if (f.reconFilter == 0)
+					WriteAtomic(f, color, pcx, pcy, c);
+				else
+				{
+					// screenreproject.glsl:186-223: 5 x 5 pixels around the rounded position, weighted by the distance to pixelPos
+					for (int y = -2; y <= 2; ++y)
+						for (int x = -2; x <= 2; ++x)
+						{
+							int px = pcx + x, py = pcy + y;
+							float ddx = pixelPos.x - float(px), ddy = pixelPos.y - float(py);
+							float d = sqrtf(ddx * ddx + ddy * ddy);
+							float filterValue = reconstructionFilterValue(f.reconFilter, d);
+							if (filterValue != 0.0f) WriteAtomic(f, filterValue * color, px, py, c);
+						}
+				}
 			}
 		}
 	}
@@ -884,6 +954,12 @@ void LighttracerPath(const Frame& f, uint32_t gid, int numRaysPerLightSample, Li
 		V2 zero2; zero2.x = 0.0f; zero2.y = 0.0f;
 		saveLightCache(*lc, gid, v3(ls.intensity) / PI_2 / float(numRaysPerLightSample), -1, v3(ls.position), pn, zero2, v3(0.0f), 0, c);
 	}
+	// CHAINED_MIS state of the light path (lighttracer.comp:62-69)
+	const bool cmis = f.chainedMIS && lc && !lc->warmup;
+	float lastConnectionProbability = 0.0f; // Point light init (cannot be traced by a PT)
+	float lastCosAbs = 1.0f;
+	float chainedMISWeightN = 1.0f, chainedMISWeightT = 1.0f;
+	if (cmis && gid < lc->capacity) { lc->entries[gid].ChainedMISWeightN = chainedMISWeightN; lc->entries[gid].ChainedMISWeightT = chainedMISWeightT; }
 	V3 pathThroughput = v3(ls.intensity) * (PI / float(numRaysPerLightSample));
 	Ray ray;
 	ray.Origin = v3(ls.position);
@@ -898,6 +974,12 @@ void LighttracerPath(const Frame& f, uint32_t gid, int numRaysPerLightSample, Li
 		V3 U, V;
 		CreateONB(normal, U, V);
 		ray.Direction = SampleHemisphereCosine(Random2(randomSeed), U, V, normal);
+		if (cmis)
+		{
+			// lighttracer.comp:89-92
+			lastCosAbs = saturate(dot(normal, ray.Direction));
+			lastConnectionProbability = MISHeuristic(lastCosAbs / PI);
+		}
 	}
 	for (int i = 0; i < f.maxPathLength; ++i)
 	{
@@ -911,11 +993,11 @@ void LighttracerPath(const Frame& f, uint32_t gid, int numRaysPerLightSample, Li
 		GetTriangleHitInfo(s, triangle, bary, shadingNormal, hitTexcoord);
 		MaterialData md = SampleMaterialData(s, int(triangle.material), hitTexcoord);
 		++c.shaded_vertices;
+		uint32_t lightCacheEntryIndex = ~0u;
 		if (lc)
 		{
 			if (md.Reflectiveness.w < 100.0f)
 			{
-				uint32_t lightCacheEntryIndex;
 #pragma omp atomic capture
 				lightCacheEntryIndex = lc->numEntries++;
 				if (lc->warmup)
@@ -929,12 +1011,34 @@ void LighttracerPath(const Frame& f, uint32_t gid, int numRaysPerLightSample, Li
 			}
 		}
 		if (!(lc && lc->warmup))
-			ProjectToScreen(f, ray, geometryNormal, shadingNormal, md, pathThroughput, true, lc != nullptr, c, tc);
+		{
+			if (cmis) // lighttracer.comp:141-144
+				ProjectToScreen(f, ray, geometryNormal, shadingNormal, md, pathThroughput, true, true, c, tc, chainedMISWeightN, chainedMISWeightT, lastConnectionProbability,
+				                DistanceMISHeuristic(rayHit, lastCosAbs));
+			else
+				ProjectToScreen(f, ray, geometryNormal, shadingNormal, md, pathThroughput, true, lc != nullptr, c, tc);
+		}
 		V3 throughput = v3(1.0f);
 		float samplePDF; bool isReflectedDiffuse;
 		V3 newDirection = SampleBSDFImpl(ray.Direction, md, randomSeed, shadingNormal, throughput, true, samplePDF, isReflectedDiffuse);
 		throughput *= AdjointBSDFShadingNormalCorrection(ray.Direction, newDirection, geometryNormal, shadingNormal);
 		pathThroughput *= throughput;
+		if (cmis)
+		{
+			// lighttracer.comp:165-181: how likely a PT could have generated the last path segment
+			float reverseConnectionProbability = MISHeuristic(samplePDF);
+			float distMIS = DistanceMISHeuristic(rayHit, lastCosAbs);
+			float mis = lastConnectionProbability / fmaxf(lastConnectionProbability + distMIS * reverseConnectionProbability, DIVISOR_EPSILON);
+			updateQuality(chainedMISWeightN, mis);
+			updateQuality(chainedMISWeightT, 1.0f - mis);
+			if (lightCacheEntryIndex != ~0u && lightCacheEntryIndex < lc->capacity)
+			{
+				lc->entries[lightCacheEntryIndex].ChainedMISWeightN = chainedMISWeightN;
+				lc->entries[lightCacheEntryIndex].ChainedMISWeightT = chainedMISWeightT;
+			}
+			lastConnectionProbability = reverseConnectionProbability;
+			lastCosAbs = fabsf(dot(ray.Direction, geometryNormal)); // (the old direction and the un-normalised geometry normal, as written)
+		}
 		float continuationPropability = saturate(GetLuminance(throughput));
 		if (Random(randomSeed) >= continuationPropability)
 			break;
@@ -997,6 +1101,8 @@ void BidirPathtracerPixel(const Frame& f, int gx, int gy, const LightCache& lc, 
 	float lastConnectionProbability = InitialMIS();
 	float lastCosAbs = 1.0f;
 	float mis = 0.0f;
+	float g_mis[OR_MAX_PATHLENGTH];
+	for (int i = 0; i < OR_MAX_PATHLENGTH; ++i) g_mis[i] = 0.0f; // pathtracer_bidir.comp:49-52
 	for (int i = 0; i < f.maxPathLength; ++i)
 	{
 		GiTriangle triangle; V3 bary; float rayHit = RAY_MAX; V3 geometryNormal; int hitIndex[2];
@@ -1014,6 +1120,12 @@ void BidirPathtracerPixel(const Frame& f, int gx, int gy, const LightCache& lc, 
 			float incidentSurfaceCosSat = saturate(-dot(hitNormal, ray.Direction));
 			float connectionLightToEyePath = DistanceMISHeuristic(rayHit, lastCosAbs) * MISHeuristic(incidentSurfaceCosSat / PI);
 			mis = (i == 0) ? 1.0f : (lastConnectionProbability / fmaxf(lastConnectionProbability + connectionLightToEyePath, DIVISOR_EPSILON));
+			if (f.chainedMIS)
+			{
+				// pathtracer_bidir.comp:85-89
+				g_mis[i] = mis;
+				mis = cmisPathThroughputWeight(g_mis, i + 1, 1.0f, 1.0f);
+			}
 			color += mis * pathThroughput * md.Emissivity;
 		}
 		Ray lightRay;
@@ -1082,6 +1194,17 @@ void BidirPathtracerPixel(const Frame& f, int gx, int gy, const LightCache& lc, 
 					lightSampleIntensity = lightSampleFlux * (PI_2);
 					misLight = 1.0f;
 				}
+				if (f.chainedMIS)
+				{
+					// pathtracer_bidir.comp:187-199
+					float quality_nee = e.ChainedMISWeightN;
+					float quality_trace = e.ChainedMISWeightT;
+					misLight = qualityWeightedMIS_NEE(misLight, quality_nee, quality_trace);
+					updateQuality(quality_nee, 1.0f - misLight);
+					updateQuality(quality_trace, misLight);
+					g_mis[i] = mis;
+					mis = cmisPathThroughputWeight(g_mis, i + 1, quality_nee, quality_trace);
+				}
 				mis *= misLight;
 				V3 irradiance = (mis * lightSampleWeight * cosCamera / lightDistSq) * lightSampleIntensity;
 				color += irradiance * pathThroughput * bsdf;
@@ -1107,7 +1230,8 @@ void BidirPathtracerPixel(const Frame& f, int gx, int gy, const LightCache& lc, 
 			if (md.Reflectiveness.w >= 100.0f)
 				mis = 1.0f;
 		}
-		pathThroughput *= mis;
+		if (f.chainedMIS) g_mis[i] = mis; // pathtracer_bidir.comp:236-242: the weight changes with the future of the path
+		else pathThroughput *= mis;
 		lastConnectionProbability = reverseConnectionProbability;
 		lastCosAbs = fabsf(dot(ray.Direction, hitNormal));
 	}
@@ -1232,11 +1356,18 @@ OR_API int or_intersect_triangle(const float o[3], const float d[3], const float
 
 struct OrRegion { int x0, y0, x1, y1; }; // pixel rectangle [x0,x1) x [y0,y1); all-zero => full frame
 
+// shader #defines that select variants (RECONSTRUCTION_FILTER: screenreproject.glsl:14-17, CHAINED_MIS: bidirectionalpathtracer.cpp:142); they apply
+// to the render calls that follow
+static int g_reconFilter = 0;
+static int g_chainedMIS = 0;
+OR_API void or_set_variant(int reconstruction_filter, int chained_mis) { g_reconFilter = reconstruction_filter; g_chainedMIS = chained_mis; }
+
 static Frame makeFrame(const Scene& s, const GiCamera* cam, int w, int h, const GiLightSample* ls, int nls, uint32_t frameSeed, int maxLen, float* accum)
 {
 	Frame f;
 	f.scene = &s; f.cam = *cam; f.width = w; f.height = h; f.lightSamples = ls; f.numLightSamples = nls; f.frameSeed = frameSeed; f.maxPathLength = maxLen;
 	f.accum = accum;
+	f.reconFilter = g_reconFilter; f.chainedMIS = g_chainedMIS != 0;
 	return f;
 }
 

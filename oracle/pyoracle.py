@@ -194,6 +194,15 @@ def set_environment_cube(faces):
 _env_keep = None
 
 
+lib.or_set_variant.restype = None
+lib.or_set_variant.argtypes = [C.c_int, C.c_int]
+
+
+def set_variant(reconstruction_filter=0, chained_mis=False):
+    """Shader #define variants for the render calls that follow: RECONSTRUCTION_FILTER 0-3 (screenreproject.glsl:14-17), CHAINED_MIS."""
+    lib.or_set_variant(int(reconstruction_filter), 1 if chained_mis else 0)
+
+
 def render_lpt(scene_desc, cam, w, h, light_samples, frame_seed, num_rays_per_light_sample, max_len=16, first_path=0, num_paths=0, show_light_caches=True,
                accum=None):
     ls = np.ascontiguousarray(light_samples, dtype=LIGHT_SAMPLE_DTYPE)
