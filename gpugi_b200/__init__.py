@@ -163,6 +163,72 @@ class Scene:
         return out
 
 
+RAW_NODE_DTYPE = np.dtype([("parent", "<u4"), ("first_child", "<u4"), ("escape", "<u4")])
+RAW_VERTEX_DTYPE = np.dtype([("position", "<f4", 3), ("normal", "<f4", 3), ("texcoord", "<f4", 2)])
+RAW_LEAF_DTYPE = np.dtype([("triangles", [("v", "<u4", 3), ("material", "<u4")], 8)])
+
+
+class RawScene:
+    """bvhmake's `.rawscene` container + its kdtree / sweep / lds builders over 8-triangle leaves (host/bvhmake.hpp)."""
+
+    def __init__(self, handle):
+        if not handle:
+            raise GpugiError("RawScene: " + capi.host.gih_last_error().decode())
+        self._h = C.c_void_p(handle)
+
+    @classmethod
+    def build(cls, positions, normals, texcoords, triangles, tri_materials, material_names, method="kdtree"):
+        positions = np.ascontiguousarray(positions, dtype=np.float32)
+        normals = None if normals is None else np.ascontiguousarray(normals, dtype=np.float32)
+        texcoords = None if texcoords is None else np.ascontiguousarray(texcoords, dtype=np.float32)
+        triangles = np.ascontiguousarray(triangles, dtype=np.uint32)
+        tri_materials = None if tri_materials is None else np.ascontiguousarray(tri_materials, dtype=np.uint32)
+        names = (C.c_char_p * len(material_names))(*[n.encode() for n in material_names])
+        return cls(capi.host.gih_rawscene_build(_vp(positions), _vp(normals) if normals is not None else None, _vp(texcoords) if texcoords is not None else None,
+                                                positions.shape[0], _vp(triangles), _vp(tri_materials) if tri_materials is not None else None, triangles.shape[0],
+                                                names, len(material_names), {"kdtree": 0, "sweep": 1, "lds": 2}[method]))
+
+    @classmethod
+    def load(cls, path):
+        return cls(capi.host.gih_rawscene_load(os.fsencode(path)))
+
+    def store(self, path):
+        if capi.host.gih_rawscene_store(self._h, os.fsencode(path)) != 0:
+            raise GpugiError(capi.host.gih_last_error().decode())
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            capi.host.gih_rawscene_free(self._h)
+            self._h = None
+
+    def _get(self, which, dtype):
+        n = int(capi.host.gih_rawscene_get(self._h, which, None))
+        buf = np.zeros(n, dtype=np.uint8)
+        if n:
+            capi.host.gih_rawscene_get(self._h, which, _vp(buf))
+        return buf.view(dtype)
+
+    def material_names(self):
+        return [bytes(r).split(b"\0")[0].decode() for r in self._get(0, np.uint8).reshape(-1, 32)]
+
+    def vertices(self):
+        return self._get(1, RAW_VERTEX_DTYPE)
+
+    def boxes(self):
+        return self._get(2, np.float32).reshape(-1, 6)
+
+    def nodes(self):
+        return self._get(3, RAW_NODE_DTYPE)
+
+    def leaves(self):
+        return self._get(4, RAW_LEAF_DTYPE)
+
+    def to_scene(self, materials, texture_dir=""):
+        """Scene with the file's hierarchy, every 8-triangle leaf expanded into 2-triangle leaves; materials: dict name -> definition."""
+        env = json.dumps({"scene": "", "accelerator": "aabox", "materials": materials, "lights": {}, "cameras": {}})
+        return Scene(capi.host.gih_scene_from_rawscene(self._h, env.encode(), os.fsencode(texture_dir)))
+
+
 class LightSampler:
     """LightSampler (gpugi/scene/lightsampler.cpp) on its own, for host-logic tests."""
 

@@ -189,6 +189,12 @@ HOST_API = {
     "gih_scene_from_mesh": (vp, [vp, vp, vp, u32, vp, vp, u32, C.c_char_p, C.c_char_p, C.c_int]),
     "gih_scene_from_mesh_bvh": (vp, [vp, vp, vp, u32, vp, vp, u32, C.c_char_p, C.c_char_p, C.c_int, C.c_int]),
     "gih_scene_destroy": (None, [vp]),
+    "gih_rawscene_build": (vp, [vp, vp, vp, u32, vp, vp, u32, P(C.c_char_p), u32, C.c_int]),
+    "gih_rawscene_load": (vp, [C.c_char_p]),
+    "gih_rawscene_store": (C.c_int, [vp, C.c_char_p]),
+    "gih_rawscene_free": (None, [vp]),
+    "gih_rawscene_get": (u64, [vp, C.c_int, vp]),
+    "gih_scene_from_rawscene": (vp, [vp, C.c_char_p, C.c_char_p]),
     "gih_scene_store": (C.c_int, [vp, C.c_char_p, C.c_char_p]),
     "gih_scene_desc": (None, [vp, P(GiSceneDesc)]),
     "gih_scene_info": (None, [vp, P(GihSceneInfo)]),

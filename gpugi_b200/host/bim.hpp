@@ -179,6 +179,14 @@ public:
 	/// Use the order of the JSON "materials" object as the TRIANGLE_MAT index table
 	/// (what load() does for files without a MATERIAL_REFERENCE section, bim_io.cpp:158-163).
 	void useJsonMaterialOrder() { m_materialIndirection = m_materialOrder; }
+	/// Appends a material of the environment file to the TRIANGLE_MAT index table by name (BinaryModel::getUniqueMaterialIndex, bim.cpp:39-55);
+	/// false if there is no such material.
+	bool useMaterialName(const std::string& name)
+	{
+		if (m_materials.find(name) == m_materials.end()) return false;
+		m_materialIndirection.push_back(name);
+		return true;
+	}
 	const Box& getBoundingBox() const { return m_boundingBox; }
 	uint32_t getNumTrianglesPerLeaf() const { return 2; }
 	uint32_t getAccelerator() const { return m_accelerator; }

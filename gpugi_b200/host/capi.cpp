@@ -4,6 +4,7 @@
 #include "../../include/gpugi_b200_host.h"
 
 #include "bidirectionalpathtracer.hpp"
+#include "bvhmake.hpp"
 #include "globalconfig.hpp"
 #include "hdrimage.hpp"
 #include "lightpathtracer.hpp"
@@ -102,6 +103,89 @@ GihScene* gih_scene_from_mesh_bvh(const float* positions, const float* normals, 
 }
 
 void gih_scene_destroy(GihScene* s) { delete s; }
+
+// ---- bvhmake's legacy pipeline (host/bvhmake.hpp)
+struct GihRawScene { gi::bvhmake::RawScene raw; };
+
+GihRawScene* gih_rawscene_build(const float* positions, const float* normals, const float* texcoords, uint32_t num_vertices, const uint32_t* triangles,
+                                const uint32_t* tri_materials, uint32_t num_triangles, const char* const* material_names, uint32_t num_materials, int method)
+{
+	gi::LastHostError().clear();
+	if (!positions || !triangles || num_vertices == 0 || num_triangles == 0 || method < 0 || method > 2) { LOG_ERROR("gih_rawscene_build: bad arguments"); return nullptr; }
+	std::unique_ptr<GihRawScene> h(new GihRawScene());
+	gi::bvhmake::RawScene& r = h->raw;
+	r.vertices.resize(num_vertices);
+	for (uint32_t i = 0; i < num_vertices; ++i)
+	{
+		gi::bvhmake::Vertex& v = r.vertices[i];
+		v.position = {positions[3 * i], positions[3 * i + 1], positions[3 * i + 2]};
+		v.normal = normals ? gi::bim::Vec3{normals[3 * i], normals[3 * i + 1], normals[3 * i + 2]} : gi::bim::Vec3{0.0f, 1.0f, 0.0f};
+		v.texcoord = texcoords ? gi::bim::Vec2{texcoords[2 * i], texcoords[2 * i + 1]} : gi::bim::Vec2{0.0f, 0.0f};
+	}
+	std::vector<gi::bvhmake::Triangle> tris(num_triangles);
+	for (uint32_t t = 0; t < num_triangles; ++t)
+	{
+		for (int k = 0; k < 3; ++k)
+		{
+			if (triangles[3 * t + k] >= num_vertices) { LOG_ERROR("gih_rawscene_build: vertex index out of range"); return nullptr; }
+			tris[t].vertices[k] = triangles[3 * t + k];
+		}
+		tris[t].material = tri_materials ? tri_materials[t] : 0u;
+	}
+	r.materials.resize(num_materials);
+	for (uint32_t i = 0; i < num_materials; ++i)
+	{
+		std::memset(r.materials[i].material, 0, 32);
+		std::strncpy(r.materials[i].material, material_names[i], 31);
+	}
+	gi::bvhmake::BuildHierarchy(r, tris, method == 0 ? gi::bvhmake::BuildMethod::KDTREE : (method == 1 ? gi::bvhmake::BuildMethod::SWEEP : gi::bvhmake::BuildMethod::LDS));
+	return h.release();
+}
+
+GihRawScene* gih_rawscene_load(const char* path)
+{
+	gi::LastHostError().clear();
+	std::unique_ptr<GihRawScene> h(new GihRawScene());
+	std::string err;
+	if (!gi::bvhmake::LoadRawScene(path, h->raw, &err)) { LOG_ERROR(err); return nullptr; }
+	return h.release();
+}
+
+int gih_rawscene_store(GihRawScene* r, const char* path)
+{
+	std::string err;
+	if (!gi::bvhmake::StoreRawScene(path, r->raw, &err)) { LOG_ERROR(err); return 1; }
+	return 0;
+}
+
+void gih_rawscene_free(GihRawScene* r) { delete r; }
+
+uint64_t gih_rawscene_get(GihRawScene* r, int which, void* dst)
+{
+	const void* src = nullptr; uint64_t n = 0;
+	switch (which)
+	{
+	case 0: src = r->raw.materials.data(); n = r->raw.materials.size() * sizeof(gi::bvhmake::MaterialRef); break;
+	case 1: src = r->raw.vertices.data(); n = r->raw.vertices.size() * sizeof(gi::bvhmake::Vertex); break;
+	case 2: src = r->raw.boxes.data(); n = r->raw.boxes.size() * sizeof(gi::bim::Box); break;
+	case 3: src = r->raw.nodes.data(); n = r->raw.nodes.size() * sizeof(gi::bvhmake::Node); break;
+	case 4: src = r->raw.leaves.data(); n = r->raw.leaves.size() * sizeof(gi::bvhmake::Leaf); break;
+	}
+	if (dst && n) std::memcpy(dst, src, n);
+	return n;
+}
+
+GihScene* gih_scene_from_rawscene(GihRawScene* r, const char* env_json, const char* texture_dir)
+{
+	gi::LastHostError().clear();
+	std::unique_ptr<BinaryModel> model(new BinaryModel());
+	std::string err;
+	if (!gi::bvhmake::ToModel(r->raw, env_json ? env_json : "{}", *model, &err)) { LOG_ERROR("raw scene: " << err); return nullptr; }
+	std::unique_ptr<GihScene> h(new GihScene());
+	h->scene = std::make_shared<Scene>(std::move(model), texture_dir ? texture_dir : "", ei::Types3D::BOX);
+	if (!h->scene->IsValid()) return nullptr;
+	return h.release();
+}
 
 int gih_scene_store(GihScene* s, const char* json_path, const char* bim_name)
 {

@@ -55,6 +55,21 @@ GI_API void gih_scene_add_point_light(GihScene* s, const float pos[3], const flo
 GI_API void gih_scene_emissivity(GihScene* s, float* out_rgb /* num_materials*3 */);
 GI_API void gih_scene_point_lights(GihScene* s, float* out_pos_intensity /* num_point_lights*6 */);
 
+/* ---- bvhmake's legacy pipeline (host/bvhmake.hpp): the `.rawscene` container (bvhmake/filedef.hpp:11-89) and the three builders
+ * over 8-triangle leaves (bvhmake/buildmethods/{kdtree,sweep,lds}.cpp) ---- */
+typedef struct GihRawScene GihRawScene;
+/* BVHBuilder::BuildBVH on a mesh: method 0 kdtree, 1 sweep, 2 lds; material_names[i] = materialref entry i (<= 31 characters) */
+GI_API GihRawScene* gih_rawscene_build(const float* positions, const float* normals, const float* texcoords, uint32_t num_vertices, const uint32_t* triangles,
+                                       const uint32_t* tri_materials, uint32_t num_triangles, const char* const* material_names, uint32_t num_materials, int method);
+GI_API GihRawScene* gih_rawscene_load(const char* path);                 /* NULL on failure (gih_last_error) */
+GI_API int gih_rawscene_store(GihRawScene* r, const char* path);
+GI_API void gih_rawscene_free(GihRawScene* r);
+/* which: 0 materialref (32 B) 1 vertices (32 B) 2 bounding_aabox (24 B) 3 hierarchy {parent, firstChild, escape} (12 B) 4 triangles = leaves (128 B);
+ * copies to dst when it is not NULL and returns the size in bytes */
+GI_API uint64_t gih_rawscene_get(GihRawScene* r, int which, void* dst);
+/* The raw scene as a Scene: the file's hierarchy with its 8-triangle leaves expanded into subtrees of 2-triangle leaves; env_json = the material file's text */
+GI_API GihScene* gih_scene_from_rawscene(GihRawScene* r, const char* env_json, const char* texture_dir);
+
 /* LightSampler (lightsampler.cpp) and Camera::ComputeCameraParams (camera.cpp:76-85) on their own. */
 GI_API GihLightSampler* gih_light_sampler_create(GihScene* s);
 GI_API void gih_light_sampler_destroy(GihLightSampler* ls);

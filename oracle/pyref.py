@@ -154,3 +154,35 @@ def ei_light_sample_point(v0, v1, v2, alpha, beta, gamma, bias):
     p, n = np.zeros(3, dtype=np.float32), np.zeros(3, dtype=np.float32)
     lib().ref_ei_light_sample_point(_p(_f3(v0)), _p(_f3(v1)), _p(_f3(v2)), float(alpha), float(beta), float(gamma), float(bias), _p(p), _p(n))
     return p, n
+
+
+# ---- bvhmake's build methods (oracle/_ref/libref_bvhmake.so: buildmethods/kdtree.cpp, sweep.cpp + fitmethods/aaboxfit.cpp of the reference)
+BVHMAKE_LIB_PATH = os.path.join(_HERE, "_ref", "libref_bvhmake.so")
+_bvhmake = None
+
+
+def bvhmake_available():
+    return os.path.exists(BVHMAKE_LIB_PATH)
+
+
+def bvhmake_build(positions, triangles, tri_materials, method="kdtree"):
+    """BVHBuilder::BuildBVH with the reference's own build method -> (nodes {left, right} in pool order, boxes (n, 6), leaves (m, 8, 4) uint32)."""
+    global _bvhmake
+    if _bvhmake is None:
+        _bvhmake = C.CDLL(BVHMAKE_LIB_PATH)
+        _bvhmake.ref_bvhmake_build.restype = C.c_int
+        _bvhmake.ref_bvhmake_build.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                               C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    pos = np.ascontiguousarray(positions, dtype=np.float32)
+    tri = np.ascontiguousarray(triangles, dtype=np.uint32)
+    mat = np.ascontiguousarray(tri_materials, dtype=np.uint32)
+    t = tri.shape[0]
+    cap_nodes, cap_leaves = max(8, 4 * t // 8), max(8, 2 * t // 8)
+    lr = np.zeros((cap_nodes, 2), dtype=np.uint32)
+    boxes = np.zeros((cap_nodes, 6), dtype=np.float32)
+    leaves = np.zeros((cap_leaves, 8, 4), dtype=np.uint32)
+    n, m = C.c_uint32(), C.c_uint32()
+    st = _bvhmake.ref_bvhmake_build(_p(pos), pos.shape[0], _p(tri), _p(mat), t, {"kdtree": 0, "sweep": 1}[method], _p(lr), _p(boxes), _p(leaves), C.byref(n), C.byref(m))
+    if st != 0:
+        raise RuntimeError("reference bvhmake build failed")
+    return lr[: n.value], boxes[: n.value], leaves[: m.value]

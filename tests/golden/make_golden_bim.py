@@ -7,6 +7,7 @@ they lie, oracle/Makefile).  Run in the build container (needs /root/reference);
   ref_bim_arrays.npz                   what the reference's chunk holds for that mesh after buildHierarchy(SAH) and, separately,
                                        buildHierarchy(KD_TREE): hierarchy, parents, leaves, AABoxes, tree levels (+ the input mesh);
                                        plus a 500-triangle random soup through both builders
+  ref_bvhmake_arrays.npz               node pool {left, right}, boxes and 8-triangle leaves of bvhmake's own kdtree and sweep build methods
   ref_ei_kat.npz                       ei::intersects(Ray, Box) / (Ray, Triangle) on 2048 + 2048 seeded random cases: hit flag, distances,
                                        barycentrics
 Usage: python tests/golden/make_golden_bim.py
@@ -64,6 +65,16 @@ def main():
                 if k in ("hierarchy", "parents", "leaves", "aaboxes", "tree_levels", "bounding_box"):
                     out["%s_%s_%s" % (tag, method, k)] = v
     np.savez_compressed(os.path.join(HERE, "ref_bim_arrays.npz"), **out)
+
+    # bvhmake's own build methods (oracle/_ref/libref_bvhmake.so) on the box1 mesh (tess 4) and a 700-triangle soup
+    bv = {}
+    for tag, mesh in [("box1", scenes.box1_mesh(4)), ("soup", soup(700, 6))]:
+        mpos, _, _, mtri, mmat = mesh
+        bv[tag + "_in_positions"], bv[tag + "_in_triangles"], bv[tag + "_in_materials"] = mpos, mtri, mmat
+        for method in ["kdtree", "sweep"]:
+            lr, boxes, leaves = pyref.bvhmake_build(mpos, mtri, mmat, method)
+            bv["%s_%s_children" % (tag, method)], bv["%s_%s_boxes" % (tag, method)], bv["%s_%s_leaves" % (tag, method)] = lr, boxes, leaves
+    np.savez_compressed(os.path.join(HERE, "ref_bvhmake_arrays.npz"), **bv)
 
     # epsilon's routines
     n = 2048
