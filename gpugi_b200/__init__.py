@@ -636,6 +636,17 @@ def config_get(name):
     return [capi.host.gih_config_get(name.encode(), i).decode() for i in range(n)]
 
 
+def load_image(path):
+    """Texture file decoding of the host layer (host/imageio.cpp; the reference: stb_image) -> (h, w, 4) uint8, top row first."""
+    w, h = C.c_int(), C.c_int()
+    if capi.host.gih_load_image(os.fsencode(path), None, 0, C.byref(w), C.byref(h)) != 0:
+        raise GpugiError("load_image: " + capi.host.gih_last_error().decode())
+    out = np.zeros((h.value, w.value, 4), dtype=np.uint8)
+    if capi.host.gih_load_image(os.fsencode(path), _vp(out), w.value * h.value, C.byref(w), C.byref(h)) != 0:
+        raise GpugiError("load_image: " + capi.host.gih_last_error().decode())
+    return out
+
+
 def write_pfm(path, rgba, divisor=1):
     """WritePfm (imageut/hdrimage.cpp:6-33)."""
     rgba = np.ascontiguousarray(rgba, dtype=np.float32)

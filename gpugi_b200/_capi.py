@@ -247,6 +247,7 @@ HOST_API = {
     "gih_config_remove": (None, [C.c_char_p]),
     "gih_config_count": (C.c_int, [C.c_char_p]),
     "gih_config_get": (C.c_char_p, [C.c_char_p, C.c_int]),
+    "gih_load_image": (C.c_int, [C.c_char_p, vp, C.c_int, P(C.c_int), P(C.c_int)]),
     "gih_write_pfm": (C.c_int, [C.c_char_p, vp, C.c_int, C.c_int, u32]),
     "gih_load_pfm": (C.c_int, [C.c_char_p, vp, C.c_int, P(C.c_int), P(C.c_int)]),
 }

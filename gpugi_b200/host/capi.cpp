@@ -5,6 +5,7 @@
 
 #include "bidirectionalpathtracer.hpp"
 #include "bvhmake.hpp"
+#include "imageio.hpp"
 #include "globalconfig.hpp"
 #include "hdrimage.hpp"
 #include "lightpathtracer.hpp"
@@ -444,6 +445,21 @@ const char* gih_config_get(const char* name, int index)
 }
 
 // ---- PFM
+int gih_load_image(const char* path, unsigned char* rgba, int capacity_pixels, int* w, int* h)
+{
+	gi::LastHostError().clear();
+	std::vector<unsigned char> px;
+	std::string err;
+	int iw = 0, ih = 0;
+	if (!gi::LoadImageRGBA8(path, iw, ih, px, &err)) { LOG_ERROR(err); return 1; }
+	if (w) *w = iw;
+	if (h) *h = ih;
+	if (capacity_pixels == 0) return 0;
+	if (size_t(capacity_pixels) < size_t(iw) * ih || !rgba) return 2;
+	std::memcpy(rgba, px.data(), px.size());
+	return 0;
+}
+
 int gih_write_pfm(const char* path, const float* rgba, int w, int h, uint32_t divisor)
 {
 	return WritePfm(reinterpret_cast<const ei::Vec4*>(rgba), ei::IVec2(w, h), path, divisor) ? 0 : 1;

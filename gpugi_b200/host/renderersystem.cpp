@@ -4,6 +4,7 @@
 #include "logger.hpp"
 #include "random.hpp"
 #include "scene.hpp"
+#include "imageio.hpp"
 
 #include <chrono>
 #include <fstream>
@@ -122,22 +123,13 @@ void RendererSystem::SetScene(std::shared_ptr<Scene> _scene)
 }
 
 namespace {
-bool LoadPpmFace(const std::string& file, int size, std::vector<uint8_t>& rgba)
+// one sky face: any format imageio.cpp decodes (the reference: gl::TextureCubemap faces through stb_image), of the given size
+bool LoadSkyFace(const std::string& file, int size, std::vector<uint8_t>& rgba)
 {
-	std::ifstream f(file, std::ios::binary);
-	if (!f) return false;
-	std::string magic;
-	int w = 0, h = 0, maxv = 0;
-	f >> magic >> w >> h >> maxv;
-	f.get();
-	if (!f || magic != "P6" || w != size || h != size || maxv != 255) return false;
-	std::vector<uint8_t> rgb(size_t(w) * h * 3);
-	f.read(reinterpret_cast<char*>(rgb.data()), std::streamsize(rgb.size()));
-	if (!f) return false;
-	for (size_t i = 0; i < size_t(w) * h; ++i)
-	{
-		rgba[4 * i] = rgb[3 * i]; rgba[4 * i + 1] = rgb[3 * i + 1]; rgba[4 * i + 2] = rgb[3 * i + 2]; rgba[4 * i + 3] = 255;
-	}
+	std::vector<unsigned char> px;
+	int w = 0, h = 0;
+	if (!gi::LoadImageRGBA8(file, w, h, px) || w != size || h != size) return false;
+	rgba.assign(px.begin(), px.end());
 	return true;
 }
 }
@@ -148,8 +140,8 @@ void RendererSystem::SetEnvironmentMap(int _size, const std::string& _xneg, cons
 	auto env = std::make_shared<gl::TextureCubemap>(_size);
 	const std::string* files[6] = {&_xneg, &_xpos, &_yneg, &_ypos, &_zneg, &_zpos};
 	for (int i = 0; i < 6; ++i)
-		if (!LoadPpmFace(*files[i], _size, env->Face(i)))
-			LOG_ERROR("Failed to load environment face '" + *files[i] + "' (binary PPM of the given size expected); face stays black.");
+		if (!LoadSkyFace(*files[i], _size, env->Face(i)))
+			LOG_ERROR("Failed to load environment face '" + *files[i] + "' (an image of the given size expected); face stays black.");
 	SetEnvironmentMap(env);
 }
 

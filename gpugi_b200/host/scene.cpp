@@ -1,6 +1,7 @@
 // scene.cpp -- host mirror of gpugi/scene/scene.cpp.  Produces, on the CPU, exactly the arrays the
 // reference uploads to GL, in the layout gi_upload_scene() expects.
 #include "scene.hpp"
+#include "imageio.hpp"
 #include "logger.hpp"
 
 #include <cmath>
@@ -194,59 +195,19 @@ int32_t Scene::AddTexture(const std::string& key, int w, int h, int format, std:
 	return idx;
 }
 
-// scene.cpp:182-199: file texture -> SRGB8_ALPHA8, one level (texture2d.cpp:31-52).  The reference
-// decodes with stb_image; this host reads binary PPM (P6) and raw RGBA8 ("GITX" header) files.
+// scene.cpp:182-199: file texture -> SRGB8_ALPHA8, one level (texture2d.cpp:31-52: stbi_load(file, ..., 4)).  The decoder is imageio.cpp
+// (PNG, JPEG, TGA, BMP, PNM, GITX); a file that cannot be read becomes a 1 x 1 mid-grey texture, with an error in the log.
 int32_t Scene::GetBindlessHandle(const std::string& _name)
 {
 	auto it = m_textureIndex.find(_name);
 	if (it != m_textureIndex.end()) return it->second;
-	std::string path = m_sourceDirectory + _name;
-	std::ifstream f(path, std::ios::binary);
+	const std::string path = m_sourceDirectory + _name;
 	std::vector<unsigned char> rgba;
 	int w = 0, h = 0;
-	bool ok = false;
-	if (f)
+	std::string err;
+	if (!gi::LoadImageRGBA8(path, w, h, rgba, &err))
 	{
-		char magic[4] = {0, 0, 0, 0};
-		f.read(magic, 2);
-		if (magic[0] == 'P' && magic[1] == '6')
-		{
-			int maxv = 0;
-			auto skipComments = [&]() { f >> std::ws; while (f.peek() == '#') { std::string l; std::getline(f, l); f >> std::ws; } };
-			skipComments(); f >> w; skipComments(); f >> h; skipComments(); f >> maxv;
-			f.get();
-			if (f && w > 0 && h > 0 && maxv == 255)
-			{
-				std::vector<unsigned char> rgb(size_t(w) * h * 3);
-				f.read(reinterpret_cast<char*>(rgb.data()), std::streamsize(rgb.size()));
-				if (f)
-				{
-					rgba.resize(size_t(w) * h * 4);
-					for (size_t i = 0; i < size_t(w) * h; ++i)
-					{
-						rgba[4 * i] = rgb[3 * i]; rgba[4 * i + 1] = rgb[3 * i + 1]; rgba[4 * i + 2] = rgb[3 * i + 2]; rgba[4 * i + 3] = 255;
-					}
-					ok = true;
-				}
-			}
-		}
-		else if (magic[0] == 'G' && magic[1] == 'I')
-		{
-			f.read(magic, 2); // "TX"
-			int32_t dims[2] = {0, 0};
-			f.read(reinterpret_cast<char*>(dims), 8);
-			w = dims[0]; h = dims[1];
-			if (f && w > 0 && h > 0)
-			{
-				rgba.resize(size_t(w) * h * 4);
-				f.read(reinterpret_cast<char*>(rgba.data()), std::streamsize(rgba.size()));
-				ok = bool(f);
-			}
-		}
-	}
-	if (!ok)
-	{
-		LOG_ERROR("Failed to load texture '" + path + "' (supported: binary PPM, GITX raw RGBA8); using mid grey.");
+		LOG_ERROR("Error loading texture " + err + "; using mid grey.");
 		w = h = 1;
 		rgba = {128, 128, 128, 255};
 	}

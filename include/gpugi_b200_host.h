@@ -126,6 +126,10 @@ GI_API void gih_config_remove(const char* name);
 GI_API int gih_config_count(const char* name);                                     /* -1: no such parameter */
 GI_API const char* gih_config_get(const char* name, int index);
 
+/* Texture file decoding (host/imageio.hpp; the reference: stbi_load(file, &w, &h, &n, 4), texture2d.cpp:31-52): width * height RGBA8 texels, top row
+ * first.  capacity_pixels == 0 only queries the size.  0 = ok, 1 = cannot decode (gih_last_error), 2 = buffer too small. */
+GI_API int gih_load_image(const char* path, unsigned char* rgba, int capacity_pixels, int* w, int* h);
+
 /* WritePfm / LoadPfm (imageut/hdrimage.cpp:6-60) */
 GI_API int gih_write_pfm(const char* path, const float* rgba, int w, int h, uint32_t divisor);
 GI_API int gih_load_pfm(const char* path, float* rgb, int capacity_pixels, int* w, int* h);

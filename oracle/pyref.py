@@ -186,3 +186,27 @@ def bvhmake_build(positions, triangles, tri_materials, method="kdtree"):
     if st != 0:
         raise RuntimeError("reference bvhmake build failed")
     return lr[: n.value], boxes[: n.value], leaves[: m.value]
+
+
+# ---- stb_image as vendored by the reference (oracle/_ref/libref_stb.so)
+STB_LIB_PATH = os.path.join(_HERE, "_ref", "libref_stb.so")
+_stb = None
+
+
+def stb_available():
+    return os.path.exists(STB_LIB_PATH)
+
+
+def stbi_load(path):
+    """stbi_load(path, &w, &h, &n, 4) -> ((h, w, 4) uint8, n) or None."""
+    global _stb
+    if _stb is None:
+        _stb = C.CDLL(STB_LIB_PATH)
+        _stb.ref_stbi_load.restype = C.c_int
+        _stb.ref_stbi_load.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    w, h, n = C.c_int(), C.c_int(), C.c_int()
+    if _stb.ref_stbi_load(os.fsencode(path), None, 0, C.byref(w), C.byref(h), C.byref(n)) != 0:
+        return None
+    out = np.zeros((h.value, w.value, 4), dtype=np.uint8)
+    _stb.ref_stbi_load(os.fsencode(path), _p(out), w.value * h.value, C.byref(w), C.byref(h), C.byref(n))
+    return out, n.value
