@@ -169,6 +169,8 @@ struct DScene
 	uint32_t numMaterials;
 	int rootIsLeaf;          // scene with a single leaf: no fast nodes
 	int fastOrderValid;      // leaf indices increase in preorder (needed by nothing but asserted at upload)
+	int refTreeBinary;       // every inner node of the reference tree has exactly two children (firstChild, and firstChild's escape)
+	int oboxOrdered;         // per frame: bvhType = 1 scene walked nearest child first (traceOrderedOBox) instead of in the reference's order
 	float ambiguityAbs;      // absolute part of the near-tie window (scaled with the scene extent)
 	int textureFilterExact;  // GI_OPT_TEXTURE_FILTER
 };
@@ -440,13 +442,122 @@ done:
 	return false;
 }
 
+// ------------------------------------------------------------------ ordered walk of an oriented-box hierarchy (bvhType = 1)
+// The reference reaches a node of an OBox hierarchy iff the oriented-box test of EVERY ancestor passed (intersectiontests.glsl:114-128; unlike bim's
+// AABoxes, independently fitted oriented boxes are not nested, so the leaf's own box does not imply its ancestors').  This walk therefore stays on
+// the reference's own tree and applies the reference's own test (fetchIntersectNode: same rotation, same slab arithmetic) to every node it reaches --
+// but takes the nearer child first from a short stack and culls by entry distance, where the stackless reference walk tests every node whose
+// ancestors were hit in file order.  The set of leaves reachable without the distance cull is identical by construction; the cull and the visit
+// order can only matter among candidates inside the near-tie window, which are detected exactly as in traceFast() and re-traced in reference order.
+template <bool ANY_HIT>
+GI_HD bool traceOrderedOBox(const DScene& s, F3 o, F3 d, float& rayLength, int& hitLeafTri, TraceStats* st, bool* usedFallback)
+{
+	const F3 inv = invDir(d);
+	const float tMaxInit = rayLength;
+	const float margin = (1.0f + GI_AMBIGUITY_REL) * (1.0f + GI_AMBIGUITY_REL);
+	hitLeafTri = -1;
+	float best = tMaxInit, second = GI_INF;
+	bool ambiguous = false;
+	StackEntry stack[GI_STACK_SIZE];
+	int sp = 0;
+	// `node` is a node whose own box test has passed; the root's comes first, as in the reference (traceray.glsl:56-69)
+	int node = 0;
+	uint32_t childCode; int escape;
+	{
+		float f, l;
+		if (st) ++st->nodes;
+		if (!(fetchIntersectNode(s, o, d, inv, 0, f, l, childCode, escape) && f <= tMaxInit)) { return false; }
+	}
+	for (;;)
+	{
+		const F4 a = ld4(s.oboxNodes + 3 * size_t(node));
+		childCode = uint32_t(f2i(a.w));
+		if (childCode & 0x80000000u)
+		{
+			// leaf node: both triangle slots (traceray.glsl:122-170)
+			const int leaf = int(childCode & 0x7fffffffu);
+			for (int slot = 0; slot < 2; ++slot)
+			{
+				const int lt = 2 * leaf + slot;
+				F3 p0, p1, p2; int valid;
+				loadLeafTri(s, lt, p0, p1, p2, valid);
+				if (!valid) break;
+				if (st) ++st->tris;
+				float t; F3 nb, nn;
+				if (intersectTriangle(o, d, p0, p1, p2, t, nb, nn) && t < tMaxInit)
+				{
+					if (ANY_HIT) return true;
+					if (t < best) { if (hitLeafTri >= 0) second = best; best = t; hitLeafTri = lt; }
+					else second = fminf(second, t);
+				}
+			}
+		}
+		else
+		{
+			const float limit = ANY_HIT ? tMaxInit : (best * margin + s.ambiguityAbs);
+			const int left = int(childCode);
+			uint32_t c0, c1; int e0, e1;
+			float f0, l0, f1, l1;
+			if (st) st->nodes += 2;
+			const bool h0 = fetchIntersectNode(s, o, d, inv, left, f0, l0, c0, e0) && f0 <= limit;
+			const int right = e0; // the second child is the node behind the first child's subtree
+			const bool h1 = fetchIntersectNode(s, o, d, inv, right, f1, l1, c1, e1) && f1 <= limit;
+			if (h0 && h1)
+			{
+				const bool swap = f1 < f0;
+				const int nearNode = swap ? right : left, farNode = swap ? left : right;
+				const float farFirst = swap ? f0 : f1;
+				if (sp < GI_STACK_SIZE) { stack[sp].node = farNode; stack[sp].first = farFirst; ++sp; }
+				else ambiguous = true; // the subtree is skipped: the ray is answered by the stackless reference walk
+				node = nearNode;
+				continue;
+			}
+			if (h0) { node = left; continue; }
+			if (h1) { node = right; continue; }
+		}
+		// pop
+		for (;;)
+		{
+			if (sp == 0) goto done;
+			--sp;
+			node = stack[sp].node;
+			const float limit = ANY_HIT ? tMaxInit : (best * margin + s.ambiguityAbs);
+			if (stack[sp].first <= limit) break;
+		}
+	}
+done:
+	if (ANY_HIT)
+	{
+		if (ambiguous) { float len = tMaxInit; return traceReference<true>(s, o, d, len, hitLeafTri, st); }
+		return false;
+	}
+	if (hitLeafTri >= 0)
+	{
+		const float window = best * GI_AMBIGUITY_REL + s.ambiguityAbs;
+		if (second <= best + window) ambiguous = true;
+		if (best + window >= tMaxInit) ambiguous = true;
+	}
+	if (ambiguous)
+	{
+		if (usedFallback) *usedFallback = true;
+		rayLength = tMaxInit;
+		return traceReference<false>(s, o, d, rayLength, hitLeafTri, st);
+	}
+	rayLength = best;
+	return false;
+}
+
 // Closest hit with all outputs of TraceRay (traceray.glsl:25-48): the winning triangle is re-tested
 // once to produce barycentrics and the geometric normal (same inputs => same bits as during the walk).
 GI_HD void traceClosest(const DScene& s, int traversalMode, F3 o, F3 d, float tMax, Hit& h, TraceStats* st, bool* usedFallback)
 {
 	h.t = tMax;
 	h.leafTri = -1;
-	if (traversalMode == GI_TRAVERSAL_REFERENCE) traceReference<false>(s, o, d, h.t, h.leafTri, st);
+	if (traversalMode == GI_TRAVERSAL_REFERENCE)
+	{
+		if (s.oboxOrdered) traceOrderedOBox<false>(s, o, d, h.t, h.leafTri, st, usedFallback);
+		else traceReference<false>(s, o, d, h.t, h.leafTri, st);
+	}
 	else traceFast<false>(s, o, d, h.t, h.leafTri, st, usedFallback);
 	if (h.leafTri >= 0)
 	{
@@ -466,7 +577,11 @@ GI_HD void traceClosest(const DScene& s, int traversalMode, F3 o, F3 d, float tM
 GI_HD bool traceAny(const DScene& s, int traversalMode, F3 o, F3 d, float rayLength, TraceStats* st)
 {
 	int dummy; float len = rayLength;
-	if (traversalMode == GI_TRAVERSAL_REFERENCE) return traceReference<true>(s, o, d, len, dummy, st);
+	if (traversalMode == GI_TRAVERSAL_REFERENCE)
+	{
+		if (s.oboxOrdered) return traceOrderedOBox<true>(s, o, d, len, dummy, st, nullptr);
+		return traceReference<true>(s, o, d, len, dummy, st);
+	}
 	return traceFast<true>(s, o, d, len, dummy, st, nullptr);
 }
 

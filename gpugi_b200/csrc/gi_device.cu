@@ -640,6 +640,8 @@ static DFrame makeFrame(GiContext* c, const GiIterationParams* p)
 	std::memset(&f, 0, sizeof(f));
 	f.scene = c->scene;
 	f.scene.textureFilterExact = c->textureFilterExact;
+	// bvhType = 1: GI_TRAVERSAL_FAST selects the ordered walk on the oriented boxes (the reference-order kernels host it)
+	f.scene.oboxOrdered = (c->scene.oboxNodes && c->scene.refTreeBinary && c->traversal == GI_TRAVERSAL_FAST) ? 1 : 0;
 	f.cam = c->cam;
 	f.width = c->width; f.height = c->height;
 	f.lightSamples = c->externalLightSamples ? c->externalLightSamples : c->lightSamples + size_t(c->lightSlot) * 2u * size_t(c->numLightSamples);
@@ -1882,6 +1884,7 @@ int gi_trace_device(GiContext* c, const GiRay* d_rays, uint32_t n, GiHit* d_hits
 	if (n == 0) return GI_OK;
 	GI_CUDA(c, cudaSetDevice(c->device));
 	DScene s = c->scene;
+	s.oboxOrdered = (s.oboxNodes && s.refTreeBinary && c->traversal == GI_TRAVERSAL_FAST) ? 1 : 0;
 	const int mode = c->fastValid ? c->traversal : GI_TRAVERSAL_REFERENCE;
 	if (mode == GI_TRAVERSAL_FAST && c->scheduler == GI_SCHEDULER_WAVEFRONT)
 	{

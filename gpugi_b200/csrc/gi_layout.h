@@ -472,6 +472,21 @@ inline bool buildHostLayout(const GiSceneDesc* d, HostLayout& L, std::string& er
 		std::memcpy(L.oboxNodes.data(), d->obox_nodes, size_t(d->num_nodes) * sizeof(GiOBoxNode));
 		L.binary = false;
 	}
+	// structure only (no box conditions): what the ordered walk of an oriented-box hierarchy needs
+	{
+		bool two = true;
+		for (uint32_t i = 0; i < d->num_nodes && two; ++i)
+		{
+			const GiNode& n = d->nodes[i];
+			if (n.first_child & 0x80000000u) continue;
+			const uint32_t left = n.first_child;
+			if (left == 0 || left >= d->num_nodes) { two = false; break; }
+			const uint32_t right = d->nodes[left].escape;
+			if (right == 0 || right >= d->num_nodes || right == n.escape || d->nodes[right].escape != n.escape) two = false;
+		}
+		L.scene.refTreeBinary = two ? 1 : 0;
+	}
+	L.scene.oboxOrdered = 0;
 	L.scene.fastOrderValid = L.binary ? 1 : 0;
 	L.scene.leafPreorder = preorder ? 1 : 0;
 	{

@@ -370,7 +370,15 @@ GI_D void wfTraceLoopReference(const DScene& s, const IO& io, uint32_t* workCoun
 			io.load(s, mine, L, dummy); // ray + root test (the walk below repeats the root test itself)
 			TraceStats st = {0, 0};
 			float len = L.tMaxInit; int leafTri = -1;
-			if (L.flags & WFL_ANY) { if (traceReference<true>(s, L.o, L.d, len, leafTri, &st)) L.flags |= WFL_OCCLUDED; }
+			bool fb = false;
+			if (s.oboxOrdered)
+			{
+				// bvhType = 1 with the ordered walk (traceOrderedOBox): exact, nearest child first
+				if (L.flags & WFL_ANY) { if (traceOrderedOBox<true>(s, L.o, L.d, len, leafTri, &st, nullptr)) L.flags |= WFL_OCCLUDED; }
+				else traceOrderedOBox<false>(s, L.o, L.d, len, leafTri, &st, &fb);
+				if (fb) cnt.template add<WFC_FALLBACK>(1u);
+			}
+			else if (L.flags & WFL_ANY) { if (traceReference<true>(s, L.o, L.d, len, leafTri, &st)) L.flags |= WFL_OCCLUDED; }
 			else traceReference<false>(s, L.o, L.d, len, leafTri, &st);
 			cnt.template add<WFC_NODES>(st.nodes); cnt.template add<WFC_TRIS>(st.tris);
 			L.best = len; L.hitLeaf = leafTri; L.flags |= WFL_EXACT;

@@ -179,6 +179,8 @@ EM_API int em_trace(const GiSceneDesc* desc, const GiRay* rays, uint32_t n, GiHi
 	EmScene e; std::string err;
 	if (!makeScene(desc, e, err)) return 1;
 	if (fast_valid) *fast_valid = e.L.binary ? 1 : 0;
+	// bvhType = 1: GI_TRAVERSAL_FAST selects the ordered walk on the oriented boxes, hosted by the reference-order entry points (gi_device.cu: makeFrame)
+	e.s.oboxOrdered = (mode == GI_TRAVERSAL_FAST && e.s.oboxNodes && e.s.refTreeBinary) ? 1 : 0;
 	if (!e.L.binary) mode = GI_TRAVERSAL_REFERENCE;
 	for (uint32_t i = 0; i < n; ++i)
 	{

@@ -366,10 +366,14 @@ def test_obox_hierarchy_traversal(g, orc, emul, scenes, tmp_path):
     rays["flags"][:8000] = 1
     rays["t_max"][:8000] = rng.rand(8000) * 20
     ref = orc.trace_batch(sc1.desc, rays)
-    for mode in (0, 1, 2):  # fast / lane requests fall back to the reference-order walk: the ordered walk is built on AABoxes
+    work = {}
+    for mode in (0, 1, 2):  # 0: the ordered walk on the oriented boxes (traceOrderedOBox); 1: reference order; 2 (lane walk, built on AABoxes): falls back to 1
         hits, cnt = emul.trace(sc1.desc, rays, mode=mode)
         assert cnt["fast_valid"] == 0
         assert np.array_equal(hits["leaf_tri"], ref["leaf_tri"]) and np.array_equal(hits["t"].view(np.uint32), ref["t"].view(np.uint32))
+        work[mode] = cnt
+    assert work[0]["node_tests"] < work[1]["node_tests"] and work[2]["node_tests"] == work[1]["node_tests"]   # (a sparse soup seen from outside: little to cull)
+    assert 0 < work[0]["fallback_rays"] < 1000 and work[1]["fallback_rays"] == 0
     aabox = orc.trace_batch(sc0.desc, rays)
     assert (aabox["leaf_tri"] == ref["leaf_tri"]).mean() > 0.9995
     # .bim round trip (OBOX_BVH = 0x02000000, 40-byte ei::OBox elements)

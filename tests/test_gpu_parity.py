@@ -221,11 +221,44 @@ def test_obox_hierarchy_on_device(g, orc, scenes):
     ref = orc.trace_batch(sc.desc, rays)
     dev = g.Device(0)
     dev.upload_scene(sc)
-    for sched in (g.GI_SCHEDULER_WAVEFRONT, g.GI_SCHEDULER_MEGAKERNEL):
-        dev.set_option(g.GI_OPT_SCHEDULER, sched)
-        hits = dev.trace(rays)
-        assert np.array_equal(hits["leaf_tri"], ref["leaf_tri"])
-        assert np.array_equal(hits["t"].view(np.uint32), ref["t"].view(np.uint32))
+    tests = {}
+    for mode in (g.GI_TRAVERSAL_REFERENCE, g.GI_TRAVERSAL_FAST):
+        # GI_TRAVERSAL_FAST on an oriented-box hierarchy = the ordered walk on the reference's own tree and boxes (traceOrderedOBox): nearest
+        # child first, near ties re-traced in reference order -- the same answers from fewer box tests
+        dev.set_option(g.GI_OPT_TRAVERSAL, mode)
+        for sched in (g.GI_SCHEDULER_WAVEFRONT, g.GI_SCHEDULER_MEGAKERNEL):
+            dev.set_option(g.GI_OPT_SCHEDULER, sched)
+            dev.reset_counters()
+            hits = dev.trace(rays)
+            assert np.array_equal(hits["leaf_tri"], ref["leaf_tri"]), (mode, sched)
+            assert np.array_equal(hits["t"].view(np.uint32), ref["t"].view(np.uint32))
+            tests[(mode, sched)] = dev.counters()
+    slow, fast = tests[(g.GI_TRAVERSAL_REFERENCE, g.GI_SCHEDULER_MEGAKERNEL)], tests[(g.GI_TRAVERSAL_FAST, g.GI_SCHEDULER_MEGAKERNEL)]
+    assert fast["node_tests"] < 0.8 * slow["node_tests"] and fast["triangle_tests"] < slow["triangle_tests"]
+    assert 0 < fast["exact_fallback_rays"] < n // 20
+    dev.set_option(g.GI_OPT_TRAVERSAL, g.GI_TRAVERSAL_FAST)
+    dev.close()
+    # exact ties on an oriented-box hierarchy (coincident faces) and a whole BPT / LPT iteration in both walks
+    tie = scenes.make_box1(tess=4, coincident_faces=True, bvh_type=1)
+    from tests.conftest import make_ray_batch
+    tr = make_ray_batch(g, tie, 100000, 17, any_fraction=0.25)
+    want = orc.trace_batch(tie.desc, tr)
+    dev = g.Device(0)
+    dev.upload_scene(tie)
+    got = dev.trace(tr)
+    assert np.array_equal(got["leaf_tri"], want["leaf_tri"]) and np.array_equal(got["t"].view(np.uint32), want["t"].view(np.uint32))
+    dev.set_screen_size(64, 64)
+    C = scenes.BOX1_CAMERA
+    dev.set_camera(g.camera_params(C["pos"], C["lookat"], C["fov"], 64, 64))
+    dev.set_light_samples(g.LightSampler(tie).generate(256))
+    lpt = {}
+    for mode in (g.GI_TRAVERSAL_REFERENCE, g.GI_TRAVERSAL_FAST):
+        dev.set_option(g.GI_OPT_TRAVERSAL, mode)
+        dev.clear()
+        dev.render_iteration(g.GI_RENDERER_LPT, g.wang_hash(1), 16, num_rays_per_light_sample=64)
+        lpt[mode] = dev.read_accumulator(64, 64)
+    assert lpt[g.GI_TRAVERSAL_FAST][..., :3].sum() > 0
+    assert np.abs(lpt[g.GI_TRAVERSAL_FAST] - lpt[g.GI_TRAVERSAL_REFERENCE]).max() <= 1e-5 * np.abs(lpt[g.GI_TRAVERSAL_REFERENCE]).max()
     dev.close()
     from tests.conftest import pixel_mismatch_fraction
     imgs = {}
