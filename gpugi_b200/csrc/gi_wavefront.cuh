@@ -73,6 +73,70 @@ struct WfTune
 	int reserved;
 };
 
+// ---- cache policy of the queue traffic (WF_STREAM_HINTS)
+// Ray / hit / shadow records and path states stream through the GPU once per wave (several hundred MB, more than the 126 MB L2), while
+// the hierarchy, the leaf block, vertices, materials and textures are gathered again and again.  Queue loads and stores therefore carry
+// the streaming hint (ld.global.cs / st.global.cs: evict-first in L1 and L2) so that they do not push the scene out of the L2.
+#ifndef WF_STREAM_HINTS
+#define WF_STREAM_HINTS 1
+#endif
+GI_D float4 qld4(const void* p)
+{
+#if WF_STREAM_HINTS
+	return __ldcs(reinterpret_cast<const float4*>(p));
+#else
+	return *reinterpret_cast<const float4*>(p);
+#endif
+}
+GI_D F4 qldF4(const F4* p)
+{
+#if WF_STREAM_HINTS
+	const float4 v = __ldcs(reinterpret_cast<const float4*>(p)); F4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w; return r;
+#else
+	return ld4(p);
+#endif
+}
+GI_D void qst4(void* p, float4 v)
+{
+#if WF_STREAM_HINTS
+	__stcs(reinterpret_cast<float4*>(p), v);
+#else
+	*reinterpret_cast<float4*>(p) = v;
+#endif
+}
+GI_D float2 qld2(const float2* p)
+{
+#if WF_STREAM_HINTS
+	return __ldcs(p);
+#else
+	return *p;
+#endif
+}
+GI_D void qst2(float2* p, float2 v)
+{
+#if WF_STREAM_HINTS
+	__stcs(p, v);
+#else
+	*p = v;
+#endif
+}
+GI_D float qld1(const float* p)
+{
+#if WF_STREAM_HINTS
+	return __ldcs(p);
+#else
+	return *p;
+#endif
+}
+GI_D void qst1(float* p, float v)
+{
+#if WF_STREAM_HINTS
+	__stcs(p, v);
+#else
+	*p = v;
+#endif
+}
+
 GI_D F4 f4zero() { F4 r; r.x = r.y = r.z = r.w = 0.0f; return r; }
 GI_D unsigned laneId() { return threadIdx.x & 31u; }
 GI_D unsigned lanemaskLt() { unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
@@ -121,12 +185,13 @@ GI_D void wfSplat(float* accum, int width, int height, uint32_t pixel, F3 v)
 	atomicAdd(reinterpret_cast<float4*>(p), make_float4(v.x, v.y, v.z, 0.0f));
 }
 
-template <class CNT>
-GI_D void wfFinishShadow(const WfTraceIO& io, uint32_t slot, bool occluded, CNT& cnt)
+// An unoccluded shadow ray delivers what it carries: s1 = (direction, target word), v = (value, splat ring slot) of shadow record `slot`.
+// REDUCE: the path's radiance sum is updated with a reduction instead of a read-modify-write (the same single round-to-nearest addition --
+// nobody else touches the record during trace(w); red.add.f32 flushes subnormals, which a radiance sum never holds), so that the lane does
+// not wait for the old value.
+template <bool REDUCE, class CNT>
+GI_D void wfDeliverShadowImpl(const WfTraceIO& io, uint32_t slot, F4 s1, F4 v, CNT& cnt)
 {
-	if (occluded) return;
-	const F4 s1 = ld4(io.shadow + 3 * size_t(slot) + 1);
-	const F4 v = ld4(io.shadow + 3 * size_t(slot) + 2);
 	const uint32_t word = uint32_t(f2i(s1.w));
 	const uint32_t id = word & WF_ID_MASK;
 	if (word & WF_FLAG_SPLAT)
@@ -146,9 +211,29 @@ GI_D void wfFinishShadow(const WfTraceIO& io, uint32_t slot, bool occluded, CNT&
 		return;
 	}
 	// the path's radiance sum: one shadow ray per path and wave, and shade() is another kernel -> exclusive
-	float4 c = *reinterpret_cast<const float4*>(io.stateC + id);
+	if (REDUCE)
+	{
+		float* c = reinterpret_cast<float*>(io.stateC + id);
+		asm volatile("red.global.add.f32 [%0], %1;" :: "l"(c), "f"(v.x) : "memory");
+		asm volatile("red.global.add.f32 [%0], %1;" :: "l"(c + 1), "f"(v.y) : "memory");
+		asm volatile("red.global.add.f32 [%0], %1;" :: "l"(c + 2), "f"(v.z) : "memory");
+		return;
+	}
+	float4 c = qld4(io.stateC + id);
 	c.x += v.x; c.y += v.y; c.z += v.z;
-	*reinterpret_cast<float4*>(io.stateC + id) = c;
+	qst4(io.stateC + id, c);
+}
+
+template <class CNT>
+GI_D void wfDeliverShadow(const WfTraceIO& io, uint32_t slot, F4 s1, F4 v, CNT& cnt) { wfDeliverShadowImpl<true>(io, slot, s1, v, cnt); }
+
+template <class CNT>
+GI_D void wfFinishShadow(const WfTraceIO& io, uint32_t slot, bool occluded, CNT& cnt)
+{
+	if (occluded) return;
+	const F4 s1 = qldF4(io.shadow + 3 * size_t(slot) + 1);
+	const F4 v = qldF4(io.shadow + 3 * size_t(slot) + 2);
+	wfDeliverShadowImpl<false>(io, slot, s1, v, cnt);
 }
 
 // The persistent trace loop.  IO provides: total(), load(index, lane state), finish(lane state).
@@ -350,6 +435,139 @@ GI_D void wfTraceLoop(const DScene& s, const IO& io, uint32_t* workCounter, WfTu
 	}
 }
 
+// ---- the same loop with the latencies of retire and refill taken off the warp's critical path (WF_PIPELINED_REFILL)
+// A warp of the loop above stalls as a whole on every refill (work-counter atomic -> ray load from HBM -> root test: three dependent
+// round trips, ~3 us) and on every retired shadow ray (shadow record -> path state read-modify-write).  That is why it refills late
+// (24 idle lanes) and runs at ~20 of 32 lanes.  Here every one of those steps is issued in one outer iteration and consumed in the
+// next, with the data parked in shared memory by cp.async (no registers are held across the traversal steps in between):
+//   refill   S0 the leader's atomicAdd on the work counter is issued, its result is left in the register
+//            S1 (next iteration) the result is broadcast, every reserved lane starts the asynchronous copy of its ray into its staging slot
+//            S2 (next iteration) the rays are read from shared memory and begun
+//   retire   a finished shadow ray that reached its light copies (target word, value) of its record into a second staging slot; the
+//            lane is free at once; one iteration later the value joins the path's radiance sum with a fire-and-forget reduction
+//            (exclusive: one shadow ray per path and wave, and shade() is another kernel -- the same single IEEE addition as before)
+// Measured on B200 (C2 PT batch, ms per iteration, k_wf_trace alone in brackets; refill threshold 24 / 16 / 12 / 8 / 6):
+//   this loop      1.996 (1.630) / 2.160 / 2.247 / 2.372 / 2.428        the loop above   1.689 (1.323) / - / 1.749 (1.384) / - / -
+// Slower at every threshold: the reserved lanes sit idle for two more outer iterations, and what a lower threshold costs is not latency but
+// INSTRUCTIONS -- ncu of the loop above at thresholds 24 / 12 / 6: 955 / 974 / 1016 M warp instructions for the same 17.1 G thread
+// instructions (17.96 / 17.50 / 16.87 lanes per instruction): ~250 instructions of retire + per-ray setup per refill event, run at few lanes,
+// outweigh the fuller traversal steps.  Off; kept as the record of the experiment (profiles/r02_refill_experiment.md).
+#ifndef WF_PIPELINED_REFILL
+#define WF_PIPELINED_REFILL 0
+#endif
+
+GI_D void wfAsyncWaitAll() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+GI_D void wfAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+
+template <class IO, class CNT>
+GI_D void wfTraceLoopPipelined(const DScene& s, const IO& io, uint32_t* workCounter, WfTune tune, CNT& cnt)
+{
+	StackEntry entries[GI_STACK_SIZE];
+	WfStackArray stack; stack.e = entries;
+	WfCand cand[WF_MAX_CAND];
+	__shared__ F4 wfRefillA[WF_TRACE_THREADS], wfRefillB[WF_TRACE_THREADS];   // staged ray: first two F4 of the work item
+	__shared__ F4 wfFinishA[WF_TRACE_THREADS], wfFinishB[WF_TRACE_THREADS];   // staged tail of a finished work item
+	__shared__ uint32_t wfFinishIndex[WF_TRACE_THREADS];
+	WfLane L;
+	L.node = WF_NODE_DONE;
+	bool active = false;
+	bool poolEmpty = false;
+	bool finishPending = false;
+	const uint32_t total = io.total();
+	const unsigned lane = laneId();
+	// refill request in flight (warp-uniform): 0 none, 1 atomic issued, 2 ray copies issued
+	int reqStage = 0, reqLeader = 0;
+	unsigned reqMask = 0u;
+	uint32_t reqBase = 0u;     // the leader's atomic result (only consumed one iteration after it was issued)
+	uint32_t reqIndex = 0u;    // this lane's work item of the request
+	for (;;)
+	{
+		// ---- deferred tail of the work items finished in the previous iteration
+		if (__any_sync(0xffffffffu, finishPending))
+		{
+			if (finishPending)
+			{
+				wfAsyncWaitAll();
+				io.finishStaged(s, wfFinishIndex[threadIdx.x], wfFinishA[threadIdx.x], wfFinishB[threadIdx.x], cnt);
+				finishPending = false;
+			}
+		}
+		// ---- S2: the staged rays start
+		if (reqStage == 2)
+		{
+			if ((reqMask >> lane) & 1u)
+			{
+				wfAsyncWaitAll();
+				io.begin(s, reqIndex, wfRefillA[threadIdx.x], wfRefillB[threadIdx.x], L, cnt);
+				active = true;
+			}
+			reqStage = 0;
+		}
+		// ---- S1: the work counter's answer is there: start the copies
+		if (reqStage == 1)
+		{
+			const uint32_t base = __shfl_sync(0xffffffffu, reqBase, reqLeader);
+			const uint32_t n = uint32_t(__popc(reqMask));
+			reqIndex = base + uint32_t(__popc(reqMask & lanemaskLt()));
+			const bool mine = ((reqMask >> lane) & 1u) && reqIndex < total;
+			if (mine)
+			{
+				const F4* src = io.address(reqIndex);
+				wfAsyncCopy16(&wfRefillA[threadIdx.x], src);
+				wfAsyncCopy16(&wfRefillB[threadIdx.x], src + 1);
+			}
+			wfAsyncCommit();
+			reqMask = __ballot_sync(0xffffffffu, mine);
+			if (base + n >= total) poolEmpty = true;
+			reqStage = reqMask ? 2 : 0;
+		}
+		// ---- retire finished rays (together, when a refill is due or nothing else is left to do)
+		{
+			const bool finished = active && wfFinished(L);
+			const unsigned waiting = __ballot_sync(0xffffffffu, finished || !active);
+			if ((poolEmpty || __popc(waiting) >= tune.refillThreshold || waiting == 0xffffffffu) && finished && wfEndOfWalk(L, s, cand, cnt))
+			{
+				const F4* tail = io.finishNow(s, L, cnt);
+				if (tail)
+				{
+					wfAsyncCopy16(&wfFinishA[threadIdx.x], tail);
+					wfAsyncCopy16(&wfFinishB[threadIdx.x], tail + 1);
+					wfAsyncCommit();
+					wfFinishIndex[threadIdx.x] = L.index;
+					finishPending = true;
+				}
+				active = false;
+			}
+		}
+		// ---- S0: reserve work for the idle lanes
+		const unsigned idle = __ballot_sync(0xffffffffu, !active);
+		if (reqStage == 0 && !poolEmpty && (__popc(idle) >= tune.refillThreshold || idle == 0xffffffffu))
+		{
+			reqLeader = __ffs(idle) - 1;
+			reqMask = idle;
+			if (int(lane) == reqLeader) reqBase = atomicAdd(workCounter, uint32_t(__popc(idle)));
+			reqStage = 1;
+		}
+		if (idle == 0xffffffffu)
+		{
+			if (poolEmpty && reqStage == 0 && !__any_sync(0xffffffffu, finishPending)) break;
+			continue;
+		}
+		// ---- one leaf step for the lanes waiting at a leaf
+		if (active) wfStash(L, stack);
+		if (active && wfAtLeaf(L)) wfLeafStep(L, s, stack, cand, cnt);
+		// ---- inner-node steps while enough lanes are at inner nodes
+		unsigned innerMask = __ballot_sync(0xffffffffu, L.node >= 0);
+		if (innerMask == 0u) continue;
+		const int keepGoing = max(1, (__popc(__ballot_sync(0xffffffffu, active && !wfFinished(L))) * tune.minInner) >> 5); // lanes still walking
+		do
+		{
+			if (L.node >= 0) wfInnerStep(L, s, stack, cnt);
+			innerMask = __ballot_sync(0xffffffffu, L.node >= 0);
+		} while (__popc(innerMask) >= keepGoing);
+	}
+}
+
 // Reference-order variant (GI_TRAVERSAL_REFERENCE): same work distribution, every lane walks its ray with the
 // stackless escape-pointer loop of traceray.glsl from start to end.
 template <class IO, class CNT>
@@ -406,13 +624,27 @@ struct WfQueueIO
 	GI_D void load(const DScene& s, uint32_t index, WfLane& L, CNT& cnt) const
 	{
 		const F4* p = address(index);
-		begin(s, index, ld4(p), ld4(p + 1), L, cnt);
+		begin(s, index, qldF4(p), qldF4(p + 1), L, cnt);
 	}
 	template <class CNT>
 	GI_D void finish(const DScene& s, WfLane& L, CNT& cnt) const
 	{
 		if (L.flags & WFL_ANY) wfFinishShadow(q, L.index - q.numClosest, (L.flags & WFL_OCCLUDED) != 0u, cnt);
-		else q.hits[q.rayBase + L.index] = make_float2(L.best, i2f(L.hitLeaf));
+		else qst2(q.hits + q.rayBase + L.index, make_float2(L.best, i2f(L.hitLeaf)));
+	}
+	// WF_PIPELINED_REFILL: the part of finish() that needs no load; returns the two consecutive F4 the deferred part wants staged (or nullptr)
+	template <class CNT>
+	GI_D const F4* finishNow(const DScene& s, WfLane& L, CNT& cnt) const
+	{
+		if (L.flags & WFL_ANY) return (L.flags & WFL_OCCLUDED) ? nullptr : q.shadow + 3 * size_t(L.index - q.numClosest) + 1;
+		qst2(q.hits + q.rayBase + L.index, make_float2(L.best, i2f(L.hitLeaf)));
+		return nullptr;
+	}
+	// ... and the deferred part: an unoccluded shadow ray delivers its value (s1 = (direction, target word), v = (value, splat slot))
+	template <class CNT>
+	GI_D void finishStaged(const DScene& s, uint32_t index, F4 s1, F4 v, CNT& cnt) const
+	{
+		wfDeliverShadow(q, index - q.numClosest, s1, v, cnt);
 	}
 };
 
@@ -454,6 +686,10 @@ struct WfBatchIO
 		}
 		hits[L.index] = out;
 	}
+	template <class CNT>
+	GI_D const F4* finishNow(const DScene& s, WfLane& L, CNT& cnt) const { finish(s, L, cnt); return nullptr; }
+	template <class CNT>
+	GI_D void finishStaged(const DScene&, uint32_t, F4, F4, CNT&) const {}
 };
 
 // ------------------------------------------------------------------ path tracer waves (pathtracer.comp:16-110)
@@ -505,8 +741,8 @@ GI_D void wfShadePT(const WfFrame& w, uint32_t slot, bool valid, unsigned* cnt)
 	if (valid)
 	{
 		const F4* rp = q.rays[w.wave & 1] + 2 * size_t(slot);
-		const F4 r0 = ld4(rp), r1 = ld4(rp + 1);
-		const float2 hrec = q.hits[slot];
+		const F4 r0 = qldF4(rp), r1 = qldF4(rp + 1);
+		const float2 hrec = qld2(q.hits + slot);
 		const uint32_t word = uint32_t(f2i(r1.w));
 		id = word & WF_ID_MASK;
 		didNEE = (word & WF_FLAG_NEE) != 0u;
@@ -536,17 +772,17 @@ GI_D void wfShadePT(const WfFrame& w, uint32_t slot, bool valid, unsigned* cnt)
 			{
 				// the slot is recycled: iteration - S is complete, its radiance joins the accumulator (pathtracer.comp:107-109;
 				// per pixel in iteration order, alpha += 0)
-				const float4 old = *reinterpret_cast<const float4*>(q.stateC + sidx);
+				const float4 old = qld4(q.stateC + sidx);
 				float4* px = reinterpret_cast<float4*>(f.accum) + id;
-				float4 a = *px;
+				float4 a = qld4(px);
 				a.x += old.x; a.y += old.y; a.z += old.z; a.w += old.w;
-				*px = a;
+				qst4(px, a);
 			}
 		}
 		else
 		{
-			const float4 t = *reinterpret_cast<const float4*>(q.stateT + sidx);
-			const float4 c = *reinterpret_cast<const float4*>(q.stateC + sidx);
+			const float4 t = qld4(q.stateT + sidx);
+			const float4 c = qld4(q.stateC + sidx);
 			pathThroughput = f3(t.x, t.y, t.z); seed = uint32_t(f2i(t.w));
 			color = f3(c.x, c.y, c.z);
 		}
@@ -593,8 +829,8 @@ GI_D void wfShadePT(const WfFrame& w, uint32_t slot, bool valid, unsigned* cnt)
 				pushRay = true;
 			}
 		}
-		*reinterpret_cast<float4*>(q.stateC + sidx) = make_float4(color.x, color.y, color.z, 0.0f);
-		if (pushRay) *reinterpret_cast<float4*>(q.stateT + sidx) = make_float4(pathThroughput.x, pathThroughput.y, pathThroughput.z, i2f(int(seed)));
+		qst4(q.stateC + sidx, make_float4(color.x, color.y, color.z, 0.0f));
+		if (pushRay) qst4(q.stateT + sidx, make_float4(pathThroughput.x, pathThroughput.y, pathThroughput.z, i2f(int(seed))));
 	}
 	uint32_t* next = wfCounts(w, w.wave + 1);
 	const uint32_t sslot = warpPush(next + 1, pushShadow);
@@ -602,9 +838,9 @@ GI_D void wfShadePT(const WfFrame& w, uint32_t slot, bool valid, unsigned* cnt)
 	{
 		++cnt[WFC_ANY];
 		F4* sp = q.shadow + 3 * size_t(sslot);
-		*reinterpret_cast<float4*>(sp) = make_float4(nee.origin.x, nee.origin.y, nee.origin.z, nee.len);
-		*reinterpret_cast<float4*>(sp + 1) = make_float4(nee.dir.x, nee.dir.y, nee.dir.z, i2f(int(sidx)));
-		*reinterpret_cast<float4*>(sp + 2) = make_float4(neeValue.x, neeValue.y, neeValue.z, 0.0f);
+		qst4(sp, make_float4(nee.origin.x, nee.origin.y, nee.origin.z, nee.len));
+		qst4(sp + 1, make_float4(nee.dir.x, nee.dir.y, nee.dir.z, i2f(int(sidx))));
+		qst4(sp + 2, make_float4(neeValue.x, neeValue.y, neeValue.z, 0.0f));
 	}
 	const uint32_t rslot = w.pushBase + warpPush(next, pushRay);
 	if (pushRay)
@@ -612,8 +848,8 @@ GI_D void wfShadePT(const WfFrame& w, uint32_t slot, bool valid, unsigned* cnt)
 		++cnt[WFC_CLOSEST];
 		F4* rp = q.rays[(w.wave + 1) & 1] + 2 * size_t(rslot);
 		const uint32_t word = id | (didNEE ? WF_FLAG_NEE : 0u);
-		*reinterpret_cast<float4*>(rp) = make_float4(origin.x, origin.y, origin.z, i2f(bounce + 1));
-		*reinterpret_cast<float4*>(rp + 1) = make_float4(dir.x, dir.y, dir.z, i2f(int(word)));
+		qst4(rp, make_float4(origin.x, origin.y, origin.z, i2f(bounce + 1)));
+		qst4(rp + 1, make_float4(dir.x, dir.y, dir.z, i2f(int(word))));
 	}
 }
 
@@ -624,8 +860,8 @@ GI_D void wfAddCounters(unsigned* cnt, const PathCounters& pc)
 	cnt[WFC_SHADED] += pc.shadedVertices; cnt[WFC_SPLATS] += pc.splats; cnt[WFC_FALLBACK] += pc.fallbackRays;
 }
 
-GI_D F4 ldState(const F4* p) { const float4 v = *reinterpret_cast<const float4*>(p); F4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w; return r; }
-GI_D void stState(F4* p, F4 v) { *reinterpret_cast<float4*>(p) = make_float4(v.x, v.y, v.z, v.w); }
+GI_D F4 ldState(const F4* p) { const float4 v = qld4(p); F4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w; return r; }
+GI_D void stState(F4* p, F4 v) { qst4(p, make_float4(v.x, v.y, v.z, v.w)); }
 
 // warp-compacted push of what a shaded vertex produced (all 32 lanes call)
 GI_D void wfPushOut(const WfFrame& w, const WfPush& out, uint32_t shadowTarget, int bounce, uint32_t id, uint32_t splatSlot = 0u)
@@ -636,17 +872,17 @@ GI_D void wfPushOut(const WfFrame& w, const WfPush& out, uint32_t shadowTarget, 
 	if (out.shadow)
 	{
 		F4* sp = q.shadow + 3 * size_t(sslot);
-		*reinterpret_cast<float4*>(sp) = make_float4(out.sOrigin.x, out.sOrigin.y, out.sOrigin.z, out.sLen);
-		*reinterpret_cast<float4*>(sp + 1) = make_float4(out.sDir.x, out.sDir.y, out.sDir.z, i2f(int(shadowTarget)));
-		*reinterpret_cast<float4*>(sp + 2) = make_float4(out.sValue.x, out.sValue.y, out.sValue.z, i2f(int(splatSlot)));
+		qst4(sp, make_float4(out.sOrigin.x, out.sOrigin.y, out.sOrigin.z, out.sLen));
+		qst4(sp + 1, make_float4(out.sDir.x, out.sDir.y, out.sDir.z, i2f(int(shadowTarget))));
+		qst4(sp + 2, make_float4(out.sValue.x, out.sValue.y, out.sValue.z, i2f(int(splatSlot))));
 		if (q.shadowPos && (shadowTarget & WF_FLAG_SPLAT)) q.shadowPos[sslot] = make_float2(out.posX, out.posY);
 	}
 	const uint32_t rslot = w.pushBase + warpPush(next, out.ray);
 	if (out.ray)
 	{
 		F4* rp = q.rays[(w.wave + 1) & 1] + 2 * size_t(rslot);
-		*reinterpret_cast<float4*>(rp) = make_float4(out.origin.x, out.origin.y, out.origin.z, i2f(bounce + 1));
-		*reinterpret_cast<float4*>(rp + 1) = make_float4(out.dir.x, out.dir.y, out.dir.z, i2f(int(id)));
+		qst4(rp, make_float4(out.origin.x, out.origin.y, out.origin.z, i2f(bounce + 1)));
+		qst4(rp + 1, make_float4(out.dir.x, out.dir.y, out.dir.z, i2f(int(id))));
 	}
 }
 
@@ -674,8 +910,8 @@ GI_D void wfGenerateLight(const WfFrame& w, uint32_t gid, PathCounters& pc)
 	const uint32_t sidx = (uint32_t(w.wave) % w.q.numSlots) * w.q.numIds + gid;
 	stState(w.q.stateT + sidx, T);
 	F4* rp = w.q.rays[w.wave & 1] + 2 * size_t(gid);
-	*reinterpret_cast<float4*>(rp) = make_float4(origin.x, origin.y, origin.z, i2f(0));
-	*reinterpret_cast<float4*>(rp + 1) = make_float4(dir.x, dir.y, dir.z, i2f(int(gid)));
+	qst4(rp, make_float4(origin.x, origin.y, origin.z, i2f(0)));
+	qst4(rp + 1, make_float4(dir.x, dir.y, dir.z, i2f(int(gid))));
 }
 
 // shade(w) of the light tracer: one lane per hit record of a light path
@@ -687,8 +923,8 @@ GI_D void wfShadeLight(const WfFrame& w, uint32_t slot, bool valid, PathCounters
 	if (valid)
 	{
 		const F4* rp = w.q.rays[w.wave & 1] + 2 * size_t(slot);
-		const F4 r0 = ld4(rp), r1 = ld4(rp + 1);
-		const float2 hrec = w.q.hits[slot];
+		const F4 r0 = qldF4(rp), r1 = qldF4(rp + 1);
+		const float2 hrec = qld2(w.q.hits + slot);
 		id = uint32_t(f2i(r1.w)) & WF_ID_MASK;
 		bounce = f2i(r0.w);
 		const uint32_t iteration = uint32_t(w.wave - bounce);
@@ -714,8 +950,8 @@ GI_D void wfShadeEye(const WfFrame& w, uint32_t slot, bool valid, PathCounters& 
 	if (valid)
 	{
 		const F4* rp = w.q.rays[w.wave & 1] + 2 * size_t(slot);
-		const F4 r0 = ld4(rp), r1 = ld4(rp + 1);
-		const float2 hrec = w.q.hits[slot];
+		const F4 r0 = qldF4(rp), r1 = qldF4(rp + 1);
+		const float2 hrec = qld2(w.q.hits + slot);
 		id = uint32_t(f2i(r1.w)) & WF_ID_MASK;
 		bounce = f2i(r0.w);
 		const uint32_t iteration = uint32_t(w.wave - bounce);
@@ -723,20 +959,20 @@ GI_D void wfShadeEye(const WfFrame& w, uint32_t slot, bool valid, PathCounters& 
 		if (bounce == 0 && iteration >= w.q.numSlots)
 		{
 			// the slot is recycled: iteration - S is complete, its radiance joins the accumulator (pathtracer_bidir.comp:248-250)
-			const float4 old = *reinterpret_cast<const float4*>(w.q.stateC + sidx);
+			const float4 old = qld4(w.q.stateC + sidx);
 			float4* px = reinterpret_cast<float4*>(w.f.accum) + id;
-			float4 a = *px;
+			float4 a = qld4(px);
 			a.x += old.x; a.y += old.y; a.z += old.z; a.w += old.w;
-			*px = a;
+			qst4(px, a);
 		}
 		F4 T = f4zero(), C = f4zero(); float M = 1.0f;
-		if (bounce > 0) { T = ldState(w.q.stateT + sidx); C = ldState(w.q.stateC + sidx); M = w.q.stateM[sidx]; }
+		if (bounce > 0) { T = ldState(w.q.stateT + sidx); C = ldState(w.q.stateC + sidx); M = qld1(w.q.stateM + sidx); }
 		DFrame f = w.f;
 		wfSelectCache(f, iteration);
 		const uint32_t numEntries = *f.lightCacheCount; // complete: the light pass of this iteration ended before its eye pass began
 		wfShadeEyeLane(f, numEntries, f3(r0.x, r0.y, r0.z), f3(r1.x, r1.y, r1.z), bounce, id, hrec.x, f2i(hrec.y), T, C, M, out, pc);
 		stState(w.q.stateC + sidx, C);
-		if (out.ray) { stState(w.q.stateT + sidx, T); w.q.stateM[sidx] = M; }
+		if (out.ray) { stState(w.q.stateT + sidx, T); qst1(w.q.stateM + sidx, M); }
 	}
 	wfPushOut(w, out, sidx, bounce, id);
 }
