@@ -155,7 +155,8 @@ struct DScene
 	                         // unused slot = empty box; WF_WIDE4=0: 8 words per binary inner node (c0.xyz, c1.xyz, child0, child1)
 	float gridLo[3];         // grid origin (root box min) and cell size per axis
 	float gridScale[3];
-	float gridAbsMax[3];     // max(|root box min|, |root box max|) per axis: bound of every plane coordinate (WF_FLOAT_PLANES error bound)
+	float gridAbsMax[3];     // max(|root box min|, |root box max|) per axis: bound of every plane coordinate
+	float cePmax;            // the largest of the three (WF_CENTRE_EXTENT error bound)
 	const F4* leafPos;       // 6 x F4 per leaf: slot s -> [3s] = (p0.xyz, .), [3s+1] = (p1.xyz, .), [3s+2] = (p2.xyz, .); an unused slot has
 	                         // p0.x = NaN (vertex positions are checked to be finite at upload).  The six .w hold the leaf node's own box:
 	                         // [0..2].w = box.min.xyz, [3..5].w = box.max.xyz

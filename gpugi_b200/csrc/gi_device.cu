@@ -229,8 +229,8 @@ __global__ void __launch_bounds__(256) k_light_samples(DLightTables t, unsigned 
 #define WF_TRACE_THREADS 128
 #endif
 #ifndef WF_TRACE_MIN_BLOCKS
-#define WF_TRACE_MIN_BLOCKS 7   // 72 registers, 7 x 4 warps per SM (B200 A/B at refill 24 / vote 16: 6 -> 2.378*, 7 -> 2.137, 8 -> 2.168, 9 -> 2.255*, 10 -> 2.269* ms per PT iteration; * at 16/20)
-#endif
+#define WF_TRACE_MIN_BLOCKS (WF_CENTRE_EXTENT ? 9 : 7)   // centre / half-extent records: 56 registers, 9 x 4 warps per SM (B200 A/B, ms per PT iteration C2 / C5: 7 -> 1.669 / 15.04,
+#endif                                                  // 8 -> 1.649 / 14.74, 9 -> 1.645 / 14.66, 10 -> 1.705 / -); 16-bit grid records: 72 registers, 7 blocks (round 1: 6 -> 2.378, 7 -> 2.137, 8 -> 2.168, 9 -> 2.255)
 #define WF_SHADE_THREADS 128
 #ifndef WF_SHADE_MIN_BLOCKS
 #define WF_SHADE_MIN_BLOCKS 8   // k_wf_shade_pt: 64 registers, 8 blocks per SM (B200 A/B, PT batch: 1 -> 2.246, 8 -> 2.195, 10 -> 2.208, 12 -> 2.241 ms/iteration)

@@ -52,13 +52,16 @@ struct WfCounters
 #ifndef WF_WIDE4
 #define WF_WIDE4 1         // 4-wide inner nodes (gi_layout.h: emitWide4): 64-byte records, two 256-bit loads, up to three pushes per step.
 #endif                     // B200 A/B against the binary nodes (0), ms per iteration: C2 PT 1.810 -> 1.765, C3 BPT 8.82 -> 8.38, C4 LPT 4K 8.06 -> 7.32, C5 PT 4K 17.77 -> 15.42
-#ifndef WF_FLOAT_PLANES
-#define WF_FLOAT_PLANES 0  // 4-wide nodes with the child boxes as FLOATS, grouped per axis (min x4 | max x4): 128-byte records, the near / far planes
-#endif                     // are picked by the load address (sign of the direction), no decode and no select in the slab test (needs WF_WIDE4)
-#if WF_FLOAT_PLANES && !WF_WIDE4
-#error "WF_FLOAT_PLANES needs WF_WIDE4"
-#endif
-#define WF_NODE_WORDS (WF_FLOAT_PLANES ? 32 : (WF_WIDE4 ? 16 : 8)) // words per record of DScene::qNodes
+#ifndef WF_CENTRE_EXTENT
+#define WF_CENTRE_EXTENT 1 // 4-wide nodes with the child boxes as (centre: float, half extent: bfloat16): 96-byte records, three 256-bit loads, NO decode
+#endif                     // and NO near / far selection in the slab test (needs WF_WIDE4, WF_CACHE_INV): per step 24 PRMT + 24 FFMA become 36 FFMA + 6 shifts, the
+                           // lane state loses 15 registers (71 registers without spills instead of 72 with; 9 blocks per SM at 56).  B200 A/B against the 16-bit grid
+                           // records (0) at 7 blocks per SM, ms per iteration: C2 1.680 -> 1.663, C3 7.462 -> 7.281, C4 6.580 -> 6.590, C5 14.82 -> 15.02 (50 % more node
+                           // bytes); at 9 blocks per SM: C2 1.645, C3 7.175, C4 6.509, C5 14.66 (8: 1.649 / - / - / 14.74; 10: 1.705 / 7.468 / 6.841 / -).  +0.8 % box tests.
+// (History: WF_FLOAT_PLANES -- 128-byte records with the 24 planes as floats grouped per axis so that the load address picks the near / far side,
+//  seven 128-bit loads per step -- measured 1.786 vs 1.722 ms on C2 and 15.96 vs 14.95 ms on C5 in round 1: the L1 traffic cost more than the
+//  saved decode.  Removed in favour of the centre / half-extent records, which save the same decode with three loads.)
+#define WF_NODE_WORDS (WF_CENTRE_EXTENT ? 24 : (WF_WIDE4 ? 16 : 8)) // words per record of DScene::qNodes
 #ifndef WF_STEP_OVERFLOW_CHECK
 #define WF_STEP_OVERFLOW_CHECK 0 // one stack-capacity check per 4-wide step instead of one per push (B200: 1.660 vs 1.653 ms, off)
 #endif
@@ -70,6 +73,9 @@ struct WfCounters
 #endif
 #ifndef WF_CACHE_INV
 #define WF_CACHE_INV 1     // 1/d kept in the lane state for the leaf gate instead of three IEEE divisions per leaf step (B200: 1.712 -> 1.692 ms)
+#endif
+#if WF_CENTRE_EXTENT && !(WF_WIDE4 && WF_CACHE_INV)
+#error "WF_CENTRE_EXTENT needs WF_WIDE4 and WF_CACHE_INV"
 #endif
 #define WF_MAX_CAND 8
 
@@ -83,12 +89,9 @@ struct WfLane
 #if WF_CACHE_INV
 	F3 inv;          // invDir(d), the same three IEEE quotients the leaf gate would recompute
 #endif
-#if WF_FLOAT_PLANES
-	// conservative inner-node test on float planes: distance of plane p along axis k = fma(p, cellInv.k, biasNear.k / biasFar.k)
-	F3 cellInv;      // 1/d
-	F3 biasNear;     // -o * (1/d) -/+ error bound
-	F3 biasFar;
-	uint32_t offNear[3]; // word offset of the four near planes of axis k inside a node record (8k, or 8k + 4 for a negative direction); far = ^ 4
+#if WF_CENTRE_EXTENT
+	// conservative inner-node test on (centre, half extent): distance of the box centre along axis k = fma(c, inv.k, negOInv.k), near / far = -/+ h * |inv.k|
+	F3 negOInv;      // -(o * (1/d))
 #else
 	// conservative inner-node test on the 16-bit grid (wfSlabTest): distance of grid plane q along axis k
 	//   near planes  fma(2^23 + q, cellInv.k, biasNear.k)      far planes  fma(2^23 + q, cellInv.k, biasFar.k)
@@ -283,33 +286,33 @@ GI_HD float wfMin3(float a, float b, float c)
 #endif
 }
 
-#if WF_FLOAT_PLANES
-// Float planes.  Reference (exact zone): t_ref = fl(inv * fl(p - o)), |t_ref - T| <= 2.01u |T| with T = (p - o) * inv and |T| <= (|p| + |o|) |inv|.
-// Here: c = fl(-o * inv), c' = fl(c -/+ E), t = fl(p * inv + c') (one FMA):
-//   |c - (-o inv)| <= u |o inv|,   |c' - (c -/+ E)| <= u (|c| + E),   |t - (p inv + c')| <= u (|p inv| + |c| + E)
-//   => |t +/- E - T| <= u (3.01 |o| + 1.01 |p|) |inv| + 2.01 u E, and with the reference's own rounding the planes are bracketed as soon as
-//   E (1 - 2.01u) >= u |inv| (5.02 |o| + 3.02 |p|).   E := 8u |inv| (|o| + P), P = max |coordinate| of the root box >= |p|, satisfies it.
-// Hence near.k <= tmin.k and far.k >= tmax.k of IntersectBox for every box inside the root box, and
-//   (first <= last && first <= limit)  ==>  the conservative test accepts.
-// Zero / denormal direction components and products near overflow are outside the domain (answered by the reference walk).
+#if WF_CENTRE_EXTENT
+// Centre / half-extent records.  Per child and axis the record holds a float c and a bfloat16 h with [c - h0, c + h0] containing the child's box
+// in real arithmetic and h = h0 + e, e >= 330 u Pmax (u = 2^-24, Pmax = largest |coordinate| of the root box; gi_layout.h: emitWide4 checks both
+// in double).  With inv = fl(1/d), T(p) = (p - o) inv the real-number distance of plane p, the reference (exact zone) computes
+//   t_ref(p) = fl(inv * fl(p - o)),   |t_ref(p) - T(p)| <= 2.01 u |T(p)| <= 2.01 u (Pmax + |o|) |inv|.
+// Here:   m = fl(-(o inv))   tc = fl(c inv + m)   near = fl(tc - h |inv|)   far = fl(tc + h |inv|)          (three FMAs, no decode, no selection)
+//   |tc - (c - o) inv| <= u |o inv| (1 + u) + u |c - o| |inv|
+//   |near - ((c - o) inv - h |inv|)| <= 1.01 u |inv| (3 |o| + 2 |c| + h) <= 1.01 u |inv| (3 |o| + 3 P'),   P' = 1.02 Pmax >= |c| + h (checked at upload)
+// A true plane p of the child lies at least e inside [c - h, c + h], so T(p) is at least e |inv| inside [(c - o) inv -/+ h |inv|], and
+//   near <= tmin.k,  far >= tmax.k of IntersectBox (intersectiontests.glsl:12-15)   as soon as   e >= u (2.01 (Pmax + |o|) + 3.03 (|o| + P')) ,
+// which e = 330 u Pmax satisfies for every ray with |o.k| <= 60 Pmax.  Hence (first <= last && first <= limit) ==> the conservative test accepts.
+// Rays outside that domain (origin farther than 60 Pmax from the coordinate origin, zero / denormal direction components, products near
+// overflow or underflow) are answered by the stackless reference walk (WFL_OVERFLOW).
 GI_HD bool wfSlabSetup(WfLane& L, const DScene& s, F3 o, F3 inv)
 {
-	const float u = 5.9604644775390625e-08f; // 2^-24
+	const float P = s.cePmax;
 	const float iv[3] = {inv.x, inv.y, inv.z}, ov[3] = {o.x, o.y, o.z};
-	float bn[3], bf[3], m = 0.0f;
+	float m[3];
+	bool ok = true;
 	for (int k = 0; k < 3; ++k)
 	{
-		const float c = -(ov[k] * iv[k]);
-		const float reach = (fabsf(ov[k]) + s.gridAbsMax[k]) * fabsf(iv[k]);
-		const float E = (8.0f * u) * reach + 1.0e-37f;
-		bn[k] = c - E; bf[k] = c + E;
-		m = fmaxf(m, reach);
-		L.offNear[k] = uint32_t(8 * k) + (iv[k] < 0.0f ? 4u : 0u);
+		m[k] = -(ov[k] * iv[k]);
+		const float reach = fmaxf(fabsf(ov[k]), P) * fabsf(iv[k]);
+		ok = ok && (fabsf(ov[k]) <= 60.0f * P) && (reach < 1.0e30f) && (P * fabsf(iv[k]) >= 1.0e-30f); // all false for NaN
 	}
-	L.cellInv = inv;
-	L.biasNear = f3(bn[0], bn[1], bn[2]);
-	L.biasFar = f3(bf[0], bf[1], bf[2]);
-	return m < 1.0e30f; // false for NaN / inf as well
+	L.negOInv = f3(m[0], m[1], m[2]);
+	return ok;
 }
 #else
 // Per-ray constants of the conservative test.  Returns false when the ray is outside the domain of the error bound.
@@ -359,7 +362,7 @@ GI_HD void wfBegin(WfLane& L, const DScene& s, F3 o, F3 d, float tMax, bool isAn
 	if (!inDomain && L.node != WF_NODE_DONE) { L.flags |= WFL_OVERFLOW; L.node = WF_NODE_DONE; }
 }
 
-#if !WF_FLOAT_PLANES
+#if !WF_CENTRE_EXTENT
 // Conservative accept test of one child box (three words: x, y, z; min plane | max plane << 16): never rejects a box the
 // exact-zone test (first <= last && first <= limit) accepts.  nearLow is a lower bound of the exact-zone entry distance.
 GI_HD bool wfSlabTest(const WfLane& L, uint32_t wx, uint32_t wy, uint32_t wz, float& nearLow)
@@ -375,42 +378,51 @@ GI_HD bool wfSlabTest(const WfLane& L, uint32_t wx, uint32_t wy, uint32_t wz, fl
 }
 #endif
 
-#if WF_FLOAT_PLANES
-// conservative test of the four children at once is in wfInnerStep; this is the same test for ONE child of the record at `node` (test hook)
-GI_HD bool wfSlabTestChild(const WfLane& L, const uint32_t* node, int child, float& nearLow)
+#if WF_CENTRE_EXTENT
+// 96-byte record (24 words): 0..11 centre of child k, axis a at 3k + a (float); 12..17 half extents as bfloat16 pairs, word 12 + 3 (k >> 1) + a =
+// (h of the even child | h of the odd child << 16); 18..19 unused; 20..23 child links (wide index >= 0, leaf = ~leafIndex).  The odd child's half
+// extent is the word itself read as a float (the even child's bits only enlarge it, by < 2^-7), the even child's is the word shifted left by 16 --
+// a multiplication by 65536 on the FMA pipe.  An unused slot has c = 0 and h = -65536 Pmax: near > far for every ray inside the domain.
+GI_HD float wfHalfExtent(uint32_t word, int child)
 {
-	const float* f = reinterpret_cast<const float*>(node);
-	const float nx = wfFma(f[L.offNear[0] + child], L.cellInv.x, L.biasNear.x), fx = wfFma(f[(L.offNear[0] ^ 4u) + child], L.cellInv.x, L.biasFar.x);
-	const float ny = wfFma(f[L.offNear[1] + child], L.cellInv.y, L.biasNear.y), fy = wfFma(f[(L.offNear[1] ^ 4u) + child], L.cellInv.y, L.biasFar.y);
-	const float nz = wfFma(f[L.offNear[2] + child], L.cellInv.z, L.biasNear.z), fz = wfFma(f[(L.offNear[2] ^ 4u) + child], L.cellInv.z, L.biasFar.z);
-	nearLow = fmaxf(wfMax3(nx, ny, nz), 0.0f);
-	return nearLow <= fminf(wfMin3(fx, fy, fz), L.limit);
+	return i2f(int((child & 1) ? word : word * 65536u));
 }
 
-// 4-wide inner node with float planes: six 128-bit loads (near / far planes of the four children per axis, the address picks the side) + the links
+GI_HD void wfCentreTest(const WfLane& L, float cx, float cy, float cz, float hx, float hy, float hz, float& nearLow, float& farHigh)
+{
+	const float tx = wfFma(cx, L.inv.x, L.negOInv.x), ty = wfFma(cy, L.inv.y, L.negOInv.y), tz = wfFma(cz, L.inv.z, L.negOInv.z);
+	const float ax = fabsf(L.inv.x), ay = fabsf(L.inv.y), az = fabsf(L.inv.z);
+	nearLow = fmaxf(wfMax3(wfFma(hx, -ax, tx), wfFma(hy, -ay, ty), wfFma(hz, -az, tz)), 0.0f);
+	farHigh = fminf(wfMin3(wfFma(hx, ax, tx), wfFma(hy, ay, ty), wfFma(hz, az, tz)), L.limit);
+}
+
+// the conservative test of ONE child of the record at `node` (test hook; wfInnerStep does the same for all four)
+GI_HD bool wfSlabTestChild(const WfLane& L, const uint32_t* node, int child, float& nearLow)
+{
+	const int hb = 12 + 3 * (child >> 1);
+	float farHigh;
+	wfCentreTest(L, i2f(int(node[3 * child])), i2f(int(node[3 * child + 1])), i2f(int(node[3 * child + 2])),
+	             wfHalfExtent(node[hb], child), wfHalfExtent(node[hb + 1], child), wfHalfExtent(node[hb + 2], child), nearLow, farHigh);
+	return nearLow <= farHigh;
+}
+
 template <class STK, class CNT>
 GI_HD void wfInnerStep(WfLane& L, const DScene& s, const STK& stack, CNT& cnt)
 {
-	const uint32_t* nb = s.qNodes + 32 * size_t(L.node);
-	const F4 nx = ld4(reinterpret_cast<const F4*>(nb + L.offNear[0])), fx = ld4(reinterpret_cast<const F4*>(nb + (L.offNear[0] ^ 4u)));
-	const F4 ny = ld4(reinterpret_cast<const F4*>(nb + L.offNear[1])), fy = ld4(reinterpret_cast<const F4*>(nb + (L.offNear[1] ^ 4u)));
-	const F4 nz = ld4(reinterpret_cast<const F4*>(nb + L.offNear[2])), fz = ld4(reinterpret_cast<const F4*>(nb + (L.offNear[2] ^ 4u)));
-	const F4 lk = ld4(reinterpret_cast<const F4*>(nb + 24));
+	const uint32_t* nb = s.qNodes + 24 * size_t(L.node);
+	const U8 a = ld8(nb), b = ld8(nb + 8), c = ld8(nb + 16);
 	cnt.template add<WFC_NODES>(4u); cnt.template add<WFC_INNER_STEPS>(1u);
-#define WF_CHILD(m, out) { \
-		const float nn = fmaxf(wfMax3(wfFma(nx.m, L.cellInv.x, L.biasNear.x), wfFma(ny.m, L.cellInv.y, L.biasNear.y), wfFma(nz.m, L.cellInv.z, L.biasNear.z)), 0.0f); \
-		const float ff = fminf(wfMin3(wfFma(fx.m, L.cellInv.x, L.biasFar.x), wfFma(fy.m, L.cellInv.y, L.biasFar.y), wfFma(fz.m, L.cellInv.z, L.biasFar.z)), L.limit); \
-		out = nn <= ff ? nn : GI_INF; }
-	float f0, f1, f2, f3v;
-	WF_CHILD(x, f0) WF_CHILD(y, f1) WF_CHILD(z, f2) WF_CHILD(w, f3v)
-#undef WF_CHILD
-	int c0 = f2i(lk.x), c1 = f2i(lk.y), c2 = f2i(lk.z), c3 = f2i(lk.w);
-#if WF_CSWAP_MINMAX
-	// compare-exchange as min / max + two selects (5 ALU instructions); the branchy form compiles to a chain of predicated moves (~9)
+	float f0, f1, f2, f3v, far;
+	wfCentreTest(L, i2f(int(a.v[0])), i2f(int(a.v[1])), i2f(int(a.v[2])), wfHalfExtent(b.v[4], 0), wfHalfExtent(b.v[5], 0), wfHalfExtent(b.v[6], 0), f0, far);
+	if (!(f0 <= far)) f0 = GI_INF;
+	wfCentreTest(L, i2f(int(a.v[3])), i2f(int(a.v[4])), i2f(int(a.v[5])), wfHalfExtent(b.v[4], 1), wfHalfExtent(b.v[5], 1), wfHalfExtent(b.v[6], 1), f1, far);
+	if (!(f1 <= far)) f1 = GI_INF;
+	wfCentreTest(L, i2f(int(a.v[6])), i2f(int(a.v[7])), i2f(int(b.v[0])), wfHalfExtent(b.v[7], 2), wfHalfExtent(c.v[0], 2), wfHalfExtent(c.v[1], 2), f2, far);
+	if (!(f2 <= far)) f2 = GI_INF;
+	wfCentreTest(L, i2f(int(b.v[1])), i2f(int(b.v[2])), i2f(int(b.v[3])), wfHalfExtent(b.v[7], 3), wfHalfExtent(c.v[0], 3), wfHalfExtent(c.v[1], 3), f3v, far);
+	if (!(f3v <= far)) f3v = GI_INF;
+	int c0 = int(c.v[4]), c1 = int(c.v[5]), c2 = int(c.v[6]), c3 = int(c.v[7]);
 #define WF_CSWAP(fa, ca, fb, cb) { const bool sw = fb < fa; const float lo = fminf(fa, fb), hi = fmaxf(fa, fb); const int cl = sw ? cb : ca, ch = sw ? ca : cb; fa = lo; fb = hi; ca = cl; cb = ch; }
-#else
-#define WF_CSWAP(fa, ca, fb, cb) { if (fb < fa) { const float tf = fa; fa = fb; fb = tf; const int tc = ca; ca = cb; cb = tc; } }
-#endif
 	WF_CSWAP(f0, c0, f1, c1) WF_CSWAP(f2, c2, f3v, c3) WF_CSWAP(f0, c0, f2, c2) WF_CSWAP(f1, c1, f3v, c3) WF_CSWAP(f1, c1, f2, c2)
 #undef WF_CSWAP
 	if (f0 < GI_INF)

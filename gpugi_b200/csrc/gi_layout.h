@@ -3,7 +3,7 @@
 //   refNodes   the 32-byte TreeNode<Box> array as is (reference-order walk / exact fallback)
 //   fastNodes  one 64-byte record per binary INNER node carrying both child boxes + child links (one-thread-per-path kernels)
 //   qNodes     the wavefront walk's records: 4-wide nodes (emitWide4) with the child boxes on a 16-bit grid over the root box;
-//              build switches: binary records (WF_WIDE4=0), float planes (WF_FLOAT_PLANES)
+//              build switches: binary records (WF_WIDE4=0), centre / half-extent records (WF_CENTRE_EXTENT)
 //   leafPos    vertex positions gathered per leaf triangle slot (3 x 16 B) + the leaf node's own box in the .w components
 //   materials  Scene::Material with 1x1 constant textures folded into the record
 // fastNodes / qNodes stand on the reference's topology (buildHostLayout) or on any other binary tree over the reference's leaves
@@ -54,6 +54,7 @@ struct FastEmitter
 			if (!(sc > 1.0e-30f)) sc = 1.0e-30f;
 			L.scene.gridLo[k] = lo; L.scene.gridScale[k] = sc;
 			L.scene.gridAbsMax[k] = std::fmax(std::fabs(lo), std::fabs(hi));
+			L.scene.cePmax = k == 0 ? L.scene.gridAbsMax[0] : std::fmax(L.scene.cePmax, L.scene.gridAbsMax[k]);
 			gridLo[k] = double(lo); gridScale[k] = double(sc);
 		}
 	}
@@ -182,33 +183,60 @@ inline bool emitWide4(const GiSceneDesc* d, HostLayout& L, const LeafTree& t, st
 			++n;
 		}
 		const size_t base = q.size();
-#if WF_FLOAT_PLANES
-		// 32 words: axis a at 8a: (min of the four children | max of the four children) as floats, links at 24..27; an unused slot
-		// carries min = +3e38, max = -3e38, which no ray inside the domain of the error bound accepts
-		q.resize(base + 32, 0u);
+#if WF_CENTRE_EXTENT
+		// 24 words (gi_lane.h: wfInnerStep): centres as floats, half extents as bfloat16 rounded up, slack e = 330 u Pmax included; every box is
+		// checked in double against what the device's test stands for: [c - (h - e), c + (h - e)] contains it
+		q.resize(base + 24, 0u);
+		const double pmax = double(gridOnly.scene.cePmax);
+		const double slack = 330.0 * 5.9604644775390625e-08 * pmax;
+		auto bf16Up = [](double x, bool& ok) -> uint32_t {   // smallest bfloat16 >= x (x >= 0), as its 16 bits
+			float f = float(x);
+			if (double(f) < x) f = std::nextafterf(f, INFINITY);
+			uint32_t bits; std::memcpy(&bits, &f, 4);
+			if (bits & 0xffffu) bits += 0x10000u;
+			bits &= 0xffff0000u;
+			float back; std::memcpy(&back, &bits, 4);
+			if (!(double(back) >= x) || !std::isfinite(back)) ok = false;
+			return bits >> 16;
+		};
 		for (int k = 0; k < 4; ++k)
 		{
-			float mnv[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mxv[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+			float cv[3] = {0.0f, 0.0f, 0.0f};
+			uint32_t hv[3];
 			uint32_t link = uint32_t(WF_NODE_DONE);
+			bool ok = true;
 			if (k < n)
 			{
 				const float* mn = &t.boxMin[size_t(kids[k]) * 3]; const float* mx = &t.boxMax[size_t(kids[k]) * 3];
 				for (int a = 0; a < 3; ++a)
 				{
-					mnv[a] = mn[a]; mxv[a] = mx[a];
-					if (!(std::fabs(mn[a]) <= gridOnly.scene.gridAbsMax[a] && std::fabs(mx[a]) <= gridOnly.scene.gridAbsMax[a])) { why = "box outside the root box"; return false; }
+					if (!(std::fabs(mn[a]) <= gridOnly.scene.gridAbsMax[a] && std::fabs(mx[a]) <= gridOnly.scene.gridAbsMax[a] && mn[a] <= mx[a])) { why = "box outside the root box"; return false; }
+					cv[a] = float(0.5 * (double(mn[a]) + double(mx[a])));
+					const double h0 = std::fmax(double(mx[a]) - double(cv[a]), double(cv[a]) - double(mn[a]));
+					hv[a] = bf16Up(h0 + slack, ok);
+					uint32_t hb = hv[a] << 16; float hf; std::memcpy(&hf, &hb, 4);
+					if (!(double(cv[a]) - (double(hf) - slack) <= double(mn[a]) && double(cv[a]) + (double(hf) - slack) >= double(mx[a]))) ok = false;
+					if (!(std::fabs(double(cv[a])) + double(hf) * (1.0 + 1.0 / 128.0) <= 1.02 * pmax)) ok = false; // P' of the error bound (the odd child's h is read up to 2^-7 larger)
 				}
+				if (!ok) { why = "centre / half-extent record does not cover a box"; return false; }
 				FastEmitter::noteChildBox(L, base, uint32_t(k), mn, mx);
 				if (kids[k] < nl) link = uint32_t(~int(t.leafOf[kids[k]]));
 			}
+			else
+			{
+				// unused slot: h = -(65536 Pmax): near > far for every ray inside the domain of the bound
+				const uint32_t neg = bf16Up(65536.0 * pmax, ok) | 0x8000u;
+				hv[0] = hv[1] = hv[2] = neg;
+			}
 			for (int a = 0; a < 3; ++a)
 			{
-				std::memcpy(&q[base + 8 * size_t(a) + size_t(k)], &mnv[a], 4);
-				std::memcpy(&q[base + 8 * size_t(a) + 4 + size_t(k)], &mxv[a], 4);
+				std::memcpy(&q[base + 3 * size_t(k) + size_t(a)], &cv[a], 4);
+				uint32_t& w = q[base + 12 + 3 * size_t(k >> 1) + size_t(a)];
+				w |= (k & 1) ? (hv[a] << 16) : hv[a];
 			}
-			q[base + 24 + size_t(k)] = link;
+			q[base + 20 + size_t(k)] = link;
 		}
-		const size_t linkBase = base + 24;
+		const size_t linkBase = base + 20;
 #else
 		q.resize(base + 16, 0u);
 		for (int k = 0; k < 4; ++k)

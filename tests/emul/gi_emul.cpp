@@ -458,6 +458,9 @@ EM_API int em_slab_check(const GiSceneDesc* desc, const GiRay* rays, uint32_t n,
 		WfLane L;
 		const F3 o = f3(rays[r].origin), d = f3(rays[r].direction);
 		const F3 inv = invDir(d);
+#if WF_CACHE_INV
+		L.inv = inv;
+#endif
 		if (!wfSlabSetup(L, e.s, o, inv)) { ++out[4]; continue; }
 		L.limit = rays[r].t_max;
 		for (size_t bi = r % stride; bi < boxes.size(); bi += stride)

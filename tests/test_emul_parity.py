@@ -485,10 +485,10 @@ def test_quantised_child_boxes_are_conservative(g, emul, scenes, box1):
         emul.set_topology(emul.TOPOLOGY_REFERENCE)
 
 
-@pytest.mark.parametrize("variant", ["bin2", "sort3", "fplanes"])
+@pytest.mark.parametrize("variant", ["bin2", "sort3", "grid16"])
 def test_build_switches_of_the_wavefront_walk(variant):
     """The measured-and-switched-off alternatives of the wavefront walk stay exact: binary inner nodes (WF_WIDE4=0), three sort exchanges
-    (WF_SORT_EXCHANGES=3), float planes (WF_FLOAT_PLANES=1) -- tests/emul/libgi_emul_<variant>.so passes the same traversal parity tests;
+    (WF_SORT_EXCHANGES=3), 16-bit grid records (WF_CENTRE_EXTENT=0) -- tests/emul/libgi_emul_<variant>.so passes the same traversal parity tests;
     run in a child process because the emulator library is chosen at import."""
     import subprocess
     import sys
