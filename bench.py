@@ -152,12 +152,16 @@ def paths_per_iteration(cfg):
 
 
 def device_bytes(c):
-    """Bytes the wavefront walk's OWN layout touches (DESIGN.md "Data layout"), from the device's visit counters (GI_OPT_COUNT_STEPS):
-    64 B per inner-node record + 96 B per leaf record + 32 B root box per ray; queues: 32 B ray in + 8 B hit out per closest-hit ray,
-    48 B shadow record in per any-hit ray; exact re-traces (reference-order walk, 32 B per box test) are inside node_tests."""
+    """Bytes of the wavefront walk's OWN layout behind the records it visits (DESIGN.md "Data layout"), from the device's visit counters
+    (GI_OPT_COUNT_STEPS): 96 B per 4-wide inner-node record + 96 B per leaf record + 32 B root box per ray; exact re-traces
+    (reference-order walk, 32 B per box test) are inside node_tests.  Returns (record bytes, queue bytes): the queue bytes -- 32 B ray in +
+    8 B hit out per closest-hit ray, 48 B shadow record in per any-hit ray -- cross HBM once per launch whatever the caches do; the record
+    bytes are re-reads of a scene that stays in L2 / L1."""
     rays = c["closest_rays"] + c["any_rays"]
     refwalk_nodes = max(0, c["node_tests"] - 4 * c["inner_node_steps"] - c["leaf_steps"] - rays)
-    return 64 * c["inner_node_steps"] + 96 * c["leaf_steps"] + 32 * rays + 32 * refwalk_nodes + 40 * c["closest_rays"] + 48 * c["any_rays"]
+    records = 96 * c["inner_node_steps"] + 96 * c["leaf_steps"] + 32 * rays + 32 * refwalk_nodes
+    queues = 40 * c["closest_rays"] + 48 * c["any_rays"]
+    return records, queues
 
 
 def reference_layout_bytes(c):
@@ -410,7 +414,9 @@ def run_ours(args, rank, world, local_rank):
         counts[key] = dev.counters()
         dev.set_option(opt, 0)
     rays_per_iter = counts["device"]["closest_rays"] + counts["device"]["any_rays"]
-    dev_bytes_iter = device_bytes(counts["device"])
+    rec_bytes_iter, queue_bytes_iter = device_bytes(counts["device"])
+    dev_bytes_iter = rec_bytes_iter + queue_bytes_iter
+    resident = dev.scene_resident_bytes()
     ref_bytes_iter = reference_layout_bytes(counts["reference"])
 
     # ---- value: inputs resident in HBM.  Light samples of all iterations are generated up front and uploaded once; the K steps are handed
@@ -565,13 +571,19 @@ def run_ours(args, rank, world, local_rank):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    # roofline of k_wf_trace.  achieved = bytes of the kernel's own layout per launch (device visit counters) / its mean launch duration:
-    # both are totals over the SAME launches of the timed batch (steady-state waves and the drain tail alike), so nothing is mixed.
+    # roofline of k_wf_trace against HBM.  achieved = ALGORITHMIC HBM bytes per launch / mean launch duration: what one launch has to move
+    # through HBM however well the caches work -- its queue records (rays in, hits out, shadow records in) plus the traversal records it
+    # visits, each counted ONCE per launch (the inner-node and leaf records are 20-700 MB, re-read from L2 / L1 thousands of times; only the
+    # first touch can come from HBM).  Both factors are totals over the SAME launches of the timed batch (steady-state waves and drain tail).
     trace_ms, trace_launches = ktimes["trace"]
     total_iters = K * IPS
-    bytes_per_launch = dev_bytes_iter * total_iters / max(trace_launches, 1)
+    records_per_launch = rec_bytes_iter * total_iters / max(trace_launches, 1)
+    queues_per_launch = queue_bytes_iter * total_iters / max(trace_launches, 1)
+    resident_walk = resident["inner_records"] + resident["leaf_records"]
+    bytes_per_launch = queues_per_launch + min(records_per_launch, resident_walk)
     k_ms = trace_ms / max(trace_launches, 1)
     achieved = bytes_per_launch / (k_ms * 1e-3) / 1e9
+    records_gbs = records_per_launch / (k_ms * 1e-3) / 1e9
     step_ms = sum(v[0] for v in ktimes.values()) / K
     prof = {}
     try:
@@ -608,11 +620,17 @@ def run_ours(args, rank, world, local_rank):
                      "kernel": "k_wf_trace", "kernel_ms": k_ms, "launches_timed": trace_launches, "algorithmic_bytes_per_launch": bytes_per_launch,
                      "peak_source": peak_src, "share_of_step": trace_ms / K / step_ms,
                      "kernel_ms_per_iteration": {k: v[0] / total_iters for k, v in ktimes.items() if v[1]},
-                     "definition": "algorithmic bytes = what the kernel's own HBM layout holds for the records it visits, from the device's visit counters "
-                                   "(GI_OPT_COUNT_STEPS pass): 64 B per 4-wide inner-node record, 96 B per leaf record, 32 B root box, 32 B ray in + 8 B hit out "
-                                   "(closest hit) or 48 B shadow record in (any hit), 32 B per box test of an exact reference-order re-trace.  The scene is "
-                                   "L2-resident, so most of these bytes are served by L2 / L1, not DRAM: `traffic` (ncu dram bytes of one steady-state launch) "
-                                   "and `dram` say what reaches HBM, `issue` what actually bounds the kernel",
+                     "definition": "achieved = algorithmic HBM bytes per k_wf_trace launch / its mean launch duration (CUDA events on the launching stream). "
+                                   "Algorithmic HBM bytes = queue records (32 B ray in + 8 B hit out per closest-hit ray, 48 B shadow record in per any-hit ray) + the "
+                                   "traversal records the launch visits counted once (min(visited record bytes, resident inner + leaf records)): the scene stays in "
+                                   "L2 / L1, so the kernel is NOT HBM-bound and the fraction is low by design -- `traffic` (ncu dram bytes of one steady-state launch) "
+                                   "agrees with the algorithmic figure, `records` is what L2 / L1 serve, `issue` (ncu) is the roof that binds: issue slots / ALU pipe "
+                                   "at the measured lanes per instruction",
+                     "hbm_bytes_per_launch": {"queues": queues_per_launch, "records_once": min(records_per_launch, resident_walk)},
+                     "records": {"bytes_per_launch": records_per_launch, "gbs": records_gbs, "ratio_to_hbm_peak": records_gbs / peak, "served_by": "L2 / L1",
+                                 "resident_inner_record_bytes": resident["inner_records"], "resident_leaf_record_bytes": resident["leaf_records"],
+                                 "note": "visit counters of the device (GI_OPT_COUNT_STEPS pass) x record size (96 B per 4-wide inner-node record, 96 B per leaf record, "
+                                         "32 B root box per ray, 32 B per box test of an exact reference-order re-trace); a bandwidth of the cache hierarchy, not of HBM"},
                      "per_ray": {"inner_node_records": dc["inner_node_steps"] / max(rays_per_iter, 1), "leaf_records": dc["leaf_steps"] / max(rays_per_iter, 1),
                                  "box_tests": dc["node_tests"] / max(rays_per_iter, 1), "triangle_tests": dc["triangle_tests"] / max(rays_per_iter, 1),
                                  "bytes": dev_bytes_iter / max(rays_per_iter, 1)},

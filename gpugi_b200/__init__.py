@@ -455,6 +455,12 @@ class Device:
         ms = C.c_double(0.0)
         return int(capi.dev.gi_scene_topology(self._c, C.byref(ms))), float(ms.value)
 
+    def scene_resident_bytes(self):
+        """gi_scene_resident_bytes: {inner_records, leaf_records, reference_nodes, shading_records} in bytes."""
+        out = (C.c_uint64 * 4)()
+        self._check(capi.dev.gi_scene_resident_bytes(self._c, out), "gi_scene_resident_bytes")
+        return dict(zip(("inner_records", "leaf_records", "reference_nodes", "shading_records"), (int(v) for v in out)))
+
     def kernel_times(self):
         """gi_get_kernel_times: {class: (ms, launches)} collected while GI_OPT_KERNEL_TIMING is on."""
         t = capi.GiKernelTimes()

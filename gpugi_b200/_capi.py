@@ -174,6 +174,7 @@ DEVICE_API = {
     "gi_reset_counters": (C.c_int, [vp]),
     "gi_kernel_launches": (u64, [vp]),
     "gi_scene_topology": (C.c_int, [vp, P(C.c_double)]),
+    "gi_scene_resident_bytes": (C.c_int, [vp, P(C.c_uint64)]),
     "gi_get_kernel_times": (C.c_int, [vp, P(GiKernelTimes)]),
 }
 

@@ -592,6 +592,7 @@ struct GiContext
 	uint64_t wfStates[2] = {0, 0};   // allocated path state records (numSlots x numIds)
 	uint32_t* traceWork = nullptr;   // work counter of k_wf_trace_batch
 	int numSMs = 148;
+	uint64_t residentBytes[4] = {0, 0, 0, 0}; // gi_scene_resident_bytes
 	int traceBlocksPerSM = 1, shadeBlocksPerSM = 1, shadeLightBlocksPerSM = 1, shadeEyeBlocksPerSM = 1;
 
 	// multi-GPU read-out (gi_comm.cuh): exchange block shared with the peer ranks over CUDA IPC
@@ -1402,6 +1403,10 @@ int gi_upload_scene(GiContext* c, const GiSceneDesc* d)
 	if (!L.oboxNodes.empty()) GI_CUDA(c, uploadVector(c, L.oboxNodes, &s.oboxNodes));
 	GI_CUDA(c, uploadVector(c, L.fastNodes, &s.fastNodes));
 	GI_CUDA(c, uploadVector(c, L.qNodes, &s.qNodes));
+	c->residentBytes[0] = L.qNodes.size() * sizeof(uint32_t);
+	c->residentBytes[1] = L.leafPos.size() * sizeof(F4);
+	c->residentBytes[2] = L.refNodes.size() * sizeof(F4);
+	c->residentBytes[3] = L.leafTris.size() * sizeof(I4) + L.vertexInfo.size() * sizeof(F4) + L.materials.size() * sizeof(DMaterial);
 	GI_CUDA(c, uploadVector(c, L.leafPos, &s.leafPos));
 	GI_CUDA(c, uploadVector(c, L.leafTris, &s.leafTris));
 	GI_CUDA(c, uploadVector(c, L.vertexInfo, &s.vertexInfo));
@@ -2163,6 +2168,13 @@ int gi_scene_topology(const GiContext* c, double* build_ms)
 	if (!c || !c->haveScene) return -1;
 	if (build_ms) *build_ms = c->topologyBuildMs;
 	return c->sceneTopology;
+}
+
+int gi_scene_resident_bytes(const GiContext* c, uint64_t out[4])
+{
+	if (!c || !c->haveScene || !out) return GI_ERR_INVALID;
+	for (int i = 0; i < 4; ++i) out[i] = c->residentBytes[i];
+	return GI_OK;
 }
 
 int gi_synchronize(GiContext* c)

@@ -423,6 +423,11 @@ GI_API int gi_synchronize(GiContext* ctx);
  * added to gi_upload_scene. */
 GI_API int gi_scene_topology(const GiContext* ctx, double* build_ms);
 
+/* Bytes of the uploaded scene that stay resident for the kernels (no reference counterpart: the GL buffers of scene.cpp:75-130 in this
+ * path's own layout): out[0] inner-node records of the ordered walk, out[1] leaf records, out[2] the reference-order node array (exact
+ * re-traces), out[3] leaf triangles + vertex info + material records (shading; textures not included).  Used by bench.py's roofline. */
+GI_API int gi_scene_resident_bytes(const GiContext* ctx, uint64_t out[4]);
+
 /* ------------------------------------------------------------------ read-out */
 
 /* Replaces glGetTextureImage(RGBA32F) in Application::SaveImage (application.cpp:411):

@@ -23,7 +23,8 @@ STALL = "smsp__average_warps_issue_stalled_"
 
 
 def load(path):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # a .csv is the saved output of `ncu -i capture.ncu-rep --page raw --csv` (made on the GPU box so that the large capture need not travel)
+    out = open(path).read() if path.endswith(".csv") else subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units = rows[0], rows[1]
     return [dict(zip(hdr, r)) for r in rows[2:]], dict(zip(hdr, units))
