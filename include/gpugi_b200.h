@@ -273,7 +273,7 @@ typedef struct GiCounters {
 	uint32_t light_cache_entries;/* NumLightCacheEntries after the last light pass         */
 	uint32_t light_path_length_sum; /* LightPathLengthSum (warm-up)                        */
 	/* with GI_OPT_COUNT_STEPS, the record loads of the wavefront walk (DESIGN.md "Data layout"): what the kernel's own layout touches */
-	uint64_t inner_node_steps;   /* inner-node records fetched: 64 B each (one 4-wide node = 4 of the node_tests)                   */
+	uint64_t inner_node_steps;   /* inner-node records fetched: 96 B each (one 4-wide node = 4 of the node_tests)                   */
 	uint64_t leaf_steps;         /* leaf records fetched: 96 B each (both triangles + the leaf's own box = 1 of the node_tests)     */
 } GiCounters;
 
