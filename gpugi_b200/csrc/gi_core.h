@@ -156,7 +156,8 @@ struct DScene
 	float gridLo[3];         // grid origin (root box min) and cell size per axis
 	float gridScale[3];
 	float gridAbsMax[3];     // max(|root box min|, |root box max|) per axis: bound of every plane coordinate
-	float cePmax;            // the largest of the three (WF_CENTRE_EXTENT error bound)
+	float ceCentre[3];       // WF_CENTRE_EXTENT: centre of the root box (the node records' coordinates are relative to it)
+	float cePmax;            // ... and the largest half extent of the root box around it (error bound of the conservative node test)
 	const F4* leafPos;       // 6 x F4 per leaf: slot s -> [3s] = (p0.xyz, .), [3s+1] = (p1.xyz, .), [3s+2] = (p2.xyz, .); an unused slot has
 	                         // p0.x = NaN (vertex positions are checked to be finite at upload).  The six .w hold the leaf node's own box:
 	                         // [0..2].w = box.min.xyz, [3..5].w = box.max.xyz

@@ -287,29 +287,32 @@ GI_HD float wfMin3(float a, float b, float c)
 }
 
 #if WF_CENTRE_EXTENT
-// Centre / half-extent records.  Per child and axis the record holds a float c and a bfloat16 h with [c - h0, c + h0] containing the child's box
-// in real arithmetic and h = h0 + e, e >= 330 u Pmax (u = 2^-24, Pmax = largest |coordinate| of the root box; gi_layout.h: emitWide4 checks both
-// in double).  With inv = fl(1/d), T(p) = (p - o) inv the real-number distance of plane p, the reference (exact zone) computes
-//   t_ref(p) = fl(inv * fl(p - o)),   |t_ref(p) - T(p)| <= 2.01 u |T(p)| <= 2.01 u (Pmax + |o|) |inv|.
-// Here:   m = fl(-(o inv))   tc = fl(c inv + m)   near = fl(tc - h |inv|)   far = fl(tc + h |inv|)          (three FMAs, no decode, no selection)
-//   |tc - (c - o) inv| <= u |o inv| (1 + u) + u |c - o| |inv|
-//   |near - ((c - o) inv - h |inv|)| <= 1.01 u |inv| (3 |o| + 2 |c| + h) <= 1.01 u |inv| (3 |o| + 3 P'),   P' = 1.02 Pmax >= |c| + h (checked at upload)
-// A true plane p of the child lies at least e inside [c - h, c + h], so T(p) is at least e |inv| inside [(c - o) inv -/+ h |inv|], and
-//   near <= tmin.k,  far >= tmax.k of IntersectBox (intersectiontests.glsl:12-15)   as soon as   e >= u (2.01 (Pmax + |o|) + 3.03 (|o| + P')) ,
-// which e = 330 u Pmax satisfies for every ray with |o.k| <= 60 Pmax.  Hence (first <= last && first <= limit) ==> the conservative test accepts.
-// Rays outside that domain (origin farther than 60 Pmax from the coordinate origin, zero / denormal direction components, products near
+// Centre / half-extent records.  Coordinates are taken relative to the centre C0 of the root box (a float per axis, DScene::ceCentre), so that the
+// bound does not depend on where the scene lies: p' = p - C0, o' = o - C0 (real numbers), P = the largest half extent of the root box.
+// Per child and axis the record holds a float c and a bfloat16 h with [c - h0, c + h0] containing the child's box (in primed coordinates, real
+// arithmetic) and h = h0 + e, e >= 330 u P (u = 2^-24; gi_layout.h: emitWide4 checks both in double).  With inv = fl(1/d) and
+// T(p) = (p - o) inv = (p' - o') inv the real-number distance of plane p, the reference (exact zone) computes
+//   t_ref(p) = fl(inv * fl(p - o)),   |t_ref(p) - T(p)| <= 2.01 u |T(p)| <= 2.01 u (P + |o'|) |inv|.
+// Here:   q = fl(o - C0)   m = fl(-(q inv))   tc = fl(c inv + m)   near = fl(tc - h |inv|)   far = fl(tc + h |inv|)     (three FMAs per plane pair, no decode, no selection)
+//   |q - o'| <= u |o'|,   |m + o' inv| <= 2.01 u |o' inv|,   |tc - (c - o') inv| <= 2.02 u |o' inv| + u |c - o'| |inv|
+//   |near - ((c - o') inv - h |inv|)| <= 1.01 u |inv| (4 |o'| + 2 |c| + h) <= 1.01 u |inv| (4 |o'| + 3 P''),   P'' = 1.02 P >= |c| + h (checked at upload)
+// A true plane p' of the child lies at least e inside [c - h, c + h], so T(p) is at least e |inv| inside [(c - o') inv -/+ h |inv|], and
+//   near <= tmin.k,  far >= tmax.k of IntersectBox (intersectiontests.glsl:12-15)   as soon as   e >= u (2.01 (P + |o'|) + 4.04 |o'| + 3.1 P) ,
+// which e = 330 u P satisfies for every ray with |o'.k| <= 50 P.  Hence (first <= last && first <= limit) ==> the conservative test accepts.
+// Rays outside that domain (origin farther than 50 P from the centre of the scene, zero / denormal direction components, products near
 // overflow or underflow) are answered by the stackless reference walk (WFL_OVERFLOW).
 GI_HD bool wfSlabSetup(WfLane& L, const DScene& s, F3 o, F3 inv)
 {
 	const float P = s.cePmax;
-	const float iv[3] = {inv.x, inv.y, inv.z}, ov[3] = {o.x, o.y, o.z};
+	const float iv[3] = {inv.x, inv.y, inv.z};
+	const float ov[3] = {GI_SUB(o.x, s.ceCentre[0]), GI_SUB(o.y, s.ceCentre[1]), GI_SUB(o.z, s.ceCentre[2])};
 	float m[3];
 	bool ok = true;
 	for (int k = 0; k < 3; ++k)
 	{
-		m[k] = -(ov[k] * iv[k]);
+		m[k] = -GI_MUL(ov[k], iv[k]);
 		const float reach = fmaxf(fabsf(ov[k]), P) * fabsf(iv[k]);
-		ok = ok && (fabsf(ov[k]) <= 60.0f * P) && (reach < 1.0e30f) && (P * fabsf(iv[k]) >= 1.0e-30f); // all false for NaN
+		ok = ok && (fabsf(ov[k]) <= 50.0f * P) && (reach < 1.0e30f) && (P * fabsf(iv[k]) >= 1.0e-30f); // all false for NaN
 	}
 	L.negOInv = f3(m[0], m[1], m[2]);
 	return ok;
@@ -379,10 +382,10 @@ GI_HD bool wfSlabTest(const WfLane& L, uint32_t wx, uint32_t wy, uint32_t wz, fl
 #endif
 
 #if WF_CENTRE_EXTENT
-// 96-byte record (24 words): 0..11 centre of child k, axis a at 3k + a (float); 12..17 half extents as bfloat16 pairs, word 12 + 3 (k >> 1) + a =
+// 96-byte record (24 words): 0..11 centre of child k relative to the root box's centre, axis a at 3k + a (float); 12..17 half extents as bfloat16 pairs, word 12 + 3 (k >> 1) + a =
 // (h of the even child | h of the odd child << 16); 18..19 unused; 20..23 child links (wide index >= 0, leaf = ~leafIndex).  The odd child's half
 // extent is the word itself read as a float (the even child's bits only enlarge it, by < 2^-7), the even child's is the word shifted left by 16 --
-// a multiplication by 65536 on the FMA pipe.  An unused slot has c = 0 and h = -65536 Pmax: near > far for every ray inside the domain.
+// a multiplication by 65536 on the FMA pipe.  An unused slot has c = 0 and h = -65536 P: near > far for every ray inside the domain.
 GI_HD float wfHalfExtent(uint32_t word, int child)
 {
 	return i2f(int((child & 1) ? word : word * 65536u));

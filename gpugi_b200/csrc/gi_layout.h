@@ -54,7 +54,14 @@ struct FastEmitter
 			if (!(sc > 1.0e-30f)) sc = 1.0e-30f;
 			L.scene.gridLo[k] = lo; L.scene.gridScale[k] = sc;
 			L.scene.gridAbsMax[k] = std::fmax(std::fabs(lo), std::fabs(hi));
-			L.scene.cePmax = k == 0 ? L.scene.gridAbsMax[0] : std::fmax(L.scene.cePmax, L.scene.gridAbsMax[k]);
+			{
+				// centre of the root box as a float; half extent around THAT float, rounded up
+				const float c0 = float(0.5 * (double(lo) + double(hi)));
+				float he = float(std::fmax(double(hi) - double(c0), double(c0) - double(lo)));
+				if (double(he) < std::fmax(double(hi) - double(c0), double(c0) - double(lo))) he = std::nextafterf(he, INFINITY);
+				L.scene.ceCentre[k] = c0;
+				L.scene.cePmax = k == 0 ? he : std::fmax(L.scene.cePmax, he);
+			}
 			gridLo[k] = double(lo); gridScale[k] = double(sc);
 		}
 	}
@@ -184,8 +191,9 @@ inline bool emitWide4(const GiSceneDesc* d, HostLayout& L, const LeafTree& t, st
 		}
 		const size_t base = q.size();
 #if WF_CENTRE_EXTENT
-		// 24 words (gi_lane.h: wfInnerStep): centres as floats, half extents as bfloat16 rounded up, slack e = 330 u Pmax included; every box is
-		// checked in double against what the device's test stands for: [c - (h - e), c + (h - e)] contains it
+		// 24 words (gi_lane.h: wfInnerStep): centres (relative to the root box's centre) as floats, half extents as bfloat16 rounded up, slack
+		// e = 330 u P included (P = largest half extent of the root box); every box is checked in double against what the device's test stands
+		// for: [c - (h - e), c + (h - e)] contains it
 		q.resize(base + 24, 0u);
 		const double pmax = double(gridOnly.scene.cePmax);
 		const double slack = 330.0 * 5.9604644775390625e-08 * pmax;
@@ -211,12 +219,15 @@ inline bool emitWide4(const GiSceneDesc* d, HostLayout& L, const LeafTree& t, st
 				for (int a = 0; a < 3; ++a)
 				{
 					if (!(std::fabs(mn[a]) <= gridOnly.scene.gridAbsMax[a] && std::fabs(mx[a]) <= gridOnly.scene.gridAbsMax[a] && mn[a] <= mx[a])) { why = "box outside the root box"; return false; }
-					cv[a] = float(0.5 * (double(mn[a]) + double(mx[a])));
-					const double h0 = std::fmax(double(mx[a]) - double(cv[a]), double(cv[a]) - double(mn[a]));
+					// primed coordinates: relative to the root box's centre (float - float in double: exact up to 2^-53, far below the slack)
+					const double c0 = double(gridOnly.scene.ceCentre[a]);
+					const double lo = double(mn[a]) - c0, hi = double(mx[a]) - c0;
+					cv[a] = float(0.5 * (lo + hi));
+					const double h0 = std::fmax(hi - double(cv[a]), double(cv[a]) - lo);
 					hv[a] = bf16Up(h0 + slack, ok);
 					uint32_t hb = hv[a] << 16; float hf; std::memcpy(&hf, &hb, 4);
-					if (!(double(cv[a]) - (double(hf) - slack) <= double(mn[a]) && double(cv[a]) + (double(hf) - slack) >= double(mx[a]))) ok = false;
-					if (!(std::fabs(double(cv[a])) + double(hf) * (1.0 + 1.0 / 128.0) <= 1.02 * pmax)) ok = false; // P' of the error bound (the odd child's h is read up to 2^-7 larger)
+					if (!(double(cv[a]) - (double(hf) - slack) <= lo && double(cv[a]) + (double(hf) - slack) >= hi)) ok = false;
+					if (!(std::fabs(double(cv[a])) + double(hf) * (1.0 + 1.0 / 128.0) <= 1.02 * pmax)) ok = false; // P'' of the error bound (the odd child's h is read up to 2^-7 larger)
 				}
 				if (!ok) { why = "centre / half-extent record does not cover a box"; return false; }
 				FastEmitter::noteChildBox(L, base, uint32_t(k), mn, mx);

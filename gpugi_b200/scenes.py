@@ -352,10 +352,10 @@ def make_sponza_like(texture_dir, target_triangles=262144, texture_size=1024, nu
 # --------------------------------------------------------------------------------------------------
 
 
-def make_random_triangles(n, seed=0, extent=10.0, size=1.0, build_method="sah", bvh_type=0):
-    """n random triangles in a cube: the adversarial case for traversal parity (overlaps, slivers)."""
+def make_random_triangles(n, seed=0, extent=10.0, size=1.0, build_method="sah", bvh_type=0, offset=(0.0, 0.0, 0.0)):
+    """n random triangles in a cube around `offset`: the adversarial case for traversal parity (overlaps, slivers)."""
     rng = np.random.RandomState(seed)
-    c = rng.uniform(-extent, extent, size=(n, 1, 3))
+    c = rng.uniform(-extent, extent, size=(n, 1, 3)) + np.asarray(offset, dtype=np.float64)
     p = (c + rng.uniform(-size, size, size=(n, 3, 3))).astype(np.float32).reshape(-1, 3)
     nrm = np.tile(np.array([0, 1, 0], dtype=np.float32), (3 * n, 1))
     uv = rng.rand(3 * n, 2).astype(np.float32)

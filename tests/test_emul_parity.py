@@ -485,6 +485,45 @@ def test_quantised_child_boxes_are_conservative(g, emul, scenes, box1):
         emul.set_topology(emul.TOPOLOGY_REFERENCE)
 
 
+def _far_and_offset_cases(g, scenes):
+    """Scenes and rays at the edge of / outside the domain of the conservative inner-node test (gi_lane.h: wfSlabSetup): a scene far from
+    the coordinate origin (the records are relative to the root box's centre, so nothing may depend on the offset), ray origins 40 x (inside
+    the domain), 80 x and 5000 x (outside: answered by the reference walk) the scene's half extent away from its centre, aimed at the scene."""
+    cases = []
+    for off in ((0.0, 0.0, 0.0), (30000.0, -20000.0, 10000.0)):
+        sc = scenes.make_random_triangles(600, seed=9, offset=off)
+        lo, hi = np.array(sc.info.bbox_min, dtype=np.float64), np.array(sc.info.bbox_max, dtype=np.float64)
+        centre, half = 0.5 * (lo + hi), 0.5 * (hi - lo).max()
+        rng = np.random.RandomState(4)
+        n = 3000
+        rays = np.zeros(n, dtype=g.RAY_DTYPE)
+        dirs = rng.randn(n, 3); dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+        dist = np.choose(np.arange(n) % 3, [40.0, 80.0, 5000.0]) * half
+        origin = centre + dirs * dist[:, None]
+        target = lo + rng.rand(n, 3) * (hi - lo)
+        d = target - origin; d /= np.linalg.norm(d, axis=1, keepdims=True)
+        rays["origin"] = origin.astype(np.float32); rays["direction"] = d.astype(np.float32)
+        rays["t_max"] = np.float32(g.RAY_MAX)
+        rays["flags"][: n // 4] = 1
+        rays["t_max"][: n // 4] = (dist[: n // 4] * (0.9 + 0.2 * rng.rand(n // 4))).astype(np.float32)
+        cases.append((sc, rays))
+    return cases
+
+
+def test_far_origins_and_offset_scenes_stay_exact(g, orc, emul, scenes):
+    """The lane walk at and beyond the domain of its conservative node test, and on a scene 30 000 units away from the origin."""
+    for sc, rays in _far_and_offset_cases(g, scenes):
+        ref = orc.trace_batch(sc.desc, rays)
+        assert (ref["leaf_tri"][rays["flags"] == 0] >= 0).mean() > 0.3   # the rays do reach the scene
+        for mode in (FAST, LANE):
+            hits, cnt = emul.trace(sc.desc, rays, mode)
+            assert_hits_equal(hits, ref, "far / offset mode %d" % mode)
+        # the offset scene's node test is as tight as the centred one's: relative coordinates (same triangles, same rays up to the shift)
+        r = emul.slab_check(sc.desc, make_ray_batch(g, sc, 2000, 3, axis_aligned=False), stride=5)
+        assert r["violations"] == 0 and r["out_of_domain"] == 0, r
+        assert r["conservative_accepts"] <= 1.05 * r["exact_accepts"] + 10, r
+
+
 @pytest.mark.parametrize("variant", ["bin2", "sort3", "grid16"])
 def test_build_switches_of_the_wavefront_walk(variant):
     """The measured-and-switched-off alternatives of the wavefront walk stay exact: binary inner nodes (WF_WIDE4=0), three sort exchanges

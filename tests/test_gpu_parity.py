@@ -143,6 +143,29 @@ def test_trace_ragged_and_deep(g, orc, dev, scenes):
     assert_hits_equal(hits, orc.trace_batch(deep.desc, rays), "deep tree")
 
 
+def test_far_origins_and_offset_scenes_stay_exact(g, orc, dev, scenes):
+    """The trace kernel at and beyond the domain of its conservative inner-node test (gi_lane.h: wfSlabSetup), and on a scene 30 000 units away
+    from the coordinate origin (the node records are relative to the root box's centre): ray origins 40 x (inside the domain), 80 x and
+    5000 x (outside: answered by the exact reference walk) the scene's half extent away, closest-hit and any-hit -- bit-exact; the offset
+    scene does as many box tests per ray as the centred one (same triangles, same rays up to the shift)."""
+    from tests.test_emul_parity import _far_and_offset_cases
+    tests_per_ray = []
+    for sc, rays in _far_and_offset_cases(g, scenes):
+        ref = orc.trace_batch(sc.desc, rays)
+        for mode in (FAST, REFERENCE):
+            hits, cnt = _trace(g, dev, sc, rays, mode)
+            assert_hits_equal(hits, ref, "far / offset mode %d" % mode)
+            if mode == FAST:
+                assert cnt["exact_fallback_rays"] >= 0
+        near = make_ray_batch(g, sc, 20000, 3, axis_aligned=False)
+        dev.set_option(g.GI_OPT_COUNT_STEPS, 1)
+        hits, cnt = _trace(g, dev, sc, near, FAST)
+        dev.set_option(g.GI_OPT_COUNT_STEPS, 0)
+        assert_hits_equal(hits, orc.trace_batch(sc.desc, near), "offset scene, rays inside")
+        tests_per_ray.append(cnt["node_tests"] / len(near))
+    assert abs(tests_per_ray[1] / tests_per_ray[0] - 1.0) < 0.03, tests_per_ray
+
+
 def test_trace_device_buffers(g, orc, dev, box1):
     """gi_trace_device on caller-owned device memory (torch is only the allocator here)."""
     import torch
