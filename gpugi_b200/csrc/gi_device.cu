@@ -239,6 +239,9 @@ __global__ void __launch_bounds__(256) k_light_samples(DLightTables t, unsigned 
 #ifndef WF_SHADE_LIGHT_MIN_BLOCKS
 #define WF_SHADE_LIGHT_MIN_BLOCKS 8   // B200 A/B (ms per iteration, 4 / 5 / 6 / 8 / 10 blocks per SM = 118 / 96 / 80 / 64 / 48 registers): C4 LPT 4K 6.92 / 6.78 / 6.62 / 6.49 / 6.62
 #endif
+#ifndef WF_SHADE_LIGHT_COMPACT
+#define WF_SHADE_LIGHT_COMPACT 1
+#endif
 #ifndef WF_SHADE_EYE_MIN_BLOCKS
 #define WF_SHADE_EYE_MIN_BLOCKS 8     // C3 BPT 1080p 7.64 / 7.55 / 7.46 / 7.43 / 7.64 (both kernels bounded together)
 #endif
@@ -401,7 +404,39 @@ __global__ void __launch_bounds__(WF_SHADE_THREADS, WF_SHADE_LIGHT_MIN_BLOCKS) k
 	uint32_t* counts = wfCounts(w, w.wave);
 	const uint32_t n = w.numCam + counts[0];
 	PathCounters pc = {};
+#if WF_SHADE_LIGHT_COMPACT
+	// A light path that left the scene has nothing to shade (lighttracer.comp:97-98) -- in an open scene that is a third of the hit records (C4: 36 %),
+	// and their lanes would idle through the whole vertex.  Each warp therefore collects the slots of real hits in a small pool (shared memory)
+	// and shades 32 of them at a time.
+	__shared__ uint32_t pool[WF_SHADE_THREADS / 32][64];
+	uint32_t* mine = pool[threadIdx.x >> 5];
+	const unsigned lane = laneId();
+	uint32_t pooled = 0;
+	bool more = true;
+	for (;;)
+	{
+		while (more && pooled < 32u)
+		{
+			const uint32_t base = wfGrab32(counts + 3);
+			if (base >= n) { more = false; break; }
+			const uint32_t slot = base + lane;
+			const bool hit = slot < n && f2i(qld2(w.q.hits + w.rayBase + slot).y) >= 0;
+			const unsigned m = __ballot_sync(0xffffffffu, hit);
+			if (hit) mine[pooled + __popc(m & lanemaskLt())] = w.rayBase + slot;
+			pooled += uint32_t(__popc(m));
+			__syncwarp();
+		}
+		if (pooled == 0u) break;
+		const uint32_t take = min(32u, pooled);
+		const bool valid = lane < take;
+		const uint32_t slot = valid ? mine[pooled - take + lane] : 0u;
+		__syncwarp();
+		pooled -= take;
+		wfShadeLight(w, slot, valid, pc);
+	}
+#else
 	wfShadeLoop(w, counts + 3, n, [&](uint32_t slot, bool valid) { wfShadeLight(w, slot, valid, pc); });
+#endif
 	unsigned cnt[WFC_COUNT] = {};
 	wfAddCounters(cnt, pc);
 	flushWarpCounters(counters, cnt, WFC_COUNT);

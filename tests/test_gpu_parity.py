@@ -166,6 +166,16 @@ def test_far_origins_and_offset_scenes_stay_exact(g, orc, dev, scenes):
     assert abs(tests_per_ray[1] / tests_per_ray[0] - 1.0) < 0.03, tests_per_ray
 
 
+def test_scene_resident_bytes(g, dev, box1):
+    """gi_scene_resident_bytes: what bench.py's roofline counts once per launch -- 96-byte inner-node and leaf records, 32-byte reference nodes."""
+    dev.upload_scene(box1)
+    r = dev.scene_resident_bytes()
+    leaves = box1.info.num_leaf_triangles // 2
+    assert r["leaf_records"] == 96 * leaves and r["reference_nodes"] == 32 * box1.info.num_nodes
+    assert r["inner_records"] % 96 == 0 and 0 < r["inner_records"] <= 96 * (leaves - 1)
+    assert r["shading_records"] > 0
+
+
 def test_trace_device_buffers(g, orc, dev, box1):
     """gi_trace_device on caller-owned device memory (torch is only the allocator here)."""
     import torch

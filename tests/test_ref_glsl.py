@@ -1,0 +1,132 @@
+"""The oracle against the REFERENCE'S OWN SHADER SOURCE (rows a-1 .. a-5, a-9 .. a-11, a-13).
+
+oracle/_ref/libref_glsl_*.so are gpugi/shader/{traceray, intersectiontests, materials, lightsource, random, helper, scenedata}.glsl and
+pathtracer.comp themselves, compiled as C++ (oracle/ref_glsl/: a token-level rewrite + a GLSL vector shim that states the same arithmetic
+definition the oracle and the CUDA path are held to).  tests/golden/ref_glsl.npz holds what they return for fixed inputs
+(tests/golden/make_golden_glsl.py) and travels with the repository; the live tests run where the libraries exist (the build container and,
+prebuilt, the GPU box).  Bar: bit-exact -- hit flag, triangle index, distance, barycentrics; every float of the path tracer's sum image."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import ref_glsl
+from tests.conftest import make_ray_batch
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_glsl.npz")
+live = pytest.mark.skipif(not ref_glsl.available(), reason="oracle/_ref/libref_glsl_*.so not built (needs /root/reference)")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(GOLDEN)
+
+
+def assert_same_hits(got, want, rays, what):
+    anyhit = rays["flags"] == 1
+    assert np.array_equal(got["leaf_tri"], want["leaf_tri"]), what + ": hit flag / triangle index"
+    c = ~anyhit
+    for f in ("t", "bary_y", "bary_z"):
+        assert np.array_equal(got[f][c].view(np.uint32), want[f][c].view(np.uint32)), what + ": " + f
+
+
+@pytest.mark.parametrize("name", ["box1", "box1_coincident", "random_tris"])
+def test_oracle_traversal_equals_reference_glsl_golden(g, orc, scenes, gold, name):
+    """TraceRay / TraceRayAnyHit of the oracle == the reference's traceray.glsl on the committed batches (incl. exact ties on coincident faces)."""
+    from tests.golden.make_golden_glsl import scenes_for_goldens
+    sc = scenes_for_goldens(scenes)[name]
+    rays, want = gold[name + "_rays"], gold[name + "_hits"]
+    assert (want["leaf_tri"][rays["flags"] == 0] >= 0).mean() > 0.3
+    assert_same_hits(orc.trace_batch(sc.desc, rays), want, rays, name)
+
+
+def test_oracle_pathtracer_equals_reference_glsl_golden(g, orc, scenes, gold):
+    """Three iterations of the oracle's path tracer == main() of the reference's pathtracer.comp, every float of the sum image (box1, 64 x 64)."""
+    os.environ["OMP_NUM_THREADS"] = "1"
+    sc = scenes.make_box1(tess=4)
+    W = H = 64
+    acc = np.zeros((H, W, 4), dtype=np.float32)
+    for k in range(3):
+        orc.render_pt(sc.desc, gold["pt_cam"], W, H, gold["pt_samples"][k], int(gold["pt_seeds"][k]), 16, accum=acc)
+    assert acc[..., :3].sum() > 0
+    assert np.array_equal(acc.view(np.uint32), gold["pt_box1_64"].view(np.uint32))
+
+
+def test_oracle_pathtracer_textured_equals_reference_glsl_golden(g, orc, scenes, gold, sponza_small):
+    """... and on the textured Sponza-shaped scene (SampleMaterialData through textureLod, 25 materials, point lights)."""
+    W, H = 64, 40
+    img, _ = orc.render_pt(sponza_small.desc, gold["pt_sponza_cam"], W, H, gold["pt_sponza_samples"], int(gold["pt_sponza_seed"]), 16)
+    assert img[..., :3].sum() > 0
+    assert np.array_equal(img.view(np.uint32), gold["pt_sponza"].view(np.uint32))
+
+
+@live
+def test_oracle_traversal_equals_reference_glsl_live(g, orc, scenes, sponza_small):
+    """Fresh batches (other seeds, the Sponza-shaped scene, finite ray lengths, axis-aligned rays) through both."""
+    tr = ref_glsl.Trace()
+    for sc, n, seed in ((scenes.make_box1(tess=3), 30000, 21), (scenes.make_random_triangles(1200, seed=8), 30000, 22), (sponza_small, 60000, 23)):
+        rays = make_ray_batch(g, sc, n, seed)
+        tr.set_scene(sc)
+        assert_same_hits(orc.trace_batch(sc.desc, rays), tr.trace(g, rays), rays, "live seed %d" % seed)
+
+
+@live
+def test_oracle_pathtracer_equals_reference_glsl_live(g, orc, scenes):
+    """Other resolutions (not a multiple of 8: the work groups of pathtracer.cpp:50 leave a border), seeds and light-sample counts."""
+    pt = ref_glsl.PathTracer()
+    sc = scenes.make_box1(tess=2)
+    pt.set_scene(sc)
+    C = scenes.BOX1_CAMERA
+    for W, H, nls, it in ((52, 44, 32, 3), (96, 64, 256, 11)):
+        cam = orc.camera(C["pos"], C["lookat"], C["fov"], W, H)
+        ls = g.LightSampler(sc); ls.seed(100 + it)
+        s = ls.generate(nls)
+        want = pt.render(cam, W, H, s, orc.wanghash(it))
+        got, _ = orc.render_pt(sc.desc, cam, W, H, s, orc.wanghash(it), 16)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (W, H)
+        assert (want[H // 8 * 8:] == 0).all() and (want[:, W // 8 * 8:] == 0).all()
+
+
+@live
+@pytest.mark.gpu
+def test_cuda_traversal_equals_reference_glsl(g, scenes, sponza_small):
+    """The CUDA path (gi_trace, both walks) directly against the reference's traceray.glsl -- no oracle in between."""
+    tr = ref_glsl.Trace()
+    dev = g.Device(0)
+    try:
+        for sc, n, seed in ((scenes.make_box1(tess=4), 100000, 31), (scenes.make_box1(tess=2, coincident_faces=True), 50000, 32), (sponza_small, 200000, 33)):
+            rays = make_ray_batch(g, sc, n, seed)
+            tr.set_scene(sc)
+            want = tr.trace(g, rays)
+            dev.upload_scene(sc)
+            for mode in (g.GI_TRAVERSAL_FAST, g.GI_TRAVERSAL_REFERENCE):
+                dev.set_option(g.GI_OPT_TRAVERSAL, mode)
+                assert_same_hits(dev.trace(rays), want, rays, "cuda mode %d seed %d" % (mode, seed))
+    finally:
+        dev.close()
+
+
+@live
+@pytest.mark.gpu
+def test_cuda_pathtracer_vs_reference_glsl(g, orc, scenes):
+    """One path-tracer iteration of the CUDA path against pathtracer.comp itself: same paths and random numbers; what differs is the device's
+    transcendental functions and FMA contraction in shading -- relMSE <= 1e-3 (the tolerance of bench.py's relmse), <= 2 % of the pixels off by > 1 %."""
+    pt = ref_glsl.PathTracer()
+    sc = scenes.make_box1(tess=4)
+    pt.set_scene(sc)
+    W = H = 128
+    rs = g.RendererSystem(0)
+    try:
+        rs.SetScene(sc); rs.SetScreenSize(W, H)
+        rs.SetCamera(scenes.BOX1_CAMERA["pos"], scenes.BOX1_CAMERA["lookat"], scenes.BOX1_CAMERA["fov"])
+        rs.SetRenderer("PT")
+        samples, seed, cam = rs.GetInitialLightSamples(), rs.GetFrameSeed(), rs.GetCamera()
+        rs.Draw()
+        img = rs.ReadBackbuffer()
+    finally:
+        rs.close()
+    want = pt.render(np.frombuffer(bytes(cam), dtype=np.float32) if not isinstance(cam, np.ndarray) else cam, W, H, samples, seed)
+    x, r = img[..., :3].astype(np.float64), want[..., :3].astype(np.float64)
+    relmse = float((((x - r) ** 2) / (r ** 2 + 1e-2)).sum(axis=2).mean())
+    off = float((np.abs(x - r) / (np.abs(r) + 1e-3)).max(axis=2).__gt__(1e-2).mean())
+    assert relmse <= 1e-3 and off < 0.02, (relmse, off)

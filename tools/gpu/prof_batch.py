@@ -75,6 +75,9 @@ def main():
             kt = dev.kernel_times()
             r["kernel_ms_per_iteration"] = {k: v[0] / args.iters for k, v in kt.items() if v[1]}
             dev.set_option(g.GI_OPT_KERNEL_TIMING, 0)
+        cn = dev.counters()
+        r["shaded_per_closest_ray"] = cn["shaded_vertices"] / max(cn["closest_rays"], 1)
+        r["splats_per_any_ray"] = cn["splats"] / max(cn["any_rays"], 1)
         out.append(r)
         print(json.dumps(r), flush=True)
     dev.close()
