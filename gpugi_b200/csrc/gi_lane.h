@@ -77,16 +77,6 @@ struct WfCounters
 #if WF_CENTRE_EXTENT && !(WF_WIDE4 && WF_CACHE_INV)
 #error "WF_CENTRE_EXTENT needs WF_WIDE4 and WF_CACHE_INV"
 #endif
-#ifndef WF_MERGED_POP
-#define WF_MERGED_POP 0    // a lane that needs its next stack entry (after a leaf, or after an inner step that hit nothing) only notes it (WF_NODE_POP); the
-#endif                     // pop itself happens at ONE place, at the head of the next inner-node step, for all such lanes of the warp together
-#ifndef WF_ANY_UNSORTED
-#define WF_ANY_UNSORTED 0  // inner-node steps of a warp whose walking lanes are all any-hit rays skip the sorting network (the answer of an any-hit ray
-#endif                     // does not depend on the visit order) and push without entry distances
-#if WF_MERGED_POP && WF_POSTPONE_LEAF
-#error "WF_MERGED_POP and WF_POSTPONE_LEAF exclude each other"
-#endif
-#define WF_NODE_POP int(0x80000001) // not a leaf code: leaf indices stay below 2^30
 #define WF_MAX_CAND 8
 
 enum { WFL_ANY = 1u, WFL_OVERFLOW = 2u, WFL_OCCLUDED = 4u, WFL_EXACT = 8u, WFL_COLLECT = 16u, WFL_GUARD = 32u };
@@ -204,17 +194,6 @@ GI_HD void wfPop(WfLane& L, const STK& stack)
 #endif
 }
 
-// what a lane does when it has nothing left at its current node: take the next stack entry now, or (WF_MERGED_POP) note that it needs one
-template <class STK>
-GI_HD void wfNext(WfLane& L, const STK& stack)
-{
-#if WF_MERGED_POP
-	L.node = WF_NODE_POP;
-#else
-	wfPop(L, stack);
-#endif
-}
-
 // WF_POSTPONE_LEAF: a lane standing at a leaf with an empty stash moves the leaf into the stash and goes on with the next node
 template <class STK>
 GI_HD void wfStash(WfLane& L, const STK& stack)
@@ -238,7 +217,7 @@ GI_HD bool wfAtLeaf(const WfLane& L)
 #if WF_POSTPONE_LEAF
 	return L.pend != 0;
 #else
-	return L.node < 0 && L.node != WF_NODE_DONE && L.node != WF_NODE_POP;
+	return L.node < 0 && L.node != WF_NODE_DONE;
 #endif
 }
 
@@ -456,34 +435,10 @@ GI_HD void wfInnerStep(WfLane& L, const DScene& s, const STK& stack, CNT& cnt)
 		if (f1 < GI_INF) wfPush(L, stack, c1, f1);
 		L.node = c0;
 	}
-	else wfNext(L, stack);
+	else wfPop(L, stack);
 	wfStash(L, stack);
 }
 
-// WF_ANY_UNSORTED: the same step for an any-hit ray when the order of the visits is nobody's business: no sorting network, the first accepted
-// child (in slot order) is next, the others are pushed without an entry distance (0 passes every cull; an any-hit ray's limit never shrinks)
-template <class STK, class CNT>
-GI_HD void wfInnerStepAny(WfLane& L, const DScene& s, const STK& stack, CNT& cnt)
-{
-	const uint32_t* nb = s.qNodes + 24 * size_t(L.node);
-	const U8 a = ld8(nb), b = ld8(nb + 8), c = ld8(nb + 16);
-	cnt.template add<WFC_NODES>(4u); cnt.template add<WFC_INNER_STEPS>(1u);
-	float n0, n1, n2, n3, r0, r1, r2, r3;
-	wfCentreTest(L, i2f(int(a.v[0])), i2f(int(a.v[1])), i2f(int(a.v[2])), wfHalfExtent(b.v[4], 0), wfHalfExtent(b.v[5], 0), wfHalfExtent(b.v[6], 0), n0, r0);
-	wfCentreTest(L, i2f(int(a.v[3])), i2f(int(a.v[4])), i2f(int(a.v[5])), wfHalfExtent(b.v[4], 1), wfHalfExtent(b.v[5], 1), wfHalfExtent(b.v[6], 1), n1, r1);
-	wfCentreTest(L, i2f(int(a.v[6])), i2f(int(a.v[7])), i2f(int(b.v[0])), wfHalfExtent(b.v[7], 2), wfHalfExtent(c.v[0], 2), wfHalfExtent(c.v[1], 2), n2, r2);
-	wfCentreTest(L, i2f(int(b.v[1])), i2f(int(b.v[2])), i2f(int(b.v[3])), wfHalfExtent(b.v[7], 3), wfHalfExtent(c.v[0], 3), wfHalfExtent(c.v[1], 3), n3, r3);
-	const bool p0 = n0 <= r0, p1 = n1 <= r1, p2 = n2 <= r2, p3 = n3 <= r3;
-	const int c0 = int(c.v[4]), c1 = int(c.v[5]), c2 = int(c.v[6]), c3 = int(c.v[7]);
-	if (p0 || p1 || p2 || p3)
-	{
-		if (p3 && (p0 || p1 || p2)) wfPush(L, stack, c3, 0.0f);
-		if (p2 && (p0 || p1)) wfPush(L, stack, c2, 0.0f);
-		if (p1 && p0) wfPush(L, stack, c1, 0.0f);
-		L.node = p0 ? c0 : (p1 ? c1 : (p2 ? c2 : c3));
-	}
-	else wfNext(L, stack);
-}
 #elif WF_WIDE4
 GI_HD bool wfSlabTestChild(const WfLane& L, const uint32_t* node, int child, float& nearLow) { return wfSlabTest(L, node[3 * child], node[3 * child + 1], node[3 * child + 2], nearLow); }
 
@@ -527,7 +482,7 @@ GI_HD void wfInnerStep(WfLane& L, const DScene& s, const STK& stack, CNT& cnt)
 #endif
 		L.node = c0;
 	}
-	else wfNext(L, stack);
+	else wfPop(L, stack);
 #else
 	// three exchanges: the nearest child is exact (slot 0), slot 2 holds the loser of the final and is pushed last (popped first);
 	// the order of the stack is a heuristic only -- every entry carries its own entry distance for the cull at pop time
@@ -540,7 +495,7 @@ GI_HD void wfInnerStep(WfLane& L, const DScene& s, const STK& stack, CNT& cnt)
 		if (f2 < GI_INF) wfPush(L, stack, c2, f2);
 		L.node = c0;
 	}
-	else wfNext(L, stack);
+	else wfPop(L, stack);
 #endif
 	wfStash(L, stack);
 }
@@ -565,7 +520,7 @@ GI_HD void wfInnerStep(WfLane& L, const DScene& s, const STK& stack, CNT& cnt)
 	}
 	else if (h0) L.node = c0;
 	else if (h1) L.node = c1;
-	else wfNext(L, stack);
+	else wfPop(L, stack);
 	wfStash(L, stack);
 }
 
@@ -578,7 +533,7 @@ GI_HD void wfLeafDone(WfLane& L, const STK& stack)
 #if WF_POSTPONE_LEAF
 	wfStash(L, stack);
 #else
-	wfNext(L, stack);
+	wfPop(L, stack);
 #endif
 }
 
@@ -746,9 +701,6 @@ GI_HD void wfWalkSingle(WfLane& L, const DScene& s, F3 o, F3 d, float tMax, bool
 	for (;;)
 	{
 		wfStash(L, stack);
-#if WF_MERGED_POP
-		if (L.node == WF_NODE_POP) wfPop(L, stack);
-#endif
 		if (wfFinished(L)) { if (wfEndOfWalk(L, s, cand, cnt)) return; continue; }
 #if WF_POSTPONE_LEAF
 		// as late as possible: the stash is only tested when the lane is blocked at a second leaf or has run out of nodes
@@ -756,9 +708,6 @@ GI_HD void wfWalkSingle(WfLane& L, const DScene& s, F3 o, F3 d, float tMax, bool
 		else wfLeafStep(L, s, stack, cand, cnt);
 #else
 		if (L.node < 0) wfLeafStep(L, s, stack, cand, cnt);
-#if WF_ANY_UNSORTED && WF_CENTRE_EXTENT
-		else if (L.flags & WFL_ANY) wfInnerStepAny(L, s, stack, cnt);
-#endif
 		else wfInnerStep(L, s, stack, cnt);
 #endif
 	}

@@ -419,43 +419,18 @@ GI_D void wfTraceLoop(const DScene& s, const IO& io, uint32_t* workCounter, WfTu
 		// ---- one leaf step for the lanes waiting at a leaf
 		if (active) wfStash(L, stack); // (a freshly loaded / restarted ray may stand at a leaf: single-leaf scenes)
 		if (active && wfAtLeaf(L)) wfLeafStep(L, s, stack, cand, cnt);
-		// ---- inner-node steps while enough lanes are at inner nodes (WF_MERGED_POP: or in need of their next stack entry, which they take at the head of the step)
-#if WF_MERGED_POP
-#define WF_WANTS_INNER(L) ((L).node >= 0 || (L).node == WF_NODE_POP)
-#else
-#define WF_WANTS_INNER(L) ((L).node >= 0)
-#endif
-		unsigned innerMask = __ballot_sync(0xffffffffu, WF_WANTS_INNER(L));
+		// ---- inner-node steps while enough lanes are at inner nodes
+		unsigned innerMask = __ballot_sync(0xffffffffu, L.node >= 0);
 		if (innerMask == 0u) continue;
 #if WF_BATCH_RETIRE
-		const unsigned walking = __ballot_sync(0xffffffffu, active && !wfFinished(L));
-		const int keepGoing = max(1, (__popc(walking) * tune.minInner) >> 5); // lanes still walking
+		const int keepGoing = max(1, (__popc(__ballot_sync(0xffffffffu, active && !wfFinished(L))) * tune.minInner) >> 5); // lanes still walking
 #else
-		const unsigned walking = activeMask;
 		const int keepGoing = max(1, (__popc(activeMask) * tune.minInner) >> 5);
-#endif
-#if WF_ANY_UNSORTED && WF_CENTRE_EXTENT
-		// every walking lane of the warp carries an any-hit ray (the queue hands out closest-hit rays first, then the shadow rays): unsorted steps
-		if (__all_sync(0xffffffffu, !((walking >> lane) & 1u) || (L.flags & WFL_ANY)))
-		{
-			do
-			{
-#if WF_MERGED_POP
-				if (L.node == WF_NODE_POP) wfPop(L, stack);
-#endif
-				if (L.node >= 0) wfInnerStepAny(L, s, stack, cnt);
-				innerMask = __ballot_sync(0xffffffffu, WF_WANTS_INNER(L));
-			} while (__popc(innerMask) >= keepGoing);
-			continue;
-		}
 #endif
 		do
 		{
-#if WF_MERGED_POP
-			if (L.node == WF_NODE_POP) wfPop(L, stack);
-#endif
 			if (L.node >= 0) wfInnerStep(L, s, stack, cnt);
-			innerMask = __ballot_sync(0xffffffffu, WF_WANTS_INNER(L));
+			innerMask = __ballot_sync(0xffffffffu, L.node >= 0);
 		} while (__popc(innerMask) >= keepGoing);
 	}
 }
@@ -479,9 +454,6 @@ GI_D void wfTraceLoop(const DScene& s, const IO& io, uint32_t* workCounter, WfTu
 // outweigh the fuller traversal steps.  Off; kept as the record of the experiment (profiles/r02_refill_experiment.md).
 #ifndef WF_PIPELINED_REFILL
 #define WF_PIPELINED_REFILL 0
-#endif
-#if WF_PIPELINED_REFILL && (WF_MERGED_POP || WF_ANY_UNSORTED)
-#error "the pipelined loop predates WF_MERGED_POP / WF_ANY_UNSORTED"
 #endif
 
 GI_D void wfAsyncWaitAll() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
