@@ -6,6 +6,7 @@ it C++ for oracle/ref_glsl/glsl_shim.hpp -- nothing is reordered, no expression 
   * `layout(...)`, `uniform`, `restrict`, `readonly`, `volatile`, `coherent` qualifiers are dropped; the braces of uniform / buffer BLOCKS are
     dropped so that their members become globals (an unsized array `T name[];` becomes `T* name;`);
   * parameter qualifiers: `out T x` / `inout T x` -> `T& x`, `in T x` -> `T x`;
+  * a mutable variable declared at file scope (private to an invocation in GLSL) becomes thread_local;
   * floating-point literals get the `f` suffix (a GLSL literal is a float, a C++ literal a double);
   * two RNG calls inside one vec2 constructor are put in a braced list (GLSL orders argument evaluation left to right, C++ does not);
   * `void main()` -> `void shader_main()`; `gl_GlobalInvocationID.xy` / `.x` -> the shim's per-invocation variables;
@@ -22,6 +23,8 @@ LAYOUT = re.compile(r"\blayout\s*\([^)]*\)\s*")
 OUT_PARAM = re.compile(r"\b(?:inout|out)\s+(\w+)\s+(\w+)")
 IN_PARAM = re.compile(r"\bin\s+(?=(?:const\s+)?\w+\s+\w+\s*(?:[,)]|$))")
 BLOCK_HEAD = re.compile(r"^\s*(?:uniform|buffer)\s+\w+\s*$")
+PRIVATE_GLOBAL = re.compile(r"^\s*(?:float|int|uint|bool|vec[234]|ivec[234]|uvec[234])\s+\w+\s*(?:\[[^\]]*\])?\s*(?:=[^;]*)?;")
+STATE = {"depth": 0}
 UNSIZED = re.compile(r"^(\s*)(\w+)\s+(\w+)\s*\[\s*\]\s*;")
 
 
@@ -60,7 +63,9 @@ def convert(path, out, seen_depth=0):
         if s.startswith("#"):
             out.append(FLOAT_LIT.sub(r"\1f", line) if s.startswith("#define") else line)
             continue
-        if "/*" in line and "*/" not in line.split("/*", 1)[1]:
+        # a block comment that opens on this line (before any // ) and does not close on it
+        i_block, i_line = line.find("/*"), line.find("//")
+        if i_block >= 0 and (i_line < 0 or i_block < i_line) and "*/" not in line[i_block + 2:]:
             in_comment = True
             out.append(line)
             continue
@@ -84,6 +89,10 @@ def convert(path, out, seen_depth=0):
             code = re.sub(r"\}\s*\w*\s*;", "", code, count=1)
         if in_block == 2:
             code = UNSIZED.sub(r"\1\2* \3;", code)
+        # a mutable variable at file scope is private to the invocation in GLSL: one per thread here
+        if STATE["depth"] == 0 and in_block == 0 and PRIVATE_GLOBAL.match(code):
+            code = "thread_local " + code.lstrip()
+        STATE["depth"] += code.count("{") - code.count("}")
         code = OUT_PARAM.sub(r"\1& \2", code)
         code = IN_PARAM.sub("", code)
         code = FLOAT_LIT.sub(r"\1f", code)

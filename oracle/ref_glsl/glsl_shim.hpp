@@ -309,8 +309,31 @@ inline vec4 textureLod(const samplerCubeArray& s, const vec4&, float) { return s
 
 // RGBA32F image (the backbuffer): the driver points it at the caller's accumulator
 struct image2D { float* rgba = nullptr; int w = 0, h = 0; };
-inline vec4 imageLoad(const image2D& im, const ivec2& p) { const float* q = im.rgba + 4 * (size_t(p.y) * im.w + p.x); return vec4(q[0], q[1], q[2], q[3]); }
-inline void imageStore(const image2D& im, const ivec2& p, const vec4& v) { float* q = im.rgba + 4 * (size_t(p.y) * im.w + p.x); q[0] = v.x; q[1] = v.y; q[2] = v.z; q[3] = v.w; }
+// (OpenGL 4.5 section 8.26: an access outside the image loads zero / is discarded)
+inline vec4 imageLoad(const image2D& im, const ivec2& p) { if (p.x < 0 || p.y < 0 || p.x >= im.w || p.y >= im.h) return vec4(0.0f); const float* q = im.rgba + 4 * (size_t(p.y) * im.w + p.x); return vec4(q[0], q[1], q[2], q[3]); }
+inline void imageStore(const image2D& im, const ivec2& p, const vec4& v) { if (p.x < 0 || p.y < 0 || p.x >= im.w || p.y >= im.h) return; float* q = im.rgba + 4 * (size_t(p.y) * im.w + p.x); q[0] = v.x; q[1] = v.y; q[2] = v.z; q[3] = v.w; }
+
+// the same memory seen as an R32F image four times as wide (screenreproject.glsl:7,43-46: WriteAtomic adds one channel at a time with
+// GL_NV_shader_atomic_float); returns the old value like the GLSL built-in
+inline float imageAtomicAdd(const image2D& im, const ivec2& p, float v)
+{
+	if (p.x < 0 || p.y < 0 || p.x >= 4 * im.w || p.y >= im.h) return 0.0f;
+	float* q = im.rgba + size_t(p.y) * size_t(im.w) * 4 + size_t(p.x);
+	float old;
+#pragma omp atomic capture
+	{ old = *q; *q += v; }
+	return old;
+}
+struct uimage2D { uint* data = nullptr; int w = 0, h = 0; };   // LockTexture: declared by the shaders, only used in commented-out code
+inline void memoryBarrierImage() {}
+// shader storage counters (lightcache.glsl:27-37)
+inline int atomicAdd(int& mem, int v)
+{
+	int old;
+#pragma omp atomic capture
+	{ old = mem; mem += v; }
+	return old;
+}
 
 // per-invocation built-in (glsl2cpp.py rewrites gl_GlobalInvocationID.xy)
 extern thread_local uvec2 gl_GlobalInvocationID_xy;

@@ -3,6 +3,11 @@
 // the scene goes in as the GiSceneDesc the product and the oracle take, rays / images come out.  tests/ref_glsl.py binds it.
 //   REFGLSL_TRACE   (trace_batch.comp)   refglsl_trace: TraceRay / TraceRayAnyHit of traceray.glsl on a ray batch
 //   REFGLSL_PT      (pathtracer.comp)    refglsl_render_pt: one dispatch of the reference's path tracer main() over a pixel region
+//   REFGLSL_WHITTED (whittedraytracer.comp) the same entry point over the Whitted tracer's main()
+//   REFGLSL_LPT     (lighttracer.comp, optionally -DSAVE_LIGHT_CACHE [-DSAVE_LIGHT_CACHE_WARMUP])  refglsl_render_lpt: light paths first .. first + count
+//   REFGLSL_SHOW    (showlightcaches.comp)  refglsl_show_light_caches
+//   REFGLSL_BPT     (bidirpathtracer/pathtracer_bidir.comp)  refglsl_render_bpt_eye: the eye pass over a pixel region, reading a given light cache
+// Invocations run in ascending order on ONE thread wherever their order is visible in the result (atomic float adds, light-cache slots).
 #include "gpugi_b200.h"
 
 #include <vector>
@@ -111,7 +116,7 @@ REFGLSL_API int refglsl_trace(const GiRay* rays, uint32_t n, GiHit* hits)
 }
 #endif
 
-#ifdef REFGLSL_PT
+#if defined(REFGLSL_PT) || defined(REFGLSL_WHITTED)
 // One Pathtracer::Draw (pathtracer.cpp:47-50: glDispatchCompute(W / 8, H / 8, 1) of pathtracer.comp) restricted to the invocations of a pixel
 // region; uniforms as RendererSystem::PerIterationBufferUpdate / SetCamera / SetScreenSize fill them.  accum = the RGBA32F backbuffer (in / out).
 REFGLSL_API int refglsl_render_pt(const GiCamera* cam, int width, int height, const GiLightSample* samples, int num_samples, uint32_t frame_seed,
@@ -126,9 +131,111 @@ REFGLSL_API int refglsl_render_pt(const GiCamera* cam, int width, int height, co
 	PixelArea = cam->pixel_area;
 	FrameSeed = frame_seed;
 	InitialLightSampleBuffer.data = reinterpret_cast<const float*>(samples); InitialLightSampleBuffer.comps = 4;
+#ifdef REFGLSL_PT
 	EnvironmentMap.constant = vec4(0.0f);
+#endif
 	OutputTexture.rgba = accum; OutputTexture.w = width; OutputTexture.h = height;
 	const int gw = (width / 8) * 8, gh = (height / 8) * 8;   // whole work groups only (integer division, pathtracer.cpp:50)
+	x1 = x1 < gw ? x1 : gw; y1 = y1 < gh ? y1 : gh;
+#pragma omp parallel for schedule(dynamic, 1)
+	for (int y = y0; y < y1; ++y)
+		for (int x = x0; x < x1; ++x)
+		{
+			gl_GlobalInvocationID_xy = uvec2(uint(x), uint(y));
+			gl_GlobalInvocationID_x = uint(x);
+			shader_main();
+		}
+	return 0;
+}
+#endif
+
+#ifndef REFGLSL_TRACE
+namespace {
+void setFrame(const GiCamera* cam, int width, int height, const GiLightSample* samples, int num_samples, uint32_t frame_seed, float* accum)
+{
+	BackbufferSize = ivec2(width, height);
+	NumInitialLightSamples = num_samples;
+	CameraU = vec3(cam->u[0], cam->u[1], cam->u[2]);
+	CameraV = vec3(cam->v[0], cam->v[1], cam->v[2]);
+	CameraW = vec3(cam->w[0], cam->w[1], cam->w[2]);
+	CameraPosition = vec3(cam->position[0], cam->position[1], cam->position[2]);
+	PixelArea = cam->pixel_area;
+	FrameSeed = frame_seed;
+	InitialLightSampleBuffer.data = reinterpret_cast<const float*>(samples); InitialLightSampleBuffer.comps = 4;
+	OutputTexture.rgba = accum; OutputTexture.w = width; OutputTexture.h = height;
+}
+}
+#endif
+
+#ifdef REFGLSL_LPT
+// LightPathtracer::Draw / the light pass of BidirectionalPathtracer::Draw (lightpathtracer.cpp:45-51, bidirectionalpathtracer.cpp:182-195): invocations
+// first .. first + count of lighttracer.comp's main().  SAVE_LIGHT_CACHE builds: `cache` = LightCacheEntry array (64 bytes each, capacity entries),
+// counters[0] = NumLightCacheEntries (in: what resetcounter.comp set, out: after the pass), counters[1] = LightPathLengthSum.
+REFGLSL_API int refglsl_render_lpt(const GiCamera* cam, int width, int height, const GiLightSample* samples, int num_samples, uint32_t frame_seed,
+                                   int num_rays_per_light_sample, float* accum, uint32_t first, uint32_t count, void* cache, int capacity, int* counters)
+{
+	setFrame(cam, width, height, samples, num_samples, frame_seed, accum);
+	NumRaysPerLightSample = num_rays_per_light_sample;
+#ifdef SAVE_LIGHT_CACHE
+	LightRayPixelWeight = 3.14159265358979f * 2.0f / float(num_rays_per_light_sample);   // bidirectionalpathtracer.cpp:34 (not read by these shaders)
+	LightCacheCapacity = capacity;
+	AverageLightPathLength = 0;
+	LightCacheEntries = static_cast<LightCacheEntry*>(cache);
+	NumLightCacheEntries = counters[0];
+	LightPathLengthSum = counters[1];
+#endif
+	for (uint32_t i = first; i < first + count; ++i)
+	{
+		gl_GlobalInvocationID_x = i;
+		gl_GlobalInvocationID_xy = uvec2(i, 0u);
+		shader_main();
+	}
+#ifdef SAVE_LIGHT_CACHE
+	counters[0] = NumLightCacheEntries;
+	counters[1] = LightPathLengthSum;
+#endif
+	return 0;
+}
+REFGLSL_API int refglsl_light_cache_entry_size(void)
+{
+#ifdef SAVE_LIGHT_CACHE
+	return int(sizeof(LightCacheEntry));
+#else
+	return 0;
+#endif
+}
+#endif
+
+#ifdef REFGLSL_SHOW
+// the second dispatch of LightPathtracer::Draw (lightpathtracer.cpp:49-50): showlightcaches.comp, one invocation per initial light sample
+REFGLSL_API int refglsl_show_light_caches(const GiCamera* cam, int width, int height, const GiLightSample* samples, int num_samples, float* accum)
+{
+	setFrame(cam, width, height, samples, num_samples, 0u, accum);
+	for (int i = 0; i < num_samples; ++i)
+	{
+		gl_GlobalInvocationID_x = uint(i);
+		gl_GlobalInvocationID_xy = uvec2(uint(i), 0u);
+		shader_main();
+	}
+	return 0;
+}
+#endif
+
+#ifdef REFGLSL_BPT
+// the eye pass of BidirectionalPathtracer::Draw (bidirectionalpathtracer.cpp:196-201): pathtracer_bidir.comp over a pixel region, with the
+// LightPathTrace block and the light cache as the light pass left them
+REFGLSL_API int refglsl_render_bpt_eye(const GiCamera* cam, int width, int height, const GiLightSample* samples, int num_samples, uint32_t frame_seed,
+                                       int num_rays_per_light_sample, const void* cache, int capacity, int num_entries, int average_light_path_length,
+                                       float* accum, int x0, int y0, int x1, int y1)
+{
+	setFrame(cam, width, height, samples, num_samples, frame_seed, accum);
+	NumRaysPerLightSample = num_rays_per_light_sample;
+	LightRayPixelWeight = 3.14159265358979f * 2.0f / float(num_rays_per_light_sample);   // bidirectionalpathtracer.cpp:34 (not read by these shaders)
+	LightCacheCapacity = capacity;
+	AverageLightPathLength = average_light_path_length;
+	LightCacheEntries = static_cast<LightCacheEntry*>(const_cast<void*>(cache));
+	NumLightCacheEntries = num_entries;
+	const int gw = (width / 8) * 8, gh = (height / 8) * 8;
 	x1 = x1 < gw ? x1 : gw; y1 = y1 < gh ? y1 : gh;
 #pragma omp parallel for schedule(dynamic, 1)
 	for (int y = y0; y < y1; ++y)

@@ -10,6 +10,10 @@ inputs and stores inputs + outputs in ref_glsl.npz, which travels with the repos
                                  3000 random triangles (overlaps, slivers)
   pt_samples, pt_seeds, pt_cam   light samples, FrameSeeds and camera of ...
   pt_box1_64                     ... the SUM image of 3 iterations of pathtracer.comp's main() on box1 at 64 x 64, MAX_PATHLENGTH 16
+  lpt_box1_64, whitted_box1_64,  one iteration of lighttracer.comp + showlightcaches.comp, of whittedraytracer.comp, and of the bidirectional path tracer
+  bpt_box1_64, bpt_cache         (lighttracer.comp with SAVE_LIGHT_CACHE, then bidirpathtracer/pathtracer_bidir.comp) on box1 at 64 x 64 with 64 light
+                                 samples x 64 rays (x_*), invocations in ascending order on one thread; bpt_cache = the light cache the light pass wrote
+  lpt_f<k>_box1_64               lighttracer.comp compiled with RECONSTRUCTION_FILTER = 1, 2, 3;  cmis_bpt_box1_64 / cmis_cache: both BPT shaders with CHAINED_MIS
   pt_sponza_*                    the same for one iteration on the textured Sponza-shaped scene (30 k triangles, 64 x 36): textureLod with the
                                  sampler of scene.cpp:16-21 as defined in glsl_shim.hpp (GL 4.5 section 8.14.2, the oracle's definition)
 """
@@ -83,6 +87,34 @@ def main():
         out.update(pt_sponza_cam=cam2, pt_sponza_samples=s2, pt_sponza_seed=np.uint32(orc.wanghash(5)),
                    pt_sponza=pt.render(cam2, W2, H2, s2, orc.wanghash(5)))
         print("sponza mean", float(out["pt_sponza"][..., :3].mean()))
+    # the other renderers (one thread, invocations in ascending order: the order of the float atomics and of the light-cache slots is part of the result)
+    os.environ["OMP_NUM_THREADS"] = "1"
+    W = H = 64
+    nr = 64
+    s64 = samples[0][:64].copy()
+    seed = int(orc.wanghash(2))
+    lt = ref_glsl.LightTracer(); lt.set_scene(box1)
+    lpt = lt.render(cam, W, H, s64, seed, nr)
+    show = ref_glsl.ShowLightCaches(); show.set_scene(box1)
+    show.render(cam, W, H, s64, lpt)
+    wt = ref_glsl.WhittedRayTracer(); wt.set_scene(box1)
+    cap = 64 * nr * 4
+    lts = ref_glsl.LightTracer(save=True); lts.set_scene(box1)
+    bpt, cache, nent, _ = lts.render(cam, W, H, s64, seed, nr, capacity=cap)
+    eye = ref_glsl.BidirEyePass(); eye.set_scene(box1)
+    eye.render(cam, W, H, s64, seed, nr, cache, cap, nent, accum=bpt)
+    out.update(x_samples=s64, x_seed=np.uint32(seed), x_nr=np.int32(nr), x_capacity=np.int32(cap), lpt_box1_64=lpt, whitted_box1_64=wt.render(cam, W, H, s64, seed),
+               bpt_box1_64=bpt, bpt_cache=cache[:nent].copy(), bpt_entries=np.int32(nent))
+    # shader variants
+    for k in (1, 2, 3):
+        ltf = ref_glsl.LightTracer(reconstruction_filter=k); ltf.set_scene(box1)
+        out["lpt_f%d_box1_64" % k] = ltf.render(cam, W, H, s64, seed, nr)
+    ltc = ref_glsl.LightTracer(chained_mis=True); ltc.set_scene(box1)
+    cb, ccache, cn, _ = ltc.render(cam, W, H, s64, seed, nr, capacity=cap)
+    eyec = ref_glsl.BidirEyePass(chained_mis=True); eyec.set_scene(box1)
+    eyec.render(cam, W, H, s64, seed, nr, ccache, cap, cn, accum=cb)
+    out.update(cmis_bpt_box1_64=cb, cmis_cache=ccache[:cn].copy())
+    print("lpt sum", float(lpt[..., :3].sum()), "bpt sum", float(bpt[..., :3].sum()), "cache entries", nent)
     np.savez_compressed(os.path.join(HERE, "ref_glsl.npz"), **out)
     print("wrote", os.path.join(HERE, "ref_glsl.npz"), os.path.getsize(os.path.join(HERE, "ref_glsl.npz")), "bytes")
 

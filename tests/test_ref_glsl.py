@@ -22,6 +22,15 @@ def gold():
     return np.load(GOLDEN)
 
 
+@pytest.fixture
+def one_thread(orc):
+    """the oracle on one thread: float atomics and light-cache slots in invocation order, as in the single-threaded run of the shaders"""
+    n = orc.num_threads()
+    orc.set_num_threads(1)
+    yield
+    orc.set_num_threads(n)
+
+
 def assert_same_hits(got, want, rays, what):
     anyhit = rays["flags"] == 1
     assert np.array_equal(got["leaf_tri"], want["leaf_tri"]), what + ": hit flag / triangle index"
@@ -42,7 +51,6 @@ def test_oracle_traversal_equals_reference_glsl_golden(g, orc, scenes, gold, nam
 
 def test_oracle_pathtracer_equals_reference_glsl_golden(g, orc, scenes, gold):
     """Three iterations of the oracle's path tracer == main() of the reference's pathtracer.comp, every float of the sum image (box1, 64 x 64)."""
-    os.environ["OMP_NUM_THREADS"] = "1"
     sc = scenes.make_box1(tess=4)
     W = H = 64
     acc = np.zeros((H, W, 4), dtype=np.float32)
@@ -58,6 +66,67 @@ def test_oracle_pathtracer_textured_equals_reference_glsl_golden(g, orc, scenes,
     img, _ = orc.render_pt(sponza_small.desc, gold["pt_sponza_cam"], W, H, gold["pt_sponza_samples"], int(gold["pt_sponza_seed"]), 16)
     assert img[..., :3].sum() > 0
     assert np.array_equal(img.view(np.uint32), gold["pt_sponza"].view(np.uint32))
+
+
+def test_oracle_other_renderers_equal_reference_glsl_golden(g, orc, scenes, gold, one_thread):
+    """lighttracer.comp + showlightcaches.comp, whittedraytracer.comp, and the bidirectional path tracer (lighttracer.comp with SAVE_LIGHT_CACHE:
+    the light cache entry for entry; pathtracer_bidir.comp: the image) -- the oracle on one thread equals the reference's shaders in every float."""
+    sc = scenes.make_box1(tess=4)
+    W = H = 64
+    cam, s, seed, nr, cap = gold["pt_cam"], gold["x_samples"], int(gold["x_seed"]), int(gold["x_nr"]), int(gold["x_capacity"])
+    lpt, _ = orc.render_lpt(sc.desc, cam, W, H, s, seed, nr, 16, show_light_caches=True)
+    assert lpt[..., :3].sum() > 0 and np.array_equal(lpt.view(np.uint32), gold["lpt_box1_64"].view(np.uint32))
+    wh, _ = orc.render_whitted(sc.desc, cam, W, H, s, seed, 16)
+    assert np.array_equal(wh.view(np.uint32), gold["whitted_box1_64"].view(np.uint32))
+    bpt, _, counts, cache = orc.render_bpt(sc.desc, cam, W, H, s, seed, nr, cap, 16, return_cache=True)
+    n = int(gold["bpt_entries"])
+    assert counts[0] == n and np.array_equal(cache[:n].view(np.uint32), gold["bpt_cache"].view(np.uint32))
+    assert np.array_equal(bpt.view(np.uint32), gold["bpt_box1_64"].view(np.uint32))
+
+
+def test_oracle_shader_variants_equal_reference_glsl_golden(g, orc, scenes, gold, one_thread):
+    """RECONSTRUCTION_FILTER 1-3 (screenreproject.glsl:186-223) and CHAINED_MIS (chained_mis.glsl + its hooks in lighttracer.comp, screenreproject.glsl
+    and pathtracer_bidir.comp): the oracle's variants equal the reference's shaders compiled with those defines, in every float."""
+    sc = scenes.make_box1(tess=4)
+    W = H = 64
+    cam, s, seed, nr, cap = gold["pt_cam"], gold["x_samples"], int(gold["x_seed"]), int(gold["x_nr"]), int(gold["x_capacity"])
+    try:
+        for k in (1, 2, 3):
+            orc.set_variant(reconstruction_filter=k)
+            img, _ = orc.render_lpt(sc.desc, cam, W, H, s, seed, nr, 16, show_light_caches=False)
+            assert np.array_equal(img.view(np.uint32), gold["lpt_f%d_box1_64" % k].view(np.uint32)), k
+        orc.set_variant(reconstruction_filter=0, chained_mis=True)
+        img, _, counts, cache = orc.render_bpt(sc.desc, cam, W, H, s, seed, nr, cap, 16, return_cache=True)
+        n = gold["cmis_cache"].shape[0]
+        assert counts[0] == n and np.array_equal(cache[:n].view(np.uint32), gold["cmis_cache"].view(np.uint32))
+        assert np.array_equal(img.view(np.uint32), gold["cmis_bpt_box1_64"].view(np.uint32))
+        assert not np.array_equal(img, gold["bpt_box1_64"])   # (the variant does change the image)
+    finally:
+        orc.set_variant(reconstruction_filter=0, chained_mis=False)
+
+
+@live
+def test_oracle_other_renderers_equal_reference_glsl_live(g, orc, scenes, sponza_small, one_thread):
+    """Fresh seeds, another resolution, the textured scene with its point lights (omnidirectional light samples), a light cache that overflows."""
+    lt, show, wt, lts, eye = ref_glsl.LightTracer(), ref_glsl.ShowLightCaches(), ref_glsl.WhittedRayTracer(), ref_glsl.LightTracer(save=True), ref_glsl.BidirEyePass()
+    for sc, C, W, H, nls, nr, it, capf in ((scenes.make_box1(tess=2), scenes.BOX1_CAMERA, 56, 40, 32, 64, 4, 4.0), (sponza_small, scenes.SPONZA_CAMERA, 64, 40, 32, 64, 9, 0.6)):
+        cam = orc.camera(C["pos"], C["lookat"], C["fov"], W, H)
+        ls = g.LightSampler(sc); ls.seed(50 + it)
+        s = ls.generate(nls)
+        seed = orc.wanghash(it)
+        for lib in (lt, show, wt, lts, eye):
+            lib.set_scene(sc)
+        want = show.render(cam, W, H, s, lt.render(cam, W, H, s, seed, nr))
+        got, _ = orc.render_lpt(sc.desc, cam, W, H, s, seed, nr, 16, show_light_caches=True)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), "LPT"
+        got, _ = orc.render_whitted(sc.desc, cam, W, H, s, seed, 16)
+        assert np.array_equal(got.view(np.uint32), wt.render(cam, W, H, s, seed).view(np.uint32)), "Whitted"
+        cap = int(nls * nr * capf)
+        want, cache, nent, _ = lts.render(cam, W, H, s, seed, nr, capacity=cap)
+        eye.render(cam, W, H, s, seed, nr, cache, cap, nent, accum=want)
+        got, _, counts, ocache = orc.render_bpt(sc.desc, cam, W, H, s, seed, nr, cap, 16, return_cache=True)
+        assert counts[0] == nent and np.array_equal(ocache[:min(nent, cap)].view(np.uint32), cache[:min(nent, cap)].view(np.uint32)), "light cache"
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), "BPT"
 
 
 @live
