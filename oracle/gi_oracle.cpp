@@ -5,12 +5,15 @@
 // and bench.py's cpu_baseline / --impl reference legs may load this library; the product
 // (gpugi_b200/) never links, imports or calls it.
 //
-// PARITY UNPINNED: the reference ships no golden vectors, reference images or tests for
-// this path and cannot be built or run here (GLSL needing an NVIDIA GL 4.5
-// driver; MSVC-only host).  The only known-answer tests in the tree, the ray/box and
-// ray/triangle cases of dependencies/epsilon/unittest/intersection3d.cpp:236-298, are
-// checked in tests/test_oracle_kat.py; everything else is anchored on a line-by-line
-// restatement, each function citing the reference file:line it follows.
+// PARITY PINNED.  The reference ships no golden vectors, reference images or tests for this path and cannot
+// be built or run as a whole here (GLSL needing an NVIDIA GL 4.5 driver; MSVC-only host).  The restatement is pinned
+// (a) against the reference's OWN SHADER SOURCE run on the CPU -- oracle/ref_glsl/ compiles gpugi/shader/*.glsl / *.comp,
+// read where they lie, as C++ (oracle/_ref/libref_glsl_*.so); every function below that restates a shader equals it bit for
+// bit on ray batches and whole iterations of every renderer and variant (tests/test_ref_glsl.py, tests/golden/ref_glsl.npz);
+// (b) against the reference's C / C++ files compiled where they lie (random, hdrimage, bim + epsilon, bvhmake builders,
+// stb_image: tests/test_ref_pinned.py, test_bvhmake.py, test_imageio.py), and (c) the ray / box and ray / triangle KATs of
+// dependencies/epsilon/unittest/intersection3d.cpp:236-298 (tests/test_oracle_kat.py).  Each function cites the reference
+// file:line it follows.
 //
 // Arithmetic: every GLSL float op is one IEEE-754 binary32 operation, no contraction
 // (compile with -ffp-contract=off), min/max with fminf/fmaxf NaN semantics, normalize(v) =
