@@ -14,10 +14,11 @@ A "step" is one progressive refresh: --iters-per-step (default 16) sample passes
          sampling + 4-8 KB H2D + the iteration's kernels, streaming mode: one wave per call), per step one D2H read of the progressive
          RGBA32F image into pinned host memory (N > 1: every rank copies out its rows of the SUMMED image into one shared host image);
          final draining read inside the timed region.
-  relmse the iterations the CPU oracle renders for cpu_baseline, rendered on the GPU with the same light samples and frame seeds, compared
+  relmse the iterations the CPU baseline (the reference's shaders) renders for cpu_baseline, rendered on the GPU with the same light samples and frame seeds, compared
          on the oracle's pixels: mean_px sum_rgb (x - r)^2 / (r^2 + 1e-2)   (N = 1).
-  --impl reference   the reference's CPU side of this path: the oracle (CPU restatement of the reference shaders, kind "port" -- the
-         GLSL / MSVC reference cannot be built here) on all host threads, each step a bounded sample of the same iteration.
+  --impl reference   the reference's CPU side of this path: the reference's OWN shaders (gpugi/shader/*.comp, read where they lie and compiled as
+         C++ against a GLSL shim: oracle/ref_glsl, oracle/_ref/libref_glsl_*.so, kind "reference" -- the GL 4.5 / MSVC build itself cannot run here) on
+         all host threads, each step a bounded sample of the same iteration; where those libraries were not built, the oracle port (kind "port").
 Multi-GPU: one process per GPU (torchrun), iterations sharded round-robin over ranks, no data-path collective; scaling "weak".
 """
 import argparse
@@ -176,14 +177,55 @@ def stripe_regions(cfg, num_stripes):
     return [(0, y, W, y + 8) for y in ys]
 
 
-def oracle_pass(orc, cfg, scene, cam, samples, iteration, regions, acc, light_fraction=1.0):
-    """One bounded sample of iteration `iteration` on all host threads; returns (paths, rays, seconds, counters)."""
+class ReferenceShaders:
+    """The reference's OWN shaders on the host cores (oracle/_ref/libref_glsl_*.so: gpugi/shader/*.comp compiled as C++ where they lie, oracle/ref_glsl/):
+    cpu_baseline.kind = "reference".  None when the libraries were not built (no /root/reference at build time): the oracle port is timed instead."""
+
+    def __init__(self, scene):
+        from oracle import pyrefglsl as rg
+        self.pt, self.lpt, self.show, self.lpt_save, self.eye = rg.PathTracer(), rg.LightTracer(), rg.ShowLightCaches(), rg.LightTracer(save=True), rg.BidirEyePass()
+        assert self.pt.max_path_length == PATH_LENGTH
+        for lib in (self.pt, self.lpt, self.show, self.lpt_save, self.eye):
+            lib.set_scene(scene)
+
+    @staticmethod
+    def create(scene):
+        try:
+            from oracle import pyrefglsl as rg
+            return ReferenceShaders(scene) if rg.available() else None
+        except Exception as e:  # a library that does not load is not a reason to lose the baseline
+            log("reference shaders unavailable (%s): timing the oracle port" % e)
+            return None
+
+
+def oracle_pass(orc, cfg, scene, cam, samples, iteration, regions, acc, light_fraction=1.0, ref=None):
+    """One bounded sample of iteration `iteration` on all host threads; returns (paths, rays, seconds, counters).  ref: ReferenceShaders (the
+    reference's own shaders; rays are not counted there) or None (the oracle port)."""
     W, H = cfg["W"], cfg["H"]
     tot = {}
     seed = orc.wanghash(iteration)
     _, nr = paths_per_iteration(cfg)
+    gw, gh = W // 8 * 8, H // 8 * 8
+    region_paths = lambda r: max(0, min(r[2], gw) - r[0]) * max(0, min(r[3], gh) - r[1])
     t0 = time.perf_counter()
-    if cfg["renderer"] == "PT":
+    if ref is not None:
+        if cfg["renderer"] == "PT":
+            for r in regions:
+                ref.pt.render(cam, W, H, samples, seed, accum=acc, region=r)
+            tot = {"camera_paths": sum(region_paths(r) for r in regions)}
+        elif cfg["renderer"] == "LPT":
+            n = max(64, int(cfg["nls"] * nr * light_fraction) // 64 * 64)
+            ref.lpt.render(cam, W, H, samples, seed, nr, accum=acc, first=0, count=n, parallel=True)
+            if light_fraction >= 1.0:
+                ref.show.render(cam, W, H, samples, acc)
+            tot = {"light_paths": n}
+        else:
+            cap = int(cfg.get("cap") or cfg["nls"] * nr * 3)
+            n = cfg["nls"] * nr // 64 * 64
+            _, cache, nent, _ = ref.lpt_save.render(cam, W, H, samples, seed, nr, accum=acc, capacity=cap, parallel=True)
+            ref.eye.render(cam, W, H, samples, seed, nr, cache, cap, nent, accum=acc, region=regions[0])
+            tot = {"light_paths": n, "camera_paths": region_paths(regions[0])}
+    elif cfg["renderer"] == "PT":
         for r in regions:
             _, cnt = orc.render_pt(scene.desc, cam, W, H, samples, seed, PATH_LENGTH, region=r, accum=acc)
             for k, v in cnt.items():
@@ -199,6 +241,11 @@ def oracle_pass(orc, cfg, scene, cam, samples, iteration, regions, acc, light_fr
     return tot.get("camera_paths", 0) + tot.get("light_paths", 0), tot.get("closest_rays", 0) + tot.get("any_rays", 0), dt, tot
 
 
+REFERENCE_WHAT = ("the reference's own shaders (gpugi/shader/*.comp + *.glsl, read where they lie and compiled as C++: oracle/ref_glsl, oracle/_ref/libref_glsl_*.so) "
+                  "on the host cores with OpenMP over invocations")
+PORT_WHAT = "the oracle: a CPU restatement of the reference's shaders (the reference's GLSL / MSVC build cannot run here; oracle/_ref/libref_glsl_*.so not built)"
+
+
 def oracle_setup(cfg, scene):
     from oracle import pyoracle as orc
     C = cfg["cam"]
@@ -207,8 +254,9 @@ def oracle_setup(cfg, scene):
 
 
 def cpu_baseline(cfg, scene, sample_sets, budget_s=12.0):
-    """The oracle on this box's host cores over a bounded sample; also returns what it rendered (for relmse)."""
+    """The reference's own shaders (else the oracle port) on this box's host cores over a bounded sample; also returns what was rendered (for relmse)."""
     orc, cam = oracle_setup(cfg, scene)
+    ref = ReferenceShaders.create(scene)
     W, H = cfg["W"], cfg["H"]
     if cfg["renderer"] == "PT":
         regions, frac, what = stripe_regions(cfg, 9), 1.0, "9 evenly spaced 8-pixel stripes of the %dx%d frame" % (W, H)
@@ -221,16 +269,18 @@ def cpu_baseline(cfg, scene, sample_sets, budget_s=12.0):
     secs = 0.0
     tot = {}
     while secs < budget_s and it < len(sample_sets):
-        p, r, dt, cnt = oracle_pass(orc, cfg, scene, cam, sample_sets[it], it, regions, acc, frac)
+        p, r, dt, cnt = oracle_pass(orc, cfg, scene, cam, sample_sets[it], it, regions, acc, frac, ref)
         paths += p; rays += r; secs += dt; it += 1
         for k, v in cnt.items():
             tot[k] = tot.get(k, 0) + v
-    info = {"value": paths / secs / 1e6, "unit": "Mpaths/s", "mrays_per_s": rays / secs / 1e6, "cores": orc.num_threads(), "kind": "port",
+    info = {"value": paths / secs / 1e6, "unit": "Mpaths/s", "mrays_per_s": rays / secs / 1e6 if ref is None else None, "cores": orc.num_threads(),
+            "kind": "reference" if ref is not None else "port",
+            "what": REFERENCE_WHAT if ref is not None else PORT_WHAT,
             "sample": "%d iteration(s) x %s (%d paths, %.1f s)" % (it, what, paths, secs)}
     return info, acc, it, regions
 
 
-def relmse_vs_oracle(cfg, dev, g, sample_sets, oracle_acc, iterations, regions, nr, cap):
+def relmse_vs_oracle(cfg, dev, g, sample_sets, oracle_acc, iterations, regions, nr, cap, baseline_what=PORT_WHAT):
     """The oracle's iterations again on the GPU (same light samples, same FrameSeeds), compared on the pixels the oracle rendered."""
     from gpugi_b200 import parallel
     W, H = cfg["W"], cfg["H"]
@@ -251,7 +301,7 @@ def relmse_vs_oracle(cfg, dev, g, sample_sets, oracle_acc, iterations, regions, 
             mask[y0:y1, x0:x1] = True
     x = img[..., :3] / np.float32(iterations)
     r = oracle_acc[..., :3] / np.float32(iterations)
-    out = {"iterations": iterations, "pixels": int(mask.sum()), "vs": "CPU oracle (port of the reference shaders), same light samples and FrameSeeds",
+    out = {"iterations": iterations, "pixels": int(mask.sum()), "vs": baseline_what + ", same light samples and FrameSeeds",
            "definition": "mean_px sum_rgb (x - r)^2 / (r^2 + 1e-2)"}
     if cfg["renderer"] == "BPT":
         # the eye pass picks light-cache entries by slot and the slot order is scheduling dependent: the two images are two unbiased
@@ -270,7 +320,7 @@ def relmse_vs_oracle(cfg, dev, g, sample_sets, oracle_acc, iterations, regions, 
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the oracle port on this box's host cores, same config / metric."""
+    """--impl reference: the reference's own shaders (else the oracle port) on this box's host cores, same config / metric."""
     if rank != 0:
         return
     import gpugi_b200 as g
@@ -281,18 +331,19 @@ def run_reference(args, rank, world):
     cfg = configs(args)[args.config]
     scene, build_s = build_scene(cfg)
     orc, cam = oracle_setup(cfg, scene)
+    ref = ReferenceShaders.create(scene)
     W, H = cfg["W"], cfg["H"]
     ls = g.LightSampler(scene)
     acc = np.zeros((H, W, 4), dtype=np.float32)
     # calibrate the sample so that one step takes ~1.5 s
     if cfg["renderer"] == "PT":
-        oracle_pass(orc, cfg, scene, cam, ls.generate(cfg["nls"]), 0, stripe_regions(cfg, 3), acc)  # cold pass (page faults, sRGB table)
-        _, _, dt, _ = oracle_pass(orc, cfg, scene, cam, ls.generate(cfg["nls"]), 0, stripe_regions(cfg, 3), acc)
+        oracle_pass(orc, cfg, scene, cam, ls.generate(cfg["nls"]), 0, stripe_regions(cfg, 3), acc, 1.0, ref)  # cold pass (page faults, sRGB table)
+        _, _, dt, _ = oracle_pass(orc, cfg, scene, cam, ls.generate(cfg["nls"]), 0, stripe_regions(cfg, 3), acc, 1.0, ref)
         stripes = int(max(1, min(H // 8, round(3 * 1.5 / max(dt, 1e-3)))))
         regions, frac = stripe_regions(cfg, stripes), 1.0
         what = "%d evenly spaced 8-pixel stripes of one %dx%d iteration" % (stripes, W, H)
     elif cfg["renderer"] == "LPT":
-        _, _, dt, _ = oracle_pass(orc, cfg, scene, cam, ls.generate(cfg["nls"]), 0, None, acc, 0.02)
+        _, _, dt, _ = oracle_pass(orc, cfg, scene, cam, ls.generate(cfg["nls"]), 0, None, acc, 0.02, ref)
         frac = float(min(1.0, max(0.002, 0.02 * 1.5 / max(dt, 1e-3))))
         regions = None
         what = "%.1f %% of the light paths of one %dx%d iteration" % (100 * frac, W, H)
@@ -300,20 +351,21 @@ def run_reference(args, rank, world):
         regions, frac = [(0, H // 2 - 8, W, H // 2 + 8)], 1.0
         what = "the whole light pass + the eye pass of a 16-pixel band of one %dx%d iteration" % (W, H)
     for w in range(args.warmup if cfg["renderer"] == "PT" else 1):
-        oracle_pass(orc, cfg, scene, cam, ls.generate(cfg["nls"]), w, regions, acc, frac)
+        oracle_pass(orc, cfg, scene, cam, ls.generate(cfg["nls"]), w, regions, acc, frac, ref)
     paths = rays = 0
     t0 = time.perf_counter()
     for k in range(args.steps):
-        p, r, _, _ = oracle_pass(orc, cfg, scene, cam, ls.generate(cfg["nls"]), args.warmup + k, regions, acc, frac)
+        p, r, _, _ = oracle_pass(orc, cfg, scene, cam, ls.generate(cfg["nls"]), args.warmup + k, regions, acc, frac, ref)
         paths += p; rays += r
     secs = time.perf_counter() - t0
     value = paths / secs / 1e6
     sample = "each step = %s (%d paths)" % (what, paths // max(args.steps, 1))
     line = {"impl": "reference", "metric": metric_name(cfg), "value": value, "unit": "Mpaths/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": secs / max(args.steps, 1) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "mrays_per_s": rays / secs / 1e6,
+            "data": "synthetic", "mrays_per_s": rays / secs / 1e6 if ref is None else None,
             "config": {"workload": cfg["short"], "sample": sample},
-            "cpu_baseline": {"value": value, "unit": "Mpaths/s", "cores": orc.num_threads(), "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "Mpaths/s", "cores": orc.num_threads(), "kind": "reference" if ref is not None else "port",
+                             "what": REFERENCE_WHAT if ref is not None else PORT_WHAT, "sample": sample},
             "e2e": {"value": value, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -651,7 +703,7 @@ def run_ours(args, rank, world, local_rank):
         sets = [ls_host.generate(nls) for _ in range(64)]
         base, oracle_acc, its, regions = cpu_baseline(cfg, scene, sets, budget_s=args.cpu_budget)
         line["cpu_baseline"] = base
-        line["relmse"] = relmse_vs_oracle(cfg, dev, g, sets, oracle_acc, its, regions, nr, cap)
+        line["relmse"] = relmse_vs_oracle(cfg, dev, g, sets, oracle_acc, its, regions, nr, cap, base.get("what", PORT_WHAT))
     emit(line)
     rs.close()
     if dist is not None:

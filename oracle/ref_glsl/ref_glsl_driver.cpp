@@ -172,7 +172,7 @@ void setFrame(const GiCamera* cam, int width, int height, const GiLightSample* s
 // first .. first + count of lighttracer.comp's main().  SAVE_LIGHT_CACHE builds: `cache` = LightCacheEntry array (64 bytes each, capacity entries),
 // counters[0] = NumLightCacheEntries (in: what resetcounter.comp set, out: after the pass), counters[1] = LightPathLengthSum.
 REFGLSL_API int refglsl_render_lpt(const GiCamera* cam, int width, int height, const GiLightSample* samples, int num_samples, uint32_t frame_seed,
-                                   int num_rays_per_light_sample, float* accum, uint32_t first, uint32_t count, void* cache, int capacity, int* counters)
+                                   int num_rays_per_light_sample, float* accum, uint32_t first, uint32_t count, void* cache, int capacity, int* counters, int parallel)
 {
 	setFrame(cam, width, height, samples, num_samples, frame_seed, accum);
 	NumRaysPerLightSample = num_rays_per_light_sample;
@@ -184,10 +184,13 @@ REFGLSL_API int refglsl_render_lpt(const GiCamera* cam, int width, int height, c
 	NumLightCacheEntries = counters[0];
 	LightPathLengthSum = counters[1];
 #endif
-	for (uint32_t i = first; i < first + count; ++i)
+	// parallel != 0: throughput runs on all host threads (the atomics of the shim are atomic); the order of the float adds and of the
+	// light-cache slots is then scheduling dependent, as on a GPU
+#pragma omp parallel for schedule(dynamic, 64) if (parallel)
+	for (int64_t i = first; i < int64_t(first) + int64_t(count); ++i)
 	{
-		gl_GlobalInvocationID_x = i;
-		gl_GlobalInvocationID_xy = uvec2(i, 0u);
+		gl_GlobalInvocationID_x = uint(i);
+		gl_GlobalInvocationID_xy = uvec2(uint(i), 0u);
 		shader_main();
 	}
 #ifdef SAVE_LIGHT_CACHE
