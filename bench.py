@@ -268,7 +268,8 @@ def cpu_baseline(cfg, scene, sample_sets, budget_s=12.0):
     paths = rays = it = 0
     secs = 0.0
     tot = {}
-    while secs < budget_s and it < len(sample_sets):
+    # relmse is quoted at 64 iterations: keep going past the budget (up to 5 x) until they are there
+    while (secs < budget_s or (it < 64 and secs < 5.0 * budget_s)) and it < len(sample_sets):
         p, r, dt, cnt = oracle_pass(orc, cfg, scene, cam, sample_sets[it], it, regions, acc, frac, ref)
         paths += p; rays += r; secs += dt; it += 1
         for k, v in cnt.items():
@@ -312,7 +313,10 @@ def relmse_vs_oracle(cfg, dev, g, sample_sets, oracle_acc, iterations, regions, 
         out.update({"value": parallel.rel_mse(bx, br), "tolerance": 0.5, "note": "8x8 block means; statistical (light-cache slot order is scheduling dependent)",
                     "mean_ratio": float(bx.mean() / max(br.mean(), 1e-20))})
     else:
-        out.update({"value": parallel.rel_mse(x[mask], r[mask]), "tolerance": 1e-3,
+        # same paths, same random numbers: what differs is a discrete decision flipped by a transcendental's last bit on a few paths; the number of
+        # such paths grows with the iteration count N and each one's weight in the mean image falls with 1 / N, so relMSE ~ 1 / N: the
+        # tolerance is stated at 64 iterations and scaled when the CPU budget allowed fewer
+        out.update({"value": parallel.rel_mse(x[mask], r[mask]), "tolerance": 1e-3 * max(1.0, 64.0 / iterations), "tolerance_at_64_iterations": 1e-3,
                     "note": "same paths, same random numbers; differences are transcendental-function rounding (device vs libm) on a few pixels"
                             + (" and the order of the float atomics" if cfg["renderer"] == "LPT" else "")})
     out["ok"] = bool(out["value"] <= out["tolerance"])
