@@ -288,11 +288,7 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MIN_BLOCKS) k_wf_tr
 	io.q.reconFilter = w.q.shadowPos ? w.f.reconFilter : 0;
 	WfCounters<STEPS> cnt;
 	if (REFERENCE) wfTraceLoopReference(w.f.scene, io, counts + 2, cnt);
-#if WF_PIPELINED_REFILL
-	else wfTraceLoopPipelined(w.f.scene, io, counts + 2, w.tune, cnt);
-#else
 	else wfTraceLoop(w.f.scene, io, counts + 2, w.tune, cnt);
-#endif
 	flushWarpCounters(counters, cnt.v, WFC_COUNT);
 }
 
@@ -306,27 +302,13 @@ __global__ void __launch_bounds__(WF_TRACE_THREADS, WF_TRACE_MIN_BLOCKS) k_wf_tr
 	io.hits = reinterpret_cast<float4*>(hits);
 	io.n = n;
 	WfCounters<STEPS> cnt;
-#if WF_PIPELINED_REFILL
-	wfTraceLoopPipelined(s, io, workCounter, tune, cnt);
-#else
 	wfTraceLoop(s, io, workCounter, tune, cnt);
-#endif
 	flushWarpCounters(counters, cnt.v, WFC_COUNT);
 }
 
-// Work distribution of the shade kernels: 32 consecutive queue slots per warp and fetch.  WF_SHADE_PREFETCH software-pipelines the first levels
-// of the dependent gather chain (queue records from HBM -> leaf record / leaf triangle from L2 -> vertices, material -> textures): while a warp
-// shades its current 32 slots it already knows the next two fetches; the hit records of the fetch after next are loaded (one register), and the
-// ray record, leaf record and leaf triangle of the next fetch -- whose hit records arrived during the previous pass -- are prefetched.
-//   0 off   1 ray records (L2)   2 + leaf record and leaf triangle (L1)
-// B200 A/B (shade kernel per iteration, ms; 0 / 1 / 2): C2 k_wf_shade_pt 0.326 / 0.344 / 0.358, C3 k_wf_shade_eye + light 1.740 / 1.833 / 1.932,
-// C4 k_wf_shade_light 1.505 / 1.552 / 1.658 -- the prefetches cost more (instructions, spills at 64 registers) than the shorter chain saves: off.
-#ifndef WF_SHADE_PREFETCH
-#define WF_SHADE_PREFETCH 0
-#endif
-GI_D void wfPrefetchL2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
-GI_D void wfPrefetchL1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
-
+// Work distribution of the shade kernels: 32 consecutive queue slots per warp and fetch.  (A software-pipelined variant that prefetched the
+// ray records, leaf record and leaf triangle of the next fetch measured slower on B200 -- C2 k_wf_shade_pt 0.326 -> 0.344 / 0.358 ms, C3 1.740 -> 1.833 /
+// 1.932, C4 1.505 -> 1.552 / 1.658 -- and was removed)
 GI_D uint32_t wfGrab32(uint32_t* counter)
 {
 	uint32_t base = 0;
@@ -337,7 +319,6 @@ GI_D uint32_t wfGrab32(uint32_t* counter)
 template <class BODY>
 GI_D void wfShadeLoop(const WfFrame& w, uint32_t* counter, uint32_t n, BODY body)
 {
-#if WF_SHADE_PREFETCH == 0
 	for (;;)
 	{
 		const uint32_t base = wfGrab32(counter);
@@ -345,37 +326,6 @@ GI_D void wfShadeLoop(const WfFrame& w, uint32_t* counter, uint32_t n, BODY body
 		const uint32_t slot = base + laneId();
 		body(w.rayBase + slot, slot < n);
 	}
-#else
-	const float2* hits = w.q.hits + w.rayBase;
-	const F4* rays = w.q.rays[w.wave & 1] + 2 * size_t(w.rayBase);
-	const unsigned lane = laneId();
-	uint32_t cur = wfGrab32(counter);
-	if (cur >= n) return;
-	uint32_t nxt = wfGrab32(counter), nn = wfGrab32(counter);
-	// leaf triangle of this lane's slot in the next fetch / the fetch after next (-1: miss or beyond the end)
-	int triNext = (nxt + lane < n) ? f2i(hits[nxt + lane].y) : -1;
-	int triAfter = (nn + lane < n) ? f2i(hits[nn + lane].y) : -1;
-	for (;;)
-	{
-		uint32_t n3 = 0;
-		if (lane == 0) n3 = atomicAdd(counter, 32u);   // consumed after the body
-		if (nxt + lane < n) wfPrefetchL2(rays + 2 * size_t(nxt + lane));
-#if WF_SHADE_PREFETCH >= 2
-		if (triNext >= 0)
-		{
-			const F4* lp = w.f.scene.leafPos + 3 * size_t(triNext);
-			wfPrefetchL1(lp); wfPrefetchL1(lp + 2);
-			wfPrefetchL1(w.f.scene.leafTris + triNext);
-		}
-#endif
-		body(w.rayBase + cur + lane, cur + lane < n);
-		if (nxt >= n) break;
-		n3 = __shfl_sync(0xffffffffu, n3, 0);
-		cur = nxt; nxt = nn; nn = n3;
-		triNext = triAfter;
-		triAfter = (nn + lane < n) ? f2i(hits[nn + lane].y) : -1;
-	}
-#endif
 }
 
 // shade(w) of the path tracer: one lane per hit record, 32 consecutive queue slots per warp and fetch.

@@ -186,11 +186,8 @@ GI_D void wfSplat(float* accum, int width, int height, uint32_t pixel, F3 v)
 }
 
 // An unoccluded shadow ray delivers what it carries: s1 = (direction, target word), v = (value, splat ring slot) of shadow record `slot`.
-// REDUCE: the path's radiance sum is updated with a reduction instead of a read-modify-write (the same single round-to-nearest addition --
-// nobody else touches the record during trace(w); red.add.f32 flushes subnormals, which a radiance sum never holds), so that the lane does
-// not wait for the old value.
-template <bool REDUCE, class CNT>
-GI_D void wfDeliverShadowImpl(const WfTraceIO& io, uint32_t slot, F4 s1, F4 v, CNT& cnt)
+template <class CNT>
+GI_D void wfDeliverShadow(const WfTraceIO& io, uint32_t slot, F4 s1, F4 v, CNT& cnt)
 {
 	const uint32_t word = uint32_t(f2i(s1.w));
 	const uint32_t id = word & WF_ID_MASK;
@@ -211,21 +208,10 @@ GI_D void wfDeliverShadowImpl(const WfTraceIO& io, uint32_t slot, F4 s1, F4 v, C
 		return;
 	}
 	// the path's radiance sum: one shadow ray per path and wave, and shade() is another kernel -> exclusive
-	if (REDUCE)
-	{
-		float* c = reinterpret_cast<float*>(io.stateC + id);
-		asm volatile("red.global.add.f32 [%0], %1;" :: "l"(c), "f"(v.x) : "memory");
-		asm volatile("red.global.add.f32 [%0], %1;" :: "l"(c + 1), "f"(v.y) : "memory");
-		asm volatile("red.global.add.f32 [%0], %1;" :: "l"(c + 2), "f"(v.z) : "memory");
-		return;
-	}
 	float4 c = qld4(io.stateC + id);
 	c.x += v.x; c.y += v.y; c.z += v.z;
 	qst4(io.stateC + id, c);
 }
-
-template <class CNT>
-GI_D void wfDeliverShadow(const WfTraceIO& io, uint32_t slot, F4 s1, F4 v, CNT& cnt) { wfDeliverShadowImpl<true>(io, slot, s1, v, cnt); }
 
 template <class CNT>
 GI_D void wfFinishShadow(const WfTraceIO& io, uint32_t slot, bool occluded, CNT& cnt)
@@ -233,7 +219,7 @@ GI_D void wfFinishShadow(const WfTraceIO& io, uint32_t slot, bool occluded, CNT&
 	if (occluded) return;
 	const F4 s1 = qldF4(io.shadow + 3 * size_t(slot) + 1);
 	const F4 v = qldF4(io.shadow + 3 * size_t(slot) + 2);
-	wfDeliverShadowImpl<false>(io, slot, s1, v, cnt);
+	wfDeliverShadow(io, slot, s1, v, cnt);
 }
 
 // The persistent trace loop.  IO provides: total(), load(index, lane state), finish(lane state).
@@ -268,44 +254,12 @@ struct WfStackShared
 	}
 };
 
-// Build switch, measured on B200 (PT batch, ms/iteration, refill threshold 24/16/8/4): per-refill atomic + direct loads 2.130/2.162/2.181/2.251;
-// cp.async-prefetched per-warp batches of 32 rays 2.673/2.506/2.431/2.435, of 16 rays 2.877/2.476/2.454/2.435 -- the coarse batches cost more
-// in load balance at the end of every wave than the hidden latency saves.  Off.
-#ifndef WF_PREFETCH
-#define WF_PREFETCH 0
-#endif
 #ifndef WF_SHADE_HOIST
 #define WF_SHADE_HOIST 0  // k_wf_shade_pt: leaf record + triangle requested before the path state
 #endif
 #ifndef WF_BATCH_RETIRE
 #define WF_BATCH_RETIRE 1 // finished lanes are retired together when the refill is due (B200: 1.699 -> 1.680 ms per PT iteration)
 #endif
-#ifndef WF_PREFETCH_RAYS
-#define WF_PREFETCH_RAYS 32
-#endif
-
-GI_D void wfAsyncCopy16(void* sharedDst, const void* globalSrc)
-{
-	const unsigned d = unsigned(__cvta_generic_to_shared(sharedDst));
-	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(globalSrc) : "memory");
-}
-// all but the most recent group (= the prefetch of the batch after next) have landed
-GI_D void wfAsyncWaitCurrent() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
-
-// queue entries base .. base + WF_PREFETCH_RAYS - 1 -> dst (2 x F4 per ray), asynchronously
-template <class IO>
-GI_D void wfPrefetchBatch(const IO& io, F4* dst, uint32_t base, uint32_t total, unsigned lane)
-{
-	for (uint32_t i = lane; i < uint32_t(WF_PREFETCH_RAYS); i += 32u)
-		if (base + i < total)
-		{
-			const F4* src = io.address(base + i);
-			wfAsyncCopy16(dst + 2 * i, src);
-			wfAsyncCopy16(dst + 2 * i + 1, src + 1);
-		}
-	asm volatile("cp.async.commit_group;" ::: "memory");
-}
-
 template <class IO, class CNT>
 GI_D void wfTraceLoop(const DScene& s, const IO& io, uint32_t* workCounter, WfTune tune, CNT& cnt)
 {
@@ -324,22 +278,6 @@ GI_D void wfTraceLoop(const DScene& s, const IO& io, uint32_t* workCounter, WfTu
 	bool poolEmpty = false;
 	const uint32_t total = io.total();
 	const unsigned lane = laneId();
-#if WF_PREFETCH
-	// Work distribution: every warp owns two batches of WF_PREFETCH_RAYS consecutive queue entries, copied to shared memory with
-	// cp.async long before a lane needs them (one atomicAdd per batch).
-	__shared__ F4 wfPrefetchBuf[WF_TRACE_THREADS / 32][2 * 2 * WF_PREFETCH_RAYS];
-	F4* pre = wfPrefetchBuf[threadIdx.x >> 5];
-	uint32_t cur = 0u, curBase, curUsed = 0u, nextBase;
-	{
-		uint32_t b = 0;
-		if (lane == 0) b = atomicAdd(workCounter, uint32_t(2 * WF_PREFETCH_RAYS));
-		b = __shfl_sync(0xffffffffu, b, 0);
-		curBase = b; nextBase = b + uint32_t(WF_PREFETCH_RAYS);
-		wfPrefetchBatch(io, pre, curBase, total, lane);
-		wfPrefetchBatch(io, pre + 2 * WF_PREFETCH_RAYS, nextBase, total, lane);
-		if (curBase >= total) poolEmpty = true;
-	}
-#endif
 	for (;;)
 	{
 		// ---- retire finished rays
@@ -365,35 +303,6 @@ GI_D void wfTraceLoop(const DScene& s, const IO& io, uint32_t* workCounter, WfTu
 #endif
 		// ---- refill idle lanes from the queue
 		const unsigned idle = __ballot_sync(0xffffffffu, !active);
-#if WF_PREFETCH
-		if (!poolEmpty && (__popc(idle) >= tune.refillThreshold || idle == 0xffffffffu))
-		{
-			// rays come from the warp's prefetched batch in shared memory: no atomic and no DRAM round trip on this path
-			wfAsyncWaitCurrent();
-			__syncwarp();
-			const uint32_t take = min(uint32_t(__popc(idle)), uint32_t(WF_PREFETCH_RAYS) - curUsed);
-			const uint32_t rank = uint32_t(__popc(idle & lanemaskLt()));
-			const uint32_t mine = curBase + curUsed + rank;
-			if (!active && rank < take && mine < total)
-			{
-				const F4* b = pre + cur * (2 * WF_PREFETCH_RAYS) + 2 * (curUsed + rank);
-				io.begin(s, mine, b[0], b[1], L, cnt);
-				active = true;
-			}
-			curUsed += take;
-			if (curUsed == uint32_t(WF_PREFETCH_RAYS))
-			{
-				// the batch is used up: continue with the other buffer and prefetch a new batch into this one
-				__syncwarp();
-				uint32_t nb = 0;
-				if (lane == 0) nb = atomicAdd(workCounter, uint32_t(WF_PREFETCH_RAYS));
-				nb = __shfl_sync(0xffffffffu, nb, 0);
-				wfPrefetchBatch(io, pre + cur * (2 * WF_PREFETCH_RAYS), nb, total, lane);
-				cur ^= 1u; curBase = nextBase; curUsed = 0u; nextBase = nb;
-			}
-			if (curBase + curUsed >= total) poolEmpty = true;
-		}
-#else
 		if (!poolEmpty && (__popc(idle) >= tune.refillThreshold || idle == 0xffffffffu))
 		{
 			const int n = __popc(idle);
@@ -409,7 +318,6 @@ GI_D void wfTraceLoop(const DScene& s, const IO& io, uint32_t* workCounter, WfTu
 			}
 			if (base + uint32_t(n) >= total) poolEmpty = true;
 		}
-#endif
 		const unsigned activeMask = __ballot_sync(0xffffffffu, active);
 		if (activeMask == 0u)
 		{
@@ -427,139 +335,6 @@ GI_D void wfTraceLoop(const DScene& s, const IO& io, uint32_t* workCounter, WfTu
 #else
 		const int keepGoing = max(1, (__popc(activeMask) * tune.minInner) >> 5);
 #endif
-		do
-		{
-			if (L.node >= 0) wfInnerStep(L, s, stack, cnt);
-			innerMask = __ballot_sync(0xffffffffu, L.node >= 0);
-		} while (__popc(innerMask) >= keepGoing);
-	}
-}
-
-// ---- the same loop with the latencies of retire and refill taken off the warp's critical path (WF_PIPELINED_REFILL)
-// A warp of the loop above stalls as a whole on every refill (work-counter atomic -> ray load from HBM -> root test: three dependent
-// round trips, ~3 us) and on every retired shadow ray (shadow record -> path state read-modify-write).  That is why it refills late
-// (24 idle lanes) and runs at ~20 of 32 lanes.  Here every one of those steps is issued in one outer iteration and consumed in the
-// next, with the data parked in shared memory by cp.async (no registers are held across the traversal steps in between):
-//   refill   S0 the leader's atomicAdd on the work counter is issued, its result is left in the register
-//            S1 (next iteration) the result is broadcast, every reserved lane starts the asynchronous copy of its ray into its staging slot
-//            S2 (next iteration) the rays are read from shared memory and begun
-//   retire   a finished shadow ray that reached its light copies (target word, value) of its record into a second staging slot; the
-//            lane is free at once; one iteration later the value joins the path's radiance sum with a fire-and-forget reduction
-//            (exclusive: one shadow ray per path and wave, and shade() is another kernel -- the same single IEEE addition as before)
-// Measured on B200 (C2 PT batch, ms per iteration, k_wf_trace alone in brackets; refill threshold 24 / 16 / 12 / 8 / 6):
-//   this loop      1.996 (1.630) / 2.160 / 2.247 / 2.372 / 2.428        the loop above   1.689 (1.323) / - / 1.749 (1.384) / - / -
-// Slower at every threshold: the reserved lanes sit idle for two more outer iterations, and what a lower threshold costs is not latency but
-// INSTRUCTIONS -- ncu of the loop above at thresholds 24 / 12 / 6: 955 / 974 / 1016 M warp instructions for the same 17.1 G thread
-// instructions (17.96 / 17.50 / 16.87 lanes per instruction): ~250 instructions of retire + per-ray setup per refill event, run at few lanes,
-// outweigh the fuller traversal steps.  Off; kept as the record of the experiment (profiles/r02_refill_experiment.md).
-#ifndef WF_PIPELINED_REFILL
-#define WF_PIPELINED_REFILL 0
-#endif
-
-GI_D void wfAsyncWaitAll() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-GI_D void wfAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-
-template <class IO, class CNT>
-GI_D void wfTraceLoopPipelined(const DScene& s, const IO& io, uint32_t* workCounter, WfTune tune, CNT& cnt)
-{
-	StackEntry entries[GI_STACK_SIZE];
-	WfStackArray stack; stack.e = entries;
-	WfCand cand[WF_MAX_CAND];
-	__shared__ F4 wfRefillA[WF_TRACE_THREADS], wfRefillB[WF_TRACE_THREADS];   // staged ray: first two F4 of the work item
-	__shared__ F4 wfFinishA[WF_TRACE_THREADS], wfFinishB[WF_TRACE_THREADS];   // staged tail of a finished work item
-	__shared__ uint32_t wfFinishIndex[WF_TRACE_THREADS];
-	WfLane L;
-	L.node = WF_NODE_DONE;
-	bool active = false;
-	bool poolEmpty = false;
-	bool finishPending = false;
-	const uint32_t total = io.total();
-	const unsigned lane = laneId();
-	// refill request in flight (warp-uniform): 0 none, 1 atomic issued, 2 ray copies issued
-	int reqStage = 0, reqLeader = 0;
-	unsigned reqMask = 0u;
-	uint32_t reqBase = 0u;     // the leader's atomic result (only consumed one iteration after it was issued)
-	uint32_t reqIndex = 0u;    // this lane's work item of the request
-	for (;;)
-	{
-		// ---- deferred tail of the work items finished in the previous iteration
-		if (__any_sync(0xffffffffu, finishPending))
-		{
-			if (finishPending)
-			{
-				wfAsyncWaitAll();
-				io.finishStaged(s, wfFinishIndex[threadIdx.x], wfFinishA[threadIdx.x], wfFinishB[threadIdx.x], cnt);
-				finishPending = false;
-			}
-		}
-		// ---- S2: the staged rays start
-		if (reqStage == 2)
-		{
-			if ((reqMask >> lane) & 1u)
-			{
-				wfAsyncWaitAll();
-				io.begin(s, reqIndex, wfRefillA[threadIdx.x], wfRefillB[threadIdx.x], L, cnt);
-				active = true;
-			}
-			reqStage = 0;
-		}
-		// ---- S1: the work counter's answer is there: start the copies
-		if (reqStage == 1)
-		{
-			const uint32_t base = __shfl_sync(0xffffffffu, reqBase, reqLeader);
-			const uint32_t n = uint32_t(__popc(reqMask));
-			reqIndex = base + uint32_t(__popc(reqMask & lanemaskLt()));
-			const bool mine = ((reqMask >> lane) & 1u) && reqIndex < total;
-			if (mine)
-			{
-				const F4* src = io.address(reqIndex);
-				wfAsyncCopy16(&wfRefillA[threadIdx.x], src);
-				wfAsyncCopy16(&wfRefillB[threadIdx.x], src + 1);
-			}
-			wfAsyncCommit();
-			reqMask = __ballot_sync(0xffffffffu, mine);
-			if (base + n >= total) poolEmpty = true;
-			reqStage = reqMask ? 2 : 0;
-		}
-		// ---- retire finished rays (together, when a refill is due or nothing else is left to do)
-		{
-			const bool finished = active && wfFinished(L);
-			const unsigned waiting = __ballot_sync(0xffffffffu, finished || !active);
-			if ((poolEmpty || __popc(waiting) >= tune.refillThreshold || waiting == 0xffffffffu) && finished && wfEndOfWalk(L, s, cand, cnt))
-			{
-				const F4* tail = io.finishNow(s, L, cnt);
-				if (tail)
-				{
-					wfAsyncCopy16(&wfFinishA[threadIdx.x], tail);
-					wfAsyncCopy16(&wfFinishB[threadIdx.x], tail + 1);
-					wfAsyncCommit();
-					wfFinishIndex[threadIdx.x] = L.index;
-					finishPending = true;
-				}
-				active = false;
-			}
-		}
-		// ---- S0: reserve work for the idle lanes
-		const unsigned idle = __ballot_sync(0xffffffffu, !active);
-		if (reqStage == 0 && !poolEmpty && (__popc(idle) >= tune.refillThreshold || idle == 0xffffffffu))
-		{
-			reqLeader = __ffs(idle) - 1;
-			reqMask = idle;
-			if (int(lane) == reqLeader) reqBase = atomicAdd(workCounter, uint32_t(__popc(idle)));
-			reqStage = 1;
-		}
-		if (idle == 0xffffffffu)
-		{
-			if (poolEmpty && reqStage == 0 && !__any_sync(0xffffffffu, finishPending)) break;
-			continue;
-		}
-		// ---- one leaf step for the lanes waiting at a leaf
-		if (active) wfStash(L, stack);
-		if (active && wfAtLeaf(L)) wfLeafStep(L, s, stack, cand, cnt);
-		// ---- inner-node steps while enough lanes are at inner nodes
-		unsigned innerMask = __ballot_sync(0xffffffffu, L.node >= 0);
-		if (innerMask == 0u) continue;
-		const int keepGoing = max(1, (__popc(__ballot_sync(0xffffffffu, active && !wfFinished(L))) * tune.minInner) >> 5); // lanes still walking
 		do
 		{
 			if (L.node >= 0) wfInnerStep(L, s, stack, cnt);
@@ -632,20 +407,6 @@ struct WfQueueIO
 		if (L.flags & WFL_ANY) wfFinishShadow(q, L.index - q.numClosest, (L.flags & WFL_OCCLUDED) != 0u, cnt);
 		else qst2(q.hits + q.rayBase + L.index, make_float2(L.best, i2f(L.hitLeaf)));
 	}
-	// WF_PIPELINED_REFILL: the part of finish() that needs no load; returns the two consecutive F4 the deferred part wants staged (or nullptr)
-	template <class CNT>
-	GI_D const F4* finishNow(const DScene& s, WfLane& L, CNT& cnt) const
-	{
-		if (L.flags & WFL_ANY) return (L.flags & WFL_OCCLUDED) ? nullptr : q.shadow + 3 * size_t(L.index - q.numClosest) + 1;
-		qst2(q.hits + q.rayBase + L.index, make_float2(L.best, i2f(L.hitLeaf)));
-		return nullptr;
-	}
-	// ... and the deferred part: an unoccluded shadow ray delivers its value (s1 = (direction, target word), v = (value, splat slot))
-	template <class CNT>
-	GI_D void finishStaged(const DScene& s, uint32_t index, F4 s1, F4 v, CNT& cnt) const
-	{
-		wfDeliverShadow(q, index - q.numClosest, s1, v, cnt);
-	}
 };
 
 // gi_trace_device: GiRay batch in, GiHit out (the parity / Mrays/s entry point).
@@ -686,10 +447,6 @@ struct WfBatchIO
 		}
 		hits[L.index] = out;
 	}
-	template <class CNT>
-	GI_D const F4* finishNow(const DScene& s, WfLane& L, CNT& cnt) const { finish(s, L, cnt); return nullptr; }
-	template <class CNT>
-	GI_D void finishStaged(const DScene&, uint32_t, F4, F4, CNT&) const {}
 };
 
 // ------------------------------------------------------------------ path tracer waves (pathtracer.comp:16-110)
