@@ -199,3 +199,44 @@ def test_cuda_pathtracer_vs_reference_glsl(g, orc, scenes):
     relmse = float((((x - r) ** 2) / (r ** 2 + 1e-2)).sum(axis=2).mean())
     off = float((np.abs(x - r) / (np.abs(r) + 1e-3)).max(axis=2).__gt__(1e-2).mean())
     assert relmse <= 1e-3 and off < 0.02, (relmse, off)
+
+
+@live
+@pytest.mark.gpu
+def test_cuda_bidirectional_and_lighttracer_vs_reference_glsl(g, orc, scenes, box1):
+    """The CUDA light tracer against lighttracer.comp + showlightcaches.comp, and one CUDA BPT iteration against the reference's two BPT shaders run
+    on the GPU's own light cache (the slot order of the cache is scheduling dependent; everything else is a deterministic function of it)."""
+    from tests.conftest import pixel_mismatch_fraction
+    from tests.test_gpu_configs import _bpt_iteration_vs_oracle_on_the_same_cache, _device
+    W = H = 96
+    C = scenes.BOX1_CAMERA
+    camp = np.frombuffer(g.camera_params(C["pos"], C["lookat"], C["fov"], W, H), dtype=np.float32)
+    # BPT
+    img, _, cache, entries = _bpt_iteration_vs_oracle_on_the_same_cache(g, orc, box1, C, W, H, 3)
+    nls = 128
+    nr = max(64, (W * H // nls // 64) * 64)
+    samples = g.LightSampler(box1).generate(nls)   # (the helper draws the same first set from a fresh sampler)
+    seed = g.wang_hash(3)
+    cap = cache.shape[0]
+    lts, eye = ref_glsl.LightTracer(save=True), ref_glsl.BidirEyePass()
+    lts.set_scene(box1); eye.set_scene(box1)
+    want, _, n_ref, _ = lts.render(camp, W, H, samples, seed, nr, capacity=cap)
+    assert n_ref == entries
+    eye.render(camp, W, H, samples, seed, nr, cache, cap, entries, accum=want)
+    assert pixel_mismatch_fraction(img, want, 1e-2) < 0.02
+    assert abs(float(img[..., :3].sum()) - float(want[..., :3].sum())) <= 2e-3 * float(want[..., :3].sum())
+    # LPT
+    dev = _device(g, box1, W, H, C)
+    try:
+        dev.set_light_samples(samples)
+        dev.render_iteration(g.GI_RENDERER_LPT, seed, 16, num_rays_per_light_sample=nr)
+        dev.show_light_caches()
+        got = dev.read_accumulator(W, H)
+    finally:
+        dev.close()
+    lt, show = ref_glsl.LightTracer(), ref_glsl.ShowLightCaches()
+    lt.set_scene(box1); show.set_scene(box1)
+    want = show.render(camp, W, H, samples, lt.render(camp, W, H, samples, seed, nr))
+    x, r = got[..., :3].astype(np.float64), want[..., :3].astype(np.float64)
+    assert float((((x - r) ** 2) / (r ** 2 + 1e-2)).sum(axis=2).mean()) <= 1e-2   # (splats: a flipped decision moves a whole contribution to another pixel)
+    assert abs(x.sum() - r.sum()) <= 2e-3 * r.sum()
