@@ -18,5 +18,6 @@ $NCU -k regex:k_wf_shade_light -s 24 -o $O/${TAG}_ncu_c3_shade_light python tool
 $NCU -k regex:k_wf_generate_light -s 24 -o $O/${TAG}_ncu_c3_generate_light python tools/gpu/prof_batch.py --config C3 --iters 44 > $O/${TAG}_ncu_c3_generate_light.log 2>&1
 $NCU -k regex:k_wf_trace -s 70 -o $O/${TAG}_ncu_c3_trace python tools/gpu/prof_batch.py --config C3 --iters 44 > $O/${TAG}_ncu_c3_trace.log 2>&1
 $NCU -k regex:k_wf_shade_light -s 20 -o $O/${TAG}_ncu_c4_shade_light python tools/gpu/prof_batch.py --config C4 --iters 26 > $O/${TAG}_ncu_c4_shade_light.log 2>&1
+$NCU -k regex:k_wf_trace -s 20 -o $O/${TAG}_ncu_c4_trace python tools/gpu/prof_batch.py --config C4 --iters 26 > $O/${TAG}_ncu_c4_trace.log 2>&1
 $NCU -k regex:k_wf_generate_light -s 20 -o $O/${TAG}_ncu_c4_generate_light python tools/gpu/prof_batch.py --config C4 --iters 26 > $O/${TAG}_ncu_c4_generate_light.log 2>&1
 $NCU -k regex:k_wf_trace -s 20 -o $O/${TAG}_ncu_c5_trace python tools/gpu/prof_batch.py --config C5 --iters 26 > $O/${TAG}_ncu_c5_trace.log 2>&1

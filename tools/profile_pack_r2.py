@@ -28,7 +28,7 @@ def main():
         "c2": ("steady-state k_wf_trace / k_wf_shade_pt waves of C2 (prof_batch.py --config C2 --iters 26, launch 20 of each kernel)", ["c2_trace", "c2_shade"]),
         "c3": ("steady-state BPT waves of C3 (prof_batch.py --config C3 --iters 44: shade / generate kernels launch 24, k_wf_trace launch 70)",
                ["c3_trace", "c3_shade_eye", "c3_shade_light", "c3_generate_light"]),
-        "c4": ("steady-state LPT waves of C4 (prof_batch.py --config C4 --iters 26, launch 20)", ["c4_shade_light", "c4_generate_light"]),
+        "c4": ("steady-state LPT waves of C4 (prof_batch.py --config C4 --iters 26, launch 20)", ["c4_trace", "c4_shade_light", "c4_generate_light"]),
         "c5": ("steady-state k_wf_trace wave of C5 (prof_batch.py --config C5 --iters 26, launch 20)", ["c5_trace"]),
     }
     for c, (what, reps) in sets.items():
