@@ -181,8 +181,7 @@ struct WfTraceIO
 
 GI_D void wfSplat(float* accum, int width, int height, uint32_t pixel, F3 v)
 {
-	float* p = accum + 4 * size_t(pixel);
-	atomicAdd(reinterpret_cast<float4*>(p), make_float4(v.x, v.y, v.z, 0.0f));
+	splatReduce(accum + 4 * size_t(pixel), v);
 }
 
 // An unoccluded shadow ray delivers what it carries: s1 = (direction, target word), v = (value, splat ring slot) of shadow record `slot`.
