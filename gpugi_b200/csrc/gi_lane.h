@@ -77,6 +77,10 @@ struct WfCounters
 #if WF_CENTRE_EXTENT && !(WF_WIDE4 && WF_CACHE_INV)
 #error "WF_CENTRE_EXTENT needs WF_WIDE4 and WF_CACHE_INV"
 #endif
+#ifndef WF_ANY_UNSORTED
+#define WF_ANY_UNSORTED 1  // inner-node steps of a warp whose walking lanes are all any-hit rays (the queue hands out the closest-hit rays first, then the shadow
+#endif                     // rays: 40-45 % of all rays) skip the sorting network -- the answer of an any-hit ray does not depend on the visit order -- and push
+                           // without entry distances.  B200 A/B (ms per iteration, sorted -> unsorted): C2 1.659 -> 1.642, C3 7.423 -> 7.243, C4 6.335 -> 6.290, C5 14.53 -> 14.28
 #define WF_MAX_CAND 8
 
 enum { WFL_ANY = 1u, WFL_OVERFLOW = 2u, WFL_OCCLUDED = 4u, WFL_EXACT = 8u, WFL_COLLECT = 16u, WFL_GUARD = 32u };
@@ -439,6 +443,31 @@ GI_HD void wfInnerStep(WfLane& L, const DScene& s, const STK& stack, CNT& cnt)
 	wfStash(L, stack);
 }
 
+
+// WF_ANY_UNSORTED: the same step for an any-hit ray when the order of the visits is nobody's business: no sorting network, the first accepted
+// child (in slot order) is next, the others are pushed without an entry distance (0 passes every cull; an any-hit ray's limit never shrinks)
+template <class STK, class CNT>
+GI_HD void wfInnerStepAny(WfLane& L, const DScene& s, const STK& stack, CNT& cnt)
+{
+	const uint32_t* nb = s.qNodes + 24 * size_t(L.node);
+	const U8 a = ld8(nb), b = ld8(nb + 8), c = ld8(nb + 16);
+	cnt.template add<WFC_NODES>(4u); cnt.template add<WFC_INNER_STEPS>(1u);
+	float n0, n1, n2, n3, r0, r1, r2, r3;
+	wfCentreTest(L, i2f(int(a.v[0])), i2f(int(a.v[1])), i2f(int(a.v[2])), wfHalfExtent(b.v[4], 0), wfHalfExtent(b.v[5], 0), wfHalfExtent(b.v[6], 0), n0, r0);
+	wfCentreTest(L, i2f(int(a.v[3])), i2f(int(a.v[4])), i2f(int(a.v[5])), wfHalfExtent(b.v[4], 1), wfHalfExtent(b.v[5], 1), wfHalfExtent(b.v[6], 1), n1, r1);
+	wfCentreTest(L, i2f(int(a.v[6])), i2f(int(a.v[7])), i2f(int(b.v[0])), wfHalfExtent(b.v[7], 2), wfHalfExtent(c.v[0], 2), wfHalfExtent(c.v[1], 2), n2, r2);
+	wfCentreTest(L, i2f(int(b.v[1])), i2f(int(b.v[2])), i2f(int(b.v[3])), wfHalfExtent(b.v[7], 3), wfHalfExtent(c.v[0], 3), wfHalfExtent(c.v[1], 3), n3, r3);
+	const bool p0 = n0 <= r0, p1 = n1 <= r1, p2 = n2 <= r2, p3 = n3 <= r3;
+	const int c0 = int(c.v[4]), c1 = int(c.v[5]), c2 = int(c.v[6]), c3 = int(c.v[7]);
+	if (p0 || p1 || p2 || p3)
+	{
+		if (p3 && (p0 || p1 || p2)) wfPush(L, stack, c3, 0.0f);
+		if (p2 && (p0 || p1)) wfPush(L, stack, c2, 0.0f);
+		if (p1 && p0) wfPush(L, stack, c1, 0.0f);
+		L.node = p0 ? c0 : (p1 ? c1 : (p2 ? c2 : c3));
+	}
+	else wfPop(L, stack);
+}
 #elif WF_WIDE4
 GI_HD bool wfSlabTestChild(const WfLane& L, const uint32_t* node, int child, float& nearLow) { return wfSlabTest(L, node[3 * child], node[3 * child + 1], node[3 * child + 2], nearLow); }
 
@@ -708,6 +737,9 @@ GI_HD void wfWalkSingle(WfLane& L, const DScene& s, F3 o, F3 d, float tMax, bool
 		else wfLeafStep(L, s, stack, cand, cnt);
 #else
 		if (L.node < 0) wfLeafStep(L, s, stack, cand, cnt);
+#if WF_ANY_UNSORTED && WF_CENTRE_EXTENT
+		else if (L.flags & WFL_ANY) wfInnerStepAny(L, s, stack, cnt);
+#endif
 		else wfInnerStep(L, s, stack, cnt);
 #endif
 	}

@@ -334,6 +334,19 @@ GI_D void wfTraceLoop(const DScene& s, const IO& io, uint32_t* workCounter, WfTu
 #else
 		const int keepGoing = max(1, (__popc(activeMask) * tune.minInner) >> 5);
 #endif
+#if WF_ANY_UNSORTED && WF_CENTRE_EXTENT
+		// every walking lane of the warp carries an any-hit ray (the queue hands out closest-hit rays first, then the shadow rays): unsorted steps
+		const bool walkingLane = active && !wfFinished(L);
+		if (__all_sync(0xffffffffu, !walkingLane || (L.flags & WFL_ANY) != 0u))
+		{
+			do
+			{
+				if (L.node >= 0) wfInnerStepAny(L, s, stack, cnt);
+				innerMask = __ballot_sync(0xffffffffu, L.node >= 0);
+			} while (__popc(innerMask) >= keepGoing);
+			continue;
+		}
+#endif
 		do
 		{
 			if (L.node >= 0) wfInnerStep(L, s, stack, cnt);
