@@ -105,6 +105,35 @@ def test_oracle_shader_variants_equal_reference_glsl_golden(g, orc, scenes, gold
         orc.set_variant(reconstruction_filter=0, chained_mis=False)
 
 
+def test_product_device_logic_equals_reference_glsl_golden(g, emul, scenes, gold):
+    """The PRODUCT's device code (gi_core.h / gi_lane.h / gi_shade.h compiled for the host, tests/emul) against the shader-source goldens directly, no oracle in
+    between: the lane walk of the trace kernel (hit records), the path tracer, the light tracer + showlightcaches, the Whitted tracer and the bidirectional
+    path tracer incl. its light cache -- one thread, bit for bit."""
+    from tests.golden.make_golden_glsl import scenes_for_goldens
+    os.environ["OMP_NUM_THREADS"] = "1"
+    for name, sc in scenes_for_goldens(scenes).items():
+        rays, want = gold[name + "_rays"], gold[name + "_hits"]
+        for mode in (0, 2):   # ordered walk of the one-thread-per-path kernels, lane state machine of k_wf_trace
+            got, _ = emul.trace(sc.desc, rays, mode=mode)
+            assert_same_hits(got, want, rays, "%s mode %d" % (name, mode))
+    sc = scenes.make_box1(tess=4)
+    W = H = 64
+    cam, s, seed, nr, cap = gold["pt_cam"], gold["x_samples"], int(gold["x_seed"]), int(gold["x_nr"]), int(gold["x_capacity"])
+    acc = np.zeros((H, W, 4), dtype=np.float32)
+    for k in range(3):
+        emul.render(sc.desc, cam, W, H, gold["pt_samples"][k], 0, int(gold["pt_seeds"][k]), 16, accum=acc)
+    assert np.array_equal(acc.view(np.uint32), gold["pt_box1_64"].view(np.uint32)), "PT"
+    img, _ = emul.render(sc.desc, cam, W, H, s, 3, seed, 16, mode=1)
+    assert np.array_equal(img.view(np.uint32), gold["whitted_box1_64"].view(np.uint32)), "Whitted"
+    img, _ = emul.render(sc.desc, cam, W, H, s, 1, seed, 16, num_rays_per_light_sample=nr, show_light_caches=True)
+    assert np.array_equal(img.view(np.uint32), gold["lpt_box1_64"].view(np.uint32)), "LPT"
+    cache = np.zeros(cap * 16, dtype=np.float32)
+    img, cnt = emul.render(sc.desc, cam, W, H, s, 2, seed, 16, num_rays_per_light_sample=nr, capacity=cap, cache=cache)
+    n = int(gold["bpt_entries"])
+    assert cnt["light_cache_entries"] == n and np.array_equal(cache.reshape(-1, 16)[:n].view(np.uint32), gold["bpt_cache"].view(np.uint32)), "light cache"
+    assert np.array_equal(img.view(np.uint32), gold["bpt_box1_64"].view(np.uint32)), "BPT"
+
+
 @live
 def test_oracle_other_renderers_equal_reference_glsl_live(g, orc, scenes, sponza_small, one_thread):
     """Fresh seeds, another resolution, the textured scene with its point lights (omnidirectional light samples), a light cache that overflows."""
