@@ -9,6 +9,7 @@
 #include <cstdint>
 #include <cstring>
 #include <fstream>
+#include <new>
 
 namespace gi {
 namespace {
@@ -32,6 +33,13 @@ struct Reader
 	uint32_t be16() { uint32_t a = get8(); return (a << 8) | get8(); }
 	uint32_t be32() { uint32_t a = be16(); return (a << 16) | be16(); }
 };
+
+// stb_image's own limits (STBI_MAX_DIMENSIONS, stbi__mad3sizes_valid): either side <= 2^24 and width * height * 4 must fit an int;
+// a corrupt header cannot ask for more than 2 GB
+bool sizeOk(long long w, long long h)
+{
+	return w > 0 && h > 0 && w <= (1 << 24) && h <= (1 << 24) && w * h * 4 <= 0x7fffffffLL;
+}
 
 // ------------------------------------------------------------------------------------------------ PNG
 int paeth(int a, int b, int c)
@@ -92,7 +100,7 @@ bool decodePng(Reader r, int& W, int& H, std::vector<u8>& rgba, const Fail& fail
 			Reader q{d, len, 0};
 			W = int(q.be32()); H = int(q.be32()); depth = int(q.get8()); colorType = int(q.get8());
 			const int comp = int(q.get8()), flt = int(q.get8()); interlace = int(q.get8());
-			if (W <= 0 || H <= 0 || W > (1 << 24) || H > (1 << 24) || comp || flt || interlace > 1) return fail("PNG: unsupported header");
+			if (!sizeOk(W, H) || comp || flt || interlace > 1) return fail("PNG: unsupported header");
 			haveHeader = true;
 		}
 		else if (type == 0x504c5445u) palette.assign(d, d + len);  // PLTE
@@ -114,6 +122,8 @@ bool decodePng(Reader r, int& W, int& H, std::vector<u8>& rgba, const Fail& fail
 		size_t cap = 0;
 		if (!interlace) cap = ((size_t(W) * bitsPerPixel + 7) / 8 + 1) * size_t(H);
 		else cap = ((size_t(W) * bitsPerPixel + 7) / 8 + 8) * size_t(H) + 64 * 7;
+		// deflate expands at most 1032 : 1 -- a header that claims more than the IDAT bytes can hold is corrupt (no allocation for it)
+		if (!interlace && cap / 1032 > idat.size() + 16) return fail("PNG: truncated image data");
 		raw.resize(cap + 64);
 		z_stream zs;
 		std::memset(&zs, 0, sizeof(zs));
@@ -260,7 +270,7 @@ bool decodeBmp(Reader r, int& W, int& H, std::vector<u8>& rgba, const Fail& fail
 	else return fail("BMP: unknown header size");
 	const bool flip = h > 0;
 	h = std::abs(h);
-	if (w <= 0 || h <= 0 || w > (1 << 24) || h > (1 << 24)) return fail("BMP: bad size");
+	if (!sizeOk(w, h)) return fail("BMP: bad size");
 	W = w; H = h;
 	rgba.assign(size_t(w) * h * 4, 255);
 	std::vector<u8> pal;
@@ -317,7 +327,7 @@ bool decodeTga(Reader r, int& W, int& H, std::vector<u8>& rgba, const Fail& fail
 	const int bits = int(r.get8()), desc = int(r.get8());
 	const bool rle = type >= 8;
 	const int kind = int(type & 7); // 1 colour-mapped, 2 true colour, 3 grey
-	if (w <= 0 || h <= 0 || (kind != 1 && kind != 2 && kind != 3)) return fail("TGA: unsupported image type");
+	if (!sizeOk(w, h) || (kind != 1 && kind != 2 && kind != 3)) return fail("TGA: unsupported image type");
 	if (kind == 1 && (!mapType || (bits != 8 && bits != 16))) return fail("TGA: bad colour map image");
 	if (kind == 2 && bits != 15 && bits != 16 && bits != 24 && bits != 32) return fail("TGA: unsupported pixel depth");
 	if (kind == 3 && bits != 8 && bits != 16) return fail("TGA: unsupported grey depth");
@@ -577,7 +587,7 @@ struct JpegDecoder
 			{
 				if (s.get8() != 8) return fail("JPEG: only 8-bit samples are supported");
 				H = int(s.be16()); W = int(s.be16()); ncomp = int(s.get8());
-				if (W <= 0 || H <= 0 || (ncomp != 1 && ncomp != 3)) return fail("JPEG: unsupported frame");
+				if (!sizeOk(W, H) || (ncomp != 1 && ncomp != 3)) return fail("JPEG: unsupported frame");
 				for (int i = 0; i < ncomp; ++i)
 				{
 					comp[i].id = int(s.get8());
@@ -717,7 +727,7 @@ bool decodePnm(Reader r, int& W, int& H, std::vector<u8>& rgba, const Fail& fail
 	};
 	const int w = number(), h = number(), maxv = number();
 	++r.pos; // the single whitespace after maxval
-	if (w <= 0 || h <= 0 || maxv != 255) return fail("PNM: only 8-bit binary P5 / P6 files are supported");
+	if (!sizeOk(w, h) || maxv != 255) return fail("PNM: only 8-bit binary P5 / P6 files are supported");
 	const size_t need = size_t(w) * h * (colour ? 3 : 1);
 	if (!r.has(need)) return fail("PNM: truncated");
 	W = w; H = h;
@@ -731,13 +741,9 @@ bool decodePnm(Reader r, int& W, int& H, std::vector<u8>& rgba, const Fail& fail
 	return true;
 }
 
-} // namespace
-
-bool DecodeImageRGBA8(const unsigned char* data, size_t size, int& width, int& height, std::vector<unsigned char>& rgba, std::string* error)
+// format dispatch by signature
+bool decodeAny(const unsigned char* data, size_t size, Reader r, int& width, int& height, std::vector<unsigned char>& rgba, const Fail& fail)
 {
-	const Fail fail{error};
-	Reader r{data, size, 0};
-	if (size < 18) return fail("image file too short");
 	static const u8 pngSig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
 	if (!std::memcmp(data, pngSig, 8)) return decodePng(r, width, height, rgba, fail);
 	if (data[0] == 0xff && data[1] == 0xd8) { JpegDecoder d(r, fail); return d.decode(width, height, rgba); }
@@ -747,7 +753,7 @@ bool DecodeImageRGBA8(const unsigned char* data, size_t size, int& width, int& h
 	{
 		int32_t dims[2];
 		std::memcpy(dims, data + 4, 8);
-		if (dims[0] <= 0 || dims[1] <= 0 || size < 12 + size_t(dims[0]) * dims[1] * 4) return fail("GITX: truncated");
+		if (!sizeOk(dims[0], dims[1]) || size < 12 + size_t(dims[0]) * dims[1] * 4) return fail("GITX: truncated");
 		width = dims[0]; height = dims[1];
 		rgba.assign(data + 12, data + 12 + size_t(width) * height * 4);
 		return true;
@@ -759,6 +765,17 @@ bool DecodeImageRGBA8(const unsigned char* data, size_t size, int& width, int& h
 			return decodeTga(r, width, height, rgba, fail);
 	}
 	return fail("unknown image format");
+}
+
+} // namespace
+
+bool DecodeImageRGBA8(const unsigned char* data, size_t size, int& width, int& height, std::vector<unsigned char>& rgba, std::string* error)
+{
+	const Fail fail{error};
+	Reader r{data, size, 0};
+	if (size < 18) return fail("image file too short");
+	try { return decodeAny(data, size, r, width, height, rgba, fail); }
+	catch (const std::bad_alloc&) { return fail("out of memory while decoding"); }
 }
 
 bool LoadImageRGBA8(const std::string& file, int& width, int& height, std::vector<unsigned char>& rgba, std::string* error)

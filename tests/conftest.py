@@ -138,9 +138,38 @@ def assert_hits_equal(a, b, what=""):
     assert np.array_equal(a["bary_z"].view(np.uint32), b["bary_z"].view(np.uint32)), what + ": barycentric z differs"
 
 
+def _log_parity(kind, value, **extra):
+    """GPUGI_B200_PARITY_LOG=<file>: every measured parity statistic is appended as one JSON line (what the tolerances are set from)."""
+    path = os.environ.get("GPUGI_B200_PARITY_LOG")
+    if path:
+        import json
+        with open(path, "a") as f:
+            f.write(json.dumps(dict(test=os.environ.get("PYTEST_CURRENT_TEST", ""), kind=kind, value=value, **extra)) + "\n")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _parity_log_rel_mse():
+    """With GPUGI_B200_PARITY_LOG set, rel_mse values the tests compute are logged too."""
+    if not os.environ.get("GPUGI_B200_PARITY_LOG"):
+        yield
+        return
+    from gpugi_b200 import parallel
+    plain = parallel.rel_mse
+
+    def logged(*a, **k):
+        v = plain(*a, **k)
+        _log_parity("rel_mse", float(v))
+        return v
+    parallel.rel_mse = logged
+    yield
+    parallel.rel_mse = plain
+
+
 def pixel_mismatch_fraction(img, ref, rel_tol=1e-2):
     rel = np.abs(img[..., :3] - ref[..., :3]) / (np.abs(ref[..., :3]) + 1e-3)
-    return float((rel.max(axis=2) > rel_tol).mean())
+    value = float((rel.max(axis=2) > rel_tol).mean())
+    _log_parity("pixel_mismatch_fraction", value, rel_tol=rel_tol)
+    return value
 
 
 def robust_block_compare(a, b, block=8, clip=20.0):

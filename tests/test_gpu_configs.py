@@ -60,7 +60,7 @@ def test_bidirectional_eye_pass_on_the_gpu_cache_matches_oracle(g, orc, scenes, 
         img, ref, cache, entries = _bpt_iteration_vs_oracle_on_the_same_cache(g, orc, box1, scenes.BOX1_CAMERA, W, H, k, scheduler=sched)
         assert np.all(img[..., 3] == 1.0) and img[..., :3].sum() > 0
         bad = pixel_mismatch_fraction(img, ref, 1e-2)
-        assert bad < 0.02, "iteration %d: %.2f %% of the pixels differ by more than 1 %%" % (k, 100 * bad)
+        assert bad < 0.002, "iteration %d: %.2f %% of the pixels differ by more than 1 %%" % (k, 100 * bad)
         e_img, e_ref = float(img[..., :3].sum()), float(ref[..., :3].sum())
         assert abs(e_img - e_ref) <= 2e-3 * e_ref
 
@@ -105,7 +105,7 @@ def test_c3_stand_in_bidirectional_vs_oracle(g, orc, scenes, tmp_path):
     img, ref, cache, entries = _bpt_iteration_vs_oracle_on_the_same_cache(g, orc, sc, scenes.BATHROOM_CAMERA, W, H, 1)
     assert np.isfinite(img).all() and img[..., :3].mean() > 0
     bad = pixel_mismatch_fraction(img, ref, 1e-2)
-    assert bad < 0.03, "%.2f %% of the pixels differ by more than 1 %%" % (100 * bad)
+    assert bad < 0.003, "%.2f %% of the pixels differ by more than 1 %%" % (100 * bad)
     e_img, e_ref = float(img[..., :3].sum()), float(ref[..., :3].sum())
     assert abs(e_img - e_ref) <= 5e-3 * e_ref
 
@@ -137,7 +137,7 @@ def test_c4_stand_in_lighttracer_vs_oracle(g, orc, scenes, tmp_path):
     e_img, e_ref = float(img[..., :3].sum()), float(acc[..., :3].sum())
     print("LPT energy gpu %.6g oracle %.6g; negative pixels gpu %d oracle %d; min %.4g / %.4g" % (e_img, e_ref, (img[..., :3] < 0).sum(), (acc[..., :3] < 0).sum(), img.min(), acc.min()))
     assert e_ref != 0 and abs(e_img - e_ref) <= 5e-3 * abs(e_ref)
-    assert pixel_mismatch_fraction(img, acc, 1e-2) < 0.03
+    assert pixel_mismatch_fraction(img, acc, 1e-2) < 0.003
 
 
 def test_c1_box1_at_stated_size(g, orc, scenes):
@@ -161,8 +161,8 @@ def test_c1_box1_at_stated_size(g, orc, scenes):
     x, r = img[..., :3] / N, ref[..., :3] / N
     assert r.mean() > 0
     value = rel_mse(x, r)
-    assert value <= 1e-3, "relMSE %.3g of the 64-iteration image against the oracle" % value
-    assert pixel_mismatch_fraction(img, ref, 1e-2) < 0.01
+    assert value <= 1e-6, "relMSE %.3g of the 64-iteration image against the oracle" % value
+    assert pixel_mismatch_fraction(img, ref, 1e-2) < 0.001
 
 
 @pytest.fixture(scope="module")
@@ -189,10 +189,10 @@ def test_c2_one_iteration_at_1080p_on_64_stripes(g, orc, scenes, sponza_full):
         ref, _ = orc.render_pt(sponza_full.desc, cam, W, H, samples, seed, 16, region=(0, y, W, y + 8), accum=ref)
         rows[y:y + 8] = True
     assert rows.sum() == 512 and ref[rows][..., :3].mean() > 0
-    assert pixel_mismatch_fraction(img[rows], ref[rows], 1e-2) < 0.02
-    # one iteration: a pixel whose path takes another branch within rounding (< 2 % of them, above) contributes its whole value, so the
-    # relative MSE of a 1-spp image is dominated by those few; at 64 iterations it is 2e-4 (bench.py `relmse`)
-    assert rel_mse(img[rows][..., :3], ref[rows][..., :3]) <= 2e-2
+    assert pixel_mismatch_fraction(img[rows], ref[rows], 1e-2) < 0.005
+    # one iteration: a pixel whose path takes another branch within rounding (< 0.5 % of them, above; measured 0.08 %) contributes its whole value, so the
+    # relative MSE of a 1-spp image is dominated by those few; at 64 iterations it is 1.3e-5 (bench.py `relmse`); measured here 3.6e-5
+    assert rel_mse(img[rows][..., :3], ref[rows][..., :3]) <= 1e-3
 
 
 def test_ray_batch_2_22_on_the_full_size_scene(g, orc, scenes, sponza_full):

@@ -2,9 +2,12 @@
 through the Renderer API mirror (RendererSystem), against the CPU oracle on the same seeded inputs.
 
 Bar: bit-exact for hit flag / triangle id / distance / barycentrics; images: identical RNG streams and operation
-order, so a pixel only differs where CUDA's sinf/cosf/powf/atan2f (<= 2 ulp) or FMA contraction in the shading code
-flip a discrete decision -- tolerance: <= 2 % of the pixels off by more than 1 % at one iteration, and
-relMSE <= 0.02 against the oracle's image at 16 iterations (stated per test)."""
+order, and the device code is built without FMA contraction (gpugi_b200/Makefile, FMAD=false: every float operation is the one
+IEEE binary32 operation of the GLSL source, as in the oracle), so a pixel only differs where CUDA's sinf / cosf / powf / atan2f
+(<= 2 ulp against libm) flips a discrete decision -- tolerance, stated per test: <= 0.2 - 0.5 % of the pixels off by more than 1 %
+at one iteration (measured on B200: 0 on box1 and the stand-in scenes, 0.08 % on the 1080p Sponza-shaped scene; the contracted
+build had needed 2 - 3 %) and relMSE <= 1e-6 on box1 at 64 iterations (measured 2.5e-9).  profiles/r02_parity_stats_fmadoff.jsonl
+holds every measured statistic (GPUGI_B200_PARITY_LOG)."""
 import os
 
 import numpy as np
@@ -308,9 +311,9 @@ def test_obox_hierarchy_on_device(g, orc, scenes):
         imgs[bvh] = rs.ReadBackbuffer()
         if bvh == 1:
             ref_img, _ = orc.render_pt(box.desc, cam, W, H, samples, seed, 16)
-            assert pixel_mismatch_fraction(imgs[1], ref_img, 1e-2) < 0.02
+            assert pixel_mismatch_fraction(imgs[1], ref_img, 1e-2) < 0.002
         rs.close()
-    assert pixel_mismatch_fraction(imgs[1], imgs[0], 1e-2) < 0.01
+    assert pixel_mismatch_fraction(imgs[1], imgs[0], 1e-2) < 0.002
 
 
 @pytest.mark.parametrize("method", ["lbvh", "ploc"])

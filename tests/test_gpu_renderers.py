@@ -35,7 +35,7 @@ def test_pathtracer_one_iteration_matches_oracle(g, orc, scenes, box1):
     img = rs.ReadBackbuffer()
     ref, rc = orc.render_pt(box1.desc, cam, W, H, samples, seed, 16)
     bad = pixel_mismatch_fraction(img, ref, 1e-2)
-    assert bad < 0.02, "%.3f %% of the pixels differ by more than 1 %%" % (100 * bad)
+    assert bad < 0.002, "%.3f %% of the pixels differ by more than 1 %%" % (100 * bad)
     assert np.all(img[..., 3] == 0.0)  # PT adds w = 0 (pathtracer.comp:107)
     cnt = rs.device.counters()
     assert cnt["camera_paths"] == W * H
@@ -53,9 +53,9 @@ def test_pathtracer_golden_and_relmse(g, orc, scenes, box1):
     assert rs.GetIterationCount() == 8
     img = rs.ReadBackbuffer() / 8
     gold = np.load(os.path.join(GOLDEN, "box1_pt_64.npy")) / 8
-    assert pixel_mismatch_fraction(img, gold, 1e-2) < 0.05
-    # stated tolerance: relMSE <= 0.02 at equal spp and equal random streams
-    assert rel_mse(img, gold) < 0.02
+    assert pixel_mismatch_fraction(img, gold, 1e-2) < 0.002
+    # stated tolerance: relMSE <= 1e-6 at equal spp and equal random streams (measured 2.4e-14)
+    assert rel_mse(img, gold) < 1e-6
     rs.close()
 
 
@@ -79,12 +79,12 @@ def test_pathtracer_textured_scene(g, orc, scenes, sponza_small):
     rs.Draw()
     img = rs.ReadBackbuffer()
     ref, _ = orc.render_pt(sponza_small.desc, cam, W, H, samples, seed, 16)
-    assert pixel_mismatch_fraction(img, ref, 1e-2) < 0.03
-    # hardware bilinear filter (9-bit weights, sRGB LUT): same image within 2 % per pixel for > 95 % of the pixels
+    assert pixel_mismatch_fraction(img, ref, 1e-2) < 0.005
+    # hardware bilinear filter (9-bit weights, sRGB LUT): same image within 3 % per pixel for > 99 % of the pixels (measured 99.8 %)
     rs2 = _rs(g, scenes, sponza_small, "PT", W, H, cam=scenes.SPONZA_CAMERA, exact_filter=False)
     rs2.Draw()
     hw = rs2.ReadBackbuffer()
-    assert pixel_mismatch_fraction(hw, ref, 3e-2) < 0.06
+    assert pixel_mismatch_fraction(hw, ref, 3e-2) < 0.01
     rs.close(); rs2.close()
 
 
@@ -119,7 +119,7 @@ def test_environment_and_path_length(g, orc, scenes):
         img = rs.ReadBackbuffer()
         env = [orc_srgb(v) for v in (200, 128, 64)]
         ref, _ = orc.render_pt(sc.desc, cam, W, H, samples, seed, 3, env_rgb=env)
-        assert pixel_mismatch_fraction(img, ref, 1e-2) < 0.02 and img[..., :3].max() > 0.1
+        assert pixel_mismatch_fraction(img, ref, 1e-2) < 0.002 and img[..., :3].max() > 0.1
         rs.close()
     finally:
         g.set_path_length(16)
@@ -146,7 +146,7 @@ def test_lighttracer_matches_oracle(g, orc, scenes, box1):
     # splats are sparse at 1 iteration: compare total energy and a blurred image instead of single pixels
     e_img, e_ref = img[..., :3].sum(), ref[..., :3].sum()
     assert abs(e_img - e_ref) / e_ref < 0.01
-    assert pixel_mismatch_fraction(img, ref, 1e-2) < 0.03
+    assert pixel_mismatch_fraction(img, ref, 1e-2) < 0.003
     assert np.all(img[..., 3] == 0.0)
     rs.close()
 
@@ -481,7 +481,7 @@ def test_stand_in_scenes_match_oracle(g, orc, scenes, tmp_path, which):
     img = rs.ReadBackbuffer()
     ref, _ = orc.render_pt(sc.desc, camp, W, H, samples, seed, 16)
     assert np.isfinite(img).all() and img[..., :3].mean() > 0
-    assert pixel_mismatch_fraction(img, ref, 1e-2) < 0.03
+    assert pixel_mismatch_fraction(img, ref, 1e-2) < 0.003
     rs.close()
     if renderer == g.GI_RENDERER_PT:
         return
@@ -632,7 +632,7 @@ def test_environment_cube_map(g, orc, scenes):
             orc.set_environment_cube(None)
         assert ref[..., :3].max() > 0.3 and img[..., :3].mean() > 0.05
         # hardware filter: 8-bit interpolation weights + sRGB LUT -> 3 % per pixel for > 97 % of the pixels, means within 0.5 %
-        assert pixel_mismatch_fraction(img, ref, 3e-2) < 0.03
+        assert pixel_mismatch_fraction(img, ref, 3e-2) < 0.005
         assert abs(img[..., :3].mean() - ref[..., :3].mean()) / ref[..., :3].mean() < 5e-3
     dev.close()
 
@@ -679,7 +679,7 @@ def test_whitted_raytracer_matches_oracle(g, orc, scenes, box1, sponza_small):
         img = rs.ReadBackbuffer()
         ref, rc = orc.render_whitted(sc.desc, camp, W, H, samples, seed, 16)
         assert np.all(img[..., 3] == 1.0) and img[..., :3].sum() > 0
-        assert pixel_mismatch_fraction(img, ref, 1e-2) < 0.03
+        assert pixel_mismatch_fraction(img, ref, 1e-2) < 0.003
         cnt = rs.device.counters()
         assert cnt["camera_paths"] == (W // 8) * (H // 8) * 64
         assert abs(cnt["closest_rays"] - rc["closest_rays"]) / rc["closest_rays"] < 0.01

@@ -8,6 +8,7 @@ cd "$(dirname "$0")/../../gpugi_b200"
 make -s
 while [ $# -ge 2 ]; do
   tag=$1; flags=$2; shift 2
+  case "$flags" in *--fmad*) ;; *) flags="--fmad=false $flags";; esac   # the product build's setting unless the variant chooses
   mkdir -p variants/$tag
   cp libgpugi_b200_host.so variants/$tag/
   /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -ccbin /usr/bin/g++ -Xcompiler -fPIC,-fvisibility=hidden -Xptxas -v --expt-relaxed-constexpr $flags -shared -o variants/$tag/libgpugi_b200.so csrc/gi_device.cu 2> variants/$tag/ptxas.log &
