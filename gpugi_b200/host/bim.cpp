@@ -376,6 +376,7 @@ uint32_t Chunk::remapNodePointers(uint32_t root, uint32_t rootParent, uint32_t r
 void Chunk::buildHierarchy(BuildMethod method)
 {
 	m_hierarchy.clear(); m_hierarchyParents.clear(); m_hierarchyLeaves.clear(); m_aaBoxes.clear(); m_oBoxes.clear();
+	m_properties &= ~uint32_t(Property::HIERARCHY | Property::AABOX_BVH | Property::OBOX_BVH); // boxes of another tree are void
 	m_numTrianglesPerLeaf = 2;
 	if (m_triangles.empty()) return;
 	if (method == BuildMethod::KD_TREE) buildBVH_kdtree();
@@ -395,6 +396,37 @@ void Chunk::setHierarchy(const Node* nodes, const uint32_t* parents, const Box* 
 	m_numTreeLevels = numTreeLevels;
 	m_properties |= Property::HIERARCHY | Property::AABOX_BVH;
 	m_properties &= ~uint32_t(Property::OBOX_BVH);
+}
+
+bool Chunk::validate(std::string* why) const
+{
+	auto bad = [&](const std::string& text) { if (why) *why = text; return false; };
+	const size_t numVertices = m_positions.size(), numNodes = m_hierarchy.size();
+	if (m_numTrianglesPerLeaf != 2) return bad("only 2 triangles per leaf are supported (scenedata.glsl:5)");
+	for (const UVec3& t : m_triangles)
+		if (t.x >= numVertices || t.y >= numVertices || t.z >= numVertices) return bad("a triangle references a missing vertex");
+	if (!m_normals.empty() && m_normals.size() != numVertices) return bad("normal count differs from the vertex count");
+	if (!m_texCoords0.empty() && m_texCoords0.size() != numVertices) return bad("texture coordinate count differs from the vertex count");
+	if (!m_triangleMaterials.empty() && m_triangleMaterials.size() != m_triangles.size()) return bad("material index count differs from the triangle count");
+	if (numNodes == 0) return true; // no hierarchy in the file: Scene::Init builds one
+	if (m_hierarchyParents.size() != numNodes) return bad("hierarchy without one parent per node");
+	if (m_hierarchyLeaves.empty() || m_hierarchyLeaves.size() % m_numTrianglesPerLeaf) return bad("hierarchy without leaf slots");
+	if (!m_aaBoxes.empty() && m_aaBoxes.size() != numNodes) return bad("box count differs from the node count");
+	if (!m_oBoxes.empty() && m_oBoxes.size() != numNodes) return bad("oriented-box count differs from the node count");
+	const size_t numLeaves = m_hierarchyLeaves.size() / m_numTrianglesPerLeaf;
+	for (size_t i = 0; i < numNodes; ++i)
+	{
+		const Node& n = m_hierarchy[i];
+		const uint32_t child = n.firstChild & 0x7fffffffu;
+		if (n.firstChild & 0x80000000u) { if (child >= numLeaves) return bad("a node references a missing leaf"); }
+		else if (child >= numNodes || child <= i) return bad("a node's first child does not lie behind it (preorder)");
+		if (n.escape >= numNodes || (n.escape != 0 && n.escape <= i)) return bad("a node's escape pointer does not lie behind it (preorder)");
+		if (i != 0 && m_hierarchyParents[i] >= i) return bad("a node's parent does not lie in front of it (preorder)");
+	}
+	for (const UVec4& t : m_hierarchyLeaves)
+		if (t.x != t.y && (t.x >= numVertices || t.y >= numVertices || t.z >= numVertices)) return bad("a leaf triangle references a missing vertex");
+	if (numVertices == 0) return bad("hierarchy without vertices");
+	return true;
 }
 
 // bim_hierarchy.cpp:8-50: leaf box = union of its (valid) triangles, inner box = union of children.
@@ -581,12 +613,25 @@ std::string directoryOf(const std::string& file)
 	return p == std::string::npos ? std::string() : file.substr(0, p + 1);
 }
 
+// bytes between the read position and the end of the file (a section of a corrupt file must not claim more)
+uint64_t bytesLeft(std::ifstream& f)
+{
+	const std::streamoff here = f.tellg();
+	if (here < 0) return 0;
+	f.seekg(0, std::ios::end);
+	const std::streamoff end = f.tellg();
+	f.seekg(here, std::ios::beg);
+	return end > here ? uint64_t(end - here) : 0;
+}
+
 template <typename T>
 bool readSection(std::ifstream& f, const SectionHeader& h, std::vector<T>& out)
 {
+	if (h.size > bytesLeft(f)) return false;
 	if (h.uncompressedSize)
 	{
-		if (h.uncompressedSize % sizeof(T)) return false;
+		// deflate expands at most 1032 : 1
+		if (h.uncompressedSize % sizeof(T) || h.uncompressedSize / 1032 > h.size + 16) return false;
 		std::vector<unsigned char> packed(h.size);
 		f.read(reinterpret_cast<char*>(packed.data()), std::streamsize(h.size));
 		out.assign(h.uncompressedSize / sizeof(T), T());
@@ -681,7 +726,7 @@ bool BinaryModel::load(const std::string& envFile, std::string* error)
 	MetaSection meta;
 	f.read(reinterpret_cast<char*>(&meta), sizeof(meta));
 	m_boundingBox = meta.boundingBox;
-	if (meta.numChunks[0] * meta.numChunks[1] * meta.numChunks[2] != 1) { if (error) *error = "Only single-chunk files are supported"; return false; }
+	if (meta.numChunks[0] != 1 || meta.numChunks[1] != 1 || meta.numChunks[2] != 1) { if (error) *error = "Only single-chunk files are supported"; return false; }
 	m_materialIndirection.clear();
 	m_chunk = Chunk();
 	bool haveChunk = false;
@@ -691,6 +736,7 @@ bool BinaryModel::load(const std::string& envFile, std::string* error)
 		{
 			uint32_t num = 0;
 			f.read(reinterpret_cast<char*>(&num), 4);
+			if (!f || uint64_t(num) * 64 > bytesLeft(f)) { if (error) *error = "Invalid file. Truncated material reference section"; return false; }
 			char buf[65]; buf[64] = 0;
 			for (uint32_t i = 0; i < num; ++i) { f.read(buf, 64); m_materialIndirection.push_back(buf); }
 		}
@@ -737,6 +783,8 @@ bool BinaryModel::load(const std::string& envFile, std::string* error)
 	if (c.m_normals.size() != c.m_positions.size()) c.m_normals.assign(c.m_positions.size(), Vec3{0.0f, 0.0f, 0.0f});
 	if (c.m_texCoords0.size() != c.m_positions.size()) c.m_texCoords0.assign(c.m_positions.size(), Vec2{0.0f, 0.0f});
 	if (c.m_triangleMaterials.size() != c.m_triangles.size()) c.m_triangleMaterials.assign(c.m_triangles.size(), 0u);
+	std::string why;
+	if (!c.validate(&why)) { if (error) *error = "Invalid file: " + why; return false; }
 	return true;
 }
 

@@ -111,7 +111,7 @@ public:
 	uint32_t getNumLeafNodes() const { return uint32_t(m_hierarchyLeaves.size() / m_numTrianglesPerLeaf); }
 	const Node* getHierarchy() const { return m_hierarchy.data(); }
 	const uint32_t* getHierarchyParents() const { return m_hierarchyParents.data(); }
-	const Box* getHierarchyAABoxes() const { return m_aaBoxes.data(); }
+	const Box* getHierarchyAABoxes() const { return m_aaBoxes.empty() ? nullptr : m_aaBoxes.data(); }
 	const OBox* getHierarchyOBoxes() const { return m_oBoxes.empty() ? nullptr : m_oBoxes.data(); }
 	const UVec4* getLeafNodes() const { return m_hierarchyLeaves.data(); }
 	uint32_t getNumTrianglesPerLeaf() const { return m_numTrianglesPerLeaf; }
@@ -134,6 +134,10 @@ public:
 	/// orientation is the principal-axis frame of the vertices and the extent is ei::OBox(orientation, points, n) (3dtypes.cpp:205-225).
 	/// Files written by the reference's tools carry their own boxes and are used as stored.
 	void computeBVHOBoxes();
+	/// Index ranges and array sizes of a chunk read from a file (the part of Scene::SanityCheck, scene.hpp:191, that keeps the host code
+	/// inside its arrays): vertex indices, child / escape / parent links (preorder: a child and an escape target lie behind their node),
+	/// leaf slots, one box and one parent per node.  false + *why for a file that breaks one of them.
+	bool validate(std::string* why = nullptr) const;
 
 private:
 	friend class BinaryModel;

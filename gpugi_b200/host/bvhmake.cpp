@@ -377,6 +377,9 @@ bool LoadRawScene(const std::string& file, RawScene& s, std::string* error)
 	std::ifstream in(file, std::ios::binary);
 	if (!in) return setError(error, "cannot open '" + file + "'");
 	s = RawScene();
+	in.seekg(0, std::ios::end);
+	const uint64_t fileSize = uint64_t(std::max<std::streamoff>(in.tellg(), 0));
+	in.seekg(0, std::ios::beg);
 	NamedArray h;
 	while (in.read(reinterpret_cast<char*>(&h), sizeof(h)))
 	{
@@ -386,6 +389,7 @@ bool LoadRawScene(const std::string& file, RawScene& s, std::string* error)
 		auto take = [&](auto& vec, size_t elementSize) -> bool
 		{
 			if (h.elementSize != elementSize) return setError(error, "array '" + name + "': element size " + std::to_string(h.elementSize) + ", expected " + std::to_string(elementSize));
+			if (bytes > fileSize - std::min<uint64_t>(fileSize, uint64_t(std::max<std::streamoff>(in.tellg(), 0)))) return setError(error, "array '" + name + "' is truncated");
 			vec.resize(h.numElements);
 			if (bytes && !in.read(reinterpret_cast<char*>(vec.data()), std::streamsize(bytes))) return setError(error, "array '" + name + "' is truncated");
 			return true;
@@ -410,11 +414,15 @@ bool LoadRawScene(const std::string& file, RawScene& s, std::string* error)
 		for (const Triangle& t : l.triangles)
 			for (uint32_t v : t.vertices)
 				if (v >= s.vertices.size()) return setError(error, "'" + file + "': vertex index out of range");
-	for (const Node& n : s.nodes)
+	for (size_t i = 0; i < s.nodes.size(); ++i)
 	{
+		const Node& n = s.nodes[i];
 		const uint32_t c = n.firstChild & 0x7fffffffu;
 		if ((n.firstChild & 0x80000000u) ? c >= s.leaves.size() : c >= s.nodes.size()) return setError(error, "'" + file + "': child index out of range");
 		if (n.escape >= s.nodes.size()) return setError(error, "'" + file + "': escape index out of range");
+		// preorder: the first child and the escape target of a node lie behind it, and the first child's escape is its sibling
+		if (!(n.firstChild & 0x80000000u) && (c <= i || s.nodes[c].escape <= c)) return setError(error, "'" + file + "': hierarchy is not in preorder");
+		if (n.escape != 0 && n.escape <= i) return setError(error, "'" + file + "': hierarchy is not in preorder");
 	}
 	return true;
 }
@@ -484,8 +492,12 @@ bool ToModel(const RawScene& s, const std::string& envJson, bim::BinaryModel& mo
 	struct Walker
 	{
 		const RawScene& s; Expander& ex; std::vector<TNode>& tree; const std::vector<uint32_t>& firstTri;
-		uint32_t node(uint32_t i)
+		std::vector<uint8_t> visited; bool broken = false;
+		uint32_t node(uint32_t i, uint32_t depth = 0)
 		{
+			// a tree visits every node once; a file whose links share or repeat nodes, or a chain deeper than any real tree, is refused
+			if (broken || visited[i] || depth > 4096u) { broken = true; return 0xffffffffu; }
+			visited[i] = 1;
 			const Node& n = s.nodes[i];
 			if (n.firstChild & 0x80000000u)
 			{
@@ -497,13 +509,15 @@ bool ToModel(const RawScene& s, const std::string& envJson, bim::BinaryModel& mo
 			const uint32_t self = uint32_t(tree.size());
 			tree.push_back({0u, 0u, s.boxes[i], 0, 0});
 			const uint32_t lc = n.firstChild, rc = s.nodes[lc].escape;
-			const uint32_t l = node(lc);
-			const uint32_t r = node(rc);
+			const uint32_t l = node(lc, depth + 1);
+			const uint32_t r = node(rc, depth + 1);
 			tree[self].left = l; tree[self].right = r;
 			return self;
 		}
-	} walk{s, expand, tree, firstTriOfLeaf};
-	if (walk.node(0) == 0xffffffffu) return setError(error, "raw scene: the root leaf is empty");
+	} walk{s, expand, tree, firstTriOfLeaf, std::vector<uint8_t>(s.nodes.size(), 0), false};
+	const uint32_t root = walk.node(0);
+	if (walk.broken) return setError(error, "raw scene: the hierarchy is not a tree (a node is reached twice, or it is deeper than 4096 levels)");
+	if (root == 0xffffffffu) return setError(error, "raw scene: the root leaf is empty");
 	for (const TNode& t : tree)
 		if (t.leafCount == 0 && (t.left == 0xffffffffu || t.right == 0xffffffffu)) return setError(error, "raw scene: a leaf without triangles");
 	// emit in the chunk's layout: preorder nodes {firstChild, escape}, parents, two slots per leaf

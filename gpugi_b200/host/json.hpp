@@ -78,8 +78,14 @@ struct Parser
 		return true;
 	}
 
+	// nesting guard: the parser recurses per level, scene files nest 3-4 deep
+	int depth = 0;
+	struct Level { int& d; explicit Level(int& depth) : d(depth) { ++d; } ~Level() { --d; } };
+
 	bool parseValue(Value& v)
 	{
+		Level level(depth);
+		if (depth > 200) return fail("nested deeper than 200 levels");
 		skip();
 		if (p >= s.size()) return fail("unexpected end");
 		char c = s[p];
