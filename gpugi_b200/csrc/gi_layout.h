@@ -336,6 +336,39 @@ inline bool buildHostLayout(const GiSceneDesc* d, HostLayout& L, std::string& er
 			return false;
 		}
 	}
+	// ---- the links must not form a cycle: the stackless walk (traceray.glsl:56-175) goes node -> firstChild on a hit, -> escape on a miss or
+	// behind a leaf, and ends at escape == 0; on a cyclic file a ray would walk for ever ON THE DEVICE.  Node order is free (any acyclic
+	// layout is accepted, the builders here all emit preorder): iterative depth-first colouring over both links of every node.
+	{
+		std::vector<uint8_t> colour(d->num_nodes, 0); // 0 new, 1 on the stack, 2 done
+		std::vector<uint32_t> stack;
+		for (uint32_t start = 0; start < d->num_nodes; ++start)
+		{
+			if (colour[start]) continue;
+			stack.push_back(start);
+			while (!stack.empty())
+			{
+				const uint32_t i = stack.back();
+				if (colour[i] == 0)
+				{
+					colour[i] = 1;
+					const GiNode& n = d->nodes[i];
+					const uint32_t next[2] = {(n.first_child & 0x80000000u) ? 0u : n.first_child, n.escape};
+					for (uint32_t e : next)
+					{
+						if (e == 0) continue; // the root only ever ends a walk
+						if (colour[e] == 1) { err = "the child / escape links form a cycle at node " + std::to_string(e); return false; }
+						if (colour[e] == 0) stack.push_back(e);
+					}
+				}
+				else
+				{
+					colour[i] = 2;
+					stack.pop_back();
+				}
+			}
+		}
+	}
 	for (uint32_t ti = 0; ti < d->num_textures; ++ti)
 	{
 		const GiTexture& t = d->textures[ti];

@@ -202,3 +202,38 @@ def test_deeply_nested_json_is_refused(g, tmp_path):
         with pytest.raises(g.GpugiError) as e:
             g.Scene.load(str(p))
         assert "nested" in str(e.value)
+
+
+def test_upload_refuses_cyclic_links(g, emul, box1):
+    """gi_upload_scene's validation (csrc/gi_layout.h buildHostLayout, the same code in the host-built emulator): links that form a cycle are
+    refused -- also one that only a MISSED inner node would take, which the all-boxes-hit walk of the layout code never follows -- because the
+    stackless walk would never leave it on the device.  In-range, acyclic links keep loading."""
+    import ctypes as C
+    rays = np.zeros(1, dtype=g.RAY_DTYPE)
+    rays["direction"][0] = (0, 0, -1)
+    rays["origin"][0] = (0, 1.5, 2.0)
+    rays["t_max"] = g.RAY_MAX
+    d = box1.desc
+    nodes = box1.nodes()
+    inner = np.nonzero((nodes["first_child"] & 0x80000000) == 0)[0]
+    emul.trace(d, rays, 0)                                   # the untouched scene is accepted
+
+    def with_nodes(n):
+        d2 = box1.desc
+        d2.nodes = C.cast(n.ctypes.data, type(d2.nodes))
+        return d2
+
+    deep = int(inner[len(inner) // 2])
+    anc = int(inner[1])
+    assert anc < deep and nodes["escape"][deep] != anc
+    cyc = nodes.copy()
+    cyc["escape"][deep] = anc                                # a miss at `deep` jumps back to an earlier inner node that leads to `deep` again
+    with pytest.raises(RuntimeError):
+        emul.trace(with_nodes(cyc), rays, 0)
+    cyc = nodes.copy()
+    cyc["first_child"][deep] = deep                          # self loop
+    with pytest.raises(RuntimeError):
+        emul.trace(with_nodes(cyc), rays, 0)
+    ok = nodes.copy()
+    ok["escape"][deep] = 0                                   # ends the walk early: wrong picture, but every ray terminates
+    emul.trace(with_nodes(ok), rays, 0)
