@@ -157,6 +157,10 @@ EM_API void em_set_tree(uint32_t num_leaves, const uint32_t* left, const uint32_
 }
 EM_API int em_topology_applied(void) { return g_topologyApplied; }
 
+// the shader #define variants of the frame (GI_OPT_RECONSTRUCTION_FILTER 0-3, GI_OPT_CHAINED_MIS) for every following em_render* call
+static int g_reconFilter = 0, g_chainedMIS = 0;
+EM_API void em_set_variant(int reconstruction_filter, int chained_mis) { g_reconFilter = reconstruction_filter; g_chainedMIS = chained_mis ? 1 : 0; }
+
 struct EmCounters
 {
 	uint64_t closest_rays, any_rays, camera_paths, light_paths, shaded_vertices, splats, fallback_rays, node_tests, tri_tests;
@@ -240,6 +244,7 @@ EM_API int em_render(const GiSceneDesc* desc, const GiCamera* cam, int w, int h,
 	uint32_t bptCounters[2] = {0, 0};
 	DFrame f;
 	std::memset(&f, 0, sizeof(f));
+	f.reconFilter = g_reconFilter; f.chainedMIS = g_chainedMIS;
 	f.scene = e.s; f.cam = *cam; f.width = w; f.height = h;
 	f.lightSamples = reinterpret_cast<const F4*>(ls); f.numLightSamples = nls;
 	f.frameSeed = p->frame_seed; f.maxPathLength = p->max_path_length; f.traversalMode = mode; f.accum = accum;
@@ -291,7 +296,7 @@ EM_API int em_render(const GiSceneDesc* desc, const GiCamera* cam, int w, int h,
 // 2 = BPT eye pass only (light_cache / cache_count are inputs then).  cache_count: in/out NumLightCacheEntries.
 namespace {
 struct EmRay { F3 o, d; int bounce; uint32_t id; };
-struct EmShadow { F3 o, d; float len; F3 v; uint32_t target; bool splat; };
+struct EmShadow { F3 o, d; float len; F3 v; uint32_t target; bool splat; float posX, posY; };
 
 void emTraceRays(const DFrame& f, const std::vector<EmRay>& rays, std::vector<float>& t, std::vector<int>& leaf, PathCounters& pc, TraceStats& st)
 {
@@ -310,7 +315,14 @@ void emTraceShadows(const DFrame& f, const std::vector<EmShadow>& sh, std::vecto
 	for (const EmShadow& r : sh)
 	{
 		if (traceAny(f.scene, f.traversalMode, r.o, r.d, r.len, &st)) continue;
-		if (r.splat) { ++pc.splats; float* p = f.accum + 4 * size_t(r.target); p[0] += r.v.x; p[1] += r.v.y; p[2] += r.v.z; }
+		if (r.splat && f.reconFilter)
+		{
+			// wfFinishShadow (gi_wavefront.cuh): 5 x 5 weighted splats around the unrounded position carried beside the shadow record
+			++pc.splats;
+			PathCounters dummy; std::memset(&dummy, 0, sizeof(dummy));
+			splatFiltered(f.accum, f.width, f.height, f.reconFilter, r.posX, r.posY, r.v, dummy);
+		}
+		else if (r.splat) { ++pc.splats; float* p = f.accum + 4 * size_t(r.target); p[0] += r.v.x; p[1] += r.v.y; p[2] += r.v.z; }
 		else { F4& c = stateC[r.target]; c.x += r.v.x; c.y += r.v.y; c.z += r.v.z; }
 	}
 }
@@ -325,6 +337,7 @@ EM_API int em_render_wavefront(const GiSceneDesc* desc, const GiCamera* cam, int
 	uint32_t bptCounters[2] = {cache_count ? *cache_count : 0u, 0u};
 	DFrame f;
 	std::memset(&f, 0, sizeof(f));
+	f.reconFilter = g_reconFilter; f.chainedMIS = g_chainedMIS;
 	f.scene = e.s; f.cam = *cam; f.width = w; f.height = h;
 	f.lightSamples = reinterpret_cast<const F4*>(ls); f.numLightSamples = nls;
 	f.frameSeed = p->frame_seed; f.maxPathLength = p->max_path_length; f.traversalMode = mode; f.accum = accum;
@@ -364,7 +377,7 @@ EM_API int em_render_wavefront(const GiSceneDesc* desc, const GiCamera* cam, int
 			{
 				WfPush out;
 				wfShadeLightLane(f, flags, cur[i].o, cur[i].d, cur[i].bounce, t[i], leaf[i], stateT[cur[i].id], out, pc);
-				if (out.shadow) shNext.push_back(EmShadow{out.sOrigin, out.sDir, out.sLen, out.sValue, uint32_t(out.py) * uint32_t(w) + uint32_t(out.px), true});
+				if (out.shadow) shNext.push_back(EmShadow{out.sOrigin, out.sDir, out.sLen, out.sValue, uint32_t(out.py) * uint32_t(w) + uint32_t(out.px), true, out.posX, out.posY});
 				if (out.ray) next.push_back(EmRay{out.origin, out.dir, cur[i].bounce + 1, cur[i].id});
 			}
 			cur.swap(next); shCur.swap(shNext);
@@ -401,7 +414,7 @@ EM_API int em_render_wavefront(const GiSceneDesc* desc, const GiCamera* cam, int
 				WfPush out;
 				const uint32_t id = cur[i].id;
 				wfShadeEyeLane(f, numEntries, cur[i].o, cur[i].d, cur[i].bounce, id, t[i], leaf[i], stateT[id], stateC[id], stateM[id], out, pc);
-				if (out.shadow) shNext.push_back(EmShadow{out.sOrigin, out.sDir, out.sLen, out.sValue, id, false});
+				if (out.shadow) shNext.push_back(EmShadow{out.sOrigin, out.sDir, out.sLen, out.sValue, id, false, 0.0f, 0.0f});
 				if (out.ray) next.push_back(EmRay{out.origin, out.dir, cur[i].bounce + 1, id});
 			}
 			cur.swap(next); shCur.swap(shNext);
@@ -425,6 +438,7 @@ EM_API int em_bidir_eye(const GiSceneDesc* desc, const GiCamera* cam, int w, int
 	uint32_t bptCounters[2] = {cache_count, 0u};
 	DFrame f;
 	std::memset(&f, 0, sizeof(f));
+	f.reconFilter = g_reconFilter; f.chainedMIS = g_chainedMIS;
 	f.scene = e.s; f.cam = *cam; f.width = w; f.height = h;
 	f.frameSeed = p->frame_seed; f.maxPathLength = p->max_path_length; f.traversalMode = mode; f.accum = accum;
 	f.envColor = f3(0.0f);

@@ -48,11 +48,18 @@ lib.em_slab_check.restype = C.c_int
 lib.em_slab_check.argtypes = [vp, vp, u32, u32, vp]
 
 
+lib.em_set_variant.restype = None
+lib.em_set_variant.argtypes = [C.c_int, C.c_int]
 lib.em_set_topology.restype = None
 lib.em_set_topology.argtypes = [C.c_int, u32]
 lib.em_topology_applied.restype = C.c_int
 lib.em_topology_applied.argtypes = []
 TOPOLOGY_REFERENCE, TOPOLOGY_MEDIAN, TOPOLOGY_RANDOM = 0, 1, 2
+
+
+def set_variant(reconstruction_filter=0, chained_mis=False):
+    """GI_OPT_RECONSTRUCTION_FILTER / GI_OPT_CHAINED_MIS of every following render call (the one-thread-per-path forms carry CHAINED_MIS)."""
+    lib.em_set_variant(int(reconstruction_filter), 1 if chained_mis else 0)
 
 
 def set_topology(kind, seed=1):

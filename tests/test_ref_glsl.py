@@ -134,6 +134,31 @@ def test_product_device_logic_equals_reference_glsl_golden(g, emul, scenes, gold
     assert np.array_equal(img.view(np.uint32), gold["bpt_box1_64"].view(np.uint32)), "BPT"
 
 
+def test_product_device_logic_variants_equal_reference_glsl_golden(g, emul, scenes, gold):
+    """The same for the shader variants: the product's RECONSTRUCTION_FILTER 1-3 splats (one thread per path and the wavefront lane functions) and its
+    CHAINED_MIS light pass + eye pass against the goldens of the reference's shaders compiled with those defines -- image and light cache, bit for bit."""
+    os.environ["OMP_NUM_THREADS"] = "1"
+    sc = scenes.make_box1(tess=4)
+    W = H = 64
+    cam, s, seed, nr, cap = gold["pt_cam"], gold["x_samples"], int(gold["x_seed"]), int(gold["x_nr"]), int(gold["x_capacity"])
+    try:
+        for k in (1, 2, 3):
+            emul.set_variant(reconstruction_filter=k)
+            img, _ = emul.render(sc.desc, cam, W, H, s, 1, seed, 16, num_rays_per_light_sample=nr)
+            assert np.array_equal(img.view(np.uint32), gold["lpt_f%d_box1_64" % k].view(np.uint32)), "filter %d" % k
+            wf, _, _, _ = emul.render_wavefront(sc.desc, cam, W, H, s, 1, seed, 16, num_rays_per_light_sample=nr)
+            d = np.abs(wf - gold["lpt_f%d_box1_64" % k])       # the waves splat in another order: same terms, fp32 sums reordered
+            assert d.max() <= 1e-5 * gold["lpt_f%d_box1_64" % k].max(), "filter %d, waves" % k
+        emul.set_variant(reconstruction_filter=0, chained_mis=True)
+        cache = np.zeros(cap * 16, dtype=np.float32)
+        img, cnt = emul.render(sc.desc, cam, W, H, s, 2, seed, 16, num_rays_per_light_sample=nr, capacity=cap, cache=cache)
+        n = gold["cmis_cache"].shape[0]
+        assert cnt["light_cache_entries"] == n and np.array_equal(cache.reshape(-1, 16)[:n].view(np.uint32), gold["cmis_cache"].view(np.uint32)), "CHAINED_MIS light cache"
+        assert np.array_equal(img.view(np.uint32), gold["cmis_bpt_box1_64"].view(np.uint32)), "CHAINED_MIS BPT"
+    finally:
+        emul.set_variant()
+
+
 @live
 def test_oracle_other_renderers_equal_reference_glsl_live(g, orc, scenes, sponza_small, one_thread):
     """Fresh seeds, another resolution, the textured scene with its point lights (omnidirectional light samples), a light cache that overflows."""
