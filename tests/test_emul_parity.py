@@ -591,3 +591,73 @@ def test_invalid_leaf_trees_are_rejected(g, orc, alt_topology, scenes):
         assert not emul.topology_applied(), name
         assert cnt["fast_valid"] == 1
         assert_hits_equal(hits, ref, name)
+
+
+def test_axis_aligned_rays_stay_exact(g, orc, emul, scenes):
+    """Rays with one or two zero direction components (+0 and -0: 1 / d = +-inf, and inf * 0 = NaN in the slab test where the origin lies in
+    a box plane -- a third of the origins are snapped to vertex coordinates) through every walk of the product: ordered one-thread walk,
+    reference-order walk and the lane state machine of k_wf_trace (which hands such rays to its exact re-trace), on axis-aligned geometry,
+    coincident faces, a random soup and an oriented-box hierarchy -- hit flag, triangle, distance and barycentrics bit-exact vs the oracle."""
+    rng = np.random.RandomState(3)
+
+    def batch(sc, n=3000):
+        lo, hi = np.array(sc.info.bbox_min[:]), np.array(sc.info.bbox_max[:])
+        pos = sc.positions()
+        o = lo + (hi - lo) * rng.rand(n, 3)
+        o = np.where(rng.rand(n, 3) < 0.3, pos[rng.randint(0, pos.shape[0], n)], o)
+        d = np.zeros((n, 3), np.float32)
+        for i in range(n):
+            kind = i % 3
+            if kind == 0:
+                d[i, rng.randint(3)] = rng.choice([-1.0, 1.0])
+            elif kind == 1:
+                d[i, rng.permutation(3)[:2]] = rng.randn(2)
+            else:
+                v = rng.randn(3)
+                v[rng.randint(3)] = rng.choice([0.0, -0.0])
+                d[i] = v
+            d[i] /= np.linalg.norm(d[i])
+        rays = np.zeros(n, dtype=g.RAY_DTYPE)
+        rays["origin"], rays["direction"], rays["t_max"] = o.astype(np.float32), d, g.RAY_MAX
+        sh = rays[: n // 3].copy()
+        sh["flags"] = 1
+        sh["t_max"] = (rng.rand(n // 3) * 4).astype(np.float32)
+        return np.concatenate([rays, sh])
+
+    cases = [("box1", scenes.make_box1(tess=4)), ("coincident", scenes.make_box1(tess=2, coincident_faces=True)),
+             ("soup", scenes.make_random_triangles(3000, seed=1)), ("obox", scenes.make_random_triangles(2000, seed=2, bvh_type=1))]
+    for name, sc in cases:
+        rays = batch(sc)
+        ref = orc.trace_batch(sc.desc, rays)
+        assert (ref["leaf_tri"] >= 0).sum() > 1000
+        for mode in (FAST, REFERENCE, LANE):
+            hits, _ = emul.trace(sc.desc, rays, mode)
+            assert_hits_equal(hits, ref, "%s mode %d" % (name, mode))
+
+
+def test_non_finite_and_degenerate_rays_stay_exact(g, orc, emul, box1):
+    """Rays no renderer produces but a gi_trace_rays caller can: NaN / +-inf / denormal / 3.4e38 components in origin or direction, the zero
+    direction, NaN / 0 / negative / infinite lengths, closest- and any-hit.  Whatever traceray.glsl makes of them (NaN comparisons are false,
+    min / max drop NaN) every walk of the product makes too -- same hit flag, triangle and distance bits -- and every walk terminates."""
+    vals = [np.nan, np.inf, -np.inf, 0.0, -0.0, 1e-45, 1e38, -1e38, 1.0, -1.0, 3.4e38]
+    rng = np.random.RandomState(1)
+    n = 4000
+    o, d = rng.randn(n, 3).astype(np.float32), rng.randn(n, 3).astype(np.float32)
+    for i in range(n):
+        for _ in range(rng.randint(1, 3)):
+            (o if i % 2 == 0 else d)[i, rng.randint(3)] = rng.choice(vals)
+        if i % 50 == 0:
+            d[i] = 0
+    rays = np.zeros(n, dtype=g.RAY_DTYPE)
+    rays["origin"], rays["direction"] = o, d
+    tm = np.full(n, g.RAY_MAX, np.float32)
+    tm[::7] = rng.choice(vals, size=len(tm[::7]))
+    rays["t_max"] = tm
+    rays["flags"][::3] = 1
+    with np.errstate(all="ignore"):
+        ref = orc.trace_batch(box1.desc, rays)
+        assert (ref["leaf_tri"] >= 0).sum() > 500
+        for mode in (FAST, REFERENCE, LANE):
+            hits, _ = emul.trace(box1.desc, rays, mode)
+            assert np.array_equal(hits["leaf_tri"], ref["leaf_tri"]), mode
+            assert np.array_equal(hits["t"].view(np.uint32), ref["t"].view(np.uint32)), mode
