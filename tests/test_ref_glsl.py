@@ -184,6 +184,83 @@ def test_oracle_other_renderers_equal_reference_glsl_live(g, orc, scenes, sponza
 
 
 @live
+def test_extreme_materials_equal_reference_glsl_live(g, orc, emul, scenes, one_thread):
+    """Material corners the BASELINE scenes do not reach -- refraction index 1 and < 1 (total internal reflection), Fresnel0 = 1, albedo > 1, roughness 0 /
+    1e-4 / 1000 (Phong exponents 1e20 / 1e8 / 1e-6), half-transparent glossy and emissive surfaces, emissivity 1e6 beside 1e-6 -- through every renderer:
+    the reference's shaders, the oracle and the PRODUCT's device logic (host build) agree in every float of the image and of the light cache."""
+    from gpugi_b200.scenes import legacy_material as lm
+    os.environ["OMP_NUM_THREADS"] = "1"
+    materials = {
+        "DefaultMaterial": lm((0.6, 0.6, 0.6), (0, 0, 0), 1.0, 1.0),
+        "Glass": lm((1, 1, 1), (1, 1, 1), 0.0, 0.0, refraction_index=1.0),
+        "Floor": lm((0, 0, 0), (0, 0, 0), 1e-4, 1.0),
+        "RightWall": lm((2.0, 2.0, 2.0), (0.5, 0.5, 0.5), 0.3, 0.5),
+        "Wall": lm((0.5, 0.5, 0.5), (0, 0, 0), 1e3, 1.0),
+        "LeftWall": lm((0.02, 0.02, 0.33), (0.9, 0.9, 0.9), 0.05, 1.0, refraction_index=2.4),
+        "White": lm((1, 1, 1), (0, 0, 0), 0.9, 0.0, refraction_index=0.5),
+        "LightR": lm((0.5, 0.5, 0.5), (0, 0, 0), 1.0, 1.0, (1e6, 0, 1e-6)),
+        "LightL": lm((0.5, 0.5, 0.5), (0.2, 0.2, 0.2), 0.01, 0.3, (98.0, 392.2, 788.2)),
+    }
+    sc = g.Scene.from_mesh(*scenes.box1_mesh(2), materials, "", "sah")
+    W, H, nls, nr = 56, 40, 32, 64
+    C = scenes.BOX1_CAMERA
+    cam = orc.camera(C["pos"], C["lookat"], C["fov"], W, H)
+    pt, lt, show, wt, lts, eye = (ref_glsl.PathTracer(), ref_glsl.LightTracer(), ref_glsl.ShowLightCaches(), ref_glsl.WhittedRayTracer(), ref_glsl.LightTracer(save=True),
+                                  ref_glsl.BidirEyePass())
+    for lib in (pt, lt, show, wt, lts, eye):
+        lib.set_scene(sc)
+    same = lambda a, b: np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    for it in (2, 5):
+        ls = g.LightSampler(sc); ls.seed(70 + it)
+        s, seed = ls.generate(nls), orc.wanghash(it)
+        want = pt.render(cam, W, H, s, seed)
+        assert want[..., :3].mean() > 1 and np.isfinite(want).all()
+        assert same(orc.render_pt(sc.desc, cam, W, H, s, seed, 16)[0], want) and same(emul.render(sc.desc, cam, W, H, s, 0, seed, 16)[0], want), "PT"
+        want = show.render(cam, W, H, s, lt.render(cam, W, H, s, seed, nr))
+        assert same(orc.render_lpt(sc.desc, cam, W, H, s, seed, nr, 16, show_light_caches=True)[0], want), "LPT, oracle"
+        assert same(emul.render(sc.desc, cam, W, H, s, 1, seed, 16, num_rays_per_light_sample=nr, show_light_caches=True)[0], want), "LPT, product"
+        want = wt.render(cam, W, H, s, seed)
+        assert same(orc.render_whitted(sc.desc, cam, W, H, s, seed, 16)[0], want) and same(emul.render(sc.desc, cam, W, H, s, 3, seed, 16, mode=1)[0], want), "Whitted"
+        cap = nls * nr * 4
+        want, cache, nent, _ = lts.render(cam, W, H, s, seed, nr, capacity=cap)
+        eye.render(cam, W, H, s, seed, nr, cache, cap, nent, accum=want)
+        got, _, counts, ocache = orc.render_bpt(sc.desc, cam, W, H, s, seed, nr, cap, 16, return_cache=True)
+        assert counts[0] == nent and same(ocache[:nent], cache[:nent]) and same(got, want), "BPT, oracle"
+        pcache = np.zeros(cap * 16, dtype=np.float32)
+        got, cnt = emul.render(sc.desc, cam, W, H, s, 2, seed, 16, num_rays_per_light_sample=nr, capacity=cap, cache=pcache)
+        assert cnt["light_cache_entries"] == nent and same(pcache.reshape(-1, 16)[:nent], cache[:nent]) and same(got, want), "BPT, product"
+
+
+@live
+def test_degenerate_triangles_equal_reference_glsl_live(g, orc, emul, scenes):
+    """Degenerate geometry: triangles whose first two INDICES coincide (the reference's marker of an unused leaf slot, traceray.glsl:128 -- on a real
+    triangle it ends the leaf), zero area by index (y == z, x == z), coincident and collinear positions.  traceray.glsl, the oracle and the three walks of
+    the product agree on hit flag, triangle and distance bits, on the SAH and the kd hierarchy."""
+    from gpugi_b200.scenes import legacy_material as lm
+    rng = np.random.RandomState(5)
+    n = 1500
+    pos = ((rng.rand(n, 3) * 10)[:, None, :] + rng.randn(n, 3, 3) * 0.5).reshape(-1, 3).astype(np.float32)
+    tri = np.arange(3 * n, dtype=np.uint32).reshape(n, 3)
+    k = n // 10
+    tri[0:k, 1] = tri[0:k, 0]
+    tri[k:2 * k, 2] = tri[k:2 * k, 1]
+    tri[2 * k:3 * k, 2] = tri[2 * k:3 * k, 0]
+    pos[tri[3 * k:4 * k, 1]] = pos[tri[3 * k:4 * k, 0]]
+    pos[tri[4 * k:5 * k, 2]] = (pos[tri[4 * k:5 * k, 0]] + pos[tri[4 * k:5 * k, 1]]) / 2
+    nrm, uv = np.tile(np.float32([0, 0, 1]), (pos.shape[0], 1)), np.zeros((pos.shape[0], 2), np.float32)
+    tr = ref_glsl.Trace()
+    for build in ("sah", "kd"):
+        sc = g.Scene.from_mesh(pos, nrm, uv, tri, np.zeros(n, np.uint32), {"M": lm((0.5, 0.5, 0.5))}, "", build)
+        rays = make_ray_batch(g, sc, 20000, 3)
+        tr.set_scene(sc)
+        want = tr.trace(g, rays)
+        assert (want["leaf_tri"] >= 0).sum() > 5000
+        assert_same_hits(orc.trace_batch(sc.desc, rays), want, rays, "oracle, " + build)
+        for mode in (0, 1, 2):
+            assert_same_hits(emul.trace(sc.desc, rays, mode)[0], want, rays, "product mode %d, %s" % (mode, build))
+
+
+@live
 def test_oracle_traversal_equals_reference_glsl_live(g, orc, scenes, sponza_small):
     """Fresh batches (other seeds, the Sponza-shaped scene, finite ray lengths, axis-aligned rays) through both."""
     tr = ref_glsl.Trace()
