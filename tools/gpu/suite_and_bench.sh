@@ -1,6 +1,7 @@
 #!/bin/bash
-# GPU box, one GPU: GPU test suite (parity statistics logged) + smoke on the product build, then the bench lines of C2..C5 and an
-# A/B of the contracted build (gpugi_b200/variants/fmadon) on C4.   tools/gpu/final_fmadoff.sh <tag>
+# GPU box, one GPU, ~5 minutes: the GPU test suite with every parity statistic logged (GPUGI_B200_PARITY_LOG -> <tag>_parity_stats.jsonl) + smoke on
+# the product build, then the bench lines of C2..C5 and, if gpugi_b200/variants/$AB_VARIANT exists (tools/gpu/variants.sh), an A/B against it on C4.
+#   [AB_VARIANT=fmadon] tools/gpu/suite_and_bench.sh <tag>      -> gpurun_out/<tag>_*
 TAG=${1:-r2g}
 O=gpurun_out
 mkdir -p $O
@@ -12,8 +13,11 @@ timeout 60 python -c "import __graft_entry__ as e; e.smoke()" 2>&1 | tail -2 | t
 [ $rc -eq 0 ] || exit $rc
 timeout 120 python bench.py > $O/${TAG}_bench_c2_n1.json 2> $O/${TAG}_bench_c2_n1.err
 for c in C3 C4 C5; do timeout 150 python bench.py --config $c --steps 6 > $O/${TAG}_bench_$(echo $c | tr A-Z a-z)_n1.json 2> $O/${TAG}_bench_$c.err; done
-CONFIGS="C4" ITERS=24 REPS=2 tools/gpu/ab_configs.sh base fmadon > $O/${TAG}_fmad_ab_c4.txt 2>&1
-cat $O/${TAG}_fmad_ab_c4.txt
+AB=${AB_VARIANT:-fmadon}
+if [ -d gpugi_b200/variants/$AB ]; then
+  CONFIGS="C4" ITERS=24 REPS=2 tools/gpu/ab_configs.sh base $AB > $O/${TAG}_ab_${AB}_c4.txt 2>&1
+  cat $O/${TAG}_ab_${AB}_c4.txt
+fi
 python - <<PY
 import json
 for c in ("c2", "c3", "c4", "c5"):
