@@ -268,7 +268,9 @@ bool decodeBmp(Reader r, int& W, int& H, std::vector<u8>& rgba, const Fail& fail
 		else if (compress != 3) return fail("BMP: unknown compression");
 	}
 	else return fail("BMP: unknown header size");
+	if (bpp != 1 && bpp != 2 && bpp != 4 && bpp != 8 && bpp != 16 && bpp != 24 && bpp != 32) return fail("BMP: unsupported bit depth");
 	const bool flip = h > 0;
+	if (h == INT32_MIN) return fail("BMP: bad size");
 	h = std::abs(h);
 	if (!sizeOk(w, h)) return fail("BMP: bad size");
 	W = w; H = h;
@@ -627,6 +629,9 @@ struct JpegDecoder
 		int hmax = 1, vmax = 1;
 		for (int i = 0; i < ncomp; ++i) { hmax = std::max(hmax, comp[i].h); vmax = std::max(vmax, comp[i].v); }
 		const int mcuW = 8 * hmax, mcuH = 8 * vmax, mcusX = (W + mcuW - 1) / mcuW, mcusY = (H + mcuH - 1) / mcuH;
+		// the upsampling below replicates / filters by whole factors (1, 2, 3, 4): a component sampled 2 : 3 against the largest one has none
+		for (int i = 0; i < ncomp; ++i)
+			if (hmax % comp[i].h || vmax % comp[i].v) return fail("JPEG: fractional sampling ratios are not supported");
 		for (int i = 0; i < ncomp; ++i)
 		{
 			comp[i].bw = mcusX * comp[i].h; comp[i].bh = mcusY * comp[i].v;

@@ -76,6 +76,20 @@ def test_mutated_files_never_crash_and_huge_headers_are_refused(g, tmp_path):
         open(path, "wb").write(bytes(png))
         with pytest.raises(g.GpugiError):
             g.load_image(path)
+    # header fields the pixel loops index with (found by 400 000 header-only mutations under ASan / UBSan): a BMP bit depth that is not 1 / 2 / 4 / 8 /
+    # 16 / 24 / 32, a JPEG component sampled 2 : 3 against the largest one (its plane is smaller than the 1 : 1 path assumed)
+    bmp = bytearray(open(os.path.join(IMAGES, "pal8.bmp"), "rb").read())
+    bmp[28:30] = struct.pack("<H", 3)
+    open(path, "wb").write(bytes(bmp))
+    with pytest.raises(g.GpugiError):
+        g.load_image(path)
+    jpg = bytearray(open(os.path.join(IMAGES, "q90_444.jpg"), "rb").read())
+    i = jpg.find(b"\xff\xc0")
+    assert jpg[i + 11] == 0x11 and jpg[i + 14] == 0x11     # Y and Cb: 1 x 1
+    jpg[i + 11], jpg[i + 14] = 0x33, 0x22                   # Y 3 x 3, Cb 2 x 2
+    open(path, "wb").write(bytes(jpg))
+    with pytest.raises(g.GpugiError):
+        g.load_image(path)
     tga = bytearray(open(os.path.join(IMAGES, "rgb24.tga"), "rb").read())
     tga[12:16] = struct.pack("<HH", 65535, 65535)
     open(path, "wb").write(bytes(tga))
